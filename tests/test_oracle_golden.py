@@ -1,0 +1,97 @@
+"""Pin oracle/pf_oracle.py (the CPU restatement that travels to the GPU box) against fixtures produced
+by the reference's own code (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+import pf_oracle as O
+from pharmacoforge_b200.synthetic import make_pocket
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_known_answer_constants(golden):
+    c = golden("constants.npz")
+    g = O.gamma_table(100, 1e-5)
+    assert torch.equal(g, t(c["gamma"]))
+    # SURVEY.md App. A.6
+    ref = [-11.51291561, -8.46825981, -0.25130934, 7.80874634, 11.47407913]
+    assert np.allclose(g[[0, 1, 50, 99, 100]].numpy(), ref, rtol=0, atol=1e-6)
+    T = 100
+    s = torch.arange(T).float() / T
+    tt = (torch.arange(T) + 1).float() / T
+    a, v, q = O.posterior_coefficients(O.gamma_at(g, s, T), O.gamma_at(g, tt, T))
+    assert torch.equal(a, t(c["alpha_ts"])) and torch.equal(v, t(c["var_terms"])) and torch.equal(q, t(c["sigma_q"]))
+    assert np.allclose([a[99], v[99], q[99]], [0.16001807, 6.08930731, 0.98691881], atol=1e-6)
+    assert np.allclose([a[0], v[0], q[0]], [0.99989998, 0.01380232, 0.00308608], atol=1e-6)
+    assert torch.equal(O.rbf(torch.tensor([3.0])), t(c["rbf3"]))
+    assert torch.equal(O.rbf(torch.linspace(0, 20, 41)), t(c["rbf_grid"]))
+    assert torch.equal(O.norm_no_nan(torch.zeros(1, 3)), t(c["norm0"]))
+    assert abs(float(c["norm0"][0]) - 1e-4) < 1e-9
+
+
+def test_pp_radius_graph(golden):
+    gpp = golden("pp_graph_n400_seed0.npz")
+    pos, _ = make_pocket(400, seed=0)
+    src, dst = O.radius_edges(t(pos), torch.tensor([0, 400]), 3.5, 100)
+    assert np.array_equal(src.numpy(), gpp["src"]) and np.array_equal(dst.numpy(), gpp["dst"])
+    deg = np.bincount(gpp["dst"], minlength=400)
+    assert 2900 < src.numel() < 3100 and deg.max() <= 18
+
+
+def _denoiser_batch(d):
+    sizes = [int(v) for v in d["sizes"]]
+    pos, onehot = make_pocket(int(d["n_atoms"]), seed=int(d["pocket_seed"]))
+    b = O.build_batch([(t(pos), t(onehot))], [sizes])
+    b.prot_x = t(d["prot_x"]).clone()
+    b.pharm_x = t(d["x_t"]).clone()
+    b.pharm_h = t(d["h_t"]).clone()
+    return b
+
+
+def _canon(src, dst):
+    o = np.lexsort((src.numpy(), dst.numpy()))
+    return src.numpy()[o], dst.numpy()[o]
+
+
+def test_denoiser_call(golden, sd, dyn_cfg):
+    d = golden("denoiser_call.npz")
+    b = _denoiser_batch(d)
+    trace = {}
+    eps_h, eps_x = O.denoiser(sd, b, t(d["t"]), dyn_cfg, trace=trace)
+    for et in ("ff", "pf", "fp", "pp"):
+        s_, d_ = _canon(*trace["edges"][et])
+        assert np.array_equal(s_, d[f"e_{et}_src"]) and np.array_equal(d_, d[f"e_{et}_dst"]), et
+    tol = dict(rtol=1e-5, atol=1e-6)
+    assert np.allclose(trace["enc"]["pharm"].numpy(), d["enc_pharm"], **tol)
+    assert np.allclose(trace["enc"]["prot"].numpy(), d["enc_prot"], **tol)
+    for li in (0, 1):
+        for nt in ("pharm", "prot"):
+            h, v = trace[f"conv{li}"][nt]
+            assert np.allclose(h.numpy(), d[f"conv{li}_{nt}_h"], **tol), (li, nt)
+            assert np.allclose(v.numpy(), d[f"conv{li}_{nt}_v"], **tol), (li, nt)
+    assert np.allclose(eps_h.numpy(), d["eps_h"], **tol)
+    assert np.allclose(eps_x.numpy(), d["eps_x"], **tol)
+
+
+def test_full_reverse_diffusion(golden, sd, dyn_cfg):
+    d = golden("sample_traj.npz")
+    sizes = [int(v) for v in d["sizes"]]
+    pos, onehot = make_pocket(int(d["n_atoms"]), seed=int(d["pocket_seed"]))
+    b = O.build_batch([(t(pos), t(onehot))], [sizes])
+    rec = []
+    x0, h0, types, prot = O.sample(sd, b, t(d["noise"]), 100, sd["gamma.gamma"], dyn_cfg, record=rec)
+    assert len(rec) == 101
+    # same ops in the same order on the same machine: the trajectory must track the reference closely
+    # for all 100 steps (no neighbour-list flip occurs on this seed)
+    tx = torch.stack([r[0] for r in rec]).numpy()
+    th = torch.stack([r[1] for r in rec]).numpy()
+    assert np.allclose(tx, d["traj_x"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(th, d["traj_h"], rtol=1e-4, atol=1e-4)
+    tp = torch.stack([r[2][[0, 100]] for r in rec]).numpy()
+    assert np.allclose(tp, d["traj_prot0"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(x0.numpy(), d["final_x"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(h0.numpy(), d["final_h"], rtol=1e-4, atol=1e-4)
+    assert np.array_equal(types.numpy(), d["final_type"])
+    assert np.allclose(prot.numpy(), d["final_prot"], rtol=1e-4, atol=1e-3)
