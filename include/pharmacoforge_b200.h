@@ -1,0 +1,214 @@
+/*
+ * pharmacoforge_b200 -- C ABI of the B200-native PharmacoForge denoising hot path.
+ *
+ * The reference (eflynn8/pharmacophore-diffusion) is pure Python; its native compute is reached through
+ * torch_cluster, DGL and ATen.  There is no FFI layer upstream, so every entry point below cites the
+ * reference call site (file:line under /root/reference) whose work it replaces.  The Python host in
+ * pharmacoforge_b200/ binds these with ctypes and exposes them as torch.library custom ops.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never allocates or frees
+ *     device memory and keeps no pointer after a call returns;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation;
+ *   - return value: 0 on success, a negative PfStatus on bad arguments or a launch failure; the text is
+ *     available from pf_last_error() (thread-local);
+ *   - conditions only the device can detect (in-degree above the tile capacity, more pharmacophore nodes
+ *     in one graph than the graph builder stages) set bits in the caller-provided `dev_status` word;
+ *   - node feature rows are fp32: scalars h[N][128], vectors v[N][3][16] (component-major; the reference
+ *     uses [N][16][3]), coordinates x[N][3]; indices are int32.
+ *   - an edge type is described by a SEGMENT TABLE sorted by destination: segment s owns the edge slots
+ *     [seg_start[s], seg_start[s]+seg_cnt[s]) of `col` (source node ids) and aggregates onto node
+ *     seg_dst[s] (seg_dst == NULL means segment s is node s).  A TILE is a run of consecutive segments
+ *     whose edges fit one CTA tile; tiles own whole segments, so aggregation needs no atomics.
+ */
+#ifndef PHARMACOFORGE_B200_H
+#define PHARMACOFORGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+enum PfStatus {
+  PF_OK = 0,
+  PF_ERR_BAD_ARG = -1,
+  PF_ERR_LAUNCH = -2,
+  PF_ERR_UNSUPPORTED = -3,
+  PF_ERR_WORKSPACE = -4,
+};
+
+/* bits of the device status word */
+#define PF_DEV_DEGREE_OVERFLOW 1u /* a destination has more in-edges than PF_TILE_ROWS */
+#define PF_DEV_GRAPH_TOO_LARGE 2u /* a graph has more pharmacophore nodes than PF_MAX_PHARM_PER_GRAPH */
+#define PF_DEV_TILE_OVERFLOW 4u   /* the tile list capacity was exceeded */
+#define PF_DEV_EDGE_OVERFLOW 8u   /* an edge buffer capacity was exceeded */
+
+#define PF_HIDDEN 128            /* dynamics.n_hidden_scalars (configs/dev.yml:82) */
+#define PF_VEC 16                /* dynamics.vector_size (configs/dev.yml:80) */
+#define PF_RBF 16                /* GVPMultiEdgeConv rbf_dim default (gvp.py:350) */
+#define PF_TILE_ROWS 64          /* edge / node rows per CTA tile */
+#define PF_MAX_PHARM_PER_GRAPH 128
+#define PF_MAX_KNN 16
+
+int pf_abi_version(void);
+const char* pf_last_error(void);
+
+/* ---- packed GVP weights -------------------------------------------------------------------------
+ * One GVP (gvp.py:43-116) with vi/vo vector channels in/out (hidden vh = max(vi,vo)), si/so scalar
+ * features in/out is packed as six fp32 sections, each padded to a multiple of 4 floats:
+ *   Wh[vi][vh] | Wu[vh][vo] | WfT[K4][so] (to_feats_out.0.weight transposed, K4 = roundup(si+vh,4),
+ *   padding rows zero) | bf[so] | WgT[so][vo] (scalar_to_vector_gates.weight transposed) | bg[vo].
+ * pf_gvp_layout writes the six section offsets (in floats) and returns the packed size in floats. */
+int64_t pf_gvp_layout(int vi, int vo, int si, int so, int64_t offsets_out_host[6]);
+
+/* ---- exclusive scan (plumbing for CSR construction) ---------------------------------------------*/
+size_t pf_scan_workspace_bytes(int64_t n);
+/* out[i] = sum(in[0..i)), i in [0, n]; out has n+1 entries. */
+int pf_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---- K1: static radius graph -> destination-sorted CSR --------------------------------------------
+ * Replaces torch_cluster.radius_graph(prot_x, r=3.5, max_num_neighbors=100) at
+ * protein_pharm_dataset.py:235 and its per-copy replication (unorganized_utils.py:28-81, dgl.batch).
+ * Nodes of segment g are [seg_ptr[g], seg_ptr[g+1]).  Edge (src j -> dst i) exists iff same segment,
+ * i != j, ((dx*dx+dy*dy)+dz*dz) < r*r in fp32 without FMA contraction, keeping the first max_nbrs
+ * neighbours in ascending j.  Pass 1 writes deg[i]; the caller scans deg into rowptr; pass 2 writes
+ * col[rowptr[i] .. rowptr[i]+deg[i]) in ascending j. */
+int pf_radius_count(const float* x, const int32_t* seg_ptr, int32_t n_seg, float r, int32_t max_nbrs,
+                    int32_t* deg, void* stream);
+int pf_radius_fill(const float* x, const int32_t* seg_ptr, int32_t n_seg, float r, int32_t max_nbrs,
+                   const int32_t* rowptr, int32_t* col, void* stream);
+
+/* ---- K2: per-step dynamic graph ------------------------------------------------------------------
+ * Replaces, per reverse-diffusion step, dynamics_gvp.py:187-246: radius_graph(pharm x_t, r=ff_r,
+ * max 200) (:196), knn(prot x_0, pharm x_t, k) (:202) and the six DGL add/remove_edges mutations.
+ * One CTA per graph.  Outputs (all int32, caller-allocated):
+ *   ff: row i (a pharm node of graph g with nf nodes) owns slots [ff_start[i], ff_start[i]+nf-1);
+ *       ff_start is an INPUT (static, computed once per batch); ff_cnt[i] and ff_col are written.
+ *   pf: pharm node i owns slots [k*i, k*i+k) of pf_col (prot ids, ascending distance, ties to the
+ *       lower id); pf_cnt[i] = min(k, prot atoms in the graph).
+ *   fp: the reverse edges sorted by (prot id, pharm id).  Graph g owns segment slots
+ *       [k*pharm_ptr[g], k*pharm_ptr[g+1]): fp_seg_dst / fp_seg_start / fp_seg_cnt (unused slots have
+ *       cnt 0), and the same range of fp_col (pharm ids). */
+int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const float* pharm_x, const int32_t* pharm_ptr,
+                 int32_t n_graphs, float ff_r, int32_t ff_max_nbrs, int32_t pf_k, const int32_t* ff_start,
+                 int32_t* ff_cnt, int32_t* ff_col, int32_t* pf_cnt, int32_t* pf_col, int32_t* fp_seg_dst,
+                 int32_t* fp_seg_start, int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status, void* stream);
+
+/* ---- tile planner --------------------------------------------------------------------------------
+ * Greedily packs consecutive segments of each chunk [chunk_ptr[c], chunk_ptr[c+1]) into tiles of at
+ * most PF_TILE_ROWS edges and PF_TILE_ROWS segments.  tiles[2*t], tiles[2*t+1] = first / one-past-last
+ * segment.  *n_tiles must be zeroed by the caller (pf_zero_i32).  With skip_empty != 0 tiles without
+ * edges are not emitted (accumulate-mode edge types). */
+int pf_plan_tiles(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_chunks, int32_t skip_empty,
+                  int32_t* tiles, int32_t max_tiles, int32_t* n_tiles, uint32_t* dev_status, void* stream);
+int pf_zero_i32(int32_t* p, int64_t n, void* stream);
+
+/* ---- K0: time-conditioned scalar encoders --------------------------------------------------------
+ * h[n] = LayerNorm(SiLU(W [feats[n], t[graph(n)]] + b)) (dynamics_gvp.py:107-117,143-151).
+ * w = Wt[(nf+1)][128] (Linear weight transposed) | b[128] | ln_w[128] | ln_b[128]. */
+int pf_encode(const float* feats, int32_t n_feats, const int32_t* node_ptr, int32_t n_graphs, const float* t,
+              const float* w, float* h_out, void* stream);
+
+/* ---- K3: fused edge message + mean aggregation for one edge type ----------------------------------
+ * Replaces, for one edge type of one GVPMultiEdgeConv layer: u_sub_v + normalise + RBF (gvp.py:472-480),
+ * the gather of edges.src['h'|'v'] and the n_gvps-GVP message chain (gvp.py:540-551 -> 89-116), and
+ * multi_update_all(copy_e, mean) (gvp.py:488-497).  src_v == NULL means all-zero source vectors (first
+ * layer, dynamics_gvp.py:162-173).  accumulate == 0: every destination covered by a tile is written
+ * (zero rows for segments without edges); accumulate != 0: out += mean for segments with edges only
+ * (the cross-etype 'sum' reducer).  w = n_gvps packed GVPs back to back: (17,16,144,128) then
+ * (16,16,128,128) each. */
+int pf_edge_conv(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+                 const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
+                 const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const float* w, int32_t n_gvps,
+                 float* agg_h, float* agg_v, int32_t accumulate, void* stream);
+
+/* ---- K4: node update ------------------------------------------------------------------------------
+ * gvp.py:511-532 in eval mode: (h,v) <- GVPLayerNorm_msg(h + agg_h, v + agg_v); (rh,rv) = GVP x n_gvps;
+ * (h,v) <- GVPLayerNorm_upd(h + rh, v + rv).  v_in == NULL means zero.  In place is allowed
+ * (h_out == h_in).  w = ln_msg_w[128] | ln_msg_b[128] | ln_upd_w[128] | ln_upd_b[128] | n_gvps packed GVPs
+ * (16,16,128,128). */
+int pf_node_update(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v, int64_t n_nodes,
+                   const float* w, int32_t n_gvps, float* h_out, float* v_out, void* stream);
+
+/* ---- K5a: noise head -------------------------------------------------------------------------------
+ * NoisePredictionBlock (dynamics_gvp.py:10-42): (n_gvps-1) x GVP(16,16,128,128) + GVP(16,1,128,64) with
+ * identity gate activation + Linear(64 -> n_out).  w = packed GVPs | Wt[64][n_out4] | b[n_out4]
+ * (n_out4 = roundup(n_out,4)).  eps_h [n][n_out], eps_x [n][3]. */
+int pf_noise_head(const float* h, const float* v, int64_t n_nodes, const float* w, int32_t n_gvps, int32_t n_out,
+                  float* eps_h, float* eps_x, void* stream);
+
+/* ---- K5b: DDPM posterior step + centre-of-mass removal, in place ------------------------------------
+ * sample_p_zs_given_zt (pharmacodiff.py:413-429) for the eps parameterisation:
+ *   z_s = z_t/alpha_ts - var_terms*eps + sigma_q*noise   for x (3) and h (nh),
+ * then the per-graph pharmacophore COM is subtracted from pharm x AND prot x (com_removal, :88-108).
+ * The three coefficients are the same for every graph of a sampling batch. */
+int pf_posterior_step(float* pharm_x, float* pharm_h, int32_t nh, const float* eps_x, const float* eps_h,
+                      const float* noise_x, const float* noise_h, const int32_t* pharm_ptr, float* prot_x,
+                      const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms, float sigma_q,
+                      void* stream);
+
+/* per-graph mean of x over [ptr[g], ptr[g+1]) -> com[g][3]; and x[n] += sign * com[graph(n)]
+ * (dgl.readout_nodes + broadcast subtract/add, pharmacodiff.py:442-452,483-486) */
+int pf_segment_mean3(const float* x, const int32_t* ptr, int32_t n_graphs, float* com, void* stream);
+int pf_segment_shift3(float* x, const int32_t* ptr, int32_t n_graphs, const float* com, float sign, void* stream);
+
+/* ---- whole reverse-diffusion loop ---------------------------------------------------------------------
+ * sample_given_receptor's loop (pharmacodiff.py:466-472): enqueues all `n_steps` steps (graph build,
+ * tile plans, encoders, n_convs x (4 edge types + 2 node updates), noise head, posterior + COM) on
+ * `stream` without returning to Python.  All buffers are described by PfSampleArgs. */
+typedef struct PfSampleArgs {
+  int32_t n_graphs, n_prot, n_pharm, n_prot_feats, n_pharm_feats;
+  int32_t n_convs, n_msg_gvps, n_upd_gvps, n_noise_gvps, pf_k, ff_max_nbrs;
+  float ff_r;
+  /* batch (device) */
+  float* prot_x;              /* [n_prot][3], shifted in place every step */
+  const float* prot_feats;    /* [n_prot][n_prot_feats] */
+  const int32_t* prot_ptr;    /* [n_graphs+1] */
+  float* pharm_x;             /* [n_pharm][3] */
+  float* pharm_h;             /* [n_pharm][n_pharm_feats] */
+  const int32_t* pharm_ptr;   /* [n_graphs+1] */
+  /* static pp graph + its tile plan */
+  const int32_t *pp_start, *pp_cnt, *pp_col, *pp_tiles, *pp_n_tiles;
+  int32_t pp_max_tiles;
+  /* dynamic graph buffers */
+  const int32_t* ff_start;    /* [n_pharm] static */
+  int32_t *ff_cnt, *ff_col, *pf_start, *pf_cnt, *pf_col, *fp_seg_dst, *fp_seg_start, *fp_seg_cnt, *fp_col;
+  const int32_t *pharm_chunk_ptr, *fp_chunk_ptr; /* planner chunks over pharm nodes / fp segment slots */
+  int32_t n_pharm_chunks, n_fp_chunks;
+  int32_t *ff_tiles, *pf_tiles, *fp_tiles, *dyn_n_tiles; /* dyn_n_tiles[3] = ff, pf, fp */
+  int32_t dyn_max_tiles;
+  /* features */
+  float *prot_h, *prot_v, *prot_agg_h, *prot_agg_v;     /* [n_prot][128], [n_prot][48] */
+  float *pharm_hh, *pharm_v, *pharm_agg_h, *pharm_agg_v; /* [n_pharm][128], [n_pharm][48] */
+  float *eps_h, *eps_x;                                  /* [n_pharm][n_pharm_feats], [n_pharm][3] */
+  float* t_graph;                                        /* [n_graphs] scratch: timestep value per graph */
+  /* packed weights (device) */
+  const float *w_pharm_enc, *w_prot_enc;
+  const float* w_msg[8][4];   /* [conv][etype: ff, pf, fp, pp] */
+  const float* w_upd[8][2];   /* [conv][ntype: pharm, prot] */
+  const float* w_noise;
+  /* schedule (host): step i uses t = t_host[i], coefficients alpha_ts_host[i], ... */
+  const float *t_host, *alpha_ts_host, *var_terms_host, *sigma_q_host;
+  const float* noise_x;       /* device [n_steps][n_pharm][3] */
+  const float* noise_h;       /* device [n_steps][n_pharm][n_pharm_feats] */
+  int32_t n_steps;
+  uint32_t* dev_status;
+} PfSampleArgs;
+
+/* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the
+ * timestep value of graph g.  Results in a->eps_h / a->eps_x. */
+int pf_denoiser(const PfSampleArgs* a, void* stream);
+int pf_sample_loop(const PfSampleArgs* a, void* stream);
+int pf_fill_f32(float* p, int64_t n, float v, void* stream);
+size_t pf_sample_args_size(void); /* sizeof(PfSampleArgs), for binding self-checks */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

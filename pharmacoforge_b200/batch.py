@@ -1,0 +1,207 @@
+"""Flat device-resident batch of protein-pharmacophore graphs.
+
+Carries the information of the reference's batched `dgl.DGLHeteroGraph` (node types prot / pharm, edge types
+pp / pf / ff / fp; protein_pharm_dataset.py:210-266, unorganized_utils.py:28-95) as flat tensors:
+
+  * graph g owns the contiguous protein nodes [prot_ptr[g], prot_ptr[g+1]) and pharmacophore nodes
+    [pharm_ptr[g], pharm_ptr[g+1]) -- the layout `dgl.batch` produces and `get_batch_idxs` exposes;
+  * the static pp radius graph is a destination-sorted CSR over all protein nodes of the batch, with its
+    tile plan, built once per batch on the GPU (K1);
+  * the per-step pharmacophore edges (ff radius, pf kNN, fp reverse) live in fixed-capacity buffers that
+    K2 refills every reverse-diffusion step, so no structure is ever mutated on the host.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+@dataclass
+class Pocket:
+    """One receptor pocket: the reference's `ref_graph` restricted to what the hot path reads."""
+    prot_x: torch.Tensor   # [N,3] float32
+    prot_h: torch.Tensor   # [N,F] float32 (element one-hot)
+
+    @staticmethod
+    def from_numpy(pos: np.ndarray, onehot: np.ndarray) -> "Pocket":
+        return Pocket(torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float32)),
+                      torch.from_numpy(np.ascontiguousarray(onehot, dtype=np.float32)))
+
+    @staticmethod
+    def from_dgl(g) -> "Pocket":
+        """Adapter for a reference pocket graph (requires dgl; same node data names as the reference)."""
+        return Pocket(g.nodes["prot"].data["x_0"].detach().float().cpu().contiguous(),
+                      g.nodes["prot"].data["h_0"].detach().float().cpu().contiguous())
+
+
+def _chunk_graphs(weights: np.ndarray, target: int) -> np.ndarray:
+    """Group consecutive graphs into planner chunks of roughly `target` edge rows (boundaries in graphs)."""
+    bounds = [0]
+    acc = 0
+    for g, w in enumerate(weights):
+        acc += int(w)
+        if acc >= target:
+            bounds.append(g + 1)
+            acc = 0
+    if bounds[-1] != len(weights):
+        bounds.append(len(weights))
+    return np.asarray(bounds, dtype=np.int64)
+
+
+class GraphBatch:
+    """See module docstring.  Build with `GraphBatch.from_pockets`."""
+
+    def __init__(self):
+        self.device = None
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_pockets(cls, pockets: Sequence[Pocket], sizes: Sequence[Sequence[int]], device, pp_cutoff: float = 3.5,
+                     pf_k: int = 5, ff_max_nbrs: int = 200, pp_max_nbrs: int = 100,
+                     graph_range: Optional[range] = None) -> "GraphBatch":
+        """One graph per (pocket, requested pharmacophore size), pocket-major, exactly the order
+        `PharmacophoreDiff.sample` flattens them in (pharmacodiff.py:538-544).  `graph_range` restricts the batch
+        to a slice of that flattened list (max_batch_size chunking / multi-GPU sharding)."""
+        self = cls()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("GraphBatch lives on a CUDA device; there is no CPU path")
+        self.device = dev
+        self.pf_k, self.ff_max_nbrs = int(pf_k), int(ff_max_nbrs)
+        graph_pocket, graph_nf = [], []
+        for p, szs in enumerate(sizes):
+            for nf in szs:
+                graph_pocket.append(p)
+                graph_nf.append(int(nf))
+        if graph_range is not None:
+            graph_pocket = graph_pocket[graph_range.start:graph_range.stop]
+            graph_nf = graph_nf[graph_range.start:graph_range.stop]
+        B = len(graph_pocket)
+        used = sorted(set(graph_pocket))
+        remap = {p: i for i, p in enumerate(used)}
+        graph_pocket = np.asarray([remap[p] for p in graph_pocket], dtype=np.int64)
+        graph_nf = np.asarray(graph_nf, dtype=np.int64)
+        pk_n = np.asarray([pockets[p].prot_x.shape[0] for p in used], dtype=np.int64)
+        pk_off = np.concatenate([[0], np.cumsum(pk_n)])
+        graph_np = pk_n[graph_pocket] if B else np.zeros(0, dtype=np.int64)
+        prot_ptr = np.concatenate([[0], np.cumsum(graph_np)]).astype(np.int32)
+        pharm_ptr = np.concatenate([[0], np.cumsum(graph_nf)]).astype(np.int32)
+        self.n_graphs, self.n_prot, self.n_pharm = B, int(prot_ptr[-1]), int(pharm_ptr[-1])
+        self.graph_pocket = graph_pocket
+        self.pocket_ids = used
+        self.prot_ptr_host, self.pharm_ptr_host = prot_ptr, pharm_ptr
+
+        # ---- host -> device: only the distinct pockets travel; replication happens on the GPU
+        pk_x = torch.cat([pockets[p].prot_x for p in used]).float().contiguous()
+        pk_h = torch.cat([pockets[p].prot_h for p in used]).float().contiguous()
+        self.n_prot_feats = pk_h.shape[1]
+        meta = torch.from_numpy(np.concatenate([prot_ptr, pharm_ptr, pk_off[graph_pocket].astype(np.int32)]))
+        self.h2d_bytes = pk_x.numel() * 4 + pk_h.numel() * 4 + meta.numel() * 4
+        pk_x = pk_x.pin_memory().to(dev, non_blocking=True)
+        pk_h = pk_h.pin_memory().to(dev, non_blocking=True)
+        meta = meta.pin_memory().to(dev, non_blocking=True)
+        self.prot_ptr = meta[:B + 1].contiguous()
+        self.pharm_ptr = meta[B + 1:2 * B + 2].contiguous()
+        g_pk_off = meta[2 * B + 2:].long()
+        counts = (self.prot_ptr[1:] - self.prot_ptr[:-1]).long()
+        node_graph = torch.repeat_interleave(torch.arange(B, device=dev), counts, output_size=self.n_prot)
+        src_row = torch.arange(self.n_prot, device=dev) - self.prot_ptr[:-1].long()[node_graph] + g_pk_off[node_graph]
+        self.prot_x = pk_x[src_row].contiguous()
+        self.prot_feats = pk_h[src_row].contiguous()
+        self.prot_x0 = self.prot_x.clone()      # input frame, kept for the final restore / re-use of the batch
+        self.pharm_x = torch.zeros(self.n_pharm, 3, device=dev)
+        self.pharm_h = None                     # allocated by the sampler (feature width is a model property)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        # ---- K1: static pp radius graph (protein_pharm_dataset.py:234-236 + per-copy replication)
+        self.pp_rowptr, self.pp_cnt, self.pp_col = ops.radius_csr(self.prot_x, self.prot_ptr, float(pp_cutoff),
+                                                                  int(pp_max_nbrs))
+        self.pp_start = self.pp_rowptr[:-1]
+        self.n_pp_edges = int(self.pp_col.numel())
+        self.pp_tiles = torch.empty(2 * max(self.n_prot + B, 1), dtype=torch.int32, device=dev)
+        self.pp_n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.plan_tiles(self.pp_cnt, self.prot_ptr, False, self.pp_tiles, self.pp_n_tiles, self.status)
+        self.pp_num_tiles = int(self.pp_n_tiles.item())
+        self.pp_tiles = self.pp_tiles[:2 * max(self.pp_num_tiles, 1)].clone()
+
+        # ---- static description of the dynamic edge buffers (K2 refills them every step)
+        k = self.pf_k
+        nf = graph_nf
+        ff_base = np.concatenate([[0], np.cumsum(nf * np.maximum(nf - 1, 0))])
+        local = np.arange(self.n_pharm) - np.repeat(pharm_ptr[:-1].astype(np.int64), nf)
+        ff_start = (np.repeat(ff_base[:-1], nf) + local * np.repeat(np.maximum(nf - 1, 0), nf)).astype(np.int32)
+        self.ff_capacity = int(ff_base[-1])
+        gb = _chunk_graphs(np.maximum(nf * np.maximum(nf - 1, 0), k * nf), 256)
+        pharm_chunk = pharm_ptr[gb].astype(np.int32)
+        fp_chunk = (k * pharm_ptr[gb].astype(np.int64)).astype(np.int32)
+        small = torch.from_numpy(np.concatenate([ff_start, (k * np.arange(self.n_pharm)).astype(np.int32), pharm_chunk,
+                                                 fp_chunk])).to(dev)
+        n = self.n_pharm
+        self.ff_start = small[:n].contiguous()
+        self.pf_start = small[n:2 * n].contiguous()
+        self.pharm_chunk_ptr = small[2 * n:2 * n + len(gb)].contiguous()
+        self.fp_chunk_ptr = small[2 * n + len(gb):].contiguous()
+        self.n_chunks = len(gb) - 1
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.ff_cnt = torch.zeros(max(n, 1), **i32)
+        self.ff_col = torch.zeros(max(self.ff_capacity, 1), **i32)
+        self.pf_cnt = torch.zeros(max(n, 1), **i32)
+        self.pf_col = torch.zeros(max(k * n, 1), **i32)
+        self.fp_seg_dst = torch.zeros(max(k * n, 1), **i32)
+        self.fp_seg_start = torch.zeros(max(k * n, 1), **i32)
+        self.fp_seg_cnt = torch.zeros(max(k * n, 1), **i32)
+        self.fp_col = torch.zeros(max(k * n, 1), **i32)
+        self.dyn_max_tiles = k * n + self.n_chunks + 1
+        self.ff_tiles = torch.zeros(2 * self.dyn_max_tiles, **i32)
+        self.pf_tiles = torch.zeros(2 * self.dyn_max_tiles, **i32)
+        self.fp_tiles = torch.zeros(2 * self.dyn_max_tiles, **i32)
+        self.dyn_n_tiles = torch.zeros(3, **i32)
+        return self
+
+    # ------------------------------------------------------------------ reference-style accessors
+    def batch_idxs(self):
+        """unorganized_utils.get_batch_idxs: graph index of every node, per node type."""
+        B = self.n_graphs
+        ar = torch.arange(B, device=self.device)
+        return {"prot": torch.repeat_interleave(ar, (self.prot_ptr[1:] - self.prot_ptr[:-1]).long(),
+                                                output_size=self.n_prot),
+                "pharm": torch.repeat_interleave(ar, (self.pharm_ptr[1:] - self.pharm_ptr[:-1]).long(),
+                                                 output_size=self.n_pharm)}
+
+    @property
+    def batch_size(self):
+        return self.n_graphs
+
+    def check_status(self):
+        from . import _lib
+        _lib.check_dev_status(int(self.status.item()) & 0xFFFFFFFF)
+
+    def pp_edges(self):
+        """(src, dst) int64 of the static pp graph, in (dst, src) order -- for tests."""
+        dst = torch.repeat_interleave(torch.arange(self.n_prot, device=self.device), self.pp_cnt.long())
+        return self.pp_col.long(), dst
+
+    def dynamic_edges(self):
+        """Current ff / pf / fp edge lists as (src, dst) int64 -- for tests (host sync)."""
+        k = self.pf_k
+        n = self.n_pharm
+        ar = torch.arange(n, device=self.device)
+        out = {}
+        cnt = self.ff_cnt[:n].long()
+        dst = torch.repeat_interleave(ar, cnt)
+        within = torch.arange(dst.numel(), device=self.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+        out["ff"] = (self.ff_col[self.ff_start.long()[dst] + within].long(), dst)
+        cnt = self.pf_cnt[:n].long()
+        dst = torch.repeat_interleave(ar, cnt)
+        within = torch.arange(dst.numel(), device=self.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+        out["pf"] = (self.pf_col[k * dst + within].long(), dst)
+        scnt = self.fp_seg_cnt[:k * n].long()
+        seg = torch.repeat_interleave(torch.arange(k * n, device=self.device), scnt)
+        within = torch.arange(seg.numel(), device=self.device) - torch.repeat_interleave(torch.cumsum(scnt, 0) - scnt, scnt)
+        out["fp"] = (self.fp_col[self.fp_seg_start.long()[seg] + within].long(), self.fp_seg_dst.long()[seg])
+        return out

@@ -1,0 +1,226 @@
+// Error state, weight layout query, K5b posterior/COM kernels and the host-side step / loop drivers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b.  One CTA per graph.  Every operation is rounded separately in the reference's order
+// (pharmacodiff.py:416-426: mu = z/alpha - var*eps; z_s = mu + sigma*noise; com = sum/count; z -= com), so
+// that with identical eps the step is bit-identical to the CPU oracle.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ pharm_x, float* __restrict__ pharm_h,
+                                                        int nh, const float* __restrict__ eps_x,
+                                                        const float* __restrict__ eps_h,
+                                                        const float* __restrict__ noise_x,
+                                                        const float* __restrict__ noise_h,
+                                                        const int* __restrict__ pharm_ptr,
+                                                        float* __restrict__ prot_x, const int* __restrict__ prot_ptr,
+                                                        int n_graphs, float alpha_ts, float var_terms,
+                                                        float sigma_q) {
+  __shared__ float s_com[3];
+  for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
+    const int fa = pharm_ptr[g], fb = pharm_ptr[g + 1];
+    const int nf = fb - fa;
+    for (int i = threadIdx.x; i < nf * 3; i += blockDim.x) {
+      const size_t o = (size_t)fa * 3 + i;
+      const float mu = __fsub_rn(__fdiv_rn(pharm_x[o], alpha_ts), __fmul_rn(var_terms, eps_x[o]));
+      pharm_x[o] = __fadd_rn(mu, __fmul_rn(sigma_q, noise_x[o]));
+    }
+    for (int i = threadIdx.x; i < nf * nh; i += blockDim.x) {
+      const size_t o = (size_t)fa * nh + i;
+      const float mu = __fsub_rn(__fdiv_rn(pharm_h[o], alpha_ts), __fmul_rn(var_terms, eps_h[o]));
+      pharm_h[o] = __fadd_rn(mu, __fmul_rn(sigma_q, noise_h[o]));
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float acc = 0.f;
+      for (int i = 0; i < nf; ++i) acc = __fadd_rn(acc, pharm_x[(size_t)(fa + i) * 3 + threadIdx.x]);
+      s_com[threadIdx.x] = __fdiv_rn(acc, (float)nf);
+    }
+    __syncthreads();
+    if (nf > 0) {
+      for (int i = threadIdx.x; i < nf * 3; i += blockDim.x) {
+        const size_t o = (size_t)fa * 3 + i;
+        pharm_x[o] = __fsub_rn(pharm_x[o], s_com[i % 3]);
+      }
+      const int pa = prot_ptr[g], pb = prot_ptr[g + 1];
+      for (int i = threadIdx.x; i < (pb - pa) * 3; i += blockDim.x) {
+        const size_t o = (size_t)pa * 3 + i;
+        prot_x[o] = __fsub_rn(prot_x[o], s_com[i % 3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) segment_mean3_kernel(const float* __restrict__ x, const int* __restrict__ ptr,
+                                                            int n_graphs, float* __restrict__ com) {
+  // sequential sum in node order, as index_add_ on CPU does (dgl.readout_nodes 'mean')
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_graphs * 3) return;
+  const int g = t / 3, c = t - 3 * g;
+  const int a = ptr[g], b = ptr[g + 1];
+  float acc = 0.f;
+  for (int i = a; i < b; ++i) acc = __fadd_rn(acc, x[(size_t)i * 3 + c]);
+  com[t] = __fdiv_rn(acc, (float)(b - a));
+}
+
+__global__ void __launch_bounds__(128) segment_shift3_kernel(float* __restrict__ x, const int* __restrict__ ptr,
+                                                             int n_graphs, const float* __restrict__ com,
+                                                             float sign) {
+  for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
+    const int a = ptr[g], b = ptr[g + 1];
+    for (int i = threadIdx.x; i < (b - a) * 3; i += blockDim.x) {
+      const size_t o = (size_t)a * 3 + i;
+      x[o] = __fadd_rn(x[o], __fmul_rn(sign, com[g * 3 + i % 3]));
+    }
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" int pf_abi_version(void) { return PF_ABI_VERSION; }
+extern "C" const char* pf_last_error(void) { return g_err; }
+extern "C" size_t pf_sample_args_size(void) { return sizeof(PfSampleArgs); }
+
+extern "C" int64_t pf_gvp_layout(int vi, int vo, int si, int so, int64_t offsets_out_host[6]) {
+  const GvpLayout L = gvp_layout(vi, vo, si, so);
+  if (offsets_out_host) {
+    offsets_out_host[0] = L.wh;
+    offsets_out_host[1] = L.wu;
+    offsets_out_host[2] = L.wf;
+    offsets_out_host[3] = L.bf;
+    offsets_out_host[4] = L.wg;
+    offsets_out_host[5] = L.bg;
+  }
+  return L.total;
+}
+
+extern "C" int pf_posterior_step(float* pharm_x, float* pharm_h, int32_t nh, const float* eps_x, const float* eps_h,
+                                 const float* noise_x, const float* noise_h, const int32_t* pharm_ptr, float* prot_x,
+                                 const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms,
+                                 float sigma_q, void* stream) {
+  PF_CHECK_ARG(pharm_x && pharm_h && eps_x && eps_h && noise_x && noise_h && pharm_ptr && prot_x && prot_ptr,
+               "pf_posterior_step: null pointer");
+  if (n_graphs <= 0) return PF_OK;
+  const int grid = n_graphs < 32 * kNumSms ? n_graphs : 32 * kNumSms;
+  posterior_kernel<<<grid, 128, 0, as_stream(stream)>>>(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h,
+                                                        pharm_ptr, prot_x, prot_ptr, n_graphs, alpha_ts, var_terms,
+                                                        sigma_q);
+  PF_CHECK_LAUNCH("pf_posterior_step");
+  return PF_OK;
+}
+
+extern "C" int pf_segment_mean3(const float* x, const int32_t* ptr, int32_t n_graphs, float* com, void* stream) {
+  PF_CHECK_ARG(x && ptr && com, "pf_segment_mean3: null pointer");
+  if (n_graphs <= 0) return PF_OK;
+  segment_mean3_kernel<<<(n_graphs * 3 + 127) / 128, 128, 0, as_stream(stream)>>>(x, ptr, n_graphs, com);
+  PF_CHECK_LAUNCH("pf_segment_mean3");
+  return PF_OK;
+}
+
+extern "C" int pf_segment_shift3(float* x, const int32_t* ptr, int32_t n_graphs, const float* com, float sign,
+                                 void* stream) {
+  PF_CHECK_ARG(x && ptr && com, "pf_segment_shift3: null pointer");
+  if (n_graphs <= 0) return PF_OK;
+  const int grid = n_graphs < 32 * kNumSms ? n_graphs : 32 * kNumSms;
+  segment_shift3_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, ptr, n_graphs, com, sign);
+  PF_CHECK_LAUNCH("pf_segment_shift3");
+  return PF_OK;
+}
+
+extern "C" int pf_fill_f32(float* p, int64_t n, float v, void* stream) {
+  PF_CHECK_ARG(p && n >= 0, "pf_fill_f32: null pointer");
+  if (n == 0) return PF_OK;
+  fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(p, n, v);
+  PF_CHECK_LAUNCH("pf_fill_f32");
+  return PF_OK;
+}
+
+#define PF_TRY(call)       \
+  do {                     \
+    int rc_ = (call);      \
+    if (rc_ != PF_OK) return rc_; \
+  } while (0)
+
+// One eps prediction: PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185) with a->t_graph already set.
+extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
+  PF_CHECK_ARG(a != nullptr, "pf_denoiser: null args");
+  PF_CHECK_ARG(a->n_convs >= 1 && a->n_convs <= 8, "pf_denoiser: n_convs out of range (1..8)");
+  // graph of this step: ff radius + pf kNN + fp reverse (dynamics_gvp.py:176-177)
+  PF_TRY(pf_dyn_graph(a->prot_x, a->prot_ptr, a->pharm_x, a->pharm_ptr, a->n_graphs, a->ff_r, a->ff_max_nbrs, a->pf_k,
+                      a->ff_start, a->ff_cnt, a->ff_col, a->pf_cnt, a->pf_col, a->fp_seg_dst, a->fp_seg_start,
+                      a->fp_seg_cnt, a->fp_col, a->dev_status, stream));
+  PF_TRY(pf_zero_i32(a->dyn_n_tiles, 3, stream));
+  PF_TRY(pf_plan_tiles(a->ff_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 0, a->ff_tiles, a->dyn_max_tiles,
+                       a->dyn_n_tiles + 0, a->dev_status, stream));
+  PF_TRY(pf_plan_tiles(a->pf_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 1, a->pf_tiles, a->dyn_max_tiles,
+                       a->dyn_n_tiles + 1, a->dev_status, stream));
+  PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->fp_tiles, a->dyn_max_tiles,
+                       a->dyn_n_tiles + 2, a->dev_status, stream));
+  // encoders (dynamics_gvp.py:143-151); node vectors start at zero (:162-173) and are never materialised
+  PF_TRY(pf_encode(a->pharm_h, a->n_pharm_feats, a->pharm_ptr, a->n_graphs, a->t_graph, a->w_pharm_enc, a->pharm_hh,
+                   stream));
+  PF_TRY(pf_encode(a->prot_feats, a->n_prot_feats, a->prot_ptr, a->n_graphs, a->t_graph, a->w_prot_enc, a->prot_h,
+                   stream));
+  for (int l = 0; l < a->n_convs; ++l) {
+    const float* fv = l == 0 ? nullptr : a->pharm_v;
+    const float* pv = l == 0 ? nullptr : a->prot_v;
+    // pharm <- ff (store) + pf (accumulate); prot <- pp (store) + fp (accumulate)  (gvp.py:484-497)
+    PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
+                        a->ff_tiles, a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg[l][0], a->n_msg_gvps,
+                        a->pharm_agg_h, a->pharm_agg_v, 0, stream));
+    PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col, a->pf_tiles,
+                        a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->n_msg_gvps, a->pharm_agg_h,
+                        a->pharm_agg_v, 1, stream));
+    PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col, a->pp_tiles,
+                        a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v,
+                        0, stream));
+    PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
+                        a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2], a->n_msg_gvps,
+                        a->prot_agg_h, a->prot_agg_v, 1, stream));
+    // node updates, in place (gvp.py:501-536)
+    PF_TRY(pf_node_update(a->pharm_hh, fv, a->pharm_agg_h, a->pharm_agg_v, a->n_pharm, a->w_upd[l][0], a->n_upd_gvps,
+                          a->pharm_hh, a->pharm_v, stream));
+    PF_TRY(pf_node_update(a->prot_h, pv, a->prot_agg_h, a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps,
+                          a->prot_h, a->prot_v, stream));
+  }
+  PF_TRY(pf_noise_head(a->pharm_hh, a->pharm_v, a->n_pharm, a->w_noise, a->n_noise_gvps, a->n_pharm_feats, a->eps_h,
+                       a->eps_x, stream));
+  return PF_OK;
+}
+
+// sample_given_receptor's loop (pharmacodiff.py:466-472).
+extern "C" int pf_sample_loop(const PfSampleArgs* a, void* stream) {
+  PF_CHECK_ARG(a != nullptr, "pf_sample_loop: null args");
+  PF_CHECK_ARG(a->t_host && a->alpha_ts_host && a->var_terms_host && a->sigma_q_host && a->noise_x && a->noise_h,
+               "pf_sample_loop: missing schedule or noise");
+  const size_t fx = (size_t)a->n_pharm * 3, fh = (size_t)a->n_pharm * a->n_pharm_feats;
+  for (int i = 0; i < a->n_steps; ++i) {
+    PF_TRY(pf_fill_f32(a->t_graph, a->n_graphs, a->t_host[i], stream));
+    PF_TRY(pf_denoiser(a, stream));
+    PF_TRY(pf_posterior_step(a->pharm_x, a->pharm_h, a->n_pharm_feats, a->eps_x, a->eps_h, a->noise_x + i * fx,
+                             a->noise_h + i * fh, a->pharm_ptr, a->prot_x, a->prot_ptr, a->n_graphs,
+                             a->alpha_ts_host[i], a->var_terms_host[i], a->sigma_q_host[i], stream));
+  }
+  return PF_OK;
+}

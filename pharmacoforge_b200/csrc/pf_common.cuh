@@ -1,0 +1,67 @@
+// Shared helpers for the pharmacoforge_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pharmacoforge_b200.h"
+
+namespace pf {
+
+void set_error(const char* fmt, ...);
+
+#define PF_CHECK_ARG(cond, msg)                  \
+  do {                                           \
+    if (!(cond)) {                               \
+      pf::set_error("bad argument: %s", msg);    \
+      return PF_ERR_BAD_ARG;                     \
+    }                                            \
+  } while (0)
+
+#define PF_CHECK_LAUNCH(name)                                              \
+  do {                                                                     \
+    cudaError_t e_ = cudaPeekAtLastError();                                \
+    if (e_ != cudaSuccess) {                                               \
+      pf::set_error("%s: %s", name, cudaGetErrorString(e_));               \
+      (void)cudaGetLastError();                                            \
+      return PF_ERR_LAUNCH;                                                \
+    }                                                                      \
+  } while (0)
+
+constexpr int kHidden = PF_HIDDEN;
+constexpr int kVec = PF_VEC;
+constexpr int kRbf = PF_RBF;
+constexpr int kVRow = 3 * kVec;  // 48 floats per node vector row, layout [c][u]
+constexpr int kNumSms = 148;
+
+__host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
+
+// Section offsets of one packed GVP (see pharmacoforge_b200.h).
+struct GvpLayout {
+  int wh, wu, wf, bf, wg, bg, total;
+};
+__host__ __device__ inline GvpLayout gvp_layout(int vi, int vo, int si, int so) {
+  const int vh = vi > vo ? vi : vo;
+  GvpLayout L;
+  L.wh = 0;
+  L.wu = L.wh + round_up4(vi * vh);
+  L.wf = L.wu + round_up4(vh * vo);
+  L.bf = L.wf + round_up4(si + vh) * so;
+  L.wg = L.bf + round_up4(so);
+  L.bg = L.wg + round_up4(so * vo);
+  L.total = L.bg + round_up4(vo);
+  return L;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace pf

@@ -1,0 +1,456 @@
+// Graph construction: exclusive scan, K1 static radius graph, K2 per-step dynamic graph, tile planner.
+// Integer / byte work bound by memory latency; distances use the canonical fp32 form
+// ((dx*dx + dy*dy) + dz*dz) with separately rounded operations so that edge membership and kNN order
+// are bit-identical to the CPU oracle.
+#include <limits.h>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ------------------------------------------------------------------------------------------------ scan
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 4;
+constexpr int kScanBlock = kScanThreads * kScanItems;  // 2048 elements per block
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    int w = lane < nw ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < nw) s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  total = s_warp[32];
+  const int res = s_warp[warp] + inc - v;
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_local_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                                  long long n, int* __restrict__ block_sums) {
+  __shared__ int s_warp[33];
+  const long long base = (long long)blockIdx.x * kScanBlock + (long long)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = base + i < n ? in[base + i] : 0;
+    sum += v[i];
+  }
+  int total;
+  int off = block_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = off;
+    off += v[i];
+  }
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int* __restrict__ block_sums, int n_blocks) {
+  __shared__ int s_warp[33];
+  int carry = 0;
+  for (int b0 = 0; b0 < n_blocks; b0 += kScanThreads) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < n_blocks ? block_sums[i] : 0;
+    int total;
+    const int off = block_exclusive_scan(v, s_warp, total);
+    if (i < n_blocks) block_sums[i] = carry + off;
+    carry += total;
+  }
+  if (threadIdx.x == 0) block_sums[n_blocks] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict__ out, long long n,
+                                                                const int* __restrict__ block_sums, int n_blocks) {
+  const long long base = (long long)blockIdx.x * kScanBlock + (long long)threadIdx.x * kScanItems;
+  const int add = block_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) out[base + i] += add;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[n_blocks];
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+// One CTA per segment (graph); thread i owns centre i and walks every candidate j of the segment in
+// ascending order through a shared-memory staging tile (all lanes read the same j: broadcast).
+constexpr int kRadThreads = 256;
+constexpr int kRadStage = 2048;
+
+template <bool FILL>
+__global__ void __launch_bounds__(kRadThreads) radius_kernel(const float* __restrict__ x,
+                                                             const int* __restrict__ seg_ptr, int n_seg, float r2,
+                                                             int max_nbrs, int* __restrict__ deg,
+                                                             const int* __restrict__ rowptr, int* __restrict__ col) {
+  __shared__ float sx[kRadStage], sy[kRadStage], sz[kRadStage];
+  for (int g = blockIdx.x; g < n_seg; g += gridDim.x) {
+    const int a = seg_ptr[g], b = seg_ptr[g + 1];
+    for (int i0 = a; i0 < b; i0 += kRadThreads) {
+      const int i = i0 + threadIdx.x;
+      const bool live = i < b;
+      float xi = 0.f, yi = 0.f, zi = 0.f;
+      if (live) {
+        xi = x[3 * (size_t)i];
+        yi = x[3 * (size_t)i + 1];
+        zi = x[3 * (size_t)i + 2];
+      }
+      int rank = 0, kept = 0;
+      const int out0 = (FILL && live) ? rowptr[i] : 0;
+      for (int j0 = a; j0 < b; j0 += kRadStage) {
+        const int nj = min(kRadStage, b - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nj; t += kRadThreads) {
+          sx[t] = x[3 * (size_t)(j0 + t)];
+          sy[t] = x[3 * (size_t)(j0 + t) + 1];
+          sz[t] = x[3 * (size_t)(j0 + t) + 2];
+        }
+        __syncthreads();
+        if (live) {
+          for (int t = 0; t < nj; ++t) {
+            // torch_cluster: first max_nbrs+1 hits in ascending index INCLUDING the centre, then drop the centre
+            if (sqdist3(xi, yi, zi, sx[t], sy[t], sz[t]) < r2) {
+              ++rank;
+              if (rank <= max_nbrs + 1 && j0 + t != i) {
+                if (FILL) col[out0 + kept] = j0 + t;
+                ++kept;
+              }
+            }
+          }
+        }
+      }
+      if (!FILL && live) deg[i] = kept;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+constexpr int kDynThreads = 128;
+constexpr int kDynWarps = kDynThreads / 32;
+constexpr int kMaxF = PF_MAX_PHARM_PER_GRAPH;
+constexpr int kMaxK = PF_MAX_KNN;
+
+struct DynGraphParams {
+  const float *prot_x, *pharm_x;
+  const int *prot_ptr, *pharm_ptr;
+  int n_graphs;
+  float ff_r2;
+  int ff_max, k;
+  const int* ff_start;
+  int *ff_cnt, *ff_col, *pf_cnt, *pf_col, *fp_seg_dst, *fp_seg_start, *fp_seg_cnt, *fp_col;
+  unsigned* status;
+};
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
+  unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  lo = __shfl_xor_sync(0xffffffffu, lo, o);
+  hi = __shfl_xor_sync(0xffffffffu, hi, o);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kDynThreads) dyn_graph_kernel(const DynGraphParams p) {
+  __shared__ float fx[kMaxF], fy[kMaxF], fz[kMaxF];
+  __shared__ int e_dst[kMaxF * K];   // prot id of pf edge (i, j), -1 if absent
+  __shared__ int s_dst[kMaxF * K];   // fp edges sorted by (dst, src)
+  __shared__ int s_src[kMaxF * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = p.k;
+  for (int g = blockIdx.x; g < p.n_graphs; g += gridDim.x) {
+    const int pa = p.prot_ptr[g], pb = p.prot_ptr[g + 1];
+    const int fa = p.pharm_ptr[g], fb = p.pharm_ptr[g + 1];
+    const int nf = fb - fa, np_ = pb - pa;
+    if (nf > kMaxF) {
+      if (threadIdx.x == 0) atomicOr(p.status, PF_DEV_GRAPH_TOO_LARGE);
+      continue;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf; i += kDynThreads) {
+      fx[i] = p.pharm_x[3 * (size_t)(fa + i)];
+      fy[i] = p.pharm_x[3 * (size_t)(fa + i) + 1];
+      fz[i] = p.pharm_x[3 * (size_t)(fa + i) + 2];
+    }
+    __syncthreads();
+    const int kk = min(k, np_);
+
+    for (int i = warp; i < nf; i += kDynWarps) {
+      // ---- pf: k nearest prot atoms of pharm node i (knn(prot, pharm, k), dynamics_gvp.py:202)
+      float bd[K];
+      int bi[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        bd[j] = __int_as_float(0x7f800000);
+        bi[j] = INT_MAX;
+      }
+      const float qx = fx[i], qy = fy[i], qz = fz[i];
+      for (int c = pa + lane; c < pb; c += 32) {
+        const float d = sqdist3(p.prot_x[3 * (size_t)c], p.prot_x[3 * (size_t)c + 1], p.prot_x[3 * (size_t)c + 2],
+                                qx, qy, qz);
+        if (d < bd[K - 1]) {  // strict: an equal distance never displaces an earlier (lower) index
+          bd[K - 1] = d;
+          bi[K - 1] = c;
+#pragma unroll
+          for (int j = K - 1; j > 0; --j) {
+            if (bd[j] < bd[j - 1]) {
+              const float td = bd[j];
+              bd[j] = bd[j - 1];
+              bd[j - 1] = td;
+              const int ti = bi[j];
+              bi[j] = bi[j - 1];
+              bi[j - 1] = ti;
+            }
+          }
+        }
+      }
+      // k-way merge across lanes on the key (distance bits, index); distances are >= 0 so the bit
+      // pattern orders like the value
+      for (int j = 0; j < k; ++j) {
+        int sel = -1;
+        if (j < kk) {
+          const unsigned long long mine =
+              ((unsigned long long)__float_as_uint(bd[0]) << 32) | (unsigned)bi[0];
+          unsigned long long best = mine;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = shfl_xor_u64(best, o);
+            best = other < best ? other : best;
+          }
+          sel = (int)(unsigned)(best & 0xffffffffull);
+          if (mine == best) {  // indices are unique, so exactly one lane pops its head
+#pragma unroll
+            for (int q = 0; q + 1 < K; ++q) {
+              bd[q] = bd[q + 1];
+              bi[q] = bi[q + 1];
+            }
+            bd[K - 1] = __int_as_float(0x7f800000);
+            bi[K - 1] = INT_MAX;
+          }
+        }
+        if (lane == 0) {
+          p.pf_col[(size_t)k * (fa + i) + j] = sel;
+          e_dst[i * k + j] = sel;
+        }
+      }
+      if (lane == 0) p.pf_cnt[fa + i] = kk;
+
+      // ---- ff: radius_graph(pharm x_t, r, max) (dynamics_gvp.py:196); centre i, neighbours ascending
+      int rank_run = 0, kept_run = 0;
+      const int out0 = p.ff_start[fa + i];
+      for (int j0 = 0; j0 < nf; j0 += 32) {
+        const int j = j0 + lane;
+        const bool hit = j < nf && sqdist3(qx, qy, qz, fx[j < nf ? j : 0], fy[j < nf ? j : 0], fz[j < nf ? j : 0]) < p.ff_r2;
+        const unsigned hb = __ballot_sync(0xffffffffu, hit);
+        const int rank = rank_run + __popc(hb & ((1u << lane) - 1u)) + 1;
+        const bool keep = hit && rank <= p.ff_max + 1 && j != i;
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        if (keep) p.ff_col[out0 + kept_run + __popc(kb & ((1u << lane) - 1u))] = fa + j;
+        rank_run += __popc(hb);
+        kept_run += __popc(kb);
+      }
+      if (lane == 0) p.ff_cnt[fa + i] = kept_run;
+    }
+    __syncthreads();
+
+    // ---- fp: the pf edges reversed, sorted by (prot id, pharm id) by rank counting (E <= k*nf is small)
+    const int E = nf * kk;
+    for (int e = threadIdx.x; e < E; e += kDynThreads) {
+      const int i = e / kk, j = e - i * kk;
+      const int d = e_dst[i * k + j];
+      int rank = 0;
+      for (int i2 = 0; i2 < nf; ++i2)
+        for (int j2 = 0; j2 < kk; ++j2) {
+          const int d2 = e_dst[i2 * k + j2];
+          rank += (d2 < d) || (d2 == d && i2 < i);
+        }
+      s_dst[rank] = d;
+      s_src[rank] = fa + i;
+    }
+    __syncthreads();
+    const size_t base = (size_t)k * fa;
+    for (int e = threadIdx.x; e < nf * k; e += kDynThreads) {
+      if (e < E) p.fp_col[base + e] = s_src[e];
+      // segment heads: position e starts a segment iff its dst differs from its predecessor's
+      int seg = -1, cnt = 0;
+      if (e < E && (e == 0 || s_dst[e] != s_dst[e - 1])) {
+        seg = 0;
+        for (int q = 1; q <= e; ++q) seg += s_dst[q] != s_dst[q - 1];
+        cnt = 1;
+        while (e + cnt < E && s_dst[e + cnt] == s_dst[e]) ++cnt;
+        p.fp_seg_dst[base + seg] = s_dst[e];
+        p.fp_seg_start[base + seg] = (int)base + e;
+        p.fp_seg_cnt[base + seg] = cnt;
+      }
+    }
+    __syncthreads();
+    // unused segment slots: count the segments, clear the rest
+    if (threadIdx.x == 0) {
+      int nseg = E > 0 ? 1 : 0;
+      for (int q = 1; q < E; ++q) nseg += s_dst[q] != s_dst[q - 1];
+      s_src[0] = nseg;  // reuse as broadcast slot (fp_col already written)
+    }
+    __syncthreads();
+    const int nseg = s_src[0];
+    for (int s = nseg + threadIdx.x; s < nf * k; s += kDynThreads) {
+      p.fp_seg_dst[base + s] = pa;
+      p.fp_seg_start[base + s] = (int)base;
+      p.fp_seg_cnt[base + s] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ planner
+__global__ void __launch_bounds__(128) plan_tiles_kernel(const int* __restrict__ seg_cnt,
+                                                         const int* __restrict__ chunk_ptr, int n_chunks,
+                                                         int skip_empty, int* __restrict__ tiles, int max_tiles,
+                                                         int* __restrict__ n_tiles, unsigned* __restrict__ status) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  int s = chunk_ptr[c];
+  const int s_end = chunk_ptr[c + 1];
+  while (s < s_end) {
+    int rows = 0, e = s;
+    while (e < s_end && e - s < PF_TILE_ROWS) {
+      const int cnt = seg_cnt[e];
+      if (rows + cnt > PF_TILE_ROWS) break;
+      rows += cnt;
+      ++e;
+    }
+    if (e == s) {  // a single destination with more in-edges than a tile holds
+      atomicOr(status, PF_DEV_DEGREE_OVERFLOW);
+      s = s + 1;
+      continue;
+    }
+    if (!(skip_empty && rows == 0)) {
+      const int slot = atomicAdd(n_tiles, 1);
+      if (slot < max_tiles) {
+        tiles[2 * slot] = s;
+        tiles[2 * slot + 1] = e;
+      } else {
+        atomicOr(status, PF_DEV_TILE_OVERFLOW);
+      }
+    }
+    s = e;
+  }
+}
+
+__global__ void zero_i32_kernel(int* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" size_t pf_scan_workspace_bytes(int64_t n) {
+  const int64_t blocks = (n + kScanBlock - 1) / kScanBlock;
+  return (size_t)(blocks + 1) * sizeof(int32_t);
+}
+
+extern "C" int pf_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  PF_CHECK_ARG(in && out && n >= 0, "pf_exclusive_scan_i32: null pointer or negative n");
+  if (workspace_bytes < pf_scan_workspace_bytes(n) || !workspace) {
+    set_error("pf_exclusive_scan_i32: workspace too small (%zu < %zu)", workspace_bytes, pf_scan_workspace_bytes(n));
+    return PF_ERR_WORKSPACE;
+  }
+  const int blocks = (int)((n + kScanBlock - 1) / kScanBlock);
+  int* sums = static_cast<int*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  if (blocks == 0) {
+    zero_i32_kernel<<<1, 32, 0, st>>>(out, 1);
+    PF_CHECK_LAUNCH("pf_exclusive_scan_i32");
+    return PF_OK;
+  }
+  scan_local_kernel<<<blocks, kScanThreads, 0, st>>>(in, out, n, sums);
+  scan_sums_kernel<<<1, kScanThreads, 0, st>>>(sums, blocks);
+  scan_add_kernel<<<blocks, kScanThreads, 0, st>>>(out, n, sums, blocks);
+  PF_CHECK_LAUNCH("pf_exclusive_scan_i32");
+  return PF_OK;
+}
+
+extern "C" int pf_radius_count(const float* x, const int32_t* seg_ptr, int32_t n_seg, float r, int32_t max_nbrs,
+                               int32_t* deg, void* stream) {
+  PF_CHECK_ARG(x && seg_ptr && deg && max_nbrs >= 0, "pf_radius_count: null pointer");
+  if (n_seg <= 0) return PF_OK;
+  const int grid = n_seg < 16 * kNumSms ? n_seg : 16 * kNumSms;
+  radius_kernel<false><<<grid, kRadThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, r * r, max_nbrs, deg, nullptr,
+                                                                    nullptr);
+  PF_CHECK_LAUNCH("pf_radius_count");
+  return PF_OK;
+}
+
+extern "C" int pf_radius_fill(const float* x, const int32_t* seg_ptr, int32_t n_seg, float r, int32_t max_nbrs,
+                              const int32_t* rowptr, int32_t* col, void* stream) {
+  PF_CHECK_ARG(x && seg_ptr && rowptr && col && max_nbrs >= 0, "pf_radius_fill: null pointer");
+  if (n_seg <= 0) return PF_OK;
+  const int grid = n_seg < 16 * kNumSms ? n_seg : 16 * kNumSms;
+  radius_kernel<true><<<grid, kRadThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, r * r, max_nbrs, nullptr,
+                                                                   rowptr, col);
+  PF_CHECK_LAUNCH("pf_radius_fill");
+  return PF_OK;
+}
+
+extern "C" int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const float* pharm_x,
+                            const int32_t* pharm_ptr, int32_t n_graphs, float ff_r, int32_t ff_max_nbrs,
+                            int32_t pf_k, const int32_t* ff_start, int32_t* ff_cnt, int32_t* ff_col,
+                            int32_t* pf_cnt, int32_t* pf_col, int32_t* fp_seg_dst, int32_t* fp_seg_start,
+                            int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status, void* stream) {
+  PF_CHECK_ARG(prot_x && prot_ptr && pharm_x && pharm_ptr && ff_start && ff_cnt && ff_col && pf_cnt && pf_col &&
+                   fp_seg_dst && fp_seg_start && fp_seg_cnt && fp_col && dev_status,
+               "pf_dyn_graph: null pointer");
+  if (pf_k < 1 || pf_k > kMaxK) {
+    set_error("pf_dyn_graph: pf_k=%d unsupported (1..%d; the radius variant of pf edges, pf_k=0, is not built)", pf_k,
+              kMaxK);
+    return PF_ERR_UNSUPPORTED;
+  }
+  if (n_graphs <= 0) return PF_OK;
+  DynGraphParams p{prot_x,  pharm_x, prot_ptr, pharm_ptr, n_graphs,   ff_r * ff_r,  ff_max_nbrs, pf_k,  ff_start,
+                   ff_cnt,  ff_col,  pf_cnt,   pf_col,    fp_seg_dst, fp_seg_start, fp_seg_cnt,  fp_col, dev_status};
+  const int grid = n_graphs < 32 * kNumSms ? n_graphs : 32 * kNumSms;
+  if (pf_k <= 8)
+    dyn_graph_kernel<8><<<grid, kDynThreads, 0, as_stream(stream)>>>(p);
+  else
+    dyn_graph_kernel<16><<<grid, kDynThreads, 0, as_stream(stream)>>>(p);
+  PF_CHECK_LAUNCH("pf_dyn_graph");
+  return PF_OK;
+}
+
+extern "C" int pf_plan_tiles(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_chunks, int32_t skip_empty,
+                             int32_t* tiles, int32_t max_tiles, int32_t* n_tiles, uint32_t* dev_status,
+                             void* stream) {
+  PF_CHECK_ARG(seg_cnt && chunk_ptr && tiles && n_tiles && dev_status, "pf_plan_tiles: null pointer");
+  if (n_chunks <= 0) return PF_OK;
+  plan_tiles_kernel<<<(n_chunks + 127) / 128, 128, 0, as_stream(stream)>>>(seg_cnt, chunk_ptr, n_chunks, skip_empty,
+                                                                          tiles, max_tiles, n_tiles, dev_status);
+  PF_CHECK_LAUNCH("pf_plan_tiles");
+  return PF_OK;
+}
+
+extern "C" int pf_zero_i32(int32_t* p, int64_t n, void* stream) {
+  PF_CHECK_ARG(p && n >= 0, "pf_zero_i32: null pointer");
+  if (n == 0) return PF_OK;
+  zero_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(p, n);
+  PF_CHECK_LAUNCH("pf_zero_i32");
+  return PF_OK;
+}

@@ -1,0 +1,301 @@
+"""Drop-in for the reference's `PharmacophoreDiff` (pharmacoforge/models/pharmacodiff.py:25-578): same constructor
+arguments (fed by `model_from_config`, config_utils/load_from_config.py:16-30), same `state_dict` layout
+(`gamma.gamma`, `dynamics.*`), same sampling entry points; the denoiser and the reverse-diffusion loop run in
+the CUDA library.  No pytorch_lightning dependency: `load_from_checkpoint` reads the Lightning checkpoint dict
+(`hyper_parameters`, `state_dict`) directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from math import ceil
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .batch import GraphBatch, Pocket
+from .dynamics import PharmRecDynamicsGVP
+
+
+def polynomial_gamma(timesteps: int, precision: float, power: float) -> torch.Tensor:
+    """gamma_t = -(log alpha_t^2 - log sigma_t^2) of the clipped polynomial schedule, float64 on the host then
+    float32, as the reference builds it once at construction (pharmacodiff.py:602-664)."""
+    steps = timesteps + 1
+    x = np.linspace(0, steps, steps)
+    a2 = (1.0 - np.power(x / steps, power)) ** 2
+    step = np.clip(np.concatenate([np.ones(1), a2])[1:] / np.concatenate([np.ones(1), a2])[:-1], 0.001, 1.0)
+    a2 = (1.0 - 2.0 * precision) * np.cumprod(step) + precision
+    return torch.from_numpy(-(np.log(a2) - np.log(1.0 - a2))).float()
+
+
+class PredefinedNoiseSchedule(nn.Module):
+    """Lookup table gamma[round(t*T)] (pharmacodiff.py:636-668); `gamma` is a frozen Parameter so that it sits
+    in the state_dict under `gamma.gamma` like the reference's."""
+
+    def __init__(self, noise_schedule: str, timesteps: int, precision: float):
+        super().__init__()
+        self.timesteps = timesteps
+        kind, _, power = noise_schedule.partition("_")
+        if kind != "polynomial" or not power:
+            raise ValueError(noise_schedule)
+        self.gamma = nn.Parameter(polynomial_gamma(timesteps, precision, float(power)), requires_grad=False)
+
+    def forward(self, t):
+        return self.gamma[torch.round(t * self.timesteps).long()]
+
+
+class SampledPharmacophore:
+    """Result object (analysis/pharm_builder.py:7-71): coordinates, argmax types, xyz writer."""
+
+    type_idx_to_elem = ["P", "S", "F", "N", "O", "C"]
+
+    def __init__(self, ph_coords: torch.Tensor, ph_feats: torch.Tensor, pharm_type_map: List[str], traj_frames=None):
+        self.pharm_type_map = pharm_type_map
+        self.ph_coords = ph_coords
+        self.ph_feats = ph_feats
+        self.ph_feats_idxs = ph_feats.argmax(dim=1)
+        self.ph_types = [pharm_type_map[int(i)] for i in self.ph_feats_idxs]
+        self.n_ph_centers = ph_coords.shape[0]
+        self.pos_frames, self.feat_frames = traj_frames if traj_frames is not None else (None, None)
+        self.ph_type_to_elem = {pharm_type_map[i]: self.type_idx_to_elem[i] for i in range(len(pharm_type_map))}
+
+    def pharm_to_xyz(self, pos, types):
+        lines = [f"{len(pos)}"]
+        for i in range(len(pos)):
+            lines.append(f"{self.ph_type_to_elem[types[i]]} {pos[i, 0]:.3f} {pos[i, 1]:.3f} {pos[i, 2]:.3f}")
+        return "\n".join(lines) + "\n"
+
+    def to_xyz_file(self, filename: Optional[str] = None):
+        out = self.pharm_to_xyz(self.ph_coords, self.ph_types)
+        if filename is None:
+            return out
+        Path(filename).write_text(out)
+
+    def traj_to_xyz(self, filename: Optional[str] = None):
+        if self.pos_frames is None:
+            raise ValueError("no trajectory frames were recorded for this pharmacophore")
+        idx = self.feat_frames.argmax(dim=2)
+        out = "".join(self.pharm_to_xyz(self.pos_frames[i], [self.pharm_type_map[int(j)] for j in idx[i]])
+                      for i in range(self.pos_frames.shape[0]))
+        if filename is None:
+            return out
+        Path(filename).write_text(out)
+
+
+class PharmacophoreDiff(nn.Module):
+    def __init__(self, pharm_nf, rec_nf, ph_type_map: List[str], processed_data_dir=None, n_timesteps: int = 1000,
+                 graph_config={}, dynamics_config={}, lr_scheduler_config={}, sample_interval: float = 1,
+                 val_loss_interval: float = 1, batch_size: int = 64, pharms_per_pocket: int = 8,
+                 n_pockets_to_sample: int = 8, precision=1e-4, pharm_feat_norm_constant=1,
+                 endpoint_param_feat: bool = False, endpoint_param_coord: bool = False, weighted_loss: bool = False,
+                 remove_com: bool = True, **kwargs):
+        super().__init__()
+        if endpoint_param_feat or endpoint_param_coord:
+            raise NotImplementedError("only the eps parameterisation (configs/dev.yml) is built")
+        if not remove_com:
+            raise NotImplementedError("remove_com=False is not built")
+        self.hparams = dict(pharm_nf=pharm_nf, rec_nf=rec_nf, ph_type_map=ph_type_map,
+                            processed_data_dir=processed_data_dir, n_timesteps=n_timesteps, graph_config=graph_config,
+                            dynamics_config=dynamics_config, lr_scheduler_config=lr_scheduler_config,
+                            sample_interval=sample_interval, val_loss_interval=val_loss_interval,
+                            batch_size=batch_size, pharms_per_pocket=pharms_per_pocket,
+                            n_pockets_to_sample=n_pockets_to_sample, precision=precision,
+                            pharm_feat_norm_constant=pharm_feat_norm_constant,
+                            endpoint_param_feat=endpoint_param_feat, endpoint_param_coord=endpoint_param_coord,
+                            weighted_loss=weighted_loss, remove_com=remove_com, **kwargs)
+        self.n_pharm_feats, self.n_prot_feats = pharm_nf, rec_nf
+        self.batch_size = batch_size
+        self.ph_type_map = ph_type_map
+        self.n_timesteps = n_timesteps
+        self.remove_com = remove_com
+        self.pharm_feat_norm_constant = pharm_feat_norm_constant
+        self.weighted_loss = weighted_loss
+        self.gamma = PredefinedNoiseSchedule("polynomial_2", n_timesteps, precision)
+        self.dynamics = PharmRecDynamicsGVP(pharm_nf, rec_nf, **graph_config, **dynamics_config)
+        self.lr_scheduler_config = lr_scheduler_config
+        self.sample_interval, self.val_loss_interval = sample_interval, val_loss_interval
+        self.pharms_per_pocket, self.n_pockets_to_sample = pharms_per_pocket, n_pockets_to_sample
+        self.graph_cutoffs = graph_config.get("graph_cutoffs", {})
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_config(cls, config: dict) -> "PharmacophoreDiff":
+        """config_utils/load_from_config.py:6-32 (model_from_config)."""
+        ev = config["training"]["evaluation"]
+        return cls(pharm_nf=len(config["dataset"]["ph_type_map"]), rec_nf=len(config["dataset"]["prot_elements"]),
+                   ph_type_map=config["dataset"]["ph_type_map"],
+                   processed_data_dir=config["dataset"]["processed_data_dir"], n_pockets_to_sample=ev["n_pockets"],
+                   pharms_per_pocket=ev["pharms_per_pocket"], sample_interval=ev["sample_interval"],
+                   val_loss_interval=ev["val_loss_interval"], batch_size=config["training"]["batch_size"],
+                   graph_config=config["graph"], dynamics_config=config["dynamics"],
+                   lr_scheduler_config=config["lr_scheduler"], **config["diffusion"])
+
+    @classmethod
+    def load_from_checkpoint(cls, path, map_location="cpu", **overrides) -> "PharmacophoreDiff":
+        """Reads a Lightning checkpoint dict written by the reference's train.py (hyper_parameters + state_dict)."""
+        ckpt = torch.load(path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt["hyper_parameters"])
+        hp.update(overrides)
+        model = cls(**hp)
+        model.load_state_dict(ckpt["state_dict"], strict=True)
+        return model
+
+    def save_checkpoint(self, path):
+        torch.save({"state_dict": self.state_dict(), "hyper_parameters": self.hparams}, path)
+
+    @property
+    def device(self):
+        return next(self.dynamics.parameters()).device
+
+    def make_batch(self, pockets: Sequence[Pocket], n_pharms: Sequence[Sequence[int]], device=None,
+                   graph_range: Optional[range] = None) -> GraphBatch:
+        """copy_graph + dgl.batch of the reference (generate_pharmacophores.py:333-334)."""
+        return GraphBatch.from_pockets(pockets, n_pharms, device or self.device,
+                                       pp_cutoff=self.graph_cutoffs.get("pp", 3.5), pf_k=self.dynamics.pf_k,
+                                       graph_range=graph_range)
+
+    # ------------------------------------------------------------------ schedule (pharmacodiff.py:140-160)
+    def sigma(self, gamma):
+        return torch.sqrt(torch.sigmoid(gamma))
+
+    def alpha(self, gamma):
+        return torch.sqrt(torch.sigmoid(-gamma))
+
+    def sigma_and_alpha_t_given_s(self, gamma_t, gamma_s):
+        sigma2_t_given_s = -torch.expm1(F.softplus(gamma_s) - F.softplus(gamma_t))
+        log_alpha2_t, log_alpha2_s = F.logsigmoid(-gamma_t), F.logsigmoid(-gamma_s)
+        alpha_t_given_s = torch.exp(0.5 * (log_alpha2_t - log_alpha2_s))
+        return sigma2_t_given_s, torch.sqrt(sigma2_t_given_s), alpha_t_given_s, torch.exp(0.5 * log_alpha2_s)
+
+    def step_tables(self):
+        """Per-step host tables for the sampling loop, in loop order (s = T-1 .. 0): t value and the three
+        posterior coefficients of sample_p_zs_given_zt (pharmacodiff.py:387-400), computed with the same fp32
+        torch ops on the host so the coefficients are bit-identical to the reference's."""
+        T = self.n_timesteps
+        s = torch.arange(T - 1, -1, -1)
+        s_arr, t_arr = s.float() / T, (s + 1).float() / T
+        gam = self.gamma.gamma.detach().float().cpu()
+        g_s, g_t = gam[torch.round(s_arr * T).long()], gam[torch.round(t_arr * T).long()]
+        sigma2_ts, sigma_ts, alpha_ts, _ = self.sigma_and_alpha_t_given_s(g_t, g_s)
+        sigma_s, sigma_t = self.sigma(g_s), self.sigma(g_t)
+        var_terms = sigma2_ts / alpha_ts / sigma_t
+        sigma_q = sigma_ts * sigma_s / sigma_t
+        return [np.ascontiguousarray(v.numpy(), dtype=np.float32) for v in (t_arr, alpha_ts, var_terms, sigma_q)]
+
+    # ------------------------------------------------------------------ sampling
+    @torch.no_grad()
+    def sample_given_receptor(self, g: GraphBatch, init_pharm_com: Optional[torch.Tensor] = None,
+                              visualize_trajectory: bool = False, noise: Optional[torch.Tensor] = None,
+                              n_steps: Optional[int] = None, return_tensors: bool = False):
+        """pharmacodiff.py:433-514.  `noise` ([T+1, Nf, 3+nf] on any device, row 0 = z_T, row 1+i = i-th step, x
+        columns first) injects the Gaussian draws for parity runs; by default they come from torch's CUDA
+        generator in the reference's call order.  `n_steps` < T stops early (teacher-forced tests)."""
+        dev, T, nh = g.device, self.n_timesteps, self.n_pharm_feats
+        steps = T if n_steps is None else int(n_steps)
+        st = self.dynamics.bind(g)
+        nfn = g.n_pharm
+        if noise is None:
+            nx = torch.empty(steps + 1, nfn, 3, device=dev)
+            nhh = torch.empty(steps + 1, nfn, nh, device=dev)
+            for i in range(steps + 1):  # x before h, every step (pharmacodiff.py:455-456, 423-424)
+                nx[i] = torch.randn(nfn, 3, device=dev)
+                nhh[i] = torch.randn(nfn, nh, device=dev)
+        else:
+            noise = noise.to(dev, non_blocking=True).float()
+            nx = noise[:steps + 1, :, 0:3].contiguous()
+            nhh = noise[:steps + 1, :, 3:3 + nh].contiguous()
+        # frame set-up (pharmacodiff.py:442-452)
+        init_prot_com = ops.segment_mean3(g.prot_x, g.prot_ptr)
+        if init_pharm_com is None:
+            init_pharm_com = init_prot_com
+        init_pharm_com = init_pharm_com.to(dev).float().contiguous()
+        ops.segment_shift3(g.prot_x, g.prot_ptr, init_pharm_com, -1.0)
+        g.pharm_x.copy_(nx[0])
+        g.pharm_h.copy_(nhh[0])
+        t_host, alpha_ts, var_terms, sigma_q = self.step_tables()
+        a = st.args
+        a.t_host, a.alpha_ts_host = t_host.ctypes.data, alpha_ts.ctypes.data
+        a.var_terms_host, a.sigma_q_host = var_terms.ctypes.data, sigma_q.ctypes.data
+        frames = None
+        if visualize_trajectory:
+            # device-side trajectory buffer instead of a graph copy + D2H per step (pharmacodiff.py:360-378)
+            frames = (torch.empty(steps + 1, nfn, 3, device=dev), torch.empty(steps + 1, nfn, nh, device=dev))
+            self._record_frame(g, init_prot_com, frames, 0)
+            for i in range(steps):
+                self._run_steps(g, st, nx, nhh, i, 1)
+                self._record_frame(g, init_prot_com, frames, i + 1)
+        else:
+            self._run_steps(g, st, nx, nhh, 0, steps)
+        # final frame restore (pharmacodiff.py:480-488)
+        com = ops.segment_mean3(g.prot_x, g.prot_ptr)
+        x0 = g.pharm_x.clone()
+        ops.segment_shift3(x0, g.pharm_ptr, com, -1.0)
+        ops.segment_shift3(x0, g.pharm_ptr, init_prot_com, 1.0)
+        ops.segment_shift3(g.prot_x, g.prot_ptr, com, -1.0)
+        ops.segment_shift3(g.prot_x, g.prot_ptr, init_prot_com, 1.0)
+        h0 = g.pharm_h * self.pharm_feat_norm_constant
+        g.check_status()
+        if return_tensors:
+            return x0, h0
+        x0_h, h0_h = x0.cpu(), h0.cpu()
+        fr = None
+        if frames is not None:
+            fr = (frames[0].cpu(), (frames[1] * self.pharm_feat_norm_constant).cpu())
+        ptr = g.pharm_ptr_host
+        out = []
+        for b in range(g.n_graphs):
+            sl = slice(int(ptr[b]), int(ptr[b + 1]))
+            tf = (fr[0][:, sl], fr[1][:, sl]) if fr is not None else None
+            out.append(SampledPharmacophore(x0_h[sl], h0_h[sl], self.ph_type_map, traj_frames=tf))
+        return out
+
+    def _run_steps(self, g, st, nx, nhh, first: int, count: int):
+        a = st.args
+        T = self.n_timesteps
+        off = first  # tables are in loop order; the same offset applies to every table
+        t_host, alpha_ts, var_terms, sigma_q = self.step_tables()
+        self._tables = (t_host, alpha_ts, var_terms, sigma_q)  # keep alive while C reads them
+        a.t_host = t_host[off:].ctypes.data
+        a.alpha_ts_host = alpha_ts[off:].ctypes.data
+        a.var_terms_host = var_terms[off:].ctypes.data
+        a.sigma_q_host = sigma_q[off:].ctypes.data
+        a.noise_x = nx[1 + first:].data_ptr() if count else 0
+        a.noise_h = nhh[1 + first:].data_ptr() if count else 0
+        a.n_steps = count
+        if count:
+            ops.sample_loop(g.pharm_x, g.pharm_h, g.prot_x, st.addr)
+
+    def _record_frame(self, g, init_prot_com, frames, i):
+        prot_com = ops.segment_mean3(g.prot_x, g.prot_ptr)
+        x = g.pharm_x.clone()
+        ops.segment_shift3(x, g.pharm_ptr, init_prot_com - prot_com, 1.0)
+        frames[0][i] = x
+        frames[1][i] = g.pharm_h
+
+    def sample(self, ref_graphs: Sequence[Pocket], n_pharms: List[List[int]], max_batch_size: int = 32,
+               init_pharm_com: Optional[torch.Tensor] = None, visualize_trajectory: bool = False):
+        """pharmacodiff.py:516-578: pockets x samples flattened pocket-major, chunked by max_batch_size, regrouped."""
+        flat_ref = [r for r, szs in enumerate(n_pharms) for _ in szs]
+        n_total = len(flat_ref)
+        sampled: List[SampledPharmacophore] = []
+        for b in range(ceil(n_total / max_batch_size)):
+            rng = range(b * max_batch_size, min((b + 1) * max_batch_size, n_total))
+            g = self.make_batch(ref_graphs, n_pharms, graph_range=rng)
+            coms = None
+            if init_pharm_com is not None:
+                coms = init_pharm_com[flat_ref[rng.start:rng.stop]]
+            sampled.extend(self.sample_given_receptor(g, init_pharm_com=coms,
+                                                      visualize_trajectory=visualize_trajectory))
+        out, end = [], 0
+        for szs in n_pharms:
+            out.append(sampled[end:end + len(szs)])
+            end += len(szs)
+        return out
+
+    def forward(self, g, phase: str = "train"):
+        raise NotImplementedError("the training loss (pharmacodiff.py:162-243) needs the backward kernels, which are "
+                                  "not built yet; this round covers the sampling path")

@@ -1,0 +1,222 @@
+"""Drop-in for the reference's `PharmRecDynamicsGVP` (pharmacoforge/models/dynamics_gvp.py:94-246).
+
+Same constructor signature and the same `state_dict` keys and shapes, so checkpoints of the
+reference load with `load_state_dict`.  The modules below only HOLD parameters under the reference's names; the
+arithmetic runs in the CUDA library: `forward(g, timestep, batch_idxs)` packs the weights once (re-packed when
+any parameter changes), binds the batch's device buffers into a `PfSampleArgs` and launches `pf_denoiser`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .batch import GraphBatch
+from .weights import PackedWeights
+
+ALL_EDGES = [("pharm", "ff", "pharm"), ("prot", "pf", "pharm"), ("pharm", "fp", "prot"), ("prot", "pp", "prot")]
+
+
+class GVP(nn.Module):
+    """Parameter holder for one GVP; names and shapes as in the reference (gvp.py:43-87)."""
+
+    def __init__(self, dim_vectors_in, dim_vectors_out, dim_feats_in, dim_feats_out, feats_activation=None,
+                 vectors_activation=None):
+        super().__init__()
+        dim_h = max(dim_vectors_in, dim_vectors_out)
+        self.Wh = nn.Parameter(torch.empty(dim_vectors_in, dim_h).uniform_(-1 / math.sqrt(dim_vectors_in),
+                                                                          1 / math.sqrt(dim_vectors_in)))
+        self.Wu = nn.Parameter(torch.empty(dim_h, dim_vectors_out).uniform_(-1 / math.sqrt(dim_h), 1 / math.sqrt(dim_h)))
+        self.to_feats_out = nn.Sequential(nn.Linear(dim_h + dim_feats_in, dim_feats_out), nn.SiLU())
+        self.scalar_to_vector_gates = nn.Linear(dim_feats_out, dim_vectors_out)
+        self.vectors_activation = vectors_activation if vectors_activation is not None else nn.Sigmoid()
+
+
+class _VDropout(nn.Module):
+    def __init__(self, drop_rate):
+        super().__init__()
+        self.drop_rate = drop_rate
+        self.dummy_param = nn.Parameter(torch.empty(0))
+
+
+class GVPDropout(nn.Module):
+    def __init__(self, rate):
+        super().__init__()
+        self.vector_dropout = _VDropout(rate)
+        self.feat_dropout = nn.Dropout(rate)
+
+
+class GVPLayerNorm(nn.Module):
+    def __init__(self, feats_h_size, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.feat_norm = nn.LayerNorm(feats_h_size)
+
+
+class GVPMultiEdgeConv(nn.Module):
+    """Parameter holder for one heterogeneous conv layer (gvp.py:343-437)."""
+
+    def __init__(self, etypes, scalar_size=128, vector_size=16, n_message_gvps=1, n_update_gvps=1, rbf_dim=16,
+                 message_norm="mean", dropout=0.0):
+        super().__init__()
+        self.etypes = etypes
+        self.edge_message_fns = nn.ModuleDict()
+        for et in etypes:
+            gvps = []
+            for i in range(n_message_gvps):
+                vi = vector_size + 1 if i == 0 else vector_size
+                si = scalar_size + rbf_dim if i == 0 else scalar_size
+                gvps.append(GVP(vi, vector_size, si, scalar_size))
+            self.edge_message_fns["_".join(et)] = nn.Sequential(*gvps)
+        self.node_update_fns = nn.ModuleDict()
+        self.update_layer_norms = nn.ModuleDict()
+        self.message_layer_norms = nn.ModuleDict()
+        for nt in sorted({et[2] for et in etypes}):
+            self.node_update_fns[nt] = nn.Sequential(*[GVP(vector_size, vector_size, scalar_size, scalar_size)
+                                                       for _ in range(n_update_gvps)])
+            self.message_layer_norms[nt] = GVPLayerNorm(scalar_size)
+            self.update_layer_norms[nt] = GVPLayerNorm(scalar_size)
+        self.dropout = GVPDropout(dropout)
+
+
+class NoisePredictionBlock(nn.Module):
+    """dynamics_gvp.py:10-35."""
+
+    def __init__(self, in_scalar_dim, out_scalar_dim, vector_size, n_gvps=3, intermediate_scalar_dim=64):
+        super().__init__()
+        gvps = []
+        for i in range(n_gvps):
+            last = i == n_gvps - 1
+            gvps.append(GVP(vector_size, 1 if last else vector_size, in_scalar_dim,
+                            intermediate_scalar_dim if last else in_scalar_dim,
+                            vectors_activation=nn.Identity() if last else nn.Sigmoid()))
+        self.gvps = nn.Sequential(*gvps)
+        self.to_scalar_output = nn.Linear(intermediate_scalar_dim, out_scalar_dim)
+
+
+class PharmRecGVP(nn.Module):
+    """dynamics_gvp.py:44-82."""
+
+    def __init__(self, in_scalar_dim, in_vector_dim, out_scalar_dim, n_convs=4, n_message_gvps=3, n_update_gvps=2,
+                 message_norm="mean", n_noise_gvps=3, dropout=0.0):
+        super().__init__()
+        self.conv_layers = nn.ModuleList([
+            GVPMultiEdgeConv(ALL_EDGES, in_scalar_dim, in_vector_dim, n_message_gvps, n_update_gvps,
+                             message_norm=message_norm, dropout=dropout) for _ in range(n_convs)])
+        self.noise_predictor = NoisePredictionBlock(in_scalar_dim, out_scalar_dim, in_vector_dim, n_noise_gvps)
+
+
+class _DeviceState:
+    """Feature / scratch buffers and the bound PfSampleArgs of one (module, batch) pair."""
+
+    def __init__(self, dyn: "PharmRecDynamicsGVP", g: GraphBatch, w: PackedWeights):
+        dev = g.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        npn, nfn = max(g.n_prot, 1), max(g.n_pharm, 1)
+        self.prot_h = torch.empty(npn, 128, **f32)
+        self.prot_v = torch.empty(npn, 48, **f32)
+        self.prot_agg_h = torch.empty(npn, 128, **f32)
+        self.prot_agg_v = torch.empty(npn, 48, **f32)
+        self.pharm_hh = torch.empty(nfn, 128, **f32)
+        self.pharm_v = torch.empty(nfn, 48, **f32)
+        self.pharm_agg_h = torch.empty(nfn, 128, **f32)
+        self.pharm_agg_v = torch.empty(nfn, 48, **f32)
+        self.eps_h = torch.empty(nfn, dyn.n_pharm_scalars, **f32)
+        self.eps_x = torch.empty(nfn, 3, **f32)
+        self.t_graph = torch.empty(max(g.n_graphs, 1), **f32)
+        if g.pharm_h is None or g.pharm_h.shape[1] != dyn.n_pharm_scalars:
+            g.pharm_h = torch.zeros(nfn, dyn.n_pharm_scalars, **f32)
+        a = _lib.PfSampleArgs()
+        a.n_graphs, a.n_prot, a.n_pharm = g.n_graphs, g.n_prot, g.n_pharm
+        a.n_prot_feats, a.n_pharm_feats = dyn.n_prot_scalars, dyn.n_pharm_scalars
+        a.n_convs, a.n_msg_gvps, a.n_upd_gvps, a.n_noise_gvps = dyn.n_convs, dyn.n_message_gvps, dyn.n_update_gvps, dyn.n_noise_gvps
+        a.pf_k, a.ff_max_nbrs, a.ff_r = g.pf_k, g.ff_max_nbrs, float(dyn.graph_cutoffs["ff"])
+        for name in ("prot_x", "prot_feats", "prot_ptr", "pharm_x", "pharm_h", "pharm_ptr", "pp_start", "pp_cnt",
+                     "pp_col", "pp_tiles", "pp_n_tiles", "ff_start", "ff_cnt", "ff_col", "pf_start", "pf_cnt",
+                     "pf_col", "fp_seg_dst", "fp_seg_start", "fp_seg_cnt", "fp_col", "pharm_chunk_ptr",
+                     "fp_chunk_ptr", "ff_tiles", "pf_tiles", "fp_tiles", "dyn_n_tiles"):
+            setattr(a, name, getattr(g, name).data_ptr())
+        for name in ("prot_h", "prot_v", "prot_agg_h", "prot_agg_v", "pharm_hh", "pharm_v", "pharm_agg_h",
+                     "pharm_agg_v", "eps_h", "eps_x", "t_graph"):
+            setattr(a, name, getattr(self, name).data_ptr())
+        a.pp_max_tiles = g.pp_num_tiles
+        a.n_pharm_chunks = a.n_fp_chunks = g.n_chunks
+        a.dyn_max_tiles = g.dyn_max_tiles
+        a.dev_status = g.status.data_ptr()
+        a.w_pharm_enc, a.w_prot_enc, a.w_noise = w.ptr("pharm_enc"), w.ptr("prot_enc"), w.ptr("noise")
+        for l in range(dyn.n_convs):
+            for e in range(4):
+                a.w_msg[l][e] = w.ptr(f"msg{l}_{e}")
+            for n in range(2):
+                a.w_upd[l][n] = w.ptr(f"upd{l}_{n}")
+        self.args = a
+        self.weights = w          # keep alive
+        self.batch_buffers = (g.prot_x, g.pharm_x, g.pharm_h)
+
+    @property
+    def addr(self) -> int:
+        return C.addressof(self.args)
+
+
+class PharmRecDynamicsGVP(nn.Module):
+    """`self.dynamics` of the diffusion model.  forward(g, timestep, batch_idxs) -> (eps_h [Nf,6], eps_x [Nf,3])."""
+
+    def __init__(self, n_pharm_scalars, n_prot_scalars, vector_size: int = 16, n_convs=4, n_hidden_scalars=128,
+                 act_fn=nn.SiLU, message_norm: Union[float, str, Dict] = 1, graph_cutoffs: dict = {},
+                 n_message_gvps: int = 3, n_update_gvps: int = 2, n_noise_gvps: int = 3, dropout: float = 0.0,
+                 ff_k: int = 0, pf_k: int = 0):
+        super().__init__()
+        if vector_size != 16 or n_hidden_scalars != 128:
+            raise NotImplementedError("the sm_100a kernels are built for vector_size=16, n_hidden_scalars=128 "
+                                      "(configs/dev.yml); other widths need a rebuild with new tile constants")
+        if message_norm != "mean":
+            raise NotImplementedError("only message_norm='mean' (configs/dev.yml) is built")
+        if ff_k != 0 or pf_k <= 0:
+            raise NotImplementedError("only the dev.yml graph (ff radius graph, pf kNN with pf_k>0) is built")
+        if act_fn is not nn.SiLU:
+            raise NotImplementedError("only SiLU is built")
+        self.graph_cutoffs = graph_cutoffs
+        self.n_pharm_scalars, self.n_prot_scalars = n_pharm_scalars, n_prot_scalars
+        self.vector_size, self.ff_k, self.pf_k = vector_size, ff_k, pf_k
+        self.n_convs, self.n_message_gvps, self.n_update_gvps, self.n_noise_gvps = n_convs, n_message_gvps, n_update_gvps, n_noise_gvps
+        self.pharm_encoder = nn.Sequential(nn.Linear(n_pharm_scalars + 1, n_hidden_scalars), act_fn(),
+                                           nn.LayerNorm(n_hidden_scalars))
+        self.prot_encoder = nn.Sequential(nn.Linear(n_prot_scalars + 1, n_hidden_scalars), act_fn(),
+                                          nn.LayerNorm(n_hidden_scalars))
+        self.noise_predictor = PharmRecGVP(n_hidden_scalars, vector_size, n_pharm_scalars, n_convs, n_message_gvps,
+                                           n_update_gvps, message_norm, n_noise_gvps, dropout)
+        self._packed: Optional[PackedWeights] = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ weights
+    def packed_weights(self, device) -> PackedWeights:
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._packed_key != key:
+            sd = {"dyn." + k: v for k, v in self.state_dict().items()}
+            self._packed = PackedWeights(sd, "dyn", self.n_convs, self.n_message_gvps, self.n_update_gvps,
+                                         self.n_noise_gvps, device)
+            self._packed_key = key
+        return self._packed
+
+    def bind(self, g: GraphBatch) -> _DeviceState:
+        """Device buffers + argument block for batch `g` (cached on the batch)."""
+        w = self.packed_weights(g.device)
+        st = getattr(g, "_pf_state", None)
+        cur = (g.prot_x, g.pharm_x, g.pharm_h)
+        if st is None or st.weights is not w or any(a is not b for a, b in zip(st.batch_buffers, cur)):
+            st = _DeviceState(self, g, w)
+            g._pf_state = st
+        return st
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, g: GraphBatch, timestep: torch.Tensor, batch_idxs=None):
+        if self.training and self.noise_predictor.conv_layers[0].dropout.feat_dropout.p > 0:
+            raise NotImplementedError("training-mode dropout / backward kernels are not built yet; call .eval()")
+        st = self.bind(g)
+        st.t_graph.copy_(timestep.to(device=g.device, dtype=torch.float32).reshape(-1))
+        ops.denoiser(st.eps_h, st.eps_x, st.addr)
+        return st.eps_h, st.eps_x

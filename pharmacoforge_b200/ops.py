@@ -1,0 +1,202 @@
+"""torch.library custom ops over the C ABI (include/pharmacoforge_b200.h).
+
+Every op enqueues hand-written sm_100a kernels on torch's current CUDA stream through ctypes; tensors are
+passed as raw device pointers.  There is no CPU implementation and no dispatch on architecture: calling an
+op with a non-CUDA tensor raises.  Ops that write into caller-provided buffers declare them in
+`mutates_args`; shape/dtype-only fakes are registered so the ops can be traced.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_L = _lib.load()
+NS = "pharmacoforge"
+
+
+def _p(t: Optional[torch.Tensor], dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.PfError("pharmacoforge ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise _lib.PfError("pharmacoforge ops need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.PfError(f"expected {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _f(t):
+    return _p(t, torch.float32)
+
+
+def _i(t):
+    return _p(t, torch.int32)
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------ graph
+@torch.library.custom_op(f"{NS}::exclusive_scan", mutates_args=())
+def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
+    n = x.numel()
+    out = torch.empty(n + 1, dtype=torch.int32, device=x.device)
+    ws_bytes = _L.pf_scan_workspace_bytes(n)
+    ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.int32, device=x.device)
+    _lib.check(_L.pf_exclusive_scan_i32(_i(x), _i(out), n, _p(ws), ws.numel() * 4, _s()), "pf_exclusive_scan_i32")
+    return out
+
+
+@exclusive_scan.register_fake
+def _(x):
+    return x.new_empty(x.numel() + 1)
+
+
+@torch.library.custom_op(f"{NS}::radius_count", mutates_args=())
+def radius_count(x: torch.Tensor, seg_ptr: torch.Tensor, r: float, max_nbrs: int) -> torch.Tensor:
+    deg = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
+    _lib.check(_L.pf_radius_count(_f(x), _i(seg_ptr), seg_ptr.numel() - 1, r, max_nbrs, _i(deg), _s()),
+               "pf_radius_count")
+    return deg
+
+
+@radius_count.register_fake
+def _(x, seg_ptr, r, max_nbrs):
+    return x.new_empty(x.shape[0], dtype=torch.int32)
+
+
+@torch.library.custom_op(f"{NS}::radius_fill", mutates_args=())
+def radius_fill(x: torch.Tensor, seg_ptr: torch.Tensor, r: float, max_nbrs: int, rowptr: torch.Tensor,
+                n_edges: int) -> torch.Tensor:
+    col = torch.empty(max(n_edges, 1), dtype=torch.int32, device=x.device)
+    _lib.check(_L.pf_radius_fill(_f(x), _i(seg_ptr), seg_ptr.numel() - 1, r, max_nbrs, _i(rowptr), _i(col), _s()),
+               "pf_radius_fill")
+    return col[:n_edges]
+
+
+@radius_fill.register_fake
+def _(x, seg_ptr, r, max_nbrs, rowptr, n_edges):
+    return x.new_empty(n_edges, dtype=torch.int32)
+
+
+def radius_csr(x: torch.Tensor, seg_ptr: torch.Tensor, r: float, max_nbrs: int):
+    """K1: destination-sorted CSR of the radius graph within each segment -> (rowptr [N+1], deg [N], col [E])."""
+    deg = radius_count(x, seg_ptr, r, max_nbrs)
+    rowptr = exclusive_scan(deg)
+    n_edges = int(rowptr[-1].item())  # one host sync per batch, at setup
+    col = radius_fill(x, seg_ptr, r, max_nbrs, rowptr, n_edges)
+    return rowptr, deg, col
+
+
+@torch.library.custom_op(f"{NS}::dyn_graph",
+                         mutates_args=("ff_cnt", "ff_col", "pf_cnt", "pf_col", "fp_seg_dst", "fp_seg_start",
+                                       "fp_seg_cnt", "fp_col", "status"))
+def dyn_graph(prot_x: torch.Tensor, prot_ptr: torch.Tensor, pharm_x: torch.Tensor, pharm_ptr: torch.Tensor,
+              ff_r: float, ff_max_nbrs: int, pf_k: int, ff_start: torch.Tensor, ff_cnt: torch.Tensor,
+              ff_col: torch.Tensor, pf_cnt: torch.Tensor, pf_col: torch.Tensor, fp_seg_dst: torch.Tensor,
+              fp_seg_start: torch.Tensor, fp_seg_cnt: torch.Tensor, fp_col: torch.Tensor,
+              status: torch.Tensor) -> None:
+    _lib.check(_L.pf_dyn_graph(_f(prot_x), _i(prot_ptr), _f(pharm_x), _i(pharm_ptr), prot_ptr.numel() - 1, ff_r,
+                               ff_max_nbrs, pf_k, _i(ff_start), _i(ff_cnt), _i(ff_col), _i(pf_cnt), _i(pf_col),
+                               _i(fp_seg_dst), _i(fp_seg_start), _i(fp_seg_cnt), _i(fp_col), _p(status), _s()),
+               "pf_dyn_graph")
+
+
+@torch.library.custom_op(f"{NS}::plan_tiles", mutates_args=("tiles", "n_tiles", "status"))
+def plan_tiles(seg_cnt: torch.Tensor, chunk_ptr: torch.Tensor, skip_empty: bool, tiles: torch.Tensor,
+               n_tiles: torch.Tensor, status: torch.Tensor) -> None:
+    _lib.check(_L.pf_zero_i32(_i(n_tiles), 1, _s()), "pf_zero_i32")
+    _lib.check(_L.pf_plan_tiles(_i(seg_cnt), _i(chunk_ptr), chunk_ptr.numel() - 1, int(skip_empty), _i(tiles),
+                                tiles.numel() // 2, _i(n_tiles), _p(status), _s()), "pf_plan_tiles")
+
+
+# ------------------------------------------------------------------------------------------------ compute
+@torch.library.custom_op(f"{NS}::encode", mutates_args=())
+def encode(feats: torch.Tensor, node_ptr: torch.Tensor, t: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(feats.shape[0], 128, dtype=torch.float32, device=feats.device)
+    _lib.check(_L.pf_encode(_f(feats), feats.shape[1], _i(node_ptr), node_ptr.numel() - 1, _f(t), _f(w), _f(out),
+                            _s()), "pf_encode")
+    return out
+
+
+@encode.register_fake
+def _(feats, node_ptr, t, w):
+    return feats.new_empty(feats.shape[0], 128)
+
+
+@torch.library.custom_op(f"{NS}::edge_conv", mutates_args=("agg_h", "agg_v"))
+def edge_conv(src_h: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torch.Tensor, dst_x: torch.Tensor,
+              seg_start: torch.Tensor, seg_cnt: torch.Tensor, seg_dst: Optional[torch.Tensor], col: torch.Tensor,
+              tiles: torch.Tensor, n_tiles: torch.Tensor, w: torch.Tensor, n_gvps: int, agg_h: torch.Tensor,
+              agg_v: torch.Tensor, accumulate: bool) -> None:
+    _lib.check(_L.pf_edge_conv(_f(src_h), _f(src_v), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt), _i(seg_dst),
+                               _i(col), _i(tiles), _i(n_tiles), tiles.numel() // 2, _f(w), n_gvps, _f(agg_h),
+                               _f(agg_v), int(accumulate), _s()), "pf_edge_conv")
+
+
+@torch.library.custom_op(f"{NS}::node_update", mutates_args=("h_out", "v_out"))
+def node_update(h_in: torch.Tensor, v_in: Optional[torch.Tensor], agg_h: torch.Tensor, agg_v: torch.Tensor,
+                w: torch.Tensor, n_gvps: int, h_out: torch.Tensor, v_out: torch.Tensor) -> None:
+    _lib.check(_L.pf_node_update(_f(h_in), _f(v_in), _f(agg_h), _f(agg_v), h_in.shape[0], _f(w), n_gvps, _f(h_out),
+                                 _f(v_out), _s()), "pf_node_update")
+
+
+@torch.library.custom_op(f"{NS}::noise_head", mutates_args=())
+def noise_head(h: torch.Tensor, v: torch.Tensor, w: torch.Tensor, n_gvps: int,
+               n_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    n = h.shape[0]
+    eps_h = torch.empty(n, n_out, dtype=torch.float32, device=h.device)
+    eps_x = torch.empty(n, 3, dtype=torch.float32, device=h.device)
+    _lib.check(_L.pf_noise_head(_f(h), _f(v), n, _f(w), n_gvps, n_out, _f(eps_h), _f(eps_x), _s()), "pf_noise_head")
+    return eps_h, eps_x
+
+
+@noise_head.register_fake
+def _(h, v, w, n_gvps, n_out):
+    return h.new_empty(h.shape[0], n_out), h.new_empty(h.shape[0], 3)
+
+
+@torch.library.custom_op(f"{NS}::posterior_step", mutates_args=("pharm_x", "pharm_h", "prot_x"))
+def posterior_step(pharm_x: torch.Tensor, pharm_h: torch.Tensor, eps_x: torch.Tensor, eps_h: torch.Tensor,
+                   noise_x: torch.Tensor, noise_h: torch.Tensor, pharm_ptr: torch.Tensor, prot_x: torch.Tensor,
+                   prot_ptr: torch.Tensor, alpha_ts: float, var_terms: float, sigma_q: float) -> None:
+    _lib.check(_L.pf_posterior_step(_f(pharm_x), _f(pharm_h), pharm_h.shape[1], _f(eps_x), _f(eps_h), _f(noise_x),
+                                    _f(noise_h), _i(pharm_ptr), _f(prot_x), _i(prot_ptr), prot_ptr.numel() - 1,
+                                    alpha_ts, var_terms, sigma_q, _s()), "pf_posterior_step")
+
+
+@torch.library.custom_op(f"{NS}::segment_mean3", mutates_args=())
+def segment_mean3(x: torch.Tensor, ptr: torch.Tensor) -> torch.Tensor:
+    com = torch.empty(ptr.numel() - 1, 3, dtype=torch.float32, device=x.device)
+    _lib.check(_L.pf_segment_mean3(_f(x), _i(ptr), ptr.numel() - 1, _f(com), _s()), "pf_segment_mean3")
+    return com
+
+
+@segment_mean3.register_fake
+def _(x, ptr):
+    return x.new_empty(ptr.numel() - 1, 3)
+
+
+@torch.library.custom_op(f"{NS}::segment_shift3", mutates_args=("x",))
+def segment_shift3(x: torch.Tensor, ptr: torch.Tensor, com: torch.Tensor, sign: float) -> None:
+    _lib.check(_L.pf_segment_shift3(_f(x), _i(ptr), ptr.numel() - 1, _f(com), sign, _s()), "pf_segment_shift3")
+
+
+# ------------------------------------------------------------------------------------------------ drivers
+@torch.library.custom_op(f"{NS}::denoiser", mutates_args=("eps_h", "eps_x"))
+def denoiser(eps_h: torch.Tensor, eps_x: torch.Tensor, args_addr: int) -> None:
+    """One eps prediction over the buffers described by the PfSampleArgs at `args_addr`."""
+    _lib.check(_L.pf_denoiser(C.c_void_p(args_addr), _s()), "pf_denoiser")
+
+
+@torch.library.custom_op(f"{NS}::sample_loop", mutates_args=("pharm_x", "pharm_h", "prot_x"))
+def sample_loop(pharm_x: torch.Tensor, pharm_h: torch.Tensor, prot_x: torch.Tensor, args_addr: int) -> None:
+    """All reverse-diffusion steps described by the PfSampleArgs at `args_addr`, enqueued without returning to
+    Python between steps."""
+    _lib.check(_L.pf_sample_loop(C.c_void_p(args_addr), _s()), "pf_sample_loop")

@@ -1,0 +1,51 @@
+"""Sharding of independent graphs across GPUs.
+
+Sampling graphs never interact (every edge builder and reduction is restricted to one graph), so the flattened
+pocket-major graph list is cut into `world` contiguous ranges balanced by protein-atom count; each rank runs
+its own reverse-diffusion loop with replicated weights and no collective on the path.  Results are gathered
+once at the end (`gather_results`).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+def shard_ranges(n_pharms: Sequence[Sequence[int]], world: int,
+                 pocket_atoms: Optional[Sequence[int]] = None) -> List[range]:
+    """Contiguous graph ranges [start, stop) per rank over the flattened (pocket, sample) list."""
+    flat_w = []
+    for p, szs in enumerate(n_pharms):
+        w = float(pocket_atoms[p]) if pocket_atoms is not None else 1.0
+        flat_w.extend([w] * len(szs))
+    n = len(flat_w)
+    if n == 0:
+        return [range(0, 0) for _ in range(world)]
+    cum = np.concatenate([[0.0], np.cumsum(flat_w)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        cuts.append(int(np.clip(np.searchsorted(cum, target, side="left"), cuts[-1], n)))
+    cuts.append(n)
+    return [range(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def gather_results(local: torch.Tensor, group=None) -> Optional[List[torch.Tensor]]:
+    """The one collective of the sampling path: rank 0 receives every rank's [n_local, C] result rows."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [local]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    n_max = int(max(int(c.item()) for c in counts))
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    return [b[:int(c.item())] for b, c in zip(bufs, counts)]

@@ -1,0 +1,456 @@
+"""GPU parity tests: every CUDA entry point (through the torch.library ops over the C ABI) against the CPU
+oracle on the same seeded inputs, and against the golden fixtures produced by the reference's own code.
+
+Tolerances: edge lists / indices / tile plans bit-exact; the posterior + COM step bit-exact given identical eps;
+floating-point features within rtol 1e-4 (+ atol 1e-5 for entries near zero), the fp32 bar BASELINE.json states.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-5
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def canon(src, dst):
+    s = src.detach().cpu().numpy().astype(np.int64)
+    d = dst.detach().cpu().numpy().astype(np.int64)
+    o = np.lexsort((s, d))
+    return s[o], d[o]
+
+
+def close(a, b, rtol=RTOL, atol=ATOL, what=""):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b)
+    bound = atol + rtol * np.abs(b)
+    assert (err <= bound).all(), f"{what}: max abs err {err.max():.3e}, worst ratio {(err / bound).max():.2f}"
+
+
+def to_cm(v):   # reference vector layout [N,16,3] -> kernel layout [N,3,16] flattened to [N,48]
+    return v.permute(0, 2, 1).reshape(v.shape[0], 48).contiguous()
+
+
+def from_cm(v):
+    return v.reshape(v.shape[0], 3, 16).permute(0, 2, 1).contiguous()
+
+
+@pytest.fixture(scope="module")
+def env(sd, dyn_cfg):
+    import pf_oracle as O
+    from pharmacoforge_b200 import ops
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    from pharmacoforge_b200.synthetic import make_pocket
+    cfg = dict(dyn_cfg)
+    gcut = cfg.pop("graph_cutoffs")
+    model = PharmacophoreDiff(6, 11, ["Aromatic", "HydrogenDonor", "HydrogenAcceptor", "PositiveIon", "NegativeIon",
+                                      "Hydrophobic"], n_timesteps=100, graph_config={"graph_cutoffs": gcut},
+                              dynamics_config=cfg, precision=1e-5)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+
+    class Env:
+        pass
+    e = Env()
+    e.O, e.ops, e.model, e.sd, e.cfg = O, ops, model, sd, dyn_cfg
+    e.GraphBatch, e.Pocket, e.make_pocket = GraphBatch, Pocket, make_pocket
+    e.dev = torch.device("cuda:0")
+    e.W = model.dynamics.packed_weights(e.dev)
+
+    def build(pocket_specs, sizes):
+        """pocket_specs: [(n_atoms, seed)]; returns (GraphBatch, oracle FlatBatch)"""
+        pk = [make_pocket(n, seed=s) for n, s in pocket_specs]
+        g = GraphBatch.from_pockets([Pocket.from_numpy(p, h) for p, h in pk], sizes, e.dev)
+        b = O.build_batch([(t(p), t(h)) for p, h in pk], sizes)
+        return g, b
+    e.build = build
+
+    def set_state(g, b, pharm_x, pharm_h, prot_x=None):
+        st = model.dynamics.bind(g)
+        g.pharm_x.copy_(pharm_x)
+        g.pharm_h.copy_(pharm_h)
+        b.pharm_x, b.pharm_h = pharm_x.clone(), pharm_h.clone()
+        if prot_x is not None:
+            g.prot_x.copy_(prot_x)
+            b.prot_x = prot_x.clone()
+        return st
+    e.set_state = set_state
+    return e
+
+
+def random_state(b, seed, spread=3.0):
+    gen = torch.Generator().manual_seed(seed)
+    nf = int(b.pharm_ptr[-1])
+    x = torch.randn(nf, 3, generator=gen) * spread
+    h = torch.randn(nf, 6, generator=gen)
+    # centre every graph's protein near its pharmacophore, as the sampler's frame does
+    com = torch.stack([b.prot_x[int(b.prot_ptr[i]):int(b.prot_ptr[i + 1])].mean(0) for i in range(b.n_graphs)])
+    prot = b.prot_x - com[b.prot_b] + torch.randn(b.n_graphs, 3, generator=gen)[b.prot_b]
+    return x, h, prot
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def test_pp_radius_csr_matches_golden_and_oracle(env, golden):
+    g, b = env.build([(400, 0)], [[3]])
+    src, dst = canon(*g.pp_edges())
+    gold = golden("pp_graph_n400_seed0.npz")
+    assert np.array_equal(src, gold["src"]) and np.array_equal(dst, gold["dst"])
+    assert np.array_equal(g.pp_rowptr.cpu().numpy()[1:] - g.pp_rowptr.cpu().numpy()[:-1], g.pp_cnt.cpu().numpy())
+
+
+def test_pp_radius_csr_ragged_batch(env):
+    g, b = env.build([(400, 1), (37, 2), (250, 3), (1, 4), (1500, 5)], [[3, 8], [4], [5, 6, 7], [3], [16]])
+    s, d = canon(*g.pp_edges())
+    so, do = canon(*b.pp)
+    assert np.array_equal(s, so) and np.array_equal(d, do)
+    g.check_status()
+
+
+def test_radius_max_neighbors_truncation(env):
+    # dense cluster: more neighbours than max_num_neighbors -> first `max` in ascending index
+    O, ops = env.O, env.ops
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand(300, 3, generator=gen) * 4.0
+    ptr = torch.tensor([0, 120, 300], dtype=torch.int32)
+    rowptr, deg, col = ops.radius_csr(x.cuda(), ptr.cuda(), 3.0, 20)
+    so, do = O.radius_edges(x, ptr.long(), 3.0, 20)
+    dst = torch.repeat_interleave(torch.arange(300), deg.cpu().long())
+    s, d = canon(col.cpu(), dst)
+    so, do = canon(so, do)
+    assert deg.max().item() <= 21 and np.array_equal(s, so) and np.array_equal(d, do)
+
+
+def test_exclusive_scan(env):
+    for n in (0, 1, 5, 2048, 2049, 100_003, 3_000_017):
+        x = torch.randint(0, 20, (n,), dtype=torch.int32)
+        out = env.ops.exclusive_scan(x.cuda()).cpu()
+        ref = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(x.long(), 0)])
+        assert torch.equal(out.long(), ref), n
+
+
+# ------------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("spread", [1.0, 4.0, 12.0])
+def test_dynamic_graph_bit_exact(env, spread):
+    g, b = env.build([(400, 0), (60, 7), (3, 9)], [[3, 4, 5, 6, 7, 8], [16, 1], [4]])
+    x, h, prot = random_state(b, 11, spread)
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    ops = env.ops
+    ops.dyn_graph(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, 9.0, 200, 5, g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt,
+                  g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt, g.fp_col, g.status)
+    g.check_status()
+    got = g.dynamic_edges()
+    want = env.O.dynamic_edges(b, 9.0, 5)
+    for et in ("ff", "pf", "fp"):
+        s, d = canon(*got[et])
+        so, do = canon(*want[et])
+        assert np.array_equal(s, so) and np.array_equal(d, do), et
+    # pf rows are in ascending-distance order with ties to the lower index, exactly like knn()
+    q, c = env.O.knn_edges(b.prot_x, b.prot_ptr, b.pharm_x, b.pharm_ptr, 5)
+    assert np.array_equal(got["pf"][0].cpu().numpy(), c.numpy()) and np.array_equal(got["pf"][1].cpu().numpy(), q.numpy())
+
+
+def test_knn_ties_prefer_lower_index(env):
+    # duplicate protein atoms -> exact distance ties
+    O = env.O
+    pos = np.zeros((8, 3), dtype=np.float32)
+    pos[:, 0] = [1, 1, 2, 2, 3, 3, 4, 4]
+    onehot = np.zeros((8, 11), dtype=np.float32)
+    onehot[:, 0] = 1
+    g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[2]], env.dev)
+    b = O.build_batch([(t(pos), t(onehot))], [[2]])
+    x = torch.tensor([[0.0, 0, 0], [5.0, 0, 0]])
+    env.set_state(g, b, x.cuda(), torch.zeros(2, 6).cuda())
+    env.ops.dyn_graph(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, 9.0, 200, 5, g.ff_start, g.ff_cnt, g.ff_col,
+                      g.pf_cnt, g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt, g.fp_col, g.status)
+    q, c = O.knn_edges(b.prot_x, b.prot_ptr, x, b.pharm_ptr, 5)
+    assert np.array_equal(g.pf_col.cpu().numpy()[:10], c.numpy())
+
+
+# ------------------------------------------------------------------------------------------------ K0 / K3 / K4 / K5a
+def test_encoders(env):
+    g, b = env.build([(120, 3)], [[3, 5, 8, 6]])
+    x, h, prot = random_state(b, 5)
+    tt = torch.tensor([0.37, 0.99, 0.01, 0.5])
+    got_f = env.ops.encode(h.cuda(), g.pharm_ptr, tt.cuda(), env.W.view("pharm_enc"))
+    got_p = env.ops.encode(g.prot_feats, g.prot_ptr, tt.cuda(), env.W.view("prot_enc"))
+    close(got_f, env.O.encoder(env.sd, "dynamics.pharm_encoder", h, tt[b.pharm_b]), what="pharm enc")
+    close(got_p, env.O.encoder(env.sd, "dynamics.prot_encoder", b.prot_h, tt[b.prot_b]), what="prot enc")
+
+
+def _edge_conv_case(env, etype_idx, layer, with_vectors):
+    O, ops = env.O, env.ops
+    g, b = env.build([(150, 3), (90, 4)], [[3, 5, 8], [6, 4]])
+    x, h, prot = random_state(b, 21)
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    ops.dyn_graph(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, 9.0, 200, 5, g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt,
+                  g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt, g.fp_col, g.status)
+    edges = O.dynamic_edges(b, 9.0, 5)
+    gen = torch.Generator().manual_seed(3)
+    feats = {"pharm": (torch.randn(g.n_pharm, 128, generator=gen), x,
+                       torch.randn(g.n_pharm, 16, 3, generator=gen) * (1.0 if with_vectors else 0.0)),
+             "prot": (torch.randn(g.n_prot, 128, generator=gen), prot,
+                      torch.randn(g.n_prot, 16, 3, generator=gen) * (1.0 if with_vectors else 0.0))}
+    snt, et, dnt = O.ETYPES[etype_idx]
+    src, dst = edges[et]
+    key = f"dynamics.noise_predictor.conv_layers.{layer}.edge_message_fns.{snt}_{et}_{dnt}"
+    ms, mv = O.edge_messages(env.sd, key, feats[snt][0][src], feats[snt][2][src], feats[snt][1][src],
+                             feats[dnt][1][dst])
+    n_dst = feats[dnt][0].shape[0]
+    want_h, want_v = O.mean_aggregate(ms, dst, n_dst), O.mean_aggregate(mv, dst, n_dst)
+    seg = {"ff": (g.ff_start, g.ff_cnt, None, g.ff_col, g.pharm_chunk_ptr),
+           "pf": (g.pf_start, g.pf_cnt, None, g.pf_col, g.pharm_chunk_ptr),
+           "fp": (g.fp_seg_start, g.fp_seg_cnt, g.fp_seg_dst, g.fp_col, g.fp_chunk_ptr),
+           "pp": (g.pp_start, g.pp_cnt, None, g.pp_col, g.prot_ptr)}[et]
+    tiles = torch.zeros(2 * (g.n_prot + g.dyn_max_tiles), dtype=torch.int32, device=env.dev)
+    n_tiles = torch.zeros(1, dtype=torch.int32, device=env.dev)
+    accumulate = et in ("pf", "fp")
+    ops.plan_tiles(seg[1], seg[4], accumulate, tiles, n_tiles, g.status)
+    base_h = torch.randn(n_dst, 128, generator=gen) if accumulate else torch.full((n_dst, 128), float("nan"))
+    base_v = torch.randn(n_dst, 48, generator=gen) if accumulate else torch.full((n_dst, 48), float("nan"))
+    agg_h, agg_v = base_h.cuda(), base_v.cuda()
+    src_v = to_cm(feats[snt][2]).cuda() if with_vectors else None
+    ops.edge_conv(feats[snt][0].cuda(), src_v, feats[snt][1].cuda().contiguous(), feats[dnt][1].cuda().contiguous(),
+                  seg[0], seg[1], seg[2], seg[3], tiles, n_tiles, env.W.view(f"msg{layer}_{etype_idx}"), 3, agg_h,
+                  agg_v, accumulate)
+    g.check_status()
+    if accumulate:
+        want_h, want_v = base_h + want_h, base_v + to_cm(want_v)
+    else:
+        want_v = to_cm(want_v)
+    close(agg_h, want_h, what=f"{et} scalars")
+    close(agg_v, want_v, what=f"{et} vectors")
+
+
+@pytest.mark.parametrize("etype_idx", [0, 1, 2, 3])
+@pytest.mark.parametrize("with_vectors", [False, True])
+def test_edge_conv_each_etype(env, etype_idx, with_vectors):
+    _edge_conv_case(env, etype_idx, 1 if with_vectors else 0, with_vectors)
+
+
+def test_node_update(env):
+    O, ops = env.O, env.ops
+    gen = torch.Generator().manual_seed(8)
+    for n in (1, 63, 64, 65, 1000):
+        h, v = torch.randn(n, 128, generator=gen), torch.randn(n, 16, 3, generator=gen)
+        ah, av = torch.randn(n, 128, generator=gen), torch.randn(n, 16, 3, generator=gen)
+        p = "dynamics.noise_predictor.conv_layers.1"
+        s, vv = O.gvp_layernorm(env.sd, f"{p}.message_layer_norms.prot", h + ah, v + av)
+        rs, rv = s, vv
+        for i in range(2):
+            rs, rv = O.gvp(env.sd, f"{p}.node_update_fns.prot.{i}", rs, rv)
+        want_h, want_v = O.gvp_layernorm(env.sd, f"{p}.update_layer_norms.prot", s + rs, vv + rv)
+        hd, vd = h.cuda(), to_cm(v).cuda()
+        ops.node_update(hd, vd, ah.cuda(), to_cm(av).cuda(), env.W.view("upd1_1"), 2, hd, vd)   # in place
+        close(hd, want_h, what=f"node_update h n={n}")
+        close(from_cm(vd), want_v, what=f"node_update v n={n}")
+    # zero input vectors (first layer): v_in = None
+    h, ah, av = torch.randn(70, 128, generator=gen), torch.randn(70, 128, generator=gen), torch.randn(70, 16, 3, generator=gen)
+    p = "dynamics.noise_predictor.conv_layers.0"
+    s, vv = O.gvp_layernorm(env.sd, f"{p}.message_layer_norms.pharm", h + ah, av)
+    rs, rv = s, vv
+    for i in range(2):
+        rs, rv = O.gvp(env.sd, f"{p}.node_update_fns.pharm.{i}", rs, rv)
+    want_h, want_v = O.gvp_layernorm(env.sd, f"{p}.update_layer_norms.pharm", s + rs, vv + rv)
+    ho, vo = torch.empty(70, 128, device=env.dev), torch.empty(70, 48, device=env.dev)
+    ops.node_update(h.cuda(), None, ah.cuda(), to_cm(av).cuda(), env.W.view("upd0_0"), 2, ho, vo)
+    close(ho, want_h, what="node_update h (v=0)")
+    close(from_cm(vo), want_v, what="node_update v (v=0)")
+
+
+def test_noise_head(env):
+    gen = torch.Generator().manual_seed(9)
+    for n in (5, 64, 165):
+        h, v = torch.randn(n, 128, generator=gen), torch.randn(n, 16, 3, generator=gen)
+        wh, wx = env.O.noise_head(env.sd, "dynamics.noise_predictor.noise_predictor", h, v)
+        gh, gx = env.ops.noise_head(h.cuda(), to_cm(v).cuda(), env.W.view("noise"), 4, 6)
+        close(gh, wh, what="eps_h")
+        close(gx, wx, what="eps_x")
+
+
+# ------------------------------------------------------------------------------------------------ denoiser
+def test_denoiser_call_against_reference_golden(env, golden):
+    """The fixture holds inputs, edge lists, per-layer features and outputs of the REFERENCE's own code."""
+    d = golden("denoiser_call.npz")
+    sizes = [int(v) for v in d["sizes"]]
+    g, b = env.build([(int(d["n_atoms"]), int(d["pocket_seed"]))], [sizes])
+    st = env.set_state(g, b, t(d["x_t"]).cuda(), t(d["h_t"]).cuda(), t(d["prot_x"]).cuda())
+    eps_h, eps_x = env.model.dynamics(g, t(d["t"]), None)
+    g.check_status()
+    got = g.dynamic_edges()
+    got["pp"] = g.pp_edges()
+    for et in ("ff", "pf", "fp", "pp"):
+        s, dd = canon(*got[et])
+        assert np.array_equal(s, d[f"e_{et}_src"]) and np.array_equal(dd, d[f"e_{et}_dst"]), et
+    close(st.pharm_hh, d["conv1_pharm_h"], what="conv1 pharm h")
+    close(from_cm(st.pharm_v), d["conv1_pharm_v"], what="conv1 pharm v")
+    close(st.prot_h, d["conv1_prot_h"], what="conv1 prot h")
+    close(from_cm(st.prot_v), d["conv1_prot_v"], what="conv1 prot v")
+    close(eps_h, d["eps_h"], what="eps_h")
+    close(eps_x, d["eps_x"], what="eps_x")
+
+
+def test_denoiser_config1_size_against_oracle(env):
+    """configs[0] shape: one 400-atom pocket x 30 samples of sizes 3..8."""
+    from pharmacoforge_b200.synthetic import readme_sizes
+    g, b = env.build([(400, 0)], [readme_sizes(30)])
+    x, h, prot = random_state(b, 99, 4.0)
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    tt = torch.full((30,), 0.42)
+    wh, wx = env.O.denoiser(env.sd, b, tt, env.cfg)
+    gh, gx = env.model.dynamics(g, tt, None)
+    g.check_status()
+    close(gh, wh, what="eps_h")
+    close(gx, wx, what="eps_x")
+
+
+# ------------------------------------------------------------------------------------------------ K5b + loop
+def test_posterior_step_bit_exact(env):
+    O = env.O
+    g, b = env.build([(100, 5)], [[4, 7, 3]])
+    x, h, prot = random_state(b, 31)
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x.clone(), h.clone(), prot.clone()
+    gen = torch.Generator().manual_seed(4)
+    nf = g.n_pharm
+    eps_x, eps_h = torch.randn(nf, 3, generator=gen), torch.randn(nf, 6, generator=gen)
+    nx, nh = torch.randn(nf, 3, generator=gen), torch.randn(nf, 6, generator=gen)
+    t_host, a_ts, v_t, s_q = env.model.step_tables()
+    for i in (0, 50, 99):
+        a, v, q = (torch.tensor(float(val[i])) for val in (a_ts, v_t, s_q))
+        fb = b.pharm_b
+        b.pharm_x = (b.pharm_x / a - v * eps_x) + q * nx
+        b.pharm_h = (b.pharm_h / a - v * eps_h) + q * nh
+        O.remove_pharm_com(b)
+        env.ops.posterior_step(g.pharm_x, g.pharm_h, eps_x.cuda(), eps_h.cuda(), nx.cuda(), nh.cuda(), g.pharm_ptr,
+                               g.prot_x, g.prot_ptr, float(a_ts[i]), float(v_t[i]), float(s_q[i]))
+        assert torch.equal(g.pharm_x.cpu(), b.pharm_x) and torch.equal(g.pharm_h.cpu(), b.pharm_h)
+        assert torch.equal(g.prot_x.cpu(), b.prot_x)
+
+
+def test_step_tables_match_reference_constants(env, golden):
+    c = golden("constants.npz")
+    t_host, a_ts, v_t, s_q = env.model.step_tables()
+    assert np.array_equal(a_ts[::-1], c["alpha_ts"]) and np.array_equal(v_t[::-1], c["var_terms"])
+    assert np.array_equal(s_q[::-1], c["sigma_q"])
+    assert np.array_equal(env.model.gamma.gamma.detach().cpu().numpy(), c["gamma"])
+
+
+def test_teacher_forced_steps_against_reference_trajectory(env, golden):
+    """Feed the reference's state at step i, take ONE CUDA step with the reference's noise, compare with the
+    reference's state at step i+1 (SURVEY.md §7 hard part 3: the gate that chaos cannot blur)."""
+    d = golden("sample_traj.npz")
+    sizes = [int(v) for v in d["sizes"]]
+    n_atoms = int(d["n_atoms"])
+    g, b = env.build([(n_atoms, int(d["pocket_seed"]))], [sizes])
+    base = g.prot_x0.cpu()
+    noise = t(d["noise"])
+    model = env.model
+    st = model.dynamics.bind(g)
+    nx, nh = noise[:, :, 0:3].contiguous().cuda(), noise[:, :, 3:9].contiguous().cuda()
+    for i in (0, 1, 2, 10, 37, 50, 73, 98, 99):
+        # protein frame of graph j at step i = input pocket shifted so that its first atom matches the fixture
+        prot = base.clone()
+        for j in range(len(sizes)):
+            sl = slice(j * n_atoms, (j + 1) * n_atoms)
+            prot[sl] += t(d["traj_prot0"][i, j]) - prot[sl][0]
+        g.prot_x.copy_(prot.cuda())
+        g.pharm_x.copy_(t(d["traj_x"][i]).cuda())
+        g.pharm_h.copy_(t(d["traj_h"][i]).cuda())
+        model._run_steps(g, st, nx, nh, i, 1)
+        g.check_status()
+        close(g.pharm_x, d["traj_x"][i + 1], rtol=1e-4, atol=2e-5, what=f"x step {i}")
+        close(g.pharm_h, d["traj_h"][i + 1], rtol=1e-4, atol=2e-5, what=f"h step {i}")
+
+
+def test_full_reverse_diffusion_against_reference(env, golden):
+    d = golden("sample_traj.npz")
+    sizes = [int(v) for v in d["sizes"]]
+    g, b = env.build([(int(d["n_atoms"]), int(d["pocket_seed"]))], [sizes])
+    out = env.model.sample_given_receptor(g, noise=t(d["noise"]), visualize_trajectory=True)
+    x = torch.cat([p.ph_coords for p in out])
+    h = torch.cat([p.ph_feats for p in out])
+    types = torch.cat([p.ph_feats_idxs for p in out])
+    # 100 chained steps: fp32 re-association noise compounds, so the end-to-end bar is looser than per step
+    close(x, d["final_x"], rtol=1e-3, atol=2e-3, what="final x")
+    close(h, d["final_h"], rtol=1e-3, atol=2e-3, what="final h")
+    assert np.array_equal(types.numpy(), d["final_type"])
+    close(g.prot_x, d["final_prot"], rtol=1e-4, atol=1e-3, what="final prot frame")
+    assert out[0].pos_frames.shape == (101, sizes[0], 3)
+    assert out[0].to_xyz_file().splitlines()[0] == str(sizes[0])
+
+
+# ------------------------------------------------------------------------------------------------ properties
+def test_determinism_and_batch_composition_invariance(env):
+    from pharmacoforge_b200.synthetic import readme_sizes
+    model = env.model
+    specs = [(400, 0), (250, 1), (120, 2)]
+    sizes = [readme_sizes(6), [4, 8], [3, 5, 7]]
+    g, b = env.build(specs, sizes)
+    noise = torch.randn(11, g.n_pharm, 9, generator=torch.Generator().manual_seed(1))
+    x1, h1 = model.sample_given_receptor(g, noise=noise, n_steps=10, return_tensors=True)
+    g2, _ = env.build(specs, sizes)
+    x2, h2 = model.sample_given_receptor(g2, noise=noise, n_steps=10, return_tensors=True)
+    assert torch.equal(x1, x2) and torch.equal(h1, h2), "not bit-reproducible"
+    # the middle pocket alone must give bit-identical results: a graph never sees its batch neighbours
+    lo, hi = int(g.pharm_ptr_host[6]), int(g.pharm_ptr_host[8])
+    g3, _ = env.build([specs[1]], [sizes[1]])
+    x3, h3 = model.sample_given_receptor(g3, noise=noise[:, lo:hi].contiguous(), n_steps=10, return_tensors=True)
+    assert torch.equal(x3, x1[lo:hi]) and torch.equal(h3, h1[lo:hi])
+
+
+def test_shard_count_invariance(env):
+    """Results for N graphs as 1xN equal 2x(N/2) and 3 uneven shards bit for bit (multi-GPU sharding contract)."""
+    from pharmacoforge_b200.sharding import shard_ranges
+    model = env.model
+    pk = [env.make_pocket(n, seed=s) for n, s in [(200, 0), (300, 1)]]
+    pockets = [env.Pocket.from_numpy(p, h) for p, h in pk]
+    sizes = [[3, 4, 5, 6], [7, 8, 3, 4, 5]]
+    full = env.GraphBatch.from_pockets(pockets, sizes, env.dev)
+    noise = torch.randn(6, full.n_pharm, 9, generator=torch.Generator().manual_seed(2))
+    xf, hf = model.sample_given_receptor(full, noise=noise, n_steps=5, return_tensors=True)
+    ptr = full.pharm_ptr_host
+    for world in (2, 3):
+        xs = []
+        for r in range(world):
+            rng = shard_ranges(sizes, world)[r]
+            gb = env.GraphBatch.from_pockets(pockets, sizes, env.dev, graph_range=rng)
+            n = noise[:, int(ptr[rng.start]):int(ptr[rng.stop])].contiguous()
+            xs.append(model.sample_given_receptor(gb, noise=n, n_steps=5, return_tensors=True)[0])
+        assert torch.equal(torch.cat(xs), xf), world
+
+
+def test_equivariance_of_eps(env):
+    """SE(3): rotating + translating every graph rotates eps_x and leaves eps_h unchanged (up to fp32 noise)."""
+    g, b = env.build([(200, 3)], [[5, 8]])
+    x, h, prot = random_state(b, 77)
+    tt = torch.tensor([0.3, 0.8])
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    eh, ex = (v.clone() for v in env.model.dynamics(g, tt, None))
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(5)))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    shift = torch.tensor([1.5, -2.0, 0.7])
+    env.set_state(g, b, (x @ q.T + shift).cuda(), h.cuda(), (prot @ q.T + shift).cuda())
+    eh2, ex2 = env.model.dynamics(g, tt, None)
+    close(eh2, eh, rtol=1e-3, atol=1e-4, what="eps_h invariance")
+    close(ex2, ex.cpu() @ q.T, rtol=1e-3, atol=1e-4, what="eps_x equivariance")
+
+
+def test_degree_overflow_is_reported(env):
+    pos = np.random.default_rng(0).uniform(0, 1.0, size=(80, 3)).astype(np.float32)   # 79 neighbours each
+    onehot = np.zeros((80, 11), dtype=np.float32)
+    onehot[:, 0] = 1
+    from pharmacoforge_b200._lib import PfError
+    g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev)
+    with pytest.raises(PfError):
+        g.check_status()

@@ -1,0 +1,133 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports everything the header declares, the
+Python mirror keeps the reference's state_dict layout, packing, sharding and the synthetic generator."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pharmacoforge_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "pharmacoforge_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|size_t|const char\*)\s+(pf_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.pf_abi_version() == 1
+    assert lib.pf_sample_args_size() == ctypes.sizeof(_lib.PfSampleArgs)
+    assert lib.pf_scan_workspace_bytes(5000) >= 4 * 4
+
+
+def test_gvp_layout_is_16_byte_aligned():
+    from pharmacoforge_b200.weights import gvp_layout
+    for dims in [(17, 16, 144, 128), (16, 16, 128, 128), (16, 1, 128, 64)]:
+        offs, total = gvp_layout(*dims)
+        assert all(o % 4 == 0 for o in offs) and total % 4 == 0
+        vi, vo, si, so = dims
+        vh = max(vi, vo)
+        assert offs[1] - offs[0] >= vi * vh and offs[3] - offs[2] >= (si + vh) * so
+
+
+def test_state_dict_layout_matches_reference(layout):
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    from conftest import DEV_DYNAMICS
+    dyn = dict(DEV_DYNAMICS)
+    cut = dyn.pop("graph_cutoffs")
+    m = PharmacophoreDiff(6, 11, ["a", "b", "c", "d", "e", "f"], n_timesteps=100, graph_config={"graph_cutoffs": cut},
+                          dynamics_config=dyn, precision=1e-5, rl_dist_threshold=0)
+    sd = m.state_dict()
+    assert set(sd) == set(layout)
+    for k, shape in layout.items():
+        assert list(sd[k].shape) == shape, k
+    assert sum(v.numel() for v in sd.values()) == 772916
+    assert not m.gamma.gamma.requires_grad
+
+
+def test_checkpoint_round_trip(tmp_path, sd):
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    from conftest import DEV_DYNAMICS
+    dyn = dict(DEV_DYNAMICS)
+    cut = dyn.pop("graph_cutoffs")
+    m = PharmacophoreDiff(6, 11, ["a", "b", "c", "d", "e", "f"], n_timesteps=100, graph_config={"graph_cutoffs": cut},
+                          dynamics_config=dyn, precision=1e-5)
+    m.load_state_dict(sd, strict=True)
+    m.save_checkpoint(tmp_path / "last.ckpt")
+    m2 = PharmacophoreDiff.load_from_checkpoint(tmp_path / "last.ckpt")
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+
+
+def test_schedule_tables_match_reference_constants(golden, sd):
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff, polynomial_gamma
+    c = golden("constants.npz")
+    assert np.array_equal(polynomial_gamma(100, 1e-5, 2.0).numpy(), c["gamma"])
+    from conftest import DEV_DYNAMICS
+    dyn = dict(DEV_DYNAMICS)
+    cut = dyn.pop("graph_cutoffs")
+    m = PharmacophoreDiff(6, 11, ["a", "b", "c", "d", "e", "f"], n_timesteps=100, graph_config={"graph_cutoffs": cut},
+                          dynamics_config=dyn, precision=1e-5)
+    t_host, a_ts, v_t, s_q = m.step_tables()
+    assert np.array_equal(a_ts[::-1], c["alpha_ts"]) and np.array_equal(v_t[::-1], c["var_terms"])
+    assert np.array_equal(s_q[::-1], c["sigma_q"])
+    assert t_host[0] == np.float32(1.0) and t_host[-1] == np.float32(0.01)
+
+
+def test_weight_packing_places_transposed_blocks(sd):
+    from pharmacoforge_b200.weights import gvp_layout, pack_gvp, pack_noise_head, pack_update
+    p = "dynamics.noise_predictor.conv_layers.0.edge_message_fns.prot_pp_prot.0"
+    w = pack_gvp(sd, p)
+    offs, total = gvp_layout(17, 16, 144, 128)
+    assert w.numel() == total
+    Wf = sd[p + ".to_feats_out.0.weight"]
+    assert torch.equal(w[offs[2]:offs[2] + 161 * 128].view(161, 128), Wf.t())
+    assert torch.all(w[offs[2] + 161 * 128:offs[3]] == 0)      # K padding rows
+    assert torch.equal(w[offs[4]:offs[4] + 128 * 16].view(128, 16), sd[p + ".scalar_to_vector_gates.weight"].t())
+    assert pack_update(sd, "dynamics.noise_predictor.conv_layers.1", "prot", 2).numel() == 4 * 128 + 2 * gvp_layout(16, 16, 128, 128)[1]
+    assert pack_noise_head(sd, "dynamics.noise_predictor.noise_predictor", 4).numel() % 4 == 0
+
+
+def test_unsupported_configs_fail_loudly():
+    from pharmacoforge_b200.dynamics import PharmRecDynamicsGVP
+    with pytest.raises(NotImplementedError):
+        PharmRecDynamicsGVP(6, 11, vector_size=8, n_convs=2, graph_cutoffs={"ff": 9}, message_norm="mean", pf_k=5)
+    with pytest.raises(NotImplementedError):
+        PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm=10, pf_k=5)
+
+
+def test_ops_refuse_cpu_tensors():
+    from pharmacoforge_b200 import _lib, ops
+    with pytest.raises(_lib.PfError):
+        ops.exclusive_scan(torch.zeros(4, dtype=torch.int32))
+
+
+def test_shard_ranges_cover_and_balance():
+    from pharmacoforge_b200.sharding import shard_ranges
+    sizes = [[3] * 30 for _ in range(7)]
+    for world in (1, 2, 3, 4, 8):
+        rs = shard_ranges(sizes, world, pocket_atoms=[400] * 7)
+        assert rs[0].start == 0 and rs[-1].stop == 210
+        assert all(rs[i].stop == rs[i + 1].start for i in range(world - 1))
+        assert max(len(r) for r in rs) - min(len(r) for r in rs) <= 1
+    rs = shard_ranges([[3, 4], [5]], 8)
+    assert sum(len(r) for r in rs) == 3
+    assert shard_ranges([], 2) == [range(0, 0), range(0, 0)]
+
+
+def test_synthetic_pocket_properties():
+    from pharmacoforge_b200.synthetic import make_pocket, pocket_radius, readme_sizes
+    pos, onehot = make_pocket(400, seed=0)
+    assert pos.shape == (400, 3) and onehot.shape == (400, 11) and pos.dtype == np.float32
+    assert np.array_equal(onehot.sum(1), np.ones(400))
+    d = np.linalg.norm(pos[:, None] - pos[None], axis=-1) + np.eye(400) * 10
+    assert d.min() >= 1.3 - 1e-4
+    assert abs(pocket_radius(400) - 12.2) < 0.1 and abs(pocket_radius(1500) - 18.7) < 0.1
+    pos2, _ = make_pocket(400, seed=0)
+    assert np.array_equal(pos, pos2)
+    assert readme_sizes(30) == [3, 4, 5, 6, 7, 8] * 5
