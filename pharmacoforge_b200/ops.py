@@ -46,6 +46,8 @@ def _s():
 @torch.library.custom_op(f"{NS}::exclusive_scan", mutates_args=())
 def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
     n = x.numel()
+    if n == 0:
+        return torch.zeros(1, dtype=torch.int32, device=x.device)
     out = torch.empty(n + 1, dtype=torch.int32, device=x.device)
     ws_bytes = _L.pf_scan_workspace_bytes(n)
     ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.int32, device=x.device)
