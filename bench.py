@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 denoising hot path: pharmacophores/sec through a full T=100 reverse diffusion.
+
+    python bench.py --gpus 1 --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps K ...     # the reference algorithm on the host cores
+
+A "step" is one full reverse diffusion (100 denoiser calls + posterior/COM updates) of the whole workload:
+BASELINE.json configs[1] = 256 synthetic 400-atom pockets x 30 pharmacophores of sizes [3..8]x5 per GPU
+(7,680 graphs, 3.07 M protein nodes, ~23 M pp edges per conv), dev.yml model, seeded random weights.
+`value` times the loop with the batch resident in HBM; `e2e` times the public API from host pocket arrays to
+host results (H2D, K1 graph build, tile plan, loop, frame restore, D2H).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+FLOP_PER_EDGE = 136_742          # 68,371 MAC through the 3-GVP message chain
+DYN = dict(vector_size=16, n_convs=2, n_hidden_scalars=128, message_norm="mean", dropout=0.1, ff_k=0, pf_k=5,
+           n_message_gvps=3, n_update_gvps=2, n_noise_gvps=4)
+CUT = {"pp": 3.5, "pf": 8, "fp": 8, "ff": 9}
+PH_TYPES = ["Aromatic", "HydrogenDonor", "HydrogenAcceptor", "PositiveIon", "NegativeIon", "Hydrophobic"]
+T_STEPS = 100
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--pockets", type=int, default=256, help="pockets per GPU")
+    p.add_argument("--atoms", type=int, default=400)
+    p.add_argument("--samples", type=int, default=30)
+    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def load_weights():
+    from pharmacoforge_b200.synthetic import synth_state_dict
+    from pharmacoforge_b200.diffusion import polynomial_gamma
+    layout = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_layout.json")))
+    sd = synth_state_dict(layout, seed=0)
+    sd["gamma.gamma"] = polynomial_gamma(T_STEPS, 1e-5, 2.0)
+    return sd
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(hbm=6650.0, tf=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[0]) for r in rows]
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(rows[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, n in enumerate(names):
+                if any(r[2 + i].strip().lower().startswith("active") for r in rows):
+                    out["reasons"].append(n)
+            out["samples"] = len(rows)
+        except Exception as e:  # no nvidia-smi: report it, do not invent clocks
+            out["error"] = str(e)[:80]
+        return out
+
+
+def workload(args, rank):
+    from pharmacoforge_b200.batch import Pocket
+    from pharmacoforge_b200.synthetic import make_pocket, readme_sizes
+    pockets = [Pocket.from_numpy(*make_pocket(args.atoms, seed=rank * args.pockets + i)) for i in range(args.pockets)]
+    sizes = [readme_sizes(args.samples) for _ in range(args.pockets)]
+    return pockets, sizes
+
+
+def cpu_reference_rate(args, sd, seconds):
+    """The oracle port (reference algorithm, fp32, all host threads) on a bounded sample of configs[0]: one
+    400-atom pocket x 30 samples, a few of the 100 reverse steps, extrapolated linearly (every step does the
+    same work)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pf_oracle as O
+    from pharmacoforge_b200.synthetic import make_pocket, readme_sizes
+    torch.set_num_threads(os.cpu_count())
+    pos, onehot = make_pocket(args.atoms, seed=0)
+    sizes = [readme_sizes(args.samples)]
+    cfg = dict(DYN, graph_cutoffs=CUT)
+    b = O.build_batch([(torch.from_numpy(pos), torch.from_numpy(onehot))], sizes)
+    nf = int(b.pharm_ptr[-1])
+    noise = torch.randn(T_STEPS + 1, nf, 9, generator=torch.Generator().manual_seed(1234))
+    t0 = time.perf_counter()
+    O.sample(sd, b, noise, T_STEPS, sd["gamma.gamma"], cfg, steps=1)   # warm-up + cost estimate
+    per = time.perf_counter() - t0
+    n = int(max(2, min(T_STEPS, seconds / max(per, 1e-3))))
+    b = O.build_batch([(torch.from_numpy(pos), torch.from_numpy(onehot))], sizes)
+    t0 = time.perf_counter()
+    O.sample(sd, b, noise, T_STEPS, sd["gamma.gamma"], cfg, steps=n)
+    dt = time.perf_counter() - t0
+    rate = args.samples / (dt / n * T_STEPS)
+    sample = (f"1 synthetic {args.atoms}-atom pocket x {args.samples} samples (configs[0]), {n} of {T_STEPS} reverse "
+              f"steps in {dt:.1f} s, extrapolated x{T_STEPS}/{n}")
+    return rate, sample
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sd = load_weights()
+    rates, sample = [], ""
+    for _ in range(args.warmup):                       # short untimed passes (page in torch, warm the allocator)
+        cpu_reference_rate(args, sd, 1.0)
+    budget = min(args.cpu_seconds, 150.0 / max(args.steps, 1))   # whole arm stays within a few minutes
+    for _ in range(args.steps):
+        r, sample = cpu_reference_rate(args, sd, budget)
+        rates.append(r)
+    v = float(np.mean(rates))
+    line = {"impl": "reference", "metric": "pharmacophores/sec (full reverse diffusion)", "value": v,
+            "unit": "pharmacophores/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * args.samples / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1] algorithm on host cores, bounded sample", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "pharmacophores/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": "pharmacophores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pharmacoforge_b200 import _lib
+    from pharmacoforge_b200.batch import GraphBatch
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    from pharmacoforge_b200.sharding import gather_results
+    lib = _lib.load()
+
+    sd = load_weights()
+    model = PharmacophoreDiff(6, 11, PH_TYPES, n_timesteps=T_STEPS, graph_config={"graph_cutoffs": CUT},
+                              dynamics_config=DYN, precision=1e-5)
+    model.load_state_dict(sd)
+    model.eval()
+    pockets, sizes = workload(args, rank)
+    n_graphs = args.pockets * args.samples
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident-batch throughput ("value")
+    g = GraphBatch.from_pockets(pockets, sizes, dev)
+    st = model.dynamics.bind(g)
+
+    def resident_step():
+        g.prot_x.copy_(g.prot_x0)
+        return model.sample_given_receptor(g, return_tensors=True)
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    _lib.check(lib.pf_profile_enable(args.steps * T_STEPS * 16 + 64), "pf_profile_enable")
+    launches0 = lib.pf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            resident_step()
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = lib.pf_launch_count() - launches0
+    prof = _lib.profile_collect()
+    _lib.check(lib.pf_profile_enable(0), "pf_profile_enable")
+    g.check_status()
+    value = world * n_graphs * args.steps / (ms_total / 1e3)
+    n_ff = int(g.ff_cnt.sum().item())
+    edge_evals_per_call = DYN["n_convs"] * (g.n_pp_edges + 2 * DYN["pf_k"] * g.n_pharm + n_ff)
+    n_pp_edges, n_prot, n_pharm, h2d_bytes = g.n_pp_edges, g.n_prot, g.n_pharm, g.h2d_bytes
+
+    # ---------------- roofline of the dominant kernel (edge conv over the pp edges), measured live above
+    pk = peaks()
+    pp_ms, pp_n = prof["edge_pp"]
+    pp_avg_ms = pp_ms / max(pp_n, 1)
+    achieved_tf = n_pp_edges * FLOP_PER_EDGE / (pp_avg_ms * 1e-3) / 1e12 if pp_n else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "edge_pp_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"kernel": "edge_conv_kernel (pp edges)", "bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"],
+                "unit": "TFLOP/s", "frac": achieved_tf / pk["tf"], "traffic": traffic, "peak_source": pk["src"],
+                "avg_launch_ms": pp_avg_ms, "launches_timed": pp_n, "edges_per_launch": n_pp_edges,
+                "share_of_step": pp_ms / ms_total,
+                "note": "fp32 FFMA path: no tensor-pipe instructions yet; algorithmic 136,742 FLOP/edge"}
+    breakdown = {k: round(v[0] / ms_total, 4) for k, v in prof.items() if v[1]}
+    del g, st
+    torch.cuda.empty_cache()
+
+    # ---------------- end to end through the public API, host buffers in / host results out
+    def e2e_step():
+        gb = model.make_batch(pockets, sizes, device=dev)
+        x0, h0 = model.sample_given_receptor(gb, return_tensors=True)
+        res = torch.cat([x0, h0], dim=1)
+        parts = gather_results(res)          # the one collective of the sampling path (rank 0 receives)
+        host = [p.cpu() for p in parts] if parts is not None else None
+        return host, gb.h2d_bytes, res.numel() * 4
+
+    e2e_step()
+    barrier()
+    n_e2e = max(1, min(args.steps, args.e2e_steps))
+    e0.record()
+    for _ in range(n_e2e):
+        host, h2d, d2h = e2e_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_graphs * n_e2e / (float(ms2.item()) / 1e3)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r, sample = cpu_reference_rate(args, sd, args.cpu_seconds)
+            cpu = {"value": r, "unit": "pharmacophores/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
+        line = {
+            "metric": "pharmacophores/sec (full reverse diffusion)", "value": value, "unit": "pharmacophores/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: {args.pockets} synthetic {args.atoms}-atom pockets x {args.samples} "
+                                   f"samples (sizes [3..8]x5) per GPU, dev.yml denoiser, T={T_STEPS}, seeded random "
+                                   "weights, device Philox noise",
+                       "graphs_per_gpu": n_graphs, "prot_nodes_per_gpu": n_prot, "pharm_nodes_per_gpu": n_pharm,
+                       "pp_edges_per_conv_per_gpu": n_pp_edges, "parallelism": f"graphs sharded x{world}, no collective "
+                       "on the path, one final gather", "l2": "inputs_exceed_l2 (2.2 GB of node features per conv)"},
+            "denoiser_edges_per_s": edge_evals_per_call * T_STEPS * args.steps * world / (ms_total / 1e3),
+            "roofline": roofline, "kernel_time_share": breakdown, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "pharmacophores/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+                    "api": "PharmacophoreDiff.make_batch + sample_given_receptor + gather + .cpu()"},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

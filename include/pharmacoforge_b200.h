@@ -208,6 +208,17 @@ int pf_sample_loop(const PfSampleArgs* a, void* stream);
 int pf_fill_f32(float* p, int64_t n, float v, void* stream);
 size_t pf_sample_args_size(void); /* sizeof(PfSampleArgs), for binding self-checks */
 
+/* ---- measurement hooks (bench.py) ----------------------------------------------------------------------
+ * pf_launch_count: kernels this library has launched in this process so far.
+ * pf_profile_enable(n): n > 0 arms CUDA-event pairs around every kernel site of pf_denoiser /
+ * pf_sample_loop (recorded on the launching stream); 0 disarms.  After synchronising the stream,
+ * pf_profile_collect sums the elapsed ms and launch count per site and resets the recorder.  Sites:
+ * 0 dyn_graph, 1 (unused), 2 (unused), 3 edge ff, 4 edge pf, 5 edge pp, 6 edge fp, 7 update pharm,
+ * 8 update prot, 9 noise head, 10 posterior+COM. */
+int64_t pf_launch_count(void);
+int pf_profile_enable(int32_t max_pairs);
+int pf_profile_collect(double* total_ms_host, int32_t* count_host, int32_t n_sites);
+
 #ifdef __cplusplus
 }
 #endif

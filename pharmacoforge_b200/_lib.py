@@ -39,6 +39,9 @@ SIGNATURES = {
     "pf_segment_mean3": (C.c_int, [c_f32p, c_i32p, C.c_int32, c_f32p, STREAM]),
     "pf_segment_shift3": (C.c_int, [c_f32p, c_i32p, C.c_int32, c_f32p, C.c_float, STREAM]),
     "pf_sample_args_size": (C.c_size_t, []),
+    "pf_launch_count": (C.c_int64, []),
+    "pf_profile_enable": (C.c_int, [C.c_int32]),
+    "pf_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32]),
     "pf_denoiser": (C.c_int, [C.c_void_p, STREAM]),
     "pf_sample_loop": (C.c_int, [C.c_void_p, STREAM]),
 }
@@ -130,3 +133,16 @@ def check_dev_status(word: int):
     if word:
         msgs = [m for b, m in DEV_STATUS_BITS.items() if word & b]
         raise PfError("device status 0x%x: %s" % (word, "; ".join(msgs)))
+
+
+PROFILE_SITES = ("dyn_graph", "plan", "encode", "edge_ff", "edge_pf", "edge_pp", "edge_fp", "update_pharm",
+                 "update_prot", "noise_head", "posterior")
+
+
+def profile_collect():
+    """{site: (total_ms, launches)} since the last collect; call after synchronising the stream."""
+    n = len(PROFILE_SITES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int32 * n)()
+    check(load().pf_profile_collect(ms, cnt, n), "pf_profile_collect")
+    return {s: (float(ms[i]), int(cnt[i])) for i, s in enumerate(PROFILE_SITES)}

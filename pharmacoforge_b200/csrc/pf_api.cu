@@ -15,6 +15,33 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+// ---- per-site event timing: pairs are recorded on the launching stream and resolved in pf_profile_collect
+struct ProfPair {
+  cudaEvent_t a, b;
+  int site;
+};
+static ProfPair* g_pairs = nullptr;
+static int g_pair_cap = 0, g_pair_n = 0, g_pair_open[kNumSites];
+static bool g_prof_on = false;
+
+void prof_begin(int site, cudaStream_t st) {
+  if (!g_prof_on || g_pair_n >= g_pair_cap) {
+    if (g_prof_on) g_pair_open[site] = -1;
+    return;
+  }
+  g_pairs[g_pair_n].site = site;
+  cudaEventRecord(g_pairs[g_pair_n].a, st);
+  g_pair_open[site] = g_pair_n++;
+}
+void prof_end(int site, cudaStream_t st) {
+  if (!g_prof_on || g_pair_open[site] < 0) return;
+  cudaEventRecord(g_pairs[g_pair_open[site]].b, st);
+  g_pair_open[site] = -1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5b.  One CTA per graph.  Every operation is rounded separately in the reference's order
 // (pharmacodiff.py:416-426: mu = z/alpha - var*eps; z_s = mu + sigma*noise; com = sum/count; z -= com), so
@@ -101,6 +128,46 @@ using namespace pf;
 extern "C" int pf_abi_version(void) { return PF_ABI_VERSION; }
 extern "C" const char* pf_last_error(void) { return g_err; }
 extern "C" size_t pf_sample_args_size(void) { return sizeof(PfSampleArgs); }
+extern "C" int64_t pf_launch_count(void) { return g_launches; }
+
+extern "C" int pf_profile_enable(int32_t max_pairs) {
+  for (int i = 0; i < g_pair_cap; ++i) {
+    cudaEventDestroy(g_pairs[i].a);
+    cudaEventDestroy(g_pairs[i].b);
+  }
+  delete[] g_pairs;
+  g_pairs = nullptr;
+  g_pair_cap = g_pair_n = 0;
+  g_prof_on = max_pairs > 0;
+  for (int i = 0; i < kNumSites; ++i) g_pair_open[i] = -1;
+  if (!g_prof_on) return PF_OK;
+  g_pairs = new ProfPair[max_pairs];
+  for (int i = 0; i < max_pairs; ++i) {
+    if (cudaEventCreate(&g_pairs[i].a) != cudaSuccess || cudaEventCreate(&g_pairs[i].b) != cudaSuccess) {
+      set_error("pf_profile_enable: cudaEventCreate failed");
+      return PF_ERR_LAUNCH;
+    }
+  }
+  g_pair_cap = max_pairs;
+  return PF_OK;
+}
+
+extern "C" int pf_profile_collect(double* total_ms_host, int32_t* count_host, int32_t n_sites) {
+  PF_CHECK_ARG(total_ms_host && count_host && n_sites >= kNumSites, "pf_profile_collect: need >= 11 sites");
+  for (int i = 0; i < n_sites; ++i) {
+    total_ms_host[i] = 0.0;
+    count_host[i] = 0;
+  }
+  for (int i = 0; i < g_pair_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_pairs[i].a, g_pairs[i].b) == cudaSuccess) {
+      total_ms_host[g_pairs[i].site] += ms;
+      count_host[g_pairs[i].site] += 1;
+    }
+  }
+  g_pair_n = 0;
+  return PF_OK;
+}
 
 extern "C" int64_t pf_gvp_layout(int vi, int vo, int si, int so, int64_t offsets_out_host[6]) {
   const GvpLayout L = gvp_layout(vi, vo, si, so);
@@ -167,9 +234,11 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_CHECK_ARG(a != nullptr, "pf_denoiser: null args");
   PF_CHECK_ARG(a->n_convs >= 1 && a->n_convs <= 8, "pf_denoiser: n_convs out of range (1..8)");
   // graph of this step: ff radius + pf kNN + fp reverse (dynamics_gvp.py:176-177)
+  prof_begin(kSiteGraph, as_stream(stream));
   PF_TRY(pf_dyn_graph(a->prot_x, a->prot_ptr, a->pharm_x, a->pharm_ptr, a->n_graphs, a->ff_r, a->ff_max_nbrs, a->pf_k,
                       a->ff_start, a->ff_cnt, a->ff_col, a->pf_cnt, a->pf_col, a->fp_seg_dst, a->fp_seg_start,
                       a->fp_seg_cnt, a->fp_col, a->dev_status, stream));
+  prof_end(kSiteGraph, as_stream(stream));
   PF_TRY(pf_zero_i32(a->dyn_n_tiles, 3, stream));
   PF_TRY(pf_plan_tiles(a->ff_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 0, a->ff_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 0, a->dev_status, stream));
@@ -186,26 +255,40 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     const float* fv = l == 0 ? nullptr : a->pharm_v;
     const float* pv = l == 0 ? nullptr : a->prot_v;
     // pharm <- ff (store) + pf (accumulate); prot <- pp (store) + fp (accumulate)  (gvp.py:484-497)
-    PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
+    prof_begin(kSiteFF, as_stream(stream));
+  PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
                         a->ff_tiles, a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg[l][0], a->n_msg_gvps,
                         a->pharm_agg_h, a->pharm_agg_v, 0, stream));
-    PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col, a->pf_tiles,
+  prof_end(kSiteFF, as_stream(stream));
+    prof_begin(kSitePF, as_stream(stream));
+  PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col, a->pf_tiles,
                         a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->n_msg_gvps, a->pharm_agg_h,
                         a->pharm_agg_v, 1, stream));
-    PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col, a->pp_tiles,
+  prof_end(kSitePF, as_stream(stream));
+    prof_begin(kSitePP, as_stream(stream));
+  PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col, a->pp_tiles,
                         a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v,
                         0, stream));
-    PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
+  prof_end(kSitePP, as_stream(stream));
+    prof_begin(kSiteFP, as_stream(stream));
+  PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
                         a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2], a->n_msg_gvps,
                         a->prot_agg_h, a->prot_agg_v, 1, stream));
+  prof_end(kSiteFP, as_stream(stream));
     // node updates, in place (gvp.py:501-536)
-    PF_TRY(pf_node_update(a->pharm_hh, fv, a->pharm_agg_h, a->pharm_agg_v, a->n_pharm, a->w_upd[l][0], a->n_upd_gvps,
+    prof_begin(kSiteUpdPharm, as_stream(stream));
+  PF_TRY(pf_node_update(a->pharm_hh, fv, a->pharm_agg_h, a->pharm_agg_v, a->n_pharm, a->w_upd[l][0], a->n_upd_gvps,
                           a->pharm_hh, a->pharm_v, stream));
-    PF_TRY(pf_node_update(a->prot_h, pv, a->prot_agg_h, a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps,
+  prof_end(kSiteUpdPharm, as_stream(stream));
+    prof_begin(kSiteUpdProt, as_stream(stream));
+  PF_TRY(pf_node_update(a->prot_h, pv, a->prot_agg_h, a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps,
                           a->prot_h, a->prot_v, stream));
+  prof_end(kSiteUpdProt, as_stream(stream));
   }
+  prof_begin(kSiteNoise, as_stream(stream));
   PF_TRY(pf_noise_head(a->pharm_hh, a->pharm_v, a->n_pharm, a->w_noise, a->n_noise_gvps, a->n_pharm_feats, a->eps_h,
                        a->eps_x, stream));
+  prof_end(kSiteNoise, as_stream(stream));
   return PF_OK;
 }
 
@@ -218,9 +301,11 @@ extern "C" int pf_sample_loop(const PfSampleArgs* a, void* stream) {
   for (int i = 0; i < a->n_steps; ++i) {
     PF_TRY(pf_fill_f32(a->t_graph, a->n_graphs, a->t_host[i], stream));
     PF_TRY(pf_denoiser(a, stream));
-    PF_TRY(pf_posterior_step(a->pharm_x, a->pharm_h, a->n_pharm_feats, a->eps_x, a->eps_h, a->noise_x + i * fx,
+    prof_begin(kSitePosterior, as_stream(stream));
+  PF_TRY(pf_posterior_step(a->pharm_x, a->pharm_h, a->n_pharm_feats, a->eps_x, a->eps_h, a->noise_x + i * fx,
                              a->noise_h + i * fh, a->pharm_ptr, a->prot_x, a->prot_ptr, a->n_graphs,
                              a->alpha_ts_host[i], a->var_terms_host[i], a->sigma_q_host[i], stream));
+  prof_end(kSitePosterior, as_stream(stream));
   }
   return PF_OK;
 }

@@ -9,6 +9,13 @@
 namespace pf {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+
+// Optional per-site CUDA-event timing (bench.py's roofline leg).  Sites index the kernels of one denoiser call.
+enum ProfSite { kSiteGraph = 0, kSitePlan, kSiteEncode, kSiteFF, kSitePF, kSitePP, kSiteFP, kSiteUpdPharm,
+                kSiteUpdProt, kSiteNoise, kSitePosterior, kNumSites };
+void prof_begin(int site, cudaStream_t st);
+void prof_end(int site, cudaStream_t st);
 
 #define PF_CHECK_ARG(cond, msg)                  \
   do {                                           \
@@ -26,6 +33,7 @@ void set_error(const char* fmt, ...);
       (void)cudaGetLastError();                                            \
       return PF_ERR_LAUNCH;                                                \
     }                                                                      \
+    pf::count_launch();                                                    \
   } while (0)
 
 constexpr int kHidden = PF_HIDDEN;
