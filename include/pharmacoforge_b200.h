@@ -215,6 +215,11 @@ size_t pf_sample_args_size(void); /* sizeof(PfSampleArgs), for binding self-chec
  * pf_profile_collect sums the elapsed ms and launch count per site and resets the recorder.  Sites:
  * 0 dyn_graph, 1 (unused), 2 (unused), 3 edge ff, 4 edge pf, 5 edge pp, 6 edge fp, 7 update pharm,
  * 8 update prot, 9 noise head, 10 posterior+COM. */
+/* tcgen05 building-block self-test: D[128][N] = A[128][K] * B[N][K]^T on the tensor cores, A split into bf16
+ * (hi, lo) in TMEM, B given as packed bf16 shared-memory images (layout: pf_tc.cuh); npass 1 (hi*hi) or 3
+ * (hi*hi + hi*lo + lo*hi, fp32-accurate). */
+int pf_tc_selftest(const float* A, const void* b_hi, const void* b_lo, float* D, int32_t K, int32_t N, int32_t npass,
+                   void* stream);
 int64_t pf_launch_count(void);
 int pf_profile_enable(int32_t max_pairs);
 int pf_profile_collect(double* total_ms_host, int32_t* count_host, int32_t n_sites);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "pf_segment_mean3": (C.c_int, [c_f32p, c_i32p, C.c_int32, c_f32p, STREAM]),
     "pf_segment_shift3": (C.c_int, [c_f32p, c_i32p, C.c_int32, c_f32p, C.c_float, STREAM]),
     "pf_sample_args_size": (C.c_size_t, []),
+    "pf_tc_selftest": (C.c_int, [c_f32p, C.c_void_p, C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32, STREAM]),
     "pf_launch_count": (C.c_int64, []),
     "pf_profile_enable": (C.c_int, [C.c_int32]),
     "pf_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32]),

@@ -111,3 +111,20 @@ class PackedWeights:
         i = keys.index(key)
         end = self.offsets[keys[i + 1]] if i + 1 < len(keys) else self.flat.numel()
         return self.flat[self.offsets[key]:end]
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 operands
+def split_bf16(w: torch.Tensor):
+    """w ~= hi + lo with both parts bf16 (round to nearest even), as the kernels split activations on the fly."""
+    hi = w.float().to(torch.bfloat16)
+    lo = (w.float() - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def umma_b_image(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] bf16 weight (K contiguous = 'K-major') -> the SWIZZLE_NONE shared-memory image tcgen05.mma reads:
+    8x8 core matrices of 128 contiguous bytes, element (n, k) at (k/8)*(N/8)*64 + (n/8)*64 + (n%8)*8 + k%8 (in
+    bf16 units).  See csrc/pf_tc.cuh."""
+    n, k = w.shape
+    assert n % 8 == 0 and k % 8 == 0 and w.dtype == torch.bfloat16
+    return w.reshape(n // 8, 8, k // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
