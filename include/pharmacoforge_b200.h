@@ -51,7 +51,8 @@ enum PfStatus {
 #define PF_HIDDEN 128            /* dynamics.n_hidden_scalars (configs/dev.yml:82) */
 #define PF_VEC 16                /* dynamics.vector_size (configs/dev.yml:80) */
 #define PF_RBF 16                /* GVPMultiEdgeConv rbf_dim default (gvp.py:350) */
-#define PF_TILE_ROWS 64          /* edge / node rows per CTA tile */
+#define PF_TILE_ROWS 64          /* edge / node rows per CTA tile, fp32 FFMA kernels */
+#define PF_TC_TILE_ROWS 128      /* edge rows per tile of the tcgen05 kernels (= TMEM lanes) */
 #define PF_MAX_PHARM_PER_GRAPH 128
 #define PF_MAX_KNN 16
 
@@ -102,11 +103,12 @@ int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const float* phar
 
 /* ---- tile planner --------------------------------------------------------------------------------
  * Greedily packs consecutive segments of each chunk [chunk_ptr[c], chunk_ptr[c+1]) into tiles of at
- * most PF_TILE_ROWS edges and PF_TILE_ROWS segments.  tiles[2*t], tiles[2*t+1] = first / one-past-last
+ * most tile_rows edges and tile_rows segments (PF_TILE_ROWS for the FFMA kernels, PF_TC_TILE_ROWS for tcgen05).  tiles[2*t], tiles[2*t+1] = first / one-past-last
  * segment.  *n_tiles must be zeroed by the caller (pf_zero_i32).  With skip_empty != 0 tiles without
  * edges are not emitted (accumulate-mode edge types). */
 int pf_plan_tiles(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_chunks, int32_t skip_empty,
-                  int32_t* tiles, int32_t max_tiles, int32_t* n_tiles, uint32_t* dev_status, void* stream);
+                  int32_t tile_rows, int32_t* tiles, int32_t max_tiles, int32_t* n_tiles, uint32_t* dev_status,
+                  void* stream);
 int pf_zero_i32(int32_t* p, int64_t n, void* stream);
 
 /* ---- K0: time-conditioned scalar encoders --------------------------------------------------------
@@ -127,6 +129,16 @@ int pf_edge_conv(const float* src_h, const float* src_v, const float* src_x, con
                  const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
                  const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const float* w, int32_t n_gvps,
                  float* agg_h, float* agg_v, int32_t accumulate, void* stream);
+
+/* K3 on the tensor cores (tcgen05.mma, bf16 hi/lo split operands, fp32 accumulation in TMEM; fp32-accurate).
+ * Same contract as pf_edge_conv for n_gvps == 3 with tiles planned at PF_TC_TILE_ROWS; `wblob` is the
+ * pf_tc_msg_blob_bytes()-byte image built by pharmacoforge_b200/weights.py:pack_message_tc (weight slabs in the
+ * UMMA SWIZZLE_NONE K-major layout, split into bf16 hi and lo parts), 16-byte aligned. */
+size_t pf_tc_msg_blob_bytes(void);
+int pf_edge_conv_tc(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+                    const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
+                    const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const void* wblob, float* agg_h,
+                    float* agg_v, int32_t accumulate, void* stream);
 
 /* ---- K4: node update ------------------------------------------------------------------------------
  * gvp.py:511-532 in eval mode: (h,v) <- GVPLayerNorm_msg(h + agg_h, v + agg_v); (rh,rv) = GVP x n_gvps;
@@ -193,6 +205,10 @@ typedef struct PfSampleArgs {
   const float* w_msg[8][4];   /* [conv][etype: ff, pf, fp, pp] */
   const float* w_upd[8][2];   /* [conv][ntype: pharm, prot] */
   const float* w_noise;
+  /* tcgen05 path: tile_rows = PF_TC_TILE_ROWS and every w_msg_tc[conv][etype] set -> K3 runs on the tensor cores;
+   * tile_rows = PF_TILE_ROWS -> fp32 FFMA kernels */
+  const void* w_msg_tc[8][4];
+  int32_t tile_rows;
   /* schedule (host): step i uses t = t_host[i], coefficients alpha_ts_host[i], ... */
   const float *t_host, *alpha_ts_host, *var_terms_host, *sigma_q_host;
   const float* noise_x;       /* device [n_steps][n_pharm][3] */

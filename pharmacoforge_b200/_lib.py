@@ -25,7 +25,11 @@ SIGNATURES = {
     "pf_radius_fill": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, c_i32p, c_i32p, STREAM]),
     "pf_dyn_graph": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, c_i32p,
                                c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
-    "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p, STREAM]),
+    "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
+                                STREAM]),
+    "pf_tc_msg_blob_bytes": (C.c_size_t, []),
+    "pf_edge_conv_tc": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
+                                  C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, STREAM]),
     "pf_zero_i32": (C.c_int, [c_i32p, C.c_int64, STREAM]),
     "pf_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, STREAM]),
     "pf_encode": (C.c_int, [c_f32p, C.c_int32, c_i32p, C.c_int32, c_f32p, c_f32p, c_f32p, STREAM]),
@@ -79,6 +83,8 @@ class PfSampleArgs(C.Structure):
         ("w_msg", (C.c_void_p * 4) * MAX_CONVS),
         ("w_upd", (C.c_void_p * 2) * MAX_CONVS),
         ("w_noise", C.c_void_p),
+        ("w_msg_tc", (C.c_void_p * 4) * MAX_CONVS),
+        ("tile_rows", C.c_int32),
         ("t_host", C.c_void_p), ("alpha_ts_host", C.c_void_p), ("var_terms_host", C.c_void_p),
         ("sigma_q_host", C.c_void_p),
         ("noise_x", C.c_void_p), ("noise_h", C.c_void_p),
@@ -123,7 +129,7 @@ def check(rc: int, what: str = ""):
 
 
 DEV_STATUS_BITS = {
-    1: "a destination node has more in-edges than one tile holds (PF_TILE_ROWS=64)",
+    1: "a destination node has more in-edges than one tile holds (64 rows FFMA / 128 rows tcgen05)",
     2: "a graph has more pharmacophore nodes than PF_MAX_PHARM_PER_GRAPH=128",
     4: "tile list capacity exceeded",
     8: "edge buffer capacity exceeded",

@@ -12,6 +12,7 @@ pp / pf / ff / fp; protein_pharm_dataset.py:210-266, unorganized_utils.py:28-95)
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -63,7 +64,7 @@ class GraphBatch:
     @classmethod
     def from_pockets(cls, pockets: Sequence[Pocket], sizes: Sequence[Sequence[int]], device, pp_cutoff: float = 3.5,
                      pf_k: int = 5, ff_max_nbrs: int = 200, pp_max_nbrs: int = 100,
-                     graph_range: Optional[range] = None) -> "GraphBatch":
+                     graph_range: Optional[range] = None, tile_rows: int = 128) -> "GraphBatch":
         """One graph per (pocket, requested pharmacophore size), pocket-major, exactly the order
         `PharmacophoreDiff.sample` flattens them in (pharmacodiff.py:538-544).  `graph_range` restricts the batch
         to a slice of that flattened list (max_batch_size chunking / multi-GPU sharding)."""
@@ -73,6 +74,10 @@ class GraphBatch:
             raise RuntimeError("GraphBatch lives on a CUDA device; there is no CPU path")
         self.device = dev
         self.pf_k, self.ff_max_nbrs = int(pf_k), int(ff_max_nbrs)
+        tile_rows = int(os.environ.get("PF_TILE_ROWS", tile_rows))   # A/B switch: 64 = fp32 FFMA kernels
+        if tile_rows not in (64, 128):
+            raise ValueError("tile_rows: 128 (tcgen05 kernels) or 64 (fp32 FFMA kernels)")
+        self.tile_rows = int(tile_rows)
         graph_pocket, graph_nf = [], []
         for p, szs in enumerate(sizes):
             for nf in szs:
@@ -125,7 +130,7 @@ class GraphBatch:
         self.n_pp_edges = int(self.pp_col.numel())
         self.pp_tiles = torch.empty(2 * max(self.n_prot + B, 1), dtype=torch.int32, device=dev)
         self.pp_n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
-        ops.plan_tiles(self.pp_cnt, self.prot_ptr, False, self.pp_tiles, self.pp_n_tiles, self.status)
+        ops.plan_tiles(self.pp_cnt, self.prot_ptr, False, self.tile_rows, self.pp_tiles, self.pp_n_tiles, self.status)
         self.pp_num_tiles = int(self.pp_n_tiles.item())
         self.pp_tiles = self.pp_tiles[:2 * max(self.pp_num_tiles, 1)].clone()
 

@@ -229,6 +229,18 @@ extern "C" int pf_fill_f32(float* p, int64_t n, float v, void* stream) {
     if (rc_ != PF_OK) return rc_; \
   } while (0)
 
+static int edge_conv_any(bool tc, const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+                         const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
+                         const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const float* w,
+                         const void* w_tc, int32_t n_gvps, float* agg_h, float* agg_v, int32_t accumulate,
+                         void* stream) {
+  if (tc)
+    return pf_edge_conv_tc(src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles, max_tiles,
+                           w_tc, agg_h, agg_v, accumulate, stream);
+  return pf_edge_conv(src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles, max_tiles, w,
+                      n_gvps, agg_h, agg_v, accumulate, stream);
+}
+
 // One eps prediction: PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185) with a->t_graph already set.
 extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_CHECK_ARG(a != nullptr, "pf_denoiser: null args");
@@ -240,11 +252,18 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                       a->fp_seg_cnt, a->fp_col, a->dev_status, stream));
   prof_end(kSiteGraph, as_stream(stream));
   PF_TRY(pf_zero_i32(a->dyn_n_tiles, 3, stream));
-  PF_TRY(pf_plan_tiles(a->ff_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 0, a->ff_tiles, a->dyn_max_tiles,
+  PF_CHECK_ARG(a->tile_rows == PF_TILE_ROWS || a->tile_rows == PF_TC_TILE_ROWS, "pf_denoiser: tile_rows must be 64 or 128");
+  const bool tc = a->tile_rows == PF_TC_TILE_ROWS;
+  if (tc) {
+    PF_CHECK_ARG(a->n_msg_gvps == 3, "pf_denoiser: the tcgen05 message kernel is built for n_message_gvps == 3");
+    for (int l = 0; l < a->n_convs; ++l)
+      for (int e = 0; e < 4; ++e) PF_CHECK_ARG(a->w_msg_tc[l][e] != nullptr, "pf_denoiser: missing tcgen05 weight blob");
+  }
+  PF_TRY(pf_plan_tiles(a->ff_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 0, a->tile_rows, a->ff_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 0, a->dev_status, stream));
-  PF_TRY(pf_plan_tiles(a->pf_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 1, a->pf_tiles, a->dyn_max_tiles,
+  PF_TRY(pf_plan_tiles(a->pf_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 1, a->tile_rows, a->pf_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 1, a->dev_status, stream));
-  PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->fp_tiles, a->dyn_max_tiles,
+  PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->tile_rows, a->fp_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 2, a->dev_status, stream));
   // encoders (dynamics_gvp.py:143-151); node vectors start at zero (:162-173) and are never materialised
   PF_TRY(pf_encode(a->pharm_h, a->n_pharm_feats, a->pharm_ptr, a->n_graphs, a->t_graph, a->w_pharm_enc, a->pharm_hh,
@@ -256,24 +275,24 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     const float* pv = l == 0 ? nullptr : a->prot_v;
     // pharm <- ff (store) + pf (accumulate); prot <- pp (store) + fp (accumulate)  (gvp.py:484-497)
     prof_begin(kSiteFF, as_stream(stream));
-  PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
-                        a->ff_tiles, a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg[l][0], a->n_msg_gvps,
-                        a->pharm_agg_h, a->pharm_agg_v, 0, stream));
+    PF_TRY(edge_conv_any(tc, a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
+                         a->ff_tiles, a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg[l][0], a->w_msg_tc[l][0],
+                         a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 0, stream));
   prof_end(kSiteFF, as_stream(stream));
     prof_begin(kSitePF, as_stream(stream));
-  PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col, a->pf_tiles,
-                        a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->n_msg_gvps, a->pharm_agg_h,
-                        a->pharm_agg_v, 1, stream));
+    PF_TRY(edge_conv_any(tc, a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col,
+                         a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->w_msg_tc[l][1],
+                         a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
   prof_end(kSitePF, as_stream(stream));
     prof_begin(kSitePP, as_stream(stream));
-  PF_TRY(pf_edge_conv(a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col, a->pp_tiles,
-                        a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v,
-                        0, stream));
+    PF_TRY(edge_conv_any(tc, a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col,
+                         a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->w_msg_tc[l][3],
+                         a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 0, stream));
   prof_end(kSitePP, as_stream(stream));
     prof_begin(kSiteFP, as_stream(stream));
-  PF_TRY(pf_edge_conv(a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
-                        a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2], a->n_msg_gvps,
-                        a->prot_agg_h, a->prot_agg_v, 1, stream));
+    PF_TRY(edge_conv_any(tc, a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
+                         a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2],
+                         a->w_msg_tc[l][2], a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 1, stream));
   prof_end(kSiteFP, as_stream(stream));
     // node updates, in place (gvp.py:501-536)
     prof_begin(kSiteUpdPharm, as_stream(stream));

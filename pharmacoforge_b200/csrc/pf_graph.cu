@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(kDynThreads) dyn_graph_kernel(const DynGraphPa
 // ------------------------------------------------------------------------------------------------ planner
 __global__ void __launch_bounds__(128) plan_tiles_kernel(const int* __restrict__ seg_cnt,
                                                          const int* __restrict__ chunk_ptr, int n_chunks,
-                                                         int skip_empty, int* __restrict__ tiles, int max_tiles,
+                                                         int skip_empty, int tile_rows,
+                                                         int* __restrict__ tiles, int max_tiles,
                                                          int* __restrict__ n_tiles, unsigned* __restrict__ status) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_chunks) return;
@@ -329,9 +330,9 @@ __global__ void __launch_bounds__(128) plan_tiles_kernel(const int* __restrict__
   const int s_end = chunk_ptr[c + 1];
   while (s < s_end) {
     int rows = 0, e = s;
-    while (e < s_end && e - s < PF_TILE_ROWS) {
+    while (e < s_end && e - s < tile_rows) {
       const int cnt = seg_cnt[e];
-      if (rows + cnt > PF_TILE_ROWS) break;
+      if (rows + cnt > tile_rows) break;
       rows += cnt;
       ++e;
     }
@@ -437,12 +438,14 @@ extern "C" int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const 
 }
 
 extern "C" int pf_plan_tiles(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_chunks, int32_t skip_empty,
-                             int32_t* tiles, int32_t max_tiles, int32_t* n_tiles, uint32_t* dev_status,
-                             void* stream) {
+                             int32_t tile_rows, int32_t* tiles, int32_t max_tiles, int32_t* n_tiles,
+                             uint32_t* dev_status, void* stream) {
   PF_CHECK_ARG(seg_cnt && chunk_ptr && tiles && n_tiles && dev_status, "pf_plan_tiles: null pointer");
+  PF_CHECK_ARG(tile_rows == PF_TILE_ROWS || tile_rows == PF_TC_TILE_ROWS, "pf_plan_tiles: tile_rows must be 64 or 128");
   if (n_chunks <= 0) return PF_OK;
   plan_tiles_kernel<<<(n_chunks + 127) / 128, 128, 0, as_stream(stream)>>>(seg_cnt, chunk_ptr, n_chunks, skip_empty,
-                                                                          tiles, max_tiles, n_tiles, dev_status);
+                                                                          tile_rows, tiles, max_tiles, n_tiles,
+                                                                          dev_status);
   PF_CHECK_LAUNCH("pf_plan_tiles");
   return PF_OK;
 }

@@ -1,0 +1,603 @@
+// K3 on the 5th-generation tensor cores: gather -> edge features -> 3-GVP message chain -> segmented mean, one
+// persistent CTA per SM, two 128-edge tiles in flight (ping-pong between the tensor pipe and the CUDA cores).
+//
+// Replaces, per edge type of one GVPMultiEdgeConv layer, gvp.py:472-497 + 540-551 -> 89-116 of the reference.
+//
+// Numerics: every dense contraction runs as tcgen05.mma kind::f16 with both operands split into bf16 (hi, lo)
+// pairs and three passes hi*hi + hi*lo + lo*hi accumulated in fp32 TMEM (|x - hi - lo| <= 2^-17 |x|), which keeps
+// the fp32 1e-4 parity bar of BASELINE.json; SiLU / sigmoid / norms / means run in fp32 on the CUDA cores.
+//
+// Per tile and GVP g (A = TMEM region holding the scalar operand, D = the other region; they swap every GVP):
+//   V_g : Vh|Vu[128 x 32] (x3 components) = V[128 x 16] . [Wh | Wh.Wu]     A from smem (staging), B resident
+//   S_g : D[128 x 128] = [f | rbf | sh][128 x K] . Wf^T                    A from TMEM (f) + smem (rbf, sh),
+//                                                                           B streamed through a 12-slab ring
+//   G_g : gate[128 x 16] = f'[128 x 128] . Wg^T                            A from TMEM, B resident
+// with CUDA-core stages between them: EPI-A (vector norms -> sh), EPI-B (bias + SiLU, re-split in place into the
+// next A operand), EPI-C (sigmoid gate * Vu -> next vector operand).  One thread owns one edge row (= TMEM lane).
+//
+// Warp roles (320 threads): warps 0-3 epilogue of slot 0, warps 4-7 epilogue of slot 1, warp 8 lane 0 issues every
+// MMA (polling scheduler over the two slots), warp 9 lane 0 streams weight slabs with cp.async.bulk.
+#include "pf_common.cuh"
+#include "pf_tc.cuh"
+
+namespace pf {
+namespace tcc {
+
+constexpr int kRows = PF_TC_TILE_ROWS;  // 128
+constexpr int kRing = 12;               // weight slabs resident in shared memory
+constexpr int kSlab = 8192;             // one K=16 slab of Wf^T [128 x 16]: hi image 4 KB | lo image 4 KB
+constexpr int kSlabs0 = 11;             // GVP 0: K = 128 h + 16 rbf + 17 sh (+15 zero) = 176
+constexpr int kSlabs1 = 9;              // GVP 1, 2: K = 128 f + 16 sh = 144
+constexpr int kSlabsPerTile = kSlabs0 + 2 * kSlabs1;  // 29
+// packed weight blob (pharmacoforge_b200/weights.py: pack_message_tc)
+constexpr int kBlobSmallOff = kSlabsPerTile * kSlab;  // 237,568
+constexpr int kSmallBytes = 32768;                    // gate images 3 x 8 KB | vector images 3 x 2 KB | fp32 consts 2 KB
+constexpr int kGateOff = 0;
+constexpr int kVecOff = 24576;
+constexpr int kConstOff = 30720;
+constexpr int kBlobBytes = kBlobSmallOff + kSmallBytes;  // 270,336
+// fp32 constants (floats): per GVP g at 144 g: bf[128] | bg[16]; then GVP 0 extras
+constexpr int kCWh0 = 432;    // Wh0[0][h], h = 0..16  (x_diff row)
+constexpr int kCWhu0 = 452;   // (Wh0.Wu0)[0][u], u = 0..15
+constexpr int kCWhc16 = 468;  // Wh0[1+u][16], u = 0..15 (17th hidden channel)
+
+constexpr int kStage = 27648;  // per-slot staging: smem A operands (3 x 8 KB) / transpose buffers / mean buffer
+constexpr int kMetaInts = 544;
+constexpr int kOffRing = 0;
+constexpr int kOffSmall = kRing * kSlab;              // 98,304
+constexpr int kOffStage = kOffSmall + kSmallBytes;    // 131,072
+constexpr int kOffMeta = kOffStage + 2 * kStage;      // 186,368
+constexpr int kOffBars = kOffMeta + 2 * kMetaInts * 4;  // 190,720
+constexpr int kNumBars = 3 * kRing + 12 + 1;
+constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
+constexpr int kThreadsTc = 320;
+
+struct SlotBars {
+  uint64_t vecA, vecD, A, D, F, gate;
+};
+
+struct Params {
+  const float *src_h, *src_v, *src_x, *dst_x;
+  const int *seg_start, *seg_cnt, *seg_dst, *col, *tiles, *n_tiles;
+  const uint8_t* wblob;
+  float *agg_h, *agg_v;
+  int accumulate;
+};
+
+__device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
+__device__ __forceinline__ float sigmoid_fast(float y) { return __fdividef(1.0f, 1.0f + __expf(-y)); }
+
+// 16 fp32 values of row m -> bf16 (hi, lo) in the K-major SWIZZLE_NONE image of a [128 x 16] A operand:
+// byte (k/8)*2048 + (m/8)*128 + (m%8)*16 + (k%8)*2, hi image at +0, lo image at +4096.
+__device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float* x) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tc::split_pack(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+  uint8_t* a = slab + (m >> 3) * 128 + (m & 7) * 16;
+  *reinterpret_cast<uint4*>(a) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(a + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  *reinterpret_cast<uint4*>(a + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<uint4*>(a + 6144) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+__device__ __forceinline__ void slot_barrier(int T) { tc::named_bar_sync(1 + T, 128); }
+
+// ------------------------------------------------------------------------------------------------ producer
+__device__ void producer_role(const Params& p, uint8_t* smem, uint64_t* bar_full, uint64_t* bar_empty,
+                              uint64_t* bar_small, int my_tiles) {
+  if (my_tiles == 0) return;
+  tc::mbar_expect_tx(bar_small, kSmallBytes);
+#pragma unroll
+  for (int i = 0; i < kSmallBytes / 8192; ++i)
+    tc::bulk_g2s(smem + kOffSmall + i * 8192, p.wblob + kBlobSmallOff + i * 8192, 8192, bar_small);
+  const int total = ((my_tiles + 1) >> 1) * kSlabsPerTile;
+  for (int n = 0; n < total; ++n) {
+    const int slot = n % kRing;
+    if (n >= kRing) {  // the previous occupant of this ring slot must have been consumed by both tile slots
+      const int o = n - kRing;
+      const uint32_t par = (uint32_t)(o / kRing) & 1u;
+      tc::mbar_wait(&bar_empty[slot], par);
+      if (2 * (o / kSlabsPerTile) + 1 < my_tiles) tc::mbar_wait(&bar_empty[kRing + slot], par);
+    }
+    tc::mbar_expect_tx(&bar_full[slot], kSlab);
+    tc::bulk_g2s(smem + kOffRing + slot * kSlab, p.wblob + (size_t)(n % kSlabsPerTile) * kSlab, kSlab, &bar_full[slot]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MMA issuer
+template <bool HAS_V>
+__device__ void mma_role(uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint64_t* bar_empty, SlotBars* sb,
+                         uint64_t* bar_small, int my_tiles) {
+  if (my_tiles == 0) return;
+  constexpr uint32_t kI128 = tc::make_idesc_bf16(128, 128);
+  constexpr uint32_t kI32 = tc::make_idesc_bf16(128, 32);
+  constexpr uint32_t kI16 = tc::make_idesc_bf16(128, 16);
+  const uint32_t ring_a = tc::smem_u32(smem + kOffRing);
+  const uint32_t small_a = tc::smem_u32(smem + kOffSmall);
+  const uint32_t stage_a = tc::smem_u32(smem + kOffStage);
+  struct St {
+    int tiles_left, g, phase, k, a_ok;
+    uint32_t p_vecA, p_A, p_F, q;
+  } st[2];
+#pragma unroll
+  for (int T = 0; T < 2; ++T) {
+    st[T].tiles_left = (my_tiles + 1 - T) >> 1;
+    st[T].g = 0;
+    st[T].phase = HAS_V ? 0 : 1;
+    st[T].k = 0;
+    st[T].a_ok = 0;
+    st[T].p_vecA = st[T].p_A = st[T].p_F = 0;
+    st[T].q = 0;
+  }
+  tc::mbar_wait(bar_small, 0);
+  while (st[0].tiles_left > 0 || st[1].tiles_left > 0) {
+#pragma unroll
+    for (int T = 0; T < 2; ++T) {
+      St& s = st[T];
+      if (s.tiles_left == 0) continue;
+      const uint32_t regP = tmem + 256 * T, regQ = regP + 128;
+      const uint32_t Areg = s.g == 1 ? regQ : regP;
+      const uint32_t Dreg = s.g == 1 ? regP : regQ;
+      const uint32_t stage = stage_a + T * kStage;
+      if (s.phase == 0) {  // ---- V_g: vector channels, A = staged V (hi, lo), B = [Wh | Wh.Wu] image
+        if (!tc::mbar_try(&sb[T].vecA, s.p_vecA)) continue;
+        s.p_vecA ^= 1;
+        tc::fence_after_sync();
+        const uint32_t bimg = small_a + kVecOff + s.g * 2048;
+        const uint64_t b_hi = tc::make_smem_desc(bimg, 512, 128), b_lo = tc::make_smem_desc(bimg + 1024, 512, 128);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint64_t a_hi = tc::make_smem_desc(stage + c * 8192, 2048, 128);
+          const uint64_t a_lo = tc::make_smem_desc(stage + c * 8192 + 4096, 2048, 128);
+          tc::mma_ss(Dreg + 32 * c, a_hi, b_hi, kI32, 0);
+          tc::mma_ss(Dreg + 32 * c, a_hi, b_lo, kI32, 1);
+          tc::mma_ss(Dreg + 32 * c, a_lo, b_hi, kI32, 1);
+        }
+        tc::mma_commit(&sb[T].vecD);
+        s.phase = 1;
+        s.k = 0;
+        s.a_ok = 0;
+      } else if (s.phase == 1) {  // ---- S_g: scalar features, one weight slab (K = 16) at a time
+        if (!s.a_ok) {
+          if (!tc::mbar_try(&sb[T].A, s.p_A)) continue;
+          s.p_A ^= 1;
+          s.a_ok = 1;
+          tc::fence_after_sync();
+        }
+        const int nslab = s.g == 0 ? kSlabs0 : kSlabs1;
+        while (s.k < nslab) {
+          const int slot = s.q % kRing;
+          if (!tc::mbar_try(&bar_full[slot], (s.q / kRing) & 1u)) break;
+          tc::fence_after_sync();
+          const uint32_t b = ring_a + slot * kSlab;
+          const uint64_t b_hi = tc::make_smem_desc(b, 2048, 128), b_lo = tc::make_smem_desc(b + 4096, 2048, 128);
+          if (s.k < 8) {
+            const uint32_t a_hi = Areg + 32 * (s.k >> 1) + 8 * (s.k & 1), a_lo = a_hi + 16;
+            tc::mma_ts(Dreg, a_hi, b_hi, kI128, s.k > 0);
+            tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
+            tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
+          } else {
+            const uint32_t a = stage + (s.k - 8) * 8192;
+            const uint64_t a_hi = tc::make_smem_desc(a, 2048, 128), a_lo = tc::make_smem_desc(a + 4096, 2048, 128);
+            tc::mma_ss(Dreg, a_hi, b_hi, kI128, 1);
+            tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
+            tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
+          }
+          tc::mma_commit(&bar_empty[T * kRing + slot]);
+          ++s.k;
+          ++s.q;
+        }
+        if (s.k == nslab) {
+          tc::mma_commit(&sb[T].D);
+          s.phase = 2;
+        }
+      } else {  // ---- G_g: vector gates from the new scalars (now split in place in Dreg), output -> Areg[0:16)
+        if (!tc::mbar_try(&sb[T].F, s.p_F)) continue;
+        s.p_F ^= 1;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t bimg = small_a + kGateOff + s.g * 8192 + k * 1024;
+          const uint64_t b_hi = tc::make_smem_desc(bimg, 256, 128), b_lo = tc::make_smem_desc(bimg + 512, 256, 128);
+          const uint32_t a_hi = Dreg + 32 * (k >> 1) + 8 * (k & 1), a_lo = a_hi + 16;
+          tc::mma_ts(Areg, a_hi, b_hi, kI16, k > 0);
+          tc::mma_ts(Areg, a_hi, b_lo, kI16, 1);
+          tc::mma_ts(Areg, a_lo, b_hi, kI16, 1);
+        }
+        tc::mma_commit(&sb[T].gate);
+        s.k = 0;
+        s.a_ok = 0;
+        if (++s.g == 3) {
+          s.g = 0;
+          --s.tiles_left;
+          s.phase = HAS_V ? 0 : 1;
+        } else {
+          s.phase = 0;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue warps
+template <bool HAS_V>
+__device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
+                              uint64_t* bar_small, int my_tiles) {
+  const int et = threadIdx.x & 127;  // edge row of the tile == TMEM lane
+  const int ew = et >> 5, lane = et & 31;
+  const uint32_t P = tmem + 256 * T + ((uint32_t)(ew * 32) << 16), Q = P + 128;
+  uint8_t* stage = smem + kOffStage + T * kStage;
+  int* s_off = reinterpret_cast<int*>(smem + kOffMeta) + T * kMetaInts;  // [129]
+  int* s_start = s_off + 132;                                            // [128]
+  int* s_dst = s_start + 128;                                            // [128]
+  int* s_rowseg = s_dst + 128;                                           // [128]
+  int* s_wsum = s_rowseg + 128;                                          // [4]
+  const float* cst = reinterpret_cast<const float*>(smem + kOffSmall + kConstOff);
+  SlotBars& B = sb[T];
+  uint32_t par_vecD = 0, par_D = 0, par_gate = 0;
+  if (T < my_tiles) tc::mbar_wait(bar_small, 0);
+
+  for (int it = T; it < my_tiles; it += 2) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const int s0 = p.tiles[2 * tile], nseg = p.tiles[2 * tile + 1] - s0;
+    slot_barrier(T);  // everyone is done with the previous tile's metadata and staging
+    // ---- tile metadata: exclusive scan of the segment sizes (<= 128 segments)
+    {
+      int c = 0;
+      if (et < nseg) {
+        c = p.seg_cnt[s0 + et];
+        s_start[et] = p.seg_start[s0 + et];
+        s_dst[et] = p.seg_dst ? p.seg_dst[s0 + et] : s0 + et;
+      }
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) s_wsum[ew] = inc;
+      slot_barrier(T);
+      int base = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) base += w < ew ? s_wsum[w] : 0;
+      s_off[et] = base + inc - c;
+      if (et == 127) s_off[128] = base + inc;
+      slot_barrier(T);
+      if (et < nseg)
+        for (int r = s_off[et]; r < s_off[et + 1]; ++r) s_rowseg[r] = et;
+      slot_barrier(T);
+    }
+    const int nrows = s_off[nseg];
+    int src = -1;
+    float xd[3] = {0.f, 0.f, 0.f}, dist = 0.f;
+    if (et < nrows) {
+      const int j = s_rowseg[et];
+      src = __ldg(p.col + s_start[j] + (et - s_off[j]));
+      const int dst = s_dst[j];
+      const float dx = __ldg(p.src_x + (size_t)src * 3 + 0) - __ldg(p.dst_x + (size_t)dst * 3 + 0);
+      const float dy = __ldg(p.src_x + (size_t)src * 3 + 1) - __ldg(p.dst_x + (size_t)dst * 3 + 1);
+      const float dz = __ldg(p.src_x + (size_t)src * 3 + 2) - __ldg(p.dst_x + (size_t)dst * 3 + 2);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      dist = sqrtf(fmaxf(d2, 1e-8f)) + 1e-8f;
+      xd[0] = dx / dist;
+      xd[1] = dy / dist;
+      xd[2] = dz / dist;
+    }
+
+    // ---- gather h[src] (coalesced: 8 lanes x 16 B per row chunk), transpose through smem to one thread per row,
+    //      split into bf16 (hi, lo) and store as the TMEM A operand of S_0 in region P
+    {
+      float* tb = reinterpret_cast<float*>(stage + ew * 4608);  // [32][36]
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          const int sr = __shfl_sync(0xffffffffu, src, rr);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (sr >= 0) v = __ldg(reinterpret_cast<const float4*>(p.src_h + (size_t)sr * kHidden + 32 * c) + (lane & 7));
+          *reinterpret_cast<float4*>(tb + rr * 36 + 4 * (lane & 7)) = v;
+        }
+        __syncwarp();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(tb + lane * 36 + 4 * j);
+          tc::split_pack(v.x, v.y, hi[2 * j], lo[2 * j]);
+          tc::split_pack(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        __syncwarp();
+        tc::tmem_st16(P + 32 * c, hi);
+        tc::tmem_st16(P + 32 * c + 16, lo);
+      }
+    }
+    if constexpr (!HAS_V) slot_barrier(T);  // the staging writes below overlap other warps' transpose buffers
+
+    float Vu[48];
+    float vh16[3] = {0.f, 0.f, 0.f};
+    if constexpr (HAS_V) {
+      // ---- gather v[src] ([3][16] component-major rows of 192 B) the same way and stage it for V_0
+      slot_barrier(T);
+      float* tv = reinterpret_cast<float*>(stage + ew * 6656);  // [32][52]
+#pragma unroll
+      for (int ps = 0; ps < 12; ++ps) {
+        const int q = 32 * ps + lane;
+        const int rr = q / 12, pc = q - 12 * rr;
+        const int sr = __shfl_sync(0xffffffffu, src, rr);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sr >= 0) v = __ldg(reinterpret_cast<const float4*>(p.src_v + (size_t)sr * kVRow) + pc);
+        *reinterpret_cast<float4*>(tv + rr * 52 + 4 * pc) = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(tv + lane * 52 + 4 * j);
+        Vu[4 * j] = v.x;
+        Vu[4 * j + 1] = v.y;
+        Vu[4 * j + 2] = v.z;
+        Vu[4 * j + 3] = v.w;
+      }
+      slot_barrier(T);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float a = xd[c] * cst[kCWh0 + 16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) a = fmaf(Vu[16 * c + u], cst[kCWhc16 + u], a);
+        vh16[c] = a;
+        stage_store16(stage + c * 8192, et, &Vu[16 * c]);
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&B.vecA);
+    }
+
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+      const uint32_t Areg = g == 1 ? Q : P, Dreg = g == 1 ? P : Q;
+      // ================= EPI-A: hidden vector channels -> norms sh (scalar operand tail), Vu kept in registers
+      {
+        float sh[16];
+        float sh16 = 0.f;
+        if (g == 0 && !HAS_V) {
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const float w = cst[kCWh0 + h];
+            const float a0 = xd[0] * w, a1 = xd[1] * w, a2 = xd[2] * w;
+            sh[h] = sqrtf(fmaxf(a0 * a0 + a1 * a1 + a2 * a2, 1e-8f));
+          }
+          {
+            const float w = cst[kCWh0 + 16];
+            const float a0 = xd[0] * w, a1 = xd[1] * w, a2 = xd[2] * w;
+            sh16 = sqrtf(fmaxf(a0 * a0 + a1 * a1 + a2 * a2, 1e-8f));
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int u = 0; u < 16; ++u) Vu[16 * c + u] = xd[c] * cst[kCWhu0 + u];
+        } else {
+          tc::mbar_wait(&B.vecD, par_vecD);
+          par_vecD ^= 1;
+          tc::fence_after_sync();
+#pragma unroll
+          for (int h = 0; h < 16; ++h) sh[h] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            uint32_t r[32];
+            tc::tmem_ld32(Dreg + 32 * c, r);
+            tc::wait_ld();
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+              float vh = __uint_as_float(r[h]);
+              if (g == 0) vh = fmaf(xd[c], cst[kCWh0 + h], vh);
+              sh[h] = fmaf(vh, vh, sh[h]);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              float vu = __uint_as_float(r[16 + u]);
+              if (g == 0) vu = fmaf(xd[c], cst[kCWhu0 + u], vu);
+              Vu[16 * c + u] = vu;
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 16; ++h) sh[h] = sqrtf(fmaxf(sh[h], 1e-8f));
+          if (g == 0) sh16 = sqrtf(fmaxf(vh16[0] * vh16[0] + vh16[1] * vh16[1] + vh16[2] * vh16[2], 1e-8f));
+        }
+        if (g == 0) {
+          float t16[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float z = (dist - (float)k) / 0.9375f;
+            t16[k] = __expf(-(z * z));
+          }
+          stage_store16(stage, et, t16);
+          stage_store16(stage + 8192, et, sh);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) t16[k] = 0.f;
+          t16[0] = sh16;
+          stage_store16(stage + 16384, et, t16);
+        } else {
+          stage_store16(stage, et, sh);
+        }
+        tc::fence_proxy_async();
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&B.A);
+      }
+
+      // ================= EPI-B: f = SiLU(D + b), split in place into the next A operand; last GVP: mean of f
+      {
+        tc::mbar_wait(&B.D, par_D);
+        par_D ^= 1;
+        tc::fence_after_sync();
+        const float* bf = cst + 144 * g;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          uint32_t r[32];
+          tc::tmem_ld32(Dreg + 32 * j, r);
+          tc::wait_ld();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float f0 = silu_fast(__uint_as_float(r[2 * i]) + bf[32 * j + 2 * i]);
+            const float f1 = silu_fast(__uint_as_float(r[2 * i + 1]) + bf[32 * j + 2 * i + 1]);
+            r[2 * i] = __float_as_uint(f0);
+            r[2 * i + 1] = __float_as_uint(f1);
+            tc::split_pack(f0, f1, hi[i], lo[i]);
+          }
+          tc::tmem_st16(Dreg + 32 * j, hi);
+          tc::tmem_st16(Dreg + 32 * j + 16, lo);
+          if (g == 2) {  // segmented mean of the scalar messages, 32 columns at a time through shared memory
+            float* ab = reinterpret_cast<float*>(stage);  // [128][33]
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ab[et * 33 + i] = __uint_as_float(r[i]);
+            slot_barrier(T);
+            for (int jj = ew; jj < nseg; jj += 4) {
+              const int r0 = s_off[jj], r1 = s_off[jj + 1], cnt = r1 - r0;
+              if (p.accumulate && cnt == 0) continue;
+              float acc = 0.f;
+              for (int rr = r0; rr < r1; ++rr) acc += ab[rr * 33 + lane];
+              acc = acc / (float)(cnt > 0 ? cnt : 1);
+              float* o = p.agg_h + (size_t)s_dst[jj] * kHidden + 32 * j + lane;
+              *o = p.accumulate ? *o + acc : acc;
+            }
+            slot_barrier(T);
+          }
+        }
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&B.F);
+      }
+
+      // ================= EPI-C: V_out = sigmoid(gate) * Vu -> next vector operand, or the vector message mean
+      {
+        tc::mbar_wait(&B.gate, par_gate);
+        par_gate ^= 1;
+        tc::fence_after_sync();
+        uint32_t r[16];
+        tc::tmem_ld16(Areg, r);
+        tc::wait_ld();
+        const float* bg = cst + 144 * g + 128;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float gt = sigmoid_fast(__uint_as_float(r[u]) + bg[u]);
+          Vu[u] *= gt;
+          Vu[16 + u] *= gt;
+          Vu[32 + u] *= gt;
+        }
+        if (g < 2) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) stage_store16(stage + c * 8192, et, &Vu[16 * c]);
+          tc::fence_proxy_async();
+          tc::fence_before_sync();
+          tc::mbar_arrive(&B.vecA);
+        } else {
+          tc::fence_before_sync();
+          float* ab = reinterpret_cast<float*>(stage);  // [128][49]
+#pragma unroll
+          for (int i = 0; i < 48; ++i) ab[et * 49 + i] = Vu[i];
+          slot_barrier(T);
+          for (int jj = ew; jj < nseg; jj += 4) {
+            const int r0 = s_off[jj], r1 = s_off[jj + 1], cnt = r1 - r0;
+            if (p.accumulate && cnt == 0) continue;
+            const float inv = (float)(cnt > 0 ? cnt : 1);
+            float* o = p.agg_v + (size_t)s_dst[jj] * kVRow;
+            for (int k = lane; k < kVRow; k += 32) {
+              float acc = 0.f;
+              for (int rr = r0; rr < r1; ++rr) acc += ab[rr * 49 + k];
+              acc = acc / inv;
+              o[k] = p.accumulate ? o[k] + acc : acc;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool HAS_V>
+__global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* bar_full = bars;             // [kRing]
+  uint64_t* bar_empty = bars + kRing;    // [2][kRing]
+  SlotBars* sb = reinterpret_cast<SlotBars*>(bars + 3 * kRing);  // [2]
+  uint64_t* bar_small = bars + 3 * kRing + 12;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = *p.n_tiles;
+  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 8) {
+    tc::tmem_alloc(s_tmem, 512);
+    if (lane == 0) {
+      for (int i = 0; i < kRing; ++i) {
+        tc::mbar_init(&bar_full[i], 1);
+        tc::mbar_init(&bar_empty[i], 1);
+        tc::mbar_init(&bar_empty[kRing + i], 1);
+      }
+      for (int T = 0; T < 2; ++T) {
+        tc::mbar_init(&sb[T].vecA, 128);
+        tc::mbar_init(&sb[T].vecD, 1);
+        tc::mbar_init(&sb[T].A, 128);
+        tc::mbar_init(&sb[T].D, 1);
+        tc::mbar_init(&sb[T].F, 128);
+        tc::mbar_init(&sb[T].gate, 1);
+      }
+      tc::mbar_init(bar_small, 1);
+      tc::fence_mbar_init();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 8) {
+    epilogue_role<HAS_V>(p, warp >> 2, smem, tmem, sb, bar_small, my_tiles);
+  } else if (warp == 8) {
+    if (lane == 0) mma_role<HAS_V>(smem, tmem, bar_full, bar_empty, sb, bar_small, my_tiles);
+  } else {
+    if (lane == 0) producer_role(p, smem, bar_full, bar_empty, bar_small, my_tiles);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tcc
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" size_t pf_tc_msg_blob_bytes(void) { return (size_t)tcc::kBlobBytes; }
+
+extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+                               const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
+                               const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
+                               const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream) {
+  PF_CHECK_ARG(src_h && src_x && dst_x && seg_start && seg_cnt && col && tiles && n_tiles && wblob && agg_h && agg_v,
+               "pf_edge_conv_tc: null pointer");
+  PF_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 15) == 0, "pf_edge_conv_tc: weight blob must be 16-byte aligned");
+  if (max_tiles <= 0) return PF_OK;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tcc::edge_conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tcc::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tcc::edge_conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               tcc::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("pf_edge_conv_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
+      return PF_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  tcc::Params p{src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
+                static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate};
+  const int grid = max_tiles < kNumSms ? max_tiles : kNumSms;
+  if (src_v != nullptr)
+    tcc::edge_conv_tc_kernel<true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  else
+    tcc::edge_conv_tc_kernel<false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  PF_CHECK_LAUNCH("pf_edge_conv_tc");
+  return PF_OK;
+}

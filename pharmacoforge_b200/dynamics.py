@@ -153,6 +153,14 @@ class _DeviceState:
                 a.w_msg[l][e] = w.ptr(f"msg{l}_{e}")
             for n in range(2):
                 a.w_upd[l][n] = w.ptr(f"upd{l}_{n}")
+        a.tile_rows = g.tile_rows
+        if g.tile_rows == 128:
+            if w.tc is None:
+                raise NotImplementedError("the tcgen05 message kernel is built for n_message_gvps=3 (configs/dev.yml); "
+                                          "build the batch with tile_rows=64 to use the fp32 FFMA kernels")
+            for l in range(dyn.n_convs):
+                for e in range(4):
+                    a.w_msg_tc[l][e] = w.tc_ptr(l, e)
         self.args = a
         self.weights = w          # keep alive
         self.batch_buffers = (g.prot_x, g.pharm_x, g.pharm_h)

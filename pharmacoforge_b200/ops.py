@@ -111,11 +111,11 @@ def dyn_graph(prot_x: torch.Tensor, prot_ptr: torch.Tensor, pharm_x: torch.Tenso
 
 
 @torch.library.custom_op(f"{NS}::plan_tiles", mutates_args=("tiles", "n_tiles", "status"))
-def plan_tiles(seg_cnt: torch.Tensor, chunk_ptr: torch.Tensor, skip_empty: bool, tiles: torch.Tensor,
+def plan_tiles(seg_cnt: torch.Tensor, chunk_ptr: torch.Tensor, skip_empty: bool, tile_rows: int, tiles: torch.Tensor,
                n_tiles: torch.Tensor, status: torch.Tensor) -> None:
     _lib.check(_L.pf_zero_i32(_i(n_tiles), 1, _s()), "pf_zero_i32")
-    _lib.check(_L.pf_plan_tiles(_i(seg_cnt), _i(chunk_ptr), chunk_ptr.numel() - 1, int(skip_empty), _i(tiles),
-                                tiles.numel() // 2, _i(n_tiles), _p(status), _s()), "pf_plan_tiles")
+    _lib.check(_L.pf_plan_tiles(_i(seg_cnt), _i(chunk_ptr), chunk_ptr.numel() - 1, int(skip_empty), tile_rows,
+                                _i(tiles), tiles.numel() // 2, _i(n_tiles), _p(status), _s()), "pf_plan_tiles")
 
 
 # ------------------------------------------------------------------------------------------------ compute
@@ -140,6 +140,19 @@ def edge_conv(src_h: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torch.T
     _lib.check(_L.pf_edge_conv(_f(src_h), _f(src_v), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt), _i(seg_dst),
                                _i(col), _i(tiles), _i(n_tiles), tiles.numel() // 2, _f(w), n_gvps, _f(agg_h),
                                _f(agg_v), int(accumulate), _s()), "pf_edge_conv")
+
+
+@torch.library.custom_op(f"{NS}::edge_conv_tc", mutates_args=("agg_h", "agg_v"))
+def edge_conv_tc(src_h: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torch.Tensor, dst_x: torch.Tensor,
+                 seg_start: torch.Tensor, seg_cnt: torch.Tensor, seg_dst: Optional[torch.Tensor], col: torch.Tensor,
+                 tiles: torch.Tensor, n_tiles: torch.Tensor, wblob: torch.Tensor, agg_h: torch.Tensor,
+                 agg_v: torch.Tensor, accumulate: bool) -> None:
+    """K3 on the tensor cores (tcgen05): tiles must be planned with tile_rows=128; wblob from pack_message_tc."""
+    if wblob.dtype != torch.uint8 or wblob.numel() != _L.pf_tc_msg_blob_bytes():
+        raise _lib.PfError("edge_conv_tc: wblob must be the uint8 image built by weights.pack_message_tc")
+    _lib.check(_L.pf_edge_conv_tc(_f(src_h), _f(src_v), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt), _i(seg_dst),
+                                  _i(col), _i(tiles), _i(n_tiles), tiles.numel() // 2, _p(wblob), _f(agg_h),
+                                  _f(agg_v), int(accumulate), _s()), "pf_edge_conv_tc")
 
 
 @torch.library.custom_op(f"{NS}::node_update", mutates_args=("h_out", "v_out"))

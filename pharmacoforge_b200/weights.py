@@ -102,6 +102,16 @@ class PackedWeights:
         self.flat = torch.cat(list(blocks.values())).to(device)
         self.offsets = offs
         self.n_convs = n_convs
+        # tcgen05 images of the message chains (only defined for the 3-GVP chain the kernel is built for)
+        self.tc = None
+        if n_msg == 3:
+            imgs = [pack_message_tc(sd, f"{np_}.conv_layers.{l}", key) for l in range(n_convs) for key in ETYPE_KEYS]
+            self.tc_stride = imgs[0].numel()
+            assert self.tc_stride % 256 == 0
+            self.tc = torch.cat(imgs).to(device)
+
+    def tc_ptr(self, conv: int, etype: int) -> int:
+        return self.tc.data_ptr() + (conv * len(ETYPE_KEYS) + etype) * self.tc_stride
 
     def ptr(self, key: str) -> int:
         return self.flat.data_ptr() + 4 * self.offsets[key]
@@ -128,3 +138,57 @@ def umma_b_image(w: torch.Tensor) -> torch.Tensor:
     n, k = w.shape
     assert n % 8 == 0 and k % 8 == 0 and w.dtype == torch.bfloat16
     return w.reshape(n // 8, 8, k // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
+
+
+# --- K3 on the tensor cores: one byte image per (conv layer, edge type); layout constants mirror csrc/pf_tc_conv.cu
+TC_SLAB_BYTES = 8192
+TC_SLABS = (11, 9, 9)
+TC_SMALL_OFF = sum(TC_SLABS) * TC_SLAB_BYTES
+TC_GATE_OFF, TC_VEC_OFF, TC_CONST_OFF, TC_SMALL_BYTES = 0, 24576, 30720, 32768
+TC_C_WH0, TC_C_WHU0, TC_C_WHC16 = 432, 452, 468
+
+
+def _bytes(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous().view(torch.uint8).reshape(-1)
+
+
+def _hi_lo_images(w: torch.Tensor) -> torch.Tensor:
+    """[N, 16] fp32 K-slab -> bytes of (hi image | lo image)."""
+    hi, lo = split_bf16(w)
+    return torch.cat([_bytes(umma_b_image(hi)), _bytes(umma_b_image(lo))])
+
+
+def pack_message_tc(sd: Dict[str, torch.Tensor], conv_p: str, etype_key: str) -> torch.Tensor:
+    """The 3-GVP message chain of one edge type (gvp.py:392-415) as the uint8 image pf_edge_conv_tc streams:
+    29 Wf^T K-slabs (bf16 hi | lo, UMMA SWIZZLE_NONE K-major) | gate images | [Wh | Wh.Wu] images | fp32 constants."""
+    slabs, gates, vecs = [], [], []
+    consts = torch.zeros((TC_SMALL_BYTES - TC_CONST_OFF) // 4, dtype=torch.float32)
+    for g in range(3):
+        q = f"{conv_p}.edge_message_fns.{etype_key}.{g}"
+        Wh = sd[q + ".Wh"].detach().double().cpu()
+        Wu = sd[q + ".Wu"].detach().double().cpu()
+        Wf = sd[q + ".to_feats_out.0.weight"].detach().float().cpu()
+        bf = sd[q + ".to_feats_out.0.bias"].detach().float().cpu()
+        Wg = sd[q + ".scalar_to_vector_gates.weight"].detach().float().cpu()
+        bg = sd[q + ".scalar_to_vector_gates.bias"].detach().float().cpu()
+        vi, vh = Wh.shape
+        assert Wf.shape == (128, 128 + (16 if g == 0 else 0) + vh) and Wg.shape == (16, 128) and Wu.shape == (vh, 16)
+        assert (vi, vh) == ((17, 17) if g == 0 else (16, 16))
+        K = 16 * TC_SLABS[g]
+        Wp = torch.zeros(128, K)
+        Wp[:, :Wf.shape[1]] = Wf
+        slabs += [_hi_lo_images(Wp[:, 16 * s:16 * s + 16]) for s in range(TC_SLABS[g])]
+        gates += [_hi_lo_images(Wg[:, 16 * s:16 * s + 16]) for s in range(8)]
+        Whu = Wh @ Wu                                        # [vi, 16], composed in float64
+        k0 = 1 if g == 0 else 0                              # GVP 0: row 0 is the x_diff channel (CUDA cores)
+        Bv = torch.cat([Wh[k0:k0 + 16, :16].t(), Whu[k0:k0 + 16, :].t()]).float()   # [32 (n), 16 (k)]
+        vecs.append(_hi_lo_images(Bv))
+        consts[144 * g:144 * g + 128] = bf
+        consts[144 * g + 128:144 * g + 144] = bg
+        if g == 0:
+            consts[TC_C_WH0:TC_C_WH0 + 17] = Wh[0, :].float()
+            consts[TC_C_WHU0:TC_C_WHU0 + 16] = Whu[0, :].float()
+            consts[TC_C_WHC16:TC_C_WHC16 + 16] = Wh[1:17, 16].float()
+    blob = torch.cat(slabs + gates + vecs + [_bytes(consts)])
+    assert blob.numel() == TC_SMALL_OFF + TC_SMALL_BYTES, blob.numel()
+    return blob

@@ -185,7 +185,7 @@ def test_encoders(env):
     close(got_p, env.O.encoder(env.sd, "dynamics.prot_encoder", b.prot_h, tt[b.prot_b]), what="prot enc")
 
 
-def _edge_conv_case(env, etype_idx, layer, with_vectors):
+def _edge_conv_case(env, etype_idx, layer, with_vectors, impl="tc"):
     O, ops = env.O, env.ops
     g, b = env.build([(150, 3), (90, 4)], [[3, 5, 8], [6, 4]])
     x, h, prot = random_state(b, 21)
@@ -213,14 +213,21 @@ def _edge_conv_case(env, etype_idx, layer, with_vectors):
     tiles = torch.zeros(2 * (g.n_prot + g.dyn_max_tiles), dtype=torch.int32, device=env.dev)
     n_tiles = torch.zeros(1, dtype=torch.int32, device=env.dev)
     accumulate = et in ("pf", "fp")
-    ops.plan_tiles(seg[1], seg[4], accumulate, tiles, n_tiles, g.status)
+    ops.plan_tiles(seg[1], seg[4], accumulate, 128 if impl == "tc" else 64, tiles, n_tiles, g.status)
     base_h = torch.randn(n_dst, 128, generator=gen) if accumulate else torch.full((n_dst, 128), float("nan"))
     base_v = torch.randn(n_dst, 48, generator=gen) if accumulate else torch.full((n_dst, 48), float("nan"))
     agg_h, agg_v = base_h.cuda(), base_v.cuda()
     src_v = to_cm(feats[snt][2]).cuda() if with_vectors else None
-    ops.edge_conv(feats[snt][0].cuda(), src_v, feats[snt][1].cuda().contiguous(), feats[dnt][1].cuda().contiguous(),
-                  seg[0], seg[1], seg[2], seg[3], tiles, n_tiles, env.W.view(f"msg{layer}_{etype_idx}"), 3, agg_h,
-                  agg_v, accumulate)
+    if impl == "tc":
+        blob = env.W.tc[(layer * 4 + etype_idx) * env.W.tc_stride:(layer * 4 + etype_idx + 1) * env.W.tc_stride]
+        ops.edge_conv_tc(feats[snt][0].cuda(), src_v, feats[snt][1].cuda().contiguous(),
+                         feats[dnt][1].cuda().contiguous(), seg[0], seg[1], seg[2], seg[3], tiles, n_tiles, blob, agg_h,
+                         agg_v, accumulate)
+    else:
+        ops.edge_conv(feats[snt][0].cuda(), src_v, feats[snt][1].cuda().contiguous(),
+                      feats[dnt][1].cuda().contiguous(), seg[0], seg[1], seg[2], seg[3], tiles, n_tiles,
+                      env.W.view(f"msg{layer}_{etype_idx}"), 3, agg_h, agg_v, accumulate)
+    torch.cuda.synchronize()
     g.check_status()
     if accumulate:
         want_h, want_v = base_h + want_h, base_v + to_cm(want_v)
@@ -230,10 +237,11 @@ def _edge_conv_case(env, etype_idx, layer, with_vectors):
     close(agg_v, want_v, what=f"{et} vectors")
 
 
+@pytest.mark.parametrize("impl", ["tc", "ffma"])
 @pytest.mark.parametrize("etype_idx", [0, 1, 2, 3])
 @pytest.mark.parametrize("with_vectors", [False, True])
-def test_edge_conv_each_etype(env, etype_idx, with_vectors):
-    _edge_conv_case(env, etype_idx, 1 if with_vectors else 0, with_vectors)
+def test_edge_conv_each_etype(env, etype_idx, with_vectors, impl):
+    _edge_conv_case(env, etype_idx, 1 if with_vectors else 0, with_vectors, impl)
 
 
 def test_node_update(env):

@@ -131,3 +131,40 @@ def test_synthetic_pocket_properties():
     pos2, _ = make_pocket(400, seed=0)
     assert np.array_equal(pos, pos2)
     assert readme_sizes(30) == [3, 4, 5, 6, 7, 8] * 5
+
+
+def test_tc_message_blob_layout(sd):
+    """pack_message_tc: the UMMA K-slab images decode back to the reference weights (hi + lo), constants in place."""
+    import torch
+    from pharmacoforge_b200 import _lib, weights as W
+    cp = "dynamics.noise_predictor.conv_layers.1"
+    blob = W.pack_message_tc(sd, cp, "prot_pp_prot")
+    assert blob.dtype == torch.uint8 and blob.numel() == _lib.load().pf_tc_msg_blob_bytes()
+
+    def decode(img_bytes, n):      # inverse of umma_b_image for one [n, 16] K-slab
+        return img_bytes.view(torch.bfloat16).reshape(2, n // 8, 8, 8).permute(1, 2, 0, 3).reshape(n, 16).float()
+
+    off = 0
+    for g, nslab in enumerate(W.TC_SLABS):
+        Wf = sd[f"{cp}.edge_message_fns.prot_pp_prot.{g}.to_feats_out.0.weight"].float()
+        rec = torch.zeros(128, 16 * nslab)
+        for s_ in range(nslab):
+            hi = decode(blob[off:off + 4096], 128)
+            lo = decode(blob[off + 4096:off + 8192], 128)
+            rec[:, 16 * s_:16 * s_ + 16] = hi + lo
+            off += 8192
+        k = Wf.shape[1]
+        assert torch.allclose(rec[:, :k], Wf, rtol=2 ** -15, atol=1e-9) and float(rec[:, k:].abs().max() if k < rec.shape[1] else 0) == 0
+    assert off == W.TC_SMALL_OFF
+    consts = blob[W.TC_SMALL_OFF + W.TC_CONST_OFF:].view(torch.float32)
+    q = f"{cp}.edge_message_fns.prot_pp_prot"
+    assert torch.equal(consts[144:272], sd[q + ".1.to_feats_out.0.bias"].float())
+    assert torch.equal(consts[W.TC_C_WH0:W.TC_C_WH0 + 17], sd[q + ".0.Wh"][0].float())
+    Whu = (sd[q + ".0.Wh"].double() @ sd[q + ".0.Wu"].double()).float()
+    assert torch.equal(consts[W.TC_C_WHU0:W.TC_C_WHU0 + 16], Whu[0])
+    # vector image of GVP 1: rows 0..15 = Wh^T, rows 16..31 = (Wh.Wu)^T
+    v1 = blob[W.TC_SMALL_OFF + W.TC_VEC_OFF + 2048:W.TC_SMALL_OFF + W.TC_VEC_OFF + 4096]
+    rec = decode(v1[:1024], 32) + decode(v1[1024:], 32)
+    Wh1, Wu1 = sd[q + ".1.Wh"].double(), sd[q + ".1.Wu"].double()
+    want = torch.cat([Wh1.t(), (Wh1 @ Wu1).t()]).float()
+    assert torch.allclose(rec, want, rtol=2 ** -15, atol=1e-9)
