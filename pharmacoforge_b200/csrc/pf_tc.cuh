@@ -11,6 +11,7 @@
 //        (k/8)*LBO + (n/8)*128 + (n%8)*16 + (k%8)*2 with LBO = (N/8)*128, SBO = 128.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace pf {
@@ -75,6 +76,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
       : "r"(addr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -96,6 +103,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// kind::f16, A = B = fp16 (K-major), D = fp32, M x N
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 // D[tmem] (+)= A[tmem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                        uint32_t accumulate) {
@@ -112,6 +123,21 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// ---------------------------------------------------------------- fp32 -> (hi, lo) fp16 split, packed pairs
+// x ~= hi + lo with |x - hi - lo| <= max(2^-22 |x|, 2^-25): 11 + 11 significand bits; lo is subnormal for
+// |x| < 2^-3 (absolute spacing 2^-24).  Conversions saturate: |x| > 65504 (never reached by LayerNorm / SiLU /
+// sigmoid outputs) degrades to a finite value instead of inf - inf = NaN.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float x0, float x1) {  // {low half: x0, high half: x1}, saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+__device__ __forceinline__ void split_pack_h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16x2_sat(x0, x1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16x2_sat(x0 - hf.x, x1 - hf.y);
 }
 
 // ---------------------------------------------------------------- fp32 -> (hi, lo) bf16 split, packed pairs
@@ -132,6 +158,20 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread; the MMA scheduler must never sleep on one tile slot)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)

@@ -125,9 +125,19 @@ class PackedWeights:
 
 # ------------------------------------------------------------------------------------------------ tcgen05 operands
 def split_bf16(w: torch.Tensor):
-    """w ~= hi + lo with both parts bf16 (round to nearest even), as the kernels split activations on the fly."""
+    """w ~= hi + lo with both parts bf16 (round to nearest even); 16 significand bits (tcgen05 self-test only)."""
     hi = w.float().to(torch.bfloat16)
     lo = (w.float() - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def split_f16(w: torch.Tensor):
+    """w ~= hi + lo with both parts fp16 (round to nearest even), as the kernels split activations on the fly:
+    22 significand bits.  Weights beyond the fp16 range cannot be represented and are rejected."""
+    if float(w.abs().max()) > 65000.0:
+        raise ValueError("weight magnitude exceeds the fp16 range of the tcgen05 operand split")
+    hi = w.float().to(torch.float16)
+    lo = (w.float() - hi.float()).to(torch.float16)
     return hi, lo
 
 
@@ -136,7 +146,7 @@ def umma_b_image(w: torch.Tensor) -> torch.Tensor:
     8x8 core matrices of 128 contiguous bytes, element (n, k) at (k/8)*(N/8)*64 + (n/8)*64 + (n%8)*8 + k%8 (in
     bf16 units).  See csrc/pf_tc.cuh."""
     n, k = w.shape
-    assert n % 8 == 0 and k % 8 == 0 and w.dtype == torch.bfloat16
+    assert n % 8 == 0 and k % 8 == 0 and w.dtype in (torch.bfloat16, torch.float16)
     return w.reshape(n // 8, 8, k // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
 
 
@@ -154,13 +164,13 @@ def _bytes(t: torch.Tensor) -> torch.Tensor:
 
 def _hi_lo_images(w: torch.Tensor) -> torch.Tensor:
     """[N, 16] fp32 K-slab -> bytes of (hi image | lo image)."""
-    hi, lo = split_bf16(w)
+    hi, lo = split_f16(w)
     return torch.cat([_bytes(umma_b_image(hi)), _bytes(umma_b_image(lo))])
 
 
 def pack_message_tc(sd: Dict[str, torch.Tensor], conv_p: str, etype_key: str) -> torch.Tensor:
     """The 3-GVP message chain of one edge type (gvp.py:392-415) as the uint8 image pf_edge_conv_tc streams:
-    29 Wf^T K-slabs (bf16 hi | lo, UMMA SWIZZLE_NONE K-major) | gate images | [Wh | Wh.Wu] images | fp32 constants."""
+    29 Wf^T K-slabs (fp16 hi | lo, UMMA SWIZZLE_NONE K-major) | gate images | [Wh | Wh.Wu] images | fp32 constants."""
     slabs, gates, vecs = [], [], []
     consts = torch.zeros((TC_SMALL_BYTES - TC_CONST_OFF) // 4, dtype=torch.float32)
     for g in range(3):

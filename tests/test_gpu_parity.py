@@ -459,6 +459,8 @@ def test_degree_overflow_is_reported(env):
     onehot = np.zeros((80, 11), dtype=np.float32)
     onehot[:, 0] = 1
     from pharmacoforge_b200._lib import PfError
-    g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev)
-    with pytest.raises(PfError):
+    g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev, tile_rows=64)
+    with pytest.raises(PfError):     # 79 in-edges do not fit a 64-row tile of the FFMA kernels
         g.check_status()
+    g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev, tile_rows=128)
+    g.check_status()                 # max_num_neighbors=100 always fits the 128-row tcgen05 tile

@@ -142,7 +142,7 @@ def test_tc_message_blob_layout(sd):
     assert blob.dtype == torch.uint8 and blob.numel() == _lib.load().pf_tc_msg_blob_bytes()
 
     def decode(img_bytes, n):      # inverse of umma_b_image for one [n, 16] K-slab
-        return img_bytes.view(torch.bfloat16).reshape(2, n // 8, 8, 8).permute(1, 2, 0, 3).reshape(n, 16).float()
+        return img_bytes.view(torch.float16).reshape(2, n // 8, 8, 8).permute(1, 2, 0, 3).reshape(n, 16).float()
 
     off = 0
     for g, nslab in enumerate(W.TC_SLABS):
@@ -154,7 +154,7 @@ def test_tc_message_blob_layout(sd):
             rec[:, 16 * s_:16 * s_ + 16] = hi + lo
             off += 8192
         k = Wf.shape[1]
-        assert torch.allclose(rec[:, :k], Wf, rtol=2 ** -15, atol=1e-9) and float(rec[:, k:].abs().max() if k < rec.shape[1] else 0) == 0
+        assert torch.allclose(rec[:, :k], Wf, rtol=2 ** -21, atol=1e-7) and float(rec[:, k:].abs().max() if k < rec.shape[1] else 0) == 0
     assert off == W.TC_SMALL_OFF
     consts = blob[W.TC_SMALL_OFF + W.TC_CONST_OFF:].view(torch.float32)
     q = f"{cp}.edge_message_fns.prot_pp_prot"
@@ -167,4 +167,4 @@ def test_tc_message_blob_layout(sd):
     rec = decode(v1[:1024], 32) + decode(v1[1024:], 32)
     Wh1, Wu1 = sd[q + ".1.Wh"].double(), sd[q + ".1.Wu"].double()
     want = torch.cat([Wh1.t(), (Wh1 @ Wu1).t()]).float()
-    assert torch.allclose(rec, want, rtol=2 ** -15, atol=1e-9)
+    assert torch.allclose(rec, want, rtol=2 ** -21, atol=1e-7)
