@@ -140,6 +140,10 @@ int pf_edge_conv_tc(const float* src_h, const float* src_v, const float* src_x, 
                     const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const void* wblob, float* agg_h,
                     float* agg_v, int32_t accumulate, void* stream);
 
+/* Debug timeline of CTA 0 of the next pf_edge_conv_tc launches: device_buf = int64[4][4096][2] of (tag, clock64)
+ * for the epilogue of tile slot 0 / 1 and the two MMA issuers; NULL disarms.  Not used on the product path. */
+int pf_tc_trace(long long* device_buf);
+
 /* ---- K4: node update ------------------------------------------------------------------------------
  * gvp.py:511-532 in eval mode: (h,v) <- GVPLayerNorm_msg(h + agg_h, v + agg_v); (rh,rv) = GVP x n_gvps;
  * (h,v) <- GVPLayerNorm_upd(h + rh, v + rv).  v_in == NULL means zero.  In place is allowed

@@ -28,6 +28,7 @@ SIGNATURES = {
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
     "pf_tc_msg_blob_bytes": (C.c_size_t, []),
+    "pf_tc_trace": (C.c_int, [C.c_void_p]),
     "pf_edge_conv_tc": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                   C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, STREAM]),
     "pf_zero_i32": (C.c_int, [c_i32p, C.c_int64, STREAM]),

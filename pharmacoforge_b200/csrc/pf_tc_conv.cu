@@ -16,9 +16,9 @@
 // with CUDA-core stages between them: EPI-A (vector norms -> sh), EPI-B (bias + SiLU, re-split in place into the
 // next A operand), EPI-C (sigmoid gate * Vu -> next vector operand).  A TMEM lane is one edge row.
 //
-// Warp roles (576 threads): warps 0-7 epilogue of slot 0, warps 8-15 epilogue of slot 1 (two threads per edge row:
-// column halves), warp 16 lane 0 issues every MMA (non-blocking polling scheduler over the two slots), warp 17
-// lane 0 streams weight slabs with cp.async.bulk.
+// Warp roles (608 threads): warps 0-7 epilogue of slot 0, warps 8-15 epilogue of slot 1 (two threads per edge row:
+// column halves), warps 16 / 17 lane 0 issue the MMAs of slot 0 / 1, warp 18 lane 0 streams weight slabs with
+// cp.async.bulk.
 #include "pf_common.cuh"
 #include "pf_tc.cuh"
 
@@ -50,9 +50,9 @@ constexpr int kOffSmall = kRing * kSlab;              // 98,304
 constexpr int kOffStage = kOffSmall + kSmallBytes;    // 131,072
 constexpr int kOffMeta = kOffStage + 2 * kStage;      // 186,368
 constexpr int kOffBars = kOffMeta + 2 * kMetaInts * 4;  // 190,720
-constexpr int kNumBars = 3 * kRing + 12 + 1;
+constexpr int kNumBars = 3 * kRing + 12 + 2;
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
-constexpr int kThreadsTc = 576;  // 16 epilogue warps (2 slots x 2 column halves x 4 lane quarters) + MMA + producer
+constexpr int kThreadsTc = 608;  // 16 epilogue warps (2 slots x 2 column halves x 4 lane quarters) + 2 MMA + producer
 
 struct SlotBars {
   uint64_t vecA, vecD, A, D, F, gate;
@@ -64,6 +64,7 @@ struct Params {
   const uint8_t* wblob;
   float *agg_h, *agg_v;
   int accumulate;
+  long long* trace;  // optional timeline of CTA 0 (pf_tc_trace): [4 roles][kTraceCap][2] = (tag, clock64)
 };
 
 __device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
@@ -80,6 +81,15 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
   *reinterpret_cast<uint4*>(a + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
   *reinterpret_cast<uint4*>(a + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   *reinterpret_cast<uint4*>(a + 6144) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+constexpr int kTraceCap = 4096;
+__device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int tag) {
+  if (trace != nullptr && blockIdx.x == 0 && n < kTraceCap) {
+    trace[((size_t)role * kTraceCap + n) * 2] = tag;
+    trace[((size_t)role * kTraceCap + n) * 2 + 1] = clock64();
+    ++n;
+  }
 }
 
 __device__ __forceinline__ void slot_barrier(int T) { tc::named_bar_sync(1 + T, 256); }
@@ -107,45 +117,35 @@ __device__ void producer_role(const Params& p, uint8_t* smem, uint64_t* bar_full
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issuer
+// One issuing thread per tile slot (warps 16, 17): a slot's short jobs (V: 9 MMAs of N=32, G: 24 of N=16) are never
+// held back by the other slot's 27-33 N=128 MMAs being ISSUED, only by the few already queued in the tensor pipe.
 template <bool HAS_V>
-__device__ void mma_role(uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint64_t* bar_empty, SlotBars* sb,
-                         uint64_t* bar_small, int my_tiles) {
-  if (my_tiles == 0) return;
+__device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint64_t* bar_empty,
+                         SlotBars* sb, uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles, long long* trace) {
+  const int n_mine = (my_tiles + 1 - T) >> 1;
+  if (n_mine == 0) return;
+  int tn = 0;
   constexpr uint32_t kI128 = tc::make_idesc_f16(128, 128);
   constexpr uint32_t kI32 = tc::make_idesc_f16(128, 32);
   constexpr uint32_t kI16 = tc::make_idesc_f16(128, 16);
   const uint32_t ring_a = tc::smem_u32(smem + kOffRing);
   const uint32_t small_a = tc::smem_u32(smem + kOffSmall);
-  const uint32_t stage_a = tc::smem_u32(smem + kOffStage);
-  struct St {
-    int tiles_left, g, phase, k, a_ok;
-    uint32_t p_vecA, p_A, p_F, q;
-  } st[2];
-#pragma unroll
-  for (int T = 0; T < 2; ++T) {
-    st[T].tiles_left = (my_tiles + 1 - T) >> 1;
-    st[T].g = 0;
-    st[T].phase = HAS_V ? 0 : 1;
-    st[T].k = 0;
-    st[T].a_ok = 0;
-    st[T].p_vecA = st[T].p_A = st[T].p_F = 0;
-    st[T].q = 0;
-  }
+  const uint32_t stage = tc::smem_u32(smem + kOffStage) + T * kStage;
+  const uint32_t regP = tmem + 256 * T, regQ = regP + 128;
+  SlotBars& B = sb[T];
+  uint32_t p_vecA = 0, p_A = 0, p_F = 0, q = 0;
   tc::mbar_wait(bar_small, 0);
-  while (st[0].tiles_left > 0 || st[1].tiles_left > 0) {
-#pragma unroll
-    for (int T = 0; T < 2; ++T) {
-      St& s = st[T];
-      if (s.tiles_left == 0) continue;
-      const uint32_t regP = tmem + 256 * T, regQ = regP + 128;
-      const uint32_t Areg = s.g == 1 ? regQ : regP;
-      const uint32_t Dreg = s.g == 1 ? regP : regQ;
-      const uint32_t stage = stage_a + T * kStage;
-      if (s.phase == 0) {  // ---- V_g: vector channels, A = staged V (hi, lo), B = [Wh | Wh.Wu] image
-        if (!tc::mbar_test(&sb[T].vecA, s.p_vecA)) continue;
-        s.p_vecA ^= 1;
+  for (int t = 0; t < n_mine; ++t) {
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+      const uint32_t Areg = g == 1 ? regQ : regP;
+      const uint32_t Dreg = g == 1 ? regP : regQ;
+      if (HAS_V || g > 0) {  // ---- V_g: vector channels, A = staged V (hi, lo), B = [Wh | Wh.Wu] image
+        tc::mbar_wait(&B.vecA, p_vecA);
+        p_vecA ^= 1;
         tc::fence_after_sync();
-        const uint32_t bimg = small_a + kVecOff + s.g * 2048;
+        trace_ev(trace, 2 + T, tn, (g << 8) | 0x10);
+        const uint32_t bimg = small_a + kVecOff + g * 2048;
         const uint64_t b_hi = tc::make_smem_desc(bimg, 512, 128), b_lo = tc::make_smem_desc(bimg + 1024, 512, 128);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -155,68 +155,54 @@ __device__ void mma_role(uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint6
           tc::mma_ss(Dreg + 32 * c, a_hi, b_lo, kI32, 1);
           tc::mma_ss(Dreg + 32 * c, a_lo, b_hi, kI32, 1);
         }
-        tc::mma_commit(&sb[T].vecD);
-        s.phase = 1;
-        s.k = 0;
-        s.a_ok = 0;
-      } else if (s.phase == 1) {  // ---- S_g: scalar features, one weight slab (K = 16) at a time
-        if (!s.a_ok) {
-          if (!tc::mbar_test(&sb[T].A, s.p_A)) continue;
-          s.p_A ^= 1;
-          s.a_ok = 1;
-          tc::fence_after_sync();
-        }
-        const int nslab = s.g == 0 ? kSlabs0 : kSlabs1;
-        while (s.k < nslab) {
-          const int slot = s.q % kRing;
-          if (!tc::mbar_test(&bar_full[slot], (s.q / kRing) & 1u)) break;
-          tc::fence_after_sync();
-          const uint32_t b = ring_a + slot * kSlab;
-          const uint64_t b_hi = tc::make_smem_desc(b, 2048, 128), b_lo = tc::make_smem_desc(b + 4096, 2048, 128);
-          if (s.k < 8) {
-            const uint32_t a_hi = Areg + 16 * s.k, a_lo = a_hi + 8;
-            tc::mma_ts(Dreg, a_hi, b_hi, kI128, s.k > 0);
-            tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
-            tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
-          } else {
-            const uint32_t a = stage + (s.k - 8) * 8192;
-            const uint64_t a_hi = tc::make_smem_desc(a, 2048, 128), a_lo = tc::make_smem_desc(a + 4096, 2048, 128);
-            tc::mma_ss(Dreg, a_hi, b_hi, kI128, 1);
-            tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
-            tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
-          }
-          tc::mma_commit(&bar_empty[T * kRing + slot]);
-          ++s.k;
-          ++s.q;
-        }
-        if (s.k == nslab) {
-          tc::mma_commit(&sb[T].D);
-          s.phase = 2;
-        }
-      } else {  // ---- G_g: vector gates from the new scalars (now split in place in Dreg), output -> Areg[0:16)
-        if (!tc::mbar_test(&sb[T].F, s.p_F)) continue;
-        s.p_F ^= 1;
-        tc::fence_after_sync();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t bimg = small_a + kGateOff + s.g * 8192 + k * 1024;
-          const uint64_t b_hi = tc::make_smem_desc(bimg, 256, 128), b_lo = tc::make_smem_desc(bimg + 512, 256, 128);
-          const uint32_t a_hi = Dreg + 16 * k, a_lo = a_hi + 8;
-          tc::mma_ts(Areg, a_hi, b_hi, kI16, k > 0);
-          tc::mma_ts(Areg, a_hi, b_lo, kI16, 1);
-          tc::mma_ts(Areg, a_lo, b_hi, kI16, 1);
-        }
-        tc::mma_commit(&sb[T].gate);
-        s.k = 0;
-        s.a_ok = 0;
-        if (++s.g == 3) {
-          s.g = 0;
-          --s.tiles_left;
-          s.phase = HAS_V ? 0 : 1;
-        } else {
-          s.phase = 0;
-        }
+        tc::mma_commit(&B.vecD);
+        trace_ev(trace, 2 + T, tn, (g << 8) | 0x11);
       }
+      // ---- S_g: scalar features, one weight slab (K = 16) at a time
+      tc::mbar_wait(&B.A, p_A);
+      p_A ^= 1;
+      tc::fence_after_sync();
+      trace_ev(trace, 2 + T, tn, (g << 8) | 0x20);
+      const int nslab = g == 0 ? kSlabs0 : kSlabs1;
+      for (int k = 0; k < nslab; ++k, ++q) {
+        const uint32_t slot = q % kRing;
+        tc::mbar_wait(&bar_full[slot], (q / kRing) & 1u);
+        tc::fence_after_sync();
+        const uint32_t b = ring_a + slot * kSlab;
+        const uint64_t b_hi = tc::make_smem_desc(b, 2048, 128), b_lo = tc::make_smem_desc(b + 4096, 2048, 128);
+        if (k < 8) {
+          const uint32_t a_hi = Areg + 16 * k, a_lo = a_hi + 8;
+          tc::mma_ts(Dreg, a_hi, b_hi, kI128, k > 0);
+          tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
+          tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
+        } else {
+          const uint32_t a = stage + (k - 8) * 8192;
+          const uint64_t a_hi = tc::make_smem_desc(a, 2048, 128), a_lo = tc::make_smem_desc(a + 4096, 2048, 128);
+          tc::mma_ss(Dreg, a_hi, b_hi, kI128, 1);
+          tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
+          tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
+        }
+        tc::mma_commit(&bar_empty[T * kRing + slot]);
+      }
+      tc::mma_commit(&B.D);
+      if (T == 0 && t == 0 && g == 0) tc::mbar_arrive(bar_stagger);  // slot 1 starts half a phase behind slot 0
+      trace_ev(trace, 2 + T, tn, (g << 8) | 0x21);
+      // ---- G_g: vector gates from the new scalars (split in place in Dreg), output -> Areg[0:16)
+      tc::mbar_wait(&B.F, p_F);
+      p_F ^= 1;
+      tc::fence_after_sync();
+      trace_ev(trace, 2 + T, tn, (g << 8) | 0x30);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t bimg = small_a + kGateOff + g * 8192 + k * 1024;
+        const uint64_t b_hi = tc::make_smem_desc(bimg, 256, 128), b_lo = tc::make_smem_desc(bimg + 512, 256, 128);
+        const uint32_t a_hi = Dreg + 16 * k, a_lo = a_hi + 8;
+        tc::mma_ts(Areg, a_hi, b_hi, kI16, k > 0);
+        tc::mma_ts(Areg, a_hi, b_lo, kI16, 1);
+        tc::mma_ts(Areg, a_lo, b_hi, kI16, 1);
+      }
+      tc::mma_commit(&B.gate);
+      trace_ev(trace, 2 + T, tn, (g << 8) | 0x31);
     }
   }
 }
@@ -245,7 +231,7 @@ __device__ __forceinline__ void stage_store8(uint8_t* slab, int m, int kc, const
 // Two threads per edge row: half hh owns scalar columns [64 hh, 64 hh + 64) and vector channels [8 hh, 8 hh + 8).
 template <bool HAS_V>
 __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
-                              uint64_t* bar_small, int my_tiles) {
+                              uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
   const int stid = threadIdx.x & 255;
   const int hh = stid >> 7;          // column half
   const int et = stid & 127;         // edge row of the tile == TMEM lane
@@ -263,21 +249,60 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   SlotBars& B = sb[T];
   uint32_t par_vecD = 0, par_D = 0, par_gate = 0;
   if (T < my_tiles) tc::mbar_wait(bar_small, 0);
+  // ping-pong: slot 1 starts once slot 0's first scalar job is issued, so that one slot's CUDA-core stages run
+  // under the other slot's MMAs instead of both slots marching in lockstep
+  if (T == 1 && T < my_tiles) tc::mbar_wait(bar_stagger, 0);
+  long long* trace = stid == 0 ? p.trace : nullptr;
+  int tn = 0;
+
+  // Software prefetch of the tile descriptors: (first, end) segment of the slot's next-but-one tile and the segment
+  // records of its next tile are loaded one tile ahead, so the per-tile start-up does not wait on two dependent
+  // global round trips.
+  int pf_s0 = 0, pf_nseg = 0, pf_c = 0, pf_start = 0, pf_dst = 0, pf2_s0 = 0, pf2_s1 = 0;
+  auto load_segs = [&](int s0_, int nseg_) {
+    pf_c = 0;
+    if (hh == 0 && et < nseg_) {
+      pf_c = __ldg(p.seg_cnt + s0_ + et);
+      pf_start = __ldg(p.seg_start + s0_ + et);
+      pf_dst = p.seg_dst ? __ldg(p.seg_dst + s0_ + et) : s0_ + et;
+    }
+  };
+  if (T < my_tiles) {
+    const int tile = blockIdx.x + T * gridDim.x;
+    pf_s0 = __ldg(p.tiles + 2 * tile);
+    pf_nseg = __ldg(p.tiles + 2 * tile + 1) - pf_s0;
+    load_segs(pf_s0, pf_nseg);
+    if (T + 2 < my_tiles) {
+      const int tile2 = blockIdx.x + (T + 2) * gridDim.x;
+      pf2_s0 = __ldg(p.tiles + 2 * tile2);
+      pf2_s1 = __ldg(p.tiles + 2 * tile2 + 1);
+    }
+  }
 
   for (int it = T; it < my_tiles; it += 2) {
-    const int tile = blockIdx.x + it * gridDim.x;
-    const int s0 = p.tiles[2 * tile], nseg = p.tiles[2 * tile + 1] - s0;
+    const int s0 = pf_s0, nseg = pf_nseg;
+    const int cur_c = pf_c, cur_start = pf_start, cur_dst = pf_dst;
+    if (it + 2 < my_tiles) {  // prefetch for the next tile of this slot
+      pf_s0 = pf2_s0;
+      pf_nseg = pf2_s1 - pf2_s0;
+      load_segs(pf_s0, pf_nseg);
+      if (it + 4 < my_tiles) {
+        const int tile4 = blockIdx.x + (it + 4) * gridDim.x;
+        pf2_s0 = __ldg(p.tiles + 2 * tile4);
+        pf2_s1 = __ldg(p.tiles + 2 * tile4 + 1);
+      }
+    }
     slot_barrier(T);  // everyone is done with the previous tile's metadata and staging
+    trace_ev(trace, T, tn, 0x01);
     // ---- tile metadata (half 0): exclusive scan of the segment sizes (<= 128 segments)
     {
-      int c = 0, inc = 0;
+      const int c = cur_c;
+      int inc = c;
       if (hh == 0) {
         if (et < nseg) {
-          c = p.seg_cnt[s0 + et];
-          s_start[et] = p.seg_start[s0 + et];
-          s_dst[et] = p.seg_dst ? p.seg_dst[s0 + et] : s0 + et;
+          s_start[et] = cur_start;
+          s_dst[et] = cur_dst;
         }
-        inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -315,34 +340,42 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       xd[2] = dz / dist;
     }
 
+    trace_ev(trace, T, tn, 0x02);
     // ---- gather h[src] (coalesced: 8 lanes x 16 B per row chunk), transpose through smem to one thread per row,
     //      split into fp16 (hi, lo) and store as the TMEM A operand of S_0 in region P
     float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36] / [32][28]
-#pragma unroll 1
-    for (int c2 = 0; c2 < 2; ++c2) {
-      const int c = 2 * hh + c2;
+    {
+      float4 g4[2][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + (lane >> 3);
-        const int sr = __shfl_sync(0xffffffffu, src, rr);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sr >= 0) v = __ldg(reinterpret_cast<const float4*>(p.src_h + (size_t)sr * kHidden + 32 * c) + (lane & 7));
-        *reinterpret_cast<float4*>(tb + rr * 36 + 4 * (lane & 7)) = v;
-      }
-      __syncwarp();
+      for (int c2 = 0; c2 < 2; ++c2)
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {  // two K-steps of 16 columns: TMEM layout per K-step = hi (8 cols) | lo (8 cols)
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(tb + lane * 36 + 16 * ks + 4 * j);
-          tc::split_pack_h(v.x, v.y, hi[2 * j], lo[2 * j]);
-          tc::split_pack_h(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        for (int i = 0; i < 8; ++i) {
+          const int sr = __shfl_sync(0xffffffffu, src, 4 * i + (lane >> 3));
+          g4[c2][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (sr >= 0)
+            g4[c2][i] = __ldg(reinterpret_cast<const float4*>(p.src_h + (size_t)sr * kHidden + 32 * (2 * hh + c2)) + (lane & 7));
         }
-        tc::tmem_st8(P + 32 * c + 16 * ks, hi);
-        tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int c = 2 * hh + c2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(tb + (4 * i + (lane >> 3)) * 36 + 4 * (lane & 7)) = g4[c2][i];
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {  // two K-steps of 16 columns: TMEM layout per K-step = hi (8 cols) | lo (8 cols)
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(tb + lane * 36 + 16 * ks + 4 * j);
+            tc::split_pack_h(v.x, v.y, hi[2 * j], lo[2 * j]);
+            tc::split_pack_h(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+          }
+          tc::tmem_st8(P + 32 * c + 16 * ks, hi);
+          tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
 
     float Vu[24];                       // vector channels [8 hh, 8 hh + 8) of the 3 components, index 8 c + u'
@@ -381,6 +414,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       }
       s_xch[et * 2 + hh] = make_float4(pm, pv[0], pv[1], pv[2]);
     }
+    trace_ev(trace, T, tn, 0x03);
     slot_barrier(T);  // transposes done (the staging writes below overlap other warps' buffers); exchange visible
     if constexpr (HAS_V) {
       const float4 o = s_xch[et * 2 + (1 - hh)];
@@ -405,6 +439,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     for (int g = 0; g < 3; ++g) {
       const uint32_t Areg = g == 1 ? Q : P, Dreg = g == 1 ? P : Q;
       // ================= EPI-A: hidden vector channels -> norms sh (scalar operand tail), Vu kept in registers
+      trace_ev(trace, T, tn, (g << 8) | 0x10);
       {
         float sh[8];
         float sh16 = 0.f;
@@ -429,6 +464,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           tc::mbar_wait(&B.vecD, par_vecD);
           par_vecD ^= 1;
           tc::fence_after_sync();
+          trace_ev(trace, T, tn, (g << 8) | 0x11);
 #pragma unroll
           for (int h = 0; h < 8; ++h) sh[h] = 0.f;
 #pragma unroll
@@ -476,6 +512,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::wait_st();
         tc::fence_before_sync();
         tc::mbar_arrive(&B.A);
+        trace_ev(trace, T, tn, (g << 8) | 0x12);
       }
 
       // ================= EPI-B: f = SiLU(D + b), split in place into the next A operand; last GVP: mean of f
@@ -483,44 +520,69 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::mbar_wait(&B.D, par_D);
         par_D ^= 1;
         tc::fence_after_sync();
+        trace_ev(trace, T, tn, (g << 8) | 0x21);
         const float* bf = cst + 144 * g;
-#pragma unroll 1
+        // half hh owns the 16-column chunks j = 4 hh .. 4 hh + 3 (one K-step of the next scalar operand each);
+        // the TMEM load of chunk j + 1 is in flight while chunk j is processed
+        uint32_t r[2][16];
+        float keep[32];  // last GVP: fp32 copy of chunks 2, 3 for the second mean pass
+        tc::tmem_ld16(Dreg + 16 * (4 * hh), r[0]);
+        tc::wait_ld();
+        float* ab = reinterpret_cast<float*>(stage + hh * 16896);  // [128][33]
+#pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const int j = 4 * hh + j4;  // 16-column chunk == one K-step of the next scalar operand
-          uint32_t r[16];
-          tc::tmem_ld16(Dreg + 16 * j, r);
-          tc::wait_ld();
+          const int j = 4 * hh + j4;
+          if (j4 < 3) tc::tmem_ld16(Dreg + 16 * (j + 1), r[(j4 + 1) & 1]);
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float f0 = silu_fast(__uint_as_float(r[2 * i]) + bf[16 * j + 2 * i]);
-            const float f1 = silu_fast(__uint_as_float(r[2 * i + 1]) + bf[16 * j + 2 * i + 1]);
-            r[2 * i] = __float_as_uint(f0);
-            r[2 * i + 1] = __float_as_uint(f1);
+            const float f0 = silu_fast(__uint_as_float(r[j4 & 1][2 * i]) + bf[16 * j + 2 * i]);
+            const float f1 = silu_fast(__uint_as_float(r[j4 & 1][2 * i + 1]) + bf[16 * j + 2 * i + 1]);
             tc::split_pack_h(f0, f1, hi[i], lo[i]);
+            if (g == 2) {
+              if (j4 < 2) {
+                ab[et * 33 + 16 * j4 + 2 * i] = f0;
+                ab[et * 33 + 16 * j4 + 2 * i + 1] = f1;
+              } else {
+                keep[16 * (j4 - 2) + 2 * i] = f0;
+                keep[16 * (j4 - 2) + 2 * i + 1] = f1;
+              }
+            }
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
           tc::tmem_st8(Dreg + 16 * j + 8, lo);
-          if (g == 2) {  // segmented mean of the scalar messages, 16 columns per half at a time through smem
-            float* ab = reinterpret_cast<float*>(stage + hh * 8704);  // [128][17]
+          if (j4 < 3) tc::wait_ld();
+        }
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&B.F);
+        trace_ev(trace, T, tn, (g << 8) | 0x22);
+        if (g == 2) {  // segmented mean of the scalar messages, 32 columns per half and pass, through shared memory
+#pragma unroll 1
+          for (int ps = 0; ps < 2; ++ps) {
+            if (ps == 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) ab[et * 17 + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) ab[et * 33 + i] = keep[i];
+            }
             slot_barrier(T);
-            for (int jj = 2 * q + (lane >> 4); jj < nseg; jj += 8) {  // half a warp per segment
+            for (int jj = q; jj < nseg; jj += 4) {
               const int r0 = s_off[jj], r1 = s_off[jj + 1], cnt = r1 - r0;
               if (p.accumulate && cnt == 0) continue;
-              float acc = 0.f;
-              for (int rr = r0; rr < r1; ++rr) acc += ab[rr * 17 + (lane & 15)];
+              float acc = 0.f;   // rows summed in edge order (deterministic); loads of 4 rows in flight
+              int rr = r0;
+              for (; rr + 4 <= r1; rr += 4) {
+                const float a0 = ab[rr * 33 + lane], a1 = ab[(rr + 1) * 33 + lane], a2 = ab[(rr + 2) * 33 + lane],
+                            a3 = ab[(rr + 3) * 33 + lane];
+                acc = (((acc + a0) + a1) + a2) + a3;
+              }
+              for (; rr < r1; ++rr) acc += ab[rr * 33 + lane];
               acc = acc / (float)(cnt > 0 ? cnt : 1);
-              float* o = p.agg_h + (size_t)s_dst[jj] * kHidden + 16 * j + (lane & 15);
+              float* o = p.agg_h + (size_t)s_dst[jj] * kHidden + 64 * hh + 32 * ps + lane;
               *o = p.accumulate ? *o + acc : acc;
             }
             slot_barrier(T);
           }
         }
-        tc::wait_st();
-        tc::fence_before_sync();
-        tc::mbar_arrive(&B.F);
       }
 
       // ================= EPI-C: V_out = sigmoid(gate) * Vu -> next vector operand, or the vector message mean
@@ -528,6 +590,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::mbar_wait(&B.gate, par_gate);
         par_gate ^= 1;
         tc::fence_after_sync();
+        trace_ev(trace, T, tn, (g << 8) | 0x31);
         uint32_t r[8];
         tc::tmem_ld8(Areg + 8 * hh, r);
         tc::wait_ld();
@@ -556,6 +619,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           }
           tc::fence_proxy_async();
           tc::mbar_arrive(&B.vecA);
+          trace_ev(trace, T, tn, (g << 8) | 0x32);
         } else {
           float* ab = reinterpret_cast<float*>(stage);  // [128][49]
 #pragma unroll
@@ -569,7 +633,13 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
               const int r0 = s_off[jj], r1 = s_off[jj + 1], cnt = r1 - r0;
               if (p.accumulate && cnt == 0) continue;
               float acc = 0.f;
-              for (int rr = r0; rr < r1; ++rr) acc += ab[rr * 49 + k];
+              int rr = r0;
+              for (; rr + 4 <= r1; rr += 4) {
+                const float a0 = ab[rr * 49 + k], a1 = ab[(rr + 1) * 49 + k], a2 = ab[(rr + 2) * 49 + k],
+                            a3 = ab[(rr + 3) * 49 + k];
+                acc = (((acc + a0) + a1) + a2) + a3;
+              }
+              for (; rr < r1; ++rr) acc += ab[rr * 49 + k];
               acc = acc / (float)(cnt > 0 ? cnt : 1);
               float* o = p.agg_v + (size_t)s_dst[jj] * kVRow + k;
               *o = p.accumulate ? *o + acc : acc;
@@ -589,6 +659,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   uint64_t* bar_empty = bars + kRing;    // [2][kRing]
   SlotBars* sb = reinterpret_cast<SlotBars*>(bars + 3 * kRing);  // [2]
   uint64_t* bar_small = bars + 3 * kRing + 12;
+  uint64_t* bar_stagger = bars + 3 * kRing + 13;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = *p.n_tiles;
@@ -611,6 +682,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
         tc::mbar_init(&sb[T].gate, 1);
       }
       tc::mbar_init(bar_small, 1);
+      tc::mbar_init(bar_stagger, 1);
       tc::fence_mbar_init();
     }
   }
@@ -620,9 +692,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   const uint32_t tmem = *s_tmem;
 
   if (warp < 16) {
-    epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, my_tiles);
-  } else if (warp == 16) {
-    if (lane == 0) mma_role<HAS_V>(smem, tmem, bar_full, bar_empty, sb, bar_small, my_tiles);
+    epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+  } else if (warp < 18) {
+    if (lane == 0) mma_role<HAS_V>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, my_tiles, p.trace);
   } else {
     if (lane == 0) producer_role(p, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
@@ -637,6 +709,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
 using namespace pf;
 
 extern "C" size_t pf_tc_msg_blob_bytes(void) { return (size_t)tcc::kBlobBytes; }
+
+static long long* g_tc_trace = nullptr;
+extern "C" int pf_tc_trace(long long* device_buf) {  // 4 * 4096 * 2 int64; nullptr disarms
+  g_tc_trace = device_buf;
+  return PF_OK;
+}
 
 extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
                                const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
@@ -660,7 +738,7 @@ extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const flo
     configured = true;
   }
   tcc::Params p{src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
-                static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate};
+                static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate, g_tc_trace};
   const int grid = max_tiles < kNumSms ? max_tiles : kNumSms;
   if (src_v != nullptr)
     tcc::edge_conv_tc_kernel<true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
