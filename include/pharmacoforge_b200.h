@@ -152,6 +152,12 @@ int pf_tc_trace(long long* device_buf);
 int pf_node_update(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v, int64_t n_nodes,
                    const float* w, int32_t n_gvps, float* h_out, float* v_out, void* stream);
 
+/* K4 on the tensor cores (same engine as pf_edge_conv_tc, two plain GVPs): n_gvps == 2 only; `wblob` is the
+ * pf_tc_upd_blob_bytes()-byte image built by weights.py:pack_update_tc.  In place is allowed. */
+size_t pf_tc_upd_blob_bytes(void);
+int pf_node_update_tc(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v, int64_t n_nodes,
+                      const void* wblob, float* h_out, float* v_out, void* stream);
+
 /* ---- K5a: noise head -------------------------------------------------------------------------------
  * NoisePredictionBlock (dynamics_gvp.py:10-42): (n_gvps-1) x GVP(16,16,128,128) + GVP(16,1,128,64) with
  * identity gate activation + Linear(64 -> n_out).  w = packed GVPs | Wt[64][n_out4] | b[n_out4]
@@ -212,6 +218,7 @@ typedef struct PfSampleArgs {
   /* tcgen05 path: tile_rows = PF_TC_TILE_ROWS and every w_msg_tc[conv][etype] set -> K3 runs on the tensor cores;
    * tile_rows = PF_TILE_ROWS -> fp32 FFMA kernels */
   const void* w_msg_tc[8][4];
+  const void* w_upd_tc[8][2]; /* optional (n_upd_gvps == 2): K4 on the tensor cores when tile_rows = PF_TC_TILE_ROWS */
   int32_t tile_rows;
   /* schedule (host): step i uses t = t_host[i], coefficients alpha_ts_host[i], ... */
   const float *t_host, *alpha_ts_host, *var_terms_host, *sigma_q_host;

@@ -29,6 +29,8 @@ SIGNATURES = {
                                 STREAM]),
     "pf_tc_msg_blob_bytes": (C.c_size_t, []),
     "pf_tc_trace": (C.c_int, [C.c_void_p]),
+    "pf_tc_upd_blob_bytes": (C.c_size_t, []),
+    "pf_node_update_tc": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_void_p, c_f32p, c_f32p, STREAM]),
     "pf_edge_conv_tc": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                   C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, STREAM]),
     "pf_zero_i32": (C.c_int, [c_i32p, C.c_int64, STREAM]),
@@ -85,6 +87,7 @@ class PfSampleArgs(C.Structure):
         ("w_upd", (C.c_void_p * 2) * MAX_CONVS),
         ("w_noise", C.c_void_p),
         ("w_msg_tc", (C.c_void_p * 4) * MAX_CONVS),
+        ("w_upd_tc", (C.c_void_p * 2) * MAX_CONVS),
         ("tile_rows", C.c_int32),
         ("t_host", C.c_void_p), ("alpha_ts_host", C.c_void_p), ("var_terms_host", C.c_void_p),
         ("sigma_q_host", C.c_void_p),

@@ -241,6 +241,13 @@ static int edge_conv_any(bool tc, const float* src_h, const float* src_v, const 
                       n_gvps, agg_h, agg_v, accumulate, stream);
 }
 
+static int node_update_any(const void* w_tc, const float* h_in, const float* v_in, const float* agg_h,
+                           const float* agg_v, int64_t n_nodes, const float* w, int32_t n_gvps, float* h_out,
+                           float* v_out, void* stream) {
+  if (w_tc != nullptr) return pf_node_update_tc(h_in, v_in, agg_h, agg_v, n_nodes, w_tc, h_out, v_out, stream);
+  return pf_node_update(h_in, v_in, agg_h, agg_v, n_nodes, w, n_gvps, h_out, v_out, stream);
+}
+
 // One eps prediction: PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185) with a->t_graph already set.
 extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_CHECK_ARG(a != nullptr, "pf_denoiser: null args");
@@ -296,12 +303,12 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   prof_end(kSiteFP, as_stream(stream));
     // node updates, in place (gvp.py:501-536)
     prof_begin(kSiteUpdPharm, as_stream(stream));
-  PF_TRY(pf_node_update(a->pharm_hh, fv, a->pharm_agg_h, a->pharm_agg_v, a->n_pharm, a->w_upd[l][0], a->n_upd_gvps,
-                          a->pharm_hh, a->pharm_v, stream));
+    PF_TRY(node_update_any(tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][0] : nullptr, a->pharm_hh, fv, a->pharm_agg_h,
+                           a->pharm_agg_v, a->n_pharm, a->w_upd[l][0], a->n_upd_gvps, a->pharm_hh, a->pharm_v, stream));
   prof_end(kSiteUpdPharm, as_stream(stream));
     prof_begin(kSiteUpdProt, as_stream(stream));
-  PF_TRY(pf_node_update(a->prot_h, pv, a->prot_agg_h, a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps,
-                          a->prot_h, a->prot_v, stream));
+    PF_TRY(node_update_any(tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][1] : nullptr, a->prot_h, pv, a->prot_agg_h,
+                           a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps, a->prot_h, a->prot_v, stream));
   prof_end(kSiteUpdProt, as_stream(stream));
   }
   prof_begin(kSiteNoise, as_stream(stream));

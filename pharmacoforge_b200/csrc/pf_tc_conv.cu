@@ -28,16 +28,30 @@ namespace tcc {
 constexpr int kRows = PF_TC_TILE_ROWS;  // 128
 constexpr int kRing = 12;               // weight slabs resident in shared memory
 constexpr int kSlab = 8192;             // one K=16 slab of Wf^T [128 x 16]: hi image 4 KB | lo image 4 KB
-constexpr int kSlabs0 = 11;             // GVP 0: K = 128 h + 16 rbf + 17 sh (+15 zero) = 176
-constexpr int kSlabs1 = 9;              // GVP 1, 2: K = 128 f + 16 sh = 144
-constexpr int kSlabsPerTile = kSlabs0 + 2 * kSlabs1;  // 29
-// packed weight blob (pharmacoforge_b200/weights.py: pack_message_tc)
-constexpr int kBlobSmallOff = kSlabsPerTile * kSlab;  // 237,568
-constexpr int kSmallBytes = 32768;                    // gate images 3 x 8 KB | vector images 3 x 2 KB | fp32 consts 2 KB
+// Packed weight blobs (pharmacoforge_b200/weights.py: pack_message_tc / pack_update_tc): Wf^T K-slabs of every GVP,
+// then the "small" block kept resident in shared memory: gate images (8 KB per GVP) | vector images (2 KB per GVP)
+// | fp32 constants.
+template <int MODE>
+struct Cfg;
+template <>
+struct Cfg<0> {  // 3-GVP edge message chain; GVP 0: K = 128 h + 16 rbf + 17 sh (+15 zero) = 176, GVP 1, 2: K = 144
+  static constexpr int kGvps = 3, kSlabsPerTile = 29, kVecOff = 24576, kConstOff = 30720, kSmallBytes = 32768;
+  __host__ __device__ static constexpr int nslab(int g) { return g == 0 ? 11 : 9; }
+};
+template <>
+struct Cfg<1> {  // 2-GVP node update chain; K = 128 f + 16 sh = 144
+  static constexpr int kGvps = 2, kSlabsPerTile = 18, kVecOff = 16384, kConstOff = 20480, kSmallBytes = 24576;
+  __host__ __device__ static constexpr int nslab(int) { return 9; }
+};
+template <int MODE>
+constexpr int blob_small_off() { return Cfg<MODE>::kSlabsPerTile * kSlab; }
+template <int MODE>
+constexpr int blob_bytes() { return blob_small_off<MODE>() + Cfg<MODE>::kSmallBytes; }
 constexpr int kGateOff = 0;
-constexpr int kVecOff = 24576;
-constexpr int kConstOff = 30720;
-constexpr int kBlobBytes = kBlobSmallOff + kSmallBytes;  // 270,336
+constexpr int kSmallMax = 32768;
+constexpr int kConstOff = Cfg<0>::kConstOff;  // edge kernel
+// node-update constants (floats from Cfg<1>::kConstOff): per GVP g at 144 g: bf[128] | bg[16]; LayerNorm rows at 512
+constexpr int kCLnMsgW = 512, kCLnMsgB = 640, kCLnUpdW = 768, kCLnUpdB = 896;
 // fp32 constants (floats): per GVP g at 144 g: bf[128] | bg[16]; then GVP 0 extras
 constexpr int kCWh0 = 432;    // Wh0[0][h], h = 0..16  (x_diff row)
 constexpr int kCWhu0 = 452;   // (Wh0.Wu0)[0][u], u = 0..15
@@ -47,7 +61,7 @@ constexpr int kStage = 36864;  // per-slot staging: smem A operands (3 x 8 KB) /
 constexpr int kMetaInts = 1552; // tile metadata (520 ints) + per-row exchange between the two column halves
 constexpr int kOffRing = 0;
 constexpr int kOffSmall = kRing * kSlab;              // 98,304
-constexpr int kOffStage = kOffSmall + kSmallBytes;    // 131,072
+constexpr int kOffStage = kOffSmall + kSmallMax;      // 131,072
 constexpr int kOffMeta = kOffStage + 2 * kStage;      // 186,368
 constexpr int kOffBars = kOffMeta + 2 * kMetaInts * 4;  // 190,720
 constexpr int kNumBars = 3 * kRing + 12 + 2;
@@ -95,13 +109,15 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int
 __device__ __forceinline__ void slot_barrier(int T) { tc::named_bar_sync(1 + T, 256); }
 
 // ------------------------------------------------------------------------------------------------ producer
-__device__ void producer_role(const Params& p, uint8_t* smem, uint64_t* bar_full, uint64_t* bar_empty,
+template <int MODE>
+__device__ void producer_role(const uint8_t* wblob, uint8_t* smem, uint64_t* bar_full, uint64_t* bar_empty,
                               uint64_t* bar_small, int my_tiles) {
+  constexpr int kSlabsPerTile = Cfg<MODE>::kSlabsPerTile;
   if (my_tiles == 0) return;
-  tc::mbar_expect_tx(bar_small, kSmallBytes);
+  tc::mbar_expect_tx(bar_small, Cfg<MODE>::kSmallBytes);
 #pragma unroll
-  for (int i = 0; i < kSmallBytes / 8192; ++i)
-    tc::bulk_g2s(smem + kOffSmall + i * 8192, p.wblob + kBlobSmallOff + i * 8192, 8192, bar_small);
+  for (int i = 0; i < Cfg<MODE>::kSmallBytes / 8192; ++i)
+    tc::bulk_g2s(smem + kOffSmall + i * 8192, wblob + blob_small_off<MODE>() + i * 8192, 8192, bar_small);
   const int total = ((my_tiles + 1) >> 1) * kSlabsPerTile;
   for (int n = 0; n < total; ++n) {
     const int slot = n % kRing;
@@ -112,14 +128,14 @@ __device__ void producer_role(const Params& p, uint8_t* smem, uint64_t* bar_full
       if (2 * (o / kSlabsPerTile) + 1 < my_tiles) tc::mbar_wait(&bar_empty[kRing + slot], par);
     }
     tc::mbar_expect_tx(&bar_full[slot], kSlab);
-    tc::bulk_g2s(smem + kOffRing + slot * kSlab, p.wblob + (size_t)(n % kSlabsPerTile) * kSlab, kSlab, &bar_full[slot]);
+    tc::bulk_g2s(smem + kOffRing + slot * kSlab, wblob + (size_t)(n % kSlabsPerTile) * kSlab, kSlab, &bar_full[slot]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issuer
 // One issuing thread per tile slot (warps 16, 17): a slot's short jobs (V: 9 MMAs of N=32, G: 24 of N=16) are never
 // held back by the other slot's 27-33 N=128 MMAs being ISSUED, only by the few already queued in the tensor pipe.
-template <bool HAS_V>
+template <int MODE, bool HAS_V>
 __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint64_t* bar_empty,
                          SlotBars* sb, uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles, long long* trace) {
   const int n_mine = (my_tiles + 1 - T) >> 1;
@@ -137,15 +153,15 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
   tc::mbar_wait(bar_small, 0);
   for (int t = 0; t < n_mine; ++t) {
 #pragma unroll 1
-    for (int g = 0; g < 3; ++g) {
+    for (int g = 0; g < Cfg<MODE>::kGvps; ++g) {
       const uint32_t Areg = g == 1 ? regQ : regP;
       const uint32_t Dreg = g == 1 ? regP : regQ;
-      if (HAS_V || g > 0) {  // ---- V_g: vector channels, A = staged V (hi, lo), B = [Wh | Wh.Wu] image
+      if (MODE == 1 || HAS_V || g > 0) {  // ---- V_g: vector channels, A = staged V (hi, lo), B = [Wh | Wh.Wu] image
         tc::mbar_wait(&B.vecA, p_vecA);
         p_vecA ^= 1;
         tc::fence_after_sync();
         trace_ev(trace, 2 + T, tn, (g << 8) | 0x10);
-        const uint32_t bimg = small_a + kVecOff + g * 2048;
+        const uint32_t bimg = small_a + Cfg<MODE>::kVecOff + g * 2048;
         const uint64_t b_hi = tc::make_smem_desc(bimg, 512, 128), b_lo = tc::make_smem_desc(bimg + 1024, 512, 128);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -163,7 +179,7 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
       p_A ^= 1;
       tc::fence_after_sync();
       trace_ev(trace, 2 + T, tn, (g << 8) | 0x20);
-      const int nslab = g == 0 ? kSlabs0 : kSlabs1;
+      const int nslab = Cfg<MODE>::nslab(g);
       for (int k = 0; k < nslab; ++k, ++q) {
         const uint32_t slot = q % kRing;
         tc::mbar_wait(&bar_full[slot], (q / kRing) & 1u);
@@ -694,9 +710,479 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   if (warp < 16) {
     epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    if (lane == 0) mma_role<HAS_V>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, my_tiles, p.trace);
+    if (lane == 0) mma_role<0, HAS_V>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, my_tiles, p.trace);
   } else {
-    if (lane == 0) producer_role(p, smem, bar_full, bar_empty, bar_small, my_tiles);
+    if (lane == 0) producer_role<0>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 16) tc::tmem_dealloc(tmem, 512);
+}
+
+
+// =====================================================================================================================
+// K4 on the tensor cores: (h, v) <- GVPLayerNorm_msg(h + agg_h, v + agg_v); (rh, rv) = GVP x 2; (h, v) <-
+// GVPLayerNorm_upd(h + rh, v + rv)   (gvp.py:511-532, eval mode).  Same tile engine as the message kernel: a tile is
+// 128 consecutive nodes, the chain is two plain GVPs (K = 144).  The normalised input rows are written to h_out /
+// v_out by the front end and read back as the residual by the back end (same rows, same CTA), so in-place updates
+// (h_out == h_in) are allowed.
+// =====================================================================================================================
+struct NodeParams {
+  const float *h_in, *v_in, *agg_h, *agg_v;
+  long long n_nodes;
+  const uint8_t* wblob;
+  float *h_out, *v_out;
+  long long* trace;
+};
+
+__device__ __forceinline__ float xor8_sum(float v) {  // sum over the 8 lanes that share one row of a 4-row pass
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+template <bool HAS_V>
+__device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
+                                   uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
+  const int stid = threadIdx.x & 255;
+  const int hh = stid >> 7;          // column half
+  const int et = stid & 127;         // node row of the tile == TMEM lane
+  const int q = et >> 5, lane = et & 31;
+  const int wslot = stid >> 5;
+  const uint32_t P = tmem + 256 * T + ((uint32_t)(q * 32) << 16), Q = P + 128;
+  uint8_t* stage = smem + kOffStage + T * kStage;
+  float4* s_xch = reinterpret_cast<float4*>(reinterpret_cast<int*>(smem + kOffMeta) + T * kMetaInts + 520);  // [128][2]
+  const float* cst = reinterpret_cast<const float*>(smem + kOffSmall + Cfg<1>::kConstOff);
+  SlotBars& B = sb[T];
+  uint32_t par_vecD = 0, par_D = 0, par_gate = 0;
+  if (T < my_tiles) tc::mbar_wait(bar_small, 0);
+  if (T == 1 && T < my_tiles) tc::mbar_wait(bar_stagger, 0);
+  float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36]
+  const int prow = lane >> 3, piece = lane & 7;                 // cooperative layout: 8 lanes x 16 B per row chunk
+
+  for (int it = T; it < my_tiles; it += 2) {
+    const long long n0 = (long long)(blockIdx.x + (long long)it * gridDim.x) * kRows;
+    const long long rem = p.n_nodes - n0;
+    const int nrows = rem < kRows ? (int)rem : kRows;
+    slot_barrier(T);  // everyone is done with the previous tile's staging / exchange buffers
+
+    // ---- scalars: x = h_in + agg_h (own 64 columns, cooperative layout), LayerNorm_msg over the full row
+    {
+      float4 g4[2][8];
+      float rs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rs[i] = 0.f;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 32 * q + 4 * i + prow;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < nrows) {
+            const size_t o = (size_t)(n0 + row) * kHidden + 32 * (2 * hh + c2) + 4 * piece;
+            x = *reinterpret_cast<const float4*>(p.h_in + o);  // plain load: h_out may alias h_in
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.agg_h + o));
+            x.x += a.x;
+            x.y += a.y;
+            x.z += a.z;
+            x.w += a.w;
+          }
+          g4[c2][i] = x;
+          rs[i] += (x.x + x.y) + (x.z + x.w);
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rs[i] = xor8_sum(rs[i]);
+        if (piece == 0) s_xch[(32 * q + 4 * i + prow) * 2 + hh].x = rs[i];
+      }
+      slot_barrier(T);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 32 * q + 4 * i + prow;
+        const float mean = (s_xch[row * 2].x + s_xch[row * 2 + 1].x) * (1.0f / kHidden);
+        float sq = 0.f;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          float4& x = g4[c2][i];
+          x.x -= mean;
+          x.y -= mean;
+          x.z -= mean;
+          x.w -= mean;
+          sq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+        }
+        sq = xor8_sum(sq);
+        if (piece == 0) s_xch[row * 2 + hh].y = sq;
+      }
+      slot_barrier(T);
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int c = 2 * hh + c2;
+        const float4 lw = *reinterpret_cast<const float4*>(cst + kCLnMsgW + 32 * c + 4 * piece);
+        const float4 lb = *reinterpret_cast<const float4*>(cst + kCLnMsgB + 32 * c + 4 * piece);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 32 * q + 4 * i + prow;
+          const float var = (s_xch[row * 2].y + s_xch[row * 2 + 1].y) * (1.0f / kHidden);
+          const float rstd = rsqrtf(var + 1e-5f);
+          float4 y = g4[c2][i];
+          y.x = y.x * rstd * lw.x + lb.x;
+          y.y = y.y * rstd * lw.y + lb.y;
+          y.z = y.z * rstd * lw.z + lb.z;
+          y.w = y.w * rstd * lw.w + lb.w;
+          if (row < nrows) *reinterpret_cast<float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece) = y;
+          *reinterpret_cast<float4*>(tb + (4 * i + prow) * 36 + 4 * piece) = y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(tb + lane * 36 + 16 * ks + 4 * j);
+            tc::split_pack_h(v.x, v.y, hi[2 * j], lo[2 * j]);
+            tc::split_pack_h(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+          }
+          tc::tmem_st8(P + 32 * c + 16 * ks, hi);
+          tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
+        }
+        __syncwarp();
+      }
+    }
+    slot_barrier(T);  // scalar transposes done: the vector buffers below overlap them
+
+    // ---- vectors: v = v_in + agg_v, vector LayerNorm (all 16 channels), own 8 channels kept
+    float Vu[24];
+    float vsc = 1.f, vinv = 1.f;
+    {
+      float* tv = reinterpret_cast<float*>(stage + q * 6656);  // [32][52], filled by the hh == 0 warp of the quarter
+      if (hh == 0) {
+#pragma unroll
+        for (int ps = 0; ps < 12; ++ps) {
+          const int qq = 32 * ps + lane;
+          const int rr = qq / 12, pc = qq - 12 * rr;
+          const int row = 32 * q + rr;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < nrows) {
+            const size_t o = (size_t)(n0 + row) * kVRow + 4 * pc;
+            x = __ldg(reinterpret_cast<const float4*>(p.agg_v + o));
+            if constexpr (HAS_V) {
+              const float4 a = *reinterpret_cast<const float4*>(p.v_in + o);
+              x.x += a.x;
+              x.y += a.y;
+              x.z += a.z;
+              x.w += a.w;
+            }
+          }
+          *reinterpret_cast<float4*>(tv + rr * 52 + 4 * pc) = x;
+        }
+      }
+      slot_barrier(T);
+      float nrm = 0.f;
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const float4 a = *reinterpret_cast<const float4*>(tv + lane * 52 + 4 * u4);
+        const float4 b = *reinterpret_cast<const float4*>(tv + lane * 52 + 16 + 4 * u4);
+        const float4 c = *reinterpret_cast<const float4*>(tv + lane * 52 + 32 + 4 * u4);
+        nrm += fmaxf(a.x * a.x + b.x * b.x + c.x * c.x, 1e-8f) + fmaxf(a.y * a.y + b.y * b.y + c.y * c.y, 1e-8f) +
+               fmaxf(a.z * a.z + b.z * b.z + c.z * c.z, 1e-8f) + fmaxf(a.w * a.w + b.w * b.w + c.w * c.w, 1e-8f);
+      }
+      const float vn = sqrtf(nrm * (1.0f / kVec) + 1e-5f) + 1e-5f;
+      float pm = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int u4 = 0; u4 < 2; ++u4) {
+          float4 x = *reinterpret_cast<const float4*>(tv + lane * 52 + 16 * c + 8 * hh + 4 * u4);
+          x.x /= vn;
+          x.y /= vn;
+          x.z /= vn;
+          x.w /= vn;
+          Vu[8 * c + 4 * u4] = x.x;
+          Vu[8 * c + 4 * u4 + 1] = x.y;
+          Vu[8 * c + 4 * u4 + 2] = x.z;
+          Vu[8 * c + 4 * u4 + 3] = x.w;
+          if (et < nrows) *reinterpret_cast<float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4) = x;
+          pm = fmaxf(fmaxf(pm, fabsf(x.x)), fmaxf(fabsf(x.y), fmaxf(fabsf(x.z), fabsf(x.w))));
+        }
+      s_xch[et * 2 + hh].z = pm;
+      slot_barrier(T);  // all rows read (the staging writes below overlap tv); exchange visible
+      row_scale(fmaxf(pm, s_xch[et * 2 + (1 - hh)].z), vsc, vinv);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float t8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t8[u] = Vu[8 * c + u] * vsc;
+        stage_store8(stage + c * 8192, et, hh, t8);
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&B.vecA);
+    }
+
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+      const uint32_t Areg = g == 1 ? Q : P, Dreg = g == 1 ? P : Q;
+      // ================= EPI-A: hidden vector channels -> norms sh, Vu kept in registers (scaled by vsc)
+      {
+        float sh[8];
+        tc::mbar_wait(&B.vecD, par_vecD);
+        par_vecD ^= 1;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int h = 0; h < 8; ++h) sh[h] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t ra[8], rb[8];
+          tc::tmem_ld8(Dreg + 32 * c + 8 * hh, ra);
+          tc::tmem_ld8(Dreg + 32 * c + 16 + 8 * hh, rb);
+          tc::wait_ld();
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const float vh = __uint_as_float(ra[h]);
+            sh[h] = fmaf(vh, vh, sh[h]);
+            Vu[8 * c + h] = __uint_as_float(rb[h]);
+          }
+        }
+        const float inv2 = vinv * vinv;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) sh[h] = sqrtf(fmaxf(sh[h] * inv2, 1e-8f));
+        stage_store8(stage, et, hh, sh);
+        tc::fence_proxy_async();
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&B.A);
+      }
+      // ================= EPI-B: f = SiLU(D + b), split in place into the next A operand
+      {
+        tc::mbar_wait(&B.D, par_D);
+        par_D ^= 1;
+        tc::fence_after_sync();
+        const float* bf = cst + 144 * g;
+        uint32_t r[2][16];
+        tc::tmem_ld16(Dreg + 16 * (4 * hh), r[0]);
+        tc::wait_ld();
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int j = 4 * hh + j4;
+          if (j4 < 3) tc::tmem_ld16(Dreg + 16 * (j + 1), r[(j4 + 1) & 1]);
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f0 = silu_fast(__uint_as_float(r[j4 & 1][2 * i]) + bf[16 * j + 2 * i]);
+            const float f1 = silu_fast(__uint_as_float(r[j4 & 1][2 * i + 1]) + bf[16 * j + 2 * i + 1]);
+            tc::split_pack_h(f0, f1, hi[i], lo[i]);
+          }
+          tc::tmem_st8(Dreg + 16 * j, hi);
+          tc::tmem_st8(Dreg + 16 * j + 8, lo);
+          if (j4 < 3) tc::wait_ld();
+        }
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&B.F);
+      }
+      // ================= EPI-C: V_out = sigmoid(gate) * Vu
+      {
+        tc::mbar_wait(&B.gate, par_gate);
+        par_gate ^= 1;
+        tc::fence_after_sync();
+        uint32_t r[8];
+        tc::tmem_ld8(Areg + 8 * hh, r);
+        tc::wait_ld();
+        tc::fence_before_sync();
+        const float* bg = cst + 144 * g + 128 + 8 * hh;
+        float pm = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float gt = sigmoid_fast(__uint_as_float(r[u]) + bg[u]) * vinv;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            Vu[8 * c + u] *= gt;
+            pm = fmaxf(pm, fabsf(Vu[8 * c + u]));
+          }
+        }
+        if (g == 0) {
+          s_xch[et * 2 + hh].z = pm;
+          slot_barrier(T);
+          row_scale(fmaxf(pm, s_xch[et * 2 + (1 - hh)].z), vsc, vinv);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float t8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t8[u] = Vu[8 * c + u] * vsc;
+            stage_store8(stage + c * 8192, et, hh, t8);
+          }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&B.vecA);
+        }
+      }
+    }
+
+    // ================= back end: residual + GVPLayerNorm_upd.  Last GVP was g = 1: f (hi, lo) sits in region P,
+    // region Q is free (its gate columns were read above).
+    {
+      // ---- vectors: t = v_res + V_out, one norm over all 16 channels (partial over the own 8, exchanged)
+      float nrm = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int u4 = 0; u4 < 2; ++u4) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (et < nrows) x = *reinterpret_cast<const float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4);
+          Vu[8 * c + 4 * u4] += x.x;
+          Vu[8 * c + 4 * u4 + 1] += x.y;
+          Vu[8 * c + 4 * u4 + 2] += x.z;
+          Vu[8 * c + 4 * u4 + 3] += x.w;
+        }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        nrm += fmaxf(Vu[u] * Vu[u] + Vu[8 + u] * Vu[8 + u] + Vu[16 + u] * Vu[16 + u], 1e-8f);
+      s_xch[et * 2 + hh].z = nrm;
+      slot_barrier(T);  // also orders the gate reads of both halves before region Q is overwritten below
+      {
+        const float tot = nrm + s_xch[et * 2 + (1 - hh)].z;
+        const float vn = sqrtf(tot * (1.0f / kVec) + 1e-5f) + 1e-5f;
+        if (et < nrows) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int u4 = 0; u4 < 2; ++u4) {
+              float4 x;
+              x.x = Vu[8 * c + 4 * u4] / vn;
+              x.y = Vu[8 * c + 4 * u4 + 1] / vn;
+              x.z = Vu[8 * c + 4 * u4 + 2] / vn;
+              x.w = Vu[8 * c + 4 * u4 + 3] / vn;
+              *reinterpret_cast<float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4) = x;
+            }
+        }
+      }
+      // ---- scalars, pass 1: y = f + h_res (f rebuilt from its fp16 hi + lo parts), kept in region Q as fp32
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int c = 2 * hh + c2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 32 * q + 4 * i + prow;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < nrows) x = *reinterpret_cast<const float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece);
+          *reinterpret_cast<float4*>(tb + (4 * i + prow) * 36 + 4 * piece) = x;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int j = 2 * c + ks;
+          uint32_t hi[8], lo[8], y[16];
+          tc::tmem_ld8(P + 16 * j, hi);
+          tc::tmem_ld8(P + 16 * j + 8, lo);
+          tc::wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi[i]));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lo[i]));
+            const float y0 = (a.x + b.x) + tb[lane * 36 + 16 * ks + 2 * i];
+            const float y1 = (a.y + b.y) + tb[lane * 36 + 16 * ks + 2 * i + 1];
+            sum += y0 + y1;
+            y[2 * i] = __float_as_uint(y0);
+            y[2 * i + 1] = __float_as_uint(y1);
+          }
+          tc::tmem_st16(Q + 16 * j, y);
+        }
+        __syncwarp();
+      }
+      tc::wait_st();
+      s_xch[et * 2 + hh].x = sum;
+      slot_barrier(T);
+      const float mean = (sum + s_xch[et * 2 + (1 - hh)].x) * (1.0f / kHidden);
+      float sq = 0.f;
+#pragma unroll 1
+      for (int j4 = 0; j4 < 4; ++j4) {
+        uint32_t y[16];
+        tc::tmem_ld16(Q + 16 * (4 * hh + j4), y);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float d = __uint_as_float(y[i]) - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+      s_xch[et * 2 + hh].y = sq;
+      slot_barrier(T);
+      const float rstd = rsqrtf((sq + s_xch[et * 2 + (1 - hh)].y) * (1.0f / kHidden) + 1e-5f);
+      // ---- pass 3: normalise, transpose back to the cooperative layout, coalesced store
+#pragma unroll 1
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int c = 2 * hh + c2;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t y[16];
+          tc::tmem_ld16(Q + 16 * (2 * c + ks), y);
+          tc::wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = 32 * c + 16 * ks + i;
+            tb[lane * 36 + 16 * ks + i] = (__uint_as_float(y[i]) - mean) * rstd * cst[kCLnUpdW + col] + cst[kCLnUpdB + col];
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 32 * q + 4 * i + prow;
+          const float4 x = *reinterpret_cast<const float4*>(tb + (4 * i + prow) * 36 + 4 * piece);
+          if (row < nrows) *reinterpret_cast<float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece) = x;
+        }
+        __syncwarp();
+      }
+      tc::fence_before_sync();  // TMEM reads of this tile are complete before the next tile's stores
+    }
+  }
+}
+
+template <bool HAS_V>
+__global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const NodeParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + kRing;
+  SlotBars* sb = reinterpret_cast<SlotBars*>(bars + 3 * kRing);
+  uint64_t* bar_small = bars + 3 * kRing + 12;
+  uint64_t* bar_stagger = bars + 3 * kRing + 13;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = (p.n_nodes + kRows - 1) / kRows;
+  const int my_tiles = n_tiles > (long long)blockIdx.x ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+
+  if (warp == 16) {
+    tc::tmem_alloc(s_tmem, 512);
+    if (lane == 0) {
+      for (int i = 0; i < kRing; ++i) {
+        tc::mbar_init(&bar_full[i], 1);
+        tc::mbar_init(&bar_empty[i], 1);
+        tc::mbar_init(&bar_empty[kRing + i], 1);
+      }
+      for (int T = 0; T < 2; ++T) {
+        tc::mbar_init(&sb[T].vecA, 256);
+        tc::mbar_init(&sb[T].vecD, 1);
+        tc::mbar_init(&sb[T].A, 256);
+        tc::mbar_init(&sb[T].D, 1);
+        tc::mbar_init(&sb[T].F, 256);
+        tc::mbar_init(&sb[T].gate, 1);
+      }
+      tc::mbar_init(bar_small, 1);
+      tc::mbar_init(bar_stagger, 1);
+      tc::fence_mbar_init();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 16) {
+    node_epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+  } else if (warp < 18) {
+    if (lane == 0) mma_role<1, true>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, my_tiles, p.trace);
+  } else {
+    if (lane == 0) producer_role<1>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -708,7 +1194,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
 
 using namespace pf;
 
-extern "C" size_t pf_tc_msg_blob_bytes(void) { return (size_t)tcc::kBlobBytes; }
+extern "C" size_t pf_tc_msg_blob_bytes(void) { return (size_t)tcc::blob_bytes<0>(); }
+extern "C" size_t pf_tc_upd_blob_bytes(void) { return (size_t)tcc::blob_bytes<1>(); }
 
 static long long* g_tc_trace = nullptr;
 extern "C" int pf_tc_trace(long long* device_buf) {  // 4 * 4096 * 2 int64; nullptr disarms
@@ -745,5 +1232,34 @@ extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const flo
   else
     tcc::edge_conv_tc_kernel<false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_edge_conv_tc");
+  return PF_OK;
+}
+
+extern "C" int pf_node_update_tc(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
+                                 int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream) {
+  PF_CHECK_ARG(h_in && agg_h && agg_v && wblob && h_out && v_out, "pf_node_update_tc: null pointer");
+  PF_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 15) == 0, "pf_node_update_tc: weight blob must be 16-byte aligned");
+  if (n_nodes <= 0) return PF_OK;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tcc::node_update_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tcc::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tcc::node_update_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               tcc::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("pf_node_update_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
+      return PF_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  tcc::NodeParams p{h_in, v_in, agg_h, agg_v, (long long)n_nodes, static_cast<const uint8_t*>(wblob), h_out, v_out, nullptr};
+  const long long tiles = (n_nodes + tcc::kRows - 1) / tcc::kRows;
+  const int grid = (int)(tiles < kNumSms ? tiles : kNumSms);
+  if (v_in != nullptr)
+    tcc::node_update_tc_kernel<true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  else
+    tcc::node_update_tc_kernel<false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  PF_CHECK_LAUNCH("pf_node_update_tc");
   return PF_OK;
 }

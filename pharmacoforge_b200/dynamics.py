@@ -161,6 +161,9 @@ class _DeviceState:
             for l in range(dyn.n_convs):
                 for e in range(4):
                     a.w_msg_tc[l][e] = w.tc_ptr(l, e)
+                if w.tcu is not None:
+                    for n in range(2):
+                        a.w_upd_tc[l][n] = w.tcu_ptr(l, n)
         self.args = a
         self.weights = w          # keep alive
         self.batch_buffers = (g.prot_x, g.pharm_x, g.pharm_h)

@@ -162,6 +162,16 @@ def node_update(h_in: torch.Tensor, v_in: Optional[torch.Tensor], agg_h: torch.T
                                  _f(v_out), _s()), "pf_node_update")
 
 
+@torch.library.custom_op(f"{NS}::node_update_tc", mutates_args=("h_out", "v_out"))
+def node_update_tc(h_in: torch.Tensor, v_in: Optional[torch.Tensor], agg_h: torch.Tensor, agg_v: torch.Tensor,
+                   wblob: torch.Tensor, h_out: torch.Tensor, v_out: torch.Tensor) -> None:
+    """K4 on the tensor cores (tcgen05); wblob from weights.pack_update_tc."""
+    if wblob.dtype != torch.uint8 or wblob.numel() != _L.pf_tc_upd_blob_bytes():
+        raise _lib.PfError("node_update_tc: wblob must be the uint8 image built by weights.pack_update_tc")
+    _lib.check(_L.pf_node_update_tc(_f(h_in), _f(v_in), _f(agg_h), _f(agg_v), h_in.shape[0], _p(wblob), _f(h_out),
+                                    _f(v_out), _s()), "pf_node_update_tc")
+
+
 @torch.library.custom_op(f"{NS}::noise_head", mutates_args=())
 def noise_head(h: torch.Tensor, v: torch.Tensor, w: torch.Tensor, n_gvps: int,
                n_out: int) -> Tuple[torch.Tensor, torch.Tensor]:

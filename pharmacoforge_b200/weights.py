@@ -109,9 +109,22 @@ class PackedWeights:
             self.tc_stride = imgs[0].numel()
             assert self.tc_stride % 256 == 0
             self.tc = torch.cat(imgs).to(device)
+        self.tcu = None
+        if n_upd == 2:
+            imgs = [pack_update_tc(sd, f"{np_}.conv_layers.{l}", nt) for l in range(n_convs) for nt in NTYPES]
+            self.tcu_stride = imgs[0].numel()
+            assert self.tcu_stride % 256 == 0
+            self.tcu = torch.cat(imgs).to(device)
 
     def tc_ptr(self, conv: int, etype: int) -> int:
         return self.tc.data_ptr() + (conv * len(ETYPE_KEYS) + etype) * self.tc_stride
+
+    def tcu_ptr(self, conv: int, ntype: int) -> int:
+        return self.tcu.data_ptr() + (conv * len(NTYPES) + ntype) * self.tcu_stride
+
+    def tcu_view(self, conv: int, ntype: int) -> torch.Tensor:
+        o = (conv * len(NTYPES) + ntype) * self.tcu_stride
+        return self.tcu[o:o + self.tcu_stride]
 
     def ptr(self, key: str) -> int:
         return self.flat.data_ptr() + 4 * self.offsets[key]
@@ -201,4 +214,38 @@ def pack_message_tc(sd: Dict[str, torch.Tensor], conv_p: str, etype_key: str) ->
             consts[TC_C_WHC16:TC_C_WHC16 + 16] = Wh[1:17, 16].float()
     blob = torch.cat(slabs + gates + vecs + [_bytes(consts)])
     assert blob.numel() == TC_SMALL_OFF + TC_SMALL_BYTES, blob.numel()
+    return blob
+
+
+# --- K4 on the tensor cores: one byte image per (conv layer, node type); mirrors Cfg<1> in csrc/pf_tc_conv.cu
+TCU_SLABS = (9, 9)
+TCU_SMALL_OFF = sum(TCU_SLABS) * TC_SLAB_BYTES
+TCU_VEC_OFF, TCU_CONST_OFF, TCU_SMALL_BYTES = 16384, 20480, 24576
+TCU_C_LN = 512          # ln_msg_w | ln_msg_b | ln_upd_w | ln_upd_b, 128 floats each
+
+
+def pack_update_tc(sd: Dict[str, torch.Tensor], conv_p: str, ntype: str) -> torch.Tensor:
+    """The 2-GVP node update of one node type (gvp.py:417-437, 511-532) as the uint8 image pf_node_update_tc
+    streams: 18 Wf^T K-slabs | gate images | [Wh | Wh.Wu] images | fp32 constants (biases, LayerNorm rows)."""
+    slabs, gates, vecs = [], [], []
+    consts = torch.zeros((TCU_SMALL_BYTES - TCU_CONST_OFF) // 4, dtype=torch.float32)
+    for g in range(2):
+        q = f"{conv_p}.node_update_fns.{ntype}.{g}"
+        Wh = sd[q + ".Wh"].detach().double().cpu()
+        Wu = sd[q + ".Wu"].detach().double().cpu()
+        Wf = sd[q + ".to_feats_out.0.weight"].detach().float().cpu()
+        Wg = sd[q + ".scalar_to_vector_gates.weight"].detach().float().cpu()
+        assert Wh.shape == (16, 16) and Wu.shape == (16, 16) and Wf.shape == (128, 144) and Wg.shape == (16, 128)
+        slabs += [_hi_lo_images(Wf[:, 16 * s:16 * s + 16]) for s in range(9)]
+        gates += [_hi_lo_images(Wg[:, 16 * s:16 * s + 16]) for s in range(8)]
+        vecs.append(_hi_lo_images(torch.cat([Wh.t(), (Wh @ Wu).t()]).float()))
+        consts[144 * g:144 * g + 128] = sd[q + ".to_feats_out.0.bias"].detach().float().cpu()
+        consts[144 * g + 128:144 * g + 144] = sd[q + ".scalar_to_vector_gates.bias"].detach().float().cpu()
+    for i, key in enumerate((f"{conv_p}.message_layer_norms.{ntype}.feat_norm.weight",
+                             f"{conv_p}.message_layer_norms.{ntype}.feat_norm.bias",
+                             f"{conv_p}.update_layer_norms.{ntype}.feat_norm.weight",
+                             f"{conv_p}.update_layer_norms.{ntype}.feat_norm.bias")):
+        consts[TCU_C_LN + 128 * i:TCU_C_LN + 128 * (i + 1)] = sd[key].detach().float().cpu()
+    blob = torch.cat(slabs + gates + vecs + [_bytes(consts)])
+    assert blob.numel() == TCU_SMALL_OFF + TCU_SMALL_BYTES, blob.numel()
     return blob

@@ -244,10 +244,19 @@ def test_edge_conv_each_etype(env, etype_idx, with_vectors, impl):
     _edge_conv_case(env, etype_idx, 1 if with_vectors else 0, with_vectors, impl)
 
 
-def test_node_update(env):
+@pytest.mark.parametrize("impl", ["tc", "ffma"])
+def test_node_update(env, impl):
     O, ops = env.O, env.ops
     gen = torch.Generator().manual_seed(8)
-    for n in (1, 63, 64, 65, 1000):
+
+    def run(h_in, v_in, agg_h, agg_v, layer, nt, h_out, v_out):
+        if impl == "tc":
+            ops.node_update_tc(h_in, v_in, agg_h, agg_v, env.W.tcu_view(layer, nt), h_out, v_out)
+        else:
+            ops.node_update(h_in, v_in, agg_h, agg_v, env.W.view(f"upd{layer}_{nt}"), 2, h_out, v_out)
+        torch.cuda.synchronize()
+
+    for n in (1, 63, 64, 65, 127, 128, 129, 1000, 40000):
         h, v = torch.randn(n, 128, generator=gen), torch.randn(n, 16, 3, generator=gen)
         ah, av = torch.randn(n, 128, generator=gen), torch.randn(n, 16, 3, generator=gen)
         p = "dynamics.noise_predictor.conv_layers.1"
@@ -257,7 +266,7 @@ def test_node_update(env):
             rs, rv = O.gvp(env.sd, f"{p}.node_update_fns.prot.{i}", rs, rv)
         want_h, want_v = O.gvp_layernorm(env.sd, f"{p}.update_layer_norms.prot", s + rs, vv + rv)
         hd, vd = h.cuda(), to_cm(v).cuda()
-        ops.node_update(hd, vd, ah.cuda(), to_cm(av).cuda(), env.W.view("upd1_1"), 2, hd, vd)   # in place
+        run(hd, vd, ah.cuda(), to_cm(av).cuda(), 1, 1, hd, vd)   # in place
         close(hd, want_h, what=f"node_update h n={n}")
         close(from_cm(vd), want_v, what=f"node_update v n={n}")
     # zero input vectors (first layer): v_in = None
@@ -269,7 +278,7 @@ def test_node_update(env):
         rs, rv = O.gvp(env.sd, f"{p}.node_update_fns.pharm.{i}", rs, rv)
     want_h, want_v = O.gvp_layernorm(env.sd, f"{p}.update_layer_norms.pharm", s + rs, vv + rv)
     ho, vo = torch.empty(70, 128, device=env.dev), torch.empty(70, 48, device=env.dev)
-    ops.node_update(h.cuda(), None, ah.cuda(), to_cm(av).cuda(), env.W.view("upd0_0"), 2, ho, vo)
+    run(h.cuda(), None, ah.cuda(), to_cm(av).cuda(), 0, 0, ho, vo)
     close(ho, want_h, what="node_update h (v=0)")
     close(from_cm(vo), want_v, what="node_update v (v=0)")
 
