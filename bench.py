@@ -241,15 +241,21 @@ def main():
     pp_ms, pp_n = prof["edge_pp"]
     pp_avg_ms = pp_ms / max(pp_n, 1)
     achieved_tf = n_pp_edges * FLOP_PER_EDGE / (pp_avg_ms * 1e-3) / 1e12 if pp_n else 0.0
-    traffic = None
+    traffic, tnote = None, ""
     tpath = os.path.join(ROOT, "profiles", "edge_pp_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"kernel": "edge_conv_kernel (pp edges)", "bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"],
-                "unit": "TFLOP/s", "frac": achieved_tf / pk["tf"], "traffic": traffic, "peak_source": pk["src"],
-                "avg_launch_ms": pp_avg_ms, "launches_timed": pp_n, "edges_per_launch": n_pp_edges,
-                "share_of_step": pp_ms / ms_total,
-                "note": "fp32 FFMA path: no tensor-pipe instructions yet; algorithmic 136,742 FLOP/edge"}
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_edge"] * n_pp_edges     # ncu capture at 8 pockets, scaled per edge
+        tnote = (f"; traffic = {tj['dram_bytes_per_edge']:.0f} B/edge (ncu --set full at 8 pockets) x edges; ncu tensor "
+                 f"pipe active {tj['sm__pipe_tensor_cycles_active_pct']}% (3 fp16 passes per product)")
+    tc_path = g.tile_rows == 128
+    roofline = {"kernel": ("edge_conv_tc_kernel" if tc_path else "edge_conv_kernel") + " (pp edges)", "bound": "tensor",
+                "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf"],
+                "traffic": traffic, "peak_source": pk["src"], "avg_launch_ms": pp_avg_ms, "launches_timed": pp_n,
+                "edges_per_launch": n_pp_edges, "share_of_step": pp_ms / ms_total,
+                "note": ("tcgen05.mma kind::f16, fp16 hi/lo split, 3 passes (fp32-parity mode)" if tc_path
+                         else "fp32 FFMA kernels (PF_TILE_ROWS=64)") +
+                        "; achieved = ALGORITHMIC 136,742 FLOP/edge (one pass) / launch time" + tnote}
     breakdown = {k: round(v[0] / ms_total, 4) for k, v in prof.items() if v[1]}
     del g, st
     torch.cuda.empty_cache()

@@ -168,3 +168,42 @@ def test_tc_message_blob_layout(sd):
     Wh1, Wu1 = sd[q + ".1.Wh"].double(), sd[q + ".1.Wu"].double()
     want = torch.cat([Wh1.t(), (Wh1 @ Wu1).t()]).float()
     assert torch.allclose(rec, want, rtol=2 ** -21, atol=1e-7)
+
+
+def _gloo_worker(rank, world, port, sizes, out_dir):
+    import os
+    import torch
+    import torch.distributed as dist
+    from pharmacoforge_b200.sharding import gather_results, shard_ranges
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = shard_ranges(sizes, world, pocket_atoms=[400, 250, 1500])[rank]
+        flat = [(p, i, n) for p, szs in enumerate(sizes) for i, n in enumerate(szs)]
+        # every graph of the shard contributes n rows tagged with its global graph id (stand-in for [x, h] rows)
+        rows = [torch.full((flat[gidx][2], 9), float(gidx)) for gidx in rng]
+        local = torch.cat(rows) if rows else torch.zeros(0, 9)
+        parts = gather_results(local)
+        if rank == 0:
+            torch.save([p.clone() for p in parts], os.path.join(out_dir, "gathered.pt"))
+        else:
+            assert parts is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gather_world_size_2_gloo(tmp_path):
+    """The N>1 sampling path on CPU: contiguous graph shards, no collective except the final gather to rank 0."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    sizes = [[3, 4, 5], [8], [6, 7, 3, 4]]
+    mp.spawn(_gloo_worker, args=(2, port, sizes, str(tmp_path)), nprocs=2, join=True)
+    parts = torch.load(os.path.join(str(tmp_path), "gathered.pt"))
+    got = torch.cat(parts)
+    want = torch.cat([torch.full((n, 9), float(g)) for g, n in enumerate(n for szs in sizes for n in szs)])
+    assert torch.equal(got, want)      # rank order == graph order: results concatenate without a permutation
