@@ -30,17 +30,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips (or the hint expires)
+  // instead of burning issue slots in a poll loop next to the epilogue warps that share its scheduler
   const uint32_t addr = smem_u32(bar);
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}\n" ::"r"(addr),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 
@@ -215,6 +217,21 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
+}
+
+// one lane of a converged warp (elect.sync): the compiler keeps the guarded tcgen05 issue on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {

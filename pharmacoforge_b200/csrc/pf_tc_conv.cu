@@ -21,6 +21,7 @@
 // cp.async.bulk.
 #include "pf_common.cuh"
 #include "pf_tc.cuh"
+#include <type_traits>
 
 namespace pf {
 namespace tcc {
@@ -81,8 +82,20 @@ struct Params {
   long long* trace;  // optional timeline of CTA 0 (pf_tc_trace): [4 roles][kTraceCap][2] = (tag, clock64)
 };
 
-__device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
-__device__ __forceinline__ float sigmoid_fast(float y) { return __fdividef(1.0f, 1.0f + __expf(-y)); }
+// sigma(y) = 1 / (1 + 2^(-y log2 e)) on the two MUFU ops with no range fix-up code: ex2.approx overflows to +inf for
+// y << 0 and rcp.approx(+inf) = +0, which is the correct limit (relative error ~2^-22, inside the fp32 parity bar)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float y) { return rcp_approx(1.0f + ex2_approx(y * -1.4426950408889634f)); }
+__device__ __forceinline__ float silu_fast(float y) { return y * sigmoid_fast(y); }
 
 // 16 fp32 values of row m -> fp16 (hi, lo) in the K-major SWIZZLE_NONE image of a [128 x 16] A operand:
 // byte (k/8)*2048 + (m/8)*128 + (m%8)*16 + (k%8)*2, hi image at +0, lo image at +4096.
@@ -110,6 +123,12 @@ __device__ __forceinline__ void slot_barrier(int T) { tc::named_bar_sync(1 + T, 
 
 // ------------------------------------------------------------------------------------------------ producer
 template <int MODE>
+__host__ __device__ constexpr int ring_uses_p(int pos) { return (Cfg<MODE>::kSlabsPerTile - pos + kRing - 1) / kRing; }
+
+// Slab i of the tile sequence goes to ring position i % kRing (see ring_uses / full_parity below).  Before the copy,
+// the previous occupant of the position must have been consumed by both tile slots: the `empty` barrier of a slot
+// flips once per use, so the n-th use overall waits for parity (n - 1) & 1.
+template <int MODE>
 __device__ void producer_role(const uint8_t* wblob, uint8_t* smem, uint64_t* bar_full, uint64_t* bar_empty,
                               uint64_t* bar_small, int my_tiles) {
   constexpr int kSlabsPerTile = Cfg<MODE>::kSlabsPerTile;
@@ -118,28 +137,64 @@ __device__ void producer_role(const uint8_t* wblob, uint8_t* smem, uint64_t* bar
 #pragma unroll
   for (int i = 0; i < Cfg<MODE>::kSmallBytes / 8192; ++i)
     tc::bulk_g2s(smem + kOffSmall + i * 8192, wblob + blob_small_off<MODE>() + i * 8192, 8192, bar_small);
-  const int total = ((my_tiles + 1) >> 1) * kSlabsPerTile;
-  for (int n = 0; n < total; ++n) {
-    const int slot = n % kRing;
-    if (n >= kRing) {  // the previous occupant of this ring slot must have been consumed by both tile slots
-      const int o = n - kRing;
-      const uint32_t par = (uint32_t)(o / kRing) & 1u;
-      tc::mbar_wait(&bar_empty[slot], par);
-      if (2 * (o / kSlabsPerTile) + 1 < my_tiles) tc::mbar_wait(&bar_empty[kRing + slot], par);
+  const int pairs = (my_tiles + 1) >> 1;
+#pragma unroll 1
+  for (int t = 0; t < pairs; ++t) {
+#pragma unroll
+    for (int i = 0; i < kSlabsPerTile; ++i) {
+      const int pos = i % kRing, u = i / kRing;
+      const int uses = ring_uses_p<MODE>(pos);
+      const int n = uses * t + u;  // uses of this position before this one
+      if (n >= 1) {
+        const uint32_t par = (uint32_t)(n - 1) & 1u;
+        const int tprev = u > 0 ? t : t - 1;  // tile pair of the previous use
+        tc::mbar_wait(&bar_empty[pos], par);
+        if (2 * tprev + 1 < my_tiles) tc::mbar_wait(&bar_empty[kRing + pos], par);
+      }
+      tc::mbar_expect_tx(&bar_full[pos], kSlab);
+      tc::bulk_g2s(smem + kOffRing + pos * kSlab, wblob + (size_t)i * kSlab, kSlab, &bar_full[pos]);
     }
-    tc::mbar_expect_tx(&bar_full[slot], kSlab);
-    tc::bulk_g2s(smem + kOffRing + slot * kSlab, wblob + (size_t)(n % kSlabsPerTile) * kSlab, kSlab, &bar_full[slot]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issuer
-// One issuing thread per tile slot (warps 16, 17): a slot's short jobs (V: 9 MMAs of N=32, G: 24 of N=16) are never
-// held back by the other slot's 27-33 N=128 MMAs being ISSUED, only by the few already queued in the tensor pipe.
+// One issuing WARP per tile slot (warps 16, 17).  The whole warp runs the control flow converged and the tcgen05
+// instructions are issued under elect.sync with descriptors advanced by adds: a single diverged lane that rebuilds its
+// descriptors per MMA is issue-bound at ~160 cycles per MMA whatever N is (scratch/mma_bench.cu), the converged form
+// reaches 77 (N = 128) / 41 (N = 32) / 36 (N = 16) cycles.
+// Ring bookkeeping shared by the producer and the issuers: slab i of a tile's sequence (i < kSlabsPerTile) always
+// lives in ring position i % kRing, so every position, TMEM column and barrier address in the unrolled issue code
+// is a compile-time constant; only the barrier parity depends on the tile-pair counter t, and only for positions
+// that are used an odd number of times per tile.
+template <int MODE>
+__host__ __device__ constexpr int ring_uses(int pos) {  // uses of ring position `pos` per tile
+  return (Cfg<MODE>::kSlabsPerTile - pos + kRing - 1) / kRing;
+}
+template <int MODE>
+__host__ __device__ constexpr int slab_base(int g) {  // first slab of GVP g in the tile's sequence
+  return g == 0 ? 0 : slab_base<MODE>(g - 1) + Cfg<MODE>::nslab(g - 1);
+}
+// parity of the `full` barrier for the use of slab i in tile pair t
+template <int MODE>
+__device__ __forceinline__ uint32_t full_parity(int i, uint32_t t) {
+  return ((ring_uses<MODE>(i % kRing) & 1 ? t : 0u) + (uint32_t)(i / kRing)) & 1u;
+}
+
 template <int MODE, bool HAS_V>
 __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint64_t* bar_empty,
-                         SlotBars* sb, uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles, long long* trace) {
+                         SlotBars* sb, uint64_t* bar_small, uint64_t* bar_stagger, volatile int* turn, int my_tiles,
+                         long long* trace_) {
   const int n_mine = (my_tiles + 1 - T) >> 1;
   if (n_mine == 0) return;
+  const bool lane0 = (threadIdx.x & 31) == 0;
+  long long* trace = lane0 ? trace_ : nullptr;
+  // S jobs (the long N = 128 MMA runs) of the two tile slots are issued strictly alternately -- slot 0 job j, slot 1
+  // job j, slot 0 job j + 1, ... -- so that they execute back to back on the tensor pipe instead of interleaved:
+  // one slot's accumulator completes a full job ahead of the other's, and the slots settle half a GVP apart (one on
+  // the CUDA cores while the other owns the tensor pipe) instead of marching in lockstep.  The order also keeps the
+  // two consumers of the shared weight ring within one job (<= 11 of 12 slabs) of each other.
+  const int n_other_jobs = ((my_tiles + T) >> 1) * Cfg<MODE>::kGvps;  // S jobs of the other slot
+  int job = 0;
   int tn = 0;
   constexpr uint32_t kI128 = tc::make_idesc_f16(128, 128);
   constexpr uint32_t kI32 = tc::make_idesc_f16(128, 32);
@@ -148,78 +203,114 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
   const uint32_t small_a = tc::smem_u32(smem + kOffSmall);
   const uint32_t stage = tc::smem_u32(smem + kOffStage) + T * kStage;
   const uint32_t regP = tmem + 256 * T, regQ = regP + 128;
+  // descriptors of the staged A operands and of the ring (16-byte units in the low word: advancing by `bytes >> 4`)
+  const uint64_t stage_hi = tc::make_smem_desc(stage, 2048, 128), stage_lo = tc::make_smem_desc(stage + 4096, 2048, 128);
+  const uint64_t ring_hi = tc::make_smem_desc(ring_a, 2048, 128), ring_lo = tc::make_smem_desc(ring_a + 4096, 2048, 128);
+  const uint64_t vec_hi = tc::make_smem_desc(small_a + Cfg<MODE>::kVecOff, 512, 128);
+  const uint64_t vec_lo = tc::make_smem_desc(small_a + Cfg<MODE>::kVecOff + 1024, 512, 128);
+  const uint64_t gate_hi = tc::make_smem_desc(small_a + kGateOff, 256, 128);
+  const uint64_t gate_lo = tc::make_smem_desc(small_a + kGateOff + 512, 256, 128);
   SlotBars& B = sb[T];
-  uint32_t p_vecA = 0, p_A = 0, p_F = 0, q = 0;
+  uint64_t* my_empty = bar_empty + T * kRing;
+  uint32_t p_vecA = 0, p_A = 0, p_F = 0;
   tc::mbar_wait(bar_small, 0);
-  for (int t = 0; t < n_mine; ++t) {
-#pragma unroll 1
-    for (int g = 0; g < Cfg<MODE>::kGvps; ++g) {
-      const uint32_t Areg = g == 1 ? regQ : regP;
-      const uint32_t Dreg = g == 1 ? regP : regQ;
-      if (MODE == 1 || HAS_V || g > 0) {  // ---- V_g: vector channels, A = staged V (hi, lo), B = [Wh | Wh.Wu] image
-        tc::mbar_wait(&B.vecA, p_vecA);
-        p_vecA ^= 1;
-        tc::fence_after_sync();
-        trace_ev(trace, 2 + T, tn, (g << 8) | 0x10);
-        const uint32_t bimg = small_a + Cfg<MODE>::kVecOff + g * 2048;
-        const uint64_t b_hi = tc::make_smem_desc(bimg, 512, 128), b_lo = tc::make_smem_desc(bimg + 1024, 512, 128);
+
+  auto gvp = [&](auto gc, const uint32_t t) {
+    constexpr int g = decltype(gc)::value;
+    const uint32_t Areg = g == 1 ? regQ : regP;
+    const uint32_t Dreg = g == 1 ? regP : regQ;
+    if (MODE == 1 || HAS_V || g > 0) {  // ---- V_g: vector channels, A = staged V (hi, lo), B = [Wh | Wh.Wu] image
+      tc::mbar_wait(&B.vecA, p_vecA);
+      p_vecA ^= 1;
+      tc::fence_after_sync();
+      trace_ev(trace, 2 + T, tn, (g << 8) | 0x10);
+      if (tc::elect_one()) {
+        const uint64_t b_hi = vec_hi + (uint64_t)(g * (2048 >> 4)), b_lo = vec_lo + (uint64_t)(g * (2048 >> 4));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const uint64_t a_hi = tc::make_smem_desc(stage + c * 8192, 2048, 128);
-          const uint64_t a_lo = tc::make_smem_desc(stage + c * 8192 + 4096, 2048, 128);
+          const uint64_t a_hi = stage_hi + (uint64_t)(c * (8192 >> 4)), a_lo = stage_lo + (uint64_t)(c * (8192 >> 4));
           tc::mma_ss(Dreg + 32 * c, a_hi, b_hi, kI32, 0);
           tc::mma_ss(Dreg + 32 * c, a_hi, b_lo, kI32, 1);
           tc::mma_ss(Dreg + 32 * c, a_lo, b_hi, kI32, 1);
         }
         tc::mma_commit(&B.vecD);
-        trace_ev(trace, 2 + T, tn, (g << 8) | 0x11);
       }
-      // ---- S_g: scalar features, one weight slab (K = 16) at a time
-      tc::mbar_wait(&B.A, p_A);
-      p_A ^= 1;
-      tc::fence_after_sync();
-      trace_ev(trace, 2 + T, tn, (g << 8) | 0x20);
-      const int nslab = Cfg<MODE>::nslab(g);
-      for (int k = 0; k < nslab; ++k, ++q) {
-        const uint32_t slot = q % kRing;
-        tc::mbar_wait(&bar_full[slot], (q / kRing) & 1u);
-        tc::fence_after_sync();
-        const uint32_t b = ring_a + slot * kSlab;
-        const uint64_t b_hi = tc::make_smem_desc(b, 2048, 128), b_lo = tc::make_smem_desc(b + 4096, 2048, 128);
+      __syncwarp();
+      trace_ev(trace, 2 + T, tn, (g << 8) | 0x11);
+    }
+    // ---- S_g: scalar features, one weight slab (K = 16) at a time
+    tc::mbar_wait(&B.A, p_A);
+    p_A ^= 1;
+    {
+      const int need = T == 0 ? 2 * job : 2 * job + 1;       // S jobs issued before this one in the global order
+      const bool has_pred = T == 0 ? (job >= 1 && job - 1 < n_other_jobs) : true;
+      if (has_pred)
+        while (*turn < need) __nanosleep(20);
+    }
+    tc::fence_after_sync();
+    trace_ev(trace, 2 + T, tn, (g << 8) | 0x20);
+    constexpr int nslab = Cfg<MODE>::nslab(g);
+#pragma unroll
+    for (int k = 0; k < nslab; ++k) {
+      constexpr int base = slab_base<MODE>(g);
+      const int i = base + k, pos = i % kRing;
+      tc::mbar_wait(&bar_full[pos], full_parity<MODE>(i, t));
+      if (tc::elect_one()) {
+        const uint64_t b_hi = ring_hi + (uint64_t)(pos * (kSlab >> 4)), b_lo = ring_lo + (uint64_t)(pos * (kSlab >> 4));
         if (k < 8) {
           const uint32_t a_hi = Areg + 16 * k, a_lo = a_hi + 8;
           tc::mma_ts(Dreg, a_hi, b_hi, kI128, k > 0);
           tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
           tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
         } else {
-          const uint32_t a = stage + (k - 8) * 8192;
-          const uint64_t a_hi = tc::make_smem_desc(a, 2048, 128), a_lo = tc::make_smem_desc(a + 4096, 2048, 128);
+          const uint64_t a_hi = stage_hi + (uint64_t)((k - 8) * (8192 >> 4)), a_lo = stage_lo + (uint64_t)((k - 8) * (8192 >> 4));
           tc::mma_ss(Dreg, a_hi, b_hi, kI128, 1);
           tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
           tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
         }
-        tc::mma_commit(&bar_empty[T * kRing + slot]);
+        tc::mma_commit(&my_empty[pos]);
+        if (k == nslab - 1) tc::mma_commit(&B.D);
       }
-      tc::mma_commit(&B.D);
-      if (T == 0 && t == 0 && g == 0) tc::mbar_arrive(bar_stagger);  // slot 1 starts half a phase behind slot 0
-      trace_ev(trace, 2 + T, tn, (g << 8) | 0x21);
-      // ---- G_g: vector gates from the new scalars (split in place in Dreg), output -> Areg[0:16)
-      tc::mbar_wait(&B.F, p_F);
-      p_F ^= 1;
-      tc::fence_after_sync();
-      trace_ev(trace, 2 + T, tn, (g << 8) | 0x30);
+      __syncwarp();
+    }
+    {
+      // slot 0's jobs of an unpartnered last tile count double so that the numbering above stays valid
+      const bool partner_has_job = T == 0 ? job < n_other_jobs : true;
+      if (lane0) {
+        __threadfence_block();
+        *turn = *turn + (partner_has_job ? 1 : 2);
+      }
+      ++job;
+      __syncwarp();
+    }
+    if (T == 0 && t == 0 && g == 0 && lane0) tc::mbar_arrive(bar_stagger);  // slot 1 starts half a phase behind slot 0
+    trace_ev(trace, 2 + T, tn, (g << 8) | 0x21);
+    // ---- G_g: vector gates from the new scalars (split in place in Dreg), output -> Areg[0:16)
+    tc::mbar_wait(&B.F, p_F);
+    p_F ^= 1;
+    tc::fence_after_sync();
+    trace_ev(trace, 2 + T, tn, (g << 8) | 0x30);
+    if (tc::elect_one()) {
+      const uint64_t g_hi = gate_hi + (uint64_t)(g * (8192 >> 4)), g_lo = gate_lo + (uint64_t)(g * (8192 >> 4));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const uint32_t bimg = small_a + kGateOff + g * 8192 + k * 1024;
-        const uint64_t b_hi = tc::make_smem_desc(bimg, 256, 128), b_lo = tc::make_smem_desc(bimg + 512, 256, 128);
+        const uint64_t b_hi = g_hi + (uint64_t)(k * (1024 >> 4)), b_lo = g_lo + (uint64_t)(k * (1024 >> 4));
         const uint32_t a_hi = Dreg + 16 * k, a_lo = a_hi + 8;
         tc::mma_ts(Areg, a_hi, b_hi, kI16, k > 0);
         tc::mma_ts(Areg, a_hi, b_lo, kI16, 1);
         tc::mma_ts(Areg, a_lo, b_hi, kI16, 1);
       }
       tc::mma_commit(&B.gate);
-      trace_ev(trace, 2 + T, tn, (g << 8) | 0x31);
     }
+    __syncwarp();
+    trace_ev(trace, 2 + T, tn, (g << 8) | 0x31);
+  };
+
+#pragma unroll 1
+  for (uint32_t t = 0; t < (uint32_t)n_mine; ++t) {
+    gvp(std::integral_constant<int, 0>{}, t);
+    gvp(std::integral_constant<int, 1>{}, t);
+    if constexpr (Cfg<MODE>::kGvps == 3) gvp(std::integral_constant<int, 2>{}, t);
   }
 }
 
@@ -677,6 +768,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   uint64_t* bar_small = bars + 3 * kRing + 12;
   uint64_t* bar_stagger = bars + 3 * kRing + 13;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  volatile int* s_turn = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = *p.n_tiles;
   const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -699,6 +791,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
       }
       tc::mbar_init(bar_small, 1);
       tc::mbar_init(bar_stagger, 1);
+      *s_turn = 0;
       tc::fence_mbar_init();
     }
   }
@@ -710,7 +803,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   if (warp < 16) {
     epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    if (lane == 0) mma_role<0, HAS_V>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, my_tiles, p.trace);
+    mma_role<0, HAS_V>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
     if (lane == 0) producer_role<0>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
@@ -1147,6 +1240,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const Nod
   uint64_t* bar_small = bars + 3 * kRing + 12;
   uint64_t* bar_stagger = bars + 3 * kRing + 13;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  volatile int* s_turn = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = (p.n_nodes + kRows - 1) / kRows;
   const int my_tiles = n_tiles > (long long)blockIdx.x ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
@@ -1169,6 +1263,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const Nod
       }
       tc::mbar_init(bar_small, 1);
       tc::mbar_init(bar_stagger, 1);
+      *s_turn = 0;
       tc::fence_mbar_init();
     }
   }
@@ -1180,7 +1275,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const Nod
   if (warp < 16) {
     node_epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    if (lane == 0) mma_role<1, true>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, my_tiles, p.trace);
+    mma_role<1, true>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
     if (lane == 0) producer_role<1>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }

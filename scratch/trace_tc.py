@@ -44,6 +44,7 @@ for r in range(4):
         if r < 2:
             ev.append((clk - t0, f"slot{r} epi g={tag >> 8} {names.get(tag & 0xff, hex(tag & 0xff))}"))
         else:
+            if 0x40 <= (tag & 0xff) < 0x50 and len(sys.argv) <= 3: continue
             ev.append((clk - t0, f"      MMA slot{r - 2} g={(tag >> 8) & 15} {mn.get(tag & 0xff, hex(tag & 0xff))}"))
 ev.sort()
 lim = int(sys.argv[2]) if len(sys.argv) > 2 else 130
