@@ -335,6 +335,57 @@ __device__ __forceinline__ void stage_store8(uint8_t* slab, int m, int kc, const
   *reinterpret_cast<uint4*>(a + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// Segmented mean over the rows of a tile staged in shared memory as buf[row][pitch] (fp32).  The 256 threads of a tile
+// slot are 16 column quads x 16 row groups of 8 rows; a thread owns the segments that START in its row group and sums
+// each of them to its end in row order (so the result does not depend on where the segment sits in the tile: the
+// means are bit-identical under any batch composition), four independent column accumulators per thread.
+// Segments are whole destinations: exactly one thread writes a destination's columns, no atomics race.  With
+// `accumulate` the mean is added to what earlier edge types left in the row (one red.add per address and launch).
+constexpr int kMeanPitch = 68;   // 64 columns + 4: 16-byte row stores and quad loads are bank-conflict free
+constexpr int kMeanPitchV = 52;  // 48 vector entries + 4
+__device__ __forceinline__ void segment_means(const float* buf, const int pitch, const int c4, const int rg,
+                                              const int nrows, const int nseg, const int* s_off, const int* s_rowseg,
+                                              const int* s_dst, float* out, const int out_pitch, const int accumulate) {
+  const int rbeg = 8 * rg;
+  if (rbeg != 0 && rbeg >= nrows) return;
+  const bool last = rbeg + 8 >= nrows;  // the last row group also takes the trailing empty segments
+  for (int j = rbeg == 0 ? 0 : s_rowseg[rbeg - 1] + 1; j < nseg; ++j) {
+    const int r0 = s_off[j];
+    if (!last && r0 >= rbeg + 8) break;
+    const int r1 = s_off[j + 1], cnt = r1 - r0;
+    if (accumulate && cnt == 0) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* b = buf + r0 * pitch + 4 * c4;
+    int r = r0;
+    for (; r + 4 <= r1; r += 4, b += 4 * pitch) {  // four row loads in flight, summed in row order
+      const float4 x0 = *reinterpret_cast<const float4*>(b), x1 = *reinterpret_cast<const float4*>(b + pitch),
+                   x2 = *reinterpret_cast<const float4*>(b + 2 * pitch), x3 = *reinterpret_cast<const float4*>(b + 3 * pitch);
+      acc.x = (((acc.x + x0.x) + x1.x) + x2.x) + x3.x;
+      acc.y = (((acc.y + x0.y) + x1.y) + x2.y) + x3.y;
+      acc.z = (((acc.z + x0.z) + x1.z) + x2.z) + x3.z;
+      acc.w = (((acc.w + x0.w) + x1.w) + x2.w) + x3.w;
+    }
+    for (; r < r1; ++r, b += pitch) {
+      const float4 x = *reinterpret_cast<const float4*>(b);
+      acc.x += x.x;
+      acc.y += x.y;
+      acc.z += x.z;
+      acc.w += x.w;
+    }
+    const float n = (float)(cnt > 0 ? cnt : 1);
+    acc.x /= n;
+    acc.y /= n;
+    acc.z /= n;
+    acc.w /= n;
+    float* o = out + (size_t)s_dst[j] * out_pitch;
+    if (accumulate) {
+      atomicAdd(reinterpret_cast<float4*>(o), acc);
+    } else {
+      *reinterpret_cast<float4*>(o) = acc;
+    }
+  }
+}
+
 // Two threads per edge row: half hh owns scalar columns [64 hh, 64 hh + 64) and vector channels [8 hh, 8 hh + 8).
 template <bool HAS_V>
 __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
@@ -635,25 +686,30 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         float keep[32];  // last GVP: fp32 copy of chunks 2, 3 for the second mean pass
         tc::tmem_ld16(Dreg + 16 * (4 * hh), r[0]);
         tc::wait_ld();
-        float* ab = reinterpret_cast<float*>(stage + hh * 16896);  // [128][33]
+        float* ab = reinterpret_cast<float*>(stage);  // mean staging [128][kMeanPitch]: 32 columns of each half per pass
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const int j = 4 * hh + j4;
           if (j4 < 3) tc::tmem_ld16(Dreg + 16 * (j + 1), r[(j4 + 1) & 1]);
           uint32_t hi[8], lo[8];
+          float fv[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float f0 = silu_fast(__uint_as_float(r[j4 & 1][2 * i]) + bf[16 * j + 2 * i]);
             const float f1 = silu_fast(__uint_as_float(r[j4 & 1][2 * i + 1]) + bf[16 * j + 2 * i + 1]);
             tc::split_pack_h(f0, f1, hi[i], lo[i]);
-            if (g == 2) {
-              if (j4 < 2) {
-                ab[et * 33 + 16 * j4 + 2 * i] = f0;
-                ab[et * 33 + 16 * j4 + 2 * i + 1] = f1;
-              } else {
-                keep[16 * (j4 - 2) + 2 * i] = f0;
-                keep[16 * (j4 - 2) + 2 * i + 1] = f1;
-              }
+            fv[2 * i] = f0;
+            fv[2 * i + 1] = f1;
+          }
+          if (g == 2) {
+            if (j4 < 2) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 16 * j4 + 4 * i) =
+                    make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) keep[16 * (j4 - 2) + i] = fv[i];
             }
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
@@ -664,28 +720,20 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::fence_before_sync();
         tc::mbar_arrive(&B.F);
         trace_ev(trace, T, tn, (g << 8) | 0x22);
-        if (g == 2) {  // segmented mean of the scalar messages, 32 columns per half and pass, through shared memory
+        if (g == 2) {  // segmented mean of the scalar messages, two passes of 64 columns through shared memory
 #pragma unroll 1
           for (int ps = 0; ps < 2; ++ps) {
             if (ps == 1) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) ab[et * 33 + i] = keep[i];
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 4 * i) =
+                    make_float4(keep[4 * i], keep[4 * i + 1], keep[4 * i + 2], keep[4 * i + 3]);
             }
             slot_barrier(T);
-            for (int jj = q; jj < nseg; jj += 4) {
-              const int r0 = s_off[jj], r1 = s_off[jj + 1], cnt = r1 - r0;
-              if (p.accumulate && cnt == 0) continue;
-              float acc = 0.f;   // rows summed in edge order (deterministic); loads of 4 rows in flight
-              int rr = r0;
-              for (; rr + 4 <= r1; rr += 4) {
-                const float a0 = ab[rr * 33 + lane], a1 = ab[(rr + 1) * 33 + lane], a2 = ab[(rr + 2) * 33 + lane],
-                            a3 = ab[(rr + 3) * 33 + lane];
-                acc = (((acc + a0) + a1) + a2) + a3;
-              }
-              for (; rr < r1; ++rr) acc += ab[rr * 33 + lane];
-              acc = acc / (float)(cnt > 0 ? cnt : 1);
-              float* o = p.agg_h + (size_t)s_dst[jj] * kHidden + 64 * hh + 32 * ps + lane;
-              *o = p.accumulate ? *o + acc : acc;
+            {
+              const int c4 = stid & 15;
+              float* out = p.agg_h + 64 * (c4 >> 3) + 32 * ps + 4 * (c4 & 7);
+              segment_means(ab, kMeanPitch, c4, stid >> 4, nrows, nseg, s_off, s_rowseg, s_dst, out, kHidden, p.accumulate);
             }
             slot_barrier(T);
           }
@@ -728,29 +776,19 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           tc::mbar_arrive(&B.vecA);
           trace_ev(trace, T, tn, (g << 8) | 0x32);
         } else {
-          float* ab = reinterpret_cast<float*>(stage);  // [128][49]
+          float* ab = reinterpret_cast<float*>(stage);  // [128][kMeanPitchV]
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) ab[et * 49 + 16 * c + 8 * hh + u] = Vu[8 * c + u];
+            for (int u4 = 0; u4 < 2; ++u4)
+              *reinterpret_cast<float4*>(ab + et * kMeanPitchV + 16 * c + 8 * hh + 4 * u4) =
+                  make_float4(Vu[8 * c + 4 * u4], Vu[8 * c + 4 * u4 + 1], Vu[8 * c + 4 * u4 + 2], Vu[8 * c + 4 * u4 + 3]);
           slot_barrier(T);
-          const int k = 32 * hh + lane;
-          if (k < kVRow) {
-            for (int jj = q; jj < nseg; jj += 4) {
-              const int r0 = s_off[jj], r1 = s_off[jj + 1], cnt = r1 - r0;
-              if (p.accumulate && cnt == 0) continue;
-              float acc = 0.f;
-              int rr = r0;
-              for (; rr + 4 <= r1; rr += 4) {
-                const float a0 = ab[rr * 49 + k], a1 = ab[(rr + 1) * 49 + k], a2 = ab[(rr + 2) * 49 + k],
-                            a3 = ab[(rr + 3) * 49 + k];
-                acc = (((acc + a0) + a1) + a2) + a3;
-              }
-              for (; rr < r1; ++rr) acc += ab[rr * 49 + k];
-              acc = acc / (float)(cnt > 0 ? cnt : 1);
-              float* o = p.agg_v + (size_t)s_dst[jj] * kVRow + k;
-              *o = p.accumulate ? *o + acc : acc;
-            }
+          {
+            const int c4 = stid & 15;
+            if (c4 < kVRow / 4)
+              segment_means(ab, kMeanPitchV, c4, stid >> 4, nrows, nseg, s_off, s_rowseg, s_dst, p.agg_v + 4 * c4, kVRow,
+                            p.accumulate);
           }
         }
       }
