@@ -142,6 +142,61 @@ __device__ __forceinline__ void split_pack_h(float x0, float x1, uint32_t& hi, u
   lo = pack_f16x2_sat(x0 - hf.x, x1 - hf.y);
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (Blackwell FADD2 / FMUL2)
+// Two fp32 lanes per instruction: the epilogues are issue-bound, not FP32-pipe-bound, so halving the instruction count
+// of the elementwise chains is a direct win.  A pair lives in one 64-bit register (even-aligned register pair).
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// (f0, f1) = SiLU((a0, a1) + (b0, b1)) and its fp16 (hi, lo) split: 6.5 instructions per element
+// (3 FADD2 + 2 FMUL2 + 4 MUFU + 2 F2FP + 2 HADD2.F32 per pair).  sigma(y) = 1 / (1 + 2^(-y log2 e)): ex2.approx
+// overflows to +inf for y << 0 and rcp.approx(+inf) = +0, the correct limit, so no range fix-up code is needed.
+__device__ __forceinline__ void silu_split2(uint32_t a0, uint32_t a1, uint64_t bias, float& f0, float& f1, uint32_t& hi,
+                                            uint32_t& lo) {
+  const uint64_t v = add2(pack2(__uint_as_float(a0), __uint_as_float(a1)), bias);
+  const uint64_t t = mul2(v, pack2(-1.4426950408889634f, -1.4426950408889634f));
+  float t0, t1;
+  unpack2(t, t0, t1);
+  const uint64_t d = add2(pack2(ex2_approx(t0), ex2_approx(t1)), pack2(1.0f, 1.0f));
+  float d0, d1;
+  unpack2(d, d0, d1);
+  const uint64_t f = mul2(v, pack2(rcp_approx(d0), rcp_approx(d1)));
+  unpack2(f, f0, f1);
+  hi = pack_f16x2_sat(f0, f1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  float l0, l1;
+  unpack2(sub2(f, pack2(hf.x, hf.y)), l0, l1);
+  lo = pack_f16x2_sat(l0, l1);
+}
+
 // ---------------------------------------------------------------- fp32 -> (hi, lo) bf16 split, packed pairs
 // x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|; word = {low half: element 2j, high half: element 2j+1}
 __device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {

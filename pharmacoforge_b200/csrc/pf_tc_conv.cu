@@ -59,7 +59,7 @@ constexpr int kCWhu0 = 452;   // (Wh0.Wu0)[0][u], u = 0..15
 constexpr int kCWhc16 = 468;  // Wh0[1+u][16], u = 0..15 (17th hidden channel)
 
 constexpr int kStage = 36864;  // per-slot staging: smem A operands (3 x 8 KB) / 8 transpose buffers / mean buffers
-constexpr int kMetaInts = 1552; // tile metadata (520 ints) + per-row exchange between the two column halves
+constexpr int kMetaInts = 2064; // tile metadata (520 ints) + per-row exchange between the column halves (1024) + segment records (512)
 constexpr int kOffRing = 0;
 constexpr int kOffSmall = kRing * kSlab;              // 98,304
 constexpr int kOffStage = kOffSmall + kSmallMax;      // 131,072
@@ -84,17 +84,7 @@ struct Params {
 
 // sigma(y) = 1 / (1 + 2^(-y log2 e)) on the two MUFU ops with no range fix-up code: ex2.approx overflows to +inf for
 // y << 0 and rcp.approx(+inf) = +0, which is the correct limit (relative error ~2^-22, inside the fp32 parity bar)
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sigmoid_fast(float y) { return rcp_approx(1.0f + ex2_approx(y * -1.4426950408889634f)); }
+__device__ __forceinline__ float sigmoid_fast(float y) { return tc::rcp_approx(1.0f + tc::ex2_approx(y * -1.4426950408889634f)); }
 __device__ __forceinline__ float silu_fast(float y) { return y * sigmoid_fast(y); }
 
 // 16 fp32 values of row m -> fp16 (hi, lo) in the K-major SWIZZLE_NONE image of a [128 x 16] A operand:
@@ -335,53 +325,72 @@ __device__ __forceinline__ void stage_store8(uint8_t* slab, int m, int kc, const
   *reinterpret_cast<uint4*>(a + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// Segmented mean over the rows of a tile staged in shared memory as buf[row][pitch] (fp32).  The 256 threads of a tile
-// slot are 16 column quads x 16 row groups of 8 rows; a thread owns the segments that START in its row group and sums
-// each of them to its end in row order (so the result does not depend on where the segment sits in the tile: the
-// means are bit-identical under any batch composition), four independent column accumulators per thread.
-// Segments are whole destinations: exactly one thread writes a destination's columns, no atomics race.  With
-// `accumulate` the mean is added to what earlier edge types left in the row (one red.add per address and launch).
+// Segmented mean over the rows of a tile staged in shared memory as buf[row][pitch] (fp32).  Work item = (segment,
+// 8 columns): the 256 threads of a tile slot are 8 column groups x 32 segments in flight; a segment's rows are
+// loaded eight at a time (all loads issued before the first add: shared-memory latency is paid once, not per row)
+// and summed in row order, so the result does not depend on where the segment sits in the tile -- the means are
+// bit-identical under any batch composition.  Segments are whole destinations: exactly one thread writes a
+// destination's columns, no atomics race.  With `accumulate` the mean is added to what earlier edge types left in the
+// row (one red.add per address and launch, hence still deterministic).  s_rec[j] = (first row, end row, dst, 1/count).
 constexpr int kMeanPitch = 68;   // 64 columns + 4: 16-byte row stores and quad loads are bank-conflict free
 constexpr int kMeanPitchV = 52;  // 48 vector entries + 4
-__device__ __forceinline__ void segment_means(const float* buf, const int pitch, const int c4, const int rg,
-                                              const int nrows, const int nseg, const int* s_off, const int* s_rowseg,
-                                              const int* s_dst, float* out, const int out_pitch, const int accumulate) {
-  const int rbeg = 8 * rg;
-  if (rbeg != 0 && rbeg >= nrows) return;
-  const bool last = rbeg + 8 >= nrows;  // the last row group also takes the trailing empty segments
-  for (int j = rbeg == 0 ? 0 : s_rowseg[rbeg - 1] + 1; j < nseg; ++j) {
-    const int r0 = s_off[j];
-    if (!last && r0 >= rbeg + 8) break;
-    const int r1 = s_off[j + 1], cnt = r1 - r0;
-    if (accumulate && cnt == 0) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* b = buf + r0 * pitch + 4 * c4;
-    int r = r0;
-    for (; r + 4 <= r1; r += 4, b += 4 * pitch) {  // four row loads in flight, summed in row order
-      const float4 x0 = *reinterpret_cast<const float4*>(b), x1 = *reinterpret_cast<const float4*>(b + pitch),
-                   x2 = *reinterpret_cast<const float4*>(b + 2 * pitch), x3 = *reinterpret_cast<const float4*>(b + 3 * pitch);
-      acc.x = (((acc.x + x0.x) + x1.x) + x2.x) + x3.x;
-      acc.y = (((acc.y + x0.y) + x1.y) + x2.y) + x3.y;
-      acc.z = (((acc.z + x0.z) + x1.z) + x2.z) + x3.z;
-      acc.w = (((acc.w + x0.w) + x1.w) + x2.w) + x3.w;
+// predicated 16-byte shared-memory load into pre-zeroed registers (the compiler turns the C++ form into a branch)
+__device__ __forceinline__ void lds128_if(float4& v, const float* ptr, bool pred) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}\n"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "r"(tc::smem_u32(ptr)), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void segment_means(const float* buf, const int pitch, const int c8, const int jfirst,
+                                              const int nseg, const int4* s_rec, float* out, const int out_pitch,
+                                              const int accumulate) {
+  for (int j = jfirst; j < nseg; j += 32) {
+    const int4 rec = s_rec[j];
+    const int r0 = rec.x, r1 = rec.y;
+    if (accumulate && r1 == r0) continue;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int r = r0; r < r1; r += 8) {
+      float4 x[8], y[8];
+      const float* b = buf + r * pitch + 8 * c8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        y[i] = x[i];
+        lds128_if(x[i], b + i * pitch, r + i < r1);
+        lds128_if(y[i], b + i * pitch + 4, r + i < r1);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a0.x += x[i].x;
+        a0.y += x[i].y;
+        a0.z += x[i].z;
+        a0.w += x[i].w;
+        a1.x += y[i].x;
+        a1.y += y[i].y;
+        a1.z += y[i].z;
+        a1.w += y[i].w;
+      }
     }
-    for (; r < r1; ++r, b += pitch) {
-      const float4 x = *reinterpret_cast<const float4*>(b);
-      acc.x += x.x;
-      acc.y += x.y;
-      acc.z += x.z;
-      acc.w += x.w;
-    }
-    const float n = (float)(cnt > 0 ? cnt : 1);
-    acc.x /= n;
-    acc.y /= n;
-    acc.z /= n;
-    acc.w /= n;
-    float* o = out + (size_t)s_dst[j] * out_pitch;
+    const float rc = __int_as_float(rec.w);
+    a0.x *= rc;
+    a0.y *= rc;
+    a0.z *= rc;
+    a0.w *= rc;
+    a1.x *= rc;
+    a1.y *= rc;
+    a1.z *= rc;
+    a1.w *= rc;
+    float* o = out + (size_t)rec.z * out_pitch;
     if (accumulate) {
-      atomicAdd(reinterpret_cast<float4*>(o), acc);
+      atomicAdd(reinterpret_cast<float4*>(o), a0);
+      atomicAdd(reinterpret_cast<float4*>(o) + 1, a1);
     } else {
-      *reinterpret_cast<float4*>(o) = acc;
+      *reinterpret_cast<float4*>(o) = a0;
+      *(reinterpret_cast<float4*>(o) + 1) = a1;
     }
   }
 }
@@ -403,6 +412,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   int* s_rowseg = s_dst + 128;                                           // [128]
   int* s_wsum = s_rowseg + 128;                                          // [4]
   float4* s_xch = reinterpret_cast<float4*>(s_wsum + 4);                 // [128][2]
+  int4* s_rec = reinterpret_cast<int4*>(s_xch + 256);                    // [128]
   const float* cst = reinterpret_cast<const float*>(smem + kOffSmall + kConstOff);
   SlotBars& B = sb[T];
   uint32_t par_vecD = 0, par_D = 0, par_gate = 0;
@@ -475,6 +485,8 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         for (int w = 0; w < 4; ++w) base += w < q ? s_wsum[w] : 0;
         s_off[et] = base + inc - c;
         if (et == 127) s_off[128] = base + inc;
+        if (et < nseg)
+          s_rec[et] = make_int4(base + inc - c, base + inc, cur_dst, __float_as_int(1.0f / (float)(c > 0 ? c : 1)));
       }
       slot_barrier(T);
       if (hh == 0 && et < nseg)
@@ -694,13 +706,9 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           uint32_t hi[8], lo[8];
           float fv[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float f0 = silu_fast(__uint_as_float(r[j4 & 1][2 * i]) + bf[16 * j + 2 * i]);
-            const float f1 = silu_fast(__uint_as_float(r[j4 & 1][2 * i + 1]) + bf[16 * j + 2 * i + 1]);
-            tc::split_pack_h(f0, f1, hi[i], lo[i]);
-            fv[2 * i] = f0;
-            fv[2 * i + 1] = f1;
-          }
+          for (int i = 0; i < 8; ++i)
+            tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                            fv[2 * i], fv[2 * i + 1], hi[i], lo[i]);
           if (g == 2) {
             if (j4 < 2) {
 #pragma unroll
@@ -730,12 +738,15 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
                     make_float4(keep[4 * i], keep[4 * i + 1], keep[4 * i + 2], keep[4 * i + 3]);
             }
             slot_barrier(T);
+            trace_ev(trace, T, tn, (g << 8) | (0x23 + 3 * ps));
             {
-              const int c4 = stid & 15;
-              float* out = p.agg_h + 64 * (c4 >> 3) + 32 * ps + 4 * (c4 & 7);
-              segment_means(ab, kMeanPitch, c4, stid >> 4, nrows, nseg, s_off, s_rowseg, s_dst, out, kHidden, p.accumulate);
+              const int c8 = stid & 7;
+              float* out = p.agg_h + 64 * (c8 >> 2) + 32 * ps + 8 * (c8 & 3);
+              segment_means(ab, kMeanPitch, c8, stid >> 3, nseg, s_rec, out, kHidden, p.accumulate);
             }
+            trace_ev(trace, T, tn, (g << 8) | (0x24 + 3 * ps));
             slot_barrier(T);
+            trace_ev(trace, T, tn, (g << 8) | (0x25 + 3 * ps));
           }
         }
       }
@@ -785,10 +796,9 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
                   make_float4(Vu[8 * c + 4 * u4], Vu[8 * c + 4 * u4 + 1], Vu[8 * c + 4 * u4 + 2], Vu[8 * c + 4 * u4 + 3]);
           slot_barrier(T);
           {
-            const int c4 = stid & 15;
-            if (c4 < kVRow / 4)
-              segment_means(ab, kMeanPitchV, c4, stid >> 4, nrows, nseg, s_off, s_rowseg, s_dst, p.agg_v + 4 * c4, kVRow,
-                            p.accumulate);
+            const int c8 = stid & 7;
+            if (c8 < kVRow / 8)
+              segment_means(ab, kMeanPitchV, c8, stid >> 3, nseg, s_rec, p.agg_v + 8 * c8, kVRow, p.accumulate);
           }
         }
       }
@@ -1099,9 +1109,9 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float f0 = silu_fast(__uint_as_float(r[j4 & 1][2 * i]) + bf[16 * j + 2 * i]);
-            const float f1 = silu_fast(__uint_as_float(r[j4 & 1][2 * i + 1]) + bf[16 * j + 2 * i + 1]);
-            tc::split_pack_h(f0, f1, hi[i], lo[i]);
+            float f0, f1;
+            tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                            f0, f1, hi[i], lo[i]);
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
           tc::tmem_st8(Dreg + 16 * j + 8, lo);
