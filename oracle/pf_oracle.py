@@ -361,6 +361,40 @@ def sample(sd, b: FlatBatch, noise: torch.Tensor, T: int, gamma: torch.Tensor, c
     return x0, h0, h0.argmax(dim=1), prot
 
 
+def forward_loss(sd, b: FlatBatch, x0: torch.Tensor, h0: torch.Tensor, t_int: torch.Tensor, eps_x: torch.Tensor,
+                 eps_h: torch.Tensor, T: int, gamma: torch.Tensor, cfg: dict, norm_const: float = 1.0,
+                 weighted_loss: bool = False, phase: str = "train"):
+    """PharmacophoreDiff.forward, pharmacodiff.py:162-243, eps parameterisation (dev.yml): normalise h_0 (:81-83),
+    remove the pharmacophore COM of x_0 from the complex (:178), noise with (t, eps) (:110-127), remove the COM of x_t,
+    predict, and form the two MSE losses and the four metrics.  t_int [B] in [0, T) and eps are injected."""
+    fb = b.pharm_b
+    h0 = h0 / norm_const
+    com0 = segment_mean(x0, fb, b.n_graphs)
+    x0 = x0 - com0[fb]
+    b.prot_x = b.prot_x - com0[b.prot_b]
+    t = t_int.float() / T
+    g_t = gamma_at(gamma, t, T)
+    alpha_t = torch.sqrt(torch.sigmoid(-g_t))[fb].view(-1, 1)
+    sigma_t = torch.sqrt(torch.sigmoid(g_t))[fb].view(-1, 1)
+    b.pharm_x = alpha_t * x0 + sigma_t * eps_x
+    b.pharm_h = alpha_t * h0 + sigma_t * eps_h
+    remove_pharm_com(b)
+    h_dyn, x_dyn = denoiser(sd, b, t, cfg)
+    h_loss = (eps_h - h_dyn).square().sum(dim=1)
+    x_loss = (eps_x - x_dyn).square().sum(dim=1)
+    h0_pred = (b.pharm_h - sigma_t * h_dyn) / alpha_t
+    x0_pred = (b.pharm_x - sigma_t * x_dyn) / alpha_t
+    w_metric = 1 - t[fb]
+    w_loss = w_metric if weighted_loss else torch.ones_like(w_metric)
+    losses = {phase + " pos loss": (x_loss * w_loss).sum() / eps_x.numel(),
+              phase + " feat loss": (h_loss * w_loss).sum() / eps_h.numel()}
+    sq = (x0_pred - x0).square().sum(dim=1)
+    hit = (h0_pred.argmax(dim=1) == h0.argmax(dim=1)).float()
+    metrics = {phase + " position error": sq.mean(), phase + " weighted position error": (w_metric * sq).mean(),
+               phase + " accuracy": hit.mean(), phase + " weighted accuracy": (w_metric * hit).mean()}
+    return losses, metrics
+
+
 def nominal_edge_evals(b: FlatBatch, n_ff: int, pf_k: int = 5, n_convs: int = 2) -> int:
     """Edges pushed through the message MLP by one denoiser call (metric M2)."""
     nf = int(b.pharm_ptr[-1])

@@ -168,6 +168,16 @@ class GraphBatch:
         self.dyn_n_tiles = torch.zeros(3, **i32)
         return self
 
+    def set_pharmacophores(self, x_0: torch.Tensor, h_0: torch.Tensor) -> "GraphBatch":
+        """Ground-truth pharmacophores of a training / validation batch: `g.nodes['pharm'].data['x_0' / 'h_0']` of the
+        reference (protein_pharm_dataset.py:238-243), node-major in graph order.  Only `PharmacophoreDiff.forward`
+        reads them; sampling ignores them."""
+        if x_0.shape != (self.n_pharm, 3) or h_0.shape[0] != self.n_pharm:
+            raise ValueError(f"expected x_0 [{self.n_pharm}, 3] and h_0 [{self.n_pharm}, F]")
+        self.pharm_x0 = x_0.to(self.device, torch.float32).contiguous()
+        self.pharm_h0 = h_0.to(self.device, torch.float32).contiguous()
+        return self
+
     # ------------------------------------------------------------------ reference-style accessors
     def batch_idxs(self):
         """unorganized_utils.get_batch_idxs: graph index of every node, per node type."""

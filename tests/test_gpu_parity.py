@@ -473,3 +473,27 @@ def test_degree_overflow_is_reported(env):
         g.check_status()
     g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev, tile_rows=128)
     g.check_status()                 # max_num_neighbors=100 always fits the 128-row tcgen05 tile
+
+
+def test_forward_loss_matches_reference(env, golden, sd, dyn_cfg):
+    """PharmacophoreDiff.forward (the training / validation objective, pharmacodiff.py:162-243) on the CUDA denoiser
+    against the reference's own forward (golden fixture) and the oracle, with the same injected (t, eps)."""
+    import pf_oracle as O
+    from pharmacoforge_b200.synthetic import make_pocket
+    g = golden("forward_loss.npz")
+    sizes = list(map(int, g["sizes"]))
+    pos, onehot = make_pocket(int(g["n_atoms"]), seed=int(g["pocket_seed"]))
+    gb = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [sizes], env.dev)
+    gb.set_pharmacophores(t(g["x0"]), t(g["h0"]))
+    losses, metrics = env.model.validation_step(gb, t_int=t(g["t_int"]), eps={"x": t(g["eps_x"]), "h": t(g["eps_h"])})
+    b = O.build_batch([(t(pos), t(onehot))], [sizes])
+    lo, mo = O.forward_loss(sd, b, t(g["x0"]), t(g["h0"]), t(g["t_int"]), t(g["eps_x"]), t(g["eps_h"]), 100,
+                            sd["gamma.gamma"], dyn_cfg, phase="val")
+    for k, v in {**lo, **mo}.items():
+        got = float({**losses, **metrics}[k])
+        ref = float(g[k.replace(" ", "_")])
+        tol = 2e-4 * max(1.0, abs(ref))   # sums of squares of eps errors that are each within 1e-4
+        assert abs(got - ref) <= tol and abs(got - float(v)) <= tol, (k, got, ref, float(v))
+    assert abs(float(losses["val total loss"]) - float(g["val_pos_loss"]) - float(g["val_feat_loss"])) < 1e-3
+    with pytest.raises(NotImplementedError):
+        env.model.training_step(gb)

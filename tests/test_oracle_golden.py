@@ -95,3 +95,16 @@ def test_full_reverse_diffusion(golden, sd, dyn_cfg):
     assert np.allclose(h0.numpy(), d["final_h"], rtol=1e-4, atol=1e-4)
     assert np.array_equal(types.numpy(), d["final_type"])
     assert np.allclose(prot.numpy(), d["final_prot"], rtol=1e-4, atol=1e-3)
+
+
+def test_forward_loss_matches_reference_forward(golden, sd, dyn_cfg):
+    """oracle.forward_loss against PharmacophoreDiff.forward of the reference run with injected (t, eps)
+    (oracle/make_golden_loss.py -> tests/golden/forward_loss.npz)."""
+    g = golden("forward_loss.npz")
+    pos, onehot = make_pocket(int(g["n_atoms"]), seed=int(g["pocket_seed"]))
+    b = O.build_batch([(t(pos), t(onehot))], [list(map(int, g["sizes"]))])
+    losses, metrics = O.forward_loss(sd, b, t(g["x0"]), t(g["h0"]), t(g["t_int"]), t(g["eps_x"]), t(g["eps_h"]), 100,
+                                     sd["gamma.gamma"], dyn_cfg, phase="val")
+    for k, v in {**losses, **metrics}.items():
+        ref = float(g[k.replace(" ", "_")])
+        assert abs(float(v) - ref) <= 1e-5 * max(1.0, abs(ref)), (k, float(v), ref)
