@@ -226,7 +226,13 @@ typedef struct PfSampleArgs {
   const float* noise_h;       /* device [n_steps][n_pharm][n_pharm_feats] */
   int32_t n_steps;
   uint32_t* dev_status;
+  /* PF_FLAG_SKIP_DEAD_WORK: do not compute what PharmRecGVP.forward (dynamics_gvp.py:84-92) never reads -- the
+   * protein-side outputs of the LAST conv layer (its pp and fp messages and its protein node update): only
+   * node_data['pharm'] of the last layer feeds the noise head.  eps_h / eps_x are bit-identical either way; the
+   * nominal (reference-equivalent) work is done when the flag is clear, which is the default. */
+  uint32_t flags;
 } PfSampleArgs;
+#define PF_FLAG_SKIP_DEAD_WORK 1u
 
 /* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the
  * timestep value of graph g.  Results in a->eps_h / a->eps_x. */

@@ -94,6 +94,7 @@ class PfSampleArgs(C.Structure):
         ("noise_x", C.c_void_p), ("noise_h", C.c_void_p),
         ("n_steps", C.c_int32),
         ("dev_status", C.c_void_p),
+        ("flags", C.c_uint32),
     ]
 
 

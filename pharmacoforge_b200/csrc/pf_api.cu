@@ -291,6 +291,9 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                          a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->w_msg_tc[l][1],
                          a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
   prof_end(kSitePF, as_stream(stream));
+    // exact dead-work elimination (opt-in): nothing reads the protein side of the last layer
+    const bool prot_side = !((a->flags & PF_FLAG_SKIP_DEAD_WORK) && l == a->n_convs - 1);
+    if (prot_side) {
     prof_begin(kSitePP, as_stream(stream));
     PF_TRY(edge_conv_any(tc, a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col,
                          a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->w_msg_tc[l][3],
@@ -301,15 +304,18 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                          a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2],
                          a->w_msg_tc[l][2], a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 1, stream));
   prof_end(kSiteFP, as_stream(stream));
+    }
     // node updates, in place (gvp.py:501-536)
     prof_begin(kSiteUpdPharm, as_stream(stream));
     PF_TRY(node_update_any(tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][0] : nullptr, a->pharm_hh, fv, a->pharm_agg_h,
                            a->pharm_agg_v, a->n_pharm, a->w_upd[l][0], a->n_upd_gvps, a->pharm_hh, a->pharm_v, stream));
   prof_end(kSiteUpdPharm, as_stream(stream));
+    if (prot_side) {
     prof_begin(kSiteUpdProt, as_stream(stream));
     PF_TRY(node_update_any(tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][1] : nullptr, a->prot_h, pv, a->prot_agg_h,
                            a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps, a->prot_h, a->prot_v, stream));
   prof_end(kSiteUpdProt, as_stream(stream));
+    }
   }
   prof_begin(kSiteNoise, as_stream(stream));
   PF_TRY(pf_noise_head(a->pharm_hh, a->pharm_v, a->n_pharm, a->w_noise, a->n_noise_gvps, a->n_pharm_feats, a->eps_h,

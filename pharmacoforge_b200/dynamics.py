@@ -200,6 +200,11 @@ class PharmRecDynamicsGVP(nn.Module):
                                           nn.LayerNorm(n_hidden_scalars))
         self.noise_predictor = PharmRecGVP(n_hidden_scalars, vector_size, n_pharm_scalars, n_convs, n_message_gvps,
                                            n_update_gvps, message_norm, n_noise_gvps, dropout)
+        # Opt-in exact dead-work elimination: the protein-side outputs of the last conv layer are never read
+        # (dynamics_gvp.py:84-92 feeds only node_data['pharm'] to the noise head), so their pp / fp messages and
+        # protein node update can be dropped without changing a bit of (eps_h, eps_x).  Off by default: the nominal
+        # path does the reference's full work.  Not a constructor argument (the reference signature is kept).
+        self.skip_dead_work = False
         self._packed: Optional[PackedWeights] = None
         self._packed_key = None
 
@@ -221,6 +226,7 @@ class PharmRecDynamicsGVP(nn.Module):
         if st is None or st.weights is not w or any(a is not b for a, b in zip(st.batch_buffers, cur)):
             st = _DeviceState(self, g, w)
             g._pf_state = st
+        st.args.flags = 1 if self.skip_dead_work else 0   # PF_FLAG_SKIP_DEAD_WORK
         return st
 
     # ------------------------------------------------------------------ forward

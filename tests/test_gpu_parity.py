@@ -497,3 +497,18 @@ def test_forward_loss_matches_reference(env, golden, sd, dyn_cfg):
     assert abs(float(losses["val total loss"]) - float(g["val_pos_loss"]) - float(g["val_feat_loss"])) < 1e-3
     with pytest.raises(NotImplementedError):
         env.model.training_step(gb)
+
+
+def test_dead_work_elimination_is_bit_exact(env):
+    """skip_dead_work drops the last layer's protein-side kernels (never read, dynamics_gvp.py:84-92): the sampled
+    pharmacophores must not change by a single bit."""
+    g, _ = env.build([(150, 21), (90, 22)], [[3, 6], [8, 4]])
+    noise = torch.randn(7, g.n_pharm, 9, generator=torch.Generator().manual_seed(5))
+    x_a, h_a = env.model.sample_given_receptor(g, noise=noise, n_steps=6, return_tensors=True)
+    g2, _ = env.build([(150, 21), (90, 22)], [[3, 6], [8, 4]])
+    env.model.dynamics.skip_dead_work = True
+    try:
+        x_b, h_b = env.model.sample_given_receptor(g2, noise=noise, n_steps=6, return_tensors=True)
+    finally:
+        env.model.dynamics.skip_dead_work = False
+    assert torch.equal(x_a, x_b) and torch.equal(h_a, h_b)
