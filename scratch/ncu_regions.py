@@ -1,7 +1,18 @@
 import csv, re, sys, collections
 csvp, sassp, kern = sys.argv[1:4]
-regions = [(112,133,"producer"),(139,224,"mma_role"),(277,310,"prefetch"),(311,357,"meta+xdiff"),(359,395,"gather_h"),(397,452,"gather_v+stage"),
-           (455,532,"EPI-A"),(534,575,"EPI-B"),(576,601,"mean_h"),(604,638,"EPI-C"),(639,666,"mean_v"),(670,720,"kernel")]
+SRC = open(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "..", "pharmacoforge_b200", "csrc", "pf_tc_conv.cu")).read().splitlines()
+def _ln(marker, start=0):
+    for i in range(start, len(SRC)):
+        if marker in SRC[i]: return i + 1
+    raise KeyError(marker)
+_m = [("producer", "__device__ void producer_role("), ("mma_role", "__device__ void mma_role("), ("mean_fn", "void lds128_if("),
+      ("epi_setup", "__device__ void epilogue_role("), ("meta+xdiff", "slot_barrier(T);  // everyone is done with the previous tile"),
+      ("gather_h", "// ---- gather h[src]"), ("gather_v+stage", "float Vu[24];"), ("EPI-A", "// ================= EPI-A"),
+      ("EPI-B", "// ================= EPI-B"), ("mean_h", "if (g == 2) {  // segmented mean of the scalar"),
+      ("EPI-C", "// ================= EPI-C"), ("mean_v", "float* ab = reinterpret_cast<float*>(stage);  // [128][kMeanPitchV]"),
+      ("kernel", "edge_conv_tc_kernel(const Params p)"), ("end", "// K4 on the tensor cores")]
+_l = [(n, _ln(k)) for n, k in _m]
+regions = [(_l[i][1], _l[i + 1][1] - 1, _l[i][0]) for i in range(len(_l) - 1)]
 def reg(l):
     for a,b,n in regions:
         if a<=l<=b: return n
