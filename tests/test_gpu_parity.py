@@ -330,6 +330,20 @@ def test_denoiser_config1_size_against_oracle(env):
     close(gx, wx, what="eps_x")
 
 
+def test_denoiser_large_pocket_config3_shape(env):
+    """configs[2] shape (large-pocket stress): 1,500-atom pockets, pharmacophore sizes up to 16, per-graph timesteps."""
+    g, b = env.build([(1500, 31), (1500, 32)], [[16, 3], [11]])
+    x, h, prot = random_state(b, 7, 6.0)
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    tt = torch.tensor([0.9, 0.13, 0.5])
+    wh, wx = env.O.denoiser(env.sd, b, tt, env.cfg)
+    gh, gx = env.model.dynamics(g, tt, None)
+    g.check_status()
+    close(gh, wh, what="eps_h")
+    close(gx, wx, what="eps_x")
+
+
 # ------------------------------------------------------------------------------------------------ K5b + loop
 def test_posterior_step_bit_exact(env):
     O = env.O
