@@ -241,6 +241,43 @@ int pf_sample_loop(const PfSampleArgs* a, void* stream);
 int pf_fill_f32(float* p, int64_t n, float v, void* stream);
 size_t pf_sample_args_size(void); /* sizeof(PfSampleArgs), for binding self-checks */
 
+/* ---- training path (PharmacophoreDiff.forward + backward, pharmacodiff.py:162-243) --------------------------------
+ * Differentiable primitives the reference's GVP (gvp.py:89-116), GVPLayerNorm (gvp.py:159-166) and GVPMultiEdgeConv
+ * (gvp.py:459-551) are composed of, forward and backward, fp32.  The host registers them as torch.library custom ops
+ * with register_autograd (pharmacoforge_b200/train_ops.py).  This path is unfused: per-edge tensors are materialised.
+ * Vectors are component-major [rows][3][channels].  Kernels whose name says `accumulate` / `+=` add into the output. */
+/* C[M][N] (ldc) (+)= A(m,k) B(k,n) (+ bias[n]); A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs]: nn.Linear forward
+ * (gvp.py:76-79, 84), its dgrad and wgrad, and the Wh / Wu contractions (gvp.py:99-100).  split_k > 1 splits K over
+ * CTAs (atomic accumulation: the wgrad reductions over all edges). */
+int pf_train_sgemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                   int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate, int32_t split_k,
+                   void* stream);
+int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* stream); /* out[n] += sum_m x[m][n] (bias grad) */
+/* SiLU (gvp.py:78): dy == NULL -> out = silu(x); else out = dy * silu'(x) */
+int pf_train_silu(const float* x, const float* dy, float* out, int64_t n, void* stream);
+/* vector gating (gvp.py:108-114): dout == NULL -> out = act(gate) * Vu; else dgate (in out_or_dgate) and dVu */
+int pf_train_gate(const float* gate, const float* vu, const float* dout, float* out_or_dgate, float* dvu, int64_t rows,
+                  int32_t U, int32_t act_sigmoid, void* stream);
+/* _norm_no_nan over the 3 components (gvp.py:12-19, 102): dsh == NULL -> out = sh [rows][H]; else out = dVh */
+int pf_train_vecnorm(const float* vh, const float* dsh, float* out, int64_t rows, int32_t H, void* stream);
+/* nn.LayerNorm(D), eps 1e-5 (gvp.py:157, 161; encoders dynamics_gvp.py:107-117); stats = (mean, rstd) per row */
+int pf_train_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int64_t rows,
+                           int32_t D, void* stream);
+int pf_train_layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, float* dx, float* dw,
+                           float* db, int64_t rows, int32_t D, void* stream); /* dw, db += */
+/* vector half of GVPLayerNorm (gvp.py:163-165): dout == NULL -> out = v / vn; else out = dv */
+int pf_train_vecln(const float* v, const float* dout, float* out, int64_t rows, int32_t U, void* stream);
+/* edges.src[...] (gvp.py:543-545): backward == 0 -> out[e] = x[idx[e]]; else dx[idx[e]] += dout[e] (atomic) */
+int pf_train_gather(const float* x_or_dout, const int32_t* idx, float* out_or_dx, int64_t E, int32_t D, int32_t backward,
+                    void* stream);
+/* fn.mean per destination + cross-etype sum (gvp.py:488-497) over destination-sorted message rows: segment s = rows
+ * [ptr[s], ptr[s+1]) -> node seg_dst[s] (NULL: s).  backward == 0 -> out[node] += mean; else dmsg[row] = dout[node]/cnt */
+int pf_train_segmean(const float* msg_or_dout, const int32_t* ptr, const int32_t* seg_dst, float* out_or_dmsg,
+                     int32_t n_seg, int32_t D, int32_t backward, void* stream);
+/* x_diff [E][3] and rbf [E][16] of every edge (gvp.py:472-480); inputs are data: no backward */
+int pf_train_edge_geom(const float* src_x, const float* dst_x, const int32_t* src, const int32_t* dst, float* xdiff,
+                       float* rbf, int64_t E, void* stream);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------------
  * pf_launch_count: kernels this library has launched in this process so far.
  * pf_profile_enable(n): n > 0 arms CUDA-event pairs around every kernel site of pf_denoiser /

@@ -47,14 +47,36 @@ def main():
 
     torch.randn, torch.randint = fake_randn, fake_randint
     try:
-        with torch.no_grad():
-            losses, metrics = model.forward(gb, phase="val")
+        # eval mode = dropout off (the only train / eval difference of the reference forward); gradients stay enabled so
+        # that the same call also yields the reference's own backward (pharmacodiff.py:265-297: total = pos + feat loss)
+        losses, metrics = model.forward(gb, phase="val")
     finally:
         torch.randn, torch.randint = real_randn, real_randint
+    total = torch.stack(list(losses.values())).sum()
+    model.zero_grad()
+    total.backward()
+    names, norms, sums, dead = [], [], [], []
+    keep = {}
+    for k, p_ in sorted(model.named_parameters()):
+        if p_.numel() == 0:
+            continue
+        if p_.grad is None:
+            dead.append(k)
+            continue
+        names.append(k)
+        norms.append(float(p_.grad.double().norm()))
+        sums.append(float(p_.grad.double().sum()))
+        if k in ("dynamics.pharm_encoder.0.weight", "dynamics.noise_predictor.noise_predictor.to_scalar_output.weight",
+                 "dynamics.noise_predictor.conv_layers.0.edge_message_fns.prot_pp_prot.0.Wh",
+                 "dynamics.noise_predictor.conv_layers.1.node_update_fns.pharm.1.scalar_to_vector_gates.bias",
+                 "dynamics.noise_predictor.conv_layers.0.message_layer_norms.prot.feat_norm.weight"):
+            keep["grad__" + k] = p_.grad.detach().numpy().copy()
     out = {k.replace(" ", "_"): np.asarray(float(v), dtype=np.float64) for k, v in {**losses, **metrics}.items()}
-    print(out)
+    print(out, len(names), "params with grad;", len(dead), "without (dead last-layer protein side):", dead[:3], "...")
     np.savez(os.path.join(MG.GOLD, "forward_loss.npz"), pocket_seed=5, n_atoms=120, sizes=np.asarray(sizes),
-             x0=x0.numpy(), h0=h0.numpy(), t_int=t_int.numpy(), eps_h=eps_h.numpy(), eps_x=eps_x.numpy(), **out)
+             x0=x0.numpy(), h0=h0.numpy(), t_int=t_int.numpy(), eps_h=eps_h.numpy(), eps_x=eps_x.numpy(),
+             grad_names=np.asarray(names), grad_norms=np.asarray(norms), grad_sums=np.asarray(sums),
+             dead_params=np.asarray(dead), **keep, **out)
 
 
 if __name__ == "__main__":

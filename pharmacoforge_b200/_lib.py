@@ -50,6 +50,19 @@ SIGNATURES = {
     "pf_launch_count": (C.c_int64, []),
     "pf_profile_enable": (C.c_int, [C.c_int32]),
     "pf_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32]),
+    "pf_train_sgemm": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                 C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, STREAM]),
+    "pf_train_colsum": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
+    "pf_train_silu": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, STREAM]),
+    "pf_train_gate": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, STREAM]),
+    "pf_train_vecnorm": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
+    "pf_train_layernorm_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
+    "pf_train_layernorm_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32,
+                                         STREAM]),
+    "pf_train_vecln": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
+    "pf_train_gather": (C.c_int, [c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, STREAM]),
+    "pf_train_segmean": (C.c_int, [c_f32p, c_i32p, c_i32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, STREAM]),
+    "pf_train_edge_geom": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, C.c_int64, STREAM]),
     "pf_denoiser": (C.c_int, [C.c_void_p, STREAM]),
     "pf_sample_loop": (C.c_int, [C.c_void_p, STREAM]),
 }

@@ -1,0 +1,453 @@
+// Differentiable primitives of the TRAINING path (PharmacophoreDiff.forward + backward, pharmacodiff.py:162-243):
+// forward and backward kernels of the operations GVP / GVPLayerNorm / GVPMultiEdgeConv are composed of (gvp.py:89-116,
+// 159-166, 459-551), fp32 throughout.  The Python host (pharmacoforge_b200/train_ops.py) registers them as
+// torch.library custom ops with register_autograd and composes the reference's graph out of them; this first training
+// path is UNFUSED (every per-edge tensor is materialised, like the reference) -- the fused tcgen05 kernels serve
+// sampling and evaluation.  Vector features are component-major: [rows][3][channels].
+#include "pf_common.cuh"
+
+namespace pf {
+namespace train {
+
+// ------------------------------------------------------------------------------------------------ strided SGEMM
+// C[M][N] (row-major, ldc) (+)= A(m, k) * B(k, n) (+ bias[n]); A(m, k) = A[m * a_rs + k * a_cs], B(k, n) = B[k * b_rs +
+// n * b_cs].  One kernel covers y = x W^T + b, dx = dy W and dW = dy^T x.  64 x 64 tile, K step 16, 256 threads, 4 x 4
+// outputs per thread; gridDim.z > 1 splits K and accumulates with atomicAdd into a zeroed / accumulating C.
+constexpr int kTM = 64, kTN = 64, kTK = 16;
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                    const float* __restrict__ bias, float* __restrict__ C, int M, int N,
+                                                    int K, long long a_rs, long long a_cs, long long b_rs,
+                                                    long long b_cs, int ldc, int accumulate, int k_chunk) {
+  __shared__ float sA[kTK][kTM + 4];
+  __shared__ float sB[kTK][kTN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(K, k_begin + k_chunk);
+  const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;
+  float acc[4][4] = {};
+  for (int k0 = k_begin; k0 < k_end; k0 += kTK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // 64 x 16 elements of A and of B, 4 per thread each
+      const int e = tid + 256 * i;
+      {
+        // A tile: pick the index order that makes consecutive threads walk the unit-stride dimension
+        const int m = a_cs == 1 ? e / kTK : e % kTM, k = a_cs == 1 ? e % kTK : e / kTM;
+        const int gm = m0 + m, gk = k0 + k;
+        sA[k][m] = (gm < M && gk < k_end) ? A[gm * a_rs + gk * a_cs] : 0.f;
+      }
+      {
+        const int n = b_cs == 1 ? e % kTN : e / kTK, k = b_cs == 1 ? e / kTN : e % kTK;
+        const int gn = n0 + n, gk = k0 + k;
+        sB[k][n] = (gn < N && gk < k_end) ? B[gk * b_rs + gn * b_cs] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[k][tm]);
+      const float4 b = *reinterpret_cast<const float4*>(&sB[k][tn]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + tm + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tn + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr && blockIdx.z == 0) v += bias[gn];
+      float* c = C + (size_t)gm * ldc + gn;
+      if (gridDim.z > 1)
+        atomicAdd(c, v);
+      else
+        *c = accumulate ? *c + v : v;
+    }
+  }
+}
+
+// column sums of a row-major [M][N] matrix (bias gradients), accumulated with atomicAdd into out[N]
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += x[r * N + n];
+  atomicAdd(out + n, s);
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = silu_f(x[i]);
+}
+__global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float s = sigmoid_f(x[i]);
+    dx[i] = dy[i] * s * (1.0f + x[i] * (1.0f - s));
+  }
+}
+
+// Vout[m][c][u] = act(gate[m][u]) * Vu[m][c][u], act = sigmoid (GVP default) or identity (last noise GVP)
+__global__ void gate_fwd_kernel(const float* __restrict__ gate, const float* __restrict__ vu, float* __restrict__ out,
+                                long long rows, int U, int act_sigmoid) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 3 * U) return;
+  const long long m = i / (3 * U);
+  const int u = (int)(i % U);
+  const float g = gate[m * U + u];
+  out[i] = (act_sigmoid ? sigmoid_f(g) : g) * vu[i];
+}
+__global__ void gate_bwd_kernel(const float* __restrict__ gate, const float* __restrict__ vu,
+                                const float* __restrict__ dout, float* __restrict__ dgate, float* __restrict__ dvu,
+                                long long rows, int U, int act_sigmoid) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * U) return;
+  const long long m = i / U;
+  const int u = (int)(i % U);
+  const float g = gate[i];
+  const float a = act_sigmoid ? sigmoid_f(g) : g;
+  const float da = act_sigmoid ? a * (1.0f - a) : 1.0f;
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long long j = (m * 3 + c) * U + u;
+    dvu[j] = a * dout[j];
+    dot = fmaf(dout[j], vu[j], dot);
+  }
+  dgate[i] = da * dot;
+}
+
+// sh[m][h] = sqrt(max(sum_c Vh[m][c][h]^2, 1e-8))   (_norm_no_nan, gvp.py:12-19)
+__global__ void vecnorm_fwd_kernel(const float* __restrict__ vh, float* __restrict__ sh, long long rows, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  const long long m = i / H;
+  const int h = (int)(i % H);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = vh[(m * 3 + c) * H + h];
+    s = fmaf(v, v, s);
+  }
+  sh[i] = sqrtf(fmaxf(s, 1e-8f));
+}
+__global__ void vecnorm_bwd_kernel(const float* __restrict__ vh, const float* __restrict__ dsh, float* __restrict__ dvh,
+                                   long long rows, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  const long long m = i / H;
+  const int h = (int)(i % H);
+  float v[3], s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    v[c] = vh[(m * 3 + c) * H + h];
+    s = fmaf(v[c], v[c], s);
+  }
+  const float k = s > 1e-8f ? dsh[i] / sqrtf(s) : 0.f;  // the clamp has zero gradient below eps
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dvh[(m * 3 + c) * H + h] = k * v[c];
+}
+
+// ------------------------------------------------------------------------------------------------ layer norms
+// nn.LayerNorm(D) with affine parameters, eps 1e-5; one warp per row.  Saves mean / rstd for the backward.
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ b, float* __restrict__ y, float* __restrict__ stats,
+                                     long long rows, int D) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + r * D;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s += xr[i];
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float d = xr[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + 1e-5f);
+  for (int i = lane; i < D; i += 32) y[r * D + i] = (xr[i] - mean) * rstd * w[i] + b[i];
+  if (lane == 0) {
+    stats[2 * r] = mean;
+    stats[2 * r + 1] = rstd;
+  }
+}
+// dx per row; dw / db accumulated over rows with atomicAdd (one partial per warp-row)
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ stats, const float* __restrict__ dy,
+                                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                     long long rows, int D) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float xh = (x[r * D + i] - mean) * rstd;
+    const float g = dy[r * D + i] * w[i];
+    s1 += g;
+    s2 = fmaf(g, xh, s2);
+    atomicAdd(dw + i, dy[r * D + i] * xh);
+    atomicAdd(db + i, dy[r * D + i]);
+  }
+  s1 = warp_sum(s1) / D;
+  s2 = warp_sum(s2) / D;
+  for (int i = lane; i < D; i += 32) {
+    const float xh = (x[r * D + i] - mean) * rstd;
+    dx[r * D + i] = rstd * (dy[r * D + i] * w[i] - s1 - xh * s2);
+  }
+}
+
+// GVPLayerNorm on vectors (gvp.py:163-165): out = v / vn, vn = sqrt(mean_u(max(|v_u|^2, 1e-8)) + 1e-5) + 1e-5.
+// One thread per row ([3][U], U <= 32).
+__global__ void vecln_fwd_kernel(const float* __restrict__ v, float* __restrict__ out, long long rows, int U) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const float* p = v + m * 3 * U;
+  float acc = 0.f;
+  for (int u = 0; u < U; ++u) {
+    const float n = p[u] * p[u] + p[U + u] * p[U + u] + p[2 * U + u] * p[2 * U + u];
+    acc += fmaxf(n, 1e-8f);
+  }
+  const float vn = sqrtf(acc / U + 1e-5f) + 1e-5f;
+  for (int i = 0; i < 3 * U; ++i) out[m * 3 * U + i] = p[i] / vn;
+}
+__global__ void vecln_bwd_kernel(const float* __restrict__ v, const float* __restrict__ dout, float* __restrict__ dv,
+                                 long long rows, int U) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const float* p = v + m * 3 * U;
+  const float* g = dout + m * 3 * U;
+  float acc = 0.f, dot = 0.f;
+  for (int u = 0; u < U; ++u) {
+    const float n = p[u] * p[u] + p[U + u] * p[U + u] + p[2 * U + u] * p[2 * U + u];
+    acc += fmaxf(n, 1e-8f);
+  }
+  for (int i = 0; i < 3 * U; ++i) dot = fmaf(g[i], p[i], dot);
+  const float root = sqrtf(acc / U + 1e-5f);
+  const float vn = root + 1e-5f;
+  // d vn / d v[c][u] = [|v_u|^2 > 1e-8] * v[c][u] / (U * root)
+  const float k = dot / (vn * vn) / (U * root);
+  for (int u = 0; u < U; ++u) {
+    const float n = p[u] * p[u] + p[U + u] * p[U + u] + p[2 * U + u] * p[2 * U + u];
+    const float live = n > 1e-8f ? k : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dv[m * 3 * U + c * U + u] = g[c * U + u] / vn - live * p[c * U + u];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ graph data movement
+// out[e][:] = x[idx[e]][:]  /  dx[idx[e]][:] += dout[e][:]   (edges.src[...], gvp.py:543-545)
+__global__ void gather_fwd_kernel(const float* __restrict__ x, const int* __restrict__ idx, float* __restrict__ out,
+                                  long long E, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * D) return;
+  const long long e = i / D;
+  out[i] = x[(long long)idx[e] * D + (i % D)];
+}
+__global__ void gather_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ idx, float* __restrict__ dx,
+                                  long long E, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * D) return;
+  const long long e = i / D;
+  atomicAdd(dx + (long long)idx[e] * D + (i % D), dout[i]);
+}
+// mean of the message rows of every destination (fn.mean + cross_reducer sum, gvp.py:488-497): edges are sorted by
+// destination, segment s = rows [ptr[s], ptr[s+1]) aggregates onto node seg_dst[s] (or s); out is ACCUMULATED into.
+__global__ void segmean_fwd_kernel(const float* __restrict__ msg, const int* __restrict__ ptr,
+                                   const int* __restrict__ seg_dst, float* __restrict__ out, int n_seg, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_seg * D) return;
+  const int s = (int)(i / D), d = (int)(i % D);
+  const int r0 = ptr[s], r1 = ptr[s + 1];
+  if (r1 == r0) return;
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += msg[(long long)r * D + d];
+  const int node = seg_dst ? seg_dst[s] : s;
+  out[(long long)node * D + d] += acc / (float)(r1 - r0);
+}
+__global__ void segmean_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ ptr,
+                                   const int* __restrict__ seg_dst, float* __restrict__ dmsg, int n_seg, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_seg * D) return;
+  const int s = (int)(i / D), d = (int)(i % D);
+  const int r0 = ptr[s], r1 = ptr[s + 1];
+  if (r1 == r0) return;
+  const int node = seg_dst ? seg_dst[s] : s;
+  const float g = dout[(long long)node * D + d] / (float)(r1 - r0);
+  for (int r = r0; r < r1; ++r) dmsg[(long long)r * D + d] = g;
+}
+// x_diff / rbf of every edge (gvp.py:472-480); inputs are data, there is no backward
+__global__ void edge_geom_kernel(const float* __restrict__ src_x, const float* __restrict__ dst_x,
+                                 const int* __restrict__ src, const int* __restrict__ dst, float* __restrict__ xdiff,
+                                 float* __restrict__ rbf, long long E) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int s = src[e], d = dst[e];
+  const float dx = src_x[3 * s] - dst_x[3 * d], dy = src_x[3 * s + 1] - dst_x[3 * d + 1],
+              dz = src_x[3 * s + 2] - dst_x[3 * d + 2];
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  const float dist = sqrtf(fmaxf(d2, 1e-8f)) + 1e-8f;
+  xdiff[3 * e] = dx / dist;
+  xdiff[3 * e + 1] = dy / dist;
+  xdiff[3 * e + 2] = dz / dist;
+#pragma unroll
+  for (int k = 0; k < kRbf; ++k) {
+    const float z = (dist - (float)k) / 0.9375f;
+    rbf[e * kRbf + k] = expf(-(z * z));
+  }
+}
+
+}  // namespace train
+}  // namespace pf
+
+using namespace pf;
+namespace T = pf::train;
+
+static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" int pf_train_sgemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                              int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate,
+                              int32_t split_k, void* stream) {
+  PF_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0 && ldc >= N, "pf_train_sgemm: arguments");
+  if (M == 0 || N == 0) return PF_OK;
+  int splits = split_k < 1 ? 1 : split_k;
+  int chunk = ((K + splits - 1) / splits + T::kTK - 1) / T::kTK * T::kTK;
+  if (chunk < T::kTK) chunk = T::kTK;
+  splits = K > 0 ? (K + chunk - 1) / chunk : 1;
+  if (splits > 1 && !accumulate) {
+    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, as_stream(stream));
+    if (e != cudaSuccess) {
+      set_error("pf_train_sgemm: memset: %s", cudaGetErrorString(e));
+      return PF_ERR_LAUNCH;
+    }
+  }
+  dim3 grid((N + T::kTN - 1) / T::kTN, (M + T::kTM - 1) / T::kTM, splits);
+  T::sgemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate,
+                                                      chunk);
+  PF_CHECK_LAUNCH("pf_train_sgemm");
+  return PF_OK;
+}
+
+extern "C" int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* stream) {
+  PF_CHECK_ARG(x && out && M >= 0 && N > 0, "pf_train_colsum: arguments");
+  if (M == 0) return PF_OK;
+  const int ysplit = (int)(M / 4096 > 64 ? 64 : (M / 4096 > 0 ? M / 4096 : 1));
+  dim3 grid((N + 127) / 128, ysplit);
+  T::colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, out, M, N);
+  PF_CHECK_LAUNCH("pf_train_colsum");
+  return PF_OK;
+}
+
+extern "C" int pf_train_silu(const float* x, const float* dy, float* out, int64_t n, void* stream) {
+  PF_CHECK_ARG(x && out && n >= 0, "pf_train_silu: arguments");
+  if (n == 0) return PF_OK;
+  if (dy == nullptr)
+    T::silu_fwd_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
+  else
+    T::silu_bwd_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(x, dy, out, n);
+  PF_CHECK_LAUNCH("pf_train_silu");
+  return PF_OK;
+}
+
+extern "C" int pf_train_gate(const float* gate, const float* vu, const float* dout, float* out_or_dgate, float* dvu,
+                             int64_t rows, int32_t U, int32_t act_sigmoid, void* stream) {
+  PF_CHECK_ARG(gate && vu && out_or_dgate && rows >= 0 && U > 0, "pf_train_gate: arguments");
+  if (rows == 0) return PF_OK;
+  if (dout == nullptr) {
+    T::gate_fwd_kernel<<<blocks_for(rows * 3 * U, 256), 256, 0, as_stream(stream)>>>(gate, vu, out_or_dgate, rows, U,
+                                                                                   act_sigmoid);
+  } else {
+    PF_CHECK_ARG(dvu != nullptr, "pf_train_gate: dvu");
+    T::gate_bwd_kernel<<<blocks_for(rows * U, 256), 256, 0, as_stream(stream)>>>(gate, vu, dout, out_or_dgate, dvu, rows,
+                                                                               U, act_sigmoid);
+  }
+  PF_CHECK_LAUNCH("pf_train_gate");
+  return PF_OK;
+}
+
+extern "C" int pf_train_vecnorm(const float* vh, const float* dsh, float* out, int64_t rows, int32_t H, void* stream) {
+  PF_CHECK_ARG(vh && out && rows >= 0 && H > 0, "pf_train_vecnorm: arguments");
+  if (rows == 0) return PF_OK;
+  if (dsh == nullptr)
+    T::vecnorm_fwd_kernel<<<blocks_for(rows * H, 256), 256, 0, as_stream(stream)>>>(vh, out, rows, H);
+  else
+    T::vecnorm_bwd_kernel<<<blocks_for(rows * H, 256), 256, 0, as_stream(stream)>>>(vh, dsh, out, rows, H);
+  PF_CHECK_LAUNCH("pf_train_vecnorm");
+  return PF_OK;
+}
+
+extern "C" int pf_train_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats,
+                                      int64_t rows, int32_t D, void* stream) {
+  PF_CHECK_ARG(x && w && b && y && stats && rows >= 0 && D > 0, "pf_train_layernorm_fwd: arguments");
+  if (rows == 0) return PF_OK;
+  T::layernorm_fwd_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(x, w, b, y, stats, rows, D);
+  PF_CHECK_LAUNCH("pf_train_layernorm_fwd");
+  return PF_OK;
+}
+extern "C" int pf_train_layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, float* dx,
+                                      float* dw, float* db, int64_t rows, int32_t D, void* stream) {
+  PF_CHECK_ARG(x && w && stats && dy && dx && dw && db && rows >= 0 && D > 0, "pf_train_layernorm_bwd: arguments");
+  if (rows == 0) return PF_OK;
+  T::layernorm_bwd_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(x, w, stats, dy, dx, dw, db, rows, D);
+  PF_CHECK_LAUNCH("pf_train_layernorm_bwd");
+  return PF_OK;
+}
+
+extern "C" int pf_train_vecln(const float* v, const float* dout, float* out, int64_t rows, int32_t U, void* stream) {
+  PF_CHECK_ARG(v && out && rows >= 0 && U > 0, "pf_train_vecln: arguments");
+  if (rows == 0) return PF_OK;
+  if (dout == nullptr)
+    T::vecln_fwd_kernel<<<blocks_for(rows, 128), 128, 0, as_stream(stream)>>>(v, out, rows, U);
+  else
+    T::vecln_bwd_kernel<<<blocks_for(rows, 128), 128, 0, as_stream(stream)>>>(v, dout, out, rows, U);
+  PF_CHECK_LAUNCH("pf_train_vecln");
+  return PF_OK;
+}
+
+extern "C" int pf_train_gather(const float* x_or_dout, const int32_t* idx, float* out_or_dx, int64_t E, int32_t D,
+                               int32_t backward, void* stream) {
+  PF_CHECK_ARG(x_or_dout && idx && out_or_dx && E >= 0 && D > 0, "pf_train_gather: arguments");
+  if (E == 0) return PF_OK;
+  if (!backward)
+    T::gather_fwd_kernel<<<blocks_for(E * D, 256), 256, 0, as_stream(stream)>>>(x_or_dout, idx, out_or_dx, E, D);
+  else
+    T::gather_bwd_kernel<<<blocks_for(E * D, 256), 256, 0, as_stream(stream)>>>(x_or_dout, idx, out_or_dx, E, D);
+  PF_CHECK_LAUNCH("pf_train_gather");
+  return PF_OK;
+}
+
+extern "C" int pf_train_segmean(const float* msg_or_dout, const int32_t* ptr, const int32_t* seg_dst, float* out_or_dmsg,
+                                int32_t n_seg, int32_t D, int32_t backward, void* stream) {
+  PF_CHECK_ARG(msg_or_dout && ptr && out_or_dmsg && n_seg >= 0 && D > 0, "pf_train_segmean: arguments");
+  if (n_seg == 0) return PF_OK;
+  if (!backward)
+    T::segmean_fwd_kernel<<<blocks_for((long long)n_seg * D, 256), 256, 0, as_stream(stream)>>>(msg_or_dout, ptr, seg_dst,
+                                                                                              out_or_dmsg, n_seg, D);
+  else
+    T::segmean_bwd_kernel<<<blocks_for((long long)n_seg * D, 256), 256, 0, as_stream(stream)>>>(msg_or_dout, ptr, seg_dst,
+                                                                                              out_or_dmsg, n_seg, D);
+  PF_CHECK_LAUNCH("pf_train_segmean");
+  return PF_OK;
+}
+
+extern "C" int pf_train_edge_geom(const float* src_x, const float* dst_x, const int32_t* src, const int32_t* dst,
+                                  float* xdiff, float* rbf, int64_t E, void* stream) {
+  PF_CHECK_ARG(src_x && dst_x && src && dst && xdiff && rbf && E >= 0, "pf_train_edge_geom: arguments");
+  if (E == 0) return PF_OK;
+  T::edge_geom_kernel<<<blocks_for(E, 256), 256, 0, as_stream(stream)>>>(src_x, dst_x, src, dst, xdiff, rbf, E);
+  PF_CHECK_LAUNCH("pf_train_edge_geom");
+  return PF_OK;
+}

@@ -296,56 +296,68 @@ class PharmacophoreDiff(nn.Module):
             end += len(szs)
         return out
 
-    @torch.no_grad()
     def forward(self, g: GraphBatch, phase: str = "train", t_int: Optional[torch.Tensor] = None,
                 eps: Optional[Dict[str, torch.Tensor]] = None):
-        """The training / validation objective of pharmacodiff.py:162-243 (eps parameterisation) on the CUDA
-        denoiser: returns (losses, metrics) with the reference's keys.  `g` carries the ground truth set by
+        """The training / validation objective of pharmacodiff.py:162-243 (eps parameterisation): returns
+        (losses, metrics) with the reference's keys.  `g` carries the ground truth set by
         `GraphBatch.set_pharmacophores(x_0, h_0)`; `t_int` ([B] integer timesteps in [0, T)) and `eps` ({'x': [Nf,3],
         'h': [Nf,F]}) inject the reference's `torch.randint` / `torch.randn` draws (h is drawn before x,
         pharmacodiff.py:189-192) for parity runs.
 
-        Forward only: the backward kernels are not built yet, so the returned tensors carry no autograd graph, and
-        the dynamics refuse to run in training mode with dropout > 0 (a `training_step` needs both)."""
+        In training mode with gradients enabled the eps prediction runs through the differentiable custom ops of
+        `train_ops.py` (`train_graph.dynamics_forward`: hand-written forward + backward kernels, training-mode dropout),
+        so the returned losses carry an autograd graph onto the reference-named parameters (which must live on the GPU).
+        Otherwise (eval / no_grad) it runs the fused sampling kernels."""
         if getattr(g, "pharm_x0", None) is None:
             raise ValueError("forward() needs the ground-truth pharmacophores: call g.set_pharmacophores(x_0, h_0)")
         dev, T = g.device, self.n_timesteps
         B, fb = g.n_graphs, g.batch_idxs()["pharm"]
-        if t_int is None:
-            t_int = torch.randint(0, T, size=(B,), device=dev)
-        t = t_int.to(dev).float() / T
-        if eps is None:
-            eps = {"h": torch.randn(g.n_pharm, self.n_pharm_feats, device=dev),
-                   "x": torch.randn(g.n_pharm, 3, device=dev)}
-        eps_x, eps_h = eps["x"].to(dev).float(), eps["h"].to(dev).float()
-        h0 = g.pharm_h0 / self.pharm_feat_norm_constant                      # normalize, :81-83
-        x0 = g.pharm_x0.clone()
-        com0 = ops.segment_mean3(x0, g.pharm_ptr)                             # com_removal(pharm_feat='x_0'), :178
-        ops.segment_shift3(x0, g.pharm_ptr, com0, -1.0)
-        ops.segment_shift3(g.prot_x, g.prot_ptr, com0, -1.0)
-        gamma_t = self.gamma(t.to(self.gamma.gamma.device)).to(dev)
-        alpha_t = self.alpha(gamma_t)[fb][:, None]
-        sigma_t = self.sigma(gamma_t)[fb][:, None]
-        self.dynamics.bind(g)                                                 # allocates g.pharm_h at the model width
-        g.pharm_x.copy_(alpha_t * x0 + sigma_t * eps_x)                       # noised_representation, :110-127
-        g.pharm_h.copy_(alpha_t * h0 + sigma_t * eps_h)
-        com_t = ops.segment_mean3(g.pharm_x, g.pharm_ptr)
-        ops.segment_shift3(g.pharm_x, g.pharm_ptr, com_t, -1.0)
-        ops.segment_shift3(g.prot_x, g.prot_ptr, com_t, -1.0)
-        h_dyn, x_dyn = self.dynamics(g, t)
+        differentiable = self.training and torch.is_grad_enabled()
+        with torch.no_grad():
+            if t_int is None:
+                t_int = torch.randint(0, T, size=(B,), device=dev)
+            t = t_int.to(dev).float() / T
+            if eps is None:
+                eps = {"h": torch.randn(g.n_pharm, self.n_pharm_feats, device=dev),
+                       "x": torch.randn(g.n_pharm, 3, device=dev)}
+            eps_x, eps_h = eps["x"].to(dev).float(), eps["h"].to(dev).float()
+            h0 = g.pharm_h0 / self.pharm_feat_norm_constant                   # normalize, :81-83
+            x0 = g.pharm_x0.clone()
+            com0 = ops.segment_mean3(x0, g.pharm_ptr)                          # com_removal(pharm_feat='x_0'), :178
+            ops.segment_shift3(x0, g.pharm_ptr, com0, -1.0)
+            ops.segment_shift3(g.prot_x, g.prot_ptr, com0, -1.0)
+            gamma_t = self.gamma(t.to(self.gamma.gamma.device)).to(dev)
+            alpha_t = self.alpha(gamma_t)[fb][:, None]
+            sigma_t = self.sigma(gamma_t)[fb][:, None]
+            if g.pharm_h is None or g.pharm_h.shape[1] != self.n_pharm_feats:
+                g.pharm_h = torch.zeros(max(g.n_pharm, 1), self.n_pharm_feats, device=dev)
+            g.pharm_x.copy_(alpha_t * x0 + sigma_t * eps_x)                    # noised_representation, :110-127
+            g.pharm_h.copy_(alpha_t * h0 + sigma_t * eps_h)
+            com_t = ops.segment_mean3(g.pharm_x, g.pharm_ptr)
+            ops.segment_shift3(g.pharm_x, g.pharm_ptr, com_t, -1.0)
+            ops.segment_shift3(g.prot_x, g.prot_ptr, com_t, -1.0)
+        if differentiable:
+            if not next(self.dynamics.parameters()).is_cuda:
+                raise RuntimeError("training needs the model parameters on the GPU: call model.to(g.device)")
+            from . import train_graph
+            h_dyn, x_dyn = train_graph.dynamics_forward(self.dynamics, g, t, training=True)
+        else:
+            with torch.no_grad():
+                h_dyn, x_dyn = self.dynamics(g, t)
         g.check_status()
         h_loss = (eps_h - h_dyn).square().sum(dim=1)
         x_loss = (eps_x - x_dyn).square().sum(dim=1)
-        h0_pred = (g.pharm_h - sigma_t * h_dyn) / alpha_t
-        x0_pred = (g.pharm_x - sigma_t * x_dyn) / alpha_t
         w_metric = 1 - t[fb]
         w_loss = w_metric if self.weighted_loss else torch.ones_like(w_metric)
         losses = {phase + " pos loss": (x_loss * w_loss).sum() / eps_x.numel(),
                   phase + " feat loss": (h_loss * w_loss).sum() / eps_h.numel()}
-        sq = (x0_pred - x0).square().sum(dim=1)
-        hit = (h0_pred.argmax(dim=1) == h0.argmax(dim=1)).float()
-        metrics = {phase + " position error": sq.mean(), phase + " weighted position error": (w_metric * sq).mean(),
-                   phase + " accuracy": hit.mean(), phase + " weighted accuracy": (w_metric * hit).mean()}
+        with torch.no_grad():
+            h0_pred = (g.pharm_h - sigma_t * h_dyn) / alpha_t
+            x0_pred = (g.pharm_x - sigma_t * x_dyn) / alpha_t
+            sq = (x0_pred - x0).square().sum(dim=1)
+            hit = (h0_pred.argmax(dim=1) == h0.argmax(dim=1)).float()
+            metrics = {phase + " position error": sq.mean(), phase + " weighted position error": (w_metric * sq).mean(),
+                       phase + " accuracy": hit.mean(), phase + " weighted accuracy": (w_metric * hit).mean()}
         return losses, metrics
 
     def validation_step(self, g: GraphBatch, batch_idx: int = 0, **inject):
@@ -358,7 +370,21 @@ class PharmacophoreDiff(nn.Module):
                                                     metrics[phase + " weighted accuracy"])
         return losses, metrics
 
-    def training_step(self, g: GraphBatch, batch_idx: int = 0):
-        raise NotImplementedError("training_step (pharmacodiff.py:265-297) needs the backward kernels of the edge / "
-                                  "node / noise-head kernels, which are not built yet; forward() and validation_step() "
-                                  "compute the same loss without gradients")
+    def training_step(self, g: GraphBatch, batch_idx: int = 0, **inject):
+        """pharmacodiff.py:265-297 without the Lightning logging / periodic sampling: the total loss (pos + feat) of one
+        batch, carrying the autograd graph (call `.backward()` on it), plus the loss and metric dicts."""
+        phase = "train"
+        losses, metrics = self.forward(g, phase=phase, **inject)
+        losses[phase + " total loss"] = torch.stack(list(losses.values())).sum()
+        metrics[phase + " total error"] = metrics[phase + " position error"] + 1 - metrics[phase + " accuracy"]
+        metrics[phase + " weighted total error"] = (metrics[phase + " weighted position error"] + 1 -
+                                                    metrics[phase + " weighted accuracy"])
+        return losses[phase + " total loss"], losses, metrics
+
+    def configure_optimizers(self):
+        """pharmacodiff.py:254-263: Adam(base_lr, weight_decay) + ReduceLROnPlateau from lr_scheduler_config."""
+        cfg = self.lr_scheduler_config or {}
+        opt = torch.optim.Adam(self.parameters(), lr=cfg.get("base_lr", 1e-4), weight_decay=cfg.get("weight_decay", 0.0))
+        sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, **cfg.get("reducelronplateau", {}))
+        return {"optimizer": opt, "lr_scheduler": {"scheduler": sched, "monitor": cfg.get("monitor"),
+                                                   "interval": cfg.get("interval"), "frequency": cfg.get("frequency")}}

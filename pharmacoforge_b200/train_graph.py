@@ -1,0 +1,137 @@
+"""Training-mode forward of `PharmRecDynamicsGVP` composed of the differentiable custom ops in `train_ops.py`.
+
+The graph mirrors the reference modules line by line -- GVP.forward (gvp.py:89-116), GVPLayerNorm (gvp.py:159-166),
+GVPDropout (gvp.py:121-156), GVPMultiEdgeConv.forward / message (gvp.py:459-551), NoisePredictionBlock
+(dynamics_gvp.py:37-42), the encoders and PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185) -- and reads the
+parameters straight from the `nn.Module`s of `dynamics.py`, so `loss.backward()` leaves `.grad` on the reference-named
+parameters.  Every arithmetic node is a hand-written CUDA kernel with a hand-written backward; torch does views,
+concatenation, residual adds and mask generation.  The per-step graph comes from the same K2 kernel as sampling.
+Vectors are component-major [rows, 3, channels].
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import train_ops as T
+from .batch import GraphBatch
+
+
+def gvp_forward(m, feats: torch.Tensor, vec: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GVP.forward (gvp.py:89-116) on (feats [M, n], vec [M, 3, v])."""
+    M = feats.shape[0]
+    vi, h = m.Wh.shape
+    vo = m.Wu.shape[1]
+    Vh = T.linear(vec.reshape(M * 3, vi), m.Wh.t().contiguous(), None)       # einsum 'b v c, v h -> b h c'
+    Vu = T.linear(Vh, m.Wu.t().contiguous(), None)                           # einsum 'b h c, h u -> b u c'
+    sh = T.vecnorm(Vh.view(M, 3, h))
+    lin = m.to_feats_out[0]
+    f = T.silu(T.linear(torch.cat([feats, sh], dim=1), lin.weight, lin.bias))
+    gates = T.linear(f, m.scalar_to_vector_gates.weight, m.scalar_to_vector_gates.bias)
+    vout = T.gate(gates, Vu.view(M, 3, vo), isinstance(m.vectors_activation, nn.Sigmoid))
+    return f, vout
+
+
+def gvp_layernorm(m, feats, vec):
+    """GVPLayerNorm.forward (gvp.py:159-166)."""
+    return T.layernorm(feats, m.feat_norm.weight, m.feat_norm.bias), T.vecln(vec)
+
+
+def gvp_dropout(m, feats, vec, training: bool):
+    """GVPDropout (gvp.py:148-156): nn.Dropout on scalars; whole 3-vectors dropped together (gvp.py:121-146)."""
+    p = float(m.feat_dropout.p)
+    if not training or p == 0.0:
+        return feats, vec
+    keep = 1.0 - p
+    fmask = torch.bernoulli(torch.full_like(feats, keep)) / keep
+    vmask = torch.bernoulli(torch.full((vec.shape[0], 1, vec.shape[2]), keep, device=vec.device)) / keep
+    return feats * fmask, vec * vmask
+
+
+def encoder(seq, x):
+    """nn.Sequential(Linear, SiLU, LayerNorm) (dynamics_gvp.py:107-117)."""
+    return T.layernorm(T.silu(T.linear(x, seq[0].weight, seq[0].bias)), seq[2].weight, seq[2].bias)
+
+
+def build_edges(g: GraphBatch) -> Dict[str, dict]:
+    """Destination-sorted edge lists of the four edge types as int32 tensors: src, dst (per edge), ptr (segment
+    offsets into the edge list), seg_dst (node of each segment, None = segment index), n_dst."""
+    dev = g.device
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    k, n = g.pf_k, g.n_pharm
+    dyn = g.dynamic_edges()
+    out = {}
+    pp_dst = torch.repeat_interleave(torch.arange(g.n_prot, device=dev), g.pp_cnt.long())
+    out["pp"] = dict(src=i32(g.pp_col), dst=i32(pp_dst), ptr=i32(g.pp_rowptr), seg_dst=None, n_dst=g.n_prot,
+                     src_nt="prot", dst_nt="prot")
+    for name, cnt in (("ff", g.ff_cnt), ("pf", g.pf_cnt)):
+        ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(cnt[:n].long(), 0)])
+        s, d = dyn[name]
+        out[name] = dict(src=i32(s), dst=i32(d), ptr=i32(ptr), seg_dst=None, n_dst=n,
+                         src_nt="pharm" if name == "ff" else "prot", dst_nt="pharm")
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(g.fp_seg_cnt[:k * n].long(), 0)])
+    s, d = dyn["fp"]
+    out["fp"] = dict(src=i32(s), dst=i32(d), ptr=i32(ptr), seg_dst=i32(g.fp_seg_dst[:k * n]), n_dst=g.n_prot,
+                     src_nt="pharm", dst_nt="prot")
+    return out
+
+
+def conv_forward(conv, feats, edges, geom, training: bool):
+    """GVPMultiEdgeConv.forward (gvp.py:459-538) for message_norm='mean'.  feats[ntype] = (h [N,128], v [N,3,16])."""
+    agg = {}
+    for name in ("ff", "pf", "fp", "pp"):                         # reference etype order (dynamics_gvp.py:46-54)
+        e = edges[name]
+        key = f"{e['src_nt']}_{name}_{e['dst_nt']}"
+        h_src, v_src = feats[e["src_nt"]]
+        xd, rbf = geom[name]
+        sca = torch.cat([T.gather(h_src, e["src"]), rbf], dim=1)                               # gvp.py:545
+        vec = torch.cat([xd.unsqueeze(2), T.gather(v_src, e["src"])], dim=2)                    # gvp.py:543
+        for m in conv.edge_message_fns[key]:
+            sca, vec = gvp_forward(m, sca, vec)
+        a_h = T.segmean(sca, e["ptr"], e["seg_dst"], e["n_dst"])                                # fn.mean, gvp.py:488-497
+        a_v = T.segmean(vec, e["ptr"], e["seg_dst"], e["n_dst"])
+        if e["dst_nt"] in agg:                                                                  # cross_reducer="sum"
+            agg[e["dst_nt"]] = (agg[e["dst_nt"]][0] + a_h, agg[e["dst_nt"]][1] + a_v)
+        else:
+            agg[e["dst_nt"]] = (a_h, a_v)
+    out = {}
+    for nt in ("pharm", "prot"):
+        h, v = feats[nt]
+        m_h, m_v = gvp_dropout(conv.dropout, agg[nt][0], agg[nt][1], training)                  # norm_value = 1.0
+        h, v = gvp_layernorm(conv.message_layer_norms[nt], h + m_h, v + m_v)
+        r_h, r_v = h, v
+        for m in conv.node_update_fns[nt]:
+            r_h, r_v = gvp_forward(m, r_h, r_v)
+        r_h, r_v = gvp_dropout(conv.dropout, r_h, r_v, training)
+        out[nt] = gvp_layernorm(conv.update_layer_norms[nt], h + r_h, v + r_v)
+    return out
+
+
+def dynamics_forward(dyn, g: GraphBatch, t: torch.Tensor, training: bool = True):
+    """PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185) with an autograd graph: (eps_h [Nf, F], eps_x [Nf, 3]).
+    g.pharm_x / g.pharm_h hold (x_t, h_t); t [B] is the timestep value per graph."""
+    dev = g.device
+    ops.dyn_graph(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, float(dyn.graph_cutoffs["ff"]), g.ff_max_nbrs, g.pf_k,
+                  g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt, g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt, g.fp_col,
+                  g.status)
+    edges = build_edges(g)
+    x = {"pharm": g.pharm_x, "prot": g.prot_x}
+    geom = {n: T.edge_geom(x[e["src_nt"]], x[e["dst_nt"]], e["src"], e["dst"]) for n, e in edges.items()}
+    bi = g.batch_idxs()
+    t = t.to(dev).float()
+    h_f = encoder(dyn.pharm_encoder, torch.cat([g.pharm_h, t[bi["pharm"]][:, None]], dim=1).contiguous())
+    h_p = encoder(dyn.prot_encoder, torch.cat([g.prot_feats, t[bi["prot"]][:, None]], dim=1).contiguous())
+    vs = dyn.vector_size
+    feats = {"pharm": (h_f, torch.zeros(g.n_pharm, 3, vs, device=dev)),
+             "prot": (h_p, torch.zeros(g.n_prot, 3, vs, device=dev))}
+    for conv in dyn.noise_predictor.conv_layers:
+        feats = conv_forward(conv, feats, edges, geom, training)
+    head = dyn.noise_predictor.noise_predictor
+    sca, vec = feats["pharm"]
+    for m in head.gvps:
+        sca, vec = gvp_forward(m, sca, vec)
+    eps_h = T.linear(sca, head.to_scalar_output.weight, head.to_scalar_output.bias)
+    return eps_h, vec.reshape(vec.shape[0], 3)

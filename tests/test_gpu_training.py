@@ -1,0 +1,201 @@
+"""Training path on the GPU: every differentiable custom op (forward + backward kernels) against a plain PyTorch fp32
+reference of the same op, and the end-to-end gradients of PharmacophoreDiff.training_step against the reference's own
+backward (golden fixture) and the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(a, b, rtol=2e-4, what=""):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max())
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+def check_op(fn, ref, inputs, what):
+    """fn / ref take the same tensors; compares outputs and the gradients of a random cotangent w.r.t. every
+    floating-point input that requires grad."""
+    a = [x.clone().requires_grad_(x.is_floating_point()) if torch.is_tensor(x) else x for x in inputs]
+    b = [x.clone().requires_grad_(x.is_floating_point()) if torch.is_tensor(x) else x for x in inputs]
+    ya, yb = fn(*a), ref(*b)
+    close(ya, yb, what=what + " fwd")
+    cot = torch.randn_like(yb)
+    ya.backward(cot)
+    yb.backward(cot)
+    for i, (p, q) in enumerate(zip(a, b)):
+        if torch.is_tensor(q) and q.is_floating_point():
+            assert p.grad is not None, (what, i)
+            close(p.grad, q.grad, what=f"{what} grad[{i}]")
+
+
+@pytest.fixture(scope="module")
+def T():
+    from pharmacoforge_b200 import train_ops
+    return train_ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).cuda()
+
+
+@pytest.mark.parametrize("M,K,N,bias", [(1, 7, 128, True), (200, 161, 128, True), (1000, 144, 128, True),
+                                        (999, 17, 17, False), (3001, 128, 16, True), (70000, 12, 128, True)])
+def test_linear(T, M, K, N, bias):
+    x, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    b = rnd(N, seed=3) if bias else None
+    check_op(lambda x, w, *b: T.linear(x, w, b[0] if b else None), lambda x, w, *b: torch.nn.functional.linear(x, w, *b),
+             [x, w] + ([b] if bias else []), f"linear {M}x{K}x{N}")
+
+
+def test_silu_gate_vecnorm(T):
+    x = rnd(777, 128, seed=4, scale=3.0)
+    check_op(T.silu, torch.nn.functional.silu, [x], "silu")
+    g, vu = rnd(333, 16, seed=5, scale=2.0), rnd(333, 3, 16, seed=6)
+    check_op(lambda g, v: T.gate(g, v, True), lambda g, v: torch.sigmoid(g)[:, None, :] * v, [g, vu], "gate sigmoid")
+    g1, vu1 = rnd(50, 1, seed=7), rnd(50, 3, 1, seed=8)
+    check_op(lambda g, v: T.gate(g, v, False), lambda g, v: g[:, None, :] * v, [g1, vu1], "gate identity")
+    vh = rnd(500, 3, 17, seed=9)
+    vh[::7] = 0.0                      # rows below the clamp: zero gradient, value sqrt(1e-8)
+    ref = lambda v: torch.sqrt(torch.clamp(v.square().sum(dim=1), min=1e-8))
+    check_op(T.vecnorm, ref, [vh], "vecnorm")
+
+
+def test_layernorms(T):
+    x, w, b = rnd(1234, 128, seed=10, scale=2.0), rnd(128, seed=11), rnd(128, seed=12)
+    check_op(T.layernorm, lambda x, w, b: torch.nn.functional.layer_norm(x, (128,), w, b, 1e-5), [x, w, b], "layernorm")
+    v = rnd(600, 3, 16, seed=13)
+    v[::5] *= 1e-6
+
+    def ref(v):
+        vn = torch.clamp(v.square().sum(dim=1, keepdim=True), min=1e-8)          # [M,1,U]
+        vn = torch.sqrt(vn.mean(dim=2, keepdim=True) + 1e-5) + 1e-5
+        return v / vn
+    check_op(T.vecln, ref, [v], "vector layernorm")
+
+
+def test_gather_segmean_geom(T):
+    gen = torch.Generator().manual_seed(14)
+    x = rnd(100, 3, 16, seed=15)
+    idx = torch.randint(0, 100, (999,), generator=gen).int().cuda()
+    check_op(lambda x: T.gather(x, idx), lambda x: x[idx.long()], [x], "gather")
+    cnt = torch.randint(0, 9, (60,), generator=gen)
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(cnt, 0)]).int().cuda()
+    E = int(cnt.sum())
+    seg_dst = torch.randperm(80, generator=gen)[:60].int().cuda()
+    msg = rnd(E, 128, seed=16)
+    seg_of = torch.repeat_interleave(torch.arange(60), cnt).cuda()
+
+    def ref(m, dst):
+        out = torch.zeros(80, 128, device="cuda").index_add(0, dst[seg_of], m)
+        c = torch.zeros(80, device="cuda").index_add(0, dst[seg_of], torch.ones(E, device="cuda")).clamp(min=1)
+        return out / c[:, None]
+    check_op(lambda m: T.segmean(m, ptr, seg_dst, 80), lambda m: ref(m, seg_dst.long()), [msg], "segmean seg_dst")
+    ar = torch.arange(60).cuda()
+    check_op(lambda m: T.segmean(m, ptr, None, 60), lambda m: ref(m, ar)[:60], [msg], "segmean implicit")
+    sx, dx = rnd(40, 3, seed=17, scale=4.0), rnd(30, 3, seed=18, scale=4.0)
+    s = torch.randint(0, 40, (500,), generator=gen).int().cuda()
+    d = torch.randint(0, 30, (500,), generator=gen).int().cuda()
+    xd, rbf = T.edge_geom(sx, dx, s, d)
+    diff = sx[s.long()] - dx[d.long()]
+    dist = torch.sqrt(torch.clamp(diff.square().sum(1, keepdim=True), min=1e-8)) + 1e-8
+    close(xd, diff / dist, what="x_diff")
+    mu = torch.linspace(0, 15, 16, device="cuda")
+    close(rbf, torch.exp(-((dist - mu) / (15 / 16)) ** 2), what="rbf")
+
+
+def _model(sd, dyn_cfg, dropout):
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    cfg = dict(dyn_cfg, dropout=dropout)
+    gcut = cfg.pop("graph_cutoffs")
+    m = PharmacophoreDiff(6, 11, ["a", "b", "c", "d", "e", "f"], n_timesteps=100, graph_config={"graph_cutoffs": gcut},
+                          dynamics_config=cfg, precision=1e-5, lr_scheduler_config={"base_lr": 1e-3, "weight_decay": 0.0})
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+def test_training_step_gradients_match_reference_backward(golden, sd, dyn_cfg):
+    """training_step (dropout 0, injected t / eps) -> loss.backward(): losses against the reference's forward, and the
+    gradient of every parameter against the reference's own backward (norms, sums, five full tensors) and the oracle."""
+    import pf_oracle as O
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    g = golden("forward_loss.npz")
+    sizes = list(map(int, g["sizes"]))
+    pos, onehot = make_pocket(int(g["n_atoms"]), seed=int(g["pocket_seed"]))
+    model = _model(sd, dyn_cfg, dropout=0.0).train()
+    gb = GraphBatch.from_pockets([Pocket.from_numpy(pos, onehot)], [sizes], "cuda:0")
+    gb.set_pharmacophores(t(g["x0"]), t(g["h0"]))
+    total, losses, metrics = model.training_step(gb, t_int=t(g["t_int"]), eps={"x": t(g["eps_x"]), "h": t(g["eps_h"])})
+    assert abs(float(losses["train pos loss"]) - float(g["val_pos_loss"])) < 2e-4
+    assert abs(float(losses["train feat loss"]) - float(g["val_feat_loss"])) < 2e-4
+    assert abs(float(metrics["train accuracy"]) - float(g["val_accuracy"])) < 1e-6
+    total.backward()
+    params = dict(model.named_parameters())
+    for n, norm, tot in zip(map(str, g["grad_names"]), g["grad_norms"], g["grad_sums"]):
+        gr = params[n].grad
+        assert gr is not None, n
+        assert abs(float(gr.double().norm()) - norm) <= 1e-3 * max(norm, 1e-6), (n, float(gr.norm()), norm)
+    for n in map(str, g["dead_params"]):
+        assert params[n].grad is None, n          # protein side of the last layer: unused, exactly like the reference
+    for k in g:
+        if k.startswith("grad__"):
+            close(params[k[6:]].grad, t(g[k]), rtol=1e-3, what=k)
+    # and against the oracle's autograd on every parameter, elementwise
+    b = O.build_batch([(t(pos), t(onehot))], [sizes])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k != "gamma.gamma" and v.numel() else v)
+           for k, v in sd.items()}
+    lo, _ = O.forward_loss(sdg, b, t(g["x0"]), t(g["h0"]), t(g["t_int"]), t(g["eps_x"]), t(g["eps_h"]), 100,
+                           sd["gamma.gamma"], dyn_cfg, phase="train")
+    torch.stack(list(lo.values())).sum().backward()
+    for n in map(str, g["grad_names"]):
+        close(params[n].grad, sdg[n].grad, rtol=1e-3, what=n)
+
+
+def test_adam_steps_reduce_the_loss_and_eval_path_follows(sd, dyn_cfg):
+    """A few optimisation steps with dropout 0.1 (training-mode masks) on one batch lower its loss, and the fused
+    evaluation kernels, re-packed from the updated parameters, agree with the differentiable path."""
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    torch.manual_seed(0)
+    pockets = [Pocket.from_numpy(*make_pocket(150, seed=40 + i)) for i in range(3)]
+    sizes = [[4], [6], [5]]
+    gen = torch.Generator().manual_seed(3)
+    nf = sum(s[0] for s in sizes)
+    h0 = torch.nn.functional.one_hot(torch.randint(0, 6, (nf,), generator=gen), 6).float()
+    model = _model(sd, dyn_cfg, dropout=0.1).train()
+    opt = model.configure_optimizers()["optimizer"]
+    t_int = torch.tensor([20, 50, 80])
+    eps = {"x": torch.randn(nf, 3, generator=gen), "h": torch.randn(nf, 6, generator=gen)}
+
+    def batch():
+        gb = GraphBatch.from_pockets(pockets, sizes, "cuda:0")
+        x0 = torch.cat([p.prot_x.mean(0, keepdim=True) + torch.randn(s[0], 3, generator=torch.Generator().manual_seed(9))
+                        for p, s in zip(pockets, sizes)])
+        return gb.set_pharmacophores(x0, h0)
+
+    def eval_loss():
+        model.eval()
+        lo, _ = model.validation_step(batch(), t_int=t_int, eps=eps)
+        model.train()
+        return float(lo["val total loss"])
+    first = eval_loss()
+    for _ in range(8):
+        opt.zero_grad()
+        total, _, _ = model.training_step(batch(), t_int=t_int, eps=eps)
+        total.backward()
+        opt.step()
+    last = eval_loss()
+    assert np.isfinite(last) and last < 0.9 * first, (first, last)
+    # differentiable path (dropout off in eval -> use p = 0 by toggling) vs fused kernels on the updated weights
+    for conv in model.dynamics.noise_predictor.conv_layers:
+        conv.dropout.feat_dropout.p = 0.0
+    total, _, _ = model.training_step(batch(), t_int=t_int, eps=eps)
+    assert abs(float(total) - last) <= 2e-4 * max(1.0, abs(last)), (float(total), last)

@@ -108,3 +108,30 @@ def test_forward_loss_matches_reference_forward(golden, sd, dyn_cfg):
     for k, v in {**losses, **metrics}.items():
         ref = float(g[k.replace(" ", "_")])
         assert abs(float(v) - ref) <= 1e-5 * max(1.0, abs(ref)), (k, float(v), ref)
+
+
+def test_oracle_gradients_match_reference_backward(golden, sd, dyn_cfg):
+    """Autograd through oracle.forward_loss against the reference's own backward of the same loss (total = pos + feat,
+    pharmacodiff.py:265-297): gradient norm and sum of every parameter, the full gradient of five of them, and the set
+    of parameters that get no gradient at all (protein side of the last conv layer)."""
+    g = golden("forward_loss.npz")
+    pos, onehot = make_pocket(int(g["n_atoms"]), seed=int(g["pocket_seed"]))
+    b = O.build_batch([(t(pos), t(onehot))], [list(map(int, g["sizes"]))])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k != "gamma.gamma" and v.numel() else v)
+           for k, v in sd.items()}
+    losses, _ = O.forward_loss(sdg, b, t(g["x0"]), t(g["h0"]), t(g["t_int"]), t(g["eps_x"]), t(g["eps_h"]), 100,
+                               sd["gamma.gamma"], dyn_cfg, phase="val")
+    torch.stack(list(losses.values())).sum().backward()
+    names = [str(n) for n in g["grad_names"]]
+    for n, norm, total in zip(names, g["grad_norms"], g["grad_sums"]):
+        gr = sdg[n].grad
+        assert gr is not None, n
+        assert abs(float(gr.double().norm()) - norm) <= 2e-4 * max(norm, 1e-6), (n, float(gr.norm()), norm)
+        assert abs(float(gr.double().sum()) - total) <= 2e-4 * max(norm, 1e-6) * gr.numel() ** 0.5, n
+    for n in map(str, g["dead_params"]):
+        assert sdg[n].grad is None or float(sdg[n].grad.abs().max()) == 0.0, n
+    for k in g:
+        if k.startswith("grad__"):
+            ref = t(g[k])
+            got = sdg[k[6:]].grad
+            assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max()), k
