@@ -232,7 +232,8 @@ class PharmRecDynamicsGVP(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, g: GraphBatch, timestep: torch.Tensor, batch_idxs=None):
         if self.training and self.noise_predictor.conv_layers[0].dropout.feat_dropout.p > 0:
-            raise NotImplementedError("training-mode dropout / backward kernels are not built yet; call .eval()")
+            raise NotImplementedError("the fused kernels implement eval-mode semantics (no dropout, no autograd graph): call "
+                                      ".eval(), or train through PharmacophoreDiff.training_step (train_graph.py)")
         st = self.bind(g)
         st.t_graph.copy_(timestep.to(device=g.device, dtype=torch.float32).reshape(-1))
         ops.denoiser(st.eps_h, st.eps_x, st.addr)

@@ -4,6 +4,11 @@ Sampling graphs never interact (every edge builder and reduction is restricted t
 pocket-major graph list is cut into `world` contiguous ranges balanced by protein-atom count; each rank runs
 its own reverse-diffusion loop with replicated weights and no collective on the path.  Results are gathered
 once at the end (`gather_results`).
+
+Training is data parallel: every rank runs forward + backward on its share of the batch and `allreduce_gradients`
+averages the gradients with ONE all-reduce of a flat fp32 buffer (NCCL over NVLink on the GPU box), the semantics of
+Lightning's DDP strategy the reference trains under (mean of the per-rank gradients; each rank's loss is normalised by
+its LOCAL element count, pharmacodiff.py:231-232).
 """
 from __future__ import annotations
 
@@ -49,3 +54,31 @@ def gather_results(local: torch.Tensor, group=None) -> Optional[List[torch.Tenso
     if rank != 0:
         return None
     return [b[:int(c.item())] for b, c in zip(bufs, counts)]
+
+
+def allreduce_gradients(module: torch.nn.Module, group=None) -> int:
+    """Average the gradients of `module` over the ranks with a single all-reduce of one flat fp32 buffer.
+
+    Every rank lays out ALL parameters in `named_parameters()` order; parameters without a gradient (the protein side of
+    the last conv layer is never used, so autograd leaves `grad=None` -- the same set on every rank) contribute zeros and
+    keep `grad=None` afterwards, so Adam skips them exactly as it does in the reference.  Returns the buffer length."""
+    import torch.distributed as dist
+    params = [p for _, p in module.named_parameters() if p.requires_grad and p.numel() > 0]
+    if not params:
+        return 0
+    dev = next((p.grad.device for p in params if p.grad is not None), params[0].device)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        if p.grad is not None:
+            flat[off:off + p.numel()] = p.grad.reshape(-1)
+        off += p.numel()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        if p.grad is not None:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+        off += p.numel()
+    return flat.numel()

@@ -207,3 +207,35 @@ def test_sharded_gather_world_size_2_gloo(tmp_path):
     got = torch.cat(parts)
     want = torch.cat([torch.full((n, 9), float(g)) for g, n in enumerate(n for szs in sizes for n in szs)])
     assert torch.equal(got, want)      # rank order == graph order: results concatenate without a permutation
+
+
+def _allreduce_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from pharmacoforge_b200.sharding import allreduce_gradients
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3), torch.nn.Linear(3, 3))  # last one unused
+    x = torch.full((4, 5), float(rank + 1))
+    net[1](net[0](x)).sum().backward()
+    n = allreduce_gradients(net)
+    torch.save({"n": n, "g0": net[0].weight.grad.clone(), "dead": net[2].weight.grad}, f"{out_dir}/r{rank}.pt")
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2_gloo(tmp_path):
+    """DDP semantics of the training path on CPU / gloo: one flat all-reduce, mean over ranks, parameters without a
+    gradient (dead last-layer protein side) stay grad=None on every rank."""
+    import torch.multiprocessing as mp
+    port = 29640 + (os.getpid() % 200)
+    mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    assert r0["n"] == r1["n"] == 5 * 7 + 7 + 7 * 3 + 3 + 3 * 3 + 3
+    assert torch.equal(r0["g0"], r1["g0"]) and r0["dead"] is None and r1["dead"] is None
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    g = []
+    for rank in range(2):
+        net.zero_grad()
+        net[1](net[0](torch.full((4, 5), float(rank + 1)))).sum().backward()
+        g.append(net[0].weight.grad.clone())
+    assert torch.allclose(r0["g0"], (g[0] + g[1]) / 2, rtol=1e-6, atol=1e-6)
