@@ -344,9 +344,12 @@ extern "C" int pf_train_sgemm(const float* A, const float* B, const float* bias,
 extern "C" int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* stream) {
   PF_CHECK_ARG(x && out && M >= 0 && N > 0, "pf_train_colsum: arguments");
   if (M == 0) return PF_OK;
-  const int ysplit = (int)(M / 4096 > 64 ? 64 : (M / 4096 > 0 ? M / 4096 : 1));
-  dim3 grid((N + 127) / 128, ysplit);
-  T::colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, out, M, N);
+  // rows are split over many CTAs (about 256 rows each): the reduction is bandwidth-trivial but latency-bound per thread
+  const long long want = (M + 255) / 256;
+  const int ysplit = (int)(want > 2048 ? 2048 : (want > 0 ? want : 1));
+  const int tx = N >= 128 ? 128 : 32;
+  dim3 grid((N + tx - 1) / tx, ysplit);
+  T::colsum_kernel<<<grid, tx, 0, as_stream(stream)>>>(x, out, M, N);
   PF_CHECK_LAUNCH("pf_train_colsum");
   return PF_OK;
 }

@@ -1,0 +1,204 @@
+"""Host-side front end and back end around the hot path -- plain Python / numpy, no
+BioPython, RDKit or DGL:
+
+  * `pocket_from_pdb`: the pocket extraction of generate_pharmacophores.py:120-220 (`process_ligand_and_pocket`): the
+    standard-amino-acid residues with an atom within `pocket_cutoff` of the reference ligand (or an explicit
+    `chain:resnum` list), heavy atoms only, element one-hot over `prot_elements` with the 'other' column dropped and
+    those atoms removed.  PDB ATOM records and V2000 SDF coordinates are parsed by hand.
+  * `ProteinPharmacophoreDataset`: the processed CrossDocked tensors (`prot_pharm_tensors.npz`,
+    protein_pharm_dataset.py:18-207) as (Pocket, pharmacophore x_0 / h_0, receptor pharmacophores) items, with the
+    reference's pharmacophore subsampling, plus `collate` to a training `GraphBatch`.
+  * `compute_complementarity` / `SampleAnalyzer`: the validity metric of analysis/metrics.py:9-86.
+"""
+from __future__ import annotations
+
+import random
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .batch import Pocket
+
+STANDARD_AA = {"ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU", "LYS", "MET", "PHE", "PRO",
+               "SER", "THR", "TRP", "TYR", "VAL"}
+PH_TYPES = ["Aromatic", "HydrogenDonor", "HydrogenAcceptor", "PositiveIon", "NegativeIon", "Hydrophobic"]  # constants.py
+
+
+def element_fixer(element: str) -> str:
+    """generate_pharmacophores.py:97-102: 'CL' -> 'Cl'."""
+    return element[0] + element[1:].lower() if len(element) > 1 else element
+
+
+def read_pdb_atoms(path) -> List[dict]:
+    """ATOM records of the first model: chain, resseq, icode, resname, atom name, element, xyz."""
+    atoms = []
+    for line in Path(path).read_text().splitlines():
+        rec = line[:6]
+        if rec.startswith("ENDMDL"):
+            break
+        if rec not in ("ATOM  ", "HETATM"):
+            continue
+        name = line[12:16].strip()
+        element = line[76:78].strip() if len(line) >= 78 and line[76:78].strip() else "".join(c for c in name if c.isalpha())[:1]
+        atoms.append(dict(het=rec == "HETATM", name=name, altloc=line[16], resname=line[17:20].strip(), chain=line[21],
+                          resseq=int(line[22:26]), icode=line[26], element=element_fixer(element.upper()),
+                          xyz=(float(line[30:38]), float(line[38:46]), float(line[46:54]))))
+    return atoms
+
+
+def read_sdf_coords(path, remove_hydrogen: bool = True) -> np.ndarray:
+    """Atom coordinates of the first V2000 mol block of an SDF file (generate_pharmacophores.py:68-95 uses RDKit)."""
+    lines = Path(path).read_text().splitlines()
+    n_atoms = int(lines[3][:3])
+    out = []
+    for line in lines[4:4 + n_atoms]:
+        x, y, z, el = float(line[0:10]), float(line[10:20]), float(line[20:30]), line[31:34].strip()
+        if remove_hydrogen and el == "H":
+            continue
+        out.append((x, y, z))
+    return np.asarray(out, dtype=np.float32).reshape(-1, 3)
+
+
+def onehot_encode_elements(elements: Iterable[str], element_map: Dict[str, int]) -> np.ndarray:
+    """generate_pharmacophores.py:104-117."""
+    idx = np.fromiter((element_map.get(e, element_map["other"]) for e in elements), int)
+    out = np.zeros((idx.size, len(element_map)), dtype=np.float32)
+    out[np.arange(idx.size), idx] = 1
+    return out
+
+
+def pocket_from_pdb(rec_file, prot_elements: Sequence[str], pocket_cutoff: float = 8.0, lig_file=None,
+                    lig_coords: Optional[np.ndarray] = None, residue_list: Sequence[str] = (),
+                    remove_hydrogen: bool = True) -> Tuple[Pocket, torch.Tensor]:
+    """-> (Pocket, init_com [1, 3]): what `process_ligand_and_pocket` feeds `build_initial_complex_graph`
+    (generate_pharmacophores.py:120-205).  Ligand given as an SDF file or raw coordinates, or a residue list
+    ['A:101', ...]; init_com is the ligand COM (or the COM of the listed residues' atoms)."""
+    if lig_file is None and lig_coords is None and len(residue_list) == 0:
+        raise ValueError("Either reference ligand or pocket residue list must be provided.")
+    atoms = [a for a in read_pdb_atoms(rec_file) if not a["het"] and a["altloc"] in (" ", "A")]
+    residues: Dict[tuple, List[dict]] = {}
+    for a in atoms:                                   # insertion-ordered, like BioPython's get_residues()
+        residues.setdefault((a["chain"], a["resseq"], a["icode"]), []).append(a)
+    if lig_file is not None or lig_coords is not None:
+        lig = read_sdf_coords(lig_file, remove_hydrogen) if lig_coords is None else np.asarray(lig_coords, dtype=np.float32)
+        init_com = torch.from_numpy(lig.mean(axis=0).reshape(1, 3).astype(np.float32))
+        chosen = []
+        for key, res in residues.items():
+            if res[0]["resname"] not in STANDARD_AA:
+                continue
+            xyz = np.asarray([a["xyz"] for a in res], dtype=np.float32)
+            d = np.sqrt(((lig[:, None, :] - xyz[None, :, :]) ** 2).sum(-1)).min()
+            if d < pocket_cutoff:
+                chosen.append(key)
+        if not chosen:
+            raise ValueError("no valid pocket residues found.")
+    else:
+        chosen = []
+        for spec in residue_list:
+            chain, num = spec.split(":")
+            key = (chain, int(num), " ")
+            if key not in residues:
+                raise KeyError(f"residue {spec} not found in {rec_file}")
+            chosen.append(key)
+        xyz = np.asarray([a["xyz"] for k in chosen for a in residues[k]], dtype=np.float32)
+        init_com = torch.from_numpy(xyz.mean(axis=0).reshape(1, 3))
+    pocket_atoms = [a for k in chosen for a in residues[k] if not (remove_hydrogen and a["element"] == "H")]
+    element_map = {e: i for i, e in enumerate(list(prot_elements) + ["other"])}
+    onehot = onehot_encode_elements([a["element"] for a in pocket_atoms], element_map)
+    keep = onehot[:, -1] != 1                          # drop 'other' atoms (generate_pharmacophores.py:189-196)
+    pos = np.asarray([a["xyz"] for a in pocket_atoms], dtype=np.float32)[keep]
+    return Pocket.from_numpy(pos, onehot[keep, :-1]), init_com
+
+
+class ProteinPharmacophoreDataset:
+    """protein_pharm_dataset.py:18-207 without DGL: item i -> dict(pocket, x_0, h_0, prot_ph_pos, prot_ph_feat).
+    `processed_data_dir` holds one sub-directory per split, each with `prot_pharm_tensors.npz` (keys pharm_pos,
+    pharm_feat, prot_pos, prot_feat, prot_ph_pos, prot_ph_feat and the [n, 2] start / end index arrays pharm_idx,
+    prot_idx, prot_ph_idx)."""
+
+    def __init__(self, split_idxs: Sequence[int], processed_data_dir, prot_elements: Sequence[str],
+                 ph_type_map: Sequence[str] = PH_TYPES, subsample_pharms: bool = False, subsample_min: int = 3,
+                 subsample_max: int = 9, **kwargs):
+        self.prot_elements, self.ph_type_map = list(prot_elements), list(ph_type_map)
+        self.subsample_pharms, self.subsample_min, self.subsample_max = subsample_pharms, subsample_min, subsample_max
+        root = Path(processed_data_dir)
+        if not root.exists():
+            raise FileNotFoundError(f"Could not find processed data directory at {root}")
+        keys = ("pharm_pos", "pharm_feat", "prot_pos", "prot_feat", "prot_ph_pos", "prot_ph_feat")
+        data = {k: [] for k in keys}
+        idx = {"pharm_idx": [], "prot_idx": [], "prot_ph_idx": []}
+        for split_dir in sorted(root.iterdir()):
+            if not split_dir.is_dir() or int(split_dir.name.split("_")[-1][-1]) not in split_idxs:
+                continue
+            z = np.load(split_dir / "prot_pharm_tensors.npz")
+            for k in keys:
+                data[k].append(z[k])
+            for k in idx:                              # make the per-split [start, end) indices global (:103-121)
+                off = idx[k][-1][-1, 1] if idx[k] else 0
+                idx[k].append(z[k] + off)
+        if not data["prot_pos"]:
+            raise FileNotFoundError(f"no split directories for splits {list(split_idxs)} under {root}")
+        for k in keys:
+            setattr(self, k, torch.from_numpy(np.concatenate(data[k], axis=0)))
+        for k in idx:
+            setattr(self, k, np.concatenate(idx[k], axis=0))
+
+    def __len__(self):
+        return self.prot_idx.shape[0]
+
+    def __getitem__(self, i):
+        f0, f1 = self.pharm_idx[i]
+        p0, p1 = self.prot_idx[i]
+        r0, r1 = self.prot_ph_idx[i]
+        one_hot = torch.nn.functional.one_hot
+        pharm_pos = self.pharm_pos[f0:f1].float()
+        pharm_feat = one_hot(self.pharm_feat[f0:f1].long(), len(self.ph_type_map)).float()
+        if self.subsample_pharms and len(pharm_pos) > self.subsample_min - 1:     # :159-168
+            hi = min(self.subsample_max, len(pharm_pos))
+            n = self.subsample_min if self.subsample_min == hi else random.randint(self.subsample_min, hi)
+            sel = random.sample(range(len(pharm_pos)), n)
+            pharm_pos, pharm_feat = pharm_pos[sel], pharm_feat[sel]
+        pocket = Pocket(self.prot_pos[p0:p1].float().contiguous(),
+                        one_hot(self.prot_feat[p0:p1].long(), len(self.prot_elements)).float())
+        return dict(pocket=pocket, x_0=pharm_pos, h_0=pharm_feat, prot_ph_pos=self.prot_ph_pos[r0:r1].float(),
+                    prot_ph_feat=one_hot(self.prot_ph_feat[r0:r1].long(), len(self.ph_type_map)).float())
+
+    @staticmethod
+    def collate(items: Sequence[dict], model, device=None):
+        """One training graph per item -> GraphBatch with the ground truth attached (dgl.batch of the item graphs)."""
+        g = model.make_batch([it["pocket"] for it in items], [[int(it["x_0"].shape[0])] for it in items], device=device)
+        return g.set_pharmacophores(torch.cat([it["x_0"] for it in items]), torch.cat([it["h_0"] for it in items]))
+
+
+MATCHING_TYPES = {"Aromatic": ["Aromatic", "PositiveIon"], "HydrogenDonor": ["HydrogenAcceptor"],
+                  "HydrogenAcceptor": ["HydrogenDonor"], "PositiveIon": ["NegativeIon", "Aromatic"],
+                  "NegativeIon": ["PositiveIon"], "Hydrophobic": ["Hydrophobic"]}
+MATCHING_DISTANCE = {"Aromatic": 7, "Hydrophobic": 5, "HydrogenAcceptor": 4, "HydrogenDonor": 4, "NegativeIon": 5,
+                     "PositiveIon": 5}
+
+
+def compute_complementarity(pharm_types: Sequence[str], pharm_pos: torch.Tensor, prot_ph_types: Sequence[str],
+                            prot_ph_pos: torch.Tensor, return_count: bool = False):
+    """analysis/metrics.py:54-86: pharmacophore centres within the type's matching distance of a complementary
+    receptor feature (count, or fraction of the centres)."""
+    dist = torch.cdist(pharm_pos.float(), prot_ph_pos.float())
+    cut = torch.tensor([MATCHING_DISTANCE[t] for t in pharm_types], dtype=dist.dtype, device=dist.device).reshape(-1, 1)
+    match = torch.tensor([[r in MATCHING_TYPES[t] for r in prot_ph_types] for t in pharm_types], dtype=torch.bool,
+                         device=dist.device).reshape(len(pharm_types), len(prot_ph_types))
+    count = ((dist <= cut) & match).any(dim=1).sum()
+    return count if return_count else count / max(len(pharm_types), 1)
+
+
+class SampleAnalyzer:
+    """analysis/metrics.py:7-35: validity = complementary centres / all centres over a list of sampled pharmacophores,
+    each paired with the receptor pharmacophore features of its pocket."""
+
+    def analyze(self, samples, prot_ph_pos: Sequence[torch.Tensor], prot_ph_feat: Sequence[torch.Tensor]):
+        num = den = 0
+        for ph, rpos, rfeat in zip(samples, prot_ph_pos, prot_ph_feat):
+            rtypes = [PH_TYPES[int(i)] for i in rfeat.argmax(dim=1)]
+            num += int(compute_complementarity(ph.ph_types, ph.ph_coords, rtypes, rpos, return_count=True))
+            den += ph.n_ph_centers
+        return {"validity": num / max(den, 1)}

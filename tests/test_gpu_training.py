@@ -199,3 +199,24 @@ def test_adam_steps_reduce_the_loss_and_eval_path_follows(sd, dyn_cfg):
         conv.dropout.feat_dropout.p = 0.0
     total, _, _ = model.training_step(batch(), t_int=t_int, eps=eps)
     assert abs(float(total) - last) <= 2e-4 * max(1.0, abs(last)), (float(total), last)
+
+
+def test_dataset_items_collate_into_a_training_batch(tmp_path, sd, dyn_cfg):
+    """io.ProteinPharmacophoreDataset -> collate -> training_step (the train.py data path without DGL)."""
+    from pharmacoforge_b200 import io as pio
+    rng = np.random.default_rng(1)
+    d = tmp_path / "split_0"
+    d.mkdir()
+    prot_n, ph_n, rp_n = np.array([60, 45, 80]), np.array([5, 4, 7]), np.array([3, 3, 3])
+    mk = lambda cnt: np.stack([np.cumsum(cnt) - cnt, np.cumsum(cnt)], axis=1)
+    np.savez(d / "prot_pharm_tensors.npz", prot_pos=rng.normal(size=(prot_n.sum(), 3)) * 6,
+             prot_feat=rng.integers(0, 4, prot_n.sum()), pharm_pos=rng.normal(size=(ph_n.sum(), 3)) * 3,
+             pharm_feat=rng.integers(0, 6, ph_n.sum()), prot_ph_pos=rng.normal(size=(rp_n.sum(), 3)),
+             prot_ph_feat=rng.integers(0, 6, rp_n.sum()), prot_idx=mk(prot_n), pharm_idx=mk(ph_n), prot_ph_idx=mk(rp_n))
+    ds = pio.ProteinPharmacophoreDataset([0], tmp_path, ['C', 'N', 'O', 'S', 'P', 'F', 'Cl', 'Br', 'I', 'B', 'D'])
+    model = _model(sd, dyn_cfg, dropout=0.1).train()
+    g = pio.ProteinPharmacophoreDataset.collate([ds[i] for i in range(3)], model, device="cuda:0")
+    assert g.n_graphs == 3 and g.n_pharm == 16 and g.n_prot == 185
+    total, losses, metrics = model.training_step(g)
+    total.backward()
+    assert np.isfinite(float(total)) and model.dynamics.pharm_encoder[0].weight.grad is not None
