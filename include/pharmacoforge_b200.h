@@ -278,6 +278,19 @@ int pf_train_segmean(const float* msg_or_dout, const int32_t* ptr, const int32_t
 int pf_train_edge_geom(const float* src_x, const float* dst_x, const int32_t* src, const int32_t* dst, float* xdiff,
                        float* rbf, int64_t E, void* stream);
 
+/* One whole GVP (gvp.py:89-116) per host call: the primitives above enqueued back to back, forward and backward.
+ * feats [M][n], vec [M][3][vi], Wh [vi][h], Wu [h][vo], Wf [no][n+h], Wg [vo][no]; the forward also returns what the
+ * backward needs (Vh, Vu, s = [feats | sh], z, f, gates).  dbf / dbg must come zeroed; dgates, dVu, dfz, ds, dVh are scratch. */
+int pf_train_gvp_fwd(const float* feats, const float* vec, const float* Wh, const float* Wu, const float* Wf, const float* bf,
+                     const float* Wg, const float* bg, int64_t M, int32_t n, int32_t vi, int32_t h, int32_t vo, int32_t no,
+                     int32_t act_sigmoid, float* Vh, float* Vu, float* s, float* z, float* f, float* gates, float* vout,
+                     void* stream);
+int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* Wu, const float* Wf, const float* Wg, const float* Vh,
+                     const float* Vu, const float* s, const float* z, const float* f, const float* gates, const float* df_out,
+                     const float* dvout, int64_t M, int32_t n, int32_t vi, int32_t h, int32_t vo, int32_t no,
+                     int32_t act_sigmoid, float* dgates, float* dVu, float* dfz, float* ds, float* dVh, float* dfeats,
+                     float* dvec, float* dWh, float* dWu, float* dWf, float* dbf, float* dWg, float* dbg, void* stream);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------------
  * pf_launch_count: kernels this library has launched in this process so far.
  * pf_profile_enable(n): n > 0 arms CUDA-event pairs around every kernel site of pf_denoiser /

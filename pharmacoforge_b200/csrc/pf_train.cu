@@ -11,56 +11,62 @@ namespace train {
 
 // ------------------------------------------------------------------------------------------------ strided SGEMM
 // C[M][N] (row-major, ldc) (+)= A(m, k) * B(k, n) (+ bias[n]); A(m, k) = A[m * a_rs + k * a_cs], B(k, n) = B[k * b_rs +
-// n * b_cs].  One kernel covers y = x W^T + b, dx = dy W and dW = dy^T x.  64 x 64 tile, K step 16, 256 threads, 4 x 4
-// outputs per thread; gridDim.z > 1 splits K and accumulates with atomicAdd into a zeroed / accumulating C.
-constexpr int kTM = 64, kTN = 64, kTK = 16;
+// n * b_cs].  One kernel covers y = x W^T + b, dx = dy W and dW = dy^T x.  K step 16, 256 threads, 128 x 128 tiles with
+// 8 x 8 outputs per thread (64 x 64 / 4 x 4 for narrow outputs); gridDim.z > 1 splits K and accumulates with atomicAdd
+// into a zeroed / accumulating C.
+constexpr int kTK = 16;
+template <int TM, int TN, int R>  // TM x TN tile, R x R outputs per thread, (TM / R) * (TN / R) = 256 threads
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                     const float* __restrict__ bias, float* __restrict__ C, int M, int N,
                                                     int K, long long a_rs, long long a_cs, long long b_rs,
                                                     long long b_cs, int ldc, int accumulate, int k_chunk) {
-  __shared__ float sA[kTK][kTM + 4];
-  __shared__ float sB[kTK][kTN + 4];
+  static_assert((TM / R) * (TN / R) == 256 && R % 4 == 0, "tile shape");
+  __shared__ __align__(16) float sA[kTK][TM + 4];
+  __shared__ __align__(16) float sB[kTK][TN + 4];
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int k_begin = blockIdx.z * k_chunk;
   const int k_end = min(K, k_begin + k_chunk);
-  const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;
-  float acc[4][4] = {};
+  const int tm = (tid / (TN / R)) * R, tn = (tid % (TN / R)) * R;
+  float acc[R][R] = {};
   for (int k0 = k_begin; k0 < k_end; k0 += kTK) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // 64 x 16 elements of A and of B, 4 per thread each
+    for (int i = 0; i < TM * kTK / 256; ++i) {
       const int e = tid + 256 * i;
-      {
-        // A tile: pick the index order that makes consecutive threads walk the unit-stride dimension
-        const int m = a_cs == 1 ? e / kTK : e % kTM, k = a_cs == 1 ? e % kTK : e / kTM;
-        const int gm = m0 + m, gk = k0 + k;
-        sA[k][m] = (gm < M && gk < k_end) ? A[gm * a_rs + gk * a_cs] : 0.f;
-      }
-      {
-        const int n = b_cs == 1 ? e % kTN : e / kTK, k = b_cs == 1 ? e / kTN : e % kTK;
-        const int gn = n0 + n, gk = k0 + k;
-        sB[k][n] = (gn < N && gk < k_end) ? B[gk * b_rs + gn * b_cs] : 0.f;
-      }
+      // pick the index order that makes consecutive threads walk the unit-stride dimension of the operand
+      const int m = a_cs == 1 ? e / kTK : e % TM, k = a_cs == 1 ? e % kTK : e / TM;
+      const int gm = m0 + m, gk = k0 + k;
+      sA[k][m] = (gm < M && gk < k_end) ? A[gm * a_rs + gk * a_cs] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < TN * kTK / 256; ++i) {
+      const int e = tid + 256 * i;
+      const int n = b_cs == 1 ? e % TN : e / kTK, k = b_cs == 1 ? e / TN : e % kTK;
+      const int gn = n0 + n, gk = k0 + k;
+      sB[k][n] = (gn < N && gk < k_end) ? B[gk * b_rs + gn * b_cs] : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kTK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&sA[k][tm]);
-      const float4 b = *reinterpret_cast<const float4*>(&sB[k][tn]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[R], bv[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; i += 4) {
+        *reinterpret_cast<float4*>(&av[i]) = *reinterpret_cast<const float4*>(&sA[k][tm + i]);
+        *reinterpret_cast<float4*>(&bv[i]) = *reinterpret_cast<const float4*>(&sB[k][tn + i]);
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < R; ++i) {
     const int gm = m0 + tm + i;
     if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < R; ++j) {
       const int gn = n0 + tn + j;
       if (gn >= N) continue;
       float v = acc[i][j];
@@ -130,7 +136,8 @@ __global__ void gate_bwd_kernel(const float* __restrict__ gate, const float* __r
 }
 
 // sh[m][h] = sqrt(max(sum_c Vh[m][c][h]^2, 1e-8))   (_norm_no_nan, gvp.py:12-19)
-__global__ void vecnorm_fwd_kernel(const float* __restrict__ vh, float* __restrict__ sh, long long rows, int H) {
+__global__ void vecnorm_fwd_kernel(const float* __restrict__ vh, float* __restrict__ sh, long long rows, int H,
+                                   int ld_sh) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   const long long m = i / H;
@@ -141,10 +148,10 @@ __global__ void vecnorm_fwd_kernel(const float* __restrict__ vh, float* __restri
     const float v = vh[(m * 3 + c) * H + h];
     s = fmaf(v, v, s);
   }
-  sh[i] = sqrtf(fmaxf(s, 1e-8f));
+  sh[m * ld_sh + h] = sqrtf(fmaxf(s, 1e-8f));
 }
 __global__ void vecnorm_bwd_kernel(const float* __restrict__ vh, const float* __restrict__ dsh, float* __restrict__ dvh,
-                                   long long rows, int H) {
+                                   long long rows, int H, int ld_sh) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   const long long m = i / H;
@@ -155,7 +162,7 @@ __global__ void vecnorm_bwd_kernel(const float* __restrict__ vh, const float* __
     v[c] = vh[(m * 3 + c) * H + h];
     s = fmaf(v[c], v[c], s);
   }
-  const float k = s > 1e-8f ? dsh[i] / sqrtf(s) : 0.f;  // the clamp has zero gradient below eps
+  const float k = s > 1e-8f ? dsh[m * ld_sh + h] / sqrtf(s) : 0.f;  // the clamp has zero gradient below eps
 #pragma unroll
   for (int c = 0; c < 3; ++c) dvh[(m * 3 + c) * H + h] = k * v[c];
 }
@@ -334,9 +341,11 @@ extern "C" int pf_train_sgemm(const float* A, const float* B, const float* bias,
       return PF_ERR_LAUNCH;
     }
   }
-  dim3 grid((N + T::kTN - 1) / T::kTN, (M + T::kTM - 1) / T::kTM, splits);
-  T::sgemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate,
-                                                      chunk);
+  // 64 x 64 tiles, 4 x 4 outputs per thread.  (A 128 x 128 / 8 x 8 instantiation measured SLOWER on the training step:
+  // most of its GEMMs are skinny -- N = 16 / 17 / 32 vector-channel contractions over 3E rows -- and memory-bound.)
+  dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+  T::sgemm_kernel<64, 64, 4><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc,
+                                                                 accumulate, chunk);
   PF_CHECK_LAUNCH("pf_train_sgemm");
   return PF_OK;
 }
@@ -385,9 +394,9 @@ extern "C" int pf_train_vecnorm(const float* vh, const float* dsh, float* out, i
   PF_CHECK_ARG(vh && out && rows >= 0 && H > 0, "pf_train_vecnorm: arguments");
   if (rows == 0) return PF_OK;
   if (dsh == nullptr)
-    T::vecnorm_fwd_kernel<<<blocks_for(rows * H, 256), 256, 0, as_stream(stream)>>>(vh, out, rows, H);
+    T::vecnorm_fwd_kernel<<<blocks_for(rows * H, 256), 256, 0, as_stream(stream)>>>(vh, out, rows, H, H);
   else
-    T::vecnorm_bwd_kernel<<<blocks_for(rows * H, 256), 256, 0, as_stream(stream)>>>(vh, dsh, out, rows, H);
+    T::vecnorm_bwd_kernel<<<blocks_for(rows * H, 256), 256, 0, as_stream(stream)>>>(vh, dsh, out, rows, H, H);
   PF_CHECK_LAUNCH("pf_train_vecnorm");
   return PF_OK;
 }
@@ -452,5 +461,93 @@ extern "C" int pf_train_edge_geom(const float* src_x, const float* dst_x, const 
   if (E == 0) return PF_OK;
   T::edge_geom_kernel<<<blocks_for(E, 256), 256, 0, as_stream(stream)>>>(src_x, dst_x, src, dst, xdiff, rbf, E);
   PF_CHECK_LAUNCH("pf_train_edge_geom");
+  return PF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one GVP per call
+// GVP.forward (gvp.py:89-116) and its backward as ONE host call each: the same kernels as above, enqueued back to back
+// (the Python-side cost of ~16 custom-op round trips per GVP dominated the first training step).  All buffers are the
+// caller's.  Shapes: feats [M][n], vec [M][3][vi], Wh [vi][h], Wu [h][vo], Wf [no][n + h], Wg [vo][no];
+// saved for the backward: Vh [3M][h], Vu [3M][vo], s = [feats | sh] [M][n + h], z [M][no], f [M][no], gates [M][vo].
+static int sgemm_ld(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, long long a_rs,
+                    long long a_cs, long long b_rs, long long b_cs, int ldc, int accumulate, int split_k, void* stream) {
+  return pf_train_sgemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, stream);
+}
+static int wgrad_splits(long long rows) { return rows / 512 > 64 ? 64 : (rows / 512 > 1 ? (int)(rows / 512) : 1); }
+
+extern "C" int pf_train_gvp_fwd(const float* feats, const float* vec, const float* Wh, const float* Wu, const float* Wf,
+                                const float* bf, const float* Wg, const float* bg, int64_t M, int32_t n, int32_t vi,
+                                int32_t h, int32_t vo, int32_t no, int32_t act_sigmoid, float* Vh, float* Vu, float* s,
+                                float* z, float* f, float* gates, float* vout, void* stream) {
+  PF_CHECK_ARG(feats && vec && Wh && Wu && Wf && bf && Wg && bg && Vh && Vu && s && z && f && gates && vout,
+               "pf_train_gvp_fwd: null pointer");
+  if (M == 0) return PF_OK;
+  const int M3 = (int)(3 * M), K = n + h;
+  int rc;
+  if ((rc = sgemm_ld(vec, Wh, nullptr, Vh, M3, h, vi, vi, 1, h, 1, h, 0, 1, stream)) != PF_OK) return rc;   // Vh = V Wh
+  if ((rc = sgemm_ld(Vh, Wu, nullptr, Vu, M3, vo, h, h, 1, vo, 1, vo, 0, 1, stream)) != PF_OK) return rc;   // Vu = Vh Wu
+  cudaError_t e = cudaMemcpy2DAsync(s, (size_t)K * 4, feats, (size_t)n * 4, (size_t)n * 4, (size_t)M,
+                                    cudaMemcpyDeviceToDevice, as_stream(stream));
+  if (e != cudaSuccess) {
+    set_error("pf_train_gvp_fwd: copy: %s", cudaGetErrorString(e));
+    return PF_ERR_LAUNCH;
+  }
+  T::vecnorm_fwd_kernel<<<blocks_for(M * h, 256), 256, 0, as_stream(stream)>>>(Vh, s + n, M, h, K);      // s = [feats|sh]
+  PF_CHECK_LAUNCH("pf_train_gvp_fwd(vecnorm)");
+  if ((rc = sgemm_ld(s, Wf, bf, z, (int)M, no, K, K, 1, 1, K, no, 0, 1, stream)) != PF_OK) return rc;       // z = s Wf^T + bf
+  T::silu_fwd_kernel<<<blocks_for(M * no, 256), 256, 0, as_stream(stream)>>>(z, f, M * no);
+  PF_CHECK_LAUNCH("pf_train_gvp_fwd(silu)");
+  if ((rc = sgemm_ld(f, Wg, bg, gates, (int)M, vo, no, no, 1, 1, no, vo, 0, 1, stream)) != PF_OK) return rc;
+  T::gate_fwd_kernel<<<blocks_for(M * 3 * vo, 256), 256, 0, as_stream(stream)>>>(gates, Vu, vout, M, vo, act_sigmoid);
+  PF_CHECK_LAUNCH("pf_train_gvp_fwd(gate)");
+  return PF_OK;
+}
+
+// grads: dfeats [M][n], dvec [M][3][vi], dWh, dWu, dWf, dbf, dWg, dbg (all overwritten; dbf / dbg must come ZEROED).
+// scratch: dgates [M][vo], dVu [3M][vo], dfz [M][no] (df then dz), ds [M][n + h], dVh [3M][h].
+extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* Wu, const float* Wf, const float* Wg,
+                                const float* Vh, const float* Vu, const float* s, const float* z, const float* f,
+                                const float* gates, const float* df_out, const float* dvout, int64_t M, int32_t n,
+                                int32_t vi, int32_t h, int32_t vo, int32_t no, int32_t act_sigmoid, float* dgates,
+                                float* dVu, float* dfz, float* ds, float* dVh, float* dfeats, float* dvec, float* dWh,
+                                float* dWu, float* dWf, float* dbf, float* dWg, float* dbg, void* stream) {
+  PF_CHECK_ARG(vec && Wh && Wu && Wf && Wg && Vh && Vu && s && z && f && gates && df_out && dvout && dgates && dVu && dfz &&
+                   ds && dVh && dfeats && dvec && dWh && dWu && dWf && dbf && dWg && dbg,
+               "pf_train_gvp_bwd: null pointer");
+  if (M == 0) return PF_OK;
+  const int M3 = (int)(3 * M), K = n + h, Mi = (int)M;
+  const int sk = wgrad_splits(M), sk3 = wgrad_splits(3 * M);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  T::gate_bwd_kernel<<<blocks_for(M * vo, 256), 256, 0, st>>>(gates, Vu, dvout, dgates, dVu, M, vo, act_sigmoid);
+  PF_CHECK_LAUNCH("pf_train_gvp_bwd(gate)");
+  // gates = f Wg^T + bg
+  if ((rc = sgemm_ld(dgates, f, nullptr, dWg, vo, no, Mi, 1, vo, no, 1, no, 0, sk, stream)) != PF_OK) return rc;  // dWg = dgates^T f
+  if ((rc = pf_train_colsum(dgates, dbg, M, vo, stream)) != PF_OK) return rc;
+  cudaError_t e = cudaMemcpyAsync(dfz, df_out, (size_t)M * no * 4, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) {
+    set_error("pf_train_gvp_bwd: copy: %s", cudaGetErrorString(e));
+    return PF_ERR_LAUNCH;
+  }
+  if ((rc = sgemm_ld(dgates, Wg, nullptr, dfz, Mi, no, vo, vo, 1, no, 1, no, 1, 1, stream)) != PF_OK) return rc;  // df += dgates Wg
+  T::silu_bwd_kernel<<<blocks_for(M * no, 256), 256, 0, st>>>(z, dfz, dfz, M * no);                              // dz in place
+  PF_CHECK_LAUNCH("pf_train_gvp_bwd(silu)");
+  // z = s Wf^T + bf
+  if ((rc = sgemm_ld(dfz, s, nullptr, dWf, no, K, Mi, 1, no, K, 1, K, 0, sk, stream)) != PF_OK) return rc;       // dWf = dz^T s
+  if ((rc = pf_train_colsum(dfz, dbf, M, no, stream)) != PF_OK) return rc;
+  if ((rc = sgemm_ld(dfz, Wf, nullptr, ds, Mi, K, no, no, 1, K, 1, K, 0, 1, stream)) != PF_OK) return rc;        // ds = dz Wf
+  e = cudaMemcpy2DAsync(dfeats, (size_t)n * 4, ds, (size_t)K * 4, (size_t)n * 4, (size_t)M, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) {
+    set_error("pf_train_gvp_bwd: copy: %s", cudaGetErrorString(e));
+    return PF_ERR_LAUNCH;
+  }
+  T::vecnorm_bwd_kernel<<<blocks_for(M * h, 256), 256, 0, st>>>(Vh, ds + n, dVh, M, h, K);                        // via sh
+  PF_CHECK_LAUNCH("pf_train_gvp_bwd(vecnorm)");
+  // Vu = Vh Wu
+  if ((rc = sgemm_ld(dVu, Wu, nullptr, dVh, M3, h, vo, vo, 1, 1, vo, h, 1, 1, stream)) != PF_OK) return rc;      // dVh += dVu Wu^T
+  if ((rc = sgemm_ld(Vh, dVu, nullptr, dWu, h, vo, M3, 1, h, vo, 1, vo, 0, sk3, stream)) != PF_OK) return rc;    // dWu = Vh^T dVu
+  // Vh = V Wh
+  if ((rc = sgemm_ld(dVh, Wh, nullptr, dvec, M3, vi, h, h, 1, 1, h, vi, 0, 1, stream)) != PF_OK) return rc;      // dV = dVh Wh^T
+  if ((rc = sgemm_ld(vec, dVh, nullptr, dWh, vi, h, M3, 1, vi, h, 1, h, 0, sk3, stream)) != PF_OK) return rc;    // dWh = V^T dVh
   return PF_OK;
 }

@@ -21,7 +21,15 @@ from .batch import GraphBatch
 
 
 def gvp_forward(m, feats: torch.Tensor, vec: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """GVP.forward (gvp.py:89-116) on (feats [M, n], vec [M, 3, v])."""
+    """GVP.forward (gvp.py:89-116) on (feats [M, n], vec [M, 3, v]): one differentiable op whose forward / backward
+    enqueue the primitive kernels back to back (Vh, Vu, norms, Linear + SiLU, gates, gating)."""
+    lin, gl = m.to_feats_out[0], m.scalar_to_vector_gates
+    return T.gvp(feats, vec, m.Wh, m.Wu, lin.weight, lin.bias, gl.weight, gl.bias,
+                 isinstance(m.vectors_activation, nn.Sigmoid))
+
+
+def gvp_forward_unfused(m, feats: torch.Tensor, vec: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The same GVP composed of the single-kernel ops (kept for the op-level tests and as the readable definition)."""
     M = feats.shape[0]
     vi, h = m.Wh.shape
     vo = m.Wu.shape[1]

@@ -351,3 +351,82 @@ def edge_geom(src_x: torch.Tensor, dst_x: torch.Tensor, src: torch.Tensor, dst: 
 @edge_geom.register_fake
 def _(src_x, dst_x, src, dst):
     return src_x.new_empty(src.numel(), 3), src_x.new_empty(src.numel(), 16)
+
+
+# ------------------------------------------------------------------------------------------------ one GVP per op
+@torch.library.custom_op(f"{NS}::train_gvp", mutates_args=())
+def _gvp_fwd(feats: torch.Tensor, vec: torch.Tensor, Wh: torch.Tensor, Wu: torch.Tensor, Wf: torch.Tensor,
+             bf: torch.Tensor, Wg: torch.Tensor, bg: torch.Tensor, act_sigmoid: bool) -> Tuple[
+                 torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    M, n = feats.shape
+    vi, h = Wh.shape
+    vo, no = Wu.shape[1], Wf.shape[0]
+    e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=feats.device)
+    Vh, Vu, s, z, f, gates, vout = e(3 * M, h), e(3 * M, vo), e(M, n + h), e(M, no), e(M, no), e(M, vo), e(M, 3, vo)
+    _lib.check(_L.pf_train_gvp_fwd(_f(feats), _f(vec), _f(Wh), _f(Wu), _f(Wf), _f(bf), _f(Wg), _f(bg), M, n, vi, h, vo, no,
+                                   int(act_sigmoid), _f(Vh), _f(Vu), _f(s), _f(z), _f(f), _f(gates), _f(vout), _s()),
+               "pf_train_gvp_fwd")
+    return f, vout, Vh, Vu, s, z, gates
+
+
+@_gvp_fwd.register_fake
+def _(feats, vec, Wh, Wu, Wf, bf, Wg, bg, act_sigmoid):
+    M, n = feats.shape
+    h, vo, no = Wh.shape[1], Wu.shape[1], Wf.shape[0]
+    e = feats.new_empty
+    return e(M, no), e(M, 3, vo), e(3 * M, h), e(3 * M, vo), e(M, n + h), e(M, no), e(M, vo)
+
+
+@torch.library.custom_op(f"{NS}::train_gvp_bwd", mutates_args=())
+def _gvp_bwd(vec: torch.Tensor, Wh: torch.Tensor, Wu: torch.Tensor, Wf: torch.Tensor, Wg: torch.Tensor, Vh: torch.Tensor,
+             Vu: torch.Tensor, s: torch.Tensor, z: torch.Tensor, f: torch.Tensor, gates: torch.Tensor, df: torch.Tensor,
+             dvout: torch.Tensor, act_sigmoid: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                                                              torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    M = z.shape[0]
+    vi, h = Wh.shape
+    vo, no = Wu.shape[1], Wf.shape[0]
+    n = Wf.shape[1] - h
+    e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=z.device)
+    dgates, dVu, dfz, ds, dVh = e(M, vo), e(3 * M, vo), e(M, no), e(M, n + h), e(3 * M, h)
+    dfeats, dvec = e(M, n), e(M, 3, vi)
+    dWh, dWu, dWf, dWg = e(vi, h), e(h, vo), e(no, n + h), e(vo, no)
+    dbf, dbg = torch.zeros(no, device=z.device), torch.zeros(vo, device=z.device)
+    _lib.check(_L.pf_train_gvp_bwd(_f(vec), _f(Wh), _f(Wu), _f(Wf), _f(Wg), _f(Vh), _f(Vu), _f(s), _f(z), _f(f), _f(gates),
+                                   _f(df), _f(dvout), M, n, vi, h, vo, no, int(act_sigmoid), _f(dgates), _f(dVu), _f(dfz),
+                                   _f(ds), _f(dVh), _f(dfeats), _f(dvec), _f(dWh), _f(dWu), _f(dWf), _f(dbf), _f(dWg),
+                                   _f(dbg), _s()), "pf_train_gvp_bwd")
+    return dfeats, dvec, dWh, dWu, dWf, dbf, dWg, dbg
+
+
+@_gvp_bwd.register_fake
+def _(vec, Wh, Wu, Wf, Wg, Vh, Vu, s, z, f, gates, df, dvout, act_sigmoid):
+    M = z.shape[0]
+    n = Wf.shape[1] - Wh.shape[1]
+    e = z.new_empty
+    return (e(M, n), e(M, 3, Wh.shape[0]), e(Wh.shape), e(Wu.shape), e(Wf.shape), e(Wf.shape[0]), e(Wg.shape),
+            e(Wg.shape[0]))
+
+
+def _gvp_setup(ctx, inputs, output):
+    feats, vec, Wh, Wu, Wf, bf, Wg, bg, act = inputs
+    f, vout, Vh, Vu, s, z, gates = output
+    ctx.save_for_backward(vec, Wh, Wu, Wf, Wg, Vh, Vu, s, z, f, gates)
+    ctx.act = act
+
+
+def _gvp_backward(ctx, df, dvout, *unused):
+    vec, Wh, Wu, Wf, Wg, Vh, Vu, s, z, f, gates = ctx.saved_tensors
+    df = torch.zeros_like(f) if df is None else df.contiguous()
+    dvout = torch.zeros(z.shape[0], 3, Wu.shape[1], device=z.device) if dvout is None else dvout.contiguous()
+    dfeats, dvec, dWh, dWu, dWf, dbf, dWg, dbg = _gvp_bwd(vec, Wh, Wu, Wf, Wg, Vh, Vu, s, z, f, gates, df, dvout, ctx.act)
+    return dfeats, dvec, dWh, dWu, dWf, dbf, dWg, dbg, None
+
+
+_gvp_fwd.register_autograd(_gvp_backward, setup_context=_gvp_setup)
+
+
+def gvp(feats: torch.Tensor, vec: torch.Tensor, Wh: torch.Tensor, Wu: torch.Tensor, Wf: torch.Tensor, bf: torch.Tensor,
+        Wg: torch.Tensor, bg: torch.Tensor, act_sigmoid: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GVP.forward (gvp.py:89-116) as one differentiable op: (feats [M,n], vec [M,3,vi]) -> (f [M,no], vout [M,3,vo])."""
+    out = _gvp_fwd(feats.contiguous(), vec.contiguous(), Wh, Wu, Wf, bf, Wg, bg, act_sigmoid)
+    return out[0], out[1]

@@ -111,6 +111,26 @@ def test_gather_segmean_geom(T):
     close(rbf, torch.exp(-((dist - mu) / (15 / 16)) ** 2), what="rbf")
 
 
+@pytest.mark.parametrize("vi,vo,n,no,act", [(17, 16, 144, 128, True), (16, 16, 128, 128, True), (16, 1, 128, 64, False)])
+def test_fused_gvp_op_matches_the_unfused_composition(T, vi, vo, n, no, act):
+    """T.gvp (one host call per GVP, forward and backward) against the same GVP composed of the single-kernel ops."""
+    from pharmacoforge_b200 import train_graph
+    from pharmacoforge_b200.dynamics import GVP
+    torch.manual_seed(vi * 100 + no)
+    m = GVP(vi, vo, n, no, vectors_activation=None if act else torch.nn.Identity()).cuda()
+    M = 777
+    feats, vec = rnd(M, n, seed=21), rnd(M, 3, vi, seed=22)
+    outs = []
+    for fn in (train_graph.gvp_forward, train_graph.gvp_forward_unfused):
+        m.zero_grad()
+        a, b = feats.clone().requires_grad_(True), vec.clone().requires_grad_(True)
+        f, v = fn(m, a, b)
+        (f * rnd(M, no, seed=23)).sum().add((v * rnd(M, 3, vo, seed=24)).sum()).backward()
+        outs.append([f, v, a.grad, b.grad] + [p.grad.clone() for p in m.parameters()])
+    for i, (x, y) in enumerate(zip(*outs)):
+        close(x, y, rtol=5e-4, what=f"gvp output/grad {i}")
+
+
 def _model(sd, dyn_cfg, dropout):
     from pharmacoforge_b200.diffusion import PharmacophoreDiff
     cfg = dict(dyn_cfg, dropout=dropout)
