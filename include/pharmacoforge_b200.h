@@ -139,6 +139,14 @@ int pf_edge_conv_tc(const float* src_h, const float* src_v, const float* src_x, 
                     const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
                     const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const void* wblob, float* agg_h,
                     float* agg_v, int32_t accumulate, void* stream);
+/* Single-pass fp16 variant -- the reduced-precision edge-MLP path of BASELINE.json configs[3]: same arguments and weight
+ * image; every contraction is ONE tcgen05.mma pass over the fp16 hi parts (11-bit operands, fp32 accumulation) and SiLU
+ * runs on packed fp16 pairs.  Tolerance: eps within 2e-2 of max|eps| per call (tests/test_gpu_tcgen05.py), not the
+ * 1e-4 fp32 bar -- never used unless asked for (PF_FLAG_FP16_SINGLE_PASS / dynamics.edge_mlp_precision = "fp16"). */
+int pf_edge_conv_tc_f16(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+                        const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
+                        const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const void* wblob,
+                        float* agg_h, float* agg_v, int32_t accumulate, void* stream);
 
 /* Debug timeline of CTA 0 of the next pf_edge_conv_tc launches: device_buf = int64[4][4096][2] of (tag, clock64)
  * for the epilogue of tile slot 0 / 1 and the two MMA issuers; NULL disarms.  Not used on the product path. */
@@ -157,6 +165,8 @@ int pf_node_update(const float* h_in, const float* v_in, const float* agg_h, con
 size_t pf_tc_upd_blob_bytes(void);
 int pf_node_update_tc(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v, int64_t n_nodes,
                       const void* wblob, float* h_out, float* v_out, void* stream);
+int pf_node_update_tc_f16(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v, int64_t n_nodes,
+                          const void* wblob, float* h_out, float* v_out, void* stream); /* single fp16 pass, see above */
 
 /* ---- K5a: noise head -------------------------------------------------------------------------------
  * NoisePredictionBlock (dynamics_gvp.py:10-42): (n_gvps-1) x GVP(16,16,128,128) + GVP(16,1,128,64) with
@@ -233,6 +243,9 @@ typedef struct PfSampleArgs {
   uint32_t flags;
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
+/* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph
+ * kernels, noise head and posterior step are unchanged (fp32).  Off by default: the default is the fp32-parity mode. */
+#define PF_FLAG_FP16_SINGLE_PASS 2u
 
 /* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the
  * timestep value of graph g.  Results in a->eps_h / a->eps_x. */

@@ -229,22 +229,25 @@ extern "C" int pf_fill_f32(float* p, int64_t n, float v, void* stream) {
     if (rc_ != PF_OK) return rc_; \
   } while (0)
 
-static int edge_conv_any(bool tc, const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+static int edge_conv_any(bool tc, bool f16, const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
                          const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
                          const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const float* w,
                          const void* w_tc, int32_t n_gvps, float* agg_h, float* agg_v, int32_t accumulate,
                          void* stream) {
   if (tc)
-    return pf_edge_conv_tc(src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles, max_tiles,
-                           w_tc, agg_h, agg_v, accumulate, stream);
+    return (f16 ? pf_edge_conv_tc_f16 : pf_edge_conv_tc)(src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col,
+                                                         tiles, n_tiles, max_tiles, w_tc, agg_h, agg_v, accumulate,
+                                                         stream);
   return pf_edge_conv(src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles, max_tiles, w,
                       n_gvps, agg_h, agg_v, accumulate, stream);
 }
 
-static int node_update_any(const void* w_tc, const float* h_in, const float* v_in, const float* agg_h,
+static int node_update_any(bool f16, const void* w_tc, const float* h_in, const float* v_in, const float* agg_h,
                            const float* agg_v, int64_t n_nodes, const float* w, int32_t n_gvps, float* h_out,
                            float* v_out, void* stream) {
-  if (w_tc != nullptr) return pf_node_update_tc(h_in, v_in, agg_h, agg_v, n_nodes, w_tc, h_out, v_out, stream);
+  if (w_tc != nullptr)
+    return (f16 ? pf_node_update_tc_f16 : pf_node_update_tc)(h_in, v_in, agg_h, agg_v, n_nodes, w_tc, h_out, v_out,
+                                                             stream);
   return pf_node_update(h_in, v_in, agg_h, agg_v, n_nodes, w, n_gvps, h_out, v_out, stream);
 }
 
@@ -261,6 +264,8 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_TRY(pf_zero_i32(a->dyn_n_tiles, 3, stream));
   PF_CHECK_ARG(a->tile_rows == PF_TILE_ROWS || a->tile_rows == PF_TC_TILE_ROWS, "pf_denoiser: tile_rows must be 64 or 128");
   const bool tc = a->tile_rows == PF_TC_TILE_ROWS;
+  const bool f16 = (a->flags & PF_FLAG_FP16_SINGLE_PASS) != 0;
+  PF_CHECK_ARG(!f16 || tc, "pf_denoiser: PF_FLAG_FP16_SINGLE_PASS needs the tcgen05 path (tile_rows = 128)");
   if (tc) {
     PF_CHECK_ARG(a->n_msg_gvps == 3, "pf_denoiser: the tcgen05 message kernel is built for n_message_gvps == 3");
     for (int l = 0; l < a->n_convs; ++l)
@@ -282,12 +287,12 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     const float* pv = l == 0 ? nullptr : a->prot_v;
     // pharm <- ff (store) + pf (accumulate); prot <- pp (store) + fp (accumulate)  (gvp.py:484-497)
     prof_begin(kSiteFF, as_stream(stream));
-    PF_TRY(edge_conv_any(tc, a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
+    PF_TRY(edge_conv_any(tc, f16, a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
                          a->ff_tiles, a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg[l][0], a->w_msg_tc[l][0],
                          a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 0, stream));
   prof_end(kSiteFF, as_stream(stream));
     prof_begin(kSitePF, as_stream(stream));
-    PF_TRY(edge_conv_any(tc, a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col,
+    PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col,
                          a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->w_msg_tc[l][1],
                          a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
   prof_end(kSitePF, as_stream(stream));
@@ -295,24 +300,24 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     const bool prot_side = !((a->flags & PF_FLAG_SKIP_DEAD_WORK) && l == a->n_convs - 1);
     if (prot_side) {
     prof_begin(kSitePP, as_stream(stream));
-    PF_TRY(edge_conv_any(tc, a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col,
+    PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col,
                          a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->w_msg_tc[l][3],
                          a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 0, stream));
   prof_end(kSitePP, as_stream(stream));
     prof_begin(kSiteFP, as_stream(stream));
-    PF_TRY(edge_conv_any(tc, a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
+    PF_TRY(edge_conv_any(tc, f16, a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
                          a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2],
                          a->w_msg_tc[l][2], a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 1, stream));
   prof_end(kSiteFP, as_stream(stream));
     }
     // node updates, in place (gvp.py:501-536)
     prof_begin(kSiteUpdPharm, as_stream(stream));
-    PF_TRY(node_update_any(tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][0] : nullptr, a->pharm_hh, fv, a->pharm_agg_h,
+    PF_TRY(node_update_any(f16, tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][0] : nullptr, a->pharm_hh, fv, a->pharm_agg_h,
                            a->pharm_agg_v, a->n_pharm, a->w_upd[l][0], a->n_upd_gvps, a->pharm_hh, a->pharm_v, stream));
   prof_end(kSiteUpdPharm, as_stream(stream));
     if (prot_side) {
     prof_begin(kSiteUpdProt, as_stream(stream));
-    PF_TRY(node_update_any(tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][1] : nullptr, a->prot_h, pv, a->prot_agg_h,
+    PF_TRY(node_update_any(f16, tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][1] : nullptr, a->prot_h, pv, a->prot_agg_h,
                            a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps, a->prot_h, a->prot_v, stream));
   prof_end(kSiteUpdProt, as_stream(stream));
     }

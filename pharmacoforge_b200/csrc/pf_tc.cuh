@@ -54,6 +54,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// L2 prefetch of a contiguous global range by the bulk-copy engine (one instruction, no destination): 16-byte aligned
+// address, size a multiple of 16
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -195,6 +201,32 @@ __device__ __forceinline__ void silu_split2(uint32_t a0, uint32_t a1, uint64_t b
   float l0, l1;
   unpack2(sub2(f, pack2(hf.x, hf.y)), l0, l1);
   lo = pack_f16x2_sat(l0, l1);
+}
+
+// ---------------------------------------------------------------- single-pass fp16 mode (PF_FLAG_FP16_SINGLE_PASS)
+// SiLU on packed fp16 pairs: silu(y) = h + h tanh(h), h = y / 2, with ONE MUFU op per PAIR of elements
+// (tanh.approx.f16x2, relative error ~2^-11 -- the precision of the fp16 operand it feeds) instead of the four of the
+// fp32-parity form: 5 instructions per pair (FADD2, F2FP, HMUL2, MUFU.TANH, HFMA2) against 13.
+__device__ __forceinline__ uint32_t tanh_h2(uint32_t x) {
+  uint32_t r;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t hmul2_u(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t silu_h2(uint32_t a0, uint32_t a1, uint64_t bias) {
+  float y0, y1;
+  unpack2(add2(pack2(__uint_as_float(a0), __uint_as_float(a1)), bias), y0, y1);
+  const uint32_t h = hmul2_u(pack_f16x2_sat(y0, y1), 0x38003800u);  // x 0.5 (exact)
+  return hfma2_u(h, tanh_h2(h), h);
 }
 
 // ---------------------------------------------------------------- fp32 -> (hi, lo) bf16 split, packed pairs

@@ -177,7 +177,7 @@ __device__ __forceinline__ uint32_t full_parity(int i, uint32_t t) {
   return ((ring_uses<MODE>(i % kRing) & 1 ? t : 0u) + (uint32_t)(i / kRing)) & 1u;
 }
 
-template <int MODE, bool HAS_V>
+template <int MODE, bool HAS_V, bool FAST>
 __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint64_t* bar_empty,
                          SlotBars* sb, uint64_t* bar_small, uint64_t* bar_stagger, volatile int* turn, int my_tiles,
                          long long* trace_) {
@@ -227,8 +227,10 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
         for (int c = 0; c < 3; ++c) {
           const uint64_t a_hi = stage_hi + (uint64_t)(c * (8192 >> 4)), a_lo = stage_lo + (uint64_t)(c * (8192 >> 4));
           tc::mma_ss(Dreg + 32 * c, a_hi, b_hi, kI32, 0);
-          tc::mma_ss(Dreg + 32 * c, a_hi, b_lo, kI32, 1);
-          tc::mma_ss(Dreg + 32 * c, a_lo, b_hi, kI32, 1);
+          if constexpr (!FAST) {
+            tc::mma_ss(Dreg + 32 * c, a_hi, b_lo, kI32, 1);
+            tc::mma_ss(Dreg + 32 * c, a_lo, b_hi, kI32, 1);
+          }
         }
         tc::mma_commit(&B.vecD);
       }
@@ -257,13 +259,17 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
         if (k < 8) {
           const uint32_t a_hi = Areg + 16 * k, a_lo = a_hi + 8;
           tc::mma_ts(Dreg, a_hi, b_hi, kI128, k > 0);
-          tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
-          tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
+          if constexpr (!FAST) {
+            tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
+            tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
+          }
         } else {
           const uint64_t a_hi = stage_hi + (uint64_t)((k - 8) * (8192 >> 4)), a_lo = stage_lo + (uint64_t)((k - 8) * (8192 >> 4));
           tc::mma_ss(Dreg, a_hi, b_hi, kI128, 1);
-          tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
-          tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
+          if constexpr (!FAST) {
+            tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
+            tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
+          }
         }
         tc::mma_commit(&my_empty[pos]);
         if (k == nslab - 1) tc::mma_commit(&B.D);
@@ -294,8 +300,10 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
         const uint64_t b_hi = g_hi + (uint64_t)(k * (1024 >> 4)), b_lo = g_lo + (uint64_t)(k * (1024 >> 4));
         const uint32_t a_hi = Dreg + 16 * k, a_lo = a_hi + 8;
         tc::mma_ts(Areg, a_hi, b_hi, kI16, k > 0);
-        tc::mma_ts(Areg, a_hi, b_lo, kI16, 1);
-        tc::mma_ts(Areg, a_lo, b_hi, kI16, 1);
+        if constexpr (!FAST) {
+          tc::mma_ts(Areg, a_hi, b_lo, kI16, 1);
+          tc::mma_ts(Areg, a_lo, b_hi, kI16, 1);
+        }
       }
       tc::mma_commit(&B.gate);
     }
@@ -323,13 +331,19 @@ __device__ __forceinline__ void row_scale(float m, float& sc, float& inv) {
 }
 
 // 8 fp32 values of row m, K positions [8 kc, 8 kc + 8) of a [128 x 16] A operand slab (see stage layout above)
+template <bool FAST = false>
 __device__ __forceinline__ void stage_store8(uint8_t* slab, int m, int kc, const float* x) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) tc::split_pack_h(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
   uint8_t* a = slab + kc * 2048 + (m >> 3) * 128 + (m & 7) * 16;
-  *reinterpret_cast<uint4*>(a) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(a + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  if constexpr (FAST) {  // single fp16 pass: the lo image is never read
+    *reinterpret_cast<uint4*>(a) = make_uint4(tc::pack_f16x2_sat(x[0], x[1]), tc::pack_f16x2_sat(x[2], x[3]),
+                                              tc::pack_f16x2_sat(x[4], x[5]), tc::pack_f16x2_sat(x[6], x[7]));
+  } else {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc::split_pack_h(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+    *reinterpret_cast<uint4*>(a) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
 // Segmented mean over the rows of a tile staged in shared memory as buf[row][pitch] (fp32).  Work item = (segment,
@@ -397,7 +411,7 @@ __device__ __forceinline__ void segment_means(const float* buf, const int pitch,
 }
 
 // Two threads per edge row: half hh owns scalar columns [64 hh, 64 hh + 64) and vector channels [8 hh, 8 hh + 8).
-template <bool HAS_V>
+template <bool HAS_V, bool FAST>
 __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
                               uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
   const int stid = threadIdx.x & 255;
@@ -539,11 +553,16 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 v = *reinterpret_cast<const float4*>(tb + lane * 36 + 16 * ks + 4 * j);
-            tc::split_pack_h(v.x, v.y, hi[2 * j], lo[2 * j]);
-            tc::split_pack_h(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+            if constexpr (FAST) {
+              hi[2 * j] = tc::pack_f16x2_sat(v.x, v.y);
+              hi[2 * j + 1] = tc::pack_f16x2_sat(v.z, v.w);
+            } else {
+              tc::split_pack_h(v.x, v.y, hi[2 * j], lo[2 * j]);
+              tc::split_pack_h(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+            }
           }
           tc::tmem_st8(P + 32 * c + 16 * ks, hi);
-          tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
+          if constexpr (!FAST) tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
         }
         __syncwarp();
       }
@@ -600,7 +619,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         float t8[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t8[u] = Vu[8 * c + u] * vsc;
-        stage_store8(stage + c * 8192, et, hh, t8);
+        stage_store8<FAST>(stage + c * 8192, et, hh, t8);
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(&B.vecA);
@@ -670,14 +689,14 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
             const float z = (dist - (float)(8 * hh + k)) / 0.9375f;
             t8[k] = __expf(-(z * z));
           }
-          stage_store8(stage, et, hh, t8);
-          stage_store8(stage + 8192, et, hh, sh);
+          stage_store8<FAST>(stage, et, hh, t8);
+          stage_store8<FAST>(stage + 8192, et, hh, sh);
 #pragma unroll
           for (int k = 0; k < 8; ++k) t8[k] = 0.f;
           if (hh == 0) t8[0] = sh16;
-          stage_store8(stage + 16384, et, hh, t8);
+          stage_store8<FAST>(stage + 16384, et, hh, t8);
         } else {
-          stage_store8(stage, et, hh, sh);
+          stage_store8<FAST>(stage, et, hh, sh);
         }
         tc::fence_proxy_async();
         tc::wait_st();
@@ -696,7 +715,8 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         // half hh owns the 16-column chunks j = 4 hh .. 4 hh + 3 (one K-step of the next scalar operand each);
         // the TMEM load of chunk j + 1 is in flight while chunk j is processed
         uint32_t r[2][16];
-        float keep[32];  // last GVP: fp32 copy of chunks 2, 3 for the second mean pass
+        float keep[FAST ? 1 : 32];      // last GVP: fp32 copy of chunks 2, 3 for the second mean pass
+        uint32_t keeph[FAST ? 16 : 1];  // single-pass mode: the same as packed fp16 pairs
         tc::tmem_ld16(Dreg + 16 * (4 * hh), r[0]);
         tc::wait_ld();
         float* ab = reinterpret_cast<float*>(stage);  // mean staging [128][kMeanPitch]: 32 columns of each half per pass
@@ -707,22 +727,39 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           uint32_t hi[8], lo[8];
           float fv[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
-                            fv[2 * i], fv[2 * i + 1], hi[i], lo[i]);
+          for (int i = 0; i < 8; ++i) {
+            if constexpr (FAST) {
+              hi[i] = tc::silu_h2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i));
+            } else {
+              tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                              fv[2 * i], fv[2 * i + 1], hi[i], lo[i]);
+            }
+          }
           if (g == 2) {
             if (j4 < 2) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 16 * j4 + 4 * i) =
-                    make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
+              for (int i = 0; i < 4; ++i) {
+                if constexpr (FAST) {
+                  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * i]));
+                  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * i + 1]));
+                  *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 16 * j4 + 4 * i) = make_float4(a.x, a.y, b.x, b.y);
+                } else {
+                  *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 16 * j4 + 4 * i) =
+                      make_float4(fv[4 * i], fv[4 * i + 1], fv[4 * i + 2], fv[4 * i + 3]);
+                }
+              }
             } else {
+              if constexpr (FAST) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) keep[16 * (j4 - 2) + i] = fv[i];
+                for (int i = 0; i < 8; ++i) keeph[8 * (j4 - 2) + i] = hi[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) keep[16 * (j4 - 2) + i] = fv[i];
+              }
             }
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
-          tc::tmem_st8(Dreg + 16 * j + 8, lo);
+          if constexpr (!FAST) tc::tmem_st8(Dreg + 16 * j + 8, lo);
           if (j4 < 3) tc::wait_ld();
         }
         tc::wait_st();
@@ -734,9 +771,16 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           for (int ps = 0; ps < 2; ++ps) {
             if (ps == 1) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 4 * i) =
-                    make_float4(keep[4 * i], keep[4 * i + 1], keep[4 * i + 2], keep[4 * i + 3]);
+              for (int i = 0; i < 8; ++i) {
+                if constexpr (FAST) {
+                  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&keeph[2 * i]));
+                  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&keeph[2 * i + 1]));
+                  *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 4 * i) = make_float4(a.x, a.y, b.x, b.y);
+                } else {
+                  *reinterpret_cast<float4*>(ab + et * kMeanPitch + 32 * hh + 4 * i) =
+                      make_float4(keep[4 * i], keep[4 * i + 1], keep[4 * i + 2], keep[4 * i + 3]);
+                }
+              }
             }
             slot_barrier(T);
             trace_ev(trace, T, tn, (g << 8) | (0x23 + 3 * ps));
@@ -782,7 +826,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
             float t8[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) t8[u] = Vu[8 * c + u] * vsc;
-            stage_store8(stage + c * 8192, et, hh, t8);
+            stage_store8<FAST>(stage + c * 8192, et, hh, t8);
           }
           tc::fence_proxy_async();
           tc::mbar_arrive(&B.vecA);
@@ -807,7 +851,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   }
 }
 
-template <bool HAS_V>
+template <bool HAS_V, bool FAST>
 __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -850,9 +894,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   const uint32_t tmem = *s_tmem;
 
   if (warp < 16) {
-    epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+    epilogue_role<HAS_V, FAST>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    mma_role<0, HAS_V>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
+    mma_role<0, HAS_V, FAST>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
     if (lane == 0) producer_role<0>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
@@ -884,7 +928,7 @@ __device__ __forceinline__ float xor8_sum(float v) {  // sum over the 8 lanes th
   return v;
 }
 
-template <bool HAS_V>
+template <bool HAS_V, bool FAST>
 __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
                                    uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
   const int stid = threadIdx.x & 255;
@@ -982,11 +1026,16 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 v = *reinterpret_cast<const float4*>(tb + lane * 36 + 16 * ks + 4 * j);
-            tc::split_pack_h(v.x, v.y, hi[2 * j], lo[2 * j]);
-            tc::split_pack_h(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+            if constexpr (FAST) {
+              hi[2 * j] = tc::pack_f16x2_sat(v.x, v.y);
+              hi[2 * j + 1] = tc::pack_f16x2_sat(v.z, v.w);
+            } else {
+              tc::split_pack_h(v.x, v.y, hi[2 * j], lo[2 * j]);
+              tc::split_pack_h(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+            }
           }
           tc::tmem_st8(P + 32 * c + 16 * ks, hi);
-          tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
+          if constexpr (!FAST) tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
         }
         __syncwarp();
       }
@@ -1055,7 +1104,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         float t8[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t8[u] = Vu[8 * c + u] * vsc;
-        stage_store8(stage + c * 8192, et, hh, t8);
+        stage_store8<FAST>(stage + c * 8192, et, hh, t8);
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(&B.vecA);
@@ -1088,7 +1137,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         const float inv2 = vinv * vinv;
 #pragma unroll
         for (int h = 0; h < 8; ++h) sh[h] = sqrt_clamped(sh[h] * inv2);
-        stage_store8(stage, et, hh, sh);
+        stage_store8<FAST>(stage, et, hh, sh);
         tc::fence_proxy_async();
         tc::wait_st();
         tc::fence_before_sync();
@@ -1110,12 +1159,16 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float f0, f1;
-            tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
-                            f0, f1, hi[i], lo[i]);
+            if constexpr (FAST) {
+              hi[i] = tc::silu_h2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i));
+            } else {
+              float f0, f1;
+              tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                              f0, f1, hi[i], lo[i]);
+            }
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
-          tc::tmem_st8(Dreg + 16 * j + 8, lo);
+          if constexpr (!FAST) tc::tmem_st8(Dreg + 16 * j + 8, lo);
           if (j4 < 3) tc::wait_ld();
         }
         tc::wait_st();
@@ -1151,7 +1204,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
             float t8[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) t8[u] = Vu[8 * c + u] * vsc;
-            stage_store8(stage + c * 8192, et, hh, t8);
+            stage_store8<FAST>(stage + c * 8192, et, hh, t8);
           }
           tc::fence_proxy_async();
           tc::mbar_arrive(&B.vecA);
@@ -1215,12 +1268,12 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           const int j = 2 * c + ks;
           uint32_t hi[8], lo[8], y[16];
           tc::tmem_ld8(P + 16 * j, hi);
-          tc::tmem_ld8(P + 16 * j + 8, lo);
+          if constexpr (!FAST) tc::tmem_ld8(P + 16 * j + 8, lo);
           tc::wait_ld();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi[i]));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lo[i]));
+            const float2 b = FAST ? make_float2(0.f, 0.f) : __half22float2(*reinterpret_cast<const __half2*>(&lo[i]));
             const float y0 = (a.x + b.x) + tb[lane * 36 + 16 * ks + 2 * i];
             const float y1 = (a.y + b.y) + tb[lane * 36 + 16 * ks + 2 * i + 1];
             sum += y0 + y1;
@@ -1279,7 +1332,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
   }
 }
 
-template <bool HAS_V>
+template <bool HAS_V, bool FAST>
 __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const NodeParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -1322,9 +1375,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const Nod
   const uint32_t tmem = *s_tmem;
 
   if (warp < 16) {
-    node_epilogue_role<HAS_V>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+    node_epilogue_role<HAS_V, FAST>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    mma_role<1, true>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
+    mma_role<1, true, FAST>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
     if (lane == 0) producer_role<1>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
@@ -1347,7 +1400,7 @@ extern "C" int pf_tc_trace(long long* device_buf) {  // 4 * 4096 * 2 int64; null
   return PF_OK;
 }
 
-extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+static int launch_edge_conv_tc(bool fast, const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
                                const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
                                const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
                                const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream) {
@@ -1357,53 +1410,97 @@ extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const flo
   if (max_tiles <= 0) return PF_OK;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tcc::edge_conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tcc::kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tcc::edge_conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               tcc::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("pf_edge_conv_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
-      return PF_ERR_LAUNCH;
+    const void* fns[4] = {(const void*)tcc::edge_conv_tc_kernel<false, false>, (const void*)tcc::edge_conv_tc_kernel<true, false>,
+                          (const void*)tcc::edge_conv_tc_kernel<false, true>, (const void*)tcc::edge_conv_tc_kernel<true, true>};
+    for (const void* f : fns) {
+      const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tcc::kSmemBytes);
+      if (e != cudaSuccess) {
+        set_error("pf_edge_conv_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
+        return PF_ERR_LAUNCH;
+      }
     }
     configured = true;
   }
   tcc::Params p{src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
                 static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate, g_tc_trace};
   const int grid = max_tiles < kNumSms ? max_tiles : kNumSms;
-  if (src_v != nullptr)
-    tcc::edge_conv_tc_kernel<true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
-  else
-    tcc::edge_conv_tc_kernel<false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  cudaStream_t st = as_stream(stream);
+  if (fast) {
+    if (src_v != nullptr)
+      tcc::edge_conv_tc_kernel<true, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+    else
+      tcc::edge_conv_tc_kernel<false, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+  } else {
+    if (src_v != nullptr)
+      tcc::edge_conv_tc_kernel<true, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+    else
+      tcc::edge_conv_tc_kernel<false, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+  }
   PF_CHECK_LAUNCH("pf_edge_conv_tc");
   return PF_OK;
 }
 
-extern "C" int pf_node_update_tc(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
+extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+                               const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
+                               const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
+                               const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream) {
+  return launch_edge_conv_tc(false, src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
+                             max_tiles, wblob, agg_h, agg_v, accumulate, stream);
+}
+
+// Single-pass fp16 variant (the "bf16 edge-MLP path" of BASELINE.json configs[3]): same arguments and weight image,
+// products hi x hi only (11-bit operands, fp32 accumulation), SiLU on packed fp16 pairs.
+extern "C" int pf_edge_conv_tc_f16(const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
+                                   const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
+                                   const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
+                                   const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream) {
+  return launch_edge_conv_tc(true, src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
+                             max_tiles, wblob, agg_h, agg_v, accumulate, stream);
+}
+
+static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
                                  int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream) {
   PF_CHECK_ARG(h_in && agg_h && agg_v && wblob && h_out && v_out, "pf_node_update_tc: null pointer");
   PF_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 15) == 0, "pf_node_update_tc: weight blob must be 16-byte aligned");
   if (n_nodes <= 0) return PF_OK;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tcc::node_update_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tcc::kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tcc::node_update_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               tcc::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("pf_node_update_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
-      return PF_ERR_LAUNCH;
+    const void* fns[4] = {(const void*)tcc::node_update_tc_kernel<false, false>, (const void*)tcc::node_update_tc_kernel<true, false>,
+                          (const void*)tcc::node_update_tc_kernel<false, true>, (const void*)tcc::node_update_tc_kernel<true, true>};
+    for (const void* f : fns) {
+      const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tcc::kSmemBytes);
+      if (e != cudaSuccess) {
+        set_error("pf_node_update_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
+        return PF_ERR_LAUNCH;
+      }
     }
     configured = true;
   }
   tcc::NodeParams p{h_in, v_in, agg_h, agg_v, (long long)n_nodes, static_cast<const uint8_t*>(wblob), h_out, v_out, nullptr};
   const long long tiles = (n_nodes + tcc::kRows - 1) / tcc::kRows;
   const int grid = (int)(tiles < kNumSms ? tiles : kNumSms);
-  if (v_in != nullptr)
-    tcc::node_update_tc_kernel<true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
-  else
-    tcc::node_update_tc_kernel<false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  cudaStream_t st = as_stream(stream);
+  if (fast) {
+    if (v_in != nullptr)
+      tcc::node_update_tc_kernel<true, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+    else
+      tcc::node_update_tc_kernel<false, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+  } else {
+    if (v_in != nullptr)
+      tcc::node_update_tc_kernel<true, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+    else
+      tcc::node_update_tc_kernel<false, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
+  }
   PF_CHECK_LAUNCH("pf_node_update_tc");
   return PF_OK;
+}
+
+extern "C" int pf_node_update_tc(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
+                                 int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream) {
+  return launch_node_update_tc(false, h_in, v_in, agg_h, agg_v, n_nodes, wblob, h_out, v_out, stream);
+}
+
+extern "C" int pf_node_update_tc_f16(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
+                                     int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream) {
+  return launch_node_update_tc(true, h_in, v_in, agg_h, agg_v, n_nodes, wblob, h_out, v_out, stream);
 }

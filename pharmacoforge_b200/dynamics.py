@@ -205,6 +205,10 @@ class PharmRecDynamicsGVP(nn.Module):
         # protein node update can be dropped without changing a bit of (eps_h, eps_x).  Off by default: the nominal
         # path does the reference's full work.  Not a constructor argument (the reference signature is kept).
         self.skip_dead_work = False
+        # Edge / update MLP precision on the tensor cores: "fp32" (default; fp16 hi/lo split, three passes, inside the
+        # 1e-4 parity bar) or "fp16" (PF_FLAG_FP16_SINGLE_PASS: one pass over 11-bit operands, SiLU on packed fp16
+        # pairs -- the reduced-precision path of BASELINE.json configs[3], tolerance stated in the tests).
+        self.edge_mlp_precision = "fp32"
         self._packed: Optional[PackedWeights] = None
         self._packed_key = None
 
@@ -226,7 +230,10 @@ class PharmRecDynamicsGVP(nn.Module):
         if st is None or st.weights is not w or any(a is not b for a, b in zip(st.batch_buffers, cur)):
             st = _DeviceState(self, g, w)
             g._pf_state = st
-        st.args.flags = 1 if self.skip_dead_work else 0   # PF_FLAG_SKIP_DEAD_WORK
+        if self.edge_mlp_precision not in ("fp32", "fp16"):
+            raise ValueError("edge_mlp_precision must be 'fp32' or 'fp16'")
+        st.args.flags = ((1 if self.skip_dead_work else 0) |               # PF_FLAG_SKIP_DEAD_WORK
+                         (2 if self.edge_mlp_precision == "fp16" else 0))   # PF_FLAG_FP16_SINGLE_PASS
         return st
 
     # ------------------------------------------------------------------ forward

@@ -146,11 +146,12 @@ def edge_conv(src_h: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torch.T
 def edge_conv_tc(src_h: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torch.Tensor, dst_x: torch.Tensor,
                  seg_start: torch.Tensor, seg_cnt: torch.Tensor, seg_dst: Optional[torch.Tensor], col: torch.Tensor,
                  tiles: torch.Tensor, n_tiles: torch.Tensor, wblob: torch.Tensor, agg_h: torch.Tensor,
-                 agg_v: torch.Tensor, accumulate: bool) -> None:
-    """K3 on the tensor cores (tcgen05): tiles must be planned with tile_rows=128; wblob from pack_message_tc."""
+                 agg_v: torch.Tensor, accumulate: bool, fp16: bool = False) -> None:
+    """K3 on the tensor cores (tcgen05): tiles must be planned with tile_rows=128; wblob from pack_message_tc.
+    fp16=True: the single-pass reduced-precision variant (pf_edge_conv_tc_f16)."""
     if wblob.dtype != torch.uint8 or wblob.numel() != _L.pf_tc_msg_blob_bytes():
         raise _lib.PfError("edge_conv_tc: wblob must be the uint8 image built by weights.pack_message_tc")
-    _lib.check(_L.pf_edge_conv_tc(_f(src_h), _f(src_v), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt), _i(seg_dst),
+    _lib.check((_L.pf_edge_conv_tc_f16 if fp16 else _L.pf_edge_conv_tc)(_f(src_h), _f(src_v), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt), _i(seg_dst),
                                   _i(col), _i(tiles), _i(n_tiles), tiles.numel() // 2, _p(wblob), _f(agg_h),
                                   _f(agg_v), int(accumulate), _s()), "pf_edge_conv_tc")
 
@@ -164,11 +165,11 @@ def node_update(h_in: torch.Tensor, v_in: Optional[torch.Tensor], agg_h: torch.T
 
 @torch.library.custom_op(f"{NS}::node_update_tc", mutates_args=("h_out", "v_out"))
 def node_update_tc(h_in: torch.Tensor, v_in: Optional[torch.Tensor], agg_h: torch.Tensor, agg_v: torch.Tensor,
-                   wblob: torch.Tensor, h_out: torch.Tensor, v_out: torch.Tensor) -> None:
-    """K4 on the tensor cores (tcgen05); wblob from weights.pack_update_tc."""
+                   wblob: torch.Tensor, h_out: torch.Tensor, v_out: torch.Tensor, fp16: bool = False) -> None:
+    """K4 on the tensor cores (tcgen05); wblob from weights.pack_update_tc.  fp16=True: pf_node_update_tc_f16."""
     if wblob.dtype != torch.uint8 or wblob.numel() != _L.pf_tc_upd_blob_bytes():
         raise _lib.PfError("node_update_tc: wblob must be the uint8 image built by weights.pack_update_tc")
-    _lib.check(_L.pf_node_update_tc(_f(h_in), _f(v_in), _f(agg_h), _f(agg_v), h_in.shape[0], _p(wblob), _f(h_out),
+    _lib.check((_L.pf_node_update_tc_f16 if fp16 else _L.pf_node_update_tc)(_f(h_in), _f(v_in), _f(agg_h), _f(agg_v), h_in.shape[0], _p(wblob), _f(h_out),
                                     _f(v_out), _s()), "pf_node_update_tc")
 
 

@@ -14,6 +14,7 @@ model = PharmacophoreDiff(6, 11, ["a","b","c","d","e","f"], n_timesteps=100, gra
 model.load_state_dict(sd); model.eval()
 dev = torch.device("cuda:0")
 npk = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+FP16 = len(sys.argv) > 3 and sys.argv[3] == 'fp16'
 pockets = [Pocket.from_numpy(*make_pocket(400, seed=i)) for i in range(npk)]
 g = GraphBatch.from_pockets(pockets, [readme_sizes(30)] * npk, dev)
 W = model.dynamics.packed_weights(dev)
@@ -22,7 +23,7 @@ prot_h = torch.randn(g.n_prot, 128, device=dev); prot_v = torch.randn(g.n_prot, 
 agg_h = torch.zeros(g.n_prot, 128, device=dev); agg_v = torch.zeros(g.n_prot, 48, device=dev)
 blob = W.tc[3 * W.tc_stride:4 * W.tc_stride]
 def run(v):
-    ops.edge_conv_tc(prot_h, v, g.prot_x, g.prot_x, g.pp_start, g.pp_cnt, None, g.pp_col, g.pp_tiles, g.pp_n_tiles, blob, agg_h, agg_v, False)
+    ops.edge_conv_tc(prot_h, v, g.prot_x, g.prot_x, g.pp_start, g.pp_cnt, None, g.pp_col, g.pp_tiles, g.pp_n_tiles, blob, agg_h, agg_v, False, FP16)
 for v in (None, prot_v):
     run(v); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -44,7 +45,7 @@ for r in range(4):
         if r < 2:
             ev.append((clk - t0, f"slot{r} epi g={tag >> 8} {names.get(tag & 0xff, hex(tag & 0xff))}"))
         else:
-            if 0x40 <= (tag & 0xff) < 0x50 and len(sys.argv) <= 3: continue
+            if 0x40 <= (tag & 0xff) < 0x50: continue
             ev.append((clk - t0, f"      MMA slot{r - 2} g={(tag >> 8) & 15} {mn.get(tag & 0xff, hex(tag & 0xff))}"))
 ev.sort()
 lim = int(sys.argv[2]) if len(sys.argv) > 2 else 130
