@@ -321,6 +321,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// named barrier + AND-reduction of a predicate over its participants (bar.red): one barrier that is also a vote
+__device__ __forceinline__ bool named_bar_and(int id, int threads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "bar.red.and.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(r)
+      : "r"(id), "r"(threads), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

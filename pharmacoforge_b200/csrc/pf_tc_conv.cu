@@ -366,9 +366,12 @@ __device__ __forceinline__ void lds128_if(float4& v, const float* ptr, bool pred
       : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
       : "r"(tc::smem_u32(ptr)), "r"((uint32_t)pred));
 }
-__device__ __forceinline__ void segment_means(const float* buf, const int pitch, const int c8, const int jfirst,
-                                              const int nseg, const int4* s_rec, float* out, const int out_pitch,
-                                              const int accumulate) {
+// A thread owns two column quads, `bx` and `by` (buffer addresses of row 0) -> `ox` and `oy` (output addresses of
+// destination 0): the eight threads of a segment read 128 contiguous bytes per quad and row, i.e. one shared-memory
+// wavefront per quarter warp (8 consecutive columns per thread cost two).
+__device__ __forceinline__ void segment_means(const float* bx, const float* by, const int pitch, const int jfirst,
+                                              const int nseg, const int4* s_rec, float* ox, float* oy,
+                                              const int out_pitch, const int accumulate) {
   for (int j = jfirst; j < nseg; j += 32) {
     const int4 rec = s_rec[j];
     const int r0 = rec.x, r1 = rec.y;
@@ -376,13 +379,12 @@ __device__ __forceinline__ void segment_means(const float* buf, const int pitch,
     uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;  // four packed fp32 pairs: columns (0,1) (2,3) (4,5) (6,7) of the group
     for (int r = r0; r < r1; r += 8) {
       float4 x[8], y[8];
-      const float* b = buf + r * pitch + 8 * c8;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         y[i] = x[i];
-        lds128_if(x[i], b + i * pitch, r + i < r1);
-        lds128_if(y[i], b + i * pitch + 4, r + i < r1);
+        lds128_if(x[i], bx + (r + i) * pitch, r + i < r1);
+        lds128_if(y[i], by + (r + i) * pitch, r + i < r1);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {  // row order, two columns per FADD2
@@ -399,13 +401,13 @@ __device__ __forceinline__ void segment_means(const float* buf, const int pitch,
     tc::unpack2(tc::mul2(s1, rc2), a0.z, a0.w);
     tc::unpack2(tc::mul2(s2, rc2), a1.x, a1.y);
     tc::unpack2(tc::mul2(s3, rc2), a1.z, a1.w);
-    float* o = out + (size_t)rec.z * out_pitch;
+    const size_t o = (size_t)rec.z * out_pitch;
     if (accumulate) {
-      atomicAdd(reinterpret_cast<float4*>(o), a0);
-      atomicAdd(reinterpret_cast<float4*>(o) + 1, a1);
+      atomicAdd(reinterpret_cast<float4*>(ox + o), a0);
+      atomicAdd(reinterpret_cast<float4*>(oy + o), a1);
     } else {
-      *reinterpret_cast<float4*>(o) = a0;
-      *(reinterpret_cast<float4*>(o) + 1) = a1;
+      *reinterpret_cast<float4*>(ox + o) = a0;
+      *reinterpret_cast<float4*>(oy + o) = a1;
     }
   }
 }
@@ -442,11 +444,14 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   // records of its next tile are loaded one tile ahead, so the per-tile start-up does not wait on two dependent
   // global round trips.
   int pf_s0 = 0, pf_nseg = 0, pf_c = 0, pf_start = 0, pf_dst = 0, pf2_s0 = 0, pf2_s1 = 0;
+  int pf_off = 0, pf_next = 0;  // start - start of the tile's first segment; start of the next segment
   auto load_segs = [&](int s0_, int nseg_) {
     pf_c = 0;
     if (hh == 0 && et < nseg_) {
       pf_c = __ldg(p.seg_cnt + s0_ + et);
       pf_start = __ldg(p.seg_start + s0_ + et);
+      pf_off = pf_start - __ldg(p.seg_start + s0_);
+      pf_next = et + 1 < nseg_ ? __ldg(p.seg_start + s0_ + et + 1) : pf_start + pf_c;
       pf_dst = p.seg_dst ? __ldg(p.seg_dst + s0_ + et) : s0_ + et;
     }
   };
@@ -464,7 +469,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
 
   for (int it = T; it < my_tiles; it += 2) {
     const int s0 = pf_s0, nseg = pf_nseg;
-    const int cur_c = pf_c, cur_start = pf_start, cur_dst = pf_dst;
+    const int cur_c = pf_c, cur_start = pf_start, cur_dst = pf_dst, cur_off = pf_off, cur_next = pf_next;
     if (it + 2 < my_tiles) {  // prefetch for the next tile of this slot
       pf_s0 = pf2_s0;
       pf_nseg = pf2_s1 - pf2_s0;
@@ -477,8 +482,21 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     }
     slot_barrier(T);  // everyone is done with the previous tile's metadata and staging
     trace_ev(trace, T, tn, 0x01);
-    // ---- tile metadata (half 0): exclusive scan of the segment sizes (<= 128 segments)
-    {
+    // ---- tile metadata.  Short path: when the tile's segments are stored back to back (start[j] + cnt[j] ==
+    // start[j + 1], e.g. the pp CSR, 78 % of a step), a segment's first row is start[j] - start[0] -- no scan, no
+    // row -> segment table (rows find their segment by binary search) and ONE barrier, which also carries the vote.
+    bool contig_ok = true;
+    if (hh == 0 && et < nseg) {
+      s_start[et] = cur_start;
+      s_dst[et] = cur_dst;
+      s_off[et] = cur_off;
+      s_rec[et] = make_int4(cur_off, cur_off + cur_c, cur_dst, __float_as_int(1.0f / (float)(cur_c > 0 ? cur_c : 1)));
+      if (et == nseg - 1) s_off[nseg] = cur_off + cur_c;
+      contig_ok = cur_start + cur_c == cur_next;
+    }
+    const bool contig = tc::named_bar_and(1 + T, 256, contig_ok);
+    // ---- general path (half 0): exclusive scan of the segment sizes (<= 128 segments)
+    if (!contig) {
       const int c = cur_c;
       int inc = c;
       if (hh == 0) {
@@ -512,7 +530,16 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     int src = -1;
     float xd[3] = {0.f, 0.f, 0.f}, dist = 0.f;
     if (et < nrows) {
-      const int j = s_rowseg[et];
+      int j = 0;
+      if (contig) {  // largest j with s_off[j] <= et (empty segments share their successor's offset and lose)
+#pragma unroll
+        for (int step = 64; step >= 1; step >>= 1) {
+          const int c = j + step;
+          if (c < nseg && s_off[c] <= et) j = c;
+        }
+      } else {
+        j = s_rowseg[et];
+      }
       src = __ldg(p.col + s_start[j] + (et - s_off[j]));
       const int dst = s_dst[j];
       const float dx = __ldg(p.src_x + (size_t)src * 3 + 0) - __ldg(p.dst_x + (size_t)dst * 3 + 0);
@@ -686,7 +713,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           float t8[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const float z = (dist - (float)(8 * hh + k)) / 0.9375f;
+            const float z = (dist - (float)(8 * hh + k)) * (1.0f / 0.9375f);  // 1 ulp from the division, no IEEE div sequence
             t8[k] = __expf(-(z * z));
           }
           stage_store8<FAST>(stage, et, hh, t8);
@@ -785,9 +812,11 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
             slot_barrier(T);
             trace_ev(trace, T, tn, (g << 8) | (0x23 + 3 * ps));
             {
+              // staging columns [0, 32) = columns 32 ps .. of half 0, [32, 64) = the same of half 1
               const int c8 = stid & 7;
-              float* out = p.agg_h + 64 * (c8 >> 2) + 32 * ps + 8 * (c8 & 3);
-              segment_means(ab, kMeanPitch, c8, stid >> 3, nseg, s_rec, out, kHidden, p.accumulate);
+              float* out = p.agg_h + 32 * ps + 4 * c8;
+              segment_means(ab + 4 * c8, ab + 32 + 4 * c8, kMeanPitch, stid >> 3, nseg, s_rec, out, out + 64, kHidden,
+                            p.accumulate);
             }
             trace_ev(trace, T, tn, (g << 8) | (0x24 + 3 * ps));
             slot_barrier(T);
@@ -843,7 +872,8 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           {
             const int c8 = stid & 7;
             if (c8 < kVRow / 8)
-              segment_means(ab, kMeanPitchV, c8, stid >> 3, nseg, s_rec, p.agg_v + 8 * c8, kVRow, p.accumulate);
+              segment_means(ab + 4 * c8, ab + 24 + 4 * c8, kMeanPitchV, stid >> 3, nseg, s_rec, p.agg_v + 4 * c8,
+                            p.agg_v + 24 + 4 * c8, kVRow, p.accumulate);
           }
         }
       }
