@@ -149,7 +149,8 @@ int pf_edge_conv_tc_f16(const float* src_h, const float* src_v, const float* src
                         float* agg_h, float* agg_v, int32_t accumulate, void* stream);
 
 /* Debug timeline of CTA 0 of the next pf_edge_conv_tc launches: device_buf = int64[4][4096][2] of (tag, clock64)
- * for the epilogue of tile slot 0 / 1 and the two MMA issuers; NULL disarms.  Not used on the product path. */
+ * for the epilogue of tile slot 0 / 1 and the two MMA issuers, followed by int64[148][2] = (begin, end) globaltimer ns of
+ * every CTA; NULL disarms.  Not used on the product path. */
 int pf_tc_trace(long long* device_buf);
 
 /* ---- K4: node update ------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem)); }
 // L2 prefetch of a contiguous global range by the bulk-copy engine (one instruction, no destination): 16-byte aligned
 // address, size a multiple of 16
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gmem_src, uint32_t bytes) {

@@ -445,8 +445,15 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   // global round trips.
   int pf_s0 = 0, pf_nseg = 0, pf_c = 0, pf_start = 0, pf_dst = 0, pf2_s0 = 0, pf2_s1 = 0;
   int pf_off = 0, pf_next = 0;  // start - start of the tile's first segment; start of the next segment
+  // Gather pipeline, one tile ahead (contiguous tiles only): pf_e0 / pf_rows = first edge / row count of the slot's
+  // next tile (uniform), nx_src = the source row of edge row `et` in it -- loaded in the middle of the current tile, its
+  // feature rows are then pulled into L2 before the next tile's gather, which would otherwise wait on DRAM twice
+  // (col -> rows) with nothing to overlap.
+  int pf_e0 = 0, pf_rows = 0, nx_src = -1, cur_pre_src = -1;
   auto load_segs = [&](int s0_, int nseg_) {
     pf_c = 0;
+    pf_e0 = __ldg(p.seg_start + s0_);
+    pf_rows = __ldg(p.seg_start + s0_ + nseg_ - 1) + __ldg(p.seg_cnt + s0_ + nseg_ - 1) - pf_e0;
     if (hh == 0 && et < nseg_) {
       pf_c = __ldg(p.seg_cnt + s0_ + et);
       pf_start = __ldg(p.seg_start + s0_ + et);
@@ -470,6 +477,9 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   for (int it = T; it < my_tiles; it += 2) {
     const int s0 = pf_s0, nseg = pf_nseg;
     const int cur_c = pf_c, cur_start = pf_start, cur_dst = pf_dst, cur_off = pf_off, cur_next = pf_next;
+    cur_pre_src = nx_src;  // meaningful only if this tile turns out contiguous (it was loaded as col[first edge + et])
+    nx_src = -1;
+    const bool have_next = it + 2 < my_tiles;
     if (it + 2 < my_tiles) {  // prefetch for the next tile of this slot
       pf_s0 = pf2_s0;
       pf_nseg = pf2_s1 - pf2_s0;
@@ -540,7 +550,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       } else {
         j = s_rowseg[et];
       }
-      src = __ldg(p.col + s_start[j] + (et - s_off[j]));
+      src = contig && cur_pre_src >= 0 ? cur_pre_src : __ldg(p.col + s_start[j] + (et - s_off[j]));
       const int dst = s_dst[j];
       const float dx = __ldg(p.src_x + (size_t)src * 3 + 0) - __ldg(p.dst_x + (size_t)dst * 3 + 0);
       const float dy = __ldg(p.src_x + (size_t)src * 3 + 1) - __ldg(p.dst_x + (size_t)dst * 3 + 1);
@@ -655,6 +665,22 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
 #pragma unroll 1
     for (int g = 0; g < 3; ++g) {
       const uint32_t Areg = g == 1 ? Q : P, Dreg = g == 1 ? P : Q;
+      if (have_next) {  // gather pipeline for the slot's next tile (see above); pf_* arrived long ago
+        if (g == 1) {
+          if (et < pf_rows && pf_rows <= kRows) nx_src = __ldg(p.col + pf_e0 + et);
+        } else if (g == 2 && nx_src >= 0) {
+          const char* hrow = reinterpret_cast<const char*>(p.src_h + (size_t)nx_src * kHidden) + 256 * hh;
+          tc::prefetch_l2(hrow);
+          tc::prefetch_l2(hrow + 128);
+          if (hh == 0) {
+            tc::prefetch_l2(p.src_x + (size_t)nx_src * 3);
+          } else if constexpr (HAS_V) {
+            const char* vrow = reinterpret_cast<const char*>(p.src_v + (size_t)nx_src * kVRow);
+            tc::prefetch_l2(vrow);
+            tc::prefetch_l2(vrow + 128);
+          }
+        }
+      }
       // ================= EPI-A: hidden vector channels -> norms sh (scalar operand tail), Vu kept in registers
       trace_ev(trace, T, tn, (g << 8) | 0x10);
       {
@@ -895,6 +921,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = *p.n_tiles;
   const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  long long t_begin = 0;
+  if (p.trace != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
 
   if (warp == 16) {
     tc::tmem_alloc(s_tmem, 512);
@@ -933,6 +961,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 16) tc::tmem_dealloc(tmem, 512);
+  if (p.trace != nullptr && threadIdx.x == 0) {  // debug: (begin, end) of every CTA in ns after the timeline block
+    long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    p.trace[(size_t)4 * kTraceCap * 2 + 2 * blockIdx.x] = t_begin;
+    p.trace[(size_t)4 * kTraceCap * 2 + 2 * blockIdx.x + 1] = t_end;
+  }
 }
 
 
@@ -1070,6 +1104,8 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         __syncwarp();
       }
     }
+    // (Measured and rejected: prefetching the slot's next tile into L2 -- by bulk-copy prefetch or per-thread
+    // prefetch.global.L2 -- makes this kernel 5 % SLOWER at 3 M nodes: 296 tiles in flight x 270 KB already fill L2.)
     slot_barrier(T);  // scalar transposes done: the vector buffers below overlap them
 
     // ---- vectors: v = v_in + agg_v, vector LayerNorm (all 16 channels), own 8 channels kept
@@ -1425,7 +1461,7 @@ extern "C" size_t pf_tc_msg_blob_bytes(void) { return (size_t)tcc::blob_bytes<0>
 extern "C" size_t pf_tc_upd_blob_bytes(void) { return (size_t)tcc::blob_bytes<1>(); }
 
 static long long* g_tc_trace = nullptr;
-extern "C" int pf_tc_trace(long long* device_buf) {  // 4 * 4096 * 2 int64; nullptr disarms
+extern "C" int pf_tc_trace(long long* device_buf) {  // (4 * 4096 + 148) * 2 int64; nullptr disarms
   g_tc_trace = device_buf;
   return PF_OK;
 }

@@ -29,11 +29,15 @@ for v in (None, prot_v):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(v); e1.record(); torch.cuda.synchronize()
     print("HAS_V", v is not None, "edges", g.n_pp_edges, "tiles", int(g.pp_n_tiles), "ms", e0.elapsed_time(e1))
-tr = torch.zeros(4 * 4096 * 2, dtype=torch.int64, device=dev)
+tr = torch.zeros((4 * 4096 + 148) * 2, dtype=torch.int64, device=dev)
 lib.pf_tc_trace(C.c_void_p(tr.data_ptr()))
 run(prot_v); torch.cuda.synchronize()
 lib.pf_tc_trace(None)
-t = tr.cpu().numpy().reshape(4, 4096, 2)
+cta = tr.cpu().numpy()[4 * 4096 * 2:].reshape(148, 2)
+t = tr.cpu().numpy()[:4 * 4096 * 2].reshape(4, 4096, 2)
+b0 = cta[:, 0].min()
+print('CTA spans us: begin', np.round((cta[:, 0] - b0) / 1e3, 1).tolist()[:16], 'dur min/med/max', float(np.min(cta[:,1]-cta[:,0]))/1e3, float(np.median(cta[:,1]-cta[:,0]))/1e3, float(np.max(cta[:,1]-cta[:,0]))/1e3, 'kernel', float(cta[:,1].max()-b0)/1e3)
+print('dur per CTA us', np.round((cta[:,1]-cta[:,0])/1e3).astype(int).tolist())
 t0 = min(t[r, 0, 1] for r in range(4) if t[r, 0, 1] > 0)
 names = {0x01: "tile start", 0x02: "meta done", 0x03: "gather done", 0x10: "EPI-A start", 0x11: "vecD ok", 0x12: "A arrived", 0x21: "D ok", 0x22: "F arrived", 0x31: "gate ok", 0x32: "vecA arrived"}
 mn = {0x10: "V issue", 0x11: "V committed", 0x20: "S start", 0x21: "S committed", 0x30: "G issue", 0x31: "G committed"}
