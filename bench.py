@@ -45,10 +45,17 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--workload", default="configs[1]", choices=["configs[1]", "configs[2]"],
+                   help="configs[1] (default, the headline): 256 x 400-atom pockets x 30 samples of sizes [3..8]x5.  "
+                        "configs[2]: the large-pocket stress case, 1,500-atom pockets, sizes uniform 3..16, 512 graphs "
+                        "(32 pockets x 16 samples) per batch")
     p.add_argument("--precision", default="fp32", choices=["fp32", "fp16"],
                    help="fp32: the parity mode (fp16 hi/lo split, 3 tensor passes; the headline).  fp16: the single-pass "
                         "reduced-precision edge-MLP path of configs[3] (tolerance 2e-2, tests/test_gpu_parity.py)")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.workload == "configs[2]":
+        a.atoms, a.pockets, a.samples = 1500, 32, 16
+    return a
 
 
 def load_weights():
@@ -114,9 +121,12 @@ class ClockSampler:
 
 def workload(args, rank):
     from pharmacoforge_b200.batch import Pocket
-    from pharmacoforge_b200.synthetic import make_pocket, readme_sizes
+    from pharmacoforge_b200.synthetic import make_pocket, readme_sizes, uniform_sizes
     pockets = [Pocket.from_numpy(*make_pocket(args.atoms, seed=rank * args.pockets + i)) for i in range(args.pockets)]
-    sizes = [readme_sizes(args.samples) for _ in range(args.pockets)]
+    if args.workload == "configs[2]":
+        sizes = [uniform_sizes(args.samples, 3, 16, seed=rank * args.pockets + i) for i in range(args.pockets)]
+    else:
+        sizes = [readme_sizes(args.samples) for _ in range(args.pockets)]
     return pockets, sizes
 
 
@@ -341,8 +351,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "f16 (single tensor pass, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {args.pockets} synthetic {args.atoms}-atom pockets x {args.samples} "
-                                   f"samples (sizes [3..8]x5) per GPU, dev.yml denoiser, T={T_STEPS}, seeded random "
+            "config": {"workload": f"{args.workload}: {args.pockets} synthetic {args.atoms}-atom pockets x {args.samples} "
+                                   f"samples (sizes {'[3..8]x5' if args.workload == 'configs[1]' else 'uniform 3..16'}) per GPU, dev.yml denoiser, T={T_STEPS}, seeded random "
                                    "weights, device Philox noise",
                        "graphs_per_gpu": n_graphs, "prot_nodes_per_gpu": n_prot, "pharm_nodes_per_gpu": n_pharm,
                        "pp_edges_per_conv_per_gpu": n_pp_edges, "parallelism": f"graphs sharded x{world}, no collective "
