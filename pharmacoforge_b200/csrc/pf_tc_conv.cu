@@ -1010,12 +1010,15 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
   if (T == 1 && T < my_tiles) tc::mbar_wait(bar_stagger, 0);
   float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36]
   const int prow = lane >> 3, piece = lane & 7;                 // cooperative layout: 8 lanes x 16 B per row chunk
+  long long* trace = stid == 0 ? p.trace : nullptr;
+  int tn = 0;
 
   for (int it = T; it < my_tiles; it += 2) {
     const long long n0 = (long long)(blockIdx.x + (long long)it * gridDim.x) * kRows;
     const long long rem = p.n_nodes - n0;
     const int nrows = rem < kRows ? (int)rem : kRows;
     slot_barrier(T);  // everyone is done with the previous tile's staging / exchange buffers
+    trace_ev(trace, T, tn, 0x01);
 
     // ---- scalars: x = h_in + agg_h (own 64 columns, cooperative layout), LayerNorm_msg over the full row
     {
@@ -1104,37 +1107,48 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         __syncwarp();
       }
     }
-    // (Measured and rejected: prefetching the slot's next tile into L2 -- by bulk-copy prefetch or per-thread
-    // prefetch.global.L2 -- makes this kernel 5 % SLOWER at 3 M nodes: 296 tiles in flight x 270 KB already fill L2.)
+    trace_ev(trace, T, tn, 0x41);
     slot_barrier(T);  // scalar transposes done: the vector buffers below overlap them
+    trace_ev(trace, T, tn, 0x42);
 
     // ---- vectors: v = v_in + agg_v, vector LayerNorm (all 16 channels), own 8 channels kept
     float Vu[24];
     float vsc = 1.f, vinv = 1.f;
     {
-      float* tv = reinterpret_cast<float*>(stage + q * 6656);  // [32][52], filled by the hh == 0 warp of the quarter
-      if (hh == 0) {
+      float* tv = reinterpret_cast<float*>(stage + q * 6656);  // [32][52], filled by the two warps of the quarter
+      {
+        // Loads first, stores after, in small batches of passes: a plain (possibly aliased: v_out may be v_in) global
+        // load cannot be hoisted above a store through the generic staging pointer, and one pass at a time this loop was
+        // 12 dependent L2 round trips -- 30 k of the tile's 95 k cycles on the device timeline.
+        // (half hh takes passes 6 hh .. 6 hh + 5, three at a time)
 #pragma unroll
-        for (int ps = 0; ps < 12; ++ps) {
-          const int qq = 32 * ps + lane;
-          const int rr = qq / 12, pc = qq - 12 * rr;
-          const int row = 32 * q + rr;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < nrows) {
-            const size_t o = (size_t)(n0 + row) * kVRow + 4 * pc;
-            x = __ldg(reinterpret_cast<const float4*>(p.agg_v + o));
-            if constexpr (HAS_V) {
-              const float4 a = *reinterpret_cast<const float4*>(p.v_in + o);
-              x.x += a.x;
-              x.y += a.y;
-              x.z += a.z;
-              x.w += a.w;
+        for (int pb = 0; pb < 6; pb += 3) {
+          float4 xs[3], as[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int qq = 32 * (6 * hh + pb + k) + lane;
+            const int rr = qq / 12, pc = qq - 12 * rr;
+            const int row = 32 * q + rr;
+            xs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            as[k] = xs[k];
+            if (row < nrows) {
+              const size_t o = (size_t)(n0 + row) * kVRow + 4 * pc;
+              xs[k] = __ldg(reinterpret_cast<const float4*>(p.agg_v + o));
+              if constexpr (HAS_V) as[k] = *reinterpret_cast<const float4*>(p.v_in + o);
             }
           }
-          *reinterpret_cast<float4*>(tv + rr * 52 + 4 * pc) = x;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int qq = 32 * (6 * hh + pb + k) + lane;
+            const int rr = qq / 12, pc = qq - 12 * rr;
+            *reinterpret_cast<float4*>(tv + rr * 52 + 4 * pc) =
+                make_float4(xs[k].x + as[k].x, xs[k].y + as[k].y, xs[k].z + as[k].z, xs[k].w + as[k].w);
+          }
         }
       }
+      trace_ev(trace, T, tn, 0x46);
       slot_barrier(T);
+      trace_ev(trace, T, tn, 0x47);
       float nrm = 0.f;
 #pragma unroll
       for (int u4 = 0; u4 < 4; ++u4) {
@@ -1163,7 +1177,9 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           pm = fmaxf(fmaxf(pm, fabsf(x.x)), fmaxf(fabsf(x.y), fmaxf(fabsf(x.z), fabsf(x.w))));
         }
       s_xch[et * 2 + hh].z = pm;
+      trace_ev(trace, T, tn, 0x48);
       slot_barrier(T);  // all rows read (the staging writes below overlap tv); exchange visible
+      trace_ev(trace, T, tn, 0x49);
       row_scale(fmaxf(pm, s_xch[et * 2 + (1 - hh)].z), vsc, vinv);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -1176,9 +1192,29 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       tc::mbar_arrive(&B.vecA);
     }
 
+    // The device timeline shows every CTA of the grid in the same phase: a front end that saturates DRAM (all 296 tile
+    // slots load 180 KB and store 88 KB at once: ~60 k cycles) followed by ~35 k cycles of GVP chain and back end
+    // during which DRAM idles.  Pull the rows of the slot's NEXT tile into L2 now, under the GVP chain (per-thread
+    // prefetches: the bulk-copy engine would queue them in front of the weight slabs).  Issued at tile start instead,
+    // the same prefetch made the kernel 5 % slower (it joins the demand burst and doubles the L2 footprint).
+    if (it + 2 < my_tiles) {
+      const long long m0 = n0 + 2LL * gridDim.x * kRows;
+      const long long mrem = p.n_nodes - m0;
+      const int mrows = mrem < kRows ? (int)mrem : kRows;
+      const int lines_h = mrows * 4, lines_v = (mrows * kVRow * 4 + 127) / 128;  // 128-byte lines
+      for (int l = stid; l < lines_h; l += 256) {
+        tc::prefetch_l2(reinterpret_cast<const char*>(p.h_in + m0 * kHidden) + (size_t)l * 128);
+        tc::prefetch_l2(reinterpret_cast<const char*>(p.agg_h + m0 * kHidden) + (size_t)l * 128);
+      }
+      for (int l = stid; l < lines_v; l += 256) {
+        tc::prefetch_l2(reinterpret_cast<const char*>(p.agg_v + m0 * kVRow) + (size_t)l * 128);
+        if constexpr (HAS_V) tc::prefetch_l2(reinterpret_cast<const char*>(p.v_in + m0 * kVRow) + (size_t)l * 128);
+      }
+    }
 #pragma unroll 1
     for (int g = 0; g < 2; ++g) {
       const uint32_t Areg = g == 1 ? Q : P, Dreg = g == 1 ? P : Q;
+      trace_ev(trace, T, tn, (g << 8) | 0x10);
       // ================= EPI-A: hidden vector channels -> norms sh, Vu kept in registers (scaled by vsc)
       {
         float sh[8];
@@ -1280,6 +1316,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 
     // ================= back end: residual + GVPLayerNorm_upd.  Last GVP was g = 1: f (hi, lo) sits in region P,
     // region Q is free (its gate columns were read above).
+    trace_ev(trace, T, tn, 0x43);
     {
       // ---- vectors: t = v_res + V_out, one norm over all 16 channels (partial over the own 8, exchanged)
       float nrm = 0.f;
@@ -1316,18 +1353,21 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
             }
         }
       }
+      trace_ev(trace, T, tn, 0x44);
       // ---- scalars, pass 1: y = f + h_res (f rebuilt from its fp16 hi + lo parts), kept in region Q as fp32
       float sum = 0.f;
 #pragma unroll 1
       for (int c2 = 0; c2 < 2; ++c2) {
         const int c = 2 * hh + c2;
+        float4 xr[8];  // all eight loads before the first staging store (see the front end: aliasing serialises them)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = 32 * q + 4 * i + prow;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < nrows) x = *reinterpret_cast<const float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece);
-          *reinterpret_cast<float4*>(tb + (4 * i + prow) * 36 + 4 * piece) = x;
+          xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < nrows) xr[i] = *reinterpret_cast<const float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(tb + (4 * i + prow) * 36 + 4 * piece) = xr[i];
         __syncwarp();
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
@@ -1369,6 +1409,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       s_xch[et * 2 + hh].y = sq;
       slot_barrier(T);
       const float rstd = rsqrtf((sq + s_xch[et * 2 + (1 - hh)].y) * (1.0f / kHidden) + 1e-5f);
+      trace_ev(trace, T, tn, 0x45);
       // ---- pass 3: normalise, transpose back to the cooperative layout, coalesced store
 #pragma unroll 1
       for (int c2 = 0; c2 < 2; ++c2) {
@@ -1542,7 +1583,8 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
     }
     configured = true;
   }
-  tcc::NodeParams p{h_in, v_in, agg_h, agg_v, (long long)n_nodes, static_cast<const uint8_t*>(wblob), h_out, v_out, nullptr};
+  tcc::NodeParams p{h_in, v_in, agg_h, agg_v, (long long)n_nodes, static_cast<const uint8_t*>(wblob), h_out, v_out,
+                    g_tc_trace};
   const long long tiles = (n_nodes + tcc::kRows - 1) / tcc::kRows;
   const int grid = (int)(tiles < kNumSms ? tiles : kNumSms);
   cudaStream_t st = as_stream(stream);
