@@ -764,6 +764,17 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         par_D ^= 1;
         tc::fence_after_sync();
         trace_ev(trace, T, tn, (g << 8) | 0x21);
+        // Park the 24 vector channels in TMEM while this stage runs: the S job is done, so its operand region (Areg) is
+        // dead except for columns [0, 16), where the gate will land; half hh uses [32 + 32 hh, 56 + 32 hh).  At 96
+        // registers per thread the compiler otherwise spills them to local memory around the SiLU loop, and with
+        // 217 KB of the SM's 256 KB configured as shared memory those reloads come from L2.
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pk[u] = __float_as_uint(Vu[8 * c + u]);
+          tc::tmem_st8(Areg + 32 + 32 * hh + 8 * c, pk);
+        }
         const float* bf = cst + 144 * g;
         // half hh owns the 16-column chunks j = 4 hh .. 4 hh + 3 (one K-step of the next scalar operand each);
         // the TMEM load of chunk j + 1 is in flight while chunk j is processed
@@ -853,6 +864,16 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
 
       // ================= EPI-C: V_out = sigmoid(gate) * Vu -> next vector operand, or the vector message mean
       {
+        {  // vector channels back from their TMEM parking columns (the loads fly while the gate MMAs finish)
+          uint32_t pk[3][8];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tc::tmem_ld8(Areg + 32 + 32 * hh + 8 * c, pk[c]);
+          tc::wait_ld();
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) Vu[8 * c + u] = __uint_as_float(pk[c][u]);
+        }
         tc::mbar_wait(&B.gate, par_gate);
         par_gate ^= 1;
         tc::fence_after_sync();
