@@ -108,7 +108,11 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
 }
 
 constexpr int kTraceCap = 4096;
+// TRACE is a compile-time switch (the traced kernels are separate instantiations, launched only while pf_tc_trace is
+// armed): the product kernels carry neither the event counter nor the pointer -- at 96 registers per thread both spilled.
+template <bool TRACE>
 __device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int tag) {
+  if constexpr (!TRACE) return;
   if (trace != nullptr && blockIdx.x == 0 && n < kTraceCap) {
     trace[((size_t)role * kTraceCap + n) * 2] = tag;
     trace[((size_t)role * kTraceCap + n) * 2 + 1] = clock64();
@@ -177,14 +181,14 @@ __device__ __forceinline__ uint32_t full_parity(int i, uint32_t t) {
   return ((ring_uses<MODE>(i % kRing) & 1 ? t : 0u) + (uint32_t)(i / kRing)) & 1u;
 }
 
-template <int MODE, bool HAS_V, bool FAST>
+template <int MODE, bool HAS_V, bool FAST, bool TRACE>
 __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* bar_full, uint64_t* bar_empty,
                          SlotBars* sb, uint64_t* bar_small, uint64_t* bar_stagger, volatile int* turn, int my_tiles,
                          long long* trace_) {
   const int n_mine = (my_tiles + 1 - T) >> 1;
   if (n_mine == 0) return;
   const bool lane0 = (threadIdx.x & 31) == 0;
-  long long* trace = lane0 ? trace_ : nullptr;
+  long long* trace = TRACE && lane0 ? trace_ : nullptr;
   // S jobs (the long N = 128 MMA runs) of the two tile slots are issued strictly alternately -- slot 0 job j, slot 1
   // job j, slot 0 job j + 1, ... -- so that they execute back to back on the tensor pipe instead of interleaved:
   // one slot's accumulator completes a full job ahead of the other's, and the slots settle half a GVP apart (one on
@@ -220,7 +224,7 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
       tc::mbar_wait(&B.vecA, p_vecA);
       p_vecA ^= 1;
       tc::fence_after_sync();
-      trace_ev(trace, 2 + T, tn, (g << 8) | 0x10);
+      trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x10);
       if (tc::elect_one()) {
         const uint64_t b_hi = vec_hi + (uint64_t)(g * (2048 >> 4)), b_lo = vec_lo + (uint64_t)(g * (2048 >> 4));
 #pragma unroll
@@ -235,7 +239,7 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
         tc::mma_commit(&B.vecD);
       }
       __syncwarp();
-      trace_ev(trace, 2 + T, tn, (g << 8) | 0x11);
+      trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x11);
     }
     // ---- S_g: scalar features, one weight slab (K = 16) at a time
     tc::mbar_wait(&B.A, p_A);
@@ -247,7 +251,7 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
         while (*turn < need) __nanosleep(20);
     }
     tc::fence_after_sync();
-    trace_ev(trace, 2 + T, tn, (g << 8) | 0x20);
+    trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x20);
     constexpr int nslab = Cfg<MODE>::nslab(g);
 #pragma unroll
     for (int k = 0; k < nslab; ++k) {
@@ -287,12 +291,12 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
       __syncwarp();
     }
     if (T == 0 && t == 0 && g == 0 && lane0) tc::mbar_arrive(bar_stagger);  // slot 1 starts half a phase behind slot 0
-    trace_ev(trace, 2 + T, tn, (g << 8) | 0x21);
+    trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x21);
     // ---- G_g: vector gates from the new scalars (split in place in Dreg), output -> Areg[0:16)
     tc::mbar_wait(&B.F, p_F);
     p_F ^= 1;
     tc::fence_after_sync();
-    trace_ev(trace, 2 + T, tn, (g << 8) | 0x30);
+    trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x30);
     if (tc::elect_one()) {
       const uint64_t g_hi = gate_hi + (uint64_t)(g * (8192 >> 4)), g_lo = gate_lo + (uint64_t)(g * (8192 >> 4));
 #pragma unroll
@@ -308,7 +312,7 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
       tc::mma_commit(&B.gate);
     }
     __syncwarp();
-    trace_ev(trace, 2 + T, tn, (g << 8) | 0x31);
+    trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x31);
   };
 
 #pragma unroll 1
@@ -413,7 +417,7 @@ __device__ __forceinline__ void segment_means(const float* bx, const float* by, 
 }
 
 // Two threads per edge row: half hh owns scalar columns [64 hh, 64 hh + 64) and vector channels [8 hh, 8 hh + 8).
-template <bool HAS_V, bool FAST>
+template <bool HAS_V, bool FAST, bool TRACE>
 __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
                               uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
   const int stid = threadIdx.x & 255;
@@ -437,7 +441,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   // ping-pong: slot 1 starts once slot 0's first scalar job is issued, so that one slot's CUDA-core stages run
   // under the other slot's MMAs instead of both slots marching in lockstep
   if (T == 1 && T < my_tiles) tc::mbar_wait(bar_stagger, 0);
-  long long* trace = stid == 0 ? p.trace : nullptr;
+  long long* trace = TRACE && stid == 0 ? p.trace : nullptr;
   int tn = 0;
 
   // Software prefetch of the tile descriptors: (first, end) segment of the slot's next-but-one tile and the segment
@@ -491,7 +495,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       }
     }
     slot_barrier(T);  // everyone is done with the previous tile's metadata and staging
-    trace_ev(trace, T, tn, 0x01);
+    trace_ev<TRACE>(trace, T, tn, 0x01);
     // ---- tile metadata.  Short path: when the tile's segments are stored back to back (start[j] + cnt[j] ==
     // start[j + 1], e.g. the pp CSR, 78 % of a step), a segment's first row is start[j] - start[0] -- no scan, no
     // row -> segment table (rows find their segment by binary search) and ONE barrier, which also carries the vote.
@@ -562,30 +566,32 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       xd[2] = dz / dist;
     }
 
-    trace_ev(trace, T, tn, 0x02);
+    trace_ev<TRACE>(trace, T, tn, 0x02);
     // ---- gather h[src] (coalesced: 8 lanes x 16 B per row chunk), transpose through smem to one thread per row,
     //      split into fp16 (hi, lo) and store as the TMEM A operand of S_0 in region P
     float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36] / [32][28]
     {
-      float4 g4[2][8];
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2)
+      // Two rounds of 8 row loads (32 registers each) instead of 16 at once: the second round is issued right after the
+      // first one's staging stores and flies under its fp16 split.  With all 16 loads in flight the 64 data registers did
+      // not fit next to the tile state (96 registers per thread): 23 of the loaded values went through local memory.
+      float4 ga[8], gb[8];
+      auto load8 = [&](float4 (&g)[8], const int c2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int sr = __shfl_sync(0xffffffffu, src, 4 * i + (lane >> 3));
-          g4[c2][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (sr >= 0)
-            g4[c2][i] = __ldg(reinterpret_cast<const float4*>(p.src_h + (size_t)sr * kHidden + 32 * (2 * hh + c2)) + (lane & 7));
+            g[i] = __ldg(reinterpret_cast<const float4*>(p.src_h + (size_t)sr * kHidden + 32 * (2 * hh + c2)) + (lane & 7));
         }
+      };
+      auto stage8 = [&](const float4 (&g)[8]) {
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int c = 2 * hh + c2;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(tb + (4 * i + (lane >> 3)) * 36 + 4 * (lane & 7)) = g4[c2][i];
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(tb + (4 * i + (lane >> 3)) * 36 + 4 * (lane & 7)) = g[i];
         __syncwarp();
+      };
+      auto split32 = [&](const int c) {  // 32 staged columns of the own row -> two K-steps in TMEM: hi (8 cols) | lo (8 cols)
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {  // two K-steps of 16 columns: TMEM layout per K-step = hi (8 cols) | lo (8 cols)
+        for (int ks = 0; ks < 2; ++ks) {
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -602,7 +608,13 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           if constexpr (!FAST) tc::tmem_st8(P + 32 * c + 16 * ks + 8, lo);
         }
         __syncwarp();
-      }
+      };
+      load8(ga, 0);
+      stage8(ga);
+      load8(gb, 1);
+      split32(2 * hh);
+      stage8(gb);
+      split32(2 * hh + 1);
     }
 
     float Vu[24];                       // vector channels [8 hh, 8 hh + 8) of the 3 components, index 8 c + u'
@@ -641,7 +653,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       }
       s_xch[et * 2 + hh] = make_float4(pm, pv[0], pv[1], pv[2]);
     }
-    trace_ev(trace, T, tn, 0x03);
+    trace_ev<TRACE>(trace, T, tn, 0x03);
     slot_barrier(T);  // transposes done (the staging writes below overlap other warps' buffers); exchange visible
     if constexpr (HAS_V) {
       const float4 o = s_xch[et * 2 + (1 - hh)];
@@ -682,7 +694,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         }
       }
       // ================= EPI-A: hidden vector channels -> norms sh (scalar operand tail), Vu kept in registers
-      trace_ev(trace, T, tn, (g << 8) | 0x10);
+      trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x10);
       {
         float sh[8];
         float sh16 = 0.f;
@@ -707,7 +719,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           tc::mbar_wait(&B.vecD, par_vecD);
           par_vecD ^= 1;
           tc::fence_after_sync();
-          trace_ev(trace, T, tn, (g << 8) | 0x11);
+          trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x11);
 #pragma unroll
           for (int h = 0; h < 8; ++h) sh[h] = 0.f;
 #pragma unroll
@@ -755,7 +767,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::wait_st();
         tc::fence_before_sync();
         tc::mbar_arrive(&B.A);
-        trace_ev(trace, T, tn, (g << 8) | 0x12);
+        trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x12);
       }
 
       // ================= EPI-B: f = SiLU(D + b), split in place into the next A operand; last GVP: mean of f
@@ -763,7 +775,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::mbar_wait(&B.D, par_D);
         par_D ^= 1;
         tc::fence_after_sync();
-        trace_ev(trace, T, tn, (g << 8) | 0x21);
+        trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x21);
         // Park the 24 vector channels in TMEM while this stage runs: the S job is done, so its operand region (Areg) is
         // dead except for columns [0, 16), where the gate will land; half hh uses [32 + 32 hh, 56 + 32 hh).  At 96
         // registers per thread the compiler otherwise spills them to local memory around the SiLU loop, and with
@@ -829,7 +841,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::wait_st();
         tc::fence_before_sync();
         tc::mbar_arrive(&B.F);
-        trace_ev(trace, T, tn, (g << 8) | 0x22);
+        trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x22);
         if (g == 2) {  // segmented mean of the scalar messages, two passes of 64 columns through shared memory
 #pragma unroll 1
           for (int ps = 0; ps < 2; ++ps) {
@@ -847,7 +859,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
               }
             }
             slot_barrier(T);
-            trace_ev(trace, T, tn, (g << 8) | (0x23 + 3 * ps));
+            trace_ev<TRACE>(trace, T, tn, (g << 8) | (0x23 + 3 * ps));
             {
               // staging columns [0, 32) = columns 32 ps .. of half 0, [32, 64) = the same of half 1
               const int c8 = stid & 7;
@@ -855,9 +867,9 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
               segment_means(ab + 4 * c8, ab + 32 + 4 * c8, kMeanPitch, stid >> 3, nseg, s_rec, out, out + 64, kHidden,
                             p.accumulate);
             }
-            trace_ev(trace, T, tn, (g << 8) | (0x24 + 3 * ps));
+            trace_ev<TRACE>(trace, T, tn, (g << 8) | (0x24 + 3 * ps));
             slot_barrier(T);
-            trace_ev(trace, T, tn, (g << 8) | (0x25 + 3 * ps));
+            trace_ev<TRACE>(trace, T, tn, (g << 8) | (0x25 + 3 * ps));
           }
         }
       }
@@ -877,7 +889,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         tc::mbar_wait(&B.gate, par_gate);
         par_gate ^= 1;
         tc::fence_after_sync();
-        trace_ev(trace, T, tn, (g << 8) | 0x31);
+        trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x31);
         uint32_t r[8];
         tc::tmem_ld8(Areg + 8 * hh, r);
         tc::wait_ld();
@@ -906,7 +918,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           }
           tc::fence_proxy_async();
           tc::mbar_arrive(&B.vecA);
-          trace_ev(trace, T, tn, (g << 8) | 0x32);
+          trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x32);
         } else {
           float* ab = reinterpret_cast<float*>(stage);  // [128][kMeanPitchV]
 #pragma unroll
@@ -928,7 +940,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   }
 }
 
-template <bool HAS_V, bool FAST>
+template <bool HAS_V, bool FAST, bool TRACE>
 __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -943,7 +955,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   const int n_tiles = *p.n_tiles;
   const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   long long t_begin = 0;
-  if (p.trace != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+  if (TRACE && p.trace != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
 
   if (warp == 16) {
     tc::tmem_alloc(s_tmem, 512);
@@ -973,16 +985,16 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   const uint32_t tmem = *s_tmem;
 
   if (warp < 16) {
-    epilogue_role<HAS_V, FAST>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+    epilogue_role<HAS_V, FAST, TRACE>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    mma_role<0, HAS_V, FAST>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
+    mma_role<0, HAS_V, FAST, TRACE>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
     if (lane == 0) producer_role<0>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 16) tc::tmem_dealloc(tmem, 512);
-  if (p.trace != nullptr && threadIdx.x == 0) {  // debug: (begin, end) of every CTA in ns after the timeline block
+  if (TRACE && p.trace != nullptr && threadIdx.x == 0) {  // debug: (begin, end) of every CTA in ns after the timeline block
     long long t_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
     p.trace[(size_t)4 * kTraceCap * 2 + 2 * blockIdx.x] = t_begin;
@@ -1013,7 +1025,7 @@ __device__ __forceinline__ float xor8_sum(float v) {  // sum over the 8 lanes th
   return v;
 }
 
-template <bool HAS_V, bool FAST>
+template <bool HAS_V, bool FAST, bool TRACE>
 __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
                                    uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
   const int stid = threadIdx.x & 255;
@@ -1031,7 +1043,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
   if (T == 1 && T < my_tiles) tc::mbar_wait(bar_stagger, 0);
   float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36]
   const int prow = lane >> 3, piece = lane & 7;                 // cooperative layout: 8 lanes x 16 B per row chunk
-  long long* trace = stid == 0 ? p.trace : nullptr;
+  long long* trace = TRACE && stid == 0 ? p.trace : nullptr;
   int tn = 0;
 
   for (int it = T; it < my_tiles; it += 2) {
@@ -1039,7 +1051,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
     const long long rem = p.n_nodes - n0;
     const int nrows = rem < kRows ? (int)rem : kRows;
     slot_barrier(T);  // everyone is done with the previous tile's staging / exchange buffers
-    trace_ev(trace, T, tn, 0x01);
+    trace_ev<TRACE>(trace, T, tn, 0x01);
 
     // ---- scalars: x = h_in + agg_h (own 64 columns, cooperative layout), LayerNorm_msg over the full row
     {
@@ -1128,9 +1140,9 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         __syncwarp();
       }
     }
-    trace_ev(trace, T, tn, 0x41);
+    trace_ev<TRACE>(trace, T, tn, 0x41);
     slot_barrier(T);  // scalar transposes done: the vector buffers below overlap them
-    trace_ev(trace, T, tn, 0x42);
+    trace_ev<TRACE>(trace, T, tn, 0x42);
 
     // ---- vectors: v = v_in + agg_v, vector LayerNorm (all 16 channels), own 8 channels kept
     float Vu[24];
@@ -1167,9 +1179,9 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           }
         }
       }
-      trace_ev(trace, T, tn, 0x46);
+      trace_ev<TRACE>(trace, T, tn, 0x46);
       slot_barrier(T);
-      trace_ev(trace, T, tn, 0x47);
+      trace_ev<TRACE>(trace, T, tn, 0x47);
       float nrm = 0.f;
 #pragma unroll
       for (int u4 = 0; u4 < 4; ++u4) {
@@ -1198,9 +1210,9 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           pm = fmaxf(fmaxf(pm, fabsf(x.x)), fmaxf(fabsf(x.y), fmaxf(fabsf(x.z), fabsf(x.w))));
         }
       s_xch[et * 2 + hh].z = pm;
-      trace_ev(trace, T, tn, 0x48);
+      trace_ev<TRACE>(trace, T, tn, 0x48);
       slot_barrier(T);  // all rows read (the staging writes below overlap tv); exchange visible
-      trace_ev(trace, T, tn, 0x49);
+      trace_ev<TRACE>(trace, T, tn, 0x49);
       row_scale(fmaxf(pm, s_xch[et * 2 + (1 - hh)].z), vsc, vinv);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -1235,7 +1247,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 #pragma unroll 1
     for (int g = 0; g < 2; ++g) {
       const uint32_t Areg = g == 1 ? Q : P, Dreg = g == 1 ? P : Q;
-      trace_ev(trace, T, tn, (g << 8) | 0x10);
+      trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x10);
       // ================= EPI-A: hidden vector channels -> norms sh, Vu kept in registers (scaled by vsc)
       {
         float sh[8];
@@ -1271,6 +1283,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         tc::mbar_wait(&B.D, par_D);
         par_D ^= 1;
         tc::fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {  // park the vector channels in the dead operand region (see the edge kernel)
+          uint32_t pk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pk[u] = __float_as_uint(Vu[8 * c + u]);
+          tc::tmem_st8(Areg + 32 + 32 * hh + 8 * c, pk);
+        }
         const float* bf = cst + 144 * g;
         uint32_t r[2][16];
         tc::tmem_ld16(Dreg + 16 * (4 * hh), r[0]);
@@ -1300,6 +1319,16 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       }
       // ================= EPI-C: V_out = sigmoid(gate) * Vu
       {
+        {
+          uint32_t pk[3][8];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tc::tmem_ld8(Areg + 32 + 32 * hh + 8 * c, pk[c]);
+          tc::wait_ld();
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) Vu[8 * c + u] = __uint_as_float(pk[c][u]);
+        }
         tc::mbar_wait(&B.gate, par_gate);
         par_gate ^= 1;
         tc::fence_after_sync();
@@ -1337,7 +1366,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 
     // ================= back end: residual + GVPLayerNorm_upd.  Last GVP was g = 1: f (hi, lo) sits in region P,
     // region Q is free (its gate columns were read above).
-    trace_ev(trace, T, tn, 0x43);
+    trace_ev<TRACE>(trace, T, tn, 0x43);
     {
       // ---- vectors: t = v_res + V_out, one norm over all 16 channels (partial over the own 8, exchanged)
       float nrm = 0.f;
@@ -1374,7 +1403,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
             }
         }
       }
-      trace_ev(trace, T, tn, 0x44);
+      trace_ev<TRACE>(trace, T, tn, 0x44);
       // ---- scalars, pass 1: y = f + h_res (f rebuilt from its fp16 hi + lo parts), kept in region Q as fp32
       float sum = 0.f;
 #pragma unroll 1
@@ -1430,7 +1459,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       s_xch[et * 2 + hh].y = sq;
       slot_barrier(T);
       const float rstd = rsqrtf((sq + s_xch[et * 2 + (1 - hh)].y) * (1.0f / kHidden) + 1e-5f);
-      trace_ev(trace, T, tn, 0x45);
+      trace_ev<TRACE>(trace, T, tn, 0x45);
       // ---- pass 3: normalise, transpose back to the cooperative layout, coalesced store
 #pragma unroll 1
       for (int c2 = 0; c2 < 2; ++c2) {
@@ -1460,7 +1489,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
   }
 }
 
-template <bool HAS_V, bool FAST>
+template <bool HAS_V, bool FAST, bool TRACE>
 __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const NodeParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -1503,9 +1532,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const Nod
   const uint32_t tmem = *s_tmem;
 
   if (warp < 16) {
-    node_epilogue_role<HAS_V, FAST>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+    node_epilogue_role<HAS_V, FAST, TRACE>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    mma_role<1, true, FAST>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
+    mma_role<1, true, FAST, TRACE>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
     if (lane == 0) producer_role<1>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
@@ -1536,11 +1565,15 @@ static int launch_edge_conv_tc(bool fast, const float* src_h, const float* src_v
                "pf_edge_conv_tc: null pointer");
   PF_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 15) == 0, "pf_edge_conv_tc: weight blob must be 16-byte aligned");
   if (max_tiles <= 0) return PF_OK;
+  using KernelFn = void (*)(tcc::Params);
+  static const KernelFn fns[8] = {  // index = HAS_V + 2 FAST + 4 TRACE
+      tcc::edge_conv_tc_kernel<false, false, false>, tcc::edge_conv_tc_kernel<true, false, false>,
+      tcc::edge_conv_tc_kernel<false, true, false>,  tcc::edge_conv_tc_kernel<true, true, false>,
+      tcc::edge_conv_tc_kernel<false, false, true>,  tcc::edge_conv_tc_kernel<true, false, true>,
+      tcc::edge_conv_tc_kernel<false, true, true>,   tcc::edge_conv_tc_kernel<true, true, true>};
   static bool configured = false;
   if (!configured) {
-    const void* fns[4] = {(const void*)tcc::edge_conv_tc_kernel<false, false>, (const void*)tcc::edge_conv_tc_kernel<true, false>,
-                          (const void*)tcc::edge_conv_tc_kernel<false, true>, (const void*)tcc::edge_conv_tc_kernel<true, true>};
-    for (const void* f : fns) {
+    for (KernelFn f : fns) {
       const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tcc::kSmemBytes);
       if (e != cudaSuccess) {
         set_error("pf_edge_conv_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
@@ -1552,18 +1585,8 @@ static int launch_edge_conv_tc(bool fast, const float* src_h, const float* src_v
   tcc::Params p{src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
                 static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate, g_tc_trace};
   const int grid = max_tiles < kNumSms ? max_tiles : kNumSms;
-  cudaStream_t st = as_stream(stream);
-  if (fast) {
-    if (src_v != nullptr)
-      tcc::edge_conv_tc_kernel<true, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-    else
-      tcc::edge_conv_tc_kernel<false, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-  } else {
-    if (src_v != nullptr)
-      tcc::edge_conv_tc_kernel<true, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-    else
-      tcc::edge_conv_tc_kernel<false, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-  }
+  const int which = (src_v != nullptr ? 1 : 0) + (fast ? 2 : 0) + (g_tc_trace != nullptr ? 4 : 0);
+  fns[which]<<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_edge_conv_tc");
   return PF_OK;
 }
@@ -1591,11 +1614,15 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
   PF_CHECK_ARG(h_in && agg_h && agg_v && wblob && h_out && v_out, "pf_node_update_tc: null pointer");
   PF_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 15) == 0, "pf_node_update_tc: weight blob must be 16-byte aligned");
   if (n_nodes <= 0) return PF_OK;
+  using KernelFn = void (*)(tcc::NodeParams);
+  static const KernelFn fns[8] = {  // index = HAS_V + 2 FAST + 4 TRACE
+      tcc::node_update_tc_kernel<false, false, false>, tcc::node_update_tc_kernel<true, false, false>,
+      tcc::node_update_tc_kernel<false, true, false>,  tcc::node_update_tc_kernel<true, true, false>,
+      tcc::node_update_tc_kernel<false, false, true>,  tcc::node_update_tc_kernel<true, false, true>,
+      tcc::node_update_tc_kernel<false, true, true>,   tcc::node_update_tc_kernel<true, true, true>};
   static bool configured = false;
   if (!configured) {
-    const void* fns[4] = {(const void*)tcc::node_update_tc_kernel<false, false>, (const void*)tcc::node_update_tc_kernel<true, false>,
-                          (const void*)tcc::node_update_tc_kernel<false, true>, (const void*)tcc::node_update_tc_kernel<true, true>};
-    for (const void* f : fns) {
+    for (KernelFn f : fns) {
       const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tcc::kSmemBytes);
       if (e != cudaSuccess) {
         set_error("pf_node_update_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
@@ -1608,18 +1635,8 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
                     g_tc_trace};
   const long long tiles = (n_nodes + tcc::kRows - 1) / tcc::kRows;
   const int grid = (int)(tiles < kNumSms ? tiles : kNumSms);
-  cudaStream_t st = as_stream(stream);
-  if (fast) {
-    if (v_in != nullptr)
-      tcc::node_update_tc_kernel<true, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-    else
-      tcc::node_update_tc_kernel<false, true><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-  } else {
-    if (v_in != nullptr)
-      tcc::node_update_tc_kernel<true, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-    else
-      tcc::node_update_tc_kernel<false, false><<<grid, tcc::kThreadsTc, tcc::kSmemBytes, st>>>(p);
-  }
+  const int which = (v_in != nullptr ? 1 : 0) + (fast ? 2 : 0) + (g_tc_trace != nullptr ? 4 : 0);
+  fns[which]<<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_node_update_tc");
   return PF_OK;
 }
