@@ -803,12 +803,20 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           uint32_t hi[8], lo[8];
           float fv[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 8; i += 2) {
             if constexpr (FAST) {
               hi[i] = tc::silu_h2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i));
+              hi[i + 1] = tc::silu_h2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
+                                      *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2));
             } else {
-              tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
-                              fv[2 * i], fv[2 * i + 1], hi[i], lo[i]);
+              const uint32_t a4[4] = {r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3]};
+              float f4[4];
+              tc::silu_split4(a4, *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                              *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f4, hi[i], hi[i + 1], lo[i], lo[i + 1]);
+              fv[2 * i] = f4[0];
+              fv[2 * i + 1] = f4[1];
+              fv[2 * i + 2] = f4[2];
+              fv[2 * i + 3] = f4[3];
             }
           }
           if (g == 2) {
@@ -1300,13 +1308,16 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           if (j4 < 3) tc::tmem_ld16(Dreg + 16 * (j + 1), r[(j4 + 1) & 1]);
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 8; i += 2) {
             if constexpr (FAST) {
               hi[i] = tc::silu_h2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i));
+              hi[i + 1] = tc::silu_h2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
+                                      *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2));
             } else {
-              float f0, f1;
-              tc::silu_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
-                              f0, f1, hi[i], lo[i]);
+              const uint32_t a4[4] = {r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3]};
+              float f4[4];
+              tc::silu_split4(a4, *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                              *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f4, hi[i], hi[i + 1], lo[i], lo[i + 1]);
             }
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
