@@ -80,6 +80,122 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   }
 }
 
+// The same contract with a software pipeline, for the GEMMs that carry the step (the Linear(161 / 144 -> 128) of every GVP
+// over the pp edges: forward, dgrad and wgrad are ~7.4 GFLOP each at 200 k edges): TM x TN tile with (TM / 16) x (TN / 16)
+// outputs per thread (8 x 8 at 128 x 128: one LDS.128 per 16 FFMA instead of one per 8), K step 8, two shared-memory
+// stages, and the next stage's global loads issued into registers before the current stage's FFMAs.  The single-stage
+// 64 x 64 kernel above stays for the skinny vector-channel contractions (N = 16 / 17 / 32), which are memory-bound.
+template <int TM, int TN>
+__global__ void __launch_bounds__(256, 2) sgemm_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                         const float* __restrict__ bias, float* __restrict__ C, int M,
+                                                         int N, int K, long long a_rs, long long a_cs, long long b_rs,
+                                                         long long b_cs, int ldc, int accumulate, int k_chunk) {
+  constexpr int TK = 8, RM = TM / 16, RN = TN / 16, LA = TM * TK / 256, LB = TN * TK / 256;
+  static_assert((RM == 4 || RM == 8) && (RN == 4 || RN == 8), "tile shape");
+  __shared__ __align__(16) float sA[2][TK][TM + 4];
+  __shared__ __align__(16) float sB[2][TK][TN + 4];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(K, k_begin + k_chunk);
+  const bool a_kmajor = a_cs == 1, b_nmajor = b_cs == 1;
+  float ra[LA], rb[LB];
+  auto gload = [&](const int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + 256 * i;
+      const int m = a_kmajor ? e / TK : e % TM, k = a_kmajor ? e % TK : e / TM;
+      const int gm = m0 + m, gk = k0 + k;
+      ra[i] = (gm < M && gk < k_end) ? A[gm * a_rs + gk * a_cs] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + 256 * i;
+      const int n = b_nmajor ? e % TN : e / TK, k = b_nmajor ? e / TN : e % TK;
+      const int gn = n0 + n, gk = k0 + k;
+      rb[i] = (gn < N && gk < k_end) ? B[gk * b_rs + gn * b_cs] : 0.f;
+    }
+  };
+  auto sstore = [&](const int buf) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + 256 * i;
+      const int m = a_kmajor ? e / TK : e % TM, k = a_kmajor ? e % TK : e / TM;
+      sA[buf][k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + 256 * i;
+      const int n = b_nmajor ? e % TN : e / TK, k = b_nmajor ? e / TN : e % TK;
+      sB[buf][k][n] = rb[i];
+    }
+  };
+  float acc[RM][RN] = {};
+  const int nk = (k_end - k_begin + TK - 1) / TK;
+  if (nk > 0) {
+    gload(k_begin);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) gload(k_begin + (t + 1) * TK);
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float av[RM], bv[RN];
+#pragma unroll
+      for (int i = 0; i < RM; i += 4)  // rows ty * 4 + (0..3), then TM / 2 + ty * 4 + (0..3)
+        *reinterpret_cast<float4*>(&av[i]) = *reinterpret_cast<const float4*>(&sA[buf][k][(i / 4) * (TM / 2) + ty * 4]);
+#pragma unroll
+      for (int j = 0; j < RN; j += 4)
+        *reinterpret_cast<float4*>(&bv[j]) = *reinterpret_cast<const float4*>(&sB[buf][k][(j / 4) * (TN / 2) + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (t + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+  const bool vec = gridDim.z == 1 && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < RM; ++i) {
+    const int gm = m0 + (i / 4) * (TM / 2) + ty * 4 + (i & 3);
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j4 = 0; j4 < RN; j4 += 4) {
+      const int gn = n0 + (j4 / 4) * (TN / 2) + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = acc[i][j4 + j];
+        if (bias != nullptr && blockIdx.z == 0 && gn + j < N) v[j] += bias[gn + j];
+      }
+      float* c = C + (size_t)gm * ldc + gn;
+      if (vec && gn + 3 < N) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(c);
+          o.x += old.x;
+          o.y += old.y;
+          o.z += old.z;
+          o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(c) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (gn + j >= N) continue;
+          if (gridDim.z > 1)
+            atomicAdd(c + j, v[j]);
+          else
+            c[j] = accumulate ? c[j] + v[j] : v[j];
+        }
+      }
+    }
+  }
+}
+
 // column sums of a row-major [M][N] matrix (bias gradients), accumulated with atomicAdd into out[N]
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,11 +457,31 @@ extern "C" int pf_train_sgemm(const float* A, const float* B, const float* bias,
       return PF_ERR_LAUNCH;
     }
   }
-  // 64 x 64 tiles, 4 x 4 outputs per thread.  (A 128 x 128 / 8 x 8 instantiation measured SLOWER on the training step:
-  // most of its GEMMs are skinny -- N = 16 / 17 / 32 vector-channel contractions over 3E rows -- and memory-bound.)
-  dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-  T::sgemm_kernel<64, 64, 4><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc,
-                                                                 accumulate, chunk);
+  // Shape dispatch: the pipelined 8 x 8 (or 8 x 4 / 4 x 8) kernel for the GEMMs with at least ~100 columns and rows (the
+  // scalar Linear of every GVP: forward, dgrad, wgrad), the single-stage 64 x 64 kernel for the skinny vector-channel
+  // contractions (N = 16 / 17 / 32 over 3E rows), which are memory-bound and measured slower on large tiles.
+  const long long work = (long long)M * N;
+  if (N >= 96 && M >= 96 && work >= (1 << 16)) {
+    const bool wide_n = N > 64 && (N % 128 == 0 || N % 128 > 64);   // 161 -> 3 x 64, 128 / 144 -> 128-wide tiles
+    const bool wide_m = M > 64 && (M % 128 == 0 || M % 128 > 64 || M >= 1024);
+    if (wide_m && wide_n) {
+      dim3 grid((N + 127) / 128, (M + 127) / 128, splits);
+      T::sgemm_pipe_kernel<128, 128><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
+                                                                         ldc, accumulate, chunk);
+    } else if (wide_m) {
+      dim3 grid((N + 63) / 64, (M + 127) / 128, splits);
+      T::sgemm_pipe_kernel<128, 64><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
+                                                                        ldc, accumulate, chunk);
+    } else {
+      dim3 grid((N + 127) / 128, (M + 63) / 64, splits);
+      T::sgemm_pipe_kernel<64, 128><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
+                                                                        ldc, accumulate, chunk);
+    }
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+    T::sgemm_kernel<64, 64, 4><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc,
+                                                                   accumulate, chunk);
+  }
   PF_CHECK_LAUNCH("pf_train_sgemm");
   return PF_OK;
 }
@@ -473,7 +609,17 @@ static int sgemm_ld(const float* A, const float* B, const float* bias, float* C,
                     long long a_cs, long long b_rs, long long b_cs, int ldc, int accumulate, int split_k, void* stream) {
   return pf_train_sgemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, stream);
 }
-static int wgrad_splits(long long rows) { return rows / 512 > 64 ? 64 : (rows / 512 > 1 ? (int)(rows / 512) : 1); }
+// split-K factor of a weight gradient dW[m][n] = sum over `rows`: enough CTAs to fill the 148 SMs four times over even when
+// dW is a single 17 x 17 tile (the vector-channel weights: with a fixed cap of 64 splits those reductions over 3E = 600 k
+// rows ran on 64 CTAs), at least 512 rows per split.
+static int wgrad_splits(long long rows, int m, int n) {
+  const long long tiles = (long long)((m + 63) / 64) * ((n + 63) / 64);
+  long long cap = (4 * kNumSms + tiles - 1) / tiles;
+  if (cap < 1) cap = 1;
+  const long long by_rows = rows / 512;
+  const long long sp = by_rows < cap ? by_rows : cap;
+  return sp > 1 ? (int)sp : 1;
+}
 
 extern "C" int pf_train_gvp_fwd(const float* feats, const float* vec, const float* Wh, const float* Wu, const float* Wf,
                                 const float* bf, const float* Wg, const float* bg, int64_t M, int32_t n, int32_t vi,
@@ -516,13 +662,13 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
                "pf_train_gvp_bwd: null pointer");
   if (M == 0) return PF_OK;
   const int M3 = (int)(3 * M), K = n + h, Mi = (int)M;
-  const int sk = wgrad_splits(M), sk3 = wgrad_splits(3 * M);
+
   cudaStream_t st = as_stream(stream);
   int rc;
   T::gate_bwd_kernel<<<blocks_for(M * vo, 256), 256, 0, st>>>(gates, Vu, dvout, dgates, dVu, M, vo, act_sigmoid);
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(gate)");
   // gates = f Wg^T + bg
-  if ((rc = sgemm_ld(dgates, f, nullptr, dWg, vo, no, Mi, 1, vo, no, 1, no, 0, sk, stream)) != PF_OK) return rc;  // dWg = dgates^T f
+  if ((rc = sgemm_ld(dgates, f, nullptr, dWg, vo, no, Mi, 1, vo, no, 1, no, 0, wgrad_splits(M, vo, no), stream)) != PF_OK) return rc;  // dWg = dgates^T f
   if ((rc = pf_train_colsum(dgates, dbg, M, vo, stream)) != PF_OK) return rc;
   cudaError_t e = cudaMemcpyAsync(dfz, df_out, (size_t)M * no * 4, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) {
@@ -533,7 +679,7 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
   T::silu_bwd_kernel<<<blocks_for(M * no, 256), 256, 0, st>>>(z, dfz, dfz, M * no);                              // dz in place
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(silu)");
   // z = s Wf^T + bf
-  if ((rc = sgemm_ld(dfz, s, nullptr, dWf, no, K, Mi, 1, no, K, 1, K, 0, sk, stream)) != PF_OK) return rc;       // dWf = dz^T s
+  if ((rc = sgemm_ld(dfz, s, nullptr, dWf, no, K, Mi, 1, no, K, 1, K, 0, wgrad_splits(M, no, K), stream)) != PF_OK) return rc;       // dWf = dz^T s
   if ((rc = pf_train_colsum(dfz, dbf, M, no, stream)) != PF_OK) return rc;
   if ((rc = sgemm_ld(dfz, Wf, nullptr, ds, Mi, K, no, no, 1, K, 1, K, 0, 1, stream)) != PF_OK) return rc;        // ds = dz Wf
   e = cudaMemcpy2DAsync(dfeats, (size_t)n * 4, ds, (size_t)K * 4, (size_t)n * 4, (size_t)M, cudaMemcpyDeviceToDevice, st);
@@ -545,9 +691,9 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(vecnorm)");
   // Vu = Vh Wu
   if ((rc = sgemm_ld(dVu, Wu, nullptr, dVh, M3, h, vo, vo, 1, 1, vo, h, 1, 1, stream)) != PF_OK) return rc;      // dVh += dVu Wu^T
-  if ((rc = sgemm_ld(Vh, dVu, nullptr, dWu, h, vo, M3, 1, h, vo, 1, vo, 0, sk3, stream)) != PF_OK) return rc;    // dWu = Vh^T dVu
+  if ((rc = sgemm_ld(Vh, dVu, nullptr, dWu, h, vo, M3, 1, h, vo, 1, vo, 0, wgrad_splits(3 * M, h, vo), stream)) != PF_OK) return rc;    // dWu = Vh^T dVu
   // Vh = V Wh
   if ((rc = sgemm_ld(dVh, Wh, nullptr, dvec, M3, vi, h, h, 1, 1, h, vi, 0, 1, stream)) != PF_OK) return rc;      // dV = dVh Wh^T
-  if ((rc = sgemm_ld(vec, dVh, nullptr, dWh, vi, h, M3, 1, vi, h, 1, h, 0, sk3, stream)) != PF_OK) return rc;    // dWh = V^T dVh
+  if ((rc = sgemm_ld(vec, dVh, nullptr, dWh, vi, h, M3, 1, vi, h, 1, h, 0, wgrad_splits(3 * M, vi, h), stream)) != PF_OK) return rc;    // dWh = V^T dVh
   return PF_OK;
 }
