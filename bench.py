@@ -195,6 +195,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at init when NCCL_DEBUG=VERSION/INFO: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from pharmacoforge_b200 import _lib
