@@ -1063,10 +1063,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 
     // ---- scalars: x = h_in + agg_h (own 64 columns, cooperative layout), LayerNorm_msg over the full row
     {
+      // Row statistics in ONE exchange between the column halves: sum and sum of squares (var = E[x^2] - mean^2; the
+      // rows are O(1) with |mean| << std, so the cancellation costs ~1e-7 relative, far inside the parity bar) -- the
+      // two-pass form needed a second slot barrier.
       float4 g4[2][8];
-      float rs[8];
+      float rs[8], rq[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rs[i] = 0.f;
+      for (int i = 0; i < 8; ++i) rs[i] = rq[i] = 0.f;
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2)
 #pragma unroll
@@ -1084,29 +1087,17 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           }
           g4[c2][i] = x;
           rs[i] += (x.x + x.y) + (x.z + x.w);
+          rq[i] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
         }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         rs[i] = xor8_sum(rs[i]);
-        if (piece == 0) s_xch[(32 * q + 4 * i + prow) * 2 + hh].x = rs[i];
-      }
-      slot_barrier(T);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = 32 * q + 4 * i + prow;
-        const float mean = (s_xch[row * 2].x + s_xch[row * 2 + 1].x) * (1.0f / kHidden);
-        float sq = 0.f;
-#pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          float4& x = g4[c2][i];
-          x.x -= mean;
-          x.y -= mean;
-          x.z -= mean;
-          x.w -= mean;
-          sq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+        rq[i] = xor8_sum(rq[i]);
+        if (piece == 0) {
+          float4& e = s_xch[(32 * q + 4 * i + prow) * 2 + hh];
+          e.x = rs[i];
+          e.y = rq[i];
         }
-        sq = xor8_sum(sq);
-        if (piece == 0) s_xch[row * 2 + hh].y = sq;
       }
       slot_barrier(T);
 #pragma unroll
@@ -1117,13 +1108,14 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = 32 * q + 4 * i + prow;
-          const float var = (s_xch[row * 2].y + s_xch[row * 2 + 1].y) * (1.0f / kHidden);
+          const float mean = (s_xch[row * 2].x + s_xch[row * 2 + 1].x) * (1.0f / kHidden);
+          const float var = fmaxf((s_xch[row * 2].y + s_xch[row * 2 + 1].y) * (1.0f / kHidden) - mean * mean, 0.f);
           const float rstd = rsqrtf(var + 1e-5f);
           float4 y = g4[c2][i];
-          y.x = y.x * rstd * lw.x + lb.x;
-          y.y = y.y * rstd * lw.y + lb.y;
-          y.z = y.z * rstd * lw.z + lb.z;
-          y.w = y.w * rstd * lw.w + lb.w;
+          y.x = (y.x - mean) * rstd * lw.x + lb.x;
+          y.y = (y.y - mean) * rstd * lw.y + lb.y;
+          y.z = (y.z - mean) * rstd * lw.z + lb.z;
+          y.w = (y.w - mean) * rstd * lw.w + lb.w;
           if (row < nrows) *reinterpret_cast<float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece) = y;
           *reinterpret_cast<float4*>(tb + (4 * i + prow) * 36 + 4 * piece) = y;
         }
@@ -1199,17 +1191,17 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         nrm += fmaxf(a.x * a.x + b.x * b.x + c.x * c.x, 1e-8f) + fmaxf(a.y * a.y + b.y * b.y + c.y * c.y, 1e-8f) +
                fmaxf(a.z * a.z + b.z * b.z + c.z * c.z, 1e-8f) + fmaxf(a.w * a.w + b.w * b.w + c.w * c.w, 1e-8f);
       }
-      const float vn = sqrtf(nrm * (1.0f / kVec) + 1e-5f) + 1e-5f;
+      const float ivn = 1.0f / (sqrtf(nrm * (1.0f / kVec) + 1e-5f) + 1e-5f);  // one division, then multiplies (1 ulp)
       float pm = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int u4 = 0; u4 < 2; ++u4) {
           float4 x = *reinterpret_cast<const float4*>(tv + lane * 52 + 16 * c + 8 * hh + 4 * u4);
-          x.x /= vn;
-          x.y /= vn;
-          x.z /= vn;
-          x.w /= vn;
+          x.x *= ivn;
+          x.y *= ivn;
+          x.z *= ivn;
+          x.w *= ivn;
           Vu[8 * c + 4 * u4] = x.x;
           Vu[8 * c + 4 * u4 + 1] = x.y;
           Vu[8 * c + 4 * u4 + 2] = x.z;
@@ -1399,24 +1391,24 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       slot_barrier(T);  // also orders the gate reads of both halves before region Q is overwritten below
       {
         const float tot = nrm + s_xch[et * 2 + (1 - hh)].z;
-        const float vn = sqrtf(tot * (1.0f / kVec) + 1e-5f) + 1e-5f;
+        const float ivn = 1.0f / (sqrtf(tot * (1.0f / kVec) + 1e-5f) + 1e-5f);
         if (et < nrows) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int u4 = 0; u4 < 2; ++u4) {
               float4 x;
-              x.x = Vu[8 * c + 4 * u4] / vn;
-              x.y = Vu[8 * c + 4 * u4 + 1] / vn;
-              x.z = Vu[8 * c + 4 * u4 + 2] / vn;
-              x.w = Vu[8 * c + 4 * u4 + 3] / vn;
+              x.x = Vu[8 * c + 4 * u4] * ivn;
+              x.y = Vu[8 * c + 4 * u4 + 1] * ivn;
+              x.z = Vu[8 * c + 4 * u4 + 2] * ivn;
+              x.w = Vu[8 * c + 4 * u4 + 3] * ivn;
               *reinterpret_cast<float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4) = x;
             }
         }
       }
       trace_ev<TRACE>(trace, T, tn, 0x44);
       // ---- scalars, pass 1: y = f + h_res (f rebuilt from its fp16 hi + lo parts), kept in region Q as fp32
-      float sum = 0.f;
+      float sum = 0.f, sq = 0.f;
 #pragma unroll 1
       for (int c2 = 0; c2 < 2; ++c2) {
         const int c = 2 * hh + c2;
@@ -1444,6 +1436,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
             const float y0 = (a.x + b.x) + tb[lane * 36 + 16 * ks + 2 * i];
             const float y1 = (a.y + b.y) + tb[lane * 36 + 16 * ks + 2 * i + 1];
             sum += y0 + y1;
+            sq = fmaf(y0, y0, fmaf(y1, y1, sq));
             y[2 * i] = __float_as_uint(y0);
             y[2 * i + 1] = __float_as_uint(y1);
           }
@@ -1453,23 +1446,11 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       }
       tc::wait_st();
       s_xch[et * 2 + hh].x = sum;
-      slot_barrier(T);
-      const float mean = (sum + s_xch[et * 2 + (1 - hh)].x) * (1.0f / kHidden);
-      float sq = 0.f;
-#pragma unroll 1
-      for (int j4 = 0; j4 < 4; ++j4) {
-        uint32_t y[16];
-        tc::tmem_ld16(Q + 16 * (4 * hh + j4), y);
-        tc::wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float d = __uint_as_float(y[i]) - mean;
-          sq = fmaf(d, d, sq);
-        }
-      }
       s_xch[et * 2 + hh].y = sq;
-      slot_barrier(T);
-      const float rstd = rsqrtf((sq + s_xch[et * 2 + (1 - hh)].y) * (1.0f / kHidden) + 1e-5f);
+      slot_barrier(T);  // one exchange of (sum, sum of squares), as in the front end
+      const float mean = (sum + s_xch[et * 2 + (1 - hh)].x) * (1.0f / kHidden);
+      const float var = fmaxf((sq + s_xch[et * 2 + (1 - hh)].y) * (1.0f / kHidden) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + 1e-5f);
       trace_ev<TRACE>(trace, T, tn, 0x45);
       // ---- pass 3: normalise, transpose back to the cooperative layout, coalesced store
 #pragma unroll 1
@@ -1481,9 +1462,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           tc::tmem_ld16(Q + 16 * (2 * c + ks), y);
           tc::wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 16; i += 4) {
             const int col = 32 * c + 16 * ks + i;
-            tb[lane * 36 + 16 * ks + i] = (__uint_as_float(y[i]) - mean) * rstd * cst[kCLnUpdW + col] + cst[kCLnUpdB + col];
+            const float4 w = *reinterpret_cast<const float4*>(cst + kCLnUpdW + col);
+            const float4 b = *reinterpret_cast<const float4*>(cst + kCLnUpdB + col);
+            *reinterpret_cast<float4*>(tb + lane * 36 + 16 * ks + i) =
+                make_float4((__uint_as_float(y[i]) - mean) * rstd * w.x + b.x, (__uint_as_float(y[i + 1]) - mean) * rstd * w.y + b.y,
+                            (__uint_as_float(y[i + 2]) - mean) * rstd * w.z + b.z, (__uint_as_float(y[i + 3]) - mean) * rstd * w.w + b.w);
           }
         }
         __syncwarp();
