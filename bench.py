@@ -31,6 +31,7 @@ DYN = dict(vector_size=16, n_convs=2, n_hidden_scalars=128, message_norm="mean",
 CUT = {"pp": 3.5, "pf": 8, "fp": 8, "ff": 9}
 PH_TYPES = ["Aromatic", "HydrogenDonor", "HydrogenAcceptor", "PositiveIon", "NegativeIon", "Hydrophobic"]
 T_STEPS = 100
+_OUT = sys.stdout
 
 
 def parse():
@@ -178,11 +179,17 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "pharmacophores/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": v, "unit": "pharmacophores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner at init, library
+    # chatter) is sent to stderr, the line itself goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -195,8 +202,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout at init when NCCL_DEBUG=VERSION/INFO: stdout carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from pharmacoforge_b200 import _lib
@@ -367,7 +372,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clk.summary(), "exact_dead_work_elimination": dce,
             "fp16_single_pass": f16,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -51,6 +51,9 @@ def main():
     ap.add_argument("--cpu-pockets", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")   # stdout carries exactly one JSON line; other writers of fd 1 go to stderr
+    os.dup2(2, 1)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch.distributed as dist
@@ -58,8 +61,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout at init when NCCL_DEBUG=VERSION/INFO: stdout carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from pharmacoforge_b200 import _lib
     from pharmacoforge_b200.batch import GraphBatch
@@ -142,7 +143,7 @@ def main():
                     "api": "GraphBatch.from_pockets + training_step + backward + allreduce_gradients + Adam.step"},
             "final_loss": losses[-1], "first_loss": losses[0], "gpu_launches": int(launches), "cpu_baseline": cpu,
             "clocks": clk.summary(), "note": "first, UNFUSED training path: per-edge tensors are materialised; every "
-                                             "arithmetic node is a hand-written CUDA kernel (train_ops.py)"}), flush=True)
+                                             "arithmetic node is a hand-written CUDA kernel (train_ops.py)"}), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
