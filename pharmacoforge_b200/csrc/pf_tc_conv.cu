@@ -121,6 +121,9 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int
 }
 
 __device__ __forceinline__ void slot_barrier(int T) { tc::named_bar_sync(1 + T, 256); }
+// The two warps that share a TMEM lane quarter (column halves hh = 0 / 1 of the same 32 rows) exchange per-row values
+// through s_xch: a 64-thread barrier (ids 3..10) instead of the slot's 256-thread one wherever nothing else is shared.
+__device__ __forceinline__ void pair_barrier(int T, int q) { tc::named_bar_sync(3 + 4 * T + q, 64); }
 
 // ------------------------------------------------------------------------------------------------ producer
 template <int MODE>
@@ -915,7 +918,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         }
         if (g < 2) {
           s_xch[et * 2 + hh].x = pm;
-          slot_barrier(T);
+          pair_barrier(T, q);
           row_scale(fmaxf(pm, s_xch[et * 2 + (1 - hh)].x), vsc, vinv);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -1099,7 +1102,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           e.y = rq[i];
         }
       }
-      slot_barrier(T);
+      pair_barrier(T, q);
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         const int c = 2 * hh + c2;
@@ -1180,7 +1183,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         }
       }
       trace_ev<TRACE>(trace, T, tn, 0x46);
-      slot_barrier(T);
+      pair_barrier(T, q);
       trace_ev<TRACE>(trace, T, tn, 0x47);
       float nrm = 0.f;
 #pragma unroll
@@ -1352,7 +1355,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         }
         if (g == 0) {
           s_xch[et * 2 + hh].z = pm;
-          slot_barrier(T);
+          pair_barrier(T, q);
           row_scale(fmaxf(pm, s_xch[et * 2 + (1 - hh)].z), vsc, vinv);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -1388,7 +1391,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       for (int u = 0; u < 8; ++u)
         nrm += fmaxf(Vu[u] * Vu[u] + Vu[8 + u] * Vu[8 + u] + Vu[16 + u] * Vu[16 + u], 1e-8f);
       s_xch[et * 2 + hh].z = nrm;
-      slot_barrier(T);  // also orders the gate reads of both halves before region Q is overwritten below
+      pair_barrier(T, q);  // also orders the gate reads of both halves before region Q is overwritten below
       {
         const float tot = nrm + s_xch[et * 2 + (1 - hh)].z;
         const float ivn = 1.0f / (sqrtf(tot * (1.0f / kVec) + 1e-5f) + 1e-5f);
@@ -1447,7 +1450,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       tc::wait_st();
       s_xch[et * 2 + hh].x = sum;
       s_xch[et * 2 + hh].y = sq;
-      slot_barrier(T);  // one exchange of (sum, sum of squares), as in the front end
+      pair_barrier(T, q);  // one exchange of (sum, sum of squares), as in the front end
       const float mean = (sum + s_xch[et * 2 + (1 - hh)].x) * (1.0f / kHidden);
       const float var = fmaxf((sq + s_xch[et * 2 + (1 - hh)].y) * (1.0f / kHidden) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-5f);
