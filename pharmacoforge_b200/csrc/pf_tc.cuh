@@ -305,6 +305,12 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// wait with a sleep between polls, for waits that are known to be long (an epilogue warp waiting for its slot's S job:
+// >= 1.7 k cycles).  mbar_wait's try_wait returns every ~50 cycles on this part: its polls were 14 % of all issued
+// instructions of the edge kernel, taken from the other slot's working warps on the same scheduler.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

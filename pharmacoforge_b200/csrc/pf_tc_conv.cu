@@ -108,6 +108,10 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
 }
 
 constexpr int kTraceCap = 4096;
+#ifndef PF_DSLEEP
+#define PF_DSLEEP 100
+#endif
+constexpr unsigned kDSleepNs = PF_DSLEEP;  // sleep between polls of the S-job barrier
 // TRACE is a compile-time switch (the traced kernels are separate instantiations, launched only while pf_tc_trace is
 // armed): the product kernels carry neither the event counter nor the pointer -- at 96 registers per thread both spilled.
 template <bool TRACE>
@@ -775,7 +779,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
 
       // ================= EPI-B: f = SiLU(D + b), split in place into the next A operand; last GVP: mean of f
       {
-        tc::mbar_wait(&B.D, par_D);
+        tc::mbar_wait_sleep(&B.D, par_D, kDSleepNs);
         par_D ^= 1;
         tc::fence_after_sync();
         trace_ev<TRACE>(trace, T, tn, (g << 8) | 0x21);
@@ -1283,7 +1287,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       }
       // ================= EPI-B: f = SiLU(D + b), split in place into the next A operand
       {
-        tc::mbar_wait(&B.D, par_D);
+        tc::mbar_wait_sleep(&B.D, par_D, kDSleepNs);
         par_D ^= 1;
         tc::fence_after_sync();
 #pragma unroll
