@@ -279,6 +279,21 @@ def main():
                          else "fp32 FFMA kernels (PF_TILE_ROWS=64)") +
                         "; achieved = ALGORITHMIC 136,742 FLOP/edge (one pass) / launch time" + tnote}
     breakdown = {k: round(v[0] / ms_total, 4) for k, v in prof.items() if v[1]}
+    # the HBM-bound kernels of the step against the measured copy bandwidth (algorithmic bytes per unit)
+    def hbm_line(site, nbytes, what):
+        ms_site, n_site = prof.get(site, (0.0, 0))
+        if not n_site:
+            return None
+        gbs = nbytes / (ms_site / n_site * 1e-3) / 1e9
+        return {"kernel": what, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                "avg_launch_ms": ms_site / n_site, "algorithmic_bytes_per_launch": int(nbytes),
+                "share_of_step": ms_site / ms_total}
+    other_rooflines = [r for r in (
+        hbm_line("update_prot", 3 * 704 * n_prot, "node_update_tc_kernel (prot nodes): 3 x 704 B per node"),
+        hbm_line("dyn_graph", 12 * (n_prot + n_pharm) + 4 * (2 * DYN["pf_k"] * n_pharm + 2 * n_ff),
+                 "dyn_graph_kernel (ff radius + pf kNN + fp reverse): 12 B per node read, 4 B per edge written"),
+        hbm_line("posterior", 24 * n_prot + 116 * n_pharm, "posterior_kernel (DDPM step + COM shift): 24 Np + 116 Nf B"),
+    ) if r is not None]
 
     # ---------------- reported separately, never as `value`: exact dead-work elimination (bit-identical results;
     # the protein-side kernels of the last conv layer, whose outputs nothing reads, are not launched)
@@ -365,7 +380,7 @@ def main():
                        "pp_edges_per_conv_per_gpu": n_pp_edges, "parallelism": f"graphs sharded x{world}, no collective "
                        "on the path, one final gather", "l2": "inputs_exceed_l2 (2.2 GB of node features per conv)"},
             "denoiser_edges_per_s": edge_evals_per_call * T_STEPS * args.steps * world / (ms_total / 1e3),
-            "roofline": roofline, "kernel_time_share": breakdown, "cpu_baseline": cpu,
+            "roofline": roofline, "other_rooflines": other_rooflines, "kernel_time_share": breakdown, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "pharmacophores/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
                     "api": "PharmacophoreDiff.make_batch + sample_given_receptor + gather + .cpu()"},

@@ -56,14 +56,25 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
                                                         float* __restrict__ prot_x, const int* __restrict__ prot_ptr,
                                                         int n_graphs, float alpha_ts, float var_terms,
                                                         float sigma_q) {
+  // The new coordinates of a graph are kept in shared memory between the update and the centre-of-mass pass (up to
+  // kPostCache / 3 pharmacophore centres; larger graphs go through global memory as before): the three sequential sums
+  // -- node order, as index_add_ does on the CPU -- were a chain of dependent global loads of just-written values.
+  // The kernel stays latency-bound (one CTA per graph, ~25-28 % of the copy bandwidth, 0.1 % of a step).
+  constexpr int kPostCache = 384;
+  __shared__ float s_z[kPostCache];
   __shared__ float s_com[3];
   for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
     const int fa = pharm_ptr[g], fb = pharm_ptr[g + 1];
     const int nf = fb - fa;
+    const bool cached = nf * 3 <= kPostCache;
     for (int i = threadIdx.x; i < nf * 3; i += blockDim.x) {
       const size_t o = (size_t)fa * 3 + i;
       const float mu = __fsub_rn(__fdiv_rn(pharm_x[o], alpha_ts), __fmul_rn(var_terms, eps_x[o]));
-      pharm_x[o] = __fadd_rn(mu, __fmul_rn(sigma_q, noise_x[o]));
+      const float z = __fadd_rn(mu, __fmul_rn(sigma_q, noise_x[o]));
+      if (cached)
+        s_z[i] = z;
+      else
+        pharm_x[o] = z;
     }
     for (int i = threadIdx.x; i < nf * nh; i += blockDim.x) {
       const size_t o = (size_t)fa * nh + i;
@@ -73,14 +84,18 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
     __syncthreads();
     if (threadIdx.x < 3) {
       float acc = 0.f;
-      for (int i = 0; i < nf; ++i) acc = __fadd_rn(acc, pharm_x[(size_t)(fa + i) * 3 + threadIdx.x]);
+      if (cached) {
+        for (int i = 0; i < nf; ++i) acc = __fadd_rn(acc, s_z[i * 3 + threadIdx.x]);
+      } else {
+        for (int i = 0; i < nf; ++i) acc = __fadd_rn(acc, pharm_x[(size_t)(fa + i) * 3 + threadIdx.x]);
+      }
       s_com[threadIdx.x] = __fdiv_rn(acc, (float)nf);
     }
     __syncthreads();
     if (nf > 0) {
       for (int i = threadIdx.x; i < nf * 3; i += blockDim.x) {
         const size_t o = (size_t)fa * 3 + i;
-        pharm_x[o] = __fsub_rn(pharm_x[o], s_com[i % 3]);
+        pharm_x[o] = __fsub_rn(cached ? s_z[i] : pharm_x[o], s_com[i % 3]);
       }
       const int pa = prot_ptr[g], pb = prot_ptr[g + 1];
       for (int i = threadIdx.x; i < (pb - pa) * 3; i += blockDim.x) {
