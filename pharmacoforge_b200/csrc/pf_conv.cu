@@ -9,12 +9,47 @@ namespace pf {
 // ------------------------------------------------------------------------------------------------
 constexpr int kEncMaxIn = 32;
 
+// One encoder row: LN(SiLU(W [x, t] + b)) of one node by one warp (4 columns per lane); x[i] is read through `xin`.
+template <typename XIn>
+__device__ __forceinline__ float4 encode_row(const XIn& xin, int nf, float tg, const float* s_w, const float* s_p, int lane) {
+  float4 z = *reinterpret_cast<const float4*>(s_p + 4 * lane);
+  for (int i = 0; i <= nf; ++i) {
+    const float xi = i < nf ? xin(i) : tg;
+    const float4 wv = *reinterpret_cast<const float4*>(s_w + i * kHidden + 4 * lane);
+    z.x = fmaf(xi, wv.x, z.x);
+    z.y = fmaf(xi, wv.y, z.y);
+    z.z = fmaf(xi, wv.z, z.z);
+    z.w = fmaf(xi, wv.w, z.w);
+  }
+  z.x = silu_f(z.x);
+  z.y = silu_f(z.y);
+  z.z = silu_f(z.z);
+  z.w = silu_f(z.w);
+  const float mean = warp_sum(z.x + z.y + z.z + z.w) * (1.0f / kHidden);
+  const float dx = z.x - mean, dy = z.y - mean, dz = z.z - mean, dw = z.w - mean;
+  const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / kHidden);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float4 lw = *reinterpret_cast<const float4*>(s_p + kHidden + 4 * lane);
+  const float4 lb = *reinterpret_cast<const float4*>(s_p + 2 * kHidden + 4 * lane);
+  float4 o;
+  o.x = dx * rstd * lw.x + lb.x;
+  o.y = dy * rstd * lw.y + lb.y;
+  o.z = dz * rstd * lw.z + lb.z;
+  o.w = dw * rstd * lw.w + lb.w;
+  return o;
+}
+
+// A one-hot node (the reference's element encoding, dev.yml:57) has only nf distinct encoder rows per graph and timestep:
+// the CTA computes them once per graph with the SAME instruction sequence as the general path (fmaf(0, w, z) == z, so the
+// rows are bit-identical to what the per-node loop produces) and a one-hot node then costs one 44-byte read and one
+// 512-byte write instead of ~150 warp instructions; any other feature row takes the general path.
 __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ feats, int nf,
                                                      const int* __restrict__ node_ptr, int n_graphs,
                                                      const float* __restrict__ t, const float* __restrict__ w,
                                                      float* __restrict__ h_out) {
   __shared__ __align__(16) float s_w[(kEncMaxIn + 1) * kHidden];
   __shared__ __align__(16) float s_p[3 * kHidden];
+  __shared__ __align__(16) float s_tab[kEncMaxIn * kHidden];
   const int nin = nf + 1;
   for (int i = threadIdx.x; i < nin * kHidden; i += blockDim.x) s_w[i] = w[i];
   for (int i = threadIdx.x; i < 3 * kHidden; i += blockDim.x) s_p[i] = w[nin * kHidden + i];
@@ -23,34 +58,30 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ f
   for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
     const int n0 = node_ptr[g], n1 = node_ptr[g + 1];
     const float tg = t[g];
-    for (int n = n0 + warp; n < n1; n += nwarps) {
-      float4 z = *reinterpret_cast<const float4*>(s_p + 4 * lane);
-      const float* fr = feats + (size_t)n * nf;
-      for (int i = 0; i < nin; ++i) {
-        const float xi = i < nf ? __ldg(fr + i) : tg;
-        const float4 wv = *reinterpret_cast<const float4*>(s_w + i * kHidden + 4 * lane);
-        z.x = fmaf(xi, wv.x, z.x);
-        z.y = fmaf(xi, wv.y, z.y);
-        z.z = fmaf(xi, wv.z, z.z);
-        z.w = fmaf(xi, wv.w, z.w);
+    const bool use_table = n1 - n0 > 2 * nf;  // small graphs (pharmacophores): not worth nf extra rows
+    if (use_table) {
+      for (int k = warp; k < nf; k += nwarps) {
+        const float4 o = encode_row([&](int i) { return i == k ? 1.0f : 0.0f; }, nf, tg, s_w, s_p, lane);
+        *reinterpret_cast<float4*>(s_tab + k * kHidden + 4 * lane) = o;
       }
-      z.x = silu_f(z.x);
-      z.y = silu_f(z.y);
-      z.z = silu_f(z.z);
-      z.w = silu_f(z.w);
-      const float mean = warp_sum(z.x + z.y + z.z + z.w) * (1.0f / kHidden);
-      const float dx = z.x - mean, dy = z.y - mean, dz = z.z - mean, dw = z.w - mean;
-      const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / kHidden);
-      const float rstd = rsqrtf(var + 1e-5f);
-      const float4 lw = *reinterpret_cast<const float4*>(s_p + kHidden + 4 * lane);
-      const float4 lb = *reinterpret_cast<const float4*>(s_p + 2 * kHidden + 4 * lane);
+      __syncthreads();
+    }
+    for (int n = n0 + warp; n < n1; n += nwarps) {
+      const float* fr = feats + (size_t)n * nf;
+      int hot = -1;
+      if (use_table) {
+        const float x = lane < nf ? __ldg(fr + lane) : 0.0f;
+        const unsigned ones = __ballot_sync(0xffffffffu, x == 1.0f), nonzero = __ballot_sync(0xffffffffu, x != 0.0f);
+        if (ones == nonzero && __popc(ones) == 1) hot = __ffs(ones) - 1;
+      }
       float4 o;
-      o.x = dx * rstd * lw.x + lb.x;
-      o.y = dy * rstd * lw.y + lb.y;
-      o.z = dz * rstd * lw.z + lb.z;
-      o.w = dw * rstd * lw.w + lb.w;
+      if (hot >= 0)
+        o = *reinterpret_cast<const float4*>(s_tab + hot * kHidden + 4 * lane);
+      else
+        o = encode_row([&](int i) { return __ldg(fr + i); }, nf, tg, s_w, s_p, lane);
       *reinterpret_cast<float4*>(h_out + (size_t)n * kHidden + 4 * lane) = o;
     }
+    if (use_table) __syncthreads();  // the table is rewritten for the next graph
   }
 }
 

@@ -200,6 +200,27 @@ def test_encoders(env):
     close(got_p, env.O.encoder(env.sd, "dynamics.prot_encoder", b.prot_h, tt[b.prot_b]), what="prot enc")
 
 
+def test_encoder_one_hot_table_is_bit_identical(env):
+    """pf_encode computes the nf distinct rows of a one-hot graph once per graph: same bits as the per-node path (small
+    graphs take it), and rows that are not one-hot fall back to it inside a large graph."""
+    gen = torch.Generator().manual_seed(12)
+    n, nf = 240, 11
+    feats = torch.nn.functional.one_hot(torch.randint(0, nf, (n,), generator=gen), nf).float()
+    feats[7] = torch.randn(nf, generator=gen)          # not one-hot
+    feats[8] = 0.0                                      # all zero
+    feats[9, :] = 0.0
+    feats[9, 2] = 1.0
+    feats[9, 5] = 1.0                                   # two ones
+    feats[10] = feats[10] * 2.0                         # a single 2.0
+    w = env.W.view("prot_enc")
+    t_big = torch.tensor([0.63])
+    big = env.ops.encode(feats.cuda(), torch.tensor([0, n], dtype=torch.int32).cuda(), t_big.cuda(), w)
+    ptr_small = torch.arange(0, n + 1, 10, dtype=torch.int32)     # 24 graphs of 10 nodes: below the table threshold
+    small = env.ops.encode(feats.cuda(), ptr_small.cuda(), t_big.repeat(24).cuda(), w)
+    assert torch.equal(big, small)
+    close(big, env.O.encoder(env.sd, "dynamics.prot_encoder", feats, t_big.repeat(n)), what="prot enc (table path)")
+
+
 def _edge_conv_case(env, etype_idx, layer, with_vectors, impl="tc", fp16=False):
     O, ops = env.O, env.ops
     g, b = env.build([(150, 3), (90, 4)], [[3, 5, 8], [6, 4]])
