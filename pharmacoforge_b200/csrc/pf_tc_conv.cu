@@ -366,23 +366,39 @@ __device__ __forceinline__ void stage_store8(uint8_t* slab, int m, int kc, const
 // row (one red.add per address and launch, hence still deterministic).  s_rec[j] = (first row, end row, dst, 1/count).
 constexpr int kMeanPitch = 68;   // 64 columns + 4: 16-byte row stores and quad loads are bank-conflict free
 constexpr int kMeanPitchV = 52;  // 48 vector entries + 4
-// predicated 16-byte shared-memory load into pre-zeroed registers (the compiler turns the C++ form into a branch)
-__device__ __forceinline__ void lds128_if(float4& v, const float* ptr, bool pred) {
+// predicated 16-byte shared-memory load of row I of a batch into pre-zeroed registers: one compare against an immediate
+// and one load at an immediate offset from the batch's base address (the C++ form costs an address computation and a
+// branch per row; this phase runs at ~12 cycles per instruction and warp, so the integer work was half of its time)
+template <int I, int PITCH>
+__device__ __forceinline__ void lds128_row(float4& v, uint32_t base, int rows_left) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "setp.gt.s32 p, %5, %6;\n\t"
+      "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%7];\n\t"
       "}\n"
       : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "r"(tc::smem_u32(ptr)), "r"((uint32_t)pred));
+      : "r"(base), "r"(rows_left), "n"(I), "n"(I * PITCH * 4));
+}
+template <int PITCH>
+__device__ __forceinline__ void lds128_rows8(float4 (&v)[8], uint32_t base, int rows_left) {
+  lds128_row<0, PITCH>(v[0], base, rows_left);
+  lds128_row<1, PITCH>(v[1], base, rows_left);
+  lds128_row<2, PITCH>(v[2], base, rows_left);
+  lds128_row<3, PITCH>(v[3], base, rows_left);
+  lds128_row<4, PITCH>(v[4], base, rows_left);
+  lds128_row<5, PITCH>(v[5], base, rows_left);
+  lds128_row<6, PITCH>(v[6], base, rows_left);
+  lds128_row<7, PITCH>(v[7], base, rows_left);
 }
 // A thread owns two column quads, `bx` and `by` (buffer addresses of row 0) -> `ox` and `oy` (output addresses of
 // destination 0): the eight threads of a segment read 128 contiguous bytes per quad and row, i.e. one shared-memory
 // wavefront per quarter warp (8 consecutive columns per thread cost two).
-__device__ __forceinline__ void segment_means(const float* bx, const float* by, const int pitch, const int jfirst,
-                                              const int nseg, const int4* s_rec, float* ox, float* oy,
-                                              const int out_pitch, const int accumulate) {
+template <int PITCH>
+__device__ __forceinline__ void segment_means(const float* bx, const float* by, const int jfirst, const int nseg,
+                                              const int4* s_rec, float* ox, float* oy, const int out_pitch,
+                                              const int accumulate) {
+  const uint32_t ax = tc::smem_u32(bx), ay = tc::smem_u32(by);
   for (int j = jfirst; j < nseg; j += 32) {
     const int4 rec = s_rec[j];
     const int r0 = rec.x, r1 = rec.y;
@@ -394,9 +410,9 @@ __device__ __forceinline__ void segment_means(const float* bx, const float* by, 
       for (int i = 0; i < 8; ++i) {
         x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         y[i] = x[i];
-        lds128_if(x[i], bx + (r + i) * pitch, r + i < r1);
-        lds128_if(y[i], by + (r + i) * pitch, r + i < r1);
       }
+      lds128_rows8<PITCH>(x, ax + r * (PITCH * 4), r1 - r);
+      lds128_rows8<PITCH>(y, ay + r * (PITCH * 4), r1 - r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {  // row order, two columns per FADD2
         s0 = tc::add2(s0, tc::pack2(x[i].x, x[i].y));
@@ -879,8 +895,8 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
               // staging columns [0, 32) = columns 32 ps .. of half 0, [32, 64) = the same of half 1
               const int c8 = stid & 7;
               float* out = p.agg_h + 32 * ps + 4 * c8;
-              segment_means(ab + 4 * c8, ab + 32 + 4 * c8, kMeanPitch, stid >> 3, nseg, s_rec, out, out + 64, kHidden,
-                            p.accumulate);
+              segment_means<kMeanPitch>(ab + 4 * c8, ab + 32 + 4 * c8, stid >> 3, nseg, s_rec, out, out + 64, kHidden,
+                                        p.accumulate);
             }
             trace_ev<TRACE>(trace, T, tn, (g << 8) | (0x24 + 3 * ps));
             slot_barrier(T);
@@ -946,8 +962,8 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
           {
             const int c8 = stid & 7;
             if (c8 < kVRow / 8)
-              segment_means(ab + 4 * c8, ab + 24 + 4 * c8, kMeanPitchV, stid >> 3, nseg, s_rec, p.agg_v + 4 * c8,
-                            p.agg_v + 24 + 4 * c8, kVRow, p.accumulate);
+              segment_means<kMeanPitchV>(ab + 4 * c8, ab + 24 + 4 * c8, stid >> 3, nseg, s_rec, p.agg_v + 4 * c8,
+                                         p.agg_v + 24 + 4 * c8, kVRow, p.accumulate);
           }
         }
       }
