@@ -17,8 +17,15 @@
 // next A operand), EPI-C (sigmoid gate * Vu -> next vector operand).  A TMEM lane is one edge row.
 //
 // Warp roles (608 threads): warps 0-7 epilogue of slot 0, warps 8-15 epilogue of slot 1 (two threads per edge row:
-// column halves), warps 16 / 17 lane 0 issue the MMAs of slot 0 / 1, warp 18 lane 0 streams weight slabs with
-// cp.async.bulk.
+// column halves), warps 16 / 17 issue the MMAs of slot 0 / 1 (converged, under elect.sync), warp 18 lane 0 streams
+// weight slabs with cp.async.bulk.
+//
+// Template switches of every kernel in this file: HAS_V (source vectors present: layers > 0), FAST (single fp16 pass,
+// pf_*_tc_f16: hi images only, SiLU on packed fp16 pairs; tolerance 2e-2 instead of 1e-4), TRACE (device timeline,
+// launched only while pf_tc_trace is armed).  What the epilogue warps are short of is registers (96 per thread, one
+// CTA of 19 warps per SM, L1 reduced to ~30 KB by the 217 KB of shared memory): values that must survive a long stage
+// are parked in dead TMEM columns, the row gather runs in two rounds of eight loads, and the next tile's source rows
+// are pulled into L2 one tile ahead ("r01c").
 #include "pf_common.cuh"
 #include "pf_tc.cuh"
 #include <type_traits>
