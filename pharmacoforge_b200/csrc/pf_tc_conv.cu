@@ -600,6 +600,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     // ---- gather h[src] (coalesced: 8 lanes x 16 B per row chunk), transpose through smem to one thread per row,
     //      split into fp16 (hi, lo) and store as the TMEM A operand of S_0 in region P
     float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36] / [32][28]
+    float4 vq[HAS_V ? 6 : 1];  // this half's 24 entries of v[src] ([3][16] component-major rows), cooperative layout
     {
       // Two rounds of 8 row loads (32 registers each) instead of 16 at once: the second round is issued right after the
       // first one's staging stores and flies under its fp16 split.  With all 16 loads in flight the 64 data registers did
@@ -644,6 +645,17 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       load8(gb, 1);
       split32(2 * hh);
       stage8(gb);
+      if constexpr (HAS_V) {  // the vector rows fly under the second split (they used to cost a round trip of their own)
+#pragma unroll
+        for (int ps = 0; ps < 6; ++ps) {
+          const int qq = 32 * ps + lane;
+          const int rr = qq / 6, pc = qq - 6 * rr;
+          const int sr = __shfl_sync(0xffffffffu, src, rr);
+          vq[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (sr >= 0)
+            vq[ps] = __ldg(reinterpret_cast<const float4*>(p.src_v + (size_t)sr * kVRow) + 4 * (pc >> 1) + 2 * hh + (pc & 1));
+        }
+      }
       split32(2 * hh + 1);
     }
 
@@ -651,16 +663,12 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     float vsc = 1.f, vinv = 1.f;        // power-of-two scale of the staged vector operand and its inverse
     float vh16[3] = {0.f, 0.f, 0.f};    // 17th hidden channel of GVP 0 (used by half 0)
     if constexpr (HAS_V) {
-      // ---- gather this half's 24 entries of v[src] ([3][16] component-major rows) the same way
+      // ---- transpose the vector rows (loaded above) the same way
 #pragma unroll
       for (int ps = 0; ps < 6; ++ps) {
         const int qq = 32 * ps + lane;
         const int rr = qq / 6, pc = qq - 6 * rr;
-        const int sr = __shfl_sync(0xffffffffu, src, rr);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sr >= 0)
-          v = __ldg(reinterpret_cast<const float4*>(p.src_v + (size_t)sr * kVRow) + 4 * (pc >> 1) + 2 * hh + (pc & 1));
-        *reinterpret_cast<float4*>(tb + rr * 28 + 4 * pc) = v;
+        *reinterpret_cast<float4*>(tb + rr * 28 + 4 * pc) = vq[ps];
       }
       __syncwarp();
       float pm = 0.f;
