@@ -573,6 +573,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     const int nrows = s_off[nseg];
     int src = -1;
     float xd[3] = {0.f, 0.f, 0.f}, dist = 0.f;
+    float gx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // coordinates of the edge's source and destination
     if (et < nrows) {
       int j = 0;
       if (contig) {  // largest j with s_off[j] <= et (empty segments share their successor's offset and lose)
@@ -586,14 +587,11 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       }
       src = contig && cur_pre_src >= 0 ? cur_pre_src : __ldg(p.col + s_start[j] + (et - s_off[j]));
       const int dst = s_dst[j];
-      const float dx = __ldg(p.src_x + (size_t)src * 3 + 0) - __ldg(p.dst_x + (size_t)dst * 3 + 0);
-      const float dy = __ldg(p.src_x + (size_t)src * 3 + 1) - __ldg(p.dst_x + (size_t)dst * 3 + 1);
-      const float dz = __ldg(p.src_x + (size_t)src * 3 + 2) - __ldg(p.dst_x + (size_t)dst * 3 + 2);
-      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      dist = sqrtf(fmaxf(d2, 1e-8f)) + 1e-8f;
-      xd[0] = dx / dist;
-      xd[1] = dy / dist;
-      xd[2] = dz / dist;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {  // loads only: the geometry is computed under the first round of row loads below
+        gx[c] = __ldg(p.src_x + (size_t)src * 3 + c);
+        gx[3 + c] = __ldg(p.dst_x + (size_t)dst * 3 + c);
+      }
     }
 
     trace_ev<TRACE>(trace, T, tn, 0x02);
@@ -641,6 +639,14 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         __syncwarp();
       };
       load8(ga, 0);
+      if (src >= 0) {  // edge geometry (gvp.py:474-479) while the first eight row loads are in flight
+        const float dx = gx[0] - gx[3], dy = gx[1] - gx[4], dz = gx[2] - gx[5];
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        dist = sqrtf(fmaxf(d2, 1e-8f)) + 1e-8f;
+        xd[0] = dx / dist;
+        xd[1] = dy / dist;
+        xd[2] = dz / dist;
+      }
       stage8(ga);
       load8(gb, 1);
       split32(2 * hh);
