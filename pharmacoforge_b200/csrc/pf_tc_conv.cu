@@ -267,30 +267,39 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
     tc::fence_after_sync();
     trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x20);
     constexpr int nslab = Cfg<MODE>::nslab(g);
-#pragma unroll
-    for (int k = 0; k < nslab; ++k) {
-      constexpr int base = slab_base<MODE>(g);
-      const int i = base + k, pos = i % kRing;
-      tc::mbar_wait(&bar_full[pos], full_parity<MODE>(i, t));
-      if (tc::elect_one()) {
-        const uint64_t b_hi = ring_hi + (uint64_t)(pos * (kSlab >> 4)), b_lo = ring_lo + (uint64_t)(pos * (kSlab >> 4));
-        if (k < 8) {
-          const uint32_t a_hi = Areg + 16 * k, a_lo = a_hi + 8;
-          tc::mma_ts(Dreg, a_hi, b_hi, kI128, k > 0);
-          if constexpr (!FAST) {
-            tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
-            tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
-          }
-        } else {
-          const uint64_t a_hi = stage_hi + (uint64_t)((k - 8) * (8192 >> 4)), a_lo = stage_lo + (uint64_t)((k - 8) * (8192 >> 4));
-          tc::mma_ss(Dreg, a_hi, b_hi, kI128, 1);
-          if constexpr (!FAST) {
-            tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
-            tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
-          }
+    // Two weight slabs per trip through the issue code (wait for both, one elected issue block, two commits): the
+    // per-slab overhead -- barrier poll, elect, warp re-convergence -- is paid once per pair.
+    auto issue_slab = [&](const int k, const int pos) {
+      const uint64_t b_hi = ring_hi + (uint64_t)(pos * (kSlab >> 4)), b_lo = ring_lo + (uint64_t)(pos * (kSlab >> 4));
+      if (k < 8) {
+        const uint32_t a_hi = Areg + 16 * k, a_lo = a_hi + 8;
+        tc::mma_ts(Dreg, a_hi, b_hi, kI128, k > 0);
+        if constexpr (!FAST) {
+          tc::mma_ts(Dreg, a_hi, b_lo, kI128, 1);
+          tc::mma_ts(Dreg, a_lo, b_hi, kI128, 1);
         }
-        tc::mma_commit(&my_empty[pos]);
-        if (k == nslab - 1) tc::mma_commit(&B.D);
+      } else {
+        const uint64_t a_hi = stage_hi + (uint64_t)((k - 8) * (8192 >> 4)), a_lo = stage_lo + (uint64_t)((k - 8) * (8192 >> 4));
+        tc::mma_ss(Dreg, a_hi, b_hi, kI128, 1);
+        if constexpr (!FAST) {
+          tc::mma_ss(Dreg, a_hi, b_lo, kI128, 1);
+          tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
+        }
+      }
+      tc::mma_commit(&my_empty[pos]);
+    };
+#pragma unroll
+    for (int k = 0; k < nslab; k += 2) {
+      constexpr int base = slab_base<MODE>(g);
+      const int i0 = base + k, pos0 = i0 % kRing;
+      const bool two = k + 1 < nslab;
+      const int i1 = i0 + 1, pos1 = i1 % kRing;
+      tc::mbar_wait(&bar_full[pos0], full_parity<MODE>(i0, t));
+      if (two) tc::mbar_wait(&bar_full[pos1], full_parity<MODE>(i1, t));
+      if (tc::elect_one()) {
+        issue_slab(k, pos0);
+        if (two) issue_slab(k + 1, pos1);
+        if (k + 2 >= nslab) tc::mma_commit(&B.D);
       }
       __syncwarp();
     }
