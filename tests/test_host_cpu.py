@@ -239,3 +239,23 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
         net[1](net[0](torch.full((4, 5), float(rank + 1)))).sum().backward()
         g.append(net[0].weight.grad.clone())
     assert torch.allclose(r0["g0"], (g[0] + g[1]) / 2, rtol=1e-6, atol=1e-6)
+
+
+def test_bench_arguments_name_the_configs(monkeypatch):
+    """bench.py: the default is BASELINE.json configs[1]; --workload "configs[2]" selects the 1,500-atom stress shape and
+    --precision fp16 the single-pass mode (parsed on the CPU, nothing is launched)."""
+    import importlib
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse()
+    assert (a.gpus, a.pockets, a.atoms, a.samples, a.precision, a.workload) == (1, 256, 400, 30, "fp32", "configs[1]")
+    assert a.warmup >= 3
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "configs[2]", "--precision", "fp16"])
+    a = bench.parse()
+    assert (a.atoms, a.pockets, a.samples, a.precision) == (1500, 32, 16, "fp16")
+    pockets, sizes = None, None
+    from pharmacoforge_b200.synthetic import uniform_sizes
+    s = uniform_sizes(16, 3, 16, seed=0)
+    assert len(s) == 16 and min(s) >= 3 and max(s) <= 16
