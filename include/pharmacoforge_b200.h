@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 
 enum PfStatus {
   PF_OK = 0,
@@ -148,6 +148,21 @@ int pf_edge_conv_tc_f16(const float* src_h, const float* src_v, const float* src
                         const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const void* wblob,
                         float* agg_h, float* agg_v, int32_t accumulate, void* stream);
 
+/* First conv layer with one-hot source features: the exact split of SURVEY.md hard part 2,
+ *   Wf0 [h_src; rbf; sh] = Wf0[:, 0:128] h_src  (per source NODE)  +  Wf0[:, 128:161] [rbf; sh]  (per edge).
+ * pf_seed_table: table[r][:] = k * Wf0[:, 0:128] h[rep_node[r]][:] for r < n_rows (rows with rep_node[r] < 0 are left
+ * untouched), fp32 FFMA; w_msg is the fp32 packed message chain of the edge type (pf_edge_conv's `w`), k = -log2(e) the
+ * factor the tcgen05 weight images carry.  pf_edge_conv_tc_seeded: pf_edge_conv_tc / _f16 without source scalars and
+ * vectors: edge e starts GVP 0's accumulator from table row seed_row[col[e]] and contracts only [rbf; sh] per edge
+ * (3 of the 11 K-steps of GVP 0); no 512-byte row gather, no fp16 split of gathered features.  Replaces the same
+ * reference lines as pf_edge_conv (gvp.py:472-497, 540-551) for conv layer 0, where edges.src['v'] is zero and
+ * edges.src['h'] is the encoder output (dynamics_gvp.py:143-173). */
+int pf_seed_table(const float* h, const int32_t* rep_node, int32_t n_rows, const float* w_msg, float* table, void* stream);
+int pf_edge_conv_tc_seeded(const int32_t* seed_row, const float* seed_table, const float* src_x, const float* dst_x,
+                           const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst, const int32_t* col,
+                           const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles, const void* wblob,
+                           float* agg_h, float* agg_v, int32_t accumulate, int32_t fp16_single_pass, void* stream);
+
 /* Debug timeline of CTA 0 of the next pf_edge_conv_tc launches: device_buf = int64[4][4096][2] of (tag, clock64)
  * for the epilogue of tile slot 0 / 1 and the two MMA issuers, followed by int64[148][2] = (begin, end) globaltimer ns of
  * every CTA; NULL disarms.  Not used on the product path. */
@@ -242,11 +257,23 @@ typedef struct PfSampleArgs {
    * node_data['pharm'] of the last layer feeds the noise head.  eps_h / eps_x are bit-identical either way; the
    * nominal (reference-equivalent) work is done when the flag is clear, which is the default. */
   uint32_t flags;
+  /* First-layer seeding (tcgen05 path; seed_row == NULL disables it): when the protein features are one-hot, the encoder
+   * output of a protein node depends only on (graph, atom type), so the per-node part of the first message GVP's scalar
+   * contraction is one table row per (graph, type) -- see pf_seed_table / pf_edge_conv_tc_seeded.  seed_row and seed_rep are
+   * static per batch; seed_table is scratch rewritten by every pf_denoiser call. */
+  const int32_t* seed_row;  /* [n_prot] table row of every protein node: graph * n_prot_feats + type */
+  const int32_t* seed_rep;  /* [n_seed_rows] one protein node with that (graph, type), or -1 if the graph has none */
+  float* seed_table;        /* [n_seed_rows][128] */
+  int32_t n_seed_rows;
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph
  * kernels, noise head and posterior step are unchanged (fp32).  Off by default: the default is the fp32-parity mode. */
 #define PF_FLAG_FP16_SINGLE_PASS 2u
+
+/* PF_FLAG_NO_LAYER0_SEED: run the first conv layer's pp messages through the general kernel (row gather + all 11 K-steps of
+ * GVP 0) even when the seed arrays are bound -- the A/B switch of the seeded path (results agree to fp32 rounding). */
+#define PF_FLAG_NO_LAYER0_SEED 4u
 
 /* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the
  * timestep value of graph g.  Results in a->eps_h / a->eps_x. */

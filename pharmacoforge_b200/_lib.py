@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpharmacoforge_b200.so")
+# PF_LIB_PATH: A/B builds of the same library (csrc/Makefile `variant`); experiments only
+LIB_PATH = os.environ.get("PF_LIB_PATH") or os.path.join(_HERE, "libpharmacoforge_b200.so")
 
 c_i32p = C.c_void_p
 c_f32p = C.c_void_p
@@ -36,6 +37,9 @@ SIGNATURES = {
     "pf_node_update_tc_f16": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_void_p, c_f32p, c_f32p, STREAM]),
     "pf_edge_conv_tc_f16": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                       C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, STREAM]),
+    "pf_seed_table": (C.c_int, [c_f32p, c_i32p, C.c_int32, c_f32p, c_f32p, STREAM]),
+    "pf_edge_conv_tc_seeded": (C.c_int, [c_i32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
+                                         C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, C.c_int32, STREAM]),
     "pf_zero_i32": (C.c_int, [c_i32p, C.c_int64, STREAM]),
     "pf_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, STREAM]),
     "pf_encode": (C.c_int, [c_f32p, C.c_int32, c_i32p, C.c_int32, c_f32p, c_f32p, c_f32p, STREAM]),
@@ -73,6 +77,7 @@ SIGNATURES = {
 }
 
 MAX_CONVS = 8
+ABI_VERSION = 2
 
 
 class PfSampleArgs(C.Structure):
@@ -113,6 +118,7 @@ class PfSampleArgs(C.Structure):
         ("n_steps", C.c_int32),
         ("dev_status", C.c_void_p),
         ("flags", C.c_uint32),
+        ("seed_row", C.c_void_p), ("seed_rep", C.c_void_p), ("seed_table", C.c_void_p), ("n_seed_rows", C.c_int32),
     ]
 
 
@@ -133,7 +139,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.pf_abi_version() != 1:
+    if lib.pf_abi_version() != ABI_VERSION:
         raise ImportError("libpharmacoforge_b200.so ABI version mismatch")
     if lib.pf_sample_args_size() != C.sizeof(PfSampleArgs):
         raise ImportError("PfSampleArgs layout differs between _lib.py and the compiled library")

@@ -54,6 +54,19 @@ def _chunk_graphs(weights: np.ndarray, target: int) -> np.ndarray:
     return np.asarray(bounds, dtype=np.int64)
 
 
+def on_batch_device(fn):
+    """Method decorator for `(self, g: GraphBatch, ...)` entry points: the kernels launch on the CURRENT device, so the
+    batch's device is entered for the duration of the call (a batch on cuda:1 works whatever the caller's current
+    device is; ops.py rejects tensors that do not live on the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, g, *args, **kwargs):
+        with torch.cuda.device(g.device):
+            return fn(self, g, *args, **kwargs)
+    return wrapper
+
+
 class GraphBatch:
     """See module docstring.  Build with `GraphBatch.from_pockets`."""
 
@@ -68,10 +81,18 @@ class GraphBatch:
         """One graph per (pocket, requested pharmacophore size), pocket-major, exactly the order
         `PharmacophoreDiff.sample` flattens them in (pharmacodiff.py:538-544).  `graph_range` restricts the batch
         to a slice of that flattened list (max_batch_size chunking / multi-GPU sharding)."""
-        self = cls()
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("GraphBatch lives on a CUDA device; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):   # the kernels launch on the current device
+            return cls._from_pockets(pockets, sizes, dev, pp_cutoff, pf_k, ff_max_nbrs, pp_max_nbrs, graph_range,
+                                     tile_rows)
+
+    @classmethod
+    def _from_pockets(cls, pockets, sizes, dev, pp_cutoff, pf_k, ff_max_nbrs, pp_max_nbrs, graph_range, tile_rows):
+        self = cls()
         self.device = dev
         self.pf_k, self.ff_max_nbrs = int(pf_k), int(ff_max_nbrs)
         tile_rows = int(os.environ.get("PF_TILE_ROWS", tile_rows))   # A/B switch: 64 = fp32 FFMA kernels
@@ -132,6 +153,7 @@ class GraphBatch:
         self.pp_n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
         ops.plan_tiles(self.pp_cnt, self.prot_ptr, False, self.tile_rows, self.pp_tiles, self.pp_n_tiles, self.status)
         self.pp_num_tiles = int(self.pp_n_tiles.item())
+        self.check_status()   # e.g. PF_DEV_DEGREE_OVERFLOW: a pp in-degree above the tile capacity, reported now
         self.pp_tiles = self.pp_tiles[:2 * max(self.pp_num_tiles, 1)].clone()
 
         # ---- static description of the dynamic edge buffers (K2 refills them every step)
@@ -177,6 +199,27 @@ class GraphBatch:
         self.pharm_x0 = x_0.to(self.device, torch.float32).contiguous()
         self.pharm_h0 = h_0.to(self.device, torch.float32).contiguous()
         return self
+
+    def seed_arrays(self):
+        """(seed_row [n_prot] int32, seed_rep [n_graphs * F] int32) for the first-layer seeding of the pp messages, or
+        None when the protein features are not one-hot.  The encoder output of a one-hot row depends only on (graph, atom
+        type) -- SURVEY.md §8 a4 -- so protein node n reads table row graph(n) * F + type(n), and row r is computed from
+        the representative node seed_rep[r] (-1: no atom of that type in that graph)."""
+        cached = getattr(self, "_seed_arrays", False)
+        if cached is not False:
+            return cached
+        f = self.prot_feats
+        F = f.shape[1]
+        onehot = bool(((f == 0) | (f == 1)).all().item()) and bool((f.sum(dim=1) == 1).all().item())
+        if not onehot:
+            self._seed_arrays = None
+            return None
+        row = self.batch_idxs()["prot"] * F + f.argmax(dim=1)
+        rep = torch.full((self.n_graphs * F,), self.n_prot, dtype=torch.int64, device=self.device)
+        rep.scatter_reduce_(0, row, torch.arange(self.n_prot, device=self.device), reduce="amin")
+        rep[rep == self.n_prot] = -1
+        self._seed_arrays = (row.to(torch.int32).contiguous(), rep.to(torch.int32).contiguous())
+        return self._seed_arrays
 
     # ------------------------------------------------------------------ reference-style accessors
     def batch_idxs(self):

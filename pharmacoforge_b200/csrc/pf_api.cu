@@ -204,7 +204,7 @@ extern "C" int pf_posterior_step(float* pharm_x, float* pharm_h, int32_t nh, con
   PF_CHECK_ARG(pharm_x && pharm_h && eps_x && eps_h && noise_x && noise_h && pharm_ptr && prot_x && prot_ptr,
                "pf_posterior_step: null pointer");
   if (n_graphs <= 0) return PF_OK;
-  const int grid = n_graphs < 32 * kNumSms ? n_graphs : 32 * kNumSms;
+  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
   posterior_kernel<<<grid, 128, 0, as_stream(stream)>>>(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h,
                                                         pharm_ptr, prot_x, prot_ptr, n_graphs, alpha_ts, var_terms,
                                                         sigma_q);
@@ -224,7 +224,7 @@ extern "C" int pf_segment_shift3(float* x, const int32_t* ptr, int32_t n_graphs,
                                  void* stream) {
   PF_CHECK_ARG(x && ptr && com, "pf_segment_shift3: null pointer");
   if (n_graphs <= 0) return PF_OK;
-  const int grid = n_graphs < 32 * kNumSms ? n_graphs : 32 * kNumSms;
+  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
   segment_shift3_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, ptr, n_graphs, com, sign);
   PF_CHECK_LAUNCH("pf_segment_shift3");
   return PF_OK;
@@ -315,9 +315,18 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     const bool prot_side = !((a->flags & PF_FLAG_SKIP_DEAD_WORK) && l == a->n_convs - 1);
     if (prot_side) {
     prof_begin(kSitePP, as_stream(stream));
+    if (l == 0 && tc && a->seed_row != nullptr && !(a->flags & PF_FLAG_NO_LAYER0_SEED)) {
+      // first layer: the per-node part of GVP 0 from the (graph, atom type) table, the rest per edge (timed with the site)
+      PF_CHECK_ARG(a->seed_rep && a->seed_table && a->n_seed_rows > 0, "pf_denoiser: incomplete seed arrays");
+      PF_TRY(pf_seed_table(a->prot_h, a->seed_rep, a->n_seed_rows, a->w_msg[l][3], a->seed_table, stream));
+      PF_TRY(pf_edge_conv_tc_seeded(a->seed_row, a->seed_table, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr,
+                                    a->pp_col, a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg_tc[l][3],
+                                    a->prot_agg_h, a->prot_agg_v, 0, f16 ? 1 : 0, stream));
+    } else {
     PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col,
                          a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->w_msg_tc[l][3],
                          a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 0, stream));
+    }
   prof_end(kSitePP, as_stream(stream));
     prof_begin(kSiteFP, as_stream(stream));
     PF_TRY(edge_conv_any(tc, f16, a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,

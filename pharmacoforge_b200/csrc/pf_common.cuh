@@ -40,7 +40,30 @@ constexpr int kHidden = PF_HIDDEN;
 constexpr int kVec = PF_VEC;
 constexpr int kRbf = PF_RBF;
 constexpr int kVRow = 3 * kVec;  // 48 floats per node vector row, layout [c][u]
-constexpr int kNumSms = 148;
+constexpr int kNumSms = 148;  // B200; the persistent kernels size their grids with num_sms() (queried per device)
+
+// Per-device launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of the (function, device) pair,
+// so a process-wide "configured" flag breaks the second GPU of a process; the flag is kept per device ordinal.  Races are
+// benign (the attribute call is idempotent), the flags are only ever set.
+constexpr int kMaxDevices = 64;
+struct PerDeviceFlag {
+  volatile bool done[kMaxDevices];
+};
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < kMaxDevices ? d : 0;
+}
+inline int num_sms() {  // SM count of the current device (148 on B200), cached per ordinal
+  static volatile int cache[kMaxDevices];
+  const int d = current_device();
+  if (cache[d] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = kNumSms;
+    cache[d] = n;
+  }
+  return cache[d];
+}
 
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 

@@ -444,7 +444,7 @@ extern "C" int pf_encode(const float* feats, int32_t n_feats, const int32_t* nod
   PF_CHECK_ARG(feats && node_ptr && t && w && h_out, "pf_encode: null pointer");
   PF_CHECK_ARG(n_feats >= 1 && n_feats <= kEncMaxIn, "pf_encode: n_feats out of range");
   if (n_graphs <= 0) return PF_OK;
-  const int grid = n_graphs < 8 * kNumSms ? n_graphs : 8 * kNumSms;
+  const int grid = n_graphs < 8 * num_sms() ? n_graphs : 8 * num_sms();
   encode_kernel<<<grid, 256, 0, as_stream(stream)>>>(feats, n_feats, node_ptr, n_graphs, t, w, h_out);
   PF_CHECK_LAUNCH("pf_encode");
   return PF_OK;
@@ -460,15 +460,16 @@ extern "C" int pf_edge_conv(const float* src_h, const float* src_v, const float*
   PF_CHECK_ARG(n_gvps >= 1, "pf_edge_conv: n_gvps < 1");
   if (max_tiles <= 0) return PF_OK;
   const size_t smem = kTileSmemBytes + (4 * kTileRows + 1) * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured = {};
+  const int dev_ = current_device();
+  if (!configured.done[dev_]) {
     int rc = set_smem(edge_conv_kernel, smem);
     if (rc) return rc;
-    configured = true;
+    configured.done[dev_] = true;
   }
   EdgeConvParams p{src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
                    w,     n_gvps, agg_h, agg_v, accumulate};
-  const int grid = max_tiles < kNumSms ? max_tiles : kNumSms;
+  const int grid = max_tiles < num_sms() ? max_tiles : num_sms();
   edge_conv_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_edge_conv");
   return PF_OK;
@@ -480,15 +481,16 @@ extern "C" int pf_node_update(const float* h_in, const float* v_in, const float*
   PF_CHECK_ARG(h_in && agg_h && agg_v && w && h_out && v_out, "pf_node_update: null pointer");
   PF_CHECK_ARG(n_gvps >= 1, "pf_node_update: n_gvps < 1");
   if (n_nodes <= 0) return PF_OK;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured = {};
+  const int dev_ = current_device();
+  if (!configured.done[dev_]) {
     int rc = set_smem(node_update_kernel, kNodeSmemBytes);
     if (rc) return rc;
-    configured = true;
+    configured.done[dev_] = true;
   }
   NodeUpdateParams p{h_in, v_in, agg_h, agg_v, (long long)n_nodes, w, n_gvps, h_out, v_out};
   const long long tiles = (n_nodes + kTileRows - 1) / kTileRows;
-  const int grid = (int)(tiles < kNumSms ? tiles : kNumSms);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   node_update_kernel<<<grid, kThreads, kNodeSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_node_update");
   return PF_OK;
@@ -499,15 +501,16 @@ extern "C" int pf_noise_head(const float* h, const float* v, int64_t n_nodes, co
   PF_CHECK_ARG(h && v && w && eps_h && eps_x, "pf_noise_head: null pointer");
   PF_CHECK_ARG(n_gvps >= 1 && n_out >= 1 && n_out <= 64, "pf_noise_head: bad n_gvps / n_out");
   if (n_nodes <= 0) return PF_OK;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured = {};
+  const int dev_ = current_device();
+  if (!configured.done[dev_]) {
     int rc = set_smem(noise_head_kernel, kTileSmemBytes);
     if (rc) return rc;
-    configured = true;
+    configured.done[dev_] = true;
   }
   NoiseHeadParams p{h, v, (long long)n_nodes, w, n_gvps, n_out, eps_h, eps_x};
   const long long tiles = (n_nodes + kTileRows - 1) / kTileRows;
-  const int grid = (int)(tiles < kNumSms ? tiles : kNumSms);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   noise_head_kernel<<<grid, kThreads, kTileSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_noise_head");
   return PF_OK;

@@ -394,7 +394,7 @@ extern "C" int pf_radius_count(const float* x, const int32_t* seg_ptr, int32_t n
                                int32_t* deg, void* stream) {
   PF_CHECK_ARG(x && seg_ptr && deg && max_nbrs >= 0, "pf_radius_count: null pointer");
   if (n_seg <= 0) return PF_OK;
-  const int grid = n_seg < 16 * kNumSms ? n_seg : 16 * kNumSms;
+  const int grid = n_seg < 16 * num_sms() ? n_seg : 16 * num_sms();
   radius_kernel<false><<<grid, kRadThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, r * r, max_nbrs, deg, nullptr,
                                                                     nullptr);
   PF_CHECK_LAUNCH("pf_radius_count");
@@ -405,7 +405,7 @@ extern "C" int pf_radius_fill(const float* x, const int32_t* seg_ptr, int32_t n_
                               const int32_t* rowptr, int32_t* col, void* stream) {
   PF_CHECK_ARG(x && seg_ptr && rowptr && col && max_nbrs >= 0, "pf_radius_fill: null pointer");
   if (n_seg <= 0) return PF_OK;
-  const int grid = n_seg < 16 * kNumSms ? n_seg : 16 * kNumSms;
+  const int grid = n_seg < 16 * num_sms() ? n_seg : 16 * num_sms();
   radius_kernel<true><<<grid, kRadThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, r * r, max_nbrs, nullptr,
                                                                    rowptr, col);
   PF_CHECK_LAUNCH("pf_radius_fill");
@@ -428,7 +428,7 @@ extern "C" int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const 
   if (n_graphs <= 0) return PF_OK;
   DynGraphParams p{prot_x,  pharm_x, prot_ptr, pharm_ptr, n_graphs,   ff_r * ff_r,  ff_max_nbrs, pf_k,  ff_start,
                    ff_cnt,  ff_col,  pf_cnt,   pf_col,    fp_seg_dst, fp_seg_start, fp_seg_cnt,  fp_col, dev_status};
-  const int grid = n_graphs < 32 * kNumSms ? n_graphs : 32 * kNumSms;
+  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
   if (pf_k <= 8)
     dyn_graph_kernel<8><<<grid, kDynThreads, 0, as_stream(stream)>>>(p);
   else

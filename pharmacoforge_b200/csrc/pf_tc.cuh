@@ -173,6 +173,11 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -196,6 +201,34 @@ __device__ __forceinline__ void silu_split2(uint32_t a0, uint32_t a1, uint64_t b
   float d0, d1;
   unpack2(d, d0, d1);
   const uint64_t f = mul2(v, pack2(rcp_approx(d0), rcp_approx(d1)));
+  unpack2(f, f0, f1);
+  hi = pack_f16x2_sat(f0, f1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  float l0, l1;
+  unpack2(sub2(f, pack2(hf.x, hf.y)), l0, l1);
+  lo = pack_f16x2_sat(l0, l1);
+}
+
+// Pre-scaled form used by the tensor-core kernels since r02: the host folds k = -log2(e) into Wf and bf
+// (weights.py: TC_PRESCALE), so the accumulator already holds t = k (D + b) and
+//   SiLU(y) = y / (1 + 2^t) = t * rcp(k (2^t + 1)),  y = t / k
+// costs 3.5 instructions per element (FADD2 bias, 2 MUFU.EX2, FFMA2, 2 MUFU.RCP, FMUL2 per pair) + 2.5 for the fp16
+// (hi, lo) split, against 8.5 for the shared-reciprocal form below.  The XU pipe was 20 % busy there: the kernels are
+// bound by instruction issue and latency, not by MUFU throughput, so two MUFU per element is the cheaper trade.
+// Limits: t -> +inf (y << 0): 2^t = +inf, k * inf = -inf, rcp = -0, f = -0;  t -> -inf (y >> 0): 2^t = 0, f = t / k = y.
+constexpr float kSiluK = -1.4426950408889634f;  // -log2(e)
+__device__ __forceinline__ uint64_t silu_pre2(uint32_t a0, uint32_t a1, uint64_t bias) {
+  const uint64_t t = add2(pack2(__uint_as_float(a0), __uint_as_float(a1)), bias);
+  float t0, t1;
+  unpack2(t, t0, t1);
+  const uint64_t kk = pack2(kSiluK, kSiluK);
+  float d0, d1;
+  unpack2(fma2(pack2(ex2_approx(t0), ex2_approx(t1)), kk, kk), d0, d1);
+  return mul2(t, pack2(rcp_approx(d0), rcp_approx(d1)));
+}
+__device__ __forceinline__ void silu_pre_split2(uint32_t a0, uint32_t a1, uint64_t bias, float& f0, float& f1,
+                                                uint32_t& hi, uint32_t& lo) {
+  const uint64_t f = silu_pre2(a0, a1, bias);
   unpack2(f, f0, f1);
   hi = pack_f16x2_sat(f0, f1);
   const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
@@ -260,9 +293,11 @@ __device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) 
   return r;
 }
 __device__ __forceinline__ uint32_t silu_h2(uint32_t a0, uint32_t a1, uint64_t bias) {
+  // the accumulator and the bias carry the host-side factor k = -log2(e) (see silu_pre2): h = y / 2 = t * (0.5 / k)
   float y0, y1;
-  unpack2(add2(pack2(__uint_as_float(a0), __uint_as_float(a1)), bias), y0, y1);
-  const uint32_t h = hmul2_u(pack_f16x2_sat(y0, y1), 0x38003800u);  // x 0.5 (exact)
+  const uint64_t hk = pack2(0.5f / kSiluK, 0.5f / kSiluK);
+  unpack2(mul2(add2(pack2(__uint_as_float(a0), __uint_as_float(a1)), bias), hk), y0, y1);
+  const uint32_t h = pack_f16x2_sat(y0, y1);
   return hfma2_u(h, tanh_h2(h), h);
 }
 

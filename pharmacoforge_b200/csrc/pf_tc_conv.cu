@@ -44,15 +44,24 @@ struct Cfg;
 template <>
 struct Cfg<0> {  // 3-GVP edge message chain; GVP 0: K = 128 h + 16 rbf + 17 sh (+15 zero) = 176, GVP 1, 2: K = 144
   static constexpr int kGvps = 3, kSlabsPerTile = 29, kVecOff = 24576, kConstOff = 30720, kSmallBytes = 32768;
+  static constexpr int kBlobSlab0 = 0, kBlobSlabs = 29;  // first slab of the tile sequence / slabs in the blob
   __host__ __device__ static constexpr int nslab(int g) { return g == 0 ? 11 : 9; }
 };
 template <>
 struct Cfg<1> {  // 2-GVP node update chain; K = 128 f + 16 sh = 144
   static constexpr int kGvps = 2, kSlabsPerTile = 18, kVecOff = 16384, kConstOff = 20480, kSmallBytes = 24576;
+  static constexpr int kBlobSlab0 = 0, kBlobSlabs = 18;
   __host__ __device__ static constexpr int nslab(int) { return 9; }
 };
+template <>
+struct Cfg<2> {  // seeded first-layer message chain (same blob as Cfg<0>): the h part of GVP 0 (its first 8 K-steps) is
+                 // precomputed per source node and arrives as the accumulator seed, so a tile streams slabs 8 .. 28 only
+  static constexpr int kGvps = 3, kSlabsPerTile = 21, kVecOff = 24576, kConstOff = 30720, kSmallBytes = 32768;
+  static constexpr int kBlobSlab0 = 8, kBlobSlabs = 29;
+  __host__ __device__ static constexpr int nslab(int g) { return g == 0 ? 3 : 9; }
+};
 template <int MODE>
-constexpr int blob_small_off() { return Cfg<MODE>::kSlabsPerTile * kSlab; }
+constexpr int blob_small_off() { return Cfg<MODE>::kBlobSlabs * kSlab; }
 template <int MODE>
 constexpr int blob_bytes() { return blob_small_off<MODE>() + Cfg<MODE>::kSmallBytes; }
 constexpr int kGateOff = 0;
@@ -87,6 +96,10 @@ struct Params {
   float *agg_h, *agg_v;
   int accumulate;
   long long* trace;  // optional timeline of CTA 0 (pf_tc_trace): [4 roles][kTraceCap][2] = (tag, clock64)
+  // SEED kernels only (first conv layer, one-hot source features): row seed_row[src] of `seed` ([rows][128] fp32) is
+  // k Wf0[:, 0:128] h_src, the per-node part of GVP 0's scalar contraction (pf_seed_table); src_h is not read
+  const int* seed_row;
+  const float* seed;
 };
 
 // sigma(y) = 1 / (1 + 2^(-y log2 e)) on the two MUFU ops with no range fix-up code: ex2.approx overflows to +inf for
@@ -114,6 +127,14 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
   *reinterpret_cast<uint4*>(a + 6144) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
 }
 
+// Experiment switches of the node-update kernel: tile-wise alternation of the two slots' S jobs,
+// and a start-up delay of the odd CTAs (ns) so that half of the grid runs half a tile behind the other half.
+#ifndef PF_K4_TILE_ALT
+#define PF_K4_TILE_ALT 0
+#endif
+#ifndef PF_K4_CTA_STAGGER_NS
+#define PF_K4_CTA_STAGGER_NS 0
+#endif
 constexpr int kTraceCap = 4096;
 #ifndef PF_DSLEEP
 #define PF_DSLEEP 100
@@ -167,7 +188,7 @@ __device__ void producer_role(const uint8_t* wblob, uint8_t* smem, uint64_t* bar
         if (2 * tprev + 1 < my_tiles) tc::mbar_wait(&bar_empty[kRing + pos], par);
       }
       tc::mbar_expect_tx(&bar_full[pos], kSlab);
-      tc::bulk_g2s(smem + kOffRing + pos * kSlab, wblob + (size_t)i * kSlab, kSlab, &bar_full[pos]);
+      tc::bulk_g2s(smem + kOffRing + pos * kSlab, wblob + (size_t)(i + Cfg<MODE>::kBlobSlab0) * kSlab, kSlab, &bar_full[pos]);
     }
   }
 }
@@ -209,6 +230,27 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
   // the CUDA cores while the other owns the tensor pipe) instead of marching in lockstep.  The order also keeps the
   // two consumers of the shared weight ring within one job (<= 11 of 12 slabs) of each other.
   const int n_other_jobs = ((my_tiles + T) >> 1) * Cfg<MODE>::kGvps;  // S jobs of the other slot
+  const int n_my_jobs = n_mine * Cfg<MODE>::kGvps;
+  // Global issue order of the S jobs: *turn holds the sequence number that may issue next.  Edge kernels: job-wise
+  // alternation (slot 0 job j, slot 1 job j, ...).  Node update (kTileAlt): TILE-wise alternation (both jobs of slot 0's
+  // tile, then both of slot 1's): a slot's GVP chain then runs under the other slot's memory phases (back end + front end)
+  // instead of both slots loading, computing and storing in lockstep.
+  constexpr bool kTileAlt = (MODE == 1) && (PF_K4_TILE_ALT != 0);
+  constexpr int kG = Cfg<MODE>::kGvps;
+  auto seq_of = [&](int slot, int j) { return kTileAlt ? (2 * (j / kG) + slot) * kG + (j % kG) : 2 * j + slot; };
+  auto seq_valid = [&](int sq) {   // does the job with this sequence number exist?
+    int slot, j;
+    if (kTileAlt) {
+      const int blk = sq / kG;
+      slot = blk & 1;
+      j = (blk >> 1) * kG + sq % kG;
+    } else {
+      slot = sq & 1;
+      j = sq >> 1;
+    }
+    return j < (slot == T ? n_my_jobs : n_other_jobs);
+  };
+  const int seq_end = kTileAlt ? 2 * kG * ((my_tiles + 1) >> 1) + 2 * kG : 2 * (n_my_jobs > n_other_jobs ? n_my_jobs : n_other_jobs) + 2;
   int job = 0;
   int tn = 0;
   constexpr uint32_t kI128 = tc::make_idesc_f16(128, 128);
@@ -259,17 +301,19 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
     tc::mbar_wait(&B.A, p_A);
     p_A ^= 1;
     {
-      const int need = T == 0 ? 2 * job : 2 * job + 1;       // S jobs issued before this one in the global order
-      const bool has_pred = T == 0 ? (job >= 1 && job - 1 < n_other_jobs) : true;
-      if (has_pred)
-        while (*turn < need) __nanosleep(20);
+      const int my_seq = seq_of(T, job);
+      while (*turn != my_seq) __nanosleep(20);
     }
     tc::fence_after_sync();
     trace_ev<TRACE>(trace, 2 + T, tn, (g << 8) | 0x20);
     constexpr int nslab = Cfg<MODE>::nslab(g);
     // Two weight slabs per trip through the issue code (wait for both, one elected issue block, two commits): the
     // per-slab overhead -- barrier poll, elect, warp re-convergence -- is paid once per pair.
-    auto issue_slab = [&](const int k, const int pos) {
+    // MODE 2, GVP 0: the accumulator was seeded by the epilogue warps (K-steps 0 .. 7 precomputed per node); the job is
+    // the three staged K-steps (rbf, sh, 17th hidden channel) and accumulates from its first MMA
+    constexpr int kstep0 = (MODE == 2 && g == 0) ? 8 : 0;
+    auto issue_slab = [&](const int kslab, const int pos) {
+      const int k = kslab + kstep0;
       const uint64_t b_hi = ring_hi + (uint64_t)(pos * (kSlab >> 4)), b_lo = ring_lo + (uint64_t)(pos * (kSlab >> 4));
       if (k < 8) {
         const uint32_t a_hi = Areg + 16 * k, a_lo = a_hi + 8;
@@ -304,11 +348,12 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
       __syncwarp();
     }
     {
-      // slot 0's jobs of an unpartnered last tile count double so that the numbering above stays valid
-      const bool partner_has_job = T == 0 ? job < n_other_jobs : true;
+      // hand the turn to the next job that exists (an unpartnered last tile leaves gaps in the other slot's numbering)
+      int nxt = seq_of(T, job) + 1;
+      while (nxt < seq_end && !seq_valid(nxt)) ++nxt;
       if (lane0) {
         __threadfence_block();
-        *turn = *turn + (partner_has_job ? 1 : 2);
+        *turn = nxt;
       }
       ++job;
       __syncwarp();
@@ -456,9 +501,10 @@ __device__ __forceinline__ void segment_means(const float* bx, const float* by, 
 }
 
 // Two threads per edge row: half hh owns scalar columns [64 hh, 64 hh + 64) and vector channels [8 hh, 8 hh + 8).
-template <bool HAS_V, bool FAST, bool TRACE>
+template <bool HAS_V, bool FAST, bool TRACE, bool SEED>
 __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
                               uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
+  static_assert(!(SEED && HAS_V), "the seeded chain is the first conv layer: no source vectors");
   const int stid = threadIdx.x & 255;
   const int hh = stid >> 7;          // column half
   const int et = stid & 127;         // edge row of the tile == TMEM lane
@@ -493,6 +539,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   // feature rows are then pulled into L2 before the next tile's gather, which would otherwise wait on DRAM twice
   // (col -> rows) with nothing to overlap.
   int pf_e0 = 0, pf_rows = 0, nx_src = -1, cur_pre_src = -1;
+  int nx_srow = -1, cur_pre_srow = -1;  // SEED: seed-table row of nx_src, loaded one tile ahead as well
   auto load_segs = [&](int s0_, int nseg_) {
     pf_c = 0;
     pf_e0 = __ldg(p.seg_start + s0_);
@@ -522,6 +569,8 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     const int cur_c = pf_c, cur_start = pf_start, cur_dst = pf_dst, cur_off = pf_off, cur_next = pf_next;
     cur_pre_src = nx_src;  // meaningful only if this tile turns out contiguous (it was loaded as col[first edge + et])
     nx_src = -1;
+    cur_pre_srow = nx_srow;
+    nx_srow = -1;
     const bool have_next = it + 2 < my_tiles;
     if (it + 2 < my_tiles) {  // prefetch for the next tile of this slot
       pf_s0 = pf2_s0;
@@ -608,6 +657,40 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
     //      split into fp16 (hi, lo) and store as the TMEM A operand of S_0 in region P
     float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36] / [32][28]
     float4 vq[HAS_V ? 6 : 1];  // this half's 24 entries of v[src] ([3][16] component-major rows), cooperative layout
+    if constexpr (SEED) {
+      // ---- seeded layer: no row gather, no fp16 split.  The accumulator of S_0 (region Q) is initialised with this edge's
+      // row of the per-node table (k Wf0[:, 0:128] h_src); the table has one row per (graph, atom type), so the rows of
+      // a tile are a handful of 512-byte lines that stay in L1 / L2.  Two rounds of 32 columns (8 loads in flight).
+      const bool pre = contig && cur_pre_src >= 0 && cur_pre_srow >= 0;
+      const int srow = src >= 0 ? (pre ? cur_pre_srow : __ldg(p.seed_row + src)) : -1;
+      const float4* prow = reinterpret_cast<const float4*>(p.seed + (size_t)(srow < 0 ? 0 : srow) * kHidden + 64 * hh);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float4 r8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r8[i] = srow >= 0 ? __ldg(prow + 8 * c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c == 0 && src >= 0) {  // edge geometry (gvp.py:474-479) while the first eight loads are in flight
+          const float dx = gx[0] - gx[3], dy = gx[1] - gx[4], dz = gx[2] - gx[5];
+          const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          dist = sqrtf(fmaxf(d2, 1e-8f)) + 1e-8f;
+          xd[0] = dx / dist;
+          xd[1] = dy / dist;
+          xd[2] = dz / dist;
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            w[4 * i] = __float_as_uint(r8[4 * h2 + i].x);
+            w[4 * i + 1] = __float_as_uint(r8[4 * h2 + i].y);
+            w[4 * i + 2] = __float_as_uint(r8[4 * h2 + i].z);
+            w[4 * i + 3] = __float_as_uint(r8[4 * h2 + i].w);
+          }
+          tc::tmem_st16(Q + 64 * hh + 32 * c + 16 * h2, w);
+        }
+      }
+    } else
     {
       // Two rounds of 8 row loads (32 registers each) instead of 16 at once: the second round is issued right after the
       // first one's staging stores and flies under its fp16 split.  With all 16 loads in flight the 64 data registers did
@@ -707,7 +790,9 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       s_xch[et * 2 + hh] = make_float4(pm, pv[0], pv[1], pv[2]);
     }
     trace_ev<TRACE>(trace, T, tn, 0x03);
-    slot_barrier(T);  // transposes done (the staging writes below overlap other warps' buffers); exchange visible
+    // transposes done (the staging writes below overlap other warps' buffers); exchange visible.  The seeded kernel has
+    // neither: its first staging write comes after the tile-start barrier, which orders it behind the previous tile's mean.
+    if constexpr (!SEED) slot_barrier(T);
     if constexpr (HAS_V) {
       const float4 o = s_xch[et * 2 + (1 - hh)];
       const float4 m = s_xch[et * 2 + hh];
@@ -734,9 +819,13 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         if (g == 1) {
           if (et < pf_rows && pf_rows <= kRows) nx_src = __ldg(p.col + pf_e0 + et);
         } else if (g == 2 && nx_src >= 0) {
-          const char* hrow = reinterpret_cast<const char*>(p.src_h + (size_t)nx_src * kHidden) + 256 * hh;
-          tc::prefetch_l2(hrow);
-          tc::prefetch_l2(hrow + 128);
+          if constexpr (SEED) {
+            nx_srow = __ldg(p.seed_row + nx_src);
+          } else {
+            const char* hrow = reinterpret_cast<const char*>(p.src_h + (size_t)nx_src * kHidden) + 256 * hh;
+            tc::prefetch_l2(hrow);
+            tc::prefetch_l2(hrow + 128);
+          }
           if (hh == 0) {
             tc::prefetch_l2(p.src_x + (size_t)nx_src * 3);
           } else if constexpr (HAS_V) {
@@ -862,14 +951,11 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
               hi[i + 1] = tc::silu_h2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
                                       *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2));
             } else {
-              const uint32_t a4[4] = {r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3]};
-              float f4[4];
-              tc::silu_split4(a4, *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
-                              *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f4, hi[i], hi[i + 1], lo[i], lo[i + 1]);
-              fv[2 * i] = f4[0];
-              fv[2 * i + 1] = f4[1];
-              fv[2 * i + 2] = f4[2];
-              fv[2 * i + 3] = f4[3];
+              tc::silu_pre_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                                  fv[2 * i], fv[2 * i + 1], hi[i], lo[i]);
+              tc::silu_pre_split2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
+                                  *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), fv[2 * i + 2], fv[2 * i + 3],
+                                  hi[i + 1], lo[i + 1]);
             }
           }
           if (g == 2) {
@@ -1001,7 +1087,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
   }
 }
 
-template <bool HAS_V, bool FAST, bool TRACE>
+template <bool HAS_V, bool FAST, bool TRACE, bool SEED = false>
 __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -1046,11 +1132,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) edge_conv_tc_kernel(const Param
   const uint32_t tmem = *s_tmem;
 
   if (warp < 16) {
-    epilogue_role<HAS_V, FAST, TRACE>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+    epilogue_role<HAS_V, FAST, TRACE, SEED>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
-    mma_role<0, HAS_V, FAST, TRACE>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
+    mma_role<SEED ? 2 : 0, HAS_V, FAST, TRACE>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
-    if (lane == 0) producer_role<0>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
+    if (lane == 0) producer_role<SEED ? 2 : 0>(p.wblob, smem, bar_full, bar_empty, bar_small, my_tiles);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1102,6 +1188,16 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
   uint32_t par_vecD = 0, par_D = 0, par_gate = 0;
   if (T < my_tiles) tc::mbar_wait(bar_small, 0);
   if (T == 1 && T < my_tiles) tc::mbar_wait(bar_stagger, 0);
+  if (PF_K4_CTA_STAGGER_NS > 0 && (blockIdx.x & 1) && T < my_tiles) {
+    // de-phase the grid: all CTAs have identical work, so without this every SM is in its load phase, its GVP chain and
+    // its store phase at the same time and DRAM alternates between a burst and idling
+    long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(1000);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < PF_K4_CTA_STAGGER_NS);
+  }
   float* tb = reinterpret_cast<float*>(stage + wslot * 4608);  // private to the warp: [32][36]
   const int prow = lane >> 3, piece = lane & 7;                 // cooperative layout: 8 lanes x 16 B per row chunk
   long long* trace = TRACE && stid == 0 ? p.trace : nullptr;
@@ -1359,10 +1455,11 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
               hi[i + 1] = tc::silu_h2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
                                       *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2));
             } else {
-              const uint32_t a4[4] = {r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3]};
-              float f4[4];
-              tc::silu_split4(a4, *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
-                              *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f4, hi[i], hi[i + 1], lo[i], lo[i + 1]);
+              float f0, f1;
+              tc::silu_pre_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                                  f0, f1, hi[i], lo[i]);
+              tc::silu_pre_split2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
+                                  *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f0, f1, hi[i + 1], lo[i + 1]);
             }
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
@@ -1609,9 +1706,12 @@ extern "C" int pf_tc_trace(long long* device_buf) {  // (4 * 4096 + 148) * 2 int
 static int launch_edge_conv_tc(bool fast, const float* src_h, const float* src_v, const float* src_x, const float* dst_x,
                                const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
                                const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
-                               const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream) {
-  PF_CHECK_ARG(src_h && src_x && dst_x && seg_start && seg_cnt && col && tiles && n_tiles && wblob && agg_h && agg_v,
+                               const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream,
+                               const int32_t* seed_row = nullptr, const float* seed = nullptr) {
+  const bool seeded = seed_row != nullptr;
+  PF_CHECK_ARG((src_h || seeded) && src_x && dst_x && seg_start && seg_cnt && col && tiles && n_tiles && wblob && agg_h && agg_v,
                "pf_edge_conv_tc: null pointer");
+  PF_CHECK_ARG(!seeded || (seed != nullptr && src_v == nullptr), "pf_edge_conv_tc_seeded: needs the seed table and no source vectors");
   PF_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 15) == 0, "pf_edge_conv_tc: weight blob must be 16-byte aligned");
   if (max_tiles <= 0) return PF_OK;
   using KernelFn = void (*)(tcc::Params);
@@ -1620,22 +1720,28 @@ static int launch_edge_conv_tc(bool fast, const float* src_h, const float* src_v
       tcc::edge_conv_tc_kernel<false, true, false>,  tcc::edge_conv_tc_kernel<true, true, false>,
       tcc::edge_conv_tc_kernel<false, false, true>,  tcc::edge_conv_tc_kernel<true, false, true>,
       tcc::edge_conv_tc_kernel<false, true, true>,   tcc::edge_conv_tc_kernel<true, true, true>};
-  static bool configured = false;
-  if (!configured) {
-    for (KernelFn f : fns) {
+  static const KernelFn seeded_fns[4] = {  // index = FAST + 2 TRACE (no source vectors)
+      tcc::edge_conv_tc_kernel<false, false, false, true>, tcc::edge_conv_tc_kernel<false, true, false, true>,
+      tcc::edge_conv_tc_kernel<false, false, true, true>,  tcc::edge_conv_tc_kernel<false, true, true, true>};
+  static PerDeviceFlag configured = {};
+  const int dev_ = current_device();
+  if (!configured.done[dev_]) {
+    for (int i = 0; i < 12; ++i) {
+      const KernelFn f = i < 8 ? fns[i] : seeded_fns[i - 8];
       const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tcc::kSmemBytes);
       if (e != cudaSuccess) {
         set_error("pf_edge_conv_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
         return PF_ERR_LAUNCH;
       }
     }
-    configured = true;
+    configured.done[dev_] = true;
   }
   tcc::Params p{src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
-                static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate, g_tc_trace};
-  const int grid = max_tiles < kNumSms ? max_tiles : kNumSms;
+                static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate, g_tc_trace, seed_row, seed};
+  const int grid = max_tiles < num_sms() ? max_tiles : num_sms();
   const int which = (src_v != nullptr ? 1 : 0) + (fast ? 2 : 0) + (g_tc_trace != nullptr ? 4 : 0);
-  fns[which]<<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  const KernelFn fn = seeded ? seeded_fns[(fast ? 1 : 0) + (g_tc_trace != nullptr ? 2 : 0)] : fns[which];
+  fn<<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_edge_conv_tc");
   return PF_OK;
 }
@@ -1658,6 +1764,83 @@ extern "C" int pf_edge_conv_tc_f16(const float* src_h, const float* src_v, const
                              max_tiles, wblob, agg_h, agg_v, accumulate, stream);
 }
 
+// ---- first conv layer, one-hot source features (SURVEY.md hard part 2: W [h_src; rbf; sh] = W_h h_src per NODE + the per-edge
+// rest).  pf_seed_table computes table[r] = k Wf0[:, 0:128] h[rep[r]] for every distinct source row r (one per (graph,
+// atom type): the encoder output of a one-hot row depends on nothing else), fp32 FFMA; pf_edge_conv_tc_seeded initialises
+// GVP 0's accumulator with row seed_row[src] and runs only the per-edge K-steps (rbf, sh) of that contraction.
+namespace pf {
+namespace tcc {
+constexpr int kSeedRowsPerBlock = 8;
+__global__ void __launch_bounds__(128) seed_table_kernel(const float* __restrict__ h, const int* __restrict__ rep, int n_rows,
+                                                         const float* __restrict__ wfT, float scale, float* __restrict__ table) {
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;                      // [128 (j)][128 (n)]: Wf0^T rows 0 .. 127 (the h part), as packed for the FFMA kernels
+  float* hs = sm + kHidden * kHidden;  // [kSeedRowsPerBlock][128]
+  const int n = threadIdx.x;
+  for (int i = n; i < kHidden * kHidden / 4; i += 128)
+    reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wfT) + i);
+  for (int r0 = blockIdx.x * kSeedRowsPerBlock; r0 < n_rows; r0 += gridDim.x * kSeedRowsPerBlock) {
+    __syncthreads();
+    int node[kSeedRowsPerBlock];
+#pragma unroll
+    for (int r = 0; r < kSeedRowsPerBlock; ++r) {
+      node[r] = r0 + r < n_rows ? __ldg(rep + r0 + r) : -1;
+      hs[r * kHidden + n] = node[r] >= 0 ? __ldg(h + (size_t)node[r] * kHidden + n) : 0.f;
+    }
+    __syncthreads();
+    float acc[kSeedRowsPerBlock];
+#pragma unroll
+    for (int r = 0; r < kSeedRowsPerBlock; ++r) acc[r] = 0.f;
+    for (int j = 0; j < kHidden; j += 4) {
+      const float w0 = ws[(j + 0) * kHidden + n], w1 = ws[(j + 1) * kHidden + n];
+      const float w2 = ws[(j + 2) * kHidden + n], w3 = ws[(j + 3) * kHidden + n];
+#pragma unroll
+      for (int r = 0; r < kSeedRowsPerBlock; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(hs + r * kHidden + j);
+        acc[r] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[r]))));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kSeedRowsPerBlock; ++r)
+      if (node[r] >= 0) table[(size_t)(r0 + r) * kHidden + n] = acc[r] * scale;
+  }
+}
+}  // namespace tcc
+}  // namespace pf
+
+extern "C" int pf_seed_table(const float* h, const int32_t* rep_node, int32_t n_rows, const float* w_msg, float* table,
+                             void* stream) {
+  PF_CHECK_ARG(h && rep_node && w_msg && table, "pf_seed_table: null pointer");
+  if (n_rows <= 0) return PF_OK;
+  const size_t smem = (size_t)(kHidden * kHidden + tcc::kSeedRowsPerBlock * kHidden) * sizeof(float);
+  static PerDeviceFlag configured = {};
+  const int dev_ = current_device();
+  if (!configured.done[dev_]) {
+    const cudaError_t e = cudaFuncSetAttribute(tcc::seed_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("pf_seed_table: cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+      return PF_ERR_LAUNCH;
+    }
+    configured.done[dev_] = true;
+  }
+  const GvpLayout L = gvp_layout(17, 16, 144, 128);  // GVP 0 of a message chain (pharmacoforge_b200.h: packed GVP sections)
+  const int blocks = (n_rows + tcc::kSeedRowsPerBlock - 1) / tcc::kSeedRowsPerBlock;
+  const int grid = blocks < 2 * num_sms() ? blocks : 2 * num_sms();
+  tcc::seed_table_kernel<<<grid, 128, smem, as_stream(stream)>>>(h, rep_node, n_rows, w_msg + L.wf, -1.4426950408889634f, table);
+  PF_CHECK_LAUNCH("pf_seed_table");
+  return PF_OK;
+}
+
+extern "C" int pf_edge_conv_tc_seeded(const int32_t* seed_row, const float* seed_table, const float* src_x, const float* dst_x,
+                                      const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
+                                      const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
+                                      const void* wblob, float* agg_h, float* agg_v, int32_t accumulate,
+                                      int32_t fp16_single_pass, void* stream) {
+  PF_CHECK_ARG(seed_row && seed_table, "pf_edge_conv_tc_seeded: null seed");
+  return launch_edge_conv_tc(fp16_single_pass != 0, nullptr, nullptr, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles,
+                             n_tiles, max_tiles, wblob, agg_h, agg_v, accumulate, stream, seed_row, seed_table);
+}
+
 static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
                                  int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream) {
   PF_CHECK_ARG(h_in && agg_h && agg_v && wblob && h_out && v_out, "pf_node_update_tc: null pointer");
@@ -1669,8 +1852,9 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
       tcc::node_update_tc_kernel<false, true, false>,  tcc::node_update_tc_kernel<true, true, false>,
       tcc::node_update_tc_kernel<false, false, true>,  tcc::node_update_tc_kernel<true, false, true>,
       tcc::node_update_tc_kernel<false, true, true>,   tcc::node_update_tc_kernel<true, true, true>};
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured = {};
+  const int dev_ = current_device();
+  if (!configured.done[dev_]) {
     for (KernelFn f : fns) {
       const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tcc::kSmemBytes);
       if (e != cudaSuccess) {
@@ -1678,12 +1862,12 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
         return PF_ERR_LAUNCH;
       }
     }
-    configured = true;
+    configured.done[dev_] = true;
   }
   tcc::NodeParams p{h_in, v_in, agg_h, agg_v, (long long)n_nodes, static_cast<const uint8_t*>(wblob), h_out, v_out,
                     g_tc_trace};
   const long long tiles = (n_nodes + tcc::kRows - 1) / tcc::kRows;
-  const int grid = (int)(tiles < kNumSms ? tiles : kNumSms);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   const int which = (v_in != nullptr ? 1 : 0) + (fast ? 2 : 0) + (g_tc_trace != nullptr ? 4 : 0);
   fns[which]<<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_node_update_tc");

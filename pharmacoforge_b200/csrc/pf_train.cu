@@ -614,7 +614,7 @@ static int sgemm_ld(const float* A, const float* B, const float* bias, float* C,
 // rows ran on 64 CTAs), at least 512 rows per split.
 static int wgrad_splits(long long rows, int m, int n) {
   const long long tiles = (long long)((m + 63) / 64) * ((n + 63) / 64);
-  long long cap = (4 * kNumSms + tiles - 1) / tiles;
+  long long cap = (4 * num_sms() + tiles - 1) / tiles;
   if (cap < 1) cap = 1;
   const long long by_rows = rows / 512;
   const long long sp = by_rows < cap ? by_rows : cap;

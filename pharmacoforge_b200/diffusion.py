@@ -17,19 +17,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .batch import GraphBatch, Pocket
+from .batch import GraphBatch, Pocket, on_batch_device
 from .dynamics import PharmRecDynamicsGVP
-
-
-def polynomial_gamma(timesteps: int, precision: float, power: float) -> torch.Tensor:
-    """gamma_t = -(log alpha_t^2 - log sigma_t^2) of the clipped polynomial schedule, float64 on the host then
-    float32, as the reference builds it once at construction (pharmacodiff.py:602-664)."""
-    steps = timesteps + 1
-    x = np.linspace(0, steps, steps)
-    a2 = (1.0 - np.power(x / steps, power)) ** 2
-    step = np.clip(np.concatenate([np.ones(1), a2])[1:] / np.concatenate([np.ones(1), a2])[:-1], 0.001, 1.0)
-    a2 = (1.0 - 2.0 * precision) * np.cumprod(step) + precision
-    return torch.from_numpy(-(np.log(a2) - np.log(1.0 - a2))).float()
+from .hostutil import polynomial_gamma  # noqa: F401  (re-exported: the schedule is host-only code)
 
 
 class PredefinedNoiseSchedule(nn.Module):
@@ -120,6 +110,7 @@ class PharmacophoreDiff(nn.Module):
         self.sample_interval, self.val_loss_interval = sample_interval, val_loss_interval
         self.pharms_per_pocket, self.n_pockets_to_sample = pharms_per_pocket, n_pockets_to_sample
         self.graph_cutoffs = graph_config.get("graph_cutoffs", {})
+        self._tables = None
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -174,7 +165,8 @@ class PharmacophoreDiff(nn.Module):
     def step_tables(self):
         """Per-step host tables for the sampling loop, in loop order (s = T-1 .. 0): t value and the three
         posterior coefficients of sample_p_zs_given_zt (pharmacodiff.py:387-400), computed with the same fp32
-        torch ops on the host so the coefficients are bit-identical to the reference's."""
+        torch ops on the host: bit-identical to the reference run on the CPU (the CPU oracle); a reference run on a
+        CUDA device evaluates softplus / expm1 / logsigmoid with the device's libm and may differ in the last bit."""
         T = self.n_timesteps
         s = torch.arange(T - 1, -1, -1)
         s_arr, t_arr = s.float() / T, (s + 1).float() / T
@@ -188,6 +180,7 @@ class PharmacophoreDiff(nn.Module):
 
     # ------------------------------------------------------------------ sampling
     @torch.no_grad()
+    @on_batch_device
     def sample_given_receptor(self, g: GraphBatch, init_pharm_com: Optional[torch.Tensor] = None,
                               visualize_trajectory: bool = False, noise: Optional[torch.Tensor] = None,
                               n_steps: Optional[int] = None, return_tensors: bool = False):
@@ -216,10 +209,7 @@ class PharmacophoreDiff(nn.Module):
         ops.segment_shift3(g.prot_x, g.prot_ptr, init_pharm_com, -1.0)
         g.pharm_x.copy_(nx[0])
         g.pharm_h.copy_(nhh[0])
-        t_host, alpha_ts, var_terms, sigma_q = self.step_tables()
-        a = st.args
-        a.t_host, a.alpha_ts_host = t_host.ctypes.data, alpha_ts.ctypes.data
-        a.var_terms_host, a.sigma_q_host = var_terms.ctypes.data, sigma_q.ctypes.data
+        self._tables = self.step_tables()   # once per call; kept alive while C reads them
         frames = None
         if visualize_trajectory:
             # device-side trajectory buffer instead of a graph copy + D2H per step (pharmacodiff.py:360-378)
@@ -239,12 +229,15 @@ class PharmacophoreDiff(nn.Module):
         ops.segment_shift3(g.prot_x, g.prot_ptr, init_prot_com, 1.0)
         h0 = g.pharm_h * self.pharm_feat_norm_constant
         g.check_status()
+        self._tables = None   # read on the host while the steps were enqueued; never cached across calls
         if return_tensors:
             return x0, h0
         x0_h, h0_h = x0.cpu(), h0.cpu()
         fr = None
         if frames is not None:
-            fr = (frames[0].cpu(), (frames[1] * self.pharm_feat_norm_constant).cpu())
+            # frames carry x_t moved back to the input frame and h_t as is: the reference's get_pos_feat_for_visual
+            # un-normalises h_0 only (pharmacodiff.py:84-86, 360-378), never the h_t it records
+            fr = (frames[0].cpu(), frames[1].cpu())
         ptr = g.pharm_ptr_host
         out = []
         for b in range(g.n_graphs):
@@ -257,8 +250,9 @@ class PharmacophoreDiff(nn.Module):
         a = st.args
         T = self.n_timesteps
         off = first  # tables are in loop order; the same offset applies to every table
-        t_host, alpha_ts, var_terms, sigma_q = self.step_tables()
-        self._tables = (t_host, alpha_ts, var_terms, sigma_q)  # keep alive while C reads them
+        if getattr(self, "_tables", None) is None:      # direct callers (tests) that did not go through the sampler
+            self._tables = self.step_tables()
+        t_host, alpha_ts, var_terms, sigma_q = self._tables
         a.t_host = t_host[off:].ctypes.data
         a.alpha_ts_host = alpha_ts[off:].ctypes.data
         a.var_terms_host = var_terms[off:].ctypes.data
@@ -296,6 +290,7 @@ class PharmacophoreDiff(nn.Module):
             end += len(szs)
         return out
 
+    @on_batch_device
     def forward(self, g: GraphBatch, phase: str = "train", t_int: Optional[torch.Tensor] = None,
                 eps: Optional[Dict[str, torch.Tensor]] = None):
         """The training / validation objective of pharmacodiff.py:162-243 (eps parameterisation): returns
@@ -321,6 +316,10 @@ class PharmacophoreDiff(nn.Module):
                 eps = {"h": torch.randn(g.n_pharm, self.n_pharm_feats, device=dev),
                        "x": torch.randn(g.n_pharm, 3, device=dev)}
             eps_x, eps_h = eps["x"].to(dev).float(), eps["h"].to(dev).float()
+            # The reference shifts pharm x_0 and prot x_0 together and in place; here the ground truth stays untouched
+            # in g.pharm_x0, so the protein must start from its input frame too -- otherwise a second forward() on the
+            # same batch (cached validation batches, several epochs) would subtract the pharmacophore COM twice.
+            g.prot_x.copy_(g.prot_x0)
             h0 = g.pharm_h0 / self.pharm_feat_norm_constant                   # normalize, :81-83
             x0 = g.pharm_x0.clone()
             com0 = ops.segment_mean3(x0, g.pharm_ptr)                          # com_removal(pharm_feat='x_0'), :178
@@ -343,7 +342,11 @@ class PharmacophoreDiff(nn.Module):
             h_dyn, x_dyn = train_graph.dynamics_forward(self.dynamics, g, t, training=True)
         else:
             with torch.no_grad():
-                h_dyn, x_dyn = self.dynamics(g, t)
+                self.dynamics.check_status_every_call = False
+                try:
+                    h_dyn, x_dyn = self.dynamics(g, t)
+                finally:
+                    self.dynamics.check_status_every_call = True
         g.check_status()
         h_loss = (eps_h - h_dyn).square().sum(dim=1)
         x_loss = (eps_x - x_dyn).square().sum(dim=1)

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .batch import GraphBatch
+from .batch import GraphBatch, on_batch_device
 from .weights import PackedWeights
 
 ALL_EDGES = [("pharm", "ff", "pharm"), ("prot", "pf", "pharm"), ("pharm", "fp", "prot"), ("prot", "pp", "prot")]
@@ -154,6 +154,15 @@ class _DeviceState:
             for n in range(2):
                 a.w_upd[l][n] = w.ptr(f"upd{l}_{n}")
         a.tile_rows = g.tile_rows
+        # first-layer seeding (one-hot protein features only): static row / representative tables, per-call scratch
+        self.seed = None
+        if g.tile_rows == 128 and g.n_prot > 0 and g.n_pp_edges > 0:
+            self.seed = g.seed_arrays()
+        if self.seed is not None:
+            seed_row, seed_rep = self.seed
+            self.seed_table = torch.zeros(seed_rep.numel(), 128, **f32)
+            a.seed_row, a.seed_rep, a.seed_table = seed_row.data_ptr(), seed_rep.data_ptr(), self.seed_table.data_ptr()
+            a.n_seed_rows = seed_rep.numel()
         if g.tile_rows == 128:
             if w.tc is None:
                 raise NotImplementedError("the tcgen05 message kernel is built for n_message_gvps=3 (configs/dev.yml); "
@@ -209,6 +218,13 @@ class PharmRecDynamicsGVP(nn.Module):
         # 1e-4 parity bar) or "fp16" (PF_FLAG_FP16_SINGLE_PASS: one pass over 11-bit operands, SiLU on packed fp16
         # pairs -- the reduced-precision path of BASELINE.json configs[3], tolerance stated in the tests).
         self.edge_mlp_precision = "fp32"
+        # First conv layer, pp edges: the per-node part of GVP 0's scalar contraction (Wf0[:, :128] h_src) comes from a
+        # (graph, atom type) table instead of a per-edge gather + contraction (SURVEY.md hard part 2's exact split; needs
+        # one-hot protein features, checked per batch).  False = the general kernel, the A/B switch of the parity tests.
+        self.layer0_seed = True
+        # Direct callers of forward() get the device status word checked on every call (one 4-byte D2H sync);
+        # PharmacophoreDiff's own loops check once at their end and switch this off around their calls.
+        self.check_status_every_call = True
         self._packed: Optional[PackedWeights] = None
         self._packed_key = None
 
@@ -233,10 +249,12 @@ class PharmRecDynamicsGVP(nn.Module):
         if self.edge_mlp_precision not in ("fp32", "fp16"):
             raise ValueError("edge_mlp_precision must be 'fp32' or 'fp16'")
         st.args.flags = ((1 if self.skip_dead_work else 0) |               # PF_FLAG_SKIP_DEAD_WORK
-                         (2 if self.edge_mlp_precision == "fp16" else 0))   # PF_FLAG_FP16_SINGLE_PASS
+                         (2 if self.edge_mlp_precision == "fp16" else 0) |  # PF_FLAG_FP16_SINGLE_PASS
+                         (0 if self.layer0_seed else 4))                    # PF_FLAG_NO_LAYER0_SEED
         return st
 
     # ------------------------------------------------------------------ forward
+    @on_batch_device
     def forward(self, g: GraphBatch, timestep: torch.Tensor, batch_idxs=None):
         if self.training and self.noise_predictor.conv_layers[0].dropout.feat_dropout.p > 0:
             raise NotImplementedError("the fused kernels implement eval-mode semantics (no dropout, no autograd graph): call "
@@ -244,4 +262,6 @@ class PharmRecDynamicsGVP(nn.Module):
         st = self.bind(g)
         st.t_graph.copy_(timestep.to(device=g.device, dtype=torch.float32).reshape(-1))
         ops.denoiser(st.eps_h, st.eps_x, st.addr)
+        if self.check_status_every_call:
+            g.check_status()   # device-detected conditions (degree / tile / edge overflow) must not pass silently
         return st.eps_h, st.eps_x

@@ -4,7 +4,8 @@ BioPython, RDKit or DGL:
   * `pocket_from_pdb`: the pocket extraction of generate_pharmacophores.py:120-220 (`process_ligand_and_pocket`): the
     standard-amino-acid residues with an atom within `pocket_cutoff` of the reference ligand (or an explicit
     `chain:resnum` list), heavy atoms only, element one-hot over `prot_elements` with the 'other' column dropped and
-    those atoms removed.  PDB ATOM records and V2000 SDF coordinates are parsed by hand.
+    those atoms removed.  PDB / mmCIF atom records (alternate locations resolved by occupancy, hetero residues kept
+    under their own residue ids, as Bio.PDB does) and V2000 SDF coordinates are parsed by hand.
   * `ProteinPharmacophoreDataset`: the processed CrossDocked tensors (`prot_pharm_tensors.npz`,
     protein_pharm_dataset.py:18-207) as (Pocket, pharmacophore x_0 / h_0, receptor pharmacophores) items, with the
     reference's pharmacophore subsampling, plus `collate` to a training `GraphBatch`.
@@ -32,19 +33,88 @@ def element_fixer(element: str) -> str:
 
 
 def read_pdb_atoms(path) -> List[dict]:
-    """ATOM records of the first model: chain, resseq, icode, resname, atom name, element, xyz."""
-    atoms = []
+    """ATOM / HETATM records of every model, as Bio.PDB.PDBParser presents them (generate_pharmacophores.py:128-135):
+    chain, residue id (hetero flag, resseq, icode), resname, atom name, element, xyz, model index.  Alternate
+    locations collapse to ONE atom per (residue, atom name): the location with the highest occupancy, the first one on
+    ties -- BioPython's DisorderedAtom selection -- at the position of its first record."""
+    atoms: List[dict] = []
+    slot: Dict[tuple, int] = {}
+    model = 0
     for line in Path(path).read_text().splitlines():
         rec = line[:6]
         if rec.startswith("ENDMDL"):
-            break
+            model += 1
+            continue
         if rec not in ("ATOM  ", "HETATM"):
             continue
         name = line[12:16].strip()
+        resname = line[17:20].strip()
         element = line[76:78].strip() if len(line) >= 78 and line[76:78].strip() else "".join(c for c in name if c.isalpha())[:1]
-        atoms.append(dict(het=rec == "HETATM", name=name, altloc=line[16], resname=line[17:20].strip(), chain=line[21],
-                          resseq=int(line[22:26]), icode=line[26], element=element_fixer(element.upper()),
-                          xyz=(float(line[30:38]), float(line[38:46]), float(line[46:54]))))
+        het = " " if rec == "ATOM  " else ("W" if resname in ("HOH", "WAT") else "H_" + resname)
+        try:
+            occ = float(line[54:60])
+        except ValueError:
+            occ = 1.0
+        a = dict(het=het, name=name, altloc=line[16], resname=resname, chain=line[21], resseq=int(line[22:26]),
+                 icode=line[26], element=element_fixer(element.upper()), occupancy=occ, model=model,
+                 xyz=(float(line[30:38]), float(line[38:46]), float(line[46:54])))
+        key = (model, a["chain"], het, a["resseq"], a["icode"], name)
+        if key in slot:
+            if a["altloc"] != " " and occ > atoms[slot[key]]["occupancy"]:
+                atoms[slot[key]] = a
+            continue
+        slot[key] = len(atoms)
+        atoms.append(a)
+    return atoms
+
+
+def read_mmcif_atoms(path) -> List[dict]:
+    """The `_atom_site` loop of an mmCIF file (generate_pharmacophores.py:130-131 uses Bio.PDB.MMCIFParser): same records as
+    `read_pdb_atoms`, author chain / residue numbering, alternate locations resolved the same way."""
+    lines = Path(path).read_text().splitlines()
+    cols: List[str] = []
+    rows: List[List[str]] = []
+    i = 0
+    while i < len(lines):
+        if lines[i].strip() == "loop_" and i + 1 < len(lines) and lines[i + 1].strip().startswith("_atom_site."):
+            i += 1
+            while i < len(lines) and lines[i].strip().startswith("_atom_site."):
+                cols.append(lines[i].strip().split(".", 1)[1])
+                i += 1
+            while i < len(lines) and lines[i].strip() and not lines[i].startswith(("#", "loop_", "_")):
+                rows.append(lines[i].split())
+                i += 1
+            break
+        i += 1
+    if not cols:
+        raise ValueError(f"no _atom_site loop in {path}")
+    c = {k: j for j, k in enumerate(cols)}
+    get = lambda r, k, d="": r[c[k]].strip('"\'') if k in c else d
+    atoms: List[dict] = []
+    slot: Dict[tuple, int] = {}
+    models: Dict[str, int] = {}
+    for r in rows:
+        model = models.setdefault(get(r, "pdbx_PDB_model_num", "1"), len(models))
+        resname = get(r, "auth_comp_id") or get(r, "label_comp_id")
+        name = get(r, "auth_atom_id") or get(r, "label_atom_id")
+        chain = get(r, "auth_asym_id") or get(r, "label_asym_id")
+        resseq = int(get(r, "auth_seq_id") or get(r, "label_seq_id"))
+        icode = get(r, "pdbx_PDB_ins_code", "?")
+        icode = " " if icode in ("?", ".") else icode
+        alt = get(r, "label_alt_id", ".")
+        alt = " " if alt in ("?", ".") else alt
+        het = " " if get(r, "group_PDB", "ATOM") == "ATOM" else ("W" if resname in ("HOH", "WAT") else "H_" + resname)
+        occ = float(get(r, "occupancy", "1.0"))
+        a = dict(het=het, name=name, altloc=alt, resname=resname, chain=chain, resseq=resseq, icode=icode,
+                 element=element_fixer(get(r, "type_symbol").upper()), occupancy=occ, model=model,
+                 xyz=(float(get(r, "Cartn_x")), float(get(r, "Cartn_y")), float(get(r, "Cartn_z"))))
+        key = (model, chain, het, resseq, icode, name)
+        if key in slot:
+            if alt != " " and occ > atoms[slot[key]]["occupancy"]:
+                atoms[slot[key]] = a
+            continue
+        slot[key] = len(atoms)
+        atoms.append(a)
     return atoms
 
 
@@ -77,11 +147,20 @@ def pocket_from_pdb(rec_file, prot_elements: Sequence[str], pocket_cutoff: float
     ['A:101', ...]; init_com is the ligand COM (or the COM of the listed residues' atoms)."""
     if lig_file is None and lig_coords is None and len(residue_list) == 0:
         raise ValueError("Either reference ligand or pocket residue list must be provided.")
-    atoms = [a for a in read_pdb_atoms(rec_file) if not a["het"] and a["altloc"] in (" ", "A")]
+    suffix = Path(rec_file).suffix
+    if suffix == ".pdb":
+        atoms = read_pdb_atoms(rec_file)
+    elif suffix == ".mmcif":
+        atoms = read_mmcif_atoms(rec_file)
+    else:
+        raise ValueError(f"unsupported receptor file type: {suffix}, must be .pdb or .mmcif")
+    use_ligand = lig_file is not None or lig_coords is not None
+    if not use_ligand:
+        atoms = [a for a in atoms if a["model"] == 0]   # the residue list indexes rec_struct[0] (:165-166)
     residues: Dict[tuple, List[dict]] = {}
-    for a in atoms:                                   # insertion-ordered, like BioPython's get_residues()
-        residues.setdefault((a["chain"], a["resseq"], a["icode"]), []).append(a)
-    if lig_file is not None or lig_coords is not None:
+    for a in atoms:                                   # insertion-ordered, like BioPython's get_residues() (all models)
+        residues.setdefault((a["model"], a["chain"], a["het"], a["resseq"], a["icode"]), []).append(a)
+    if use_ligand:
         lig = read_sdf_coords(lig_file, remove_hydrogen) if lig_coords is None else np.asarray(lig_coords, dtype=np.float32)
         init_com = torch.from_numpy(lig.mean(axis=0).reshape(1, 3).astype(np.float32))
         chosen = []
@@ -98,7 +177,7 @@ def pocket_from_pdb(rec_file, prot_elements: Sequence[str], pocket_cutoff: float
         chosen = []
         for spec in residue_list:
             chain, num = spec.split(":")
-            key = (chain, int(num), " ")
+            key = (0, chain, " ", int(num), " ")
             if key not in residues:
                 raise KeyError(f"residue {spec} not found in {rec_file}")
             chosen.append(key)

@@ -18,6 +18,11 @@ _L = _lib.load()
 NS = "pharmacoforge"
 
 
+import threading
+
+_call = threading.local()   # devices of the tensors marshalled for the library call being assembled
+
+
 def _p(t: Optional[torch.Tensor], dtype=None):
     if t is None:
         return None
@@ -27,6 +32,10 @@ def _p(t: Optional[torch.Tensor], dtype=None):
         raise _lib.PfError("pharmacoforge ops need contiguous tensors")
     if dtype is not None and t.dtype != dtype:
         raise _lib.PfError(f"expected {dtype}, got {t.dtype}")
+    devs = getattr(_call, "devs", None)
+    if devs is None:
+        devs = _call.devs = set()
+    devs.add(t.device.index)
     return C.c_void_p(t.data_ptr())
 
 
@@ -39,6 +48,18 @@ def _i(t):
 
 
 def _s():
+    """Stream argument of a library call; always the LAST argument, so every tensor of the call has been marshalled.
+    All of them must live on one device and that device must be the current one (the kernels launch on the current
+    device): the public entry points (`GraphBatch.from_pockets`, `PharmRecDynamicsGVP.forward`,
+    `PharmacophoreDiff.sample_given_receptor / forward`) enter `torch.cuda.device(batch.device)` themselves."""
+    devs = getattr(_call, "devs", None) or set()
+    _call.devs = set()
+    cur = torch.cuda.current_device()
+    if len(devs) > 1:
+        raise _lib.PfError(f"pharmacoforge ops need all tensors on one device, got cuda:{sorted(devs)}")
+    if devs and next(iter(devs)) != cur:
+        raise _lib.PfError(f"tensors live on cuda:{next(iter(devs))} but the current device is cuda:{cur}: wrap the "
+                           "call in torch.cuda.device(...)")
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -154,6 +175,26 @@ def edge_conv_tc(src_h: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torc
     _lib.check((_L.pf_edge_conv_tc_f16 if fp16 else _L.pf_edge_conv_tc)(_f(src_h), _f(src_v), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt), _i(seg_dst),
                                   _i(col), _i(tiles), _i(n_tiles), tiles.numel() // 2, _p(wblob), _f(agg_h),
                                   _f(agg_v), int(accumulate), _s()), "pf_edge_conv_tc")
+
+
+@torch.library.custom_op(f"{NS}::seed_table", mutates_args=("table",))
+def seed_table(h: torch.Tensor, rep_node: torch.Tensor, w_msg: torch.Tensor, table: torch.Tensor) -> None:
+    """table[r] = k Wf0[:, 0:128] h[rep_node[r]] (rows with rep_node[r] < 0 untouched); w_msg = fp32 packed message chain."""
+    _lib.check(_L.pf_seed_table(_f(h), _i(rep_node), rep_node.numel(), _f(w_msg), _f(table), _s()), "pf_seed_table")
+
+
+@torch.library.custom_op(f"{NS}::edge_conv_tc_seeded", mutates_args=("agg_h", "agg_v"))
+def edge_conv_tc_seeded(seed_row: torch.Tensor, table: torch.Tensor, src_x: torch.Tensor, dst_x: torch.Tensor,
+                        seg_start: torch.Tensor, seg_cnt: torch.Tensor, seg_dst: Optional[torch.Tensor],
+                        col: torch.Tensor, tiles: torch.Tensor, n_tiles: torch.Tensor, wblob: torch.Tensor,
+                        agg_h: torch.Tensor, agg_v: torch.Tensor, accumulate: bool, fp16: bool = False) -> None:
+    """K3 of the first conv layer with the per-node part of GVP 0 taken from `table` (see pf_seed_table)."""
+    if wblob.dtype != torch.uint8 or wblob.numel() != _L.pf_tc_msg_blob_bytes():
+        raise _lib.PfError("edge_conv_tc_seeded: wblob must be the uint8 image built by weights.pack_message_tc")
+    _lib.check(_L.pf_edge_conv_tc_seeded(_i(seed_row), _f(table), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt),
+                                         _i(seg_dst), _i(col), _i(tiles), _i(n_tiles), tiles.numel() // 2, _p(wblob),
+                                         _f(agg_h), _f(agg_v), int(accumulate), int(fp16), _s()),
+               "pf_edge_conv_tc_seeded")
 
 
 @torch.library.custom_op(f"{NS}::node_update", mutates_args=("h_out", "v_out"))

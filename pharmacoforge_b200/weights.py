@@ -169,6 +169,9 @@ TC_SLABS = (11, 9, 9)
 TC_SMALL_OFF = sum(TC_SLABS) * TC_SLAB_BYTES
 TC_GATE_OFF, TC_VEC_OFF, TC_CONST_OFF, TC_SMALL_BYTES = 0, 24576, 30720, 32768
 TC_C_WH0, TC_C_WHU0, TC_C_WHC16 = 432, 452, 468
+# The tcgen05 images carry Wf and bf multiplied by k = -log2(e): the kernels' SiLU then reads t = k (Wf s + bf)
+# straight from the accumulator, SiLU(y) = t / (k (2^t + 1))  (csrc/pf_tc.cuh: silu_pre2).
+TC_PRESCALE = -1.4426950408889634
 
 
 def _bytes(t: torch.Tensor) -> torch.Tensor:
@@ -199,14 +202,14 @@ def pack_message_tc(sd: Dict[str, torch.Tensor], conv_p: str, etype_key: str) ->
         assert (vi, vh) == ((17, 17) if g == 0 else (16, 16))
         K = 16 * TC_SLABS[g]
         Wp = torch.zeros(128, K)
-        Wp[:, :Wf.shape[1]] = Wf
+        Wp[:, :Wf.shape[1]] = (Wf.double() * TC_PRESCALE).float()
         slabs += [_hi_lo_images(Wp[:, 16 * s:16 * s + 16]) for s in range(TC_SLABS[g])]
         gates += [_hi_lo_images(Wg[:, 16 * s:16 * s + 16]) for s in range(8)]
         Whu = Wh @ Wu                                        # [vi, 16], composed in float64
         k0 = 1 if g == 0 else 0                              # GVP 0: row 0 is the x_diff channel (CUDA cores)
         Bv = torch.cat([Wh[k0:k0 + 16, :16].t(), Whu[k0:k0 + 16, :].t()]).float()   # [32 (n), 16 (k)]
         vecs.append(_hi_lo_images(Bv))
-        consts[144 * g:144 * g + 128] = bf
+        consts[144 * g:144 * g + 128] = (bf.double() * TC_PRESCALE).float()
         consts[144 * g + 128:144 * g + 144] = bg
         if g == 0:
             consts[TC_C_WH0:TC_C_WH0 + 17] = Wh[0, :].float()
@@ -236,10 +239,11 @@ def pack_update_tc(sd: Dict[str, torch.Tensor], conv_p: str, ntype: str) -> torc
         Wf = sd[q + ".to_feats_out.0.weight"].detach().float().cpu()
         Wg = sd[q + ".scalar_to_vector_gates.weight"].detach().float().cpu()
         assert Wh.shape == (16, 16) and Wu.shape == (16, 16) and Wf.shape == (128, 144) and Wg.shape == (16, 128)
-        slabs += [_hi_lo_images(Wf[:, 16 * s:16 * s + 16]) for s in range(9)]
+        Wfs = (Wf.double() * TC_PRESCALE).float()
+        slabs += [_hi_lo_images(Wfs[:, 16 * s:16 * s + 16]) for s in range(9)]
         gates += [_hi_lo_images(Wg[:, 16 * s:16 * s + 16]) for s in range(8)]
         vecs.append(_hi_lo_images(torch.cat([Wh.t(), (Wh @ Wu).t()]).float()))
-        consts[144 * g:144 * g + 128] = sd[q + ".to_feats_out.0.bias"].detach().float().cpu()
+        consts[144 * g:144 * g + 128] = (sd[q + ".to_feats_out.0.bias"].detach().double().cpu() * TC_PRESCALE).float()
         consts[144 * g + 128:144 * g + 144] = sd[q + ".scalar_to_vector_gates.bias"].detach().float().cpu()
     for i, key in enumerate((f"{conv_p}.message_layer_norms.{ntype}.feat_norm.weight",
                              f"{conv_p}.message_layer_norms.{ntype}.feat_norm.bias",

@@ -284,6 +284,98 @@ def test_edge_conv_each_etype(env, etype_idx, with_vectors, impl):
     _edge_conv_case(env, etype_idx, 1 if with_vectors else 0, with_vectors, impl)
 
 
+@pytest.mark.parametrize("fp16", [False, True])
+def test_edge_conv_seeded_first_layer(env, fp16):
+    """pf_seed_table + pf_edge_conv_tc_seeded (first conv layer, one-hot protein features): the per-node part of GVP 0 comes
+    from the (graph, atom type) table.  Checked against the oracle's edge messages computed from the full per-edge input
+    [h_src; rbf; sh] (gvp.py:540-551), and against the general kernel on the same inputs."""
+    O, ops = env.O, env.ops
+    g, b = env.build([(150, 3), (90, 4), (1, 9)], [[3, 5, 8], [6, 4], [2]])
+    x, h, prot = random_state(b, 5)
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    seed_row, seed_rep = g.seed_arrays()
+    # table rows are (graph, type); a graph's atoms of one type share their encoder row: build h that way
+    tt = torch.tensor([0.1, 0.55, 0.9])
+    enc = ops.encode(g.prot_feats, g.prot_ptr, tt.cuda(), env.W.view("prot_enc"))
+    rows = seed_row.long().cpu()
+    assert int(rows.max()) < seed_rep.numel() and torch.equal(enc.cpu()[seed_rep.long().cpu()[rows]], enc.cpu())
+    table = torch.full((seed_rep.numel(), 128), float("nan"), device=env.dev)
+    ops.seed_table(enc, seed_rep, env.W.view("msg0_3"), table)
+    Wf = env.sd["dynamics.noise_predictor.conv_layers.0.edge_message_fns.prot_pp_prot.0.to_feats_out.0.weight"]
+    used = seed_rep.cpu() >= 0
+    want_tab = -1.4426950408889634 * enc.cpu().double()[seed_rep.long().cpu()[used]] @ Wf[:, :128].double().t()
+    close(table.cpu()[used], want_tab, rtol=1e-5, atol=1e-6, what="seed table")
+    assert torch.isnan(table.cpu()[~used]).all()          # rows without a representative are never written
+    src, dst = (v.cpu() for v in g.pp_edges())
+    key = "dynamics.noise_predictor.conv_layers.0.edge_message_fns.prot_pp_prot"
+    zeros = torch.zeros(g.n_prot, 16, 3)
+    ms, mv = O.edge_messages(env.sd, key, enc.cpu()[src], zeros[src], prot[src], prot[dst])
+    want_h, want_v = O.mean_aggregate(ms, dst, g.n_prot), to_cm(O.mean_aggregate(mv, dst, g.n_prot))
+    blob = env.W.tc[3 * env.W.tc_stride:4 * env.W.tc_stride]
+    out = {}
+    for seeded in (True, False):
+        agg_h = torch.full((g.n_prot, 128), float("nan"), device=env.dev)
+        agg_v = torch.full((g.n_prot, 48), float("nan"), device=env.dev)
+        if seeded:
+            ops.edge_conv_tc_seeded(seed_row, table, g.prot_x, g.prot_x, g.pp_start, g.pp_cnt, None, g.pp_col, g.pp_tiles,
+                                    g.pp_n_tiles, blob, agg_h, agg_v, False, fp16)
+        else:
+            ops.edge_conv_tc(enc, None, g.prot_x, g.prot_x, g.pp_start, g.pp_cnt, None, g.pp_col, g.pp_tiles,
+                             g.pp_n_tiles, blob, agg_h, agg_v, False, fp16)
+        torch.cuda.synchronize()
+        g.check_status()
+        out[seeded] = (agg_h.cpu(), agg_v.cpu())
+        if fp16:
+            within(agg_h, want_h, FP16_TOL, what="seeded pp scalars (fp16)")
+            within(agg_v, want_v, FP16_TOL, what="seeded pp vectors (fp16)")
+        else:
+            close(agg_h, want_h, what=f"pp scalars (seeded={seeded})")
+            close(agg_v, want_v, what=f"pp vectors (seeded={seeded})")
+    if not fp16:   # the two kernels agree far inside the parity bar (they differ only in summation order of GVP 0)
+        close(out[True][0], out[False][0], rtol=2e-5, atol=2e-6, what="seeded vs general scalars")
+        close(out[True][1], out[False][1], rtol=2e-5, atol=2e-6, what="seeded vs general vectors")
+
+
+def test_denoiser_layer0_seed_switch(env):
+    """PF_FLAG_NO_LAYER0_SEED: the general first-layer kernel and the seeded one give the same eps (per-graph timesteps);
+    a batch whose protein features are not one-hot falls back to the general kernel by itself."""
+    g, b = env.build([(400, 0), (250, 1)], [[3, 8, 5], [4, 6]])
+    x, h, prot = random_state(b, 17, 4.0)
+    st = env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    assert st.seed is not None and st.args.n_seed_rows == 5 * 11
+    tt = torch.tensor([0.03, 0.5, 0.5, 0.77, 1.0])
+    wh, wx = env.O.denoiser(env.sd, b, tt, env.cfg)
+    dyn = env.model.dynamics
+    res = {}
+    try:
+        for on in (True, False):
+            dyn.layer0_seed = on
+            gh, gx = dyn(g, tt, None)
+            res[on] = (gh.clone(), gx.clone())
+            close(gh, wh, what=f"eps_h (layer0_seed={on})")
+            close(gx, wx, what=f"eps_x (layer0_seed={on})")
+    finally:
+        dyn.layer0_seed = True
+    close(res[True][0], res[False][0], rtol=2e-5, atol=2e-6, what="eps_h seeded vs general")
+    close(res[True][1], res[False][1], rtol=2e-5, atol=2e-6, what="eps_x seeded vs general")
+    # soft (not one-hot) protein features: no seed arrays, general kernel, still correct
+    g2, b2 = env.build([(120, 2)], [[4, 7]])
+    soft = torch.softmax(torch.randn(g2.n_prot, 11, generator=torch.Generator().manual_seed(1)), dim=1)
+    g2.prot_feats.copy_(soft.cuda())
+    b2.prot_h = soft.clone()
+    x, h, prot = random_state(b2, 3)
+    st2 = env.set_state(g2, b2, x.cuda(), h.cuda(), prot.cuda())
+    b2.pharm_x, b2.pharm_h, b2.prot_x = x, h, prot
+    assert st2.seed is None
+    tt2 = torch.tensor([0.3, 0.6])
+    wh, wx = env.O.denoiser(env.sd, b2, tt2, env.cfg)
+    gh, gx = dyn(g2, tt2, None)
+    close(gh, wh, what="eps_h (soft features)")
+    close(gx, wx, what="eps_x (soft features)")
+
+
 @pytest.mark.parametrize("impl", ["tc", "ffma"])
 def test_node_update(env, impl):
     O, ops = env.O, env.ops
@@ -522,9 +614,8 @@ def test_degree_overflow_is_reported(env):
     onehot = np.zeros((80, 11), dtype=np.float32)
     onehot[:, 0] = 1
     from pharmacoforge_b200._lib import PfError
-    g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev, tile_rows=64)
-    with pytest.raises(PfError):     # 79 in-edges do not fit a 64-row tile of the FFMA kernels
-        g.check_status()
+    with pytest.raises(PfError):     # 79 in-edges do not fit a 64-row tile of the FFMA kernels: reported at batch build
+        env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev, tile_rows=64)
     g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(pos, onehot)], [[3]], env.dev, tile_rows=128)
     g.check_status()                 # max_num_neighbors=100 always fits the 128-row tcgen05 tile
 

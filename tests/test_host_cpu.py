@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.pf_abi_version() == 1
+    assert lib.pf_abi_version() == _lib.ABI_VERSION
     assert lib.pf_sample_args_size() == ctypes.sizeof(_lib.PfSampleArgs)
     assert lib.pf_scan_workspace_bytes(5000) >= 4 * 4
 
@@ -154,11 +154,13 @@ def test_tc_message_blob_layout(sd):
             rec[:, 16 * s_:16 * s_ + 16] = hi + lo
             off += 8192
         k = Wf.shape[1]
-        assert torch.allclose(rec[:, :k], Wf, rtol=2 ** -21, atol=1e-7) and float(rec[:, k:].abs().max() if k < rec.shape[1] else 0) == 0
+        # the images carry k * Wf, k = -log2(e): the kernels' SiLU reads t = k (Wf s + bf) from the accumulator
+        assert torch.allclose(rec[:, :k], Wf * W.TC_PRESCALE, rtol=2 ** -20, atol=1e-7)
+        assert float(rec[:, k:].abs().max() if k < rec.shape[1] else 0) == 0
     assert off == W.TC_SMALL_OFF
     consts = blob[W.TC_SMALL_OFF + W.TC_CONST_OFF:].view(torch.float32)
     q = f"{cp}.edge_message_fns.prot_pp_prot"
-    assert torch.equal(consts[144:272], sd[q + ".1.to_feats_out.0.bias"].float())
+    assert torch.equal(consts[144:272], (sd[q + ".1.to_feats_out.0.bias"].double() * W.TC_PRESCALE).float())
     assert torch.equal(consts[W.TC_C_WH0:W.TC_C_WH0 + 17], sd[q + ".0.Wh"][0].float())
     Whu = (sd[q + ".0.Wh"].double() @ sd[q + ".0.Wu"].double()).float()
     assert torch.equal(consts[W.TC_C_WHU0:W.TC_C_WHU0 + 16], Whu[0])
