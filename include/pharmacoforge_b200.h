@@ -85,6 +85,22 @@ int pf_radius_count(const float* x, const int32_t* seg_ptr, int32_t n_seg, float
 int pf_radius_fill(const float* x, const int32_t* seg_ptr, int32_t n_seg, float r, int32_t max_nbrs,
                    const int32_t* rowptr, int32_t* col, void* stream);
 
+/* K1 as a cell list over DISTINCT pockets + replication (the graph is built once per pocket and copied per sample, as
+ * protein_pharm_dataset.py:234-236 + unorganized_utils.py:28-50 + dgl.batch do).  Same edge rule and the same output as
+ * pf_radius_count / pf_radius_fill (bit-identical CSR), O(N) instead of O(N^2 / pocket).  Both calls take the same
+ * workspace of pf_cell_radius_workspace_bytes(n_nodes, n_seg) bytes: count builds the cell lists in it (cell edge
+ * >= r, at most 2 n + 8 cells per pocket), fill reads them.  Rows with more than 160 hits fall back to the ordered scan. */
+size_t pf_cell_radius_workspace_bytes(int64_t n_nodes, int32_t n_seg);
+int pf_cell_radius_count(const float* x, const int32_t* seg_ptr, int32_t n_seg, int64_t n_nodes, float r, int32_t max_nbrs,
+                         void* workspace, size_t workspace_bytes, int32_t* deg, void* stream);
+int pf_cell_radius_fill(const float* x, const int32_t* seg_ptr, int32_t n_seg, int64_t n_nodes, float r, int32_t max_nbrs,
+                        void* workspace, size_t workspace_bytes, const int32_t* rowptr, int32_t* col, void* stream);
+/* Graph g of the batch is a copy of the pocket whose first node is pk_node0[g] in the pocket arrays: its nodes are
+ * [prot_ptr[g], prot_ptr[g+1]), its edges start at edge0[g] (exclusive scan of the copies' edge counts).  Writes
+ * rowptr [N+1], cnt [N], col [E] of the batched graph: 4 B per edge + 8 B per node, coalesced. */
+int pf_replicate_csr(const int32_t* pk_rowptr, const int32_t* pk_col, const int32_t* pk_node0, const int32_t* prot_ptr,
+                     const int32_t* edge0, int32_t n_graphs, int32_t* rowptr, int32_t* cnt, int32_t* col, void* stream);
+
 /* ---- K2: per-step dynamic graph ------------------------------------------------------------------
  * Replaces, per reverse-diffusion step, dynamics_gvp.py:187-246: radius_graph(pharm x_t, r=ff_r,
  * max 200) (:196), knn(prot x_0, pharm x_t, k) (:202) and the six DGL add/remove_edges mutations.
@@ -201,6 +217,16 @@ int pf_posterior_step(float* pharm_x, float* pharm_h, int32_t nh, const float* e
                       const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms, float sigma_q,
                       void* stream);
 
+/* The same step with in-kernel Gaussian noise (SURVEY.md 8d allows Philox for throughput runs; parity runs inject noise):
+ * Philox4x32-10 keyed by the 64-bit *seed_dev (device memory), counter = (element index, noise_step, stream x / h),
+ * Box-Muller.  pf_philox_normal fills out[0..n) with the draws of (stream_id, step) -- the initial z_T uses step 0 with
+ * stream 0 for x and 1 for h (pharmacodiff.py:455-456), loop iteration i uses step i + 1. */
+int pf_posterior_step_philox(float* pharm_x, float* pharm_h, int32_t nh, const float* eps_x, const float* eps_h,
+                             const uint64_t* seed_dev, uint32_t noise_step, const int32_t* pharm_ptr, float* prot_x,
+                             const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms, float sigma_q,
+                             void* stream);
+int pf_philox_normal(float* out, int64_t n, const uint64_t* seed_dev, uint32_t stream_id, uint32_t step, void* stream);
+
 /* per-graph mean of x over [ptr[g], ptr[g+1]) -> com[g][3]; and x[n] += sign * com[graph(n)]
  * (dgl.readout_nodes + broadcast subtract/add, pharmacodiff.py:442-452,483-486) */
 int pf_segment_mean3(const float* x, const int32_t* ptr, int32_t n_graphs, float* com, void* stream);
@@ -265,6 +291,10 @@ typedef struct PfSampleArgs {
   const int32_t* seed_rep;  /* [n_seed_rows] one protein node with that (graph, type), or -1 if the graph has none */
   float* seed_table;        /* [n_seed_rows][128] */
   int32_t n_seed_rows;
+  /* In-kernel noise for throughput runs (noise_x == noise_h == NULL): Philox4x32-10 keyed by *noise_seed (DEVICE memory:
+   * a captured CUDA graph replays with a new seed), loop iteration i draws with step number noise_step0 + i. */
+  const uint64_t* noise_seed;
+  int32_t noise_step0;
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph

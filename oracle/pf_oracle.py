@@ -361,6 +361,56 @@ def sample(sd, b: FlatBatch, noise: torch.Tensor, T: int, gamma: torch.Tensor, c
     return x0, h0, h0.argmax(dim=1), prot
 
 
+def visual_frames(b: FlatBatch, record, init_prot_com: torch.Tensor):
+    """get_pos_feat_for_visual, pharmacodiff.py:360-378, for every recorded state (x_t, h_t, prot x_0): the
+    pharmacophore is moved back to the input frame by init_prot_com - current protein COM; h_t is stored as is
+    (`unnormalize` touches h_0 only, :84-86).  -> (pos [F, Nf, 3], feat [F, Nf, nh])."""
+    pos, feat = [], []
+    for x_t, h_t, prot in record:
+        prot_com = segment_mean(prot, b.prot_b, b.n_graphs)
+        pos.append(x_t + (init_prot_com - prot_com)[b.pharm_b])
+        feat.append(h_t.clone())
+    return torch.stack(pos), torch.stack(feat)
+
+
+def sample_multi(sd, pockets: List[Tuple[torch.Tensor, torch.Tensor]], n_pharms: List[List[int]], noise: torch.Tensor,
+                 T: int, gamma: torch.Tensor, cfg: dict, max_batch_size: int = 32,
+                 init_pharm_com: Optional[torch.Tensor] = None, norm_const: float = 1.0, frames: bool = False,
+                 steps=None):
+    """PharmacophoreDiff.sample, pharmacodiff.py:516-578: one graph per (pocket, requested size), pocket-major; chunks of
+    max_batch_size consecutive graphs go through sample_given_receptor with init_pharm_com indexed by the graph's
+    pocket (default: each pocket's plain mean position, :531-535); results are regrouped per pocket.
+    noise [T+1, Nf_total, 9] is consumed by columns in the flattened graph order.
+    -> list (per pocket) of lists of dicts {x, h, type, pos_frames?, feat_frames?}."""
+    if init_pharm_com is None:
+        init_pharm_com = torch.stack([pos.mean(dim=0) for pos, _ in pockets])
+    flat = [(p, int(n)) for p, szs in enumerate(n_pharms) for n in szs]
+    results, col = [], 0
+    for start in range(0, len(flat), max_batch_size):
+        chunk = flat[start:start + max_batch_size]
+        # a chunk as its own batch: pockets in chunk order, one graph per entry
+        b = build_batch([pockets[p] for p, _ in chunk], [[n] for _, n in chunk], cfg["graph_cutoffs"]["pp"])
+        nf = int(b.pharm_ptr[-1])
+        coms = init_pharm_com[[p for p, _ in chunk]]
+        init_prot_com = segment_mean(b.prot_x, b.prot_b, b.n_graphs)
+        rec = [] if frames else None
+        x0, h0, typ, _ = sample(sd, b, noise[:, col:col + nf], T, gamma, cfg, init_pharm_com=coms,
+                                norm_const=norm_const, record=rec, steps=steps)
+        fr = visual_frames(b, rec, init_prot_com) if frames else None
+        for gi in range(b.n_graphs):
+            sl = slice(int(b.pharm_ptr[gi]), int(b.pharm_ptr[gi + 1]))
+            out = {"x": x0[sl], "h": h0[sl], "type": typ[sl]}
+            if fr is not None:
+                out["pos_frames"], out["feat_frames"] = fr[0][:, sl], fr[1][:, sl]
+            results.append(out)
+        col += nf
+    per_pocket, end = [], 0
+    for szs in n_pharms:
+        per_pocket.append(results[end:end + len(szs)])
+        end += len(szs)
+    return per_pocket
+
+
 def forward_loss(sd, b: FlatBatch, x0: torch.Tensor, h0: torch.Tensor, t_int: torch.Tensor, eps_x: torch.Tensor,
                  eps_h: torch.Tensor, T: int, gamma: torch.Tensor, cfg: dict, norm_const: float = 1.0,
                  weighted_loss: bool = False, phase: str = "train"):

@@ -24,6 +24,12 @@ SIGNATURES = {
     "pf_exclusive_scan_i32": (C.c_int, [c_i32p, c_i32p, C.c_int64, C.c_void_p, C.c_size_t, STREAM]),
     "pf_radius_count": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, c_i32p, STREAM]),
     "pf_radius_fill": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, c_i32p, c_i32p, STREAM]),
+    "pf_cell_radius_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "pf_cell_radius_count": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_int64, C.c_float, C.c_int32, C.c_void_p, C.c_size_t,
+                                       c_i32p, STREAM]),
+    "pf_cell_radius_fill": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_int64, C.c_float, C.c_int32, C.c_void_p, C.c_size_t,
+                                      c_i32p, c_i32p, STREAM]),
+    "pf_replicate_csr": (C.c_int, [c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int32, c_i32p, c_i32p, c_i32p, STREAM]),
     "pf_dyn_graph": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, c_i32p,
                                c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
@@ -50,6 +56,9 @@ SIGNATURES = {
     "pf_noise_head": (C.c_int, [c_f32p, c_f32p, C.c_int64, c_f32p, C.c_int32, C.c_int32, c_f32p, c_f32p, STREAM]),
     "pf_posterior_step": (C.c_int, [c_f32p, c_f32p, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p,
                                     c_i32p, C.c_int32, C.c_float, C.c_float, C.c_float, STREAM]),
+    "pf_posterior_step_philox": (C.c_int, [c_f32p, c_f32p, C.c_int32, c_f32p, c_f32p, C.c_void_p, C.c_uint32, c_i32p,
+                                           c_f32p, c_i32p, C.c_int32, C.c_float, C.c_float, C.c_float, STREAM]),
+    "pf_philox_normal": (C.c_int, [c_f32p, C.c_int64, C.c_void_p, C.c_uint32, C.c_uint32, STREAM]),
     "pf_segment_mean3": (C.c_int, [c_f32p, c_i32p, C.c_int32, c_f32p, STREAM]),
     "pf_segment_shift3": (C.c_int, [c_f32p, c_i32p, C.c_int32, c_f32p, C.c_float, STREAM]),
     "pf_sample_args_size": (C.c_size_t, []),
@@ -119,6 +128,7 @@ class PfSampleArgs(C.Structure):
         ("dev_status", C.c_void_p),
         ("flags", C.c_uint32),
         ("seed_row", C.c_void_p), ("seed_rep", C.c_void_p), ("seed_table", C.c_void_p), ("n_seed_rows", C.c_int32),
+        ("noise_seed", C.c_void_p), ("noise_step0", C.c_int32),
     ]
 
 

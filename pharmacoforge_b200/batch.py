@@ -40,6 +40,12 @@ class Pocket:
                       g.nodes["prot"].data["h_0"].detach().float().cpu().contiguous())
 
 
+    def to_dgl(self, graph_cutoffs: dict):
+        """The reference's pocket graph for this pocket (io.pocket_to_dgl); requires dgl."""
+        from .io import pocket_to_dgl
+        return pocket_to_dgl(self, graph_cutoffs)
+
+
 def _chunk_graphs(weights: np.ndarray, target: int) -> np.ndarray:
     """Group consecutive graphs into planner chunks of roughly `target` edge rows (boundaries in graphs)."""
     bounds = [0]
@@ -126,14 +132,16 @@ class GraphBatch:
         pk_x = torch.cat([pockets[p].prot_x for p in used]).float().contiguous()
         pk_h = torch.cat([pockets[p].prot_h for p in used]).float().contiguous()
         self.n_prot_feats = pk_h.shape[1]
-        meta = torch.from_numpy(np.concatenate([prot_ptr, pharm_ptr, pk_off[graph_pocket].astype(np.int32)]))
+        meta = torch.from_numpy(np.concatenate([prot_ptr, pharm_ptr, pk_off[graph_pocket].astype(np.int32),
+                                                pk_off.astype(np.int32)]))
         self.h2d_bytes = pk_x.numel() * 4 + pk_h.numel() * 4 + meta.numel() * 4
         pk_x = pk_x.pin_memory().to(dev, non_blocking=True)
         pk_h = pk_h.pin_memory().to(dev, non_blocking=True)
         meta = meta.pin_memory().to(dev, non_blocking=True)
         self.prot_ptr = meta[:B + 1].contiguous()
         self.pharm_ptr = meta[B + 1:2 * B + 2].contiguous()
-        g_pk_off = meta[2 * B + 2:].long()
+        g_pk_off = meta[2 * B + 2:3 * B + 2].long()
+        pk_ptr = meta[3 * B + 2:].contiguous()            # node ranges of the distinct pockets
         counts = (self.prot_ptr[1:] - self.prot_ptr[:-1]).long()
         node_graph = torch.repeat_interleave(torch.arange(B, device=dev), counts, output_size=self.n_prot)
         src_row = torch.arange(self.n_prot, device=dev) - self.prot_ptr[:-1].long()[node_graph] + g_pk_off[node_graph]
@@ -144,9 +152,21 @@ class GraphBatch:
         self.pharm_h = None                     # allocated by the sampler (feature width is a model property)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
 
-        # ---- K1: static pp radius graph (protein_pharm_dataset.py:234-236 + per-copy replication)
-        self.pp_rowptr, self.pp_cnt, self.pp_col = ops.radius_csr(self.prot_x, self.prot_ptr, float(pp_cutoff),
-                                                                  int(pp_max_nbrs))
+        # ---- K1: static pp radius graph.  Built ONCE PER DISTINCT POCKET with a cell list, then replicated per graph
+        # with node offsets on the device -- what protein_pharm_dataset.py:234-236 (one radius_graph per pocket) +
+        # copy_graph / dgl.batch (unorganized_utils.py:28-50) do.  PF_K1=brute: the all-pairs kernel over the
+        # replicated batch (same CSR bit for bit; kept as the A/B reference of the tests).
+        if os.environ.get("PF_K1", "cell") == "brute" or B == 0:
+            self.pp_rowptr, self.pp_cnt, self.pp_col = ops.radius_csr(self.prot_x, self.prot_ptr, float(pp_cutoff),
+                                                                      int(pp_max_nbrs))
+        else:
+            pk_rowptr, _, pk_col = ops.cell_radius_csr(pk_x, pk_ptr, float(pp_cutoff), int(pp_max_nbrs))
+            node0 = g_pk_off.to(torch.int32)
+            graph_edges = (pk_rowptr[g_pk_off + counts] - pk_rowptr[g_pk_off]).to(torch.int32)
+            edge0 = ops.exclusive_scan(graph_edges)
+            n_edges = int(edge0[-1].item())
+            self.pp_rowptr, self.pp_cnt, self.pp_col = ops.replicate_csr(pk_rowptr, pk_col, node0, self.prot_ptr, edge0,
+                                                                         self.n_prot, n_edges)
         self.pp_start = self.pp_rowptr[:-1]
         self.n_pp_edges = int(self.pp_col.numel())
         self.pp_tiles = torch.empty(2 * max(self.n_prot + B, 1), dtype=torch.int32, device=dev)

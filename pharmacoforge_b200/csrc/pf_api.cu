@@ -47,6 +47,40 @@ void prof_end(int site, cudaStream_t st) {
 // (pharmacodiff.py:416-426: mu = z/alpha - var*eps; z_s = mu + sigma*noise; com = sum/count; z -= com), so
 // that with identical eps the step is bit-identical to the CPU oracle.
 // ------------------------------------------------------------------------------------------------
+// ---- counter-based Gaussian noise for throughput runs ("in-kernel Philox allowed for throughput runs").
+// Philox4x32-10 keyed by the 64-bit seed (read from DEVICE memory, so a captured CUDA graph replays with a new seed),
+// counter = (element quad, step, stream, 0); Box-Muller on the four words.  Element e of stream s at step k is a pure
+// function of (seed, e, s, k): the draw does not depend on the launch geometry.  Parity runs inject explicit noise.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned stream, unsigned step, unsigned long long e) {
+  const uint4 w = philox4x32_10(make_uint4((unsigned)(e >> 2), (unsigned)(e >> 34), step, stream),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  const unsigned a = (e & 2) ? w.z : w.x, b = (e & 2) ? w.w : w.y;
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return (e & 1) ? rad * sn : rad * cs;
+}
+constexpr unsigned kNoiseStreamX = 0, kNoiseStreamH = 1;
+
+__global__ void philox_normal_kernel(float* __restrict__ out, long long n, const unsigned long long* __restrict__ seed,
+                                     unsigned stream_id, unsigned step) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox_normal(*seed, stream_id, step, (unsigned long long)i);
+}
+
 __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ pharm_x, float* __restrict__ pharm_h,
                                                         int nh, const float* __restrict__ eps_x,
                                                         const float* __restrict__ eps_h,
@@ -55,7 +89,9 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
                                                         const int* __restrict__ pharm_ptr,
                                                         float* __restrict__ prot_x, const int* __restrict__ prot_ptr,
                                                         int n_graphs, float alpha_ts, float var_terms,
-                                                        float sigma_q) {
+                                                        float sigma_q, const unsigned long long* __restrict__ seed_dev,
+                                                        unsigned noise_step) {
+  const unsigned long long seed = noise_x == nullptr ? *seed_dev : 0ull;
   // The new coordinates of a graph are kept in shared memory between the update and the centre-of-mass pass (up to
   // kPostCache / 3 pharmacophore centres; larger graphs go through global memory as before): the three sequential sums
   // -- node order, as index_add_ does on the CPU -- were a chain of dependent global loads of just-written values.
@@ -70,7 +106,8 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
     for (int i = threadIdx.x; i < nf * 3; i += blockDim.x) {
       const size_t o = (size_t)fa * 3 + i;
       const float mu = __fsub_rn(__fdiv_rn(pharm_x[o], alpha_ts), __fmul_rn(var_terms, eps_x[o]));
-      const float z = __fadd_rn(mu, __fmul_rn(sigma_q, noise_x[o]));
+      const float nz = noise_x != nullptr ? noise_x[o] : philox_normal(seed, kNoiseStreamX, noise_step, o);
+      const float z = __fadd_rn(mu, __fmul_rn(sigma_q, nz));
       if (cached)
         s_z[i] = z;
       else
@@ -79,7 +116,8 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
     for (int i = threadIdx.x; i < nf * nh; i += blockDim.x) {
       const size_t o = (size_t)fa * nh + i;
       const float mu = __fsub_rn(__fdiv_rn(pharm_h[o], alpha_ts), __fmul_rn(var_terms, eps_h[o]));
-      pharm_h[o] = __fadd_rn(mu, __fmul_rn(sigma_q, noise_h[o]));
+      const float nz = noise_x != nullptr ? noise_h[o] : philox_normal(seed, kNoiseStreamH, noise_step, o);
+      pharm_h[o] = __fadd_rn(mu, __fmul_rn(sigma_q, nz));
     }
     __syncthreads();
     if (threadIdx.x < 3) {
@@ -197,18 +235,46 @@ extern "C" int64_t pf_gvp_layout(int vi, int vo, int si, int so, int64_t offsets
   return L.total;
 }
 
+static int posterior_launch(float* pharm_x, float* pharm_h, int32_t nh, const float* eps_x, const float* eps_h,
+                            const float* noise_x, const float* noise_h, const int32_t* pharm_ptr, float* prot_x,
+                            const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms, float sigma_q,
+                            const uint64_t* seed_dev, uint32_t noise_step, void* stream) {
+  PF_CHECK_ARG(pharm_x && pharm_h && eps_x && eps_h && pharm_ptr && prot_x && prot_ptr, "pf_posterior_step: null pointer");
+  PF_CHECK_ARG((noise_x && noise_h) || (!noise_x && !noise_h && seed_dev),
+               "pf_posterior_step: pass both noise arrays, or neither and a device seed");
+  if (n_graphs <= 0) return PF_OK;
+  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
+  posterior_kernel<<<grid, 128, 0, as_stream(stream)>>>(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h, pharm_ptr,
+                                                        prot_x, prot_ptr, n_graphs, alpha_ts, var_terms, sigma_q,
+                                                        reinterpret_cast<const unsigned long long*>(seed_dev), noise_step);
+  PF_CHECK_LAUNCH("pf_posterior_step");
+  return PF_OK;
+}
+
 extern "C" int pf_posterior_step(float* pharm_x, float* pharm_h, int32_t nh, const float* eps_x, const float* eps_h,
                                  const float* noise_x, const float* noise_h, const int32_t* pharm_ptr, float* prot_x,
                                  const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms,
                                  float sigma_q, void* stream) {
-  PF_CHECK_ARG(pharm_x && pharm_h && eps_x && eps_h && noise_x && noise_h && pharm_ptr && prot_x && prot_ptr,
-               "pf_posterior_step: null pointer");
-  if (n_graphs <= 0) return PF_OK;
-  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
-  posterior_kernel<<<grid, 128, 0, as_stream(stream)>>>(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h,
-                                                        pharm_ptr, prot_x, prot_ptr, n_graphs, alpha_ts, var_terms,
-                                                        sigma_q);
-  PF_CHECK_LAUNCH("pf_posterior_step");
+  PF_CHECK_ARG(noise_x && noise_h, "pf_posterior_step: null noise (use pf_posterior_step_philox for in-kernel noise)");
+  return posterior_launch(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h, pharm_ptr, prot_x, prot_ptr, n_graphs,
+                          alpha_ts, var_terms, sigma_q, nullptr, 0, stream);
+}
+
+extern "C" int pf_posterior_step_philox(float* pharm_x, float* pharm_h, int32_t nh, const float* eps_x, const float* eps_h,
+                                        const uint64_t* seed_dev, uint32_t noise_step, const int32_t* pharm_ptr,
+                                        float* prot_x, const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts,
+                                        float var_terms, float sigma_q, void* stream) {
+  return posterior_launch(pharm_x, pharm_h, nh, eps_x, eps_h, nullptr, nullptr, pharm_ptr, prot_x, prot_ptr, n_graphs,
+                          alpha_ts, var_terms, sigma_q, seed_dev, noise_step, stream);
+}
+
+extern "C" int pf_philox_normal(float* out, int64_t n, const uint64_t* seed_dev, uint32_t stream_id, uint32_t step,
+                                void* stream) {
+  PF_CHECK_ARG(out && seed_dev && n >= 0, "pf_philox_normal: null pointer");
+  if (n == 0) return PF_OK;
+  philox_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      out, n, reinterpret_cast<const unsigned long long*>(seed_dev), stream_id, step);
+  PF_CHECK_LAUNCH("pf_philox_normal");
   return PF_OK;
 }
 
@@ -356,16 +422,19 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
 // sample_given_receptor's loop (pharmacodiff.py:466-472).
 extern "C" int pf_sample_loop(const PfSampleArgs* a, void* stream) {
   PF_CHECK_ARG(a != nullptr, "pf_sample_loop: null args");
-  PF_CHECK_ARG(a->t_host && a->alpha_ts_host && a->var_terms_host && a->sigma_q_host && a->noise_x && a->noise_h,
-               "pf_sample_loop: missing schedule or noise");
+  PF_CHECK_ARG(a->t_host && a->alpha_ts_host && a->var_terms_host && a->sigma_q_host, "pf_sample_loop: missing schedule");
+  const bool philox = a->noise_x == nullptr;
+  PF_CHECK_ARG(philox ? (a->noise_h == nullptr && a->noise_seed != nullptr) : a->noise_h != nullptr,
+               "pf_sample_loop: pass noise_x and noise_h, or neither and noise_seed (in-kernel Philox)");
   const size_t fx = (size_t)a->n_pharm * 3, fh = (size_t)a->n_pharm * a->n_pharm_feats;
   for (int i = 0; i < a->n_steps; ++i) {
     PF_TRY(pf_fill_f32(a->t_graph, a->n_graphs, a->t_host[i], stream));
     PF_TRY(pf_denoiser(a, stream));
     prof_begin(kSitePosterior, as_stream(stream));
-  PF_TRY(pf_posterior_step(a->pharm_x, a->pharm_h, a->n_pharm_feats, a->eps_x, a->eps_h, a->noise_x + i * fx,
-                             a->noise_h + i * fh, a->pharm_ptr, a->prot_x, a->prot_ptr, a->n_graphs,
-                             a->alpha_ts_host[i], a->var_terms_host[i], a->sigma_q_host[i], stream));
+  PF_TRY(posterior_launch(a->pharm_x, a->pharm_h, a->n_pharm_feats, a->eps_x, a->eps_h,
+                            philox ? nullptr : a->noise_x + i * fx, philox ? nullptr : a->noise_h + i * fh, a->pharm_ptr,
+                            a->prot_x, a->prot_ptr, a->n_graphs, a->alpha_ts_host[i], a->var_terms_host[i],
+                            a->sigma_q_host[i], a->noise_seed, (uint32_t)(a->noise_step0 + i), stream));
   prof_end(kSitePosterior, as_stream(stream));
   }
   return PF_OK;

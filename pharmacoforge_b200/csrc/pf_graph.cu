@@ -6,6 +6,12 @@
 
 #include "pf_common.cuh"
 
+#define PF_TRY_RC(call)           \
+  do {                            \
+    int rc_ = (call);             \
+    if (rc_ != PF_OK) return rc_; \
+  } while (0)
+
 namespace pf {
 
 __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
@@ -141,6 +147,224 @@ __global__ void __launch_bounds__(kRadThreads) radius_kernel(const float* __rest
       }
       if (!FILL && live) deg[i] = kept;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1, cell list
+// The static pp graph is a property of the POCKET, not of its copies: it is built once per distinct pocket with a cell
+// list (cell edge c >= r, so the neighbours of a centre live in its 27 surrounding cells) and then replicated per graph
+// with node offsets (protein_pharm_dataset.py:234-236 builds it once per pocket; copy_graph + dgl.batch replicate it,
+// unorganized_utils.py:28-50).  One CTA per pocket.  Workspace per pocket (ints), carved from one caller buffer:
+//   grid[8]           : min x, y, z (float bits), 1/c (float bits), nx, ny, nz, n_cells
+//   cell_end[2n + 8]  : after the build, atoms of cell k are sorted[(k ? cell_end[k-1] : 0) .. cell_end[k])
+//   atom_cell[n], sorted[n]
+// The cell edge starts at r (1 + 1e-4) -- the margin keeps a neighbour at |dx| -> r from landing two cells away under
+// fp32 rounding of (x - min) / c -- and grows by 2^(1/3) until the grid has at most 2n + 8 cells (sparse point clouds).
+// Edge membership uses the same canonical squared distance as everywhere else; a row's hits are sorted ascending and cut
+// as torch_cluster does (first max_nbrs + 1 hits INCLUDING the centre, then the centre is dropped), so the CSR is
+// bit-identical to the brute-force kernel's and to the reference's.
+constexpr int kCellThreads = 256;
+constexpr int kCellRowCap = 160;   // hits of one centre sorted in local memory; denser rows fall back to the ordered scan
+
+__host__ __device__ inline size_t cell_ws_ints(long long n_nodes, int n_seg) { return (size_t)(4 * n_nodes) + (size_t)n_seg * 16; }
+struct CellWs {
+  int *grid, *cell_end, *atom_cell, *sorted;
+};
+__device__ __forceinline__ CellWs cell_ws(int* ws, const int* seg_ptr, int n_seg, long long n_nodes, int g) {
+  CellWs w;
+  const int a = seg_ptr[g];
+  w.grid = ws + (size_t)g * 8;
+  w.cell_end = ws + (size_t)n_seg * 8 + (size_t)2 * a + (size_t)8 * g;
+  w.atom_cell = ws + (size_t)n_seg * 16 + (size_t)2 * n_nodes + a;
+  w.sorted = w.atom_cell + n_nodes;
+  return w;
+}
+
+__global__ void __launch_bounds__(kCellThreads) cell_build_kernel(const float* __restrict__ x, const int* __restrict__ seg_ptr,
+                                                                  int n_seg, long long n_nodes, float r, int* __restrict__ ws) {
+  __shared__ float s_red[6][kCellThreads / 32];
+  __shared__ float s_min[3], s_inv;
+  __shared__ int s_dim[4];
+  __shared__ int s_warp[33];
+  for (int g = blockIdx.x; g < n_seg; g += gridDim.x) {
+    const int a = seg_ptr[g], n = seg_ptr[g + 1] - a;
+    const CellWs w = cell_ws(ws, seg_ptr, n_seg, n_nodes, g);
+    // ---- bounding box
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = threadIdx.x; i < n; i += kCellThreads)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = x[3 * (size_t)(a + i) + c];
+        lo[c] = fminf(lo[c], v);
+        hi[c] = fmaxf(hi[c], v);
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+        hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+      }
+      if ((threadIdx.x & 31) == 0) {
+        s_red[c][threadIdx.x >> 5] = lo[c];
+        s_red[3 + c][threadIdx.x >> 5] = hi[c];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mn[3], mx[3];
+      for (int c = 0; c < 3; ++c) {
+        mn[c] = s_red[c][0];
+        mx[c] = s_red[3 + c][0];
+        for (int k = 1; k < kCellThreads / 32; ++k) {
+          mn[c] = fminf(mn[c], s_red[c][k]);
+          mx[c] = fmaxf(mx[c], s_red[3 + c][k]);
+        }
+        if (n == 0) mn[c] = mx[c] = 0.f;
+      }
+      float cedge = r * 1.0001f;
+      int d[3];
+      long long cells;
+      for (;;) {
+        cells = 1;
+        for (int c = 0; c < 3; ++c) {
+          const float q = floorf((mx[c] - mn[c]) / cedge);
+          d[c] = q < 1048575.f ? (int)q + 1 : 1048576;   // clamp: the loop below grows the cell until the grid is small
+          cells *= d[c];
+        }
+        if (cells <= 2LL * n + 8) break;
+        cedge *= 1.2599211f;
+      }
+      for (int c = 0; c < 3; ++c) {
+        s_min[c] = mn[c];
+        s_dim[c] = d[c];
+        w.grid[c] = __float_as_int(mn[c]);
+        w.grid[4 + c] = d[c];
+      }
+      s_inv = 1.0f / cedge;
+      s_dim[3] = (int)cells;
+      w.grid[3] = __float_as_int(s_inv);
+      w.grid[7] = (int)cells;
+    }
+    __syncthreads();
+    const int n_cells = s_dim[3];
+    for (int k = threadIdx.x; k < n_cells; k += kCellThreads) w.cell_end[k] = 0;
+    __syncthreads();
+    // ---- histogram
+    for (int i = threadIdx.x; i < n; i += kCellThreads) {
+      int cc[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int v = (int)floorf((x[3 * (size_t)(a + i) + c] - s_min[c]) * s_inv);
+        cc[c] = v < 0 ? 0 : (v >= s_dim[c] ? s_dim[c] - 1 : v);
+      }
+      const int cell = (cc[2] * s_dim[1] + cc[1]) * s_dim[0] + cc[0];
+      w.atom_cell[i] = cell;
+      atomicAdd(&w.cell_end[cell], 1);
+    }
+    __syncthreads();
+    // ---- exclusive scan of the counts, in place (cell_end[k] = first slot of cell k), block by block
+    int carry = 0;
+    for (int k0 = 0; k0 < n_cells; k0 += kCellThreads) {
+      const int k = k0 + threadIdx.x;
+      const int v = k < n_cells ? w.cell_end[k] : 0;
+      int total;
+      const int off = block_exclusive_scan(v, s_warp, total);
+      if (k < n_cells) w.cell_end[k] = carry + off;
+      carry += total;
+    }
+    __syncthreads();
+    // ---- fill: the cursor of a cell advances to its end (order inside a cell is arbitrary: rows are sorted later)
+    for (int i = threadIdx.x; i < n; i += kCellThreads) w.sorted[atomicAdd(&w.cell_end[w.atom_cell[i]], 1)] = i;
+    __syncthreads();
+  }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(kCellThreads) cell_radius_kernel(const float* __restrict__ x, const int* __restrict__ seg_ptr,
+                                                                   int n_seg, long long n_nodes, float r2, int max_nbrs,
+                                                                   int* __restrict__ ws, int* __restrict__ deg,
+                                                                   const int* __restrict__ rowptr, int* __restrict__ col) {
+  for (int g = blockIdx.x; g < n_seg; g += gridDim.x) {
+    const int a = seg_ptr[g], n = seg_ptr[g + 1] - a;
+    const CellWs w = cell_ws(ws, seg_ptr, n_seg, n_nodes, g);
+    const int nx = w.grid[4], ny = w.grid[5], nz = w.grid[6];
+    for (int i = threadIdx.x; i < n; i += kCellThreads) {
+      const float xi = x[3 * (size_t)(a + i)], yi = x[3 * (size_t)(a + i) + 1], zi = x[3 * (size_t)(a + i) + 2];
+      const int cell = w.atom_cell[i];
+      const int cx = cell % nx, cy = (cell / nx) % ny, cz = cell / (nx * ny);
+      int hits = 0, lower = 0;          // hits including the centre itself; hits with a smaller index
+      int buf[FILL ? kCellRowCap : 1];
+      for (int dz = -1; dz <= 1; ++dz) {
+        const int z = cz + dz;
+        if (z < 0 || z >= nz) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int y = cy + dy;
+          if (y < 0 || y >= ny) continue;
+          // the three cells of one x-run are contiguous in memory: one range per (dy, dz)
+          const int k0 = (z * ny + y) * nx + (cx > 0 ? cx - 1 : 0), k1 = (z * ny + y) * nx + (cx + 1 < nx ? cx + 1 : nx - 1);
+          const int beg = k0 > 0 ? w.cell_end[k0 - 1] : 0, end = w.cell_end[k1];
+          for (int t = beg; t < end; ++t) {
+            const int j = w.sorted[t];
+            if (sqdist3(xi, yi, zi, x[3 * (size_t)(a + j)], x[3 * (size_t)(a + j) + 1], x[3 * (size_t)(a + j) + 2]) < r2) {
+              if (FILL && hits < kCellRowCap) buf[hits] = j;
+              ++hits;
+              lower += j < i;
+            }
+          }
+        }
+      }
+      // torch_cluster: the first max_nbrs + 1 hits in ascending index INCLUDING the centre, then the centre is dropped
+      const int kept = (hits < max_nbrs + 1 ? hits : max_nbrs + 1) - (lower < max_nbrs + 1 ? 1 : 0);
+      if (!FILL) {
+        deg[a + i] = kept;
+      } else {
+        int* out = col + rowptr[a + i];
+        if (hits <= kCellRowCap) {
+          for (int u = 1; u < hits; ++u) {   // insertion sort, ascending
+            const int v = buf[u];
+            int q = u - 1;
+            while (q >= 0 && buf[q] > v) {
+              buf[q + 1] = buf[q];
+              --q;
+            }
+            buf[q + 1] = v;
+          }
+          int o = 0;
+          for (int u = 0; u < hits && u < max_nbrs + 1; ++u)
+            if (buf[u] != i) out[o++] = a + buf[u];
+        } else {                             // a very dense row: ordered scan of the whole pocket (the brute-force rule)
+          int rank = 0, o = 0;
+          for (int j = 0; j < n && rank < max_nbrs + 1; ++j)
+            if (sqdist3(xi, yi, zi, x[3 * (size_t)(a + j)], x[3 * (size_t)(a + j) + 1], x[3 * (size_t)(a + j) + 2]) < r2) {
+              ++rank;
+              if (j != i) out[o++] = a + j;
+            }
+        }
+      }
+    }
+  }
+}
+
+// Replication of the per-pocket CSR over the graphs of a batch (copy_graph + dgl.batch): graph g is a copy of the pocket
+// whose nodes start at pk_node0[g] in the pocket arrays; its nodes are [prot_ptr[g], prot_ptr[g+1]) and its edges start at
+// edge0[g] (exclusive scan of the copies' edge counts).  One CTA per graph, coalesced stores: 4 B per edge + 8 B per node.
+__global__ void __launch_bounds__(256) replicate_csr_kernel(const int* __restrict__ pk_rowptr, const int* __restrict__ pk_col,
+                                                            const int* __restrict__ pk_node0, const int* __restrict__ prot_ptr,
+                                                            const int* __restrict__ edge0, int n_graphs,
+                                                            int* __restrict__ rowptr, int* __restrict__ cnt,
+                                                            int* __restrict__ col) {
+  for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
+    const int p0 = pk_node0[g], n0 = prot_ptr[g], n = prot_ptr[g + 1] - n0, e0 = edge0[g];
+    const int pe0 = pk_rowptr[p0], ne = pk_rowptr[p0 + n] - pe0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int rs = pk_rowptr[p0 + i];
+      rowptr[n0 + i] = e0 + rs - pe0;
+      cnt[n0 + i] = pk_rowptr[p0 + i + 1] - rs;
+    }
+    const int shift = n0 - p0;
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) col[e0 + e] = pk_col[pe0 + e] + shift;
+    if (g == n_graphs - 1 && threadIdx.x == 0) rowptr[n0 + n] = e0 + ne;
   }
 }
 
@@ -409,6 +633,62 @@ extern "C" int pf_radius_fill(const float* x, const int32_t* seg_ptr, int32_t n_
   radius_kernel<true><<<grid, kRadThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, r * r, max_nbrs, nullptr,
                                                                    rowptr, col);
   PF_CHECK_LAUNCH("pf_radius_fill");
+  return PF_OK;
+}
+
+extern "C" size_t pf_cell_radius_workspace_bytes(int64_t n_nodes, int32_t n_seg) {
+  return cell_ws_ints(n_nodes, n_seg) * sizeof(int);
+}
+
+static int cell_radius_common(const float* x, const int32_t* seg_ptr, int32_t n_seg, int64_t n_nodes, float r, int32_t max_nbrs,
+                              void* workspace, size_t workspace_bytes, const char* who) {
+  if (!(x && seg_ptr && workspace && max_nbrs >= 0 && r > 0.f)) {
+    set_error("bad argument: %s: null pointer / bad radius", who);
+    return PF_ERR_BAD_ARG;
+  }
+  if (workspace_bytes < pf_cell_radius_workspace_bytes(n_nodes, n_seg)) {
+    set_error("%s: workspace too small (%zu < %zu bytes)", who, workspace_bytes, pf_cell_radius_workspace_bytes(n_nodes, n_seg));
+    return PF_ERR_WORKSPACE;
+  }
+  return PF_OK;
+}
+
+extern "C" int pf_cell_radius_count(const float* x, const int32_t* seg_ptr, int32_t n_seg, int64_t n_nodes, float r,
+                                    int32_t max_nbrs, void* workspace, size_t workspace_bytes, int32_t* deg, void* stream) {
+  PF_TRY_RC(cell_radius_common(x, seg_ptr, n_seg, n_nodes, r, max_nbrs, workspace, workspace_bytes, "pf_cell_radius_count"));
+  PF_CHECK_ARG(deg != nullptr, "pf_cell_radius_count: null deg");
+  if (n_seg <= 0) return PF_OK;
+  const int grid = n_seg < 16 * num_sms() ? n_seg : 16 * num_sms();
+  cell_build_kernel<<<grid, kCellThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, n_nodes, r, static_cast<int*>(workspace));
+  PF_CHECK_LAUNCH("pf_cell_radius_count (build)");
+  cell_radius_kernel<false><<<grid, kCellThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, n_nodes, r * r, max_nbrs,
+                                                                          static_cast<int*>(workspace), deg, nullptr, nullptr);
+  PF_CHECK_LAUNCH("pf_cell_radius_count");
+  return PF_OK;
+}
+
+extern "C" int pf_cell_radius_fill(const float* x, const int32_t* seg_ptr, int32_t n_seg, int64_t n_nodes, float r,
+                                   int32_t max_nbrs, void* workspace, size_t workspace_bytes, const int32_t* rowptr,
+                                   int32_t* col, void* stream) {
+  PF_TRY_RC(cell_radius_common(x, seg_ptr, n_seg, n_nodes, r, max_nbrs, workspace, workspace_bytes, "pf_cell_radius_fill"));
+  PF_CHECK_ARG(rowptr && col, "pf_cell_radius_fill: null pointer");
+  if (n_seg <= 0) return PF_OK;
+  const int grid = n_seg < 16 * num_sms() ? n_seg : 16 * num_sms();
+  cell_radius_kernel<true><<<grid, kCellThreads, 0, as_stream(stream)>>>(x, seg_ptr, n_seg, n_nodes, r * r, max_nbrs,
+                                                                         static_cast<int*>(workspace), nullptr, rowptr, col);
+  PF_CHECK_LAUNCH("pf_cell_radius_fill");
+  return PF_OK;
+}
+
+extern "C" int pf_replicate_csr(const int32_t* pk_rowptr, const int32_t* pk_col, const int32_t* pk_node0,
+                                const int32_t* prot_ptr, const int32_t* edge0, int32_t n_graphs, int32_t* rowptr,
+                                int32_t* cnt, int32_t* col, void* stream) {
+  PF_CHECK_ARG(pk_rowptr && pk_col && pk_node0 && prot_ptr && edge0 && rowptr && cnt && col, "pf_replicate_csr: null pointer");
+  if (n_graphs <= 0) return PF_OK;
+  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
+  replicate_csr_kernel<<<grid, 256, 0, as_stream(stream)>>>(pk_rowptr, pk_col, pk_node0, prot_ptr, edge0, n_graphs, rowptr,
+                                                            cnt, col);
+  PF_CHECK_LAUNCH("pf_replicate_csr");
   return PF_OK;
 }
 

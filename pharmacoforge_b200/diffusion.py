@@ -111,6 +111,9 @@ class PharmacophoreDiff(nn.Module):
         self.pharms_per_pocket, self.n_pockets_to_sample = pharms_per_pocket, n_pockets_to_sample
         self.graph_cutoffs = graph_config.get("graph_cutoffs", {})
         self._tables = None
+        # Replay the T-step loop as one captured CUDA graph when the noise comes from the in-kernel Philox generator
+        # (sample_given_receptor(noise=None)); not a constructor argument (the reference signature is kept).
+        self.use_cuda_graph = False
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -135,8 +138,11 @@ class PharmacophoreDiff(nn.Module):
         model.load_state_dict(ckpt["state_dict"], strict=True)
         return model
 
-    def save_checkpoint(self, path):
-        torch.save({"state_dict": self.state_dict(), "hyper_parameters": self.hparams}, path)
+    def save_checkpoint(self, path, **extra):
+        """A Lightning-format `.ckpt` (checkpoint.save_lightning_checkpoint): loadable by the reference's
+        `PharmacophoreDiff.load_from_checkpoint` and by this class."""
+        from .checkpoint import save_lightning_checkpoint
+        save_lightning_checkpoint(self, path, **extra)
 
     @property
     def device(self):
@@ -145,7 +151,10 @@ class PharmacophoreDiff(nn.Module):
     def make_batch(self, pockets: Sequence[Pocket], n_pharms: Sequence[Sequence[int]], device=None,
                    graph_range: Optional[range] = None) -> GraphBatch:
         """copy_graph + dgl.batch of the reference (generate_pharmacophores.py:333-334)."""
-        return GraphBatch.from_pockets(pockets, n_pharms, device or self.device,
+        if device is None:   # the reference moves the batch to self.device (pharmacodiff.py:566); the kernels need a GPU, so
+            # a model whose parameters still sit on the host samples on the current CUDA device
+            device = self.device if self.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        return GraphBatch.from_pockets(pockets, n_pharms, device,
                                        pp_cutoff=self.graph_cutoffs.get("pp", 3.5), pf_k=self.dynamics.pf_k,
                                        graph_range=graph_range)
 
@@ -192,11 +201,10 @@ class PharmacophoreDiff(nn.Module):
         st = self.dynamics.bind(g)
         nfn = g.n_pharm
         if noise is None:
-            nx = torch.empty(steps + 1, nfn, 3, device=dev)
-            nhh = torch.empty(steps + 1, nfn, nh, device=dev)
-            for i in range(steps + 1):  # x before h, every step (pharmacodiff.py:455-456, 423-424)
-                nx[i] = torch.randn(nfn, 3, device=dev)
-                nhh[i] = torch.randn(nfn, nh, device=dev)
+            # throughput path: Gaussian draws come from Philox inside the posterior kernel (no noise tensors, no 2 (T+1)
+            # randn launches); the 64-bit key is drawn from torch's CUDA generator, so torch.manual_seed reproduces a run
+            nx = nhh = None
+            st.noise_seed.copy_(torch.randint(0, 2 ** 62, (1,), device=dev, dtype=torch.int64))
         else:
             noise = noise.to(dev, non_blocking=True).float()
             nx = noise[:steps + 1, :, 0:3].contiguous()
@@ -207,8 +215,12 @@ class PharmacophoreDiff(nn.Module):
             init_pharm_com = init_prot_com
         init_pharm_com = init_pharm_com.to(dev).float().contiguous()
         ops.segment_shift3(g.prot_x, g.prot_ptr, init_pharm_com, -1.0)
-        g.pharm_x.copy_(nx[0])
-        g.pharm_h.copy_(nhh[0])
+        if nx is None:   # z_T: x before h (pharmacodiff.py:455-456) = Philox streams 0 and 1 of step 0
+            ops.philox_normal(g.pharm_x, st.noise_seed, 0, 0)
+            ops.philox_normal(g.pharm_h, st.noise_seed, 1, 0)
+        else:
+            g.pharm_x.copy_(nx[0])
+            g.pharm_h.copy_(nhh[0])
         self._tables = self.step_tables()   # once per call; kept alive while C reads them
         frames = None
         if visualize_trajectory:
@@ -257,11 +269,33 @@ class PharmacophoreDiff(nn.Module):
         a.alpha_ts_host = alpha_ts[off:].ctypes.data
         a.var_terms_host = var_terms[off:].ctypes.data
         a.sigma_q_host = sigma_q[off:].ctypes.data
-        a.noise_x = nx[1 + first:].data_ptr() if count else 0
-        a.noise_h = nhh[1 + first:].data_ptr() if count else 0
+        philox = nx is None
+        a.noise_x = nx[1 + first:].data_ptr() if (count and not philox) else 0
+        a.noise_h = nhh[1 + first:].data_ptr() if (count and not philox) else 0
+        a.noise_seed = st.noise_seed.data_ptr()
+        a.noise_step0 = first + 1
         a.n_steps = count
-        if count:
+        if not count:
+            return
+        if not (philox and self.use_cuda_graph):
             ops.sample_loop(g.pharm_x, g.pharm_h, g.prot_x, st.addr)
+            st.warmed = True
+            return
+        # The whole loop as ONE CUDA graph (Philox mode only: every kernel argument is then the same from call to call --
+        # buffers of this batch, the schedule constants, the device-resident seed).  Captured on the second use of a
+        # (batch, first, count, flags) combination: the first one runs eagerly so that every kernel has been configured.
+        key = (first, count, int(a.flags))
+        gr = st.graphs.get(key)
+        if gr is None and not st.warmed:
+            ops.sample_loop(g.pharm_x, g.pharm_h, g.prot_x, st.addr)
+            st.warmed = True
+            return
+        if gr is None:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                ops.sample_loop(g.pharm_x, g.pharm_h, g.prot_x, st.addr)
+            st.graphs[key] = gr
+        gr.replay()
 
     def _record_frame(self, g, init_prot_com, frames, i):
         prot_com = ops.segment_mean3(g.prot_x, g.prot_ptr)
@@ -271,19 +305,28 @@ class PharmacophoreDiff(nn.Module):
         frames[1][i] = g.pharm_h
 
     def sample(self, ref_graphs: Sequence[Pocket], n_pharms: List[List[int]], max_batch_size: int = 32,
-               init_pharm_com: Optional[torch.Tensor] = None, visualize_trajectory: bool = False):
-        """pharmacodiff.py:516-578: pockets x samples flattened pocket-major, chunked by max_batch_size, regrouped."""
+               init_pharm_com: Optional[torch.Tensor] = None, visualize_trajectory: bool = False,
+               noise: Optional[torch.Tensor] = None, n_steps: Optional[int] = None):
+        """pharmacodiff.py:516-578: pockets x samples flattened pocket-major, chunked by max_batch_size, regrouped per
+        pocket.  `init_pharm_com` [n_pockets, 3] defaults to each pocket's mean position (:531-535) and is indexed by the
+        pocket of every graph of a chunk (:563).  `noise` ([T+1, Nf_total, 3+nf], columns = pharmacophore nodes in the
+        flattened graph order) and `n_steps` are the parity hooks of `sample_given_receptor`."""
+        if init_pharm_com is None:
+            init_pharm_com = torch.stack([r.prot_x.float().mean(dim=0) for r in ref_graphs])
         flat_ref = [r for r, szs in enumerate(n_pharms) for _ in szs]
+        flat_nf = [int(n) for szs in n_pharms for n in szs]
         n_total = len(flat_ref)
         sampled: List[SampledPharmacophore] = []
+        col = 0
         for b in range(ceil(n_total / max_batch_size)):
             rng = range(b * max_batch_size, min((b + 1) * max_batch_size, n_total))
             g = self.make_batch(ref_graphs, n_pharms, graph_range=rng)
-            coms = None
-            if init_pharm_com is not None:
-                coms = init_pharm_com[flat_ref[rng.start:rng.stop]]
-            sampled.extend(self.sample_given_receptor(g, init_pharm_com=coms,
-                                                      visualize_trajectory=visualize_trajectory))
+            coms = init_pharm_com[flat_ref[rng.start:rng.stop]]
+            nf = sum(flat_nf[rng.start:rng.stop])
+            chunk_noise = None if noise is None else noise[:, col:col + nf]
+            col += nf
+            sampled.extend(self.sample_given_receptor(g, init_pharm_com=coms, visualize_trajectory=visualize_trajectory,
+                                                      noise=chunk_noise, n_steps=n_steps))
         out, end = [], 0
         for szs in n_pharms:
             out.append(sampled[end:end + len(szs)])

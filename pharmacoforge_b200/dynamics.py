@@ -128,6 +128,8 @@ class _DeviceState:
         self.eps_h = torch.empty(nfn, dyn.n_pharm_scalars, **f32)
         self.eps_x = torch.empty(nfn, 3, **f32)
         self.t_graph = torch.empty(max(g.n_graphs, 1), **f32)
+        self.noise_seed = torch.zeros(1, dtype=torch.int64, device=dev)   # Philox key of the sampling loop (device-resident)
+        self.graphs, self.warmed = {}, False                              # captured CUDA graphs of the loop
         if g.pharm_h is None or g.pharm_h.shape[1] != dyn.n_pharm_scalars:
             g.pharm_h = torch.zeros(nfn, dyn.n_pharm_scalars, **f32)
         a = _lib.PfSampleArgs()

@@ -191,6 +191,54 @@ def pocket_from_pdb(rec_file, prot_elements: Sequence[str], pocket_cutoff: float
     return Pocket.from_numpy(pos, onehot[keep, :-1]), init_com
 
 
+TYPE_IDX_TO_ELEM = ["P", "S", "F", "N", "O", "C"]
+
+
+def write_pharmacophore_file(coords_list, atom_types_list, pharm_type_map=None, filename=None):
+    """utils/unorganized_utils.py:111-128: several pharmacophores as concatenated xyz blocks (`n` line, then one
+    `<element> x y z` line per centre, element = TYPE_IDX_TO_ELEM[type index]); returns the text when no filename."""
+    out = ""
+    for coords, atom_types in zip(coords_list, atom_types_list):
+        assert len(coords) == len(atom_types)
+        elems = [TYPE_IDX_TO_ELEM[int(i)] for i in atom_types]
+        out += f"{len(coords)}\n"
+        for i in range(len(coords)):
+            out += f"{elems[i]} {coords[i, 0]:.3f} {coords[i, 1]:.3f} {coords[i, 2]:.3f}\n"
+    if filename is None:
+        return out
+    Path(filename).write_text(out)
+
+
+def pocket_to_dgl(pocket: Pocket, graph_cutoffs: dict, pharm_x: Optional[torch.Tensor] = None,
+                  pharm_h: Optional[torch.Tensor] = None):
+    """A reference-style pocket graph (`build_initial_complex_graph`, protein_pharm_dataset.py:210-266): node types
+    prot / pharm / prot_ph, the pp radius edges (src = neighbour, dst = centre, ascending), node data x_0 / h_0.
+    Needs dgl (and torch_cluster for nothing: the pp edges are computed here).  Inverse of `Pocket.from_dgl`."""
+    import dgl
+    x = pocket.prot_x.float()
+    n = x.shape[0]
+    r = float(graph_cutoffs["pp"])
+    src = torch.zeros(0, dtype=torch.long)
+    dst = torch.zeros(0, dtype=torch.long)
+    if r > 0 and n > 0:
+        d = x[:, None, :] - x[None, :, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        hit = d2 < r * r                                    # [centre, neighbour], self included (torch_cluster rule)
+        rank = torch.cumsum(hit.long(), dim=1)
+        keep = hit & (rank <= 100 + 1) & ~torch.eye(n, dtype=torch.bool)
+        dst, src = keep.nonzero(as_tuple=True)
+    n_pharm = 0 if pharm_x is None else pharm_x.shape[0]
+    g = dgl.heterograph({("prot", "pp", "prot"): (src, dst), ("prot", "pf", "pharm"): ([], []),
+                         ("pharm", "ff", "pharm"): ([], []), ("pharm", "fp", "prot"): ([], [])},
+                        num_nodes_dict={"prot": n, "pharm": n_pharm, "prot_ph": 0})
+    if pharm_x is not None:
+        g.nodes["pharm"].data["x_0"] = pharm_x
+        g.nodes["pharm"].data["h_0"] = pharm_h
+    g.nodes["prot"].data["x_0"] = pocket.prot_x
+    g.nodes["prot"].data["h_0"] = pocket.prot_h
+    return g
+
+
 class ProteinPharmacophoreDataset:
     """protein_pharm_dataset.py:18-207 without DGL: item i -> dict(pocket, x_0, h_0, prot_ph_pos, prot_ph_feat).
     `processed_data_dir` holds one sub-directory per split, each with `prot_pharm_tensors.npz` (keys pharm_pos,

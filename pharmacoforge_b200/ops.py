@@ -117,6 +117,48 @@ def radius_csr(x: torch.Tensor, seg_ptr: torch.Tensor, r: float, max_nbrs: int):
     return rowptr, deg, col
 
 
+@torch.library.custom_op(f"{NS}::cell_radius_csr", mutates_args=())
+def cell_radius_csr(x: torch.Tensor, seg_ptr: torch.Tensor, r: float, max_nbrs: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """K1 as a cell list: destination-sorted CSR of the radius graph within each segment (pocket) ->
+    (rowptr [N+1], deg [N], col [E]); bit-identical to `radius_csr`."""
+    n, n_seg = x.shape[0], seg_ptr.numel() - 1
+    ws_bytes = _L.pf_cell_radius_workspace_bytes(n, n_seg)
+    ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.int32, device=x.device)
+    deg = torch.empty(n, dtype=torch.int32, device=x.device)
+    _lib.check(_L.pf_cell_radius_count(_f(x), _i(seg_ptr), n_seg, n, r, max_nbrs, _p(ws), ws.numel() * 4, _i(deg), _s()),
+               "pf_cell_radius_count")
+    rowptr = exclusive_scan(deg)
+    n_edges = int(rowptr[-1].item())  # one host sync per batch, at setup
+    col = torch.empty(max(n_edges, 1), dtype=torch.int32, device=x.device)
+    _lib.check(_L.pf_cell_radius_fill(_f(x), _i(seg_ptr), n_seg, n, r, max_nbrs, _p(ws), ws.numel() * 4, _i(rowptr), _i(col),
+                                      _s()), "pf_cell_radius_fill")
+    return rowptr, deg, col[:n_edges]
+
+
+@cell_radius_csr.register_fake
+def _(x, seg_ptr, r, max_nbrs):
+    return (x.new_empty(x.shape[0] + 1, dtype=torch.int32), x.new_empty(x.shape[0], dtype=torch.int32),
+            x.new_empty(0, dtype=torch.int32))
+
+
+@torch.library.custom_op(f"{NS}::replicate_csr", mutates_args=())
+def replicate_csr(pk_rowptr: torch.Tensor, pk_col: torch.Tensor, pk_node0: torch.Tensor, prot_ptr: torch.Tensor,
+                  edge0: torch.Tensor, n_nodes: int, n_edges: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """copy_graph + dgl.batch of the static pp graph: per-pocket CSR -> batched (rowptr [N+1], cnt [N], col [E])."""
+    dev = pk_rowptr.device
+    rowptr = torch.zeros(n_nodes + 1, dtype=torch.int32, device=dev)
+    cnt = torch.empty(max(n_nodes, 1), dtype=torch.int32, device=dev)
+    col = torch.empty(max(n_edges, 1), dtype=torch.int32, device=dev)
+    _lib.check(_L.pf_replicate_csr(_i(pk_rowptr), _i(pk_col), _i(pk_node0), _i(prot_ptr), _i(edge0), prot_ptr.numel() - 1,
+                                   _i(rowptr), _i(cnt), _i(col), _s()), "pf_replicate_csr")
+    return rowptr, cnt[:n_nodes], col[:n_edges]
+
+
+@replicate_csr.register_fake
+def _(pk_rowptr, pk_col, pk_node0, prot_ptr, edge0, n_nodes, n_edges):
+    return (pk_rowptr.new_empty(n_nodes + 1), pk_rowptr.new_empty(n_nodes), pk_rowptr.new_empty(n_edges))
+
+
 @torch.library.custom_op(f"{NS}::dyn_graph",
                          mutates_args=("ff_cnt", "ff_col", "pf_cnt", "pf_col", "fp_seg_dst", "fp_seg_start",
                                        "fp_seg_cnt", "fp_col", "status"))
@@ -236,6 +278,14 @@ def posterior_step(pharm_x: torch.Tensor, pharm_h: torch.Tensor, eps_x: torch.Te
     _lib.check(_L.pf_posterior_step(_f(pharm_x), _f(pharm_h), pharm_h.shape[1], _f(eps_x), _f(eps_h), _f(noise_x),
                                     _f(noise_h), _i(pharm_ptr), _f(prot_x), _i(prot_ptr), prot_ptr.numel() - 1,
                                     alpha_ts, var_terms, sigma_q, _s()), "pf_posterior_step")
+
+
+@torch.library.custom_op(f"{NS}::philox_normal", mutates_args=("out",))
+def philox_normal(out: torch.Tensor, seed: torch.Tensor, stream_id: int, step: int) -> None:
+    """out <- N(0, 1) draws of (stream_id, step) under the int64 device seed (Philox4x32-10 + Box-Muller)."""
+    if seed.dtype != torch.int64 or seed.numel() != 1:
+        raise _lib.PfError("philox_normal: seed must be a 1-element int64 CUDA tensor")
+    _lib.check(_L.pf_philox_normal(_f(out), out.numel(), _p(seed), stream_id, step, _s()), "pf_philox_normal")
 
 
 @torch.library.custom_op(f"{NS}::segment_mean3", mutates_args=())

@@ -49,9 +49,14 @@ def k4(layer, v):
     return lambda: ops.node_update_tc(prot_h, v, agg_h, agg_v, W.tcu_view(layer, 1), out_h, out_v, FP16)
 
 
-res = {"pockets": npk, "edges": g.n_pp_edges, "nodes": g.n_prot, "fp16": FP16,
-       "k3_l0_ms": timed(k3(0, None)), "k3_l1_ms": timed(k3(1, prot_v)),
-       "k4_l0_ms": timed(k4(0, None)), "k4_l1_ms": timed(k4(1, prot_v))}
-res["k3_tflops_l1"] = g.n_pp_edges * 136742 / (res["k3_l1_ms"] * 1e-3) / 1e12
-res["k4_gbs_l1"] = 3 * 704 * g.n_prot / (res["k4_l1_ms"] * 1e-3) / 1e9
+only = os.environ.get("KB_ONLY", "")
+res = {"pockets": npk, "edges": g.n_pp_edges, "nodes": g.n_prot, "fp16": FP16, "lib": os.environ.get("PF_LIB_PATH", "")}
+if only in ("", "k3"):
+    res.update(k3_l0_ms=timed(k3(0, None)), k3_l1_ms=timed(k3(1, prot_v)))
+    res["k3_tflops_l1"] = g.n_pp_edges * 136742 / (res["k3_l1_ms"] * 1e-3) / 1e12
+if only in ("", "k4"):
+    res.update(k4_l0_ms=timed(k4(0, None)), k4_l1_ms=timed(k4(1, prot_v)))
+    res["k4_gbs_l1"] = 3 * 704 * g.n_prot / (res["k4_l1_ms"] * 1e-3) / 1e9
+    # correctness guard for A/B builds: checksum of the outputs
+    res["k4_checksum"] = float(out_h.double().sum().item()), float(out_v.double().sum().item())
 print(json.dumps(res))

@@ -142,6 +142,58 @@ def test_radius_max_neighbors_truncation(env):
     assert deg.max().item() <= 21 and np.array_equal(s, so) and np.array_equal(d, do)
 
 
+@pytest.mark.parametrize("case", ["pockets", "dense_truncated", "very_dense_fallback", "sparse_far_apart", "degenerate"])
+def test_cell_list_radius_csr_is_bit_identical_to_all_pairs(env, case):
+    """K1 as a cell list (pf_cell_radius_count / fill) against the all-pairs kernel and the oracle: same CSR bit for bit,
+    including torch_cluster's truncation rule, rows denser than the in-kernel sort buffer (ordered-scan fallback),
+    point clouds so sparse that the cell edge has to grow, and empty / single-atom / coincident-point segments."""
+    O, ops = env.O, env.ops
+    gen = torch.Generator().manual_seed(3)
+    r, mx = 3.5, 100
+    if case == "pockets":
+        xs = [t(env.make_pocket(n, seed=s)[0]) for n, s in ((400, 0), (37, 2), (1, 4), (1500, 5), (250, 3))]
+    elif case == "dense_truncated":
+        xs, r, mx = [torch.rand(120, 3, generator=gen) * 4.0, torch.rand(180, 3, generator=gen) * 4.0 + 30.0], 3.0, 20
+    elif case == "very_dense_fallback":
+        xs, mx = [torch.rand(300, 3, generator=gen) * 1.5 - 40.0, torch.rand(50, 3, generator=gen) * 2.0], 100
+    elif case == "sparse_far_apart":
+        xs = [torch.rand(40, 3, generator=gen) * 5000.0, torch.cat([torch.rand(20, 3, generator=gen) * 3.0,
+                                                                   torch.rand(20, 3, generator=gen) * 3.0 + 1.0e4])]
+    else:
+        xs = [torch.zeros(0, 3), torch.ones(1, 3) * 7.0, torch.ones(6, 3) * -2.5, torch.rand(9, 3, generator=gen)]
+    x = torch.cat(xs).float().contiguous()
+    ptr = torch.tensor(np.concatenate([[0], np.cumsum([v.shape[0] for v in xs])]), dtype=torch.int32)
+    r0, d0, c0 = ops.radius_csr(x.cuda(), ptr.cuda(), r, mx)
+    r1, d1, c1 = ops.cell_radius_csr(x.cuda(), ptr.cuda(), r, mx)
+    assert torch.equal(r0, r1) and torch.equal(d0, d1) and torch.equal(c0, c1), case
+    so, do = O.radius_edges(x, ptr.long(), r, mx)
+    dst = torch.repeat_interleave(torch.arange(x.shape[0]), d1.cpu().long())
+    s, d = canon(c1.cpu(), dst)
+    so, do = canon(so, do)
+    assert np.array_equal(s, so) and np.array_equal(d, do), case
+    # rows come out sorted by source index (the reference order of torch_cluster.radius_graph within a destination)
+    c = c1.cpu().numpy()
+    rp = r1.cpu().numpy()
+    assert all(np.all(np.diff(c[rp[i]:rp[i + 1]]) > 0) for i in range(x.shape[0]))
+
+
+def test_pp_graph_built_per_pocket_then_replicated(env, monkeypatch):
+    """GraphBatch builds the pp CSR once per DISTINCT pocket and replicates it per graph on the device
+    (protein_pharm_dataset.py:234-236 + copy_graph): identical, bit for bit, to the all-pairs build over the replicated
+    batch (PF_K1=brute), also when a graph_range cuts through a pocket's samples."""
+    pk = [env.make_pocket(n, seed=s) for n, s in ((400, 1), (37, 2), (1, 4), (250, 3))]
+    pockets = [env.Pocket.from_numpy(p, h) for p, h in pk]
+    sizes = [[3, 8, 5], [4], [3, 3], [5, 6, 7]]
+    for rng in (None, range(2, 8)):
+        g1 = env.GraphBatch.from_pockets(pockets, sizes, env.dev, graph_range=rng)
+        monkeypatch.setenv("PF_K1", "brute")
+        g0 = env.GraphBatch.from_pockets(pockets, sizes, env.dev, graph_range=rng)
+        monkeypatch.delenv("PF_K1")
+        for name in ("pp_rowptr", "pp_cnt", "pp_col", "pp_tiles", "pp_n_tiles"):
+            assert torch.equal(getattr(g0, name), getattr(g1, name)), (name, rng)
+        assert g0.n_pp_edges == g1.n_pp_edges and g0.pp_num_tiles == g1.pp_num_tiles
+
+
 def test_exclusive_scan(env):
     for n in (0, 1, 5, 2048, 2049, 100_003, 3_000_017):
         x = torch.randint(0, 20, (n,), dtype=torch.int32)
@@ -550,6 +602,214 @@ def test_full_reverse_diffusion_against_reference(env, golden):
     close(g.prot_x, d["final_prot"], rtol=1e-4, atol=1e-3, what="final prot frame")
     assert out[0].pos_frames.shape == (101, sizes[0], 3)
     assert out[0].to_xyz_file().splitlines()[0] == str(sizes[0])
+
+
+def _sample_multi_inputs(env, d):
+    pockets = [env.Pocket.from_numpy(*env.make_pocket(int(n), seed=int(s))) for n, s in d["pockets"]]
+    flat, n_pharms, i = d["n_pharms_flat"].tolist(), [], 0
+    for k in d["n_pharms_per_pocket"].tolist():
+        n_pharms.append(flat[i:i + k])
+        i += k
+    return pockets, n_pharms
+
+
+def test_sample_chunking_coms_and_frame_values_against_reference(env, golden):
+    """`PharmacophoreDiff.sample` (pharmacodiff.py:516-578) against the fixture written by the reference's own `sample`:
+    six graphs over three pockets, max_batch_size 4 (chunks of 4 + 2, the second one starting mid-pocket), an explicit
+    per-pocket init_pharm_com indexed per graph, regrouping per pocket, and the VALUES of the trajectory frames
+    (get_pos_feat_for_visual, :360-378: x_t shifted by init_prot_com - prot_com, h_t as is)."""
+    d = golden("sample_multi.npz")
+    pockets, n_pharms = _sample_multi_inputs(env, d)
+    out = env.model.sample(pockets, n_pharms, max_batch_size=int(d["max_batch_size"]),
+                           init_pharm_com=t(d["init_pharm_com"]), visualize_trajectory=True, noise=t(d["noise"]))
+    assert [len(o) for o in out] == d["n_pharms_per_pocket"].tolist()
+    ph = [p for o in out for p in o]
+    assert [p.n_ph_centers for p in ph] == d["n_pharms_flat"].tolist()
+    pos = torch.cat([p.pos_frames for p in ph], dim=1)
+    feat = torch.cat([p.feat_frames for p in ph], dim=1)
+    assert pos.shape == d["pos_frames"].shape and feat.shape == d["feat_frames"].shape
+    # frame 0 is the injected z_T moved to the input frame; the first frames are a few steps deep: the per-step bar
+    close(pos[:4], d["pos_frames"][:4], rtol=1e-4, atol=1e-4, what="first frames (pos)")
+    close(feat[:4], d["feat_frames"][:4], rtol=1e-4, atol=2e-5, what="first frames (feat)")
+    # 100 chained steps: the end-to-end bar of test_full_reverse_diffusion_against_reference
+    close(pos, d["pos_frames"], rtol=1e-3, atol=2e-3, what="all frames (pos)")
+    close(feat, d["feat_frames"], rtol=1e-3, atol=2e-3, what="all frames (feat)")
+    close(torch.cat([p.ph_coords for p in ph]), d["final_x"], rtol=1e-3, atol=2e-3, what="final x")
+    close(torch.cat([p.ph_feats for p in ph]), d["final_h"], rtol=1e-3, atol=2e-3, what="final h")
+    assert np.array_equal(torch.cat([p.ph_feats_idxs for p in ph]).numpy(), d["final_type"])
+    assert ph[0].to_xyz_file() == str(d["xyz_first"])            # writers: same text as the reference's
+    assert ph[0].traj_to_xyz().splitlines()[:5] == str(d["traj_xyz_first"]).splitlines()[:5]
+
+
+def test_sample_default_com_and_chunk_invariance(env):
+    """sample() without init_pharm_com uses each pocket's mean position (pharmacodiff.py:531-535); the result of a graph
+    does not depend on max_batch_size (bit-identical), checked against the oracle's sample_multi on a short run."""
+    specs = [(120, 41), (90, 42)]
+    n_pharms = [[3, 6, 4], [5, 8]]
+    pk = [env.make_pocket(n, seed=s) for n, s in specs]
+    pockets = [env.Pocket.from_numpy(p, h) for p, h in pk]
+    nf = sum(sum(s) for s in n_pharms)
+    noise = torch.randn(101, nf, 9, generator=torch.Generator().manual_seed(9))
+    res = {}
+    for mb in (2, 5, 32):
+        out = env.model.sample(pockets, n_pharms, max_batch_size=mb, noise=noise, n_steps=6)
+        res[mb] = (torch.cat([p.ph_coords for o in out for p in o]), torch.cat([p.ph_feats for o in out for p in o]))
+    for mb in (5, 32):
+        assert torch.equal(res[mb][0], res[2][0]) and torch.equal(res[mb][1], res[2][1]), mb
+    want = env.O.sample_multi(env.sd, [(t(p), t(h)) for p, h in pk], n_pharms, noise, 100, env.sd["gamma.gamma"],
+                              env.cfg, max_batch_size=2, steps=6)
+    close(res[2][0], torch.cat([p["x"] for o in want for p in o]), rtol=1e-4, atol=1e-4, what="x after 6 steps")
+    close(res[2][1], torch.cat([p["h"] for o in want for p in o]), rtol=1e-4, atol=2e-5, what="h after 6 steps")
+
+
+def test_configs2_shape_full_reverse_diffusion(env):
+    """BASELINE.json configs[2] shape through all 100 steps: a 1,500-atom pocket, pharmacophores of 16 and 3 centres.
+    Teacher-forced from the oracle's own trajectory at several steps (per-step bar 1e-4), then end to end."""
+    O, model = env.O, env.model
+    specs, sizes = [(1500, 61)], [[16, 3]]
+    g, b = env.build(specs, sizes)
+    noise = torch.randn(101, 19, 9, generator=torch.Generator().manual_seed(5))
+    rec = []
+    wx, wh, wt, wprot = O.sample(env.sd, b, noise, 100, env.sd["gamma.gamma"], env.cfg, record=rec)
+    st = model.dynamics.bind(g)
+    nx, nh = noise[:, :, 0:3].contiguous().cuda(), noise[:, :, 3:9].contiguous().cuda()
+    for i in (0, 25, 60, 99):
+        g.pharm_x.copy_(rec[i][0].cuda())
+        g.pharm_h.copy_(rec[i][1].cuda())
+        g.prot_x.copy_(rec[i][2].cuda())
+        model._run_steps(g, st, nx, nh, i, 1)
+        g.check_status()
+        close(g.pharm_x, rec[i + 1][0], rtol=1e-4, atol=2e-5, what=f"x step {i}")
+        close(g.pharm_h, rec[i + 1][1], rtol=1e-4, atol=2e-5, what=f"h step {i}")
+    g.prot_x.copy_(g.prot_x0)
+    x, h = model.sample_given_receptor(g, noise=noise, return_tensors=True)
+    close(x, wx, rtol=1e-3, atol=2e-3, what="final x")
+    close(h, wh, rtol=1e-3, atol=2e-3, what="final h")
+    assert torch.equal(h.argmax(dim=1).cpu(), wt)
+
+
+def test_bench_scale_batch_spot_check(env):
+    """The batch bench.py times (BASELINE.json configs[1]: 256 x 400-atom pockets x 30 samples = 7,680 graphs, 3.07 M
+    protein nodes, ~23 M pp edges): one teacher-forced reverse step at that scale, three graphs drawn at random compared
+    with the oracle run on each graph alone (graphs are independent, so the oracle needs only those three), and
+    bit-identity of the same three graphs against a small batch that contains only them."""
+    from pharmacoforge_b200.synthetic import readme_sizes
+    O, model = env.O, env.model
+    n_pockets, atoms = 256, 400
+    pk = [env.make_pocket(atoms, seed=i) for i in range(n_pockets)]
+    sizes = [readme_sizes(30)] * n_pockets
+    g = env.GraphBatch.from_pockets([env.Pocket.from_numpy(p, h) for p, h in pk], sizes, env.dev)
+    assert g.n_graphs == 7680 and g.n_prot == 7680 * atoms and g.n_pp_edges > 20_000_000
+    gen = torch.Generator().manual_seed(2024)
+    x = torch.randn(g.n_pharm, 3, generator=gen) * 3.0
+    h = torch.randn(g.n_pharm, 6, generator=gen)
+    noise = torch.randn(2, g.n_pharm, 9, generator=gen)
+    fptr, pptr = g.pharm_ptr_host.astype(np.int64), g.prot_ptr_host.astype(np.int64)
+    # sampler frame: every graph's protein centred on its pharmacophore + a small offset
+    com = torch.from_numpy(np.stack([p.mean(axis=0) for p, _ in pk])).float()
+    off = torch.randn(g.n_graphs, 3, generator=gen)
+    gi_of_prot = torch.repeat_interleave(torch.arange(g.n_graphs), atoms)
+    prot = g.prot_x0.cpu() - com[gi_of_prot // 30] + off[gi_of_prot]
+    st = model.dynamics.bind(g)
+    step = 57
+    g.pharm_x.copy_(x.cuda())
+    g.pharm_h.copy_(h.cuda())
+    g.prot_x.copy_(prot.cuda())
+    # _run_steps(first=step) reads noise row 1 + step: place the drawn row there
+    nx = torch.zeros(step + 2, g.n_pharm, 3, device=env.dev)
+    nh = torch.zeros(step + 2, g.n_pharm, 6, device=env.dev)
+    nx[step + 1], nh[step + 1] = noise[1, :, 0:3].cuda(), noise[1, :, 3:9].cuda()
+    model._run_steps(g, st, nx, nh, step, 1)
+    g.check_status()
+    gx, gh, gprot = g.pharm_x.cpu(), g.pharm_h.cpu(), g.prot_x.cpu()
+    for gidx in (3, 4097, 7679):
+        p = gidx // 30
+        fs, ps = slice(int(fptr[gidx]), int(fptr[gidx + 1])), slice(int(pptr[gidx]), int(pptr[gidx + 1]))
+        b = O.build_batch([(t(pk[p][0]), t(pk[p][1]))], [[sizes[p][gidx % 30]]])
+        b.prot_x, b.pharm_x, b.pharm_h = prot[ps].clone(), x[fs].clone(), h[fs].clone()
+        O.reverse_step(env.sd, b, 99 - step, 100, env.sd["gamma.gamma"], env.cfg, noise[1, fs, 0:3], noise[1, fs, 3:9])
+        close(gx[fs], b.pharm_x, rtol=1e-4, atol=2e-5, what=f"graph {gidx} x")
+        close(gh[fs], b.pharm_h, rtol=1e-4, atol=2e-5, what=f"graph {gidx} h")
+        close(gprot[ps], b.prot_x, rtol=1e-4, atol=1e-4, what=f"graph {gidx} prot frame")
+        # the same graph alone in a batch of one: bit-identical to its rows in the 7,680-graph batch
+        g1 = env.GraphBatch.from_pockets([env.Pocket.from_numpy(*pk[p])], [[sizes[p][gidx % 30]]], env.dev)
+        st1 = model.dynamics.bind(g1)
+        g1.pharm_x.copy_(x[fs].cuda())
+        g1.pharm_h.copy_(h[fs].cuda())
+        g1.prot_x.copy_(prot[ps].cuda())
+        model._run_steps(g1, st1, nx[:, fs].contiguous(), nh[:, fs].contiguous(), step, 1)
+        assert torch.equal(g1.pharm_x.cpu(), gx[fs]) and torch.equal(g1.pharm_h.cpu(), gh[fs]), gidx
+    del g, st
+    torch.cuda.empty_cache()
+
+
+def test_philox_noise_and_cuda_graph_loop(env):
+    """Throughput path (noise=None): in-kernel Philox noise keyed from torch's CUDA generator, and the whole T-step loop
+    replayed as one CUDA graph.  Draws are standard normal and independent across streams / steps; a run is reproducible
+    under torch.manual_seed; the graph replay is bit-identical to the eager enqueue; and one posterior step with Philox
+    noise equals the bit-exact injected-noise step fed with the same draws."""
+    ops, model = env.ops, env.model
+    seed = torch.tensor([123456789], dtype=torch.int64, device=env.dev)
+    n = 1 << 20
+    draws = {}
+    for key in ((0, 0), (1, 0), (0, 7)):
+        out = torch.empty(n, device=env.dev)
+        ops.philox_normal(out, seed, key[0], key[1])
+        draws[key] = out
+        assert abs(float(out.mean())) < 5e-3 and abs(float(out.var()) - 1.0) < 5e-3
+        assert abs(float((out ** 4).mean()) - 3.0) < 5e-2 and float(out.abs().max()) < 6.5
+    for a, b in (((0, 0), (1, 0)), ((0, 0), (0, 7))):
+        assert abs(float((draws[a] * draws[b]).mean())) < 5e-3          # streams / steps are uncorrelated
+    assert abs(float((draws[(0, 0)][1:] * draws[(0, 0)][:-1]).mean())) < 5e-3
+    out2 = torch.empty(1000, device=env.dev)
+    ops.philox_normal(out2, seed, 0, 0)
+    assert torch.equal(out2, draws[(0, 0)][:1000])                       # a pure function of (seed, stream, step, index)
+
+    g, b = env.build([(150, 3), (90, 4)], [[3, 5, 8], [6, 4]])
+    st = model.dynamics.bind(g)
+    # one Philox step == the injected-noise step with the same draws (the bit-exact posterior kernel)
+    x, h, prot = random_state(b, 13)
+    eps_x, eps_h = torch.randn(g.n_pharm, 3, device=env.dev), torch.randn(g.n_pharm, 6, device=env.dev)
+    nz_x, nz_h = torch.empty(g.n_pharm, 3, device=env.dev), torch.empty(g.n_pharm, 6, device=env.dev)
+    ops.philox_normal(nz_x, seed, 0, 5)
+    ops.philox_normal(nz_h, seed, 1, 5)
+    res = []
+    for philox in (False, True):
+        px, ph, pp = x.cuda().clone(), h.cuda().clone(), prot.cuda().clone()
+        if philox:
+            import ctypes as C
+            from pharmacoforge_b200 import _lib
+            L = _lib.load()
+            vp = lambda tt: C.c_void_p(tt.data_ptr())
+            _lib.check(L.pf_posterior_step_philox(vp(px), vp(ph), 6, vp(eps_x), vp(eps_h), vp(seed), 5, vp(g.pharm_ptr), vp(pp),
+                                                  vp(g.prot_ptr), g.n_graphs, 0.97, 0.11, 0.23,
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "philox step")
+        else:
+            ops.posterior_step(px, ph, eps_x, eps_h, nz_x, nz_h, g.pharm_ptr, pp, g.prot_ptr, 0.97, 0.11, 0.23)
+        res.append((px, ph, pp))
+    assert all(torch.equal(u, v) for u, v in zip(res[0], res[1]))
+
+    def run(graph):
+        model.use_cuda_graph = graph
+        torch.manual_seed(77)
+        g.prot_x.copy_(g.prot_x0)
+        xx, hh = model.sample_given_receptor(g, n_steps=12, return_tensors=True)
+        return xx.clone(), hh.clone()
+    try:
+        e1, e2 = run(False), run(False)
+        assert torch.equal(e1[0], e2[0]) and torch.equal(e1[1], e2[1])          # reproducible under manual_seed
+        g1 = run(True)                                                           # captures (the eager runs warmed up)
+        g2 = run(True)                                                           # replays
+        assert len(st.graphs) == 1
+        for r in (g1, g2):
+            assert torch.equal(r[0], e1[0]) and torch.equal(r[1], e1[1])
+        torch.manual_seed(78)
+        g.prot_x.copy_(g.prot_x0)
+        other = model.sample_given_receptor(g, n_steps=12, return_tensors=True)[0]
+        assert not torch.equal(other, e1[0])                                     # a new key gives a new trajectory
+        assert torch.isfinite(other).all()
+    finally:
+        model.use_cuda_graph = False
 
 
 # ------------------------------------------------------------------------------------------------ properties

@@ -101,3 +101,171 @@ def test_complementarity_matches_reference(golden):
     rfeat = torch.nn.functional.one_hot(torch.from_numpy(g["rt0"]), 6).float()
     v = pio.SampleAnalyzer().analyze([ph], [torch.from_numpy(g["rpos0"])], [rfeat])["validity"]
     assert abs(v - int(g["count0"]) / ph.n_ph_centers) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint / config I/O
+def _meta():
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "lightning_ckpt_meta.json")) as f:
+        return json.load(f)
+
+
+def _write_reference_run(tmp_path, sd, hyper_parameters, config, config_name="config.yaml"):
+    """A run directory as the reference's train.py leaves it: <run>/config.yaml + <run>/checkpoints/last.ckpt, the
+    checkpoint being the dict Lightning's ModelCheckpoint writes for the reference LightningModule."""
+    import torch
+    import yaml
+    run = tmp_path / "fancy-run_abc123"
+    (run / "checkpoints").mkdir(parents=True)
+    with open(run / config_name, "w") as f:
+        yaml.dump(config, f)
+    ckpt = {"epoch": 3, "global_step": 1234, "pytorch-lightning_version": "2.0.9",
+            "state_dict": {k: v.clone() for k, v in sd.items()}, "loops": {}, "callbacks": {},
+            "optimizer_states": [{"state": {}, "param_groups": [{"lr": 1e-4}]}], "lr_schedulers": [{}],
+            "hyper_parameters": hyper_parameters}
+    torch.save(ckpt, run / "checkpoints" / "last.ckpt")
+    return run
+
+
+def test_load_reference_format_run_directory(tmp_path, sd):
+    """generate_pharmacophores.py:231-269: config.yaml + checkpoints/last.ckpt whose `hyper_parameters` are what the
+    reference's own constructor saved (golden fixture written by oracle/make_golden_ckpt.py)."""
+    import torch
+    from pharmacoforge_b200.checkpoint import find_run_files, load_run
+    meta = _meta()
+    run = _write_reference_run(tmp_path, sd, meta["hyper_parameters"], meta["config"])
+    model, config = load_run(model_dir=run)
+    assert not model.training and config == meta["config"]
+    got = model.state_dict()
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    for k, v in meta["hyper_parameters"].items():
+        assert model.hparams[k] == v, k
+    assert model.n_timesteps == 100 and model.dynamics.pf_k == 5 and model.ph_type_map == meta["config"]["dataset"]["ph_type_map"]
+    # --ckpt form: run_dir = ckpt.parent.parent
+    cfg_file, model_file = find_run_files(ckpt=run / "checkpoints" / "last.ckpt")
+    assert cfg_file == run / "config.yaml" and model_file == run / "checkpoints" / "last.ckpt"
+    model2, _ = load_run(ckpt=run / "checkpoints" / "last.ckpt")
+    assert all(torch.equal(model2.state_dict()[k], sd[k]) for k in sd)
+
+
+def test_legacy_checkpoint_without_ph_type_map_retries(tmp_path, sd):
+    """Checkpoints trained before `ph_type_map` became a constructor argument: load_from_checkpoint raises TypeError, the
+    caller retries with the map from the config (generate_pharmacophores.py:264-268); config.yml is accepted too."""
+    import pytest
+    from pharmacoforge_b200.checkpoint import load_run
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    meta = _meta()
+    hp = {k: v for k, v in meta["hyper_parameters"].items() if k != "ph_type_map"}
+    run = _write_reference_run(tmp_path, sd, hp, meta["config"], config_name="config.yml")
+    with pytest.raises(TypeError):
+        PharmacophoreDiff.load_from_checkpoint(run / "checkpoints" / "last.ckpt")
+    model, _ = load_run(model_dir=run)
+    assert model.ph_type_map == meta["config"]["dataset"]["ph_type_map"]
+    (run / "config.yml").unlink()
+    with pytest.raises(FileNotFoundError):
+        load_run(model_dir=run)
+
+
+def test_from_config_and_run_dir_round_trip(tmp_path, sd):
+    """model_from_config (load_from_config.py:6-32) on the reference's dev.yml reproduces the hyper-parameters the
+    reference's constructor records; write_run_dir + save_checkpoint produce a directory load_run reads back."""
+    import torch
+    import yaml
+    from pharmacoforge_b200.checkpoint import load_run, write_run_dir
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    meta = _meta()
+    model = PharmacophoreDiff.from_config(meta["config"])
+    for k, v in meta["hyper_parameters"].items():
+        assert model.hparams[k] == v, k
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd)
+    run = write_run_dir(tmp_path / "runs", meta["config"], name="brisk-sun-7", run_id="x1y2z3")
+    assert run.name == "brisk-sun-7_x1y2z3" and (run / "checkpoints").is_dir()
+    written = yaml.safe_load(open(run / "config.yaml"))
+    assert written["resume"] == {"run_id": "x1y2z3"} and written["wandb"]["name"] == "brisk-sun-7"
+    assert written["dynamics"] == meta["config"]["dynamics"]
+    model.save_checkpoint(run / "checkpoints" / "last.ckpt", epoch=2, global_step=77)
+    raw = torch.load(run / "checkpoints" / "last.ckpt", weights_only=False)
+    assert {"state_dict", "hyper_parameters", "epoch", "global_step", "pytorch-lightning_version"} <= set(raw)
+    back, _ = load_run(model_dir=run)
+    assert all(torch.equal(back.state_dict()[k], sd[k]) for k in sd)
+
+
+def test_write_pharmacophore_file_matches_reference_text(tmp_path):
+    """utils/unorganized_utils.py:111-128 on the fixture input: same text, byte for byte."""
+    import torch
+    from pharmacoforge_b200.io import write_pharmacophore_file
+    w = _meta()["xyz_writer"]
+    coords = [torch.tensor(c) for c in w["coords"]]
+    assert write_pharmacophore_file(coords, w["types"], None) == w["text"]
+    write_pharmacophore_file(coords, w["types"], None, filename=tmp_path / "p.xyz")
+    assert (tmp_path / "p.xyz").read_text() == w["text"]
+
+
+def test_pocket_dgl_round_trip_over_the_dgl_shim(golden):
+    """Pocket.to_dgl / Pocket.from_dgl against the reference's graph layout (protein_pharm_dataset.py:210-266), run over
+    the pure-torch dgl stand-in of oracle/shims (dgl itself is not installable here): the pp edges equal the fixture
+    written by the reference's own build_initial_complex_graph."""
+    import os
+    import sys
+    import numpy as np
+    import torch
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    try:
+        from pharmacoforge_b200.batch import Pocket
+        from pharmacoforge_b200.synthetic import make_pocket
+        pos, onehot = make_pocket(400, seed=0)
+        p = Pocket.from_numpy(pos, onehot)
+        g = p.to_dgl({"pp": 3.5, "pf": 8, "fp": 8, "ff": 9})
+        assert set(g.ntypes) == {"prot", "pharm", "prot_ph"} and g.num_nodes("prot") == 400 and g.num_nodes("pharm") == 0
+        u, v = g.edges(form="uv", etype=("prot", "pp", "prot"))
+        order = np.lexsort((u.numpy(), v.numpy()))
+        gold = golden("pp_graph_n400_seed0.npz")
+        assert np.array_equal(u.numpy()[order], gold["src"]) and np.array_equal(v.numpy()[order], gold["dst"])
+        back = Pocket.from_dgl(g)
+        assert torch.equal(back.prot_x, p.prot_x) and torch.equal(back.prot_h, p.prot_h)
+    finally:
+        sys.path.remove(os.path.join(ROOT, "oracle", "shims"))
+        for m in [m for m in sys.modules if m == "dgl" or m.startswith("dgl.")]:
+            del sys.modules[m]
+
+
+def test_pdb_altloc_occupancy_hetero_and_mmcif(tmp_path):
+    """The hand-written PDB / mmCIF readers follow Bio.PDB's conventions (generate_pharmacophores.py:128-135): one atom
+    per (residue, name) -- the alternate location with the highest occupancy --, hetero residues keep their own residue
+    id (a standard amino acid stored as HETATM still counts, water and ligands do not), .mmcif is accepted."""
+    import numpy as np
+    from pharmacoforge_b200.io import pocket_from_pdb, read_mmcif_atoms, read_pdb_atoms
+
+    def atom(rec, serial, name, alt, res, chain, num, x, y, z, occ, el):
+        return f"{rec:<6}{serial:>5} {name:<4}{alt}{res:>3} {chain}{num:>4}    {x:>8.3f}{y:>8.3f}{z:>8.3f}{occ:>6.2f}{20.0:>6.2f}          {el:>2}\n"
+    pdb = (atom("ATOM", 1, "N", " ", "ALA", "A", 1, 0.0, 0.0, 0.0, 1.0, "N")
+           + atom("ATOM", 2, "CA", "A", "ALA", "A", 1, 1.0, 0.0, 0.0, 0.3, "C")
+           + atom("ATOM", 3, "CA", "B", "ALA", "A", 1, 1.5, 0.0, 0.0, 0.7, "C")
+           + atom("HETATM", 4, "CA", " ", "GLY", "A", 2, 3.0, 0.0, 0.0, 1.0, "C")
+           + atom("HETATM", 5, "O", " ", "HOH", "A", 3, 4.0, 0.0, 0.0, 1.0, "O")
+           + atom("ATOM", 6, "CA", " ", "LEU", "A", 9, 60.0, 0.0, 0.0, 1.0, "C"))
+    f = tmp_path / "rec.pdb"
+    f.write_text(pdb)
+    atoms = read_pdb_atoms(f)
+    assert [a["name"] for a in atoms] == ["N", "CA", "CA", "O", "CA"] and atoms[1]["altloc"] == "B"
+    els = ["C", "N", "O", "S"]
+    pocket, com = pocket_from_pdb(f, els, pocket_cutoff=8.0, lig_coords=np.array([[2.0, 0.0, 0.0]]))
+    assert pocket.prot_x.shape[0] == 3                      # ALA (N, CA alt B) + the HETATM glycine; water and far LEU out
+    assert np.allclose(pocket.prot_x.numpy()[1], [1.5, 0.0, 0.0])
+    # the same structure as mmCIF
+    head = ["group_PDB", "id", "type_symbol", "label_atom_id", "label_alt_id", "label_comp_id", "label_asym_id",
+            "label_seq_id", "pdbx_PDB_ins_code", "Cartn_x", "Cartn_y", "Cartn_z", "occupancy", "auth_seq_id",
+            "auth_asym_id", "pdbx_PDB_model_num"]
+    rows = ["ATOM 1 N N . ALA A 1 ? 0.0 0.0 0.0 1.0 1 A 1", "ATOM 2 C CA A ALA A 1 ? 1.0 0.0 0.0 0.3 1 A 1",
+            "ATOM 3 C CA B ALA A 1 ? 1.5 0.0 0.0 0.7 1 A 1", "HETATM 4 C CA . GLY A 2 ? 3.0 0.0 0.0 1.0 2 A 1",
+            "HETATM 5 O O . HOH A 3 ? 4.0 0.0 0.0 1.0 3 A 1", "ATOM 6 C CA . LEU A 9 ? 60.0 0.0 0.0 1.0 9 A 1"]
+    cif = tmp_path / "rec.mmcif"
+    cif.write_text("data_x\nloop_\n" + "".join(f"_atom_site.{h}\n" for h in head) + "\n".join(rows) + "\n#\n")
+    assert [(a["name"], a["altloc"], a["het"]) for a in read_mmcif_atoms(cif)] == \
+        [(a["name"], a["altloc"], a["het"]) for a in atoms]
+    pocket2, _ = pocket_from_pdb(cif, els, pocket_cutoff=8.0, lig_coords=np.array([[2.0, 0.0, 0.0]]))
+    assert np.array_equal(pocket2.prot_x.numpy(), pocket.prot_x.numpy())

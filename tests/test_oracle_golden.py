@@ -97,6 +97,33 @@ def test_full_reverse_diffusion(golden, sd, dyn_cfg):
     assert np.allclose(prot.numpy(), d["final_prot"], rtol=1e-4, atol=1e-3)
 
 
+def _sample_multi_inputs(d):
+    pockets = [tuple(t(a) for a in make_pocket(int(n), seed=int(s))) for n, s in d["pockets"]]
+    flat, n_pharms, i = d["n_pharms_flat"].tolist(), [], 0
+    for k in d["n_pharms_per_pocket"].tolist():
+        n_pharms.append(flat[i:i + k])
+        i += k
+    return pockets, n_pharms
+
+
+def test_sample_multi_and_trajectory_frames(golden, sd, dyn_cfg):
+    """The reference's own `PharmacophoreDiff.sample` (pharmacodiff.py:516-578) with max_batch_size chunking, an explicit
+    per-pocket init_pharm_com and visualize_trajectory=True: the oracle's restatement reproduces the final samples and
+    the VALUES of all 101 trajectory frames (get_pos_feat_for_visual, :360-378)."""
+    d = golden("sample_multi.npz")
+    pockets, n_pharms = _sample_multi_inputs(d)
+    out = O.sample_multi(sd, pockets, n_pharms, t(d["noise"]), 100, sd["gamma.gamma"], dyn_cfg,
+                         max_batch_size=int(d["max_batch_size"]), init_pharm_com=t(d["init_pharm_com"]), frames=True)
+    assert [len(o) for o in out] == d["n_pharms_per_pocket"].tolist()
+    ph = [p for o in out for p in o]
+    assert [p["x"].shape[0] for p in ph] == d["n_pharms_flat"].tolist()
+    assert np.allclose(torch.cat([p["x"] for p in ph]).numpy(), d["final_x"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(torch.cat([p["h"] for p in ph]).numpy(), d["final_h"], rtol=1e-4, atol=1e-4)
+    assert np.array_equal(torch.cat([p["type"] for p in ph]).numpy(), d["final_type"])
+    assert np.allclose(torch.cat([p["pos_frames"] for p in ph], 1).numpy(), d["pos_frames"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(torch.cat([p["feat_frames"] for p in ph], 1).numpy(), d["feat_frames"], rtol=1e-4, atol=1e-4)
+
+
 def test_forward_loss_matches_reference_forward(golden, sd, dyn_cfg):
     """oracle.forward_loss against PharmacophoreDiff.forward of the reference run with injected (t, eps)
     (oracle/make_golden_loss.py -> tests/golden/forward_loss.npz)."""
