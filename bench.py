@@ -46,16 +46,23 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--workload", default="configs[1]", choices=["configs[1]", "configs[2]"],
+    p.add_argument("--workload", default="configs[1]", choices=["configs[1]", "configs[2]", "configs[3]", "configs[4]"],
                    help="configs[1] (default, the headline): 256 x 400-atom pockets x 30 samples of sizes [3..8]x5.  "
                         "configs[2]: the large-pocket stress case, 1,500-atom pockets, sizes uniform 3..16, 512 graphs "
-                        "(32 pockets x 16 samples) per batch")
+                        "(32 pockets x 16 samples) per batch.  configs[3]: virtual-screen scale, --screen-pockets pockets "
+                        "(default 65,536) x 30 samples STRONG-sharded over the ranks by shard_ranges (balanced by pp "
+                        "edges), resident chunks of --pockets pockets, single-pass fp16 edge MLP, one final gather; one "
+                        "step = the whole screen.  configs[4]: the training step (delegates to bench_train.py)")
+    p.add_argument("--screen-pockets", type=int, default=65536, help="configs[3]: pockets in the whole screen")
+    p.add_argument("--no-cuda-graph", action="store_true", help="enqueue the T-step loop kernel by kernel")
     p.add_argument("--precision", default="fp32", choices=["fp32", "fp16"],
                    help="fp32: the parity mode (fp16 hi/lo split, 3 tensor passes; the headline).  fp16: the single-pass "
                         "reduced-precision edge-MLP path of configs[3] (tolerance 2e-2, tests/test_gpu_parity.py)")
     a = p.parse_args()
     if a.workload == "configs[2]":
         a.atoms, a.pockets, a.samples = 1500, 32, 16
+    if a.workload == "configs[3]" and "--precision" not in sys.argv:
+        a.precision = "fp16"
     return a
 
 
@@ -196,6 +203,99 @@ def run_reference(args, rank, world):
     print(json.dumps(line), file=_OUT, flush=True)
 
 
+def run_screen(args, model, dev, rank, world, dist):
+    """BASELINE.json configs[3]: a virtual-screen-sized job, STRONG scaling.  The whole screen (--screen-pockets pockets x
+    30 samples, pocket-major) is cut into contiguous graph ranges by `shard_ranges`, balanced by each pocket's pp edge
+    count; every rank walks its range in resident chunks of --pockets pockets through the public API (host pockets ->
+    make_batch -> sample_given_receptor) and the results meet in ONE final `gather_results`.  No collective on the path.
+    The pockets are 256 distinct synthetic pockets under random rigid motions (generating 65,536 rejection-sampled
+    pockets on the host would take longer than the screen); a rigid motion changes every coordinate, not the work."""
+    from pharmacoforge_b200 import ops
+    from pharmacoforge_b200.batch import Pocket
+    from pharmacoforge_b200.sharding import gather_results, shard_ranges
+    from pharmacoforge_b200.synthetic import make_pocket, readme_sizes
+    n_total, n_distinct, spp = args.screen_pockets, min(256, args.screen_pockets), args.samples
+    base = [make_pocket(args.atoms, seed=i) for i in range(n_distinct)]
+    # per-pocket cost proxy: its pp edge count (rigid motions preserve it), from the cell-list K1 on the distinct pockets
+    bx = torch.from_numpy(np.concatenate([b[0] for b in base])).to(dev)
+    bptr = torch.from_numpy(np.concatenate([[0], np.cumsum([b[0].shape[0] for b in base])]).astype(np.int32)).to(dev)
+    rowptr, _, _ = ops.cell_radius_csr(bx, bptr, CUT["pp"], 100)
+    e_base = (rowptr[bptr[1:].long()] - rowptr[bptr[:-1].long()]).cpu().numpy().astype(np.float64)
+    weights = e_base[np.arange(n_total) % n_distinct]
+    sizes_one = readme_sizes(spp)
+    sizes_all = [sizes_one] * n_total
+    my = shard_ranges(sizes_all, world, pocket_atoms=weights)[rank]
+    # this rank's pockets (a graph range may start / stop inside a pocket's samples)
+    p_lo, p_hi = my.start // spp, (my.stop + spp - 1) // spp if len(my) else my.start // spp
+
+    def pocket(i):
+        pos, onehot = base[i % n_distinct]
+        rng = np.random.default_rng(1_000_003 + i)
+        q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        c = pos.mean(axis=0, keepdims=True)
+        moved = (pos - c) @ q.astype(np.float32).T + c + rng.uniform(-20, 20, size=(1, 3)).astype(np.float32)
+        return Pocket.from_numpy(moved.astype(np.float32), onehot)
+    mine = [pocket(i) for i in range(p_lo, p_hi)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def screen():
+        out, h2d = [], 0
+        for c0 in range(p_lo, p_hi, args.pockets):
+            c1 = min(c0 + args.pockets, p_hi)
+            lo, hi = max(my.start, c0 * spp) - c0 * spp, min(my.stop, c1 * spp) - c0 * spp
+            gb = model.make_batch(mine[c0 - p_lo:c1 - p_lo], sizes_all[c0:c1], device=dev, graph_range=range(lo, hi))
+            x0, h0 = model.sample_given_receptor(gb, return_tensors=True)
+            out.append(torch.cat([x0, h0], dim=1))
+            h2d += gb.h2d_bytes
+        res = torch.cat(out) if out else torch.zeros(0, 9, device=dev)
+        parts = gather_results(res)                        # the one collective: rank 0 receives every rank's rows
+        host = [p.cpu() for p in parts] if parts is not None else None
+        return host, h2d, res.numel() * 4
+
+    for _ in range(min(args.warmup, 1)):                   # one warm-up pass over ONE chunk (kernels configured, pools grown)
+        gb = model.make_batch(mine[:min(len(mine), args.pockets)], sizes_all[:min(len(mine), args.pockets)], device=dev)
+        model.sample_given_receptor(gb, return_tensors=True)
+        del gb
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            host, h2d, d2h = screen()
+        e1.record()
+        barrier()
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    n_ph = n_total * spp
+    if rank == 0:
+        rows = sum(p.shape[0] for p in host)
+        assert rows == n_total * sum(sizes_one), (rows, n_total * sum(sizes_one))
+        value = n_ph * args.steps / (ms_total / 1e3)
+        line = {"metric": "pharmacophores/sec (full reverse diffusion)", "value": value, "unit": "pharmacophores/s",
+                "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 (single tensor pass, fp32 accumulate)" if args.precision == "fp16" else "f32", "data": "synthetic",
+                "config": {"workload": f"configs[3]: {n_total} pockets ({n_distinct} distinct synthetic {args.atoms}-atom pockets "
+                                       f"under random rigid motions) x {spp} samples (sizes [3..8]x5) = {n_ph} pharmacophores per "
+                                       f"step, split over {world} rank(s) by shard_ranges (balanced by pp edges), resident chunks "
+                                       f"of {args.pockets} pockets, dev.yml denoiser, T={T_STEPS}, device Philox noise",
+                           "graphs_rank0": len(my), "parallelism": f"graphs sharded x{world}, no collective on the path, one "
+                           "final gather", "l2": "inputs_exceed_l2 (2.2 GB of node features per chunk)"},
+                "e2e": {"value": value, "unit": "pharmacophores/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "api": "PharmacophoreDiff.make_batch + sample_given_receptor per chunk, gather_results + .cpu() at the "
+                               "end (this workload IS the end-to-end path: host pockets in, host results out)"},
+                "wall_s": wall, "clocks": clk.summary(), "roofline": None, "cpu_baseline": None, "gpu_launches": None}
+        print(json.dumps(line), file=_OUT, flush=True)
+
+
 def main():
     args = parse()
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner at init, library
@@ -210,6 +310,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    if args.workload == "configs[4]":     # the training step has its own harness (same JSON contract)
+        import bench_train
+        sys.argv = [sys.argv[0], "--gpus", str(args.gpus), "--steps", str(max(args.steps, 10)), "--warmup", str(args.warmup)]
+        os.dup2(_OUT.fileno(), 1)
+        return bench_train.main()
 
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
@@ -230,6 +336,13 @@ def main():
     model.load_state_dict(sd)
     model.eval()
     model.dynamics.edge_mlp_precision = args.precision
+    model.use_cuda_graph = not args.no_cuda_graph        # the resident loop replays as one captured CUDA graph
+    if args.workload == "configs[3]":
+        lib.pf_launch_count()
+        run_screen(args, model, dev, rank, world, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     pockets, sizes = workload(args, rank)
     n_graphs = args.pockets * args.samples
 
@@ -266,6 +379,9 @@ def main():
     # separate pass for the per-kernel numbers (CUDA-event pairs around every launch site, on the launching stream):
     # same workload, same state, immediately after the timed region
     n_prof = max(1, min(args.steps, 2))
+    graph_on = model.use_cuda_graph
+    model.use_cuda_graph = False      # event pairs are recorded at enqueue time: this pass enqueues kernel by kernel
+    launches_p0 = lib.pf_launch_count()
     _lib.check(lib.pf_profile_enable(n_prof * T_STEPS * 16 + 64), "pf_profile_enable")
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -276,6 +392,20 @@ def main():
     prof = _lib.profile_collect()
     _lib.check(lib.pf_profile_enable(0), "pf_profile_enable")
     ms_prof_total = e2.elapsed_time(e3)
+    launches_per_step = (lib.pf_launch_count() - launches_p0) // n_prof
+    if graph_on:   # a replayed graph launches the same kernels without passing through the library's launch counter
+        launches = launches_per_step * args.steps
+    # K1 on its own (once per batch, outside the loop): cell list over the distinct pockets + replication per graph
+    for _ in range(2):
+        g.build_pp_graph()
+    ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ek0.record()
+    for _ in range(5):
+        g.build_pp_graph()
+    ek1.record()
+    torch.cuda.synchronize()
+    k1_ms = ek0.elapsed_time(ek1) / 5
+    n_distinct_atoms = int(g._k1_inputs[0].shape[0])
     g.check_status()
     value = world * n_graphs * args.steps / (ms_total / 1e3)
     n_ff = int(g.ff_cnt.sum().item())
@@ -313,7 +443,14 @@ def main():
         return {"kernel": what, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                 "avg_launch_ms": ms_site / n_site, "algorithmic_bytes_per_launch": int(nbytes),
                 "share_of_step": ms_site / ms_prof_total}
-    other_rooflines = [r for r in (
+    k1_bytes = 12 * n_distinct_atoms + 4 * n_pp_edges + 8 * (n_prot + 1)
+    k1_line = {"kernel": "K1 pp graph: cell-list radius graph per distinct pocket (2 passes) + scan + replicate_csr; "
+                         "12 B per distinct atom read, 4 B per edge + 8 B per node written", "bound": "hbm",
+               "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+               "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / pk["hbm"], "avg_launch_ms": k1_ms,
+               "algorithmic_bytes_per_launch": int(k1_bytes), "share_of_step": k1_ms / (ms_prof_total / n_prof),
+               "note": "whole K1 sequence incl. two host syncs for the edge counts; runs once per batch, not per step"}
+    other_rooflines = [k1_line] + [r for r in (
         hbm_line("update_prot", 3 * 704 * n_prot, "node_update_tc_kernel (prot nodes): 3 x 704 B per node"),
         hbm_line("dyn_graph", 12 * (n_prot + n_pharm) + 4 * (2 * DYN["pf_k"] * n_pharm + 2 * n_ff),
                  "dyn_graph_kernel (ff radius + pf kNN + fp reverse): 12 B per node read, 4 B per edge written"),
@@ -322,7 +459,9 @@ def main():
 
     # ---------------- reported separately, never as `value`: exact dead-work elimination (bit-identical results;
     # the protein-side kernels of the last conv layer, whose outputs nothing reads, are not launched)
+    model.use_cuda_graph = graph_on
     model.dynamics.skip_dead_work = True
+    resident_step()
     resident_step()
     barrier()
     e0.record()
@@ -342,6 +481,7 @@ def main():
     f16 = None
     if args.precision == "fp32":
         model.dynamics.edge_mlp_precision = "fp16"
+        model.use_cuda_graph = False
         resident_step()
         barrier()
         _lib.check(lib.pf_profile_enable(args.steps * T_STEPS * 16 + 64), "pf_profile_enable")
@@ -353,6 +493,7 @@ def main():
         prof16 = _lib.profile_collect()
         _lib.check(lib.pf_profile_enable(0), "pf_profile_enable")
         model.dynamics.edge_mlp_precision = "fp32"
+        model.use_cuda_graph = graph_on
         ms16 = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms16, op=dist.ReduceOp.MAX)
@@ -409,7 +550,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pharmacophores/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
                     "api": "PharmacophoreDiff.make_batch + sample_given_receptor + gather + .cpu()"},
-            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "gpu_launches": int(launches), "cuda_graph": bool(graph_on), "clocks": clk.summary(),
             "kernel_timing_pass": {"steps": n_prof, "ms_per_step": ms_prof_total / n_prof,
                                    "note": "per-kernel CUDA-event pairs are recorded in a separate pass right after the "
                                            "timed region (which runs without them); shares are relative to this pass"}, "exact_dead_work_elimination": dce,

@@ -156,17 +156,8 @@ class GraphBatch:
         # with node offsets on the device -- what protein_pharm_dataset.py:234-236 (one radius_graph per pocket) +
         # copy_graph / dgl.batch (unorganized_utils.py:28-50) do.  PF_K1=brute: the all-pairs kernel over the
         # replicated batch (same CSR bit for bit; kept as the A/B reference of the tests).
-        if os.environ.get("PF_K1", "cell") == "brute" or B == 0:
-            self.pp_rowptr, self.pp_cnt, self.pp_col = ops.radius_csr(self.prot_x, self.prot_ptr, float(pp_cutoff),
-                                                                      int(pp_max_nbrs))
-        else:
-            pk_rowptr, _, pk_col = ops.cell_radius_csr(pk_x, pk_ptr, float(pp_cutoff), int(pp_max_nbrs))
-            node0 = g_pk_off.to(torch.int32)
-            graph_edges = (pk_rowptr[g_pk_off + counts] - pk_rowptr[g_pk_off]).to(torch.int32)
-            edge0 = ops.exclusive_scan(graph_edges)
-            n_edges = int(edge0[-1].item())
-            self.pp_rowptr, self.pp_cnt, self.pp_col = ops.replicate_csr(pk_rowptr, pk_col, node0, self.prot_ptr, edge0,
-                                                                         self.n_prot, n_edges)
+        self._k1_inputs = (pk_x, pk_ptr, g_pk_off, counts, float(pp_cutoff), int(pp_max_nbrs))
+        self.pp_rowptr, self.pp_cnt, self.pp_col = self.build_pp_graph()
         self.pp_start = self.pp_rowptr[:-1]
         self.n_pp_edges = int(self.pp_col.numel())
         self.pp_tiles = torch.empty(2 * max(self.n_prot + B, 1), dtype=torch.int32, device=dev)
@@ -219,6 +210,19 @@ class GraphBatch:
         self.pharm_x0 = x_0.to(self.device, torch.float32).contiguous()
         self.pharm_h0 = h_0.to(self.device, torch.float32).contiguous()
         return self
+
+    def build_pp_graph(self):
+        """K1 (see from_pockets): -> (rowptr [N+1], cnt [N], col [E]) of the batched static pp graph.  Re-runnable: bench.py
+        times it for the K1 roofline line."""
+        pk_x, pk_ptr, g_pk_off, counts, pp_cutoff, pp_max_nbrs = self._k1_inputs
+        if os.environ.get("PF_K1", "cell") == "brute" or self.n_graphs == 0:
+            return ops.radius_csr(self.prot_x, self.prot_ptr, pp_cutoff, pp_max_nbrs)
+        pk_rowptr, _, pk_col = ops.cell_radius_csr(pk_x, pk_ptr, pp_cutoff, pp_max_nbrs)
+        node0 = g_pk_off.to(torch.int32)
+        graph_edges = (pk_rowptr[g_pk_off + counts] - pk_rowptr[g_pk_off]).to(torch.int32)
+        edge0 = ops.exclusive_scan(graph_edges)
+        n_edges = int(edge0[-1].item())
+        return ops.replicate_csr(pk_rowptr, pk_col, node0, self.prot_ptr, edge0, self.n_prot, n_edges)
 
     def seed_arrays(self):
         """(seed_row [n_prot] int32, seed_rep [n_graphs * F] int32) for the first-layer seeding of the pp messages, or
