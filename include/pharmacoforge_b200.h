@@ -117,6 +117,14 @@ int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const float* phar
                  int32_t* ff_cnt, int32_t* ff_col, int32_t* pf_cnt, int32_t* pf_col, int32_t* fp_seg_dst,
                  int32_t* fp_seg_start, int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status, void* stream);
 
+/* The same with the ff edges taken from knn_graph(pharm x_t, k = ff_k) when ff_k > 0 (dynamics_gvp.py:193-194): per centre
+ * the ff_k + 1 nearest nodes of its graph INCLUDING itself, ordered by (distance, index), minus the self pair; stored in
+ * ascending source index in the same ff slots.  ff_k == 0 is pf_dyn_graph. */
+int pf_dyn_graph_ffk(const float* prot_x, const int32_t* prot_ptr, const float* pharm_x, const int32_t* pharm_ptr,
+                     int32_t n_graphs, float ff_r, int32_t ff_max_nbrs, int32_t ff_k, int32_t pf_k, const int32_t* ff_start,
+                     int32_t* ff_cnt, int32_t* ff_col, int32_t* pf_cnt, int32_t* pf_col, int32_t* fp_seg_dst,
+                     int32_t* fp_seg_start, int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status, void* stream);
+
 /* ---- tile planner --------------------------------------------------------------------------------
  * Greedily packs consecutive segments of each chunk [chunk_ptr[c], chunk_ptr[c+1]) into tiles of at
  * most tile_rows edges and tile_rows segments (PF_TILE_ROWS for the FFMA kernels, PF_TC_TILE_ROWS for tcgen05).  tiles[2*t], tiles[2*t+1] = first / one-past-last
@@ -295,6 +303,7 @@ typedef struct PfSampleArgs {
    * a captured CUDA graph replays with a new seed), loop iteration i draws with step number noise_step0 + i. */
   const uint64_t* noise_seed;
   int32_t noise_step0;
+  int32_t ff_k; /* > 0: ff edges are the kNN graph of the pharmacophore nodes (pf_dyn_graph_ffk) instead of the radius graph */
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph

@@ -122,6 +122,29 @@ def knn_edges(prot_x, prot_ptr, pharm_x, pharm_ptr, k: int):
     return torch.cat(qs), torch.cat(cs)
 
 
+def knn_graph_edges(x: torch.Tensor, ptr: torch.Tensor, k: int):
+    """knn_graph(x, k, batch) of torch_cluster (dynamics_gvp.py:194): per centre the k + 1 nearest nodes of its graph
+    INCLUDING itself, ordered by (distance, index) (stable sort), with the self pair dropped.  Returns (src = neighbour,
+    dst = centre) int64."""
+    srcs, dsts = [], []
+    for g in range(ptr.numel() - 1):
+        a, b = int(ptr[g]), int(ptr[g + 1])
+        if b - a < 2:
+            continue
+        d = _sqdist(x[a:b], x[a:b])
+        kk = min(k + 1, b - a)
+        order = torch.sort(d, dim=1, stable=True).indices[:, :kk]
+        ci = torch.arange(b - a)[:, None].expand(-1, kk).reshape(-1)
+        ni = order.reshape(-1)
+        m = ci != ni
+        dsts.append(ci[m] + a)
+        srcs.append(ni[m] + a)
+    if not srcs:
+        z = torch.zeros(0, dtype=torch.int64)
+        return z, z.clone()
+    return torch.cat(srcs), torch.cat(dsts)
+
+
 def batch_index(ptr: torch.Tensor) -> torch.Tensor:
     """unorganized_utils.py:83-95: arange(B).repeat_interleave(nodes per graph)."""
     return torch.arange(ptr.numel() - 1).repeat_interleave(ptr[1:] - ptr[:-1])
@@ -275,9 +298,12 @@ def build_batch(pockets: List[Tuple[torch.Tensor, torch.Tensor]], sizes: List[Li
     return FlatBatch(torch.cat(px), torch.cat(ph), torch.tensor(pptr), torch.tensor(fptr), torch.cat(es), torch.cat(ed))
 
 
-def dynamic_edges(b: FlatBatch, ff_cutoff: float = 9.0, pf_k: int = 5):
-    """dynamics_gvp.py:187-215 for dev.yml (ff_k=0 -> radius; pf_k>0 -> kNN, fp = reverse of pf)."""
-    ff_src, ff_dst = radius_edges(b.pharm_x, b.pharm_ptr, ff_cutoff, 200)
+def dynamic_edges(b: FlatBatch, ff_cutoff: float = 9.0, pf_k: int = 5, ff_k: int = 0):
+    """dynamics_gvp.py:187-215 (ff_k=0 -> radius, ff_k>0 -> kNN graph; pf_k>0 -> kNN, fp = reverse of pf)."""
+    if ff_k > 0:
+        ff_src, ff_dst = knn_graph_edges(b.pharm_x, b.pharm_ptr, ff_k)
+    else:
+        ff_src, ff_dst = radius_edges(b.pharm_x, b.pharm_ptr, ff_cutoff, 200)
     q, c = knn_edges(b.prot_x, b.prot_ptr, b.pharm_x, b.pharm_ptr, pf_k)
     return {"ff": (ff_src, ff_dst), "pf": (c, q), "fp": (q, c), "pp": b.pp}
 
@@ -289,7 +315,7 @@ def denoiser(sd, b: FlatBatch, t: torch.Tensor, cfg: dict, prefix: str = "dynami
     h_p = encoder(sd, f"{prefix}.prot_encoder", b.prot_h, t[b.prot_b])
     feats = {"pharm": (h_f, b.pharm_x, torch.zeros(h_f.shape[0], vs, 3)),
              "prot": (h_p, b.prot_x, torch.zeros(h_p.shape[0], vs, 3))}
-    edges = dynamic_edges(b, cfg["graph_cutoffs"]["ff"], cfg.get("pf_k", 5))
+    edges = dynamic_edges(b, cfg["graph_cutoffs"]["ff"], cfg.get("pf_k", 5), cfg.get("ff_k", 0))
     if trace is not None:
         trace["edges"] = edges
         trace["enc"] = {k: v[0] for k, v in feats.items()}

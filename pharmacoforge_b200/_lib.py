@@ -32,6 +32,8 @@ SIGNATURES = {
     "pf_replicate_csr": (C.c_int, [c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int32, c_i32p, c_i32p, c_i32p, STREAM]),
     "pf_dyn_graph": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, c_i32p,
                                c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
+    "pf_dyn_graph_ffk": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                   c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
     "pf_tc_msg_blob_bytes": (C.c_size_t, []),
@@ -128,7 +130,7 @@ class PfSampleArgs(C.Structure):
         ("dev_status", C.c_void_p),
         ("flags", C.c_uint32),
         ("seed_row", C.c_void_p), ("seed_rep", C.c_void_p), ("seed_table", C.c_void_p), ("n_seed_rows", C.c_int32),
-        ("noise_seed", C.c_void_p), ("noise_step0", C.c_int32),
+        ("noise_seed", C.c_void_p), ("noise_step0", C.c_int32), ("ff_k", C.c_int32),
     ]
 
 

@@ -338,7 +338,7 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_CHECK_ARG(a->n_convs >= 1 && a->n_convs <= 8, "pf_denoiser: n_convs out of range (1..8)");
   // graph of this step: ff radius + pf kNN + fp reverse (dynamics_gvp.py:176-177)
   prof_begin(kSiteGraph, as_stream(stream));
-  PF_TRY(pf_dyn_graph(a->prot_x, a->prot_ptr, a->pharm_x, a->pharm_ptr, a->n_graphs, a->ff_r, a->ff_max_nbrs, a->pf_k,
+  PF_TRY(pf_dyn_graph_ffk(a->prot_x, a->prot_ptr, a->pharm_x, a->pharm_ptr, a->n_graphs, a->ff_r, a->ff_max_nbrs, a->ff_k, a->pf_k,
                       a->ff_start, a->ff_cnt, a->ff_col, a->pf_cnt, a->pf_col, a->fp_seg_dst, a->fp_seg_start,
                       a->fp_seg_cnt, a->fp_col, a->dev_status, stream));
   prof_end(kSiteGraph, as_stream(stream));

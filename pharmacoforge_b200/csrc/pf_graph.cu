@@ -380,6 +380,7 @@ struct DynGraphParams {
   int n_graphs;
   float ff_r2;
   int ff_max, k;
+  int ff_k;  // > 0: ff edges from knn_graph(pharm x_t, k = ff_k) instead of the radius graph (dynamics_gvp.py:193-194)
   const int* ff_start;
   int *ff_cnt, *ff_col, *pf_cnt, *pf_col, *fp_seg_dst, *fp_seg_start, *fp_seg_cnt, *fp_col;
   unsigned* status;
@@ -477,9 +478,48 @@ __global__ void __launch_bounds__(kDynThreads) dyn_graph_kernel(const DynGraphPa
       }
       if (lane == 0) p.pf_cnt[fa + i] = kk;
 
-      // ---- ff: radius_graph(pharm x_t, r, max) (dynamics_gvp.py:196); centre i, neighbours ascending
       int rank_run = 0, kept_run = 0;
       const int out0 = p.ff_start[fa + i];
+      if (p.ff_k > 0) {
+        // ---- ff: knn_graph(pharm x_t, k = ff_k) (dynamics_gvp.py:194) = the ff_k + 1 nearest nodes INCLUDING the centre,
+        // ordered by (distance, index), then the self pair is dropped.  nf <= 128: four candidates per lane; the key
+        // (distance bits, index) is unique, so each round of the warp-wide minimum selects exactly one candidate.
+        unsigned long long key[kMaxF / 32];
+        unsigned sel = 0;
+#pragma unroll
+        for (int t = 0; t < kMaxF / 32; ++t) {
+          const int j = lane + 32 * t;
+          key[t] = j < nf ? (((unsigned long long)__float_as_uint(sqdist3(qx, qy, qz, fx[j], fy[j], fz[j])) << 32) | (unsigned)j)
+                          : ~0ull;
+        }
+        const int take = p.ff_k + 1 < nf ? p.ff_k + 1 : nf;
+        for (int r = 0; r < take; ++r) {
+          unsigned long long mine = ~0ull;
+#pragma unroll
+          for (int t = 0; t < kMaxF / 32; ++t)
+            if (!(sel & (1u << t)) && key[t] < mine) mine = key[t];
+          unsigned long long best = mine;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = shfl_xor_u64(best, o);
+            best = other < best ? other : best;
+          }
+          if (mine == best && best != ~0ull) {
+#pragma unroll
+            for (int t = 0; t < kMaxF / 32; ++t)
+              if (key[t] == best) sel |= 1u << t;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < kMaxF / 32; ++t) {   // neighbours in ascending index
+          const int j = lane + 32 * t;
+          const bool keep = (sel & (1u << t)) && j != i;
+          const unsigned kb = __ballot_sync(0xffffffffu, keep);
+          if (keep) p.ff_col[out0 + kept_run + __popc(kb & ((1u << lane) - 1u))] = fa + j;
+          kept_run += __popc(kb);
+        }
+      } else
+      // ---- ff: radius_graph(pharm x_t, r, max) (dynamics_gvp.py:196); centre i, neighbours ascending
       for (int j0 = 0; j0 < nf; j0 += 32) {
         const int j = j0 + lane;
         const bool hit = j < nf && sqdist3(qx, qy, qz, fx[j < nf ? j : 0], fy[j < nf ? j : 0], fz[j < nf ? j : 0]) < p.ff_r2;
@@ -697,6 +737,16 @@ extern "C" int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const 
                             int32_t pf_k, const int32_t* ff_start, int32_t* ff_cnt, int32_t* ff_col,
                             int32_t* pf_cnt, int32_t* pf_col, int32_t* fp_seg_dst, int32_t* fp_seg_start,
                             int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status, void* stream) {
+  return pf_dyn_graph_ffk(prot_x, prot_ptr, pharm_x, pharm_ptr, n_graphs, ff_r, ff_max_nbrs, 0, pf_k, ff_start, ff_cnt,
+                          ff_col, pf_cnt, pf_col, fp_seg_dst, fp_seg_start, fp_seg_cnt, fp_col, dev_status, stream);
+}
+
+extern "C" int pf_dyn_graph_ffk(const float* prot_x, const int32_t* prot_ptr, const float* pharm_x,
+                                const int32_t* pharm_ptr, int32_t n_graphs, float ff_r, int32_t ff_max_nbrs, int32_t ff_k,
+                                int32_t pf_k, const int32_t* ff_start, int32_t* ff_cnt, int32_t* ff_col,
+                                int32_t* pf_cnt, int32_t* pf_col, int32_t* fp_seg_dst, int32_t* fp_seg_start,
+                                int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status, void* stream) {
+  PF_CHECK_ARG(ff_k >= 0, "pf_dyn_graph: ff_k < 0");
   PF_CHECK_ARG(prot_x && prot_ptr && pharm_x && pharm_ptr && ff_start && ff_cnt && ff_col && pf_cnt && pf_col &&
                    fp_seg_dst && fp_seg_start && fp_seg_cnt && fp_col && dev_status,
                "pf_dyn_graph: null pointer");
@@ -706,8 +756,8 @@ extern "C" int pf_dyn_graph(const float* prot_x, const int32_t* prot_ptr, const 
     return PF_ERR_UNSUPPORTED;
   }
   if (n_graphs <= 0) return PF_OK;
-  DynGraphParams p{prot_x,  pharm_x, prot_ptr, pharm_ptr, n_graphs,   ff_r * ff_r,  ff_max_nbrs, pf_k,  ff_start,
-                   ff_cnt,  ff_col,  pf_cnt,   pf_col,    fp_seg_dst, fp_seg_start, fp_seg_cnt,  fp_col, dev_status};
+  DynGraphParams p{prot_x, pharm_x, prot_ptr, pharm_ptr,  n_graphs,     ff_r * ff_r, ff_max_nbrs, pf_k,      ff_k, ff_start,
+                   ff_cnt, ff_col,  pf_cnt,   pf_col,     fp_seg_dst,   fp_seg_start, fp_seg_cnt, fp_col, dev_status};
   const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
   if (pf_k <= 8)
     dyn_graph_kernel<8><<<grid, kDynThreads, 0, as_stream(stream)>>>(p);

@@ -137,6 +137,7 @@ class _DeviceState:
         a.n_prot_feats, a.n_pharm_feats = dyn.n_prot_scalars, dyn.n_pharm_scalars
         a.n_convs, a.n_msg_gvps, a.n_upd_gvps, a.n_noise_gvps = dyn.n_convs, dyn.n_message_gvps, dyn.n_update_gvps, dyn.n_noise_gvps
         a.pf_k, a.ff_max_nbrs, a.ff_r = g.pf_k, g.ff_max_nbrs, float(dyn.graph_cutoffs["ff"])
+        a.ff_k = int(dyn.ff_k)
         for name in ("prot_x", "prot_feats", "prot_ptr", "pharm_x", "pharm_h", "pharm_ptr", "pp_start", "pp_cnt",
                      "pp_col", "pp_tiles", "pp_n_tiles", "ff_start", "ff_cnt", "ff_col", "pf_start", "pf_cnt",
                      "pf_col", "fp_seg_dst", "fp_seg_start", "fp_seg_cnt", "fp_col", "pharm_chunk_ptr",
@@ -197,8 +198,12 @@ class PharmRecDynamicsGVP(nn.Module):
                                       "(configs/dev.yml); other widths need a rebuild with new tile constants")
         if message_norm != "mean":
             raise NotImplementedError("only message_norm='mean' (configs/dev.yml) is built")
-        if ff_k != 0 or pf_k <= 0:
-            raise NotImplementedError("only the dev.yml graph (ff radius graph, pf kNN with pf_k>0) is built")
+        if pf_k <= 0:
+            raise NotImplementedError("pf_k == 0 (pf / fp edges from radius(pharm, prot, r=8), dynamics_gvp.py:211) is not "
+                                      "built: a pharmacophore centre then has ~120 in-edges at the default cutoff, more than "
+                                      "one 128-row tile of the edge kernels holds; configs/dev.yml uses pf_k = 5")
+        if ff_k < 0:
+            raise ValueError("ff_k must be >= 0")
         if act_fn is not nn.SiLU:
             raise NotImplementedError("only SiLU is built")
         self.graph_cutoffs = graph_cutoffs

@@ -166,10 +166,11 @@ def dyn_graph(prot_x: torch.Tensor, prot_ptr: torch.Tensor, pharm_x: torch.Tenso
               ff_r: float, ff_max_nbrs: int, pf_k: int, ff_start: torch.Tensor, ff_cnt: torch.Tensor,
               ff_col: torch.Tensor, pf_cnt: torch.Tensor, pf_col: torch.Tensor, fp_seg_dst: torch.Tensor,
               fp_seg_start: torch.Tensor, fp_seg_cnt: torch.Tensor, fp_col: torch.Tensor,
-              status: torch.Tensor) -> None:
-    _lib.check(_L.pf_dyn_graph(_f(prot_x), _i(prot_ptr), _f(pharm_x), _i(pharm_ptr), prot_ptr.numel() - 1, ff_r,
-                               ff_max_nbrs, pf_k, _i(ff_start), _i(ff_cnt), _i(ff_col), _i(pf_cnt), _i(pf_col),
-                               _i(fp_seg_dst), _i(fp_seg_start), _i(fp_seg_cnt), _i(fp_col), _p(status), _s()),
+              status: torch.Tensor, ff_k: int = 0) -> None:
+    """K2.  ff_k > 0: ff edges = knn_graph(pharm x_t, k = ff_k) (dynamics_gvp.py:194) instead of the radius graph."""
+    _lib.check(_L.pf_dyn_graph_ffk(_f(prot_x), _i(prot_ptr), _f(pharm_x), _i(pharm_ptr), prot_ptr.numel() - 1, ff_r,
+                                   ff_max_nbrs, ff_k, pf_k, _i(ff_start), _i(ff_cnt), _i(ff_col), _i(pf_cnt), _i(pf_col),
+                                   _i(fp_seg_dst), _i(fp_seg_start), _i(fp_seg_cnt), _i(fp_col), _p(status), _s()),
                "pf_dyn_graph")
 
 

@@ -4,7 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from pharmacoforge_b200 import ops, _lib
 from pharmacoforge_b200.batch import GraphBatch, Pocket
-from pharmacoforge_b200.diffusion import PharmacophoreDiff, polynomial_gamma
+from pharmacoforge_b200.diffusion import PharmacophoreDiff
+from pharmacoforge_b200.hostutil import polynomial_gamma
 from pharmacoforge_b200.synthetic import make_pocket, synth_state_dict, readme_sizes
 layout = json.load(open(os.path.join(ROOT, "tests/golden/state_dict_layout.json")))
 sd = synth_state_dict(layout, seed=0); sd["gamma.gamma"] = polynomial_gamma(100, 1e-5, 2.0)
@@ -29,9 +30,23 @@ for v in (None, prot_v):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(v); e1.record(); torch.cuda.synchronize()
     print("HAS_V", v is not None, "edges", g.n_pp_edges, "tiles", int(g.pp_n_tiles), "ms", e0.elapsed_time(e1))
+MODE = sys.argv[4] if len(sys.argv) > 4 else "l1"      # l1: general kernel with vectors; seed: seeded first-layer kernel
+seed_row, seed_rep = g.seed_arrays()
+table = torch.randn(seed_rep.numel(), 128, device=dev)
+blob0 = W.tc[3 * W.tc_stride:4 * W.tc_stride]
+def run_seed():
+    ops.edge_conv_tc_seeded(seed_row, table, g.prot_x, g.prot_x, g.pp_start, g.pp_cnt, None, g.pp_col, g.pp_tiles, g.pp_n_tiles, blob0, agg_h, agg_v, False, FP16)
+run_seed(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run_seed(); e1.record(); torch.cuda.synchronize()
+print("SEEDED edges", g.n_pp_edges, "ms", e0.elapsed_time(e1))
 tr = torch.zeros((4 * 4096 + 148) * 2, dtype=torch.int64, device=dev)
 lib.pf_tc_trace(C.c_void_p(tr.data_ptr()))
-run(prot_v); torch.cuda.synchronize()
+if MODE == "seed":
+    run_seed()
+else:
+    run(prot_v)
+torch.cuda.synchronize()
 lib.pf_tc_trace(None)
 cta = tr.cpu().numpy()[4 * 4096 * 2:].reshape(148, 2)
 t = tr.cpu().numpy()[:4 * 4096 * 2].reshape(4, 4096, 2)

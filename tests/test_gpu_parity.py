@@ -224,6 +224,52 @@ def test_dynamic_graph_bit_exact(env, spread):
     assert np.array_equal(got["pf"][0].cpu().numpy(), c.numpy()) and np.array_equal(got["pf"][1].cpu().numpy(), q.numpy())
 
 
+@pytest.mark.parametrize("ff_k", [1, 3, 20])
+def test_ff_knn_graph_variant_bit_exact(env, ff_k):
+    """dynamics.ff_k > 0 (dynamics_gvp.py:193-194): ff edges = knn_graph(pharm x_t, k = ff_k).  Edge list bit-exact against the
+    oracle (graphs smaller than k + 1 keep all their other nodes; single-node graphs have no edge), pf / fp unchanged."""
+    g, b = env.build([(400, 0), (60, 7), (3, 9), (30, 2)], [[3, 4, 5, 6, 7, 8], [16, 1], [4], [2, 12]])
+    x, h, prot = random_state(b, 11, 2.0)
+    x[5] = x[4]                                   # coincident centres: the (distance, index) tie rule
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    env.ops.dyn_graph(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, 9.0, 200, 5, g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt,
+                      g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt, g.fp_col, g.status, ff_k)
+    g.check_status()
+    want = env.O.dynamic_edges(b, 9.0, 5, ff_k)
+    got = g.dynamic_edges()
+    for et in ("ff", "pf", "fp"):
+        s, d = canon(*got[et])
+        so, do = canon(*want[et])
+        assert np.array_equal(s, so) and np.array_equal(d, do), et
+    nf = np.diff(g.pharm_ptr_host)
+    assert got["ff"][0].numel() == int(sum(n * min(ff_k, n - 1) for n in nf))
+
+
+def test_denoiser_with_ff_knn_graph(env):
+    """The whole denoiser under dynamics_config ff_k = 4 against the oracle with the same switch."""
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    cfg = dict(env.cfg, ff_k=4)
+    gcut = cfg.pop("graph_cutoffs")
+    model = PharmacophoreDiff(6, 11, list("abcdef"), n_timesteps=100, graph_config={"graph_cutoffs": gcut},
+                              dynamics_config=cfg, precision=1e-5)
+    model.load_state_dict(env.sd, strict=True)
+    model.eval()
+    g, b = env.build([(300, 5), (120, 6)], [[8, 3, 6], [5, 7]])
+    x, h, prot = random_state(b, 23, 3.0)
+    g.pharm_h = h.cuda().clone()
+    g.pharm_x.copy_(x.cuda())
+    g.prot_x.copy_(prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    tt = torch.tensor([0.2, 0.2, 0.9, 0.5, 0.61])
+    wh, wx = env.O.denoiser(env.sd, b, tt, dict(cfg, graph_cutoffs=gcut))
+    gh, gx = model.dynamics(g, tt, None)
+    close(gh, wh, what="eps_h (ff kNN)")
+    close(gx, wx, what="eps_x (ff kNN)")
+    wh0, _ = env.O.denoiser(env.sd, b, tt, env.cfg)
+    assert float((wh - wh0).abs().max()) > 1e-3      # the switch changes the graph, hence the prediction
+
+
 def test_knn_ties_prefer_lower_index(env):
     # duplicate protein atoms -> exact distance ties
     O = env.O
