@@ -134,6 +134,15 @@ int pf_plan_tiles(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_ch
                   int32_t tile_rows, int32_t* tiles, int32_t max_tiles, int32_t* n_tiles, uint32_t* dev_status,
                   void* stream);
 int pf_zero_i32(int32_t* p, int64_t n, void* stream);
+/* The same plan with the tiles in CHUNK ORDER (a chunk's tiles contiguous, chunks ascending), for the static pp plan: the
+ * persistent kernels process consecutive tiles concurrently, so the source rows of a graph are fetched from DRAM once and
+ * reused from L2.  Two passes around a caller-side exclusive scan: pf_plan_tiles_count writes the number of tiles of every
+ * chunk; pf_plan_tiles_fill writes tiles[2*(chunk_tile_off[c] + i)] and *n_tiles (chunk_tile_off = exclusive scan). */
+int pf_plan_tiles_count(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_chunks, int32_t skip_empty,
+                        int32_t tile_rows, int32_t* chunk_tiles, uint32_t* dev_status, void* stream);
+int pf_plan_tiles_fill(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_chunks, int32_t skip_empty,
+                       int32_t tile_rows, const int32_t* chunk_tile_off, int32_t* tiles, int32_t max_tiles,
+                       int32_t* n_tiles, uint32_t* dev_status, void* stream);
 
 /* ---- K0: time-conditioned scalar encoders --------------------------------------------------------
  * h[n] = LayerNorm(SiLU(W [feats[n], t[graph(n)]] + b)) (dynamics_gvp.py:107-117,143-151).

@@ -36,6 +36,9 @@ SIGNATURES = {
                                    c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
+    "pf_plan_tiles_count": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_void_p, STREAM]),
+    "pf_plan_tiles_fill": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p,
+                                     C.c_void_p, STREAM]),
     "pf_tc_msg_blob_bytes": (C.c_size_t, []),
     "pf_tc_trace": (C.c_int, [C.c_void_p]),
     "pf_tc_upd_blob_bytes": (C.c_size_t, []),

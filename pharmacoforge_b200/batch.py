@@ -162,7 +162,9 @@ class GraphBatch:
         self.n_pp_edges = int(self.pp_col.numel())
         self.pp_tiles = torch.empty(2 * max(self.n_prot + B, 1), dtype=torch.int32, device=dev)
         self.pp_n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
-        ops.plan_tiles(self.pp_cnt, self.prot_ptr, False, self.tile_rows, self.pp_tiles, self.pp_n_tiles, self.status)
+        # tiles in graph order (PF_PP_PLAN=atomic: the unordered planner, the A/B switch of the L2-reuse measurement)
+        plan = ops.plan_tiles if os.environ.get("PF_PP_PLAN", "ordered") == "atomic" else ops.plan_tiles_ordered
+        plan(self.pp_cnt, self.prot_ptr, False, self.tile_rows, self.pp_tiles, self.pp_n_tiles, self.status)
         self.pp_num_tiles = int(self.pp_n_tiles.item())
         self.check_status()   # e.g. PF_DEV_DEGREE_OVERFLOW: a pp in-degree above the tile capacity, reported now
         self.pp_tiles = self.pp_tiles[:2 * max(self.pp_num_tiles, 1)].clone()

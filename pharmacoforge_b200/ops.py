@@ -182,6 +182,20 @@ def plan_tiles(seg_cnt: torch.Tensor, chunk_ptr: torch.Tensor, skip_empty: bool,
                                 _i(tiles), tiles.numel() // 2, _i(n_tiles), _p(status), _s()), "pf_plan_tiles")
 
 
+@torch.library.custom_op(f"{NS}::plan_tiles_ordered", mutates_args=("tiles", "n_tiles", "status"))
+def plan_tiles_ordered(seg_cnt: torch.Tensor, chunk_ptr: torch.Tensor, skip_empty: bool, tile_rows: int,
+                       tiles: torch.Tensor, n_tiles: torch.Tensor, status: torch.Tensor) -> None:
+    """plan_tiles with the tile list in chunk (graph) order: count per chunk, exclusive scan, fill (static plans)."""
+    n_chunks = chunk_ptr.numel() - 1
+    per_chunk = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=seg_cnt.device)
+    _lib.check(_L.pf_plan_tiles_count(_i(seg_cnt), _i(chunk_ptr), n_chunks, int(skip_empty), tile_rows, _i(per_chunk),
+                                      _p(status), _s()), "pf_plan_tiles_count")
+    off = exclusive_scan(per_chunk[:n_chunks])
+    _lib.check(_L.pf_zero_i32(_i(n_tiles), 1, _s()), "pf_zero_i32")
+    _lib.check(_L.pf_plan_tiles_fill(_i(seg_cnt), _i(chunk_ptr), n_chunks, int(skip_empty), tile_rows, _i(off), _i(tiles),
+                                     tiles.numel() // 2, _i(n_tiles), _p(status), _s()), "pf_plan_tiles_fill")
+
+
 # ------------------------------------------------------------------------------------------------ compute
 @torch.library.custom_op(f"{NS}::encode", mutates_args=())
 def encode(feats: torch.Tensor, node_ptr: torch.Tensor, t: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

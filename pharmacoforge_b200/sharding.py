@@ -44,6 +44,10 @@ def gather_results(local: torch.Tensor, group=None) -> Optional[List[torch.Tenso
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return [local]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if dist.get_backend(group) == "gloo" and local.is_cuda:
+        # gloo moves host memory: stage the (small) result rows through the CPU; NCCL gathers device to device
+        parts = gather_results(local.cpu(), group)
+        return None if parts is None else [p.to(local.device) for p in parts]
     n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
     counts = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(counts, n_local, group=group)

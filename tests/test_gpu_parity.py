@@ -194,6 +194,25 @@ def test_pp_graph_built_per_pocket_then_replicated(env, monkeypatch):
         assert g0.n_pp_edges == g1.n_pp_edges and g0.pp_num_tiles == g1.pp_num_tiles
 
 
+def test_ordered_tile_plan_matches_atomic_plan(env):
+    """The static pp plan lists its tiles in graph order (L2 reuse of source rows across the tiles of a graph): same tiles
+    as the atomic planner, sorted; every tile inside one graph, <= 128 rows, whole destinations only."""
+    g, b = env.build([(400, 1), (37, 2), (1, 4), (250, 3), (1500, 5)], [[3, 8, 5], [4], [3], [5, 6, 7], [16]])
+    n = g.pp_num_tiles
+    tiles = g.pp_tiles.cpu().numpy().reshape(-1, 2)[:n]
+    assert np.all(tiles[1:, 0] >= tiles[:-1, 1]) and tiles[0, 0] == 0 and tiles[-1, 1] == g.n_prot   # ordered, covering
+    t2 = torch.zeros_like(g.pp_tiles)
+    n2 = torch.zeros(1, dtype=torch.int32, device=env.dev)
+    env.ops.plan_tiles(g.pp_cnt, g.prot_ptr, False, 128, t2, n2, g.status)
+    other = t2.cpu().numpy().reshape(-1, 2)[:int(n2)]
+    assert int(n2) == n and np.array_equal(other[np.argsort(other[:, 0])], tiles)
+    cnt = g.pp_cnt.cpu().numpy()
+    ptr = g.prot_ptr_host
+    for s0, s1 in tiles:
+        assert cnt[s0:s1].sum() <= 128 and s1 - s0 <= 128
+        assert np.searchsorted(ptr, s0, side="right") == np.searchsorted(ptr, s1 - 1, side="right")   # one graph
+
+
 def test_exclusive_scan(env):
     for n in (0, 1, 5, 2048, 2049, 100_003, 3_000_017):
         x = torch.randint(0, 20, (n,), dtype=torch.int32)
