@@ -341,6 +341,19 @@ size_t pf_sample_args_size(void); /* sizeof(PfSampleArgs), for binding self-chec
 int pf_train_sgemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                    int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate, int32_t split_k,
                    void* stream);
+/* The same contraction on the tensor cores (csrc/pf_tc_gemm.cu): operands split on the fly into fp16 (hi, lo), three
+ * tcgen05.mma passes, fp32 accumulation in TMEM -- the numerics of the fused sampling kernels (22 significand bits).
+ * N <= 176 and either K <= 176 (forward / input-gradient shapes: B stays resident in shared memory, persistent CTAs over
+ * the rows) or M <= 128 with a long contraction (weight-gradient shapes: the contraction is split over CTAs, partials go
+ * to `workspace` (pf_tc_gemm_workspace_bytes) and are summed in CTA order: deterministic, no atomics).
+ * pf_train_gemm picks this kernel when the shape fits and a workspace is given, pf_train_sgemm (fp32 FFMA) otherwise. */
+size_t pf_tc_gemm_workspace_bytes(int32_t M, int32_t N, int64_t K);
+int pf_tc_gemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int64_t K, int64_t a_rs,
+               int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate, void* workspace,
+               size_t workspace_bytes, void* stream);
+int pf_train_gemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                  int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate, int32_t split_k,
+                  void* workspace, size_t workspace_bytes, void* stream);
 int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* stream); /* out[n] += sum_m x[m][n] (bias grad) */
 /* SiLU (gvp.py:78): dy == NULL -> out = silu(x); else out = dy * silu'(x) */
 int pf_train_silu(const float* x, const float* dy, float* out, int64_t n, void* stream);
@@ -373,12 +386,15 @@ int pf_train_edge_geom(const float* src_x, const float* dst_x, const int32_t* sr
 int pf_train_gvp_fwd(const float* feats, const float* vec, const float* Wh, const float* Wu, const float* Wf, const float* bf,
                      const float* Wg, const float* bg, int64_t M, int32_t n, int32_t vi, int32_t h, int32_t vo, int32_t no,
                      int32_t act_sigmoid, float* Vh, float* Vu, float* s, float* z, float* f, float* gates, float* vout,
-                     void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream);
 int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* Wu, const float* Wf, const float* Wg, const float* Vh,
                      const float* Vu, const float* s, const float* z, const float* f, const float* gates, const float* df_out,
                      const float* dvout, int64_t M, int32_t n, int32_t vi, int32_t h, int32_t vo, int32_t no,
                      int32_t act_sigmoid, float* dgates, float* dVu, float* dfz, float* ds, float* dVh, float* dfeats,
-                     float* dvec, float* dWh, float* dWu, float* dWf, float* dbf, float* dWg, float* dbg, void* stream);
+                     float* dvec, float* dWh, float* dWu, float* dWf, float* dbf, float* dWg, float* dbg, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* workspace / workspace_bytes of the two calls above: scratch of pf_tc_gemm_workspace_bytes(128, 176, 0) bytes for the tensor-
+ * core GEMMs (NULL: every contraction runs on the fp32 FFMA kernels). */
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------------
  * pf_launch_count: kernels this library has launched in this process so far.

@@ -84,8 +84,13 @@ SIGNATURES = {
     "pf_train_gather": (C.c_int, [c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, STREAM]),
     "pf_train_segmean": (C.c_int, [c_f32p, c_i32p, c_i32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, STREAM]),
     "pf_train_edge_geom": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, C.c_int64, STREAM]),
-    "pf_train_gvp_fwd": (C.c_int, [c_f32p] * 8 + [C.c_int64] + [C.c_int32] * 6 + [c_f32p] * 7 + [STREAM]),
-    "pf_train_gvp_bwd": (C.c_int, [c_f32p] * 13 + [C.c_int64] + [C.c_int32] * 6 + [c_f32p] * 13 + [STREAM]),
+    "pf_train_gvp_fwd": (C.c_int, [c_f32p] * 8 + [C.c_int64] + [C.c_int32] * 6 + [c_f32p] * 7 + [C.c_void_p, C.c_size_t, STREAM]),
+    "pf_train_gvp_bwd": (C.c_int, [c_f32p] * 13 + [C.c_int64] + [C.c_int32] * 6 + [c_f32p] * 13 + [C.c_void_p, C.c_size_t, STREAM]),
+    "pf_tc_gemm_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "pf_tc_gemm": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                             C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, STREAM]),
+    "pf_train_gemm": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, STREAM]),
     "pf_denoiser": (C.c_int, [C.c_void_p, STREAM]),
     "pf_sample_loop": (C.c_int, [C.c_void_p, STREAM]),
 }

@@ -605,9 +605,30 @@ extern "C" int pf_train_edge_geom(const float* src_x, const float* dst_x, const 
 // (the Python-side cost of ~16 custom-op round trips per GVP dominated the first training step).  All buffers are the
 // caller's.  Shapes: feats [M][n], vec [M][3][vi], Wh [vi][h], Wu [h][vo], Wf [no][n + h], Wg [vo][no];
 // saved for the backward: Vh [3M][h], Vu [3M][vo], s = [feats | sh] [M][n + h], z [M][no], f [M][no], gates [M][vo].
+// GEMM dispatch of the training path: the tensor-core kernel (pf_tc_gemm.cu: fp16 hi/lo split, 3 tcgen05 passes, fp32
+// accumulation; weight gradients through its deterministic two-stage split-K) wherever the shape fits it -- N <= 176 and
+// either a short contraction with many rows (forward, input gradients) or a long contraction with <= 128 output rows
+// (weight gradients, needs the workspace) -- and the fp32 FFMA kernels otherwise (small problems, no workspace).
+struct GemmWs {
+  void* ptr;
+  size_t bytes;
+};
 static int sgemm_ld(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, long long a_rs,
-                    long long a_cs, long long b_rs, long long b_cs, int ldc, int accumulate, int split_k, void* stream) {
+                    long long a_cs, long long b_rs, long long b_cs, int ldc, int accumulate, int split_k, void* stream,
+                    GemmWs ws = GemmWs{nullptr, 0}) {
+  const bool tc_ok = ws.ptr != nullptr && N <= 176 && N >= 1 && M >= 1;
+  if (tc_ok && K <= 176 && M >= 1024)
+    return pf_tc_gemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, ws.ptr, ws.bytes, stream);
+  if (tc_ok && K >= 4096 && M <= 128 && bias == nullptr && ws.bytes >= pf_tc_gemm_workspace_bytes(M, N, K))
+    return pf_tc_gemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, ws.ptr, ws.bytes, stream);
   return pf_train_sgemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, stream);
+}
+
+extern "C" int pf_train_gemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                             int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate,
+                             int32_t split_k, void* workspace, size_t workspace_bytes, void* stream) {
+  return sgemm_ld(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, stream,
+                  GemmWs{workspace, workspace_bytes});
 }
 // split-K factor of a weight gradient dW[m][n] = sum over `rows`: enough CTAs to fill the 148 SMs four times over even when
 // dW is a single 17 x 17 tile (the vector-channel weights: with a fixed cap of 64 splits those reductions over 3E = 600 k
@@ -624,14 +645,16 @@ static int wgrad_splits(long long rows, int m, int n) {
 extern "C" int pf_train_gvp_fwd(const float* feats, const float* vec, const float* Wh, const float* Wu, const float* Wf,
                                 const float* bf, const float* Wg, const float* bg, int64_t M, int32_t n, int32_t vi,
                                 int32_t h, int32_t vo, int32_t no, int32_t act_sigmoid, float* Vh, float* Vu, float* s,
-                                float* z, float* f, float* gates, float* vout, void* stream) {
+                                float* z, float* f, float* gates, float* vout, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  const GemmWs ws{workspace, workspace_bytes};
   PF_CHECK_ARG(feats && vec && Wh && Wu && Wf && bf && Wg && bg && Vh && Vu && s && z && f && gates && vout,
                "pf_train_gvp_fwd: null pointer");
   if (M == 0) return PF_OK;
   const int M3 = (int)(3 * M), K = n + h;
   int rc;
-  if ((rc = sgemm_ld(vec, Wh, nullptr, Vh, M3, h, vi, vi, 1, h, 1, h, 0, 1, stream)) != PF_OK) return rc;   // Vh = V Wh
-  if ((rc = sgemm_ld(Vh, Wu, nullptr, Vu, M3, vo, h, h, 1, vo, 1, vo, 0, 1, stream)) != PF_OK) return rc;   // Vu = Vh Wu
+  if ((rc = sgemm_ld(vec, Wh, nullptr, Vh, M3, h, vi, vi, 1, h, 1, h, 0, 1, stream, ws)) != PF_OK) return rc;   // Vh = V Wh
+  if ((rc = sgemm_ld(Vh, Wu, nullptr, Vu, M3, vo, h, h, 1, vo, 1, vo, 0, 1, stream, ws)) != PF_OK) return rc;   // Vu = Vh Wu
   cudaError_t e = cudaMemcpy2DAsync(s, (size_t)K * 4, feats, (size_t)n * 4, (size_t)n * 4, (size_t)M,
                                     cudaMemcpyDeviceToDevice, as_stream(stream));
   if (e != cudaSuccess) {
@@ -640,10 +663,10 @@ extern "C" int pf_train_gvp_fwd(const float* feats, const float* vec, const floa
   }
   T::vecnorm_fwd_kernel<<<blocks_for(M * h, 256), 256, 0, as_stream(stream)>>>(Vh, s + n, M, h, K);      // s = [feats|sh]
   PF_CHECK_LAUNCH("pf_train_gvp_fwd(vecnorm)");
-  if ((rc = sgemm_ld(s, Wf, bf, z, (int)M, no, K, K, 1, 1, K, no, 0, 1, stream)) != PF_OK) return rc;       // z = s Wf^T + bf
+  if ((rc = sgemm_ld(s, Wf, bf, z, (int)M, no, K, K, 1, 1, K, no, 0, 1, stream, ws)) != PF_OK) return rc;       // z = s Wf^T + bf
   T::silu_fwd_kernel<<<blocks_for(M * no, 256), 256, 0, as_stream(stream)>>>(z, f, M * no);
   PF_CHECK_LAUNCH("pf_train_gvp_fwd(silu)");
-  if ((rc = sgemm_ld(f, Wg, bg, gates, (int)M, vo, no, no, 1, 1, no, vo, 0, 1, stream)) != PF_OK) return rc;
+  if ((rc = sgemm_ld(f, Wg, bg, gates, (int)M, vo, no, no, 1, 1, no, vo, 0, 1, stream, ws)) != PF_OK) return rc;
   T::gate_fwd_kernel<<<blocks_for(M * 3 * vo, 256), 256, 0, as_stream(stream)>>>(gates, Vu, vout, M, vo, act_sigmoid);
   PF_CHECK_LAUNCH("pf_train_gvp_fwd(gate)");
   return PF_OK;
@@ -656,7 +679,9 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
                                 const float* gates, const float* df_out, const float* dvout, int64_t M, int32_t n,
                                 int32_t vi, int32_t h, int32_t vo, int32_t no, int32_t act_sigmoid, float* dgates,
                                 float* dVu, float* dfz, float* ds, float* dVh, float* dfeats, float* dvec, float* dWh,
-                                float* dWu, float* dWf, float* dbf, float* dWg, float* dbg, void* stream) {
+                                float* dWu, float* dWf, float* dbf, float* dWg, float* dbg, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  const GemmWs ws{workspace, workspace_bytes};
   PF_CHECK_ARG(vec && Wh && Wu && Wf && Wg && Vh && Vu && s && z && f && gates && df_out && dvout && dgates && dVu && dfz &&
                    ds && dVh && dfeats && dvec && dWh && dWu && dWf && dbf && dWg && dbg,
                "pf_train_gvp_bwd: null pointer");
@@ -668,20 +693,20 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
   T::gate_bwd_kernel<<<blocks_for(M * vo, 256), 256, 0, st>>>(gates, Vu, dvout, dgates, dVu, M, vo, act_sigmoid);
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(gate)");
   // gates = f Wg^T + bg
-  if ((rc = sgemm_ld(dgates, f, nullptr, dWg, vo, no, Mi, 1, vo, no, 1, no, 0, wgrad_splits(M, vo, no), stream)) != PF_OK) return rc;  // dWg = dgates^T f
+  if ((rc = sgemm_ld(dgates, f, nullptr, dWg, vo, no, Mi, 1, vo, no, 1, no, 0, wgrad_splits(M, vo, no), stream, ws)) != PF_OK) return rc;  // dWg = dgates^T f
   if ((rc = pf_train_colsum(dgates, dbg, M, vo, stream)) != PF_OK) return rc;
   cudaError_t e = cudaMemcpyAsync(dfz, df_out, (size_t)M * no * 4, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) {
     set_error("pf_train_gvp_bwd: copy: %s", cudaGetErrorString(e));
     return PF_ERR_LAUNCH;
   }
-  if ((rc = sgemm_ld(dgates, Wg, nullptr, dfz, Mi, no, vo, vo, 1, no, 1, no, 1, 1, stream)) != PF_OK) return rc;  // df += dgates Wg
+  if ((rc = sgemm_ld(dgates, Wg, nullptr, dfz, Mi, no, vo, vo, 1, no, 1, no, 1, 1, stream, ws)) != PF_OK) return rc;  // df += dgates Wg
   T::silu_bwd_kernel<<<blocks_for(M * no, 256), 256, 0, st>>>(z, dfz, dfz, M * no);                              // dz in place
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(silu)");
   // z = s Wf^T + bf
-  if ((rc = sgemm_ld(dfz, s, nullptr, dWf, no, K, Mi, 1, no, K, 1, K, 0, wgrad_splits(M, no, K), stream)) != PF_OK) return rc;       // dWf = dz^T s
+  if ((rc = sgemm_ld(dfz, s, nullptr, dWf, no, K, Mi, 1, no, K, 1, K, 0, wgrad_splits(M, no, K), stream, ws)) != PF_OK) return rc;       // dWf = dz^T s
   if ((rc = pf_train_colsum(dfz, dbf, M, no, stream)) != PF_OK) return rc;
-  if ((rc = sgemm_ld(dfz, Wf, nullptr, ds, Mi, K, no, no, 1, K, 1, K, 0, 1, stream)) != PF_OK) return rc;        // ds = dz Wf
+  if ((rc = sgemm_ld(dfz, Wf, nullptr, ds, Mi, K, no, no, 1, K, 1, K, 0, 1, stream, ws)) != PF_OK) return rc;        // ds = dz Wf
   e = cudaMemcpy2DAsync(dfeats, (size_t)n * 4, ds, (size_t)K * 4, (size_t)n * 4, (size_t)M, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) {
     set_error("pf_train_gvp_bwd: copy: %s", cudaGetErrorString(e));
@@ -690,10 +715,10 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
   T::vecnorm_bwd_kernel<<<blocks_for(M * h, 256), 256, 0, st>>>(Vh, ds + n, dVh, M, h, K);                        // via sh
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(vecnorm)");
   // Vu = Vh Wu
-  if ((rc = sgemm_ld(dVu, Wu, nullptr, dVh, M3, h, vo, vo, 1, 1, vo, h, 1, 1, stream)) != PF_OK) return rc;      // dVh += dVu Wu^T
-  if ((rc = sgemm_ld(Vh, dVu, nullptr, dWu, h, vo, M3, 1, h, vo, 1, vo, 0, wgrad_splits(3 * M, h, vo), stream)) != PF_OK) return rc;    // dWu = Vh^T dVu
+  if ((rc = sgemm_ld(dVu, Wu, nullptr, dVh, M3, h, vo, vo, 1, 1, vo, h, 1, 1, stream, ws)) != PF_OK) return rc;      // dVh += dVu Wu^T
+  if ((rc = sgemm_ld(Vh, dVu, nullptr, dWu, h, vo, M3, 1, h, vo, 1, vo, 0, wgrad_splits(3 * M, h, vo), stream, ws)) != PF_OK) return rc;    // dWu = Vh^T dVu
   // Vh = V Wh
-  if ((rc = sgemm_ld(dVh, Wh, nullptr, dvec, M3, vi, h, h, 1, 1, h, vi, 0, 1, stream)) != PF_OK) return rc;      // dV = dVh Wh^T
-  if ((rc = sgemm_ld(vec, dVh, nullptr, dWh, vi, h, M3, 1, vi, h, 1, h, 0, wgrad_splits(3 * M, vi, h), stream)) != PF_OK) return rc;    // dWh = V^T dVh
+  if ((rc = sgemm_ld(dVh, Wh, nullptr, dvec, M3, vi, h, h, 1, 1, h, vi, 0, 1, stream, ws)) != PF_OK) return rc;      // dV = dVh Wh^T
+  if ((rc = sgemm_ld(vec, dVh, nullptr, dWh, vi, h, M3, 1, vi, h, 1, h, 0, wgrad_splits(3 * M, vi, h), stream, ws)) != PF_OK) return rc;    // dWh = V^T dVh
   return PF_OK;
 }

@@ -20,9 +20,29 @@ from .ops import NS, _f, _i, _s
 _L = _lib.load()
 
 
+_WS = {}
+
+
+def _workspace(device):
+    """Scratch of the tensor-core GEMMs (split-K partials of the weight gradients), one per device.  PF_TRAIN_GEMM=ffma
+    disables the tensor-core kernel (A/B switch: every contraction then runs on the fp32 FFMA kernels)."""
+    import os
+    if os.environ.get("PF_TRAIN_GEMM", "tc") == "ffma":
+        return None
+    ws = _WS.get(device)
+    if ws is None:
+        ws = _WS[device] = torch.empty(_L.pf_tc_gemm_workspace_bytes(128, 176, 0) // 4, dtype=torch.float32, device=device)
+    return ws
+
+
+def _ws_args(device):
+    ws = _workspace(device)
+    return (C.c_void_p(ws.data_ptr()), ws.numel() * 4) if ws is not None else (None, 0)
+
+
 def _gemm(A, B, bias, Cm, M, N, K, a_rs, a_cs, b_rs, b_cs, accumulate=False, split_k=1):
-    _lib.check(_L.pf_train_sgemm(_f(A), _f(B), _f(bias), _f(Cm), M, N, K, a_rs, a_cs, b_rs, b_cs, N, int(accumulate),
-                                 split_k, _s()), "pf_train_sgemm")
+    _lib.check(_L.pf_train_gemm(_f(A), _f(B), _f(bias), _f(Cm), M, N, K, a_rs, a_cs, b_rs, b_cs, N, int(accumulate),
+                                split_k, *_ws_args(A.device), _s()), "pf_train_gemm")
 
 
 # ------------------------------------------------------------------------------------------------ linear
@@ -364,8 +384,8 @@ def _gvp_fwd(feats: torch.Tensor, vec: torch.Tensor, Wh: torch.Tensor, Wu: torch
     e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=feats.device)
     Vh, Vu, s, z, f, gates, vout = e(3 * M, h), e(3 * M, vo), e(M, n + h), e(M, no), e(M, no), e(M, vo), e(M, 3, vo)
     _lib.check(_L.pf_train_gvp_fwd(_f(feats), _f(vec), _f(Wh), _f(Wu), _f(Wf), _f(bf), _f(Wg), _f(bg), M, n, vi, h, vo, no,
-                                   int(act_sigmoid), _f(Vh), _f(Vu), _f(s), _f(z), _f(f), _f(gates), _f(vout), _s()),
-               "pf_train_gvp_fwd")
+                                   int(act_sigmoid), _f(Vh), _f(Vu), _f(s), _f(z), _f(f), _f(gates), _f(vout),
+                                   *_ws_args(feats.device), _s()), "pf_train_gvp_fwd")
     return f, vout, Vh, Vu, s, z, gates
 
 
@@ -394,7 +414,7 @@ def _gvp_bwd(vec: torch.Tensor, Wh: torch.Tensor, Wu: torch.Tensor, Wf: torch.Te
     _lib.check(_L.pf_train_gvp_bwd(_f(vec), _f(Wh), _f(Wu), _f(Wf), _f(Wg), _f(Vh), _f(Vu), _f(s), _f(z), _f(f), _f(gates),
                                    _f(df), _f(dvout), M, n, vi, h, vo, no, int(act_sigmoid), _f(dgates), _f(dVu), _f(dfz),
                                    _f(ds), _f(dVh), _f(dfeats), _f(dvec), _f(dWh), _f(dWu), _f(dWf), _f(dbf), _f(dWg),
-                                   _f(dbg), _s()), "pf_train_gvp_bwd")
+                                   _f(dbg), *_ws_args(z.device), _s()), "pf_train_gvp_bwd")
     return dfeats, dvec, dWh, dWu, dWf, dbf, dWg, dbg
 
 

@@ -32,3 +32,57 @@ def test_tc_gemm_selftest(K, N, npass):
     assert err <= tol * scale, f"K={K} N={N} npass={npass}: max abs err {err:.3e} (scale {scale:.2f})"
     if npass == 3:   # the compensated product must be far better than a single bf16 pass
         assert err <= 1e-3 * scale
+
+
+def _tc_gemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, accumulate=False):
+    from pharmacoforge_b200 import _lib
+    lib = _lib.load()
+    ws = torch.empty(lib.pf_tc_gemm_workspace_bytes(128, 176, 0) // 4, dtype=torch.float32, device="cuda")
+    vp = lambda t: C_.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(lib.pf_tc_gemm(vp(A), vp(B), vp(bias), vp(C), M, N, K, a_rs, a_cs, b_rs, b_cs, N, int(accumulate), vp(ws),
+                              ws.numel() * 4, C_.c_void_p(torch.cuda.current_stream().cuda_stream)), "pf_tc_gemm")
+    torch.cuda.synchronize()
+
+
+C_ = C
+
+
+@pytest.mark.parametrize("M,K,N", [(5000, 161, 128), (4096, 144, 128), (1025, 128, 161), (3000, 17, 17), (2500, 16, 32),
+                                   (1300, 128, 16), (128, 176, 176)])
+def test_tc_gemm_forward_and_dgrad_shapes(M, K, N):
+    """pf_tc_gemm, resident-B mode (training forward / input gradients): y = x W^T + b and dx = dy W on the tensor cores with
+    the fp16 hi/lo split (3 passes), against an fp64 product: relative error ~1e-6 of the row scale (fp32-accurate)."""
+    gen = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=gen).cuda()
+    w = (torch.randn(N, K, generator=gen) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=gen).cuda()
+    y = torch.full((M, N), float("nan"), device="cuda")
+    _tc_gemm(x, w, b, y, M, N, K, K, 1, 1, K)                       # B(k, n) = w[n, k]
+    ref = x.double() @ w.double().t() + b.double()
+    scale = ref.abs().max().item()
+    assert (y.double() - ref).abs().max().item() <= 2e-6 * scale + 1e-6
+    # input gradient: dx[M, K] = dy[M, N] w[N, K]  (B(k', n') = w[k', n'], row-major) accumulated onto a base
+    dy = torch.randn(M, N, generator=gen).cuda()
+    base = torch.randn(M, K, generator=gen).cuda()
+    dx = base.clone()
+    _tc_gemm(dy, w, None, dx, M, K, N, N, 1, K, 1, accumulate=True)
+    ref = base.double() + dy.double() @ w.double()
+    assert (dx.double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("rows,N,K", [(128, 161, 50000), (128, 144, 4096), (16, 128, 33333), (17, 16, 70001)])
+def test_tc_gemm_weight_gradient_is_accurate_and_deterministic(rows, N, K):
+    """pf_tc_gemm, split-K mode (training weight gradients): dW[rows, N] = dy^T x with the contraction over K edges split
+    across CTAs and reduced in CTA order: fp32-accurate and bit-identical run to run (the FFMA path used atomics)."""
+    gen = torch.Generator().manual_seed(rows * 7 + N)
+    dy = torch.randn(K, rows, generator=gen).cuda()                 # A(m, k) = dy[k, m]: a_rs = 1, a_cs = rows
+    x = torch.randn(K, N, generator=gen).cuda()                     # B(k, n) = x[k, n]:  b_rs = N, b_cs = 1
+    outs = []
+    for _ in range(2):
+        dw = torch.full((rows, N), float("nan"), device="cuda")
+        _tc_gemm(dy, x, None, dw, rows, N, K, 1, rows, N, 1)
+        outs.append(dw)
+    assert torch.equal(outs[0], outs[1])
+    ref = dy.double().t() @ x.double()
+    err = (outs[0].double() - ref).abs().max().item()
+    assert err <= 3e-6 * (K ** 0.5) * 4 + 1e-5, err                # entries are ~sqrt(K); error ~1e-6 relative of that
