@@ -3,14 +3,19 @@
 //
 //   C[M][N] (+)= sum_k A(m, k) B(k, n) (+ bias[n]),   A(m, k) = A[m a_rs + k a_cs],  B(k, n) = B[k b_rs + n b_cs]
 //
-// Numerics are those of the fused sampling kernels (pf_tc_conv.cu): both operands split on the fly into fp16 (hi, lo),
-// three tcgen05.mma kind::f16 passes hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM (22 significand bits).
+// Numerics: both operands are split on the fly into bf16 (hi, lo) and contracted in three tcgen05.mma kind::f16 passes
+// hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM: 16 significand bits per operand with the exponent range of fp32.
+// The fp16 split of the sampling kernels (22 bits) is not usable here: gradients reach 1e-8, far below fp16's subnormal
+// range (a 2 % error on the smallest weight gradients when tried), and the training parity bar is 1e-3, not 1e-4.
+// The tensor core accumulates with truncation, so the error of one accumulator grows linearly with the number of MMAs
+// (measured: 1.6e-3 absolute on sums of magnitude 180 after 384 MMAs); a split-K CTA therefore flushes its accumulator
+// after at most ~2048 contraction elements per CTA when the problem is large enough to fill the grid (k_per_cta below).
 //
 // One persistent CTA per SM, warp-specialised (416 threads):
 //   warps 0-3   A producers: thread r owns tile row r = TMEM lane r; per K-chunk of 16 it loads its 16 values, splits them
 //               and stores the chunk as the MMA's A operand in TMEM (tcgen05.st; 8 chunks in flight)
 //   warps 4-7   epilogue: accumulator (TMEM, double buffered) -> registers -> C (+ bias / accumulate)
-//   warps 8-11  B producers: B as fp16 (hi, lo) UMMA K-major SWIZZLE_NONE images in shared memory
+//   warps 8-11  B producers: B as bf16 (hi, lo) UMMA K-major SWIZZLE_NONE images in shared memory
 //   warp 12     MMA issue (one elected lane), tcgen05.commit hands buffers back through mbarriers
 // MODE 0 (forward, dgrad): N, K <= 176; the whole B image is built once per CTA and stays resident; tiles run over M.
 // MODE 1 (wgrad): M <= 128 output rows, the contraction index (edges / nodes) is split across CTAs; A and B chunks are both
@@ -51,7 +56,7 @@ struct Bars {
 __device__ __forceinline__ void store_b8(uint8_t* chunk, uint32_t lbo, uint32_t lo_off, int n, int k8, const float (&x)[8]) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) tc::split_pack_h(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+  for (int i = 0; i < 4; ++i) tc::split_pack(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
   uint8_t* a = chunk + (size_t)k8 * lbo + (n >> 3) * 128 + (n & 7) * 16;
   *reinterpret_cast<uint4*>(a) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(a + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -104,28 +109,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
     const int r = threadIdx.x;                                    // tile row == TMEM lane
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     uint32_t it = 0;
-    for (int t = 0; t < my_tiles; ++t) {
+    // the loads of chunk i + 1 are issued before chunk i is split and stored: one global-memory latency per tile row is
+    // paid once, not once per chunk (the chunk sequence runs across tile boundaries)
+    auto load_chunk = [&](float (&x)[16], int t, int c) {
       const long long m = MODE == 1 ? r : ((long long)(blockIdx.x + (long long)t * gridDim.x) * kRows + r);
-      const bool row_ok = m < p.M;
-      const float* arow = p.A + m * p.a_rs;
+      const bool row_ok = t < my_tiles && m < p.M;
+      const float* arow = p.A + (row_ok ? m : 0) * p.a_rs;
+      const int k0 = k_begin + 16 * c;
+      if (row_ok && p.a_cs == 1 && k0 + 16 <= k_end && ((reinterpret_cast<uintptr_t>(arow + k0) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(arow + k0) + j);
+          x[4 * j] = v.x, x[4 * j + 1] = v.y, x[4 * j + 2] = v.z, x[4 * j + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = (row_ok && k0 + j < k_end) ? __ldg(arow + (long long)(k0 + j) * p.a_cs) : 0.f;
+      }
+    };
+    float xn[16];
+    if (my_tiles > 0 && n_chunks > 0) load_chunk(xn, 0, 0);
+    for (int t = 0; t < my_tiles; ++t) {
       for (int c = 0; c < n_chunks; ++c, ++it) {
         const int s = it % kAStages;
-        if (it >= kAStages) tc::mbar_wait(&bars.a_empty[s], ((it / kAStages) - 1) & 1);
-        const int k0 = k_begin + 16 * c;
         float x[16];
-        if (row_ok && p.a_cs == 1 && k0 + 16 <= k_end && ((reinterpret_cast<uintptr_t>(arow + k0) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(arow + k0) + j);
-            x[4 * j] = v.x, x[4 * j + 1] = v.y, x[4 * j + 2] = v.z, x[4 * j + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = (row_ok && k0 + j < k_end) ? __ldg(arow + (long long)(k0 + j) * p.a_cs) : 0.f;
-        }
+        for (int j = 0; j < 16; ++j) x[j] = xn[j];
+        if (c + 1 < n_chunks)
+          load_chunk(xn, t, c + 1);
+        else if (t + 1 < my_tiles)
+          load_chunk(xn, t + 1, 0);
+        if (it >= kAStages) tc::mbar_wait(&bars.a_empty[s], ((it / kAStages) - 1) & 1);
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tc::split_pack_h(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+        for (int j = 0; j < 8; ++j) tc::split_pack(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
         tc::tmem_st8(tmem + lane_base + kColA + 16 * s, hi);
         tc::tmem_st8(tmem + lane_base + kColA + 16 * s + 8, lo);
         tc::wait_st();
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
   } else {
     // ------------------------------------------------------------------ MMA issue
     if (lane == 0 && my_tiles > 0) {
-      const uint32_t idesc = tc::make_idesc_f16(kRows, n_pad);
+      const uint32_t idesc = tc::make_idesc_bf16(kRows, n_pad);
       const uint32_t smem_a = tc::smem_u32(smem);
       if (MODE == 0) tc::mbar_wait(&bars.b_res, 0);
       uint32_t it = 0;

@@ -51,7 +51,8 @@ C_ = C
                                    (1300, 128, 16), (128, 176, 176)])
 def test_tc_gemm_forward_and_dgrad_shapes(M, K, N):
     """pf_tc_gemm, resident-B mode (training forward / input gradients): y = x W^T + b and dx = dy W on the tensor cores with
-    the fp16 hi/lo split (3 passes), against an fp64 product: relative error ~1e-6 of the row scale (fp32-accurate)."""
+    the bf16 hi/lo split (3 passes, fp32 exponent range), against an fp64 product: error ~2^-16 of the row scale, far
+    inside the 1e-3 bar of the training parity tests; tiny operands (1e-7, gradient-sized) keep that relative accuracy."""
     gen = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=gen).cuda()
     w = (torch.randn(N, K, generator=gen) / K ** 0.5).cuda()
@@ -60,20 +61,25 @@ def test_tc_gemm_forward_and_dgrad_shapes(M, K, N):
     _tc_gemm(x, w, b, y, M, N, K, K, 1, 1, K)                       # B(k, n) = w[n, k]
     ref = x.double() @ w.double().t() + b.double()
     scale = ref.abs().max().item()
-    assert (y.double() - ref).abs().max().item() <= 2e-6 * scale + 1e-6
+    assert (y.double() - ref).abs().max().item() <= 3e-5 * scale + 1e-6
+    tiny = torch.full((M, N), float("nan"), device="cuda")
+    _tc_gemm(x * 1e-7, w, None, tiny, M, N, K, K, 1, 1, K)           # gradient-sized operand: no fp16 range problem
+    ref_t = (x.double() * 1e-7) @ w.double().t()
+    assert (tiny.double() - ref_t).abs().max().item() <= 3e-5 * ref_t.abs().max().item()
     # input gradient: dx[M, K] = dy[M, N] w[N, K]  (B(k', n') = w[k', n'], row-major) accumulated onto a base
     dy = torch.randn(M, N, generator=gen).cuda()
     base = torch.randn(M, K, generator=gen).cuda()
     dx = base.clone()
     _tc_gemm(dy, w, None, dx, M, K, N, N, 1, K, 1, accumulate=True)
     ref = base.double() + dy.double() @ w.double()
-    assert (dx.double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 1e-6
+    assert (dx.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item() + 1e-6
 
 
 @pytest.mark.parametrize("rows,N,K", [(128, 161, 50000), (128, 144, 4096), (16, 128, 33333), (17, 16, 70001)])
 def test_tc_gemm_weight_gradient_is_accurate_and_deterministic(rows, N, K):
     """pf_tc_gemm, split-K mode (training weight gradients): dW[rows, N] = dy^T x with the contraction over K edges split
-    across CTAs and reduced in CTA order: fp32-accurate and bit-identical run to run (the FFMA path used atomics)."""
+    across CTAs and reduced in CTA order: bit-identical run to run (the FFMA path used atomics), error ~1e-5 of the result
+    scale (bf16 split + the tensor core's truncating accumulation over <= 128 K-steps per accumulator)."""
     gen = torch.Generator().manual_seed(rows * 7 + N)
     dy = torch.randn(K, rows, generator=gen).cuda()                 # A(m, k) = dy[k, m]: a_rs = 1, a_cs = rows
     x = torch.randn(K, N, generator=gen).cuda()                     # B(k, n) = x[k, n]:  b_rs = N, b_cs = 1
@@ -85,4 +91,4 @@ def test_tc_gemm_weight_gradient_is_accurate_and_deterministic(rows, N, K):
     assert torch.equal(outs[0], outs[1])
     ref = dy.double().t() @ x.double()
     err = (outs[0].double() - ref).abs().max().item()
-    assert err <= 3e-6 * (K ** 0.5) * 4 + 1e-5, err                # entries are ~sqrt(K); error ~1e-6 relative of that
+    assert err <= 5e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
