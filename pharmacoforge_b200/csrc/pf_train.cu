@@ -619,9 +619,11 @@ static int sgemm_ld(const float* A, const float* B, const float* bias, float* C,
   const bool tc_ok = ws.ptr != nullptr && N <= 176 && N >= 1 && M >= 1;
   // row threshold: a persistent launch pays TMEM allocation, the B image build and a pipeline fill per CTA (~5 us); the
   // small edge types (ff / pf / fp: a few thousand rows) stay on the FFMA kernels
-  if (tc_ok && K <= 176 && M >= 16384)
+  // and so do the skinny vector-channel contractions (N, K = 16 / 17 / 32): one or two K-steps per 128-row tile make the
+  // tile hand-offs, not the arithmetic, the cost (measured 80 us per launch against 25-37 us on the FFMA kernel)
+  if (tc_ok && K <= 176 && M >= 16384 && N >= 64 && K >= 64)
     return pf_tc_gemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, ws.ptr, ws.bytes, stream);
-  if (tc_ok && K >= 16384 && M <= 128 && bias == nullptr && ws.bytes >= pf_tc_gemm_workspace_bytes(M, N, K))
+  if (tc_ok && K >= 16384 && M <= 128 && M >= 64 && N >= 64 && bias == nullptr && ws.bytes >= pf_tc_gemm_workspace_bytes(M, N, K))
     return pf_tc_gemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, ws.ptr, ws.bytes, stream);
   return pf_train_sgemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, stream);
 }
