@@ -237,6 +237,40 @@ __device__ __forceinline__ void silu_pre_split2(uint32_t a0, uint32_t a1, uint64
   lo = pack_f16x2_sat(l0, l1);
 }
 
+// Pre-scaled form with ONE reciprocal per four elements (PF_SILU_SHARED_RCP=1, A/B variant): 1.25 MUFU and 8 instructions
+// per element instead of 2 and 6 -- trades XU-pipe time (16 lanes / clk / SM) for issue slots.  2^t is clamped at 2^30 so the
+// product of four denominators stays finite (absolute error below 3e-8 for y < -20.8).
+__device__ __forceinline__ void silu_pre_split4(const uint32_t (&a)[4], uint64_t bias01, uint64_t bias23, float (&f)[4],
+                                                uint32_t& hi01, uint32_t& hi23, uint32_t& lo01, uint32_t& lo23) {
+  const uint64_t kk = pack2(kSiluK, kSiluK);
+  const uint64_t t01 = add2(pack2(__uint_as_float(a[0]), __uint_as_float(a[1])), bias01);
+  const uint64_t t23 = add2(pack2(__uint_as_float(a[2]), __uint_as_float(a[3])), bias23);
+  float t0, t1, t2, t3;
+  unpack2(t01, t0, t1);
+  unpack2(t23, t2, t3);
+  const float e0 = fminf(ex2_approx(t0), 1073741824.0f), e1 = fminf(ex2_approx(t1), 1073741824.0f);
+  const float e2 = fminf(ex2_approx(t2), 1073741824.0f), e3 = fminf(ex2_approx(t3), 1073741824.0f);
+  float d0, d1, d2, d3;                       // d = k (2^t + 1): f = t / d
+  unpack2(fma2(pack2(e0, e1), kk, kk), d0, d1);
+  unpack2(fma2(pack2(e2, e3), kk, kk), d2, d3);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_approx(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
+  const uint64_t f01 = mul2(t01, mul2(pack2(r01, r01), pack2(d1, d0)));
+  const uint64_t f23 = mul2(t23, mul2(pack2(r23, r23), pack2(d3, d2)));
+  unpack2(f01, f[0], f[1]);
+  unpack2(f23, f[2], f[3]);
+  hi01 = pack_f16x2_sat(f[0], f[1]);
+  hi23 = pack_f16x2_sat(f[2], f[3]);
+  const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi01));
+  const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi23));
+  float l0, l1, l2, l3;
+  unpack2(sub2(f01, pack2(h01.x, h01.y)), l0, l1);
+  unpack2(sub2(f23, pack2(h23.x, h23.y)), l2, l3);
+  lo01 = pack_f16x2_sat(l0, l1);
+  lo23 = pack_f16x2_sat(l2, l3);
+}
+
 // Four elements per call with ONE reciprocal: 1 / d_k = (1 / (d0 d1 d2 d3)) * (product of the other three).  EPI-B is
 // bound by the MUFU pipe (16 lanes / clk / SM: 8 cycles per warp instruction and scheduler), so this trades 3 of every
 // 8 MUFU operations for 5 multiplies: 5 MUFU and 34 instructions per 4 elements instead of 8 and 26.  2^t is clamped at

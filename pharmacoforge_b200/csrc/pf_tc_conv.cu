@@ -129,6 +129,11 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
 
 // Experiment switches of the node-update kernel: tile-wise alternation of the two slots' S jobs,
 // and a start-up delay of the odd CTAs (ns) so that half of the grid runs half a tile behind the other half.
+#ifndef PF_SILU_SHARED_RCP
+#define PF_SILU_SHARED_RCP 1   // 1 (default, measured -2.5 .. -3 % per pp launch): one reciprocal per four SiLU elements in
+                               // EPI-B (1.25 MUFU + 8 instructions per element); 0: one per element (2 MUFU + 6): the XU pipe,
+                               // not the issue slots, is the scarcer resource of that stage
+#endif
 #ifndef PF_K4_TILE_ALT
 #define PF_K4_TILE_ALT 0
 #endif
@@ -951,11 +956,19 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
               hi[i + 1] = tc::silu_h2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
                                       *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2));
             } else {
+#if PF_SILU_SHARED_RCP
+              const uint32_t a4[4] = {r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3]};
+              float f4[4];
+              tc::silu_pre_split4(a4, *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                                  *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f4, hi[i], hi[i + 1], lo[i], lo[i + 1]);
+              fv[2 * i] = f4[0], fv[2 * i + 1] = f4[1], fv[2 * i + 2] = f4[2], fv[2 * i + 3] = f4[3];
+#else
               tc::silu_pre_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
                                   fv[2 * i], fv[2 * i + 1], hi[i], lo[i]);
               tc::silu_pre_split2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
                                   *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), fv[2 * i + 2], fv[2 * i + 3],
                                   hi[i + 1], lo[i + 1]);
+#endif
             }
           }
           if (g == 2) {
@@ -1455,11 +1468,18 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
               hi[i + 1] = tc::silu_h2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
                                       *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2));
             } else {
+#if PF_SILU_SHARED_RCP
+              const uint32_t a4[4] = {r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3]};
+              float f4[4];
+              tc::silu_pre_split4(a4, *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
+                                  *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f4, hi[i], hi[i + 1], lo[i], lo[i + 1]);
+#else
               float f0, f1;
               tc::silu_pre_split2(r[j4 & 1][2 * i], r[j4 & 1][2 * i + 1], *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i),
                                   f0, f1, hi[i], lo[i]);
               tc::silu_pre_split2(r[j4 & 1][2 * i + 2], r[j4 & 1][2 * i + 3],
                                   *reinterpret_cast<const uint64_t*>(bf + 16 * j + 2 * i + 2), f0, f1, hi[i + 1], lo[i + 1]);
+#endif
             }
           }
           tc::tmem_st8(Dreg + 16 * j, hi);
