@@ -313,6 +313,20 @@ typedef struct PfSampleArgs {
   const uint64_t* noise_seed;
   int32_t noise_step0;
   int32_t ff_k; /* > 0: ff edges are the kNN graph of the pharmacophore nodes (pf_dyn_graph_ffk) instead of the radius graph */
+  /* PF_FLAG_SHARE_POCKET_MESSAGES: buffers of the opt-in shared-pocket mode (csrc/pf_share.cu); NULL when unused */
+  const float* pk_x;           /* [n_distinct][3] input coordinates of the DISTINCT pockets of the batch */
+  const int32_t *pk_start, *pk_cnt, *pk_col, *pk_tiles, *pk_n_tiles; /* their pp CSR + tile plan */
+  int32_t pk_max_tiles, n_distinct;
+  const int32_t* pk_seed_row;  /* [n_distinct] seed-table row of every distinct protein node */
+  const int32_t* pk_node0;     /* [n_graphs] first distinct node of the graph's pocket */
+  const float* enc_feats;      /* [n_graphs * n_prot_feats][n_prot_feats] identity blocks: input of the encoder table */
+  const int32_t* enc_ptr;      /* [n_graphs + 1] = n_prot_feats * g */
+  const int32_t* enc_rep;      /* [n_graphs * n_prot_feats] identity (every table row is its own representative) */
+  float* enc_table;            /* [n_graphs * n_prot_feats][128] encoder output per (graph, atom type) */
+  float *aggd_h, *aggd_v;      /* [n_distinct][128], [n_distinct][48] pp means per distinct node */
+  float *c_x, *c_h, *c_v, *c_agg_h, *c_agg_v; /* compact protein rows, one per fp segment slot: [pf_k * n_pharm][...] */
+  const int32_t* c_seg_id;     /* [pf_k * n_pharm] identity */
+  int32_t* pf_col_c;           /* [pf_k * n_pharm] compact source row of every pf edge */
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph
@@ -322,6 +336,20 @@ typedef struct PfSampleArgs {
 /* PF_FLAG_NO_LAYER0_SEED: run the first conv layer's pp messages through the general kernel (row gather + all 11 K-steps of
  * GVP 0) even when the seed arrays are bound -- the A/B switch of the seeded path (results agree to fp32 rounding). */
 #define PF_FLAG_NO_LAYER0_SEED 4u
+
+/* PF_FLAG_SHARE_POCKET_MESSAGES (with PF_FLAG_SKIP_DEAD_WORK, n_convs == 2, tcgen05 path, seed arrays bound, and THE SAME
+ * TIMESTEP FOR EVERY GRAPH -- the reverse-diffusion loop): exact work elimination of SURVEY.md hard part 5b + 5c.  The
+ * first layer's pp messages are computed once per distinct pocket (they depend only on (pocket, t)), and only the protein
+ * rows the last layer's pf edges read (the fp segment destinations) are encoded and updated, in a compact buffer.  Equal to
+ * the nominal path up to fp32 rounding of x_src - x_dst; never the default, reported separately by bench.py. */
+#define PF_FLAG_SHARE_POCKET_MESSAGES 8u
+int pf_share_index(const int32_t* pharm_ptr, int32_t n_graphs, int32_t pf_k, const int32_t* pf_cnt, const int32_t* pf_col,
+                   const int32_t* fp_seg_dst, const int32_t* fp_seg_cnt, int32_t* pf_col_c, void* stream);
+/* stage 0: c_x / c_h from prot_x and the encoder table; stage 1: c_agg += pp means of the row's distinct node */
+int pf_share_gather(const int32_t* pharm_ptr, const int32_t* prot_ptr, const int32_t* pk_node0, int32_t n_graphs,
+                    int32_t pf_k, const int32_t* fp_seg_dst, const float* prot_x, const int32_t* seed_row,
+                    const float* enc_table, const float* aggd_h, const float* aggd_v, float* c_x, float* c_h,
+                    float* c_agg_h, float* c_agg_v, int32_t stage, void* stream);
 
 /* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the
  * timestep value of graph g.  Results in a->eps_h / a->eps_x. */

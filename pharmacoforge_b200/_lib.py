@@ -36,6 +36,9 @@ SIGNATURES = {
                                    c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
+    "pf_share_index": (C.c_int, [c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, STREAM]),
+    "pf_share_gather": (C.c_int, [c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_f32p, c_i32p, c_f32p, c_f32p,
+                                  c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, STREAM]),
     "pf_plan_tiles_count": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_void_p, STREAM]),
     "pf_plan_tiles_fill": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p,
                                      C.c_void_p, STREAM]),
@@ -139,6 +142,12 @@ class PfSampleArgs(C.Structure):
         ("flags", C.c_uint32),
         ("seed_row", C.c_void_p), ("seed_rep", C.c_void_p), ("seed_table", C.c_void_p), ("n_seed_rows", C.c_int32),
         ("noise_seed", C.c_void_p), ("noise_step0", C.c_int32), ("ff_k", C.c_int32),
+        ("pk_x", C.c_void_p), ("pk_start", C.c_void_p), ("pk_cnt", C.c_void_p), ("pk_col", C.c_void_p),
+        ("pk_tiles", C.c_void_p), ("pk_n_tiles", C.c_void_p), ("pk_max_tiles", C.c_int32), ("n_distinct", C.c_int32),
+        ("pk_seed_row", C.c_void_p), ("pk_node0", C.c_void_p), ("enc_feats", C.c_void_p), ("enc_ptr", C.c_void_p),
+        ("enc_rep", C.c_void_p), ("enc_table", C.c_void_p), ("aggd_h", C.c_void_p), ("aggd_v", C.c_void_p),
+        ("c_x", C.c_void_p), ("c_h", C.c_void_p), ("c_v", C.c_void_p), ("c_agg_h", C.c_void_p), ("c_agg_v", C.c_void_p),
+        ("c_seg_id", C.c_void_p), ("pf_col_c", C.c_void_p),
     ]
 
 

@@ -1,5 +1,8 @@
 // Error state, weight layout query, K5b posterior/COM kernels and the host-side step / loop drivers.
 #include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
 #include <string.h>
 
 #include "pf_common.cuh"
@@ -15,8 +18,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static long long g_launches = 0;
-void count_launch() { ++g_launches; }
+// Process-wide state of the library is limited to DIAGNOSTICS (nothing on the compute path reads it): the launch counter
+// (atomic), the per-site event recorder below (armed only by bench.py's kernel-timing pass, guarded by a mutex) and the
+// device-timeline pointer of pf_tc_trace.  Every compute entry point is a pure function of its arguments.
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::mutex g_prof_mu;
 
 // ---- per-site event timing: pairs are recorded on the launching stream and resolved in pf_profile_collect
 struct ProfPair {
@@ -25,9 +32,11 @@ struct ProfPair {
 };
 static ProfPair* g_pairs = nullptr;
 static int g_pair_cap = 0, g_pair_n = 0, g_pair_open[kNumSites];
-static bool g_prof_on = false;
+static volatile bool g_prof_on = false;
 
 void prof_begin(int site, cudaStream_t st) {
+  if (!g_prof_on) return;   // the common case: one relaxed read, no lock
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_prof_on || g_pair_n >= g_pair_cap) {
     if (g_prof_on) g_pair_open[site] = -1;
     return;
@@ -37,6 +46,8 @@ void prof_begin(int site, cudaStream_t st) {
   g_pair_open[site] = g_pair_n++;
 }
 void prof_end(int site, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_prof_on || g_pair_open[site] < 0) return;
   cudaEventRecord(g_pairs[g_pair_open[site]].b, st);
   g_pair_open[site] = -1;
@@ -181,9 +192,10 @@ using namespace pf;
 extern "C" int pf_abi_version(void) { return PF_ABI_VERSION; }
 extern "C" const char* pf_last_error(void) { return g_err; }
 extern "C" size_t pf_sample_args_size(void) { return sizeof(PfSampleArgs); }
-extern "C" int64_t pf_launch_count(void) { return g_launches; }
+extern "C" int64_t pf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int pf_profile_enable(int32_t max_pairs) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   for (int i = 0; i < g_pair_cap; ++i) {
     cudaEventDestroy(g_pairs[i].a);
     cudaEventDestroy(g_pairs[i].b);
@@ -207,6 +219,7 @@ extern "C" int pf_profile_enable(int32_t max_pairs) {
 
 extern "C" int pf_profile_collect(double* total_ms_host, int32_t* count_host, int32_t n_sites) {
   PF_CHECK_ARG(total_ms_host && count_host && n_sites >= kNumSites, "pf_profile_collect: need >= 11 sites");
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   for (int i = 0; i < n_sites; ++i) {
     total_ms_host[i] = 0.0;
     count_host[i] = 0;
@@ -304,6 +317,7 @@ extern "C" int pf_fill_f32(float* p, int64_t n, float v, void* stream) {
   return PF_OK;
 }
 
+
 #define PF_TRY(call)       \
   do {                     \
     int rc_ = (call);      \
@@ -332,6 +346,76 @@ static int node_update_any(bool f16, const void* w_tc, const float* h_in, const 
   return pf_node_update(h_in, v_in, agg_h, agg_v, n_nodes, w, n_gvps, h_out, v_out, stream);
 }
 
+// The opt-in shared-pocket denoiser (PF_FLAG_SHARE_POCKET_MESSAGES, see pf_share.cu): same kernels as the nominal path, run
+// on the distinct pockets (first-layer pp messages) and on the compact protein rows (everything else on the protein side).
+static int denoiser_shared(const PfSampleArgs* a, void* stream) {
+  const bool f16 = (a->flags & PF_FLAG_FP16_SINGLE_PASS) != 0;
+  PF_CHECK_ARG(a->tile_rows == PF_TC_TILE_ROWS && a->n_convs == 2 && a->n_msg_gvps == 3 && a->n_upd_gvps == 2 &&
+                   (a->flags & PF_FLAG_SKIP_DEAD_WORK),
+               "pf_denoiser: PF_FLAG_SHARE_POCKET_MESSAGES needs the tcgen05 path, n_convs == 2 and PF_FLAG_SKIP_DEAD_WORK");
+  PF_CHECK_ARG(a->seed_row && a->seed_table && a->pk_x && a->pk_start && a->pk_cnt && a->pk_col && a->pk_tiles && a->pk_n_tiles &&
+                   a->pk_seed_row && a->pk_node0 && a->enc_feats && a->enc_ptr && a->enc_rep && a->enc_table && a->aggd_h &&
+                   a->aggd_v && a->c_x && a->c_h && a->c_v && a->c_agg_h && a->c_agg_v && a->c_seg_id && a->pf_col_c,
+               "pf_denoiser: incomplete shared-pocket buffers");
+  const int64_t n_c = (int64_t)a->pf_k * a->n_pharm;
+  const int n_rows = a->n_graphs * a->n_prot_feats;
+  // encoder output per (graph, atom type) instead of per protein node; pharmacophore encoder as usual
+  PF_TRY(pf_encode(a->pharm_h, a->n_pharm_feats, a->pharm_ptr, a->n_graphs, a->t_graph, a->w_pharm_enc, a->pharm_hh, stream));
+  PF_TRY(pf_encode(a->enc_feats, a->n_prot_feats, a->enc_ptr, a->n_graphs, a->t_graph, a->w_prot_enc, a->enc_table, stream));
+  // compact protein rows of this step: coordinates + encoder rows of the fp destinations, compact source ids of the pf edges
+  PF_TRY(pf_share_index(a->pharm_ptr, a->n_graphs, a->pf_k, a->pf_cnt, a->pf_col, a->fp_seg_dst, a->fp_seg_cnt, a->pf_col_c, stream));
+  PF_TRY(pf_share_gather(a->pharm_ptr, a->prot_ptr, a->pk_node0, a->n_graphs, a->pf_k, a->fp_seg_dst, a->prot_x, a->seed_row,
+                         a->enc_table, nullptr, nullptr, a->c_x, a->c_h, nullptr, nullptr, 0, stream));
+  auto conv = f16 ? pf_edge_conv_tc_f16 : pf_edge_conv_tc;
+  auto upd = f16 ? pf_node_update_tc_f16 : pf_node_update_tc;
+  // ---- layer 0.  pharm <- ff (store) + pf (accumulate, sources = compact rows)
+  prof_begin(kSiteFF, as_stream(stream));
+  PF_TRY(conv(a->pharm_hh, nullptr, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col, a->ff_tiles,
+              a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg_tc[0][0], a->pharm_agg_h, a->pharm_agg_v, 0, stream));
+  prof_end(kSiteFF, as_stream(stream));
+  prof_begin(kSitePF, as_stream(stream));
+  PF_TRY(conv(a->c_h, nullptr, a->c_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col_c, a->pf_tiles,
+              a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg_tc[0][1], a->pharm_agg_h, a->pharm_agg_v, 1, stream));
+  prof_end(kSitePF, as_stream(stream));
+  // pp once per DISTINCT pocket (input coordinates: x_src - x_dst is translation invariant)
+  prof_begin(kSitePP, as_stream(stream));
+  PF_TRY(pf_seed_table(a->enc_table, a->enc_rep, n_rows, a->w_msg[0][3], a->seed_table, stream));
+  PF_TRY(pf_edge_conv_tc_seeded(a->pk_seed_row, a->seed_table, a->pk_x, a->pk_x, a->pk_start, a->pk_cnt, nullptr, a->pk_col,
+                                a->pk_tiles, a->pk_n_tiles, a->pk_max_tiles, a->w_msg_tc[0][3], a->aggd_h, a->aggd_v, 0,
+                                f16 ? 1 : 0, stream));
+  prof_end(kSitePP, as_stream(stream));
+  // fp means land in the compact rows (segment slot s -> row s), then the shared pp means join them
+  prof_begin(kSiteFP, as_stream(stream));
+  PF_TRY(conv(a->pharm_hh, nullptr, a->pharm_x, a->c_x, a->fp_seg_start, a->fp_seg_cnt, a->c_seg_id, a->fp_col, a->fp_tiles,
+              a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg_tc[0][2], a->c_agg_h, a->c_agg_v, 0, stream));
+  PF_TRY(pf_share_gather(a->pharm_ptr, a->prot_ptr, a->pk_node0, a->n_graphs, a->pf_k, a->fp_seg_dst, nullptr, nullptr, nullptr,
+                         a->aggd_h, a->aggd_v, nullptr, nullptr, a->c_agg_h, a->c_agg_v, 1, stream));
+  prof_end(kSiteFP, as_stream(stream));
+  prof_begin(kSiteUpdPharm, as_stream(stream));
+  PF_TRY(upd(a->pharm_hh, nullptr, a->pharm_agg_h, a->pharm_agg_v, a->n_pharm, a->w_upd_tc[0][0], a->pharm_hh, a->pharm_v, stream));
+  prof_end(kSiteUpdPharm, as_stream(stream));
+  prof_begin(kSiteUpdProt, as_stream(stream));
+  PF_TRY(upd(a->c_h, nullptr, a->c_agg_h, a->c_agg_v, n_c, a->w_upd_tc[0][1], a->c_h, a->c_v, stream));
+  prof_end(kSiteUpdProt, as_stream(stream));
+  // ---- layer 1 (last): pharmacophore side only
+  prof_begin(kSiteFF, as_stream(stream));
+  PF_TRY(conv(a->pharm_hh, a->pharm_v, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col, a->ff_tiles,
+              a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg_tc[1][0], a->pharm_agg_h, a->pharm_agg_v, 0, stream));
+  prof_end(kSiteFF, as_stream(stream));
+  prof_begin(kSitePF, as_stream(stream));
+  PF_TRY(conv(a->c_h, a->c_v, a->c_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col_c, a->pf_tiles, a->dyn_n_tiles + 1,
+              a->dyn_max_tiles, a->w_msg_tc[1][1], a->pharm_agg_h, a->pharm_agg_v, 1, stream));
+  prof_end(kSitePF, as_stream(stream));
+  prof_begin(kSiteUpdPharm, as_stream(stream));
+  PF_TRY(upd(a->pharm_hh, a->pharm_v, a->pharm_agg_h, a->pharm_agg_v, a->n_pharm, a->w_upd_tc[1][0], a->pharm_hh, a->pharm_v, stream));
+  prof_end(kSiteUpdPharm, as_stream(stream));
+  prof_begin(kSiteNoise, as_stream(stream));
+  PF_TRY(pf_noise_head(a->pharm_hh, a->pharm_v, a->n_pharm, a->w_noise, a->n_noise_gvps, a->n_pharm_feats, a->eps_h, a->eps_x,
+                       stream));
+  prof_end(kSiteNoise, as_stream(stream));
+  return PF_OK;
+}
+
 // One eps prediction: PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185) with a->t_graph already set.
 extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_CHECK_ARG(a != nullptr, "pf_denoiser: null args");
@@ -358,6 +442,7 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                        a->dyn_n_tiles + 1, a->dev_status, stream));
   PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->tile_rows, a->fp_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 2, a->dev_status, stream));
+  if (a->flags & PF_FLAG_SHARE_POCKET_MESSAGES) return denoiser_shared(a, stream);
   // encoders (dynamics_gvp.py:143-151); node vectors start at zero (:162-173) and are never materialised
   PF_TRY(pf_encode(a->pharm_h, a->n_pharm_feats, a->pharm_ptr, a->n_graphs, a->t_graph, a->w_pharm_enc, a->pharm_hh,
                    stream));
