@@ -476,6 +476,28 @@ def main():
     dce = {"value": world * n_graphs * args.steps / (float(ms_dce.item()) / 1e3), "unit": "pharmacophores/s",
            "note": "NOT the headline: same outputs bit for bit, but the last conv layer's pp / fp messages and protein "
                    "node update (never read, dynamics_gvp.py:84-92) are skipped; `value` does the reference's full work"}
+    # ---------------- reported separately as well: the full exact work elimination for sampling (dead work + first-layer pp
+    # messages once per distinct pocket + protein rows only where the last layer reads them; csrc/pf_share.cu)
+    model.dynamics.share_pocket_messages = True
+    resident_step()
+    resident_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        resident_step()
+    e1.record()
+    barrier()
+    model.dynamics.share_pocket_messages = False
+    ms_sh = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_sh, op=dist.ReduceOp.MAX)
+    shared = {"value": world * n_graphs * args.steps / (float(ms_sh.item()) / 1e3), "unit": "pharmacophores/s",
+              "note": "NOT the headline: opt-in sampling mode (dynamics.share_pocket_messages). With one timestep per batch the "
+                      "first conv layer's pp messages depend only on (pocket, t) and only the <= 5 protein atoms per "
+                      "pharmacophore centre that the last layer's pf edges gather are ever read after the first layer; they "
+                      "are computed once per distinct pocket / only for those rows. Equal to the nominal path up to fp32 "
+                      "rounding of x_src - x_dst (tests: 2e-5 against the nominal kernels); `value` does the reference's full "
+                      "work for every sample"}
     # ---------------- reported separately: the single-pass fp16 edge / update MLP mode (configs[3]'s "bf16 edge-MLP
     # path"; 2e-2 tolerance instead of the 1e-4 fp32 bar, see tests/test_gpu_parity.py::test_fp16_single_pass_*)
     f16 = None
@@ -553,7 +575,7 @@ def main():
             "gpu_launches": int(launches), "cuda_graph": bool(graph_on), "clocks": clk.summary(),
             "kernel_timing_pass": {"steps": n_prof, "ms_per_step": ms_prof_total / n_prof,
                                    "note": "per-kernel CUDA-event pairs are recorded in a separate pass right after the "
-                                           "timed region (which runs without them); shares are relative to this pass"}, "exact_dead_work_elimination": dce,
+                                           "timed region (which runs without them); shares are relative to this pass"}, "exact_dead_work_elimination": dce, "exact_shared_pocket_messages": shared,
             "fp16_single_pass": f16,
         }
         print(json.dumps(line), file=_OUT, flush=True)

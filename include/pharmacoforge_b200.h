@@ -347,8 +347,8 @@ int pf_share_index(const int32_t* pharm_ptr, int32_t n_graphs, int32_t pf_k, con
                    const int32_t* fp_seg_dst, const int32_t* fp_seg_cnt, int32_t* pf_col_c, void* stream);
 /* stage 0: c_x / c_h from prot_x and the encoder table; stage 1: c_agg += pp means of the row's distinct node */
 int pf_share_gather(const int32_t* pharm_ptr, const int32_t* prot_ptr, const int32_t* pk_node0, int32_t n_graphs,
-                    int32_t pf_k, const int32_t* fp_seg_dst, const float* prot_x, const int32_t* seed_row,
-                    const float* enc_table, const float* aggd_h, const float* aggd_v, float* c_x, float* c_h,
+                    int32_t pf_k, const int32_t* fp_seg_dst, const int32_t* fp_seg_cnt, const float* prot_x,
+                    const int32_t* seed_row, const float* enc_table, const float* aggd_h, const float* aggd_v, float* c_x, float* c_h,
                     float* c_agg_h, float* c_agg_v, int32_t stage, void* stream);
 
 /* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the

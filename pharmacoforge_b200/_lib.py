@@ -37,7 +37,7 @@ SIGNATURES = {
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
     "pf_share_index": (C.c_int, [c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, STREAM]),
-    "pf_share_gather": (C.c_int, [c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_f32p, c_i32p, c_f32p, c_f32p,
+    "pf_share_gather": (C.c_int, [c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_f32p, c_i32p, c_f32p, c_f32p,
                                   c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, STREAM]),
     "pf_plan_tiles_count": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_void_p, STREAM]),
     "pf_plan_tiles_fill": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p,

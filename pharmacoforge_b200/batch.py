@@ -219,12 +219,53 @@ class GraphBatch:
         pk_x, pk_ptr, g_pk_off, counts, pp_cutoff, pp_max_nbrs = self._k1_inputs
         if os.environ.get("PF_K1", "cell") == "brute" or self.n_graphs == 0:
             return ops.radius_csr(self.prot_x, self.prot_ptr, pp_cutoff, pp_max_nbrs)
-        pk_rowptr, _, pk_col = ops.cell_radius_csr(pk_x, pk_ptr, pp_cutoff, pp_max_nbrs)
+        pk_rowptr, pk_cnt, pk_col = ops.cell_radius_csr(pk_x, pk_ptr, pp_cutoff, pp_max_nbrs)
+        self.pk_csr = (pk_rowptr, pk_cnt, pk_col)      # kept: the shared-pocket mode runs the first layer's pp messages on it
         node0 = g_pk_off.to(torch.int32)
         graph_edges = (pk_rowptr[g_pk_off + counts] - pk_rowptr[g_pk_off]).to(torch.int32)
         edge0 = ops.exclusive_scan(graph_edges)
         n_edges = int(edge0[-1].item())
         return ops.replicate_csr(pk_rowptr, pk_col, node0, self.prot_ptr, edge0, self.n_prot, n_edges)
+
+    def share_arrays(self):
+        """Static arrays of the opt-in shared-pocket mode (dynamics.share_pocket_messages, csrc/pf_share.cu), or None when
+        the batch does not qualify (protein features not one-hot / built with the all-pairs K1): the distinct pockets'
+        coordinates, pp CSR and tile plan, the seed-table row of every distinct node, the first distinct node of every
+        graph's pocket, and the identity inputs of the per-(graph, type) encoder table."""
+        cached = getattr(self, "_share_arrays", False)
+        if cached is not False:
+            return cached
+        self._share_arrays = None
+        if self.seed_arrays() is None or getattr(self, "pk_csr", None) is None or self.n_graphs == 0:
+            return None
+        dev = self.device
+        pk_x, pk_ptr, g_pk_off, counts, _, _ = self._k1_inputs
+        pk_rowptr, pk_cnt, pk_col = self.pk_csr
+        n_d, F, B = int(pk_x.shape[0]), self.n_prot_feats, self.n_graphs
+        tiles = torch.empty(2 * max(n_d + pk_ptr.numel(), 1), dtype=torch.int32, device=dev)
+        n_tiles = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.plan_tiles_ordered(pk_cnt, pk_ptr, False, self.tile_rows, tiles, n_tiles, self.status)
+        n = int(n_tiles.item())
+        # first graph of every distinct pocket (graphs are pocket-major): its (graph, type) rows seed the pocket's messages
+        first_graph = np.full(len(self.pocket_ids), -1, dtype=np.int64)
+        for gi in range(B - 1, -1, -1):
+            first_graph[self.graph_pocket[gi]] = gi
+        pk_sizes = (pk_ptr[1:] - pk_ptr[:-1]).long()
+        node_pocket = torch.repeat_interleave(torch.arange(pk_sizes.numel(), device=dev), pk_sizes, output_size=n_d)
+        # one-hot type of every distinct node: read it back from the replicated features of the pocket's first graph
+        fg = torch.from_numpy(first_graph).to(dev)
+        local = torch.arange(n_d, device=dev) - pk_ptr[:-1].long()[node_pocket]
+        rep_node = self.prot_ptr[:-1].long()[fg[node_pocket]] + local
+        types = self.prot_feats[rep_node].argmax(dim=1)
+        pk_seed_row = (fg[node_pocket] * F + types).to(torch.int32).contiguous()
+        self._share_arrays = dict(
+            pk_x=pk_x.contiguous(), pk_start=pk_rowptr[:-1].contiguous(), pk_cnt=pk_cnt, pk_col=pk_col,
+            pk_tiles=tiles[:2 * max(n, 1)].clone(), pk_n_tiles=n_tiles, pk_max_tiles=n, n_distinct=n_d,
+            pk_seed_row=pk_seed_row, pk_node0=g_pk_off.to(torch.int32).contiguous(),
+            enc_feats=torch.eye(F, device=dev).repeat(B, 1).contiguous(),
+            enc_ptr=(F * torch.arange(B + 1, device=dev)).to(torch.int32),
+            enc_rep=torch.arange(B * F, device=dev, dtype=torch.int32))
+        return self._share_arrays
 
     def seed_arrays(self):
         """(seed_row [n_prot] int32, seed_rep [n_graphs * F] int32) for the first-layer seeding of the pp messages, or

@@ -364,7 +364,7 @@ static int denoiser_shared(const PfSampleArgs* a, void* stream) {
   PF_TRY(pf_encode(a->enc_feats, a->n_prot_feats, a->enc_ptr, a->n_graphs, a->t_graph, a->w_prot_enc, a->enc_table, stream));
   // compact protein rows of this step: coordinates + encoder rows of the fp destinations, compact source ids of the pf edges
   PF_TRY(pf_share_index(a->pharm_ptr, a->n_graphs, a->pf_k, a->pf_cnt, a->pf_col, a->fp_seg_dst, a->fp_seg_cnt, a->pf_col_c, stream));
-  PF_TRY(pf_share_gather(a->pharm_ptr, a->prot_ptr, a->pk_node0, a->n_graphs, a->pf_k, a->fp_seg_dst, a->prot_x, a->seed_row,
+  PF_TRY(pf_share_gather(a->pharm_ptr, a->prot_ptr, a->pk_node0, a->n_graphs, a->pf_k, a->fp_seg_dst, a->fp_seg_cnt, a->prot_x, a->seed_row,
                          a->enc_table, nullptr, nullptr, a->c_x, a->c_h, nullptr, nullptr, 0, stream));
   auto conv = f16 ? pf_edge_conv_tc_f16 : pf_edge_conv_tc;
   auto upd = f16 ? pf_node_update_tc_f16 : pf_node_update_tc;
@@ -388,7 +388,7 @@ static int denoiser_shared(const PfSampleArgs* a, void* stream) {
   prof_begin(kSiteFP, as_stream(stream));
   PF_TRY(conv(a->pharm_hh, nullptr, a->pharm_x, a->c_x, a->fp_seg_start, a->fp_seg_cnt, a->c_seg_id, a->fp_col, a->fp_tiles,
               a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg_tc[0][2], a->c_agg_h, a->c_agg_v, 0, stream));
-  PF_TRY(pf_share_gather(a->pharm_ptr, a->prot_ptr, a->pk_node0, a->n_graphs, a->pf_k, a->fp_seg_dst, nullptr, nullptr, nullptr,
+  PF_TRY(pf_share_gather(a->pharm_ptr, a->prot_ptr, a->pk_node0, a->n_graphs, a->pf_k, a->fp_seg_dst, a->fp_seg_cnt, nullptr, nullptr, nullptr,
                          a->aggd_h, a->aggd_v, nullptr, nullptr, a->c_agg_h, a->c_agg_v, 1, stream));
   prof_end(kSiteFP, as_stream(stream));
   prof_begin(kSiteUpdPharm, as_stream(stream));

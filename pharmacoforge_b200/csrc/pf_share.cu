@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(128) share_index_kernel(const int* __restrict_
 // One warp per slot; empty slots carry dst = first node of the graph (K2's convention) and are processed like any other.
 __global__ void __launch_bounds__(256) share_gather_kernel(const int* __restrict__ pharm_ptr, const int* __restrict__ prot_ptr,
                                                            const int* __restrict__ pk_node0, int n_graphs, int k,
-                                                           const int* __restrict__ fp_seg_dst, const float* __restrict__ prot_x,
+                                                           const int* __restrict__ fp_seg_dst, const int* __restrict__ fp_seg_cnt,
+                                                           const float* __restrict__ prot_x,
                                                            const int* __restrict__ seed_row, const float* __restrict__ enc_table,
                                                            const float* __restrict__ aggd_h, const float* __restrict__ aggd_v,
                                                            float* __restrict__ c_x, float* __restrict__ c_h,
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) share_gather_kernel(const int* __restrict
         if (lane < 3) c_x[row * 3 + lane] = prot_x[(size_t)dst * 3 + lane];
         const float4 v = __ldg(reinterpret_cast<const float4*>(enc_table + (size_t)seed_row[dst] * kHidden) + lane);
         reinterpret_cast<float4*>(c_h + row * kHidden)[lane] = v;
-      } else {
+      } else if (fp_seg_cnt[base + s] > 0) {   // empty slots are never read downstream: leave their rows alone
         const size_t d = (size_t)(dst + shift);
         float4* oh = reinterpret_cast<float4*>(c_agg_h + row * kHidden) + lane;
         const float4 a = __ldg(reinterpret_cast<const float4*>(aggd_h + d * kHidden) + lane);
@@ -103,15 +104,16 @@ extern "C" int pf_share_index(const int32_t* pharm_ptr, int32_t n_graphs, int32_
 }
 
 extern "C" int pf_share_gather(const int32_t* pharm_ptr, const int32_t* prot_ptr, const int32_t* pk_node0, int32_t n_graphs,
-                               int32_t pf_k, const int32_t* fp_seg_dst, const float* prot_x, const int32_t* seed_row,
+                               int32_t pf_k, const int32_t* fp_seg_dst, const int32_t* fp_seg_cnt, const float* prot_x,
+                               const int32_t* seed_row,
                                const float* enc_table, const float* aggd_h, const float* aggd_v, float* c_x, float* c_h,
                                float* c_agg_h, float* c_agg_v, int32_t stage, void* stream) {
-  PF_CHECK_ARG(pharm_ptr && prot_ptr && pk_node0 && fp_seg_dst, "pf_share_gather: null pointer");
+  PF_CHECK_ARG(pharm_ptr && prot_ptr && pk_node0 && fp_seg_dst && fp_seg_cnt, "pf_share_gather: null pointer");
   PF_CHECK_ARG(stage == 0 ? (prot_x && seed_row && enc_table && c_x && c_h) : (aggd_h && aggd_v && c_agg_h && c_agg_v),
                "pf_share_gather: null pointer for this stage");
   if (n_graphs <= 0) return PF_OK;
   const int grid = n_graphs < 16 * num_sms() ? n_graphs : 16 * num_sms();
-  share_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(pharm_ptr, prot_ptr, pk_node0, n_graphs, pf_k, fp_seg_dst, prot_x,
+  share_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(pharm_ptr, prot_ptr, pk_node0, n_graphs, pf_k, fp_seg_dst, fp_seg_cnt, prot_x,
                                                            seed_row, enc_table, aggd_h, aggd_v, c_x, c_h, c_agg_h, c_agg_v, stage);
   PF_CHECK_LAUNCH("pf_share_gather");
   return PF_OK;

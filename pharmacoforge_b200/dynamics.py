@@ -166,6 +166,7 @@ class _DeviceState:
             self.seed_table = torch.zeros(seed_rep.numel(), 128, **f32)
             a.seed_row, a.seed_rep, a.seed_table = seed_row.data_ptr(), seed_rep.data_ptr(), self.seed_table.data_ptr()
             a.n_seed_rows = seed_rep.numel()
+        self.share = None     # buffers of the shared-pocket mode, bound on first use (bind_share)
         if g.tile_rows == 128:
             if w.tc is None:
                 raise NotImplementedError("the tcgen05 message kernel is built for n_message_gvps=3 (configs/dev.yml); "
@@ -179,6 +180,32 @@ class _DeviceState:
         self.args = a
         self.weights = w          # keep alive
         self.batch_buffers = (g.prot_x, g.pharm_x, g.pharm_h)
+
+    def bind_share(self, g: GraphBatch) -> bool:
+        """Bind the static arrays and scratch of the shared-pocket mode; False when the batch does not qualify."""
+        if self.share is not None:
+            return True
+        sh = g.share_arrays()
+        if sh is None or self.seed is None:
+            return False
+        dev, a = g.device, self.args
+        f32 = dict(dtype=torch.float32, device=dev)
+        n_c, n_d, rows = max(g.pf_k * g.n_pharm, 1), sh["n_distinct"], sh["enc_rep"].numel()
+        buf = dict(enc_table=torch.zeros(rows, 128, **f32), aggd_h=torch.zeros(n_d, 128, **f32),
+                   aggd_v=torch.zeros(n_d, 48, **f32), c_x=torch.zeros(n_c, 3, **f32), c_h=torch.zeros(n_c, 128, **f32),
+                   c_v=torch.zeros(n_c, 48, **f32), c_agg_h=torch.zeros(n_c, 128, **f32), c_agg_v=torch.zeros(n_c, 48, **f32),
+                   c_seg_id=torch.arange(n_c, dtype=torch.int32, device=dev),
+                   pf_col_c=torch.zeros(n_c, dtype=torch.int32, device=dev))
+        for name in ("pk_x", "pk_start", "pk_cnt", "pk_col", "pk_tiles", "pk_n_tiles", "pk_seed_row", "pk_node0", "enc_feats",
+                     "enc_ptr", "enc_rep"):
+            setattr(a, name, sh[name].data_ptr())
+        for name, t in buf.items():
+            setattr(a, name, t.data_ptr())
+        a.pk_max_tiles, a.n_distinct = sh["pk_max_tiles"], n_d
+        if self.seed_table.shape[0] < rows:      # the table is indexed by (graph, type) in both modes: same size
+            raise AssertionError("seed table smaller than the encoder table")
+        self.share = (sh, buf)                   # keep alive
+        return True
 
     @property
     def addr(self) -> int:
@@ -229,6 +256,11 @@ class PharmRecDynamicsGVP(nn.Module):
         # (graph, atom type) table instead of a per-edge gather + contraction (SURVEY.md hard part 2's exact split; needs
         # one-hot protein features, checked per batch).  False = the general kernel, the A/B switch of the parity tests.
         self.layer0_seed = True
+        # Opt-in exact work elimination for SAMPLING (SURVEY.md hard part 5a + 5b + 5c, csrc/pf_share.cu): first-layer pp
+        # messages once per distinct pocket, protein rows encoded / updated only where the last layer reads them.  Needs
+        # the same timestep for every graph (the reverse-diffusion loop; forward() checks it) and one-hot protein
+        # features; equals the nominal path up to fp32 rounding of x_src - x_dst.  Never the default, never the headline.
+        self.share_pocket_messages = False
         # Direct callers of forward() get the device status word checked on every call (one 4-byte D2H sync);
         # PharmacophoreDiff's own loops check once at their end and switch this off around their calls.
         self.check_status_every_call = True
@@ -255,9 +287,16 @@ class PharmRecDynamicsGVP(nn.Module):
             g._pf_state = st
         if self.edge_mlp_precision not in ("fp32", "fp16"):
             raise ValueError("edge_mlp_precision must be 'fp32' or 'fp16'")
-        st.args.flags = ((1 if self.skip_dead_work else 0) |               # PF_FLAG_SKIP_DEAD_WORK
+        share = False
+        if self.share_pocket_messages:
+            if self.n_convs != 2 or self.n_message_gvps != 3 or self.n_update_gvps != 2 or g.tile_rows != 128:
+                raise NotImplementedError("share_pocket_messages is built for the dev.yml shape (n_convs=2, 3 message / 2 "
+                                          "update GVPs) on the tcgen05 path")
+            share = st.bind_share(g)             # False: the batch does not qualify (features not one-hot): nominal path
+        st.args.flags = ((1 if (self.skip_dead_work or share) else 0) |     # PF_FLAG_SKIP_DEAD_WORK
                          (2 if self.edge_mlp_precision == "fp16" else 0) |  # PF_FLAG_FP16_SINGLE_PASS
-                         (0 if self.layer0_seed else 4))                    # PF_FLAG_NO_LAYER0_SEED
+                         (0 if self.layer0_seed else 4) |                   # PF_FLAG_NO_LAYER0_SEED
+                         (8 if share else 0))                               # PF_FLAG_SHARE_POCKET_MESSAGES
         return st
 
     # ------------------------------------------------------------------ forward
@@ -267,7 +306,10 @@ class PharmRecDynamicsGVP(nn.Module):
             raise NotImplementedError("the fused kernels implement eval-mode semantics (no dropout, no autograd graph): call "
                                       ".eval(), or train through PharmacophoreDiff.training_step (train_graph.py)")
         st = self.bind(g)
-        st.t_graph.copy_(timestep.to(device=g.device, dtype=torch.float32).reshape(-1))
+        tt = timestep.to(device=g.device, dtype=torch.float32).reshape(-1)
+        if (st.args.flags & 8) and tt.numel() > 1 and not bool((tt == tt[0]).all().item()):
+            raise ValueError("share_pocket_messages needs the same timestep for every graph of the batch")
+        st.t_graph.copy_(tt)
         ops.denoiser(st.eps_h, st.eps_x, st.addr)
         if self.check_status_every_call:
             g.check_status()   # device-detected conditions (degree / tile / edge overflow) must not pass silently

@@ -967,6 +967,61 @@ def test_forward_loss_matches_reference(env, golden, sd, dyn_cfg):
     assert abs(float(losses["val total loss"]) - float(g["val_pos_loss"]) - float(g["val_feat_loss"])) < 1e-3
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_shared_pocket_messages_match_nominal(env, precision):
+    """dynamics.share_pocket_messages (SURVEY.md hard part 5a + 5b + 5c, opt-in): first-layer pp messages once per distinct
+    pocket, protein rows encoded / updated only where the last layer's pf edges read them.  eps equals the nominal path up
+    to fp32 rounding of x_src - x_dst (bar 2e-5, well inside the 1e-4 parity bar), over a ragged batch with several samples
+    per pocket, a graph_range that starts mid-pocket, and a short sampling run; per-graph timesteps are rejected."""
+    dyn = env.model.dynamics
+    pk = [env.make_pocket(n, seed=s) for n, s in ((400, 0), (120, 2), (250, 1))]
+    pockets = [env.Pocket.from_numpy(p, h) for p, h in pk]
+    sizes = [[3, 8, 5, 4], [4, 6], [7, 3, 5]]
+    gr = range(1, 9)
+    g = env.GraphBatch.from_pockets(pockets, sizes, env.dev, graph_range=gr)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(g.n_pharm, 3, generator=gen) * 3.0
+    h = torch.randn(g.n_pharm, 6, generator=gen)
+    # sampler frame: proteins centred near their pharmacophores
+    bidx = g.batch_idxs()["prot"].cpu()
+    com = torch.stack([g.prot_x0.cpu()[bidx == i].mean(0) for i in range(g.n_graphs)])
+    prot = g.prot_x0.cpu() - com[bidx] + torch.randn(g.n_graphs, 3, generator=gen)[bidx]
+    tt = torch.full((g.n_graphs,), 0.37)
+    old = (dyn.edge_mlp_precision, dyn.share_pocket_messages, dyn.skip_dead_work)
+    try:
+        dyn.edge_mlp_precision = precision
+        res = {}
+        for share in (False, True):
+            dyn.share_pocket_messages = share
+            g.pharm_h = h.cuda().clone()
+            g.pharm_x.copy_(x.cuda())
+            g.prot_x.copy_(prot.cuda())
+            eh, ex = dyn(g, tt, None)
+            res[share] = (eh.clone(), ex.clone())
+        st = dyn.bind(g)
+        assert st.share is not None and (st.args.flags & 8)
+        if precision == "fp32":
+            close(res[True][0], res[False][0], rtol=2e-5, atol=2e-6, what="eps_h shared vs nominal")
+            close(res[True][1], res[False][1], rtol=2e-5, atol=2e-6, what="eps_x shared vs nominal")
+        else:   # single-pass fp16: rounding of x_diff moves fp16 operands by an ulp here and there
+            within(res[True][0], res[False][0], 2e-3, what="eps_h shared vs nominal (fp16)")
+            within(res[True][1], res[False][1], 2e-3, what="eps_x shared vs nominal (fp16)")
+        with pytest.raises(ValueError):
+            dyn(g, torch.linspace(0.1, 0.9, g.n_graphs), None)
+        # a short reverse-diffusion run in both modes with the same injected noise
+        noise = torch.randn(9, g.n_pharm, 9, generator=gen)
+        runs = {}
+        for share in (False, True):
+            dyn.share_pocket_messages = share
+            g.prot_x.copy_(g.prot_x0)
+            runs[share] = env.model.sample_given_receptor(g, noise=noise, n_steps=8, return_tensors=True)
+        tol = dict(rtol=1e-4, atol=1e-4) if precision == "fp32" else dict(rtol=5e-2, atol=5e-2)
+        close(runs[True][0], runs[False][0], what="x after 8 steps", **tol)
+        close(runs[True][1], runs[False][1], what="h after 8 steps", **tol)
+    finally:
+        dyn.edge_mlp_precision, dyn.share_pocket_messages, dyn.skip_dead_work = old
+
+
 def test_dead_work_elimination_is_bit_exact(env):
     """skip_dead_work drops the last layer's protein-side kernels (never read, dynamics_gvp.py:84-92): the sampled
     pharmacophores must not change by a single bit."""
