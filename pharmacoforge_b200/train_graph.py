@@ -15,9 +15,16 @@ from typing import Dict, Tuple
 import torch
 import torch.nn as nn
 
+import os
+
 from . import ops
+from . import train_fused as F
 from . import train_ops as T
 from .batch import GraphBatch
+
+# One autograd node per message chain / node update (train_fused.py) instead of one per kernel: same kernels, same
+# numbers, ~8x fewer autograd records and op dispatches.  PF_TRAIN_HOST=ops selects the op-by-op graph (A/B, tests).
+HOST_FUSED = os.environ.get("PF_TRAIN_HOST", "fused") != "ops"
 
 
 def gvp_forward(m, feats: torch.Tensor, vec: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -87,8 +94,25 @@ def build_edges(g: GraphBatch) -> Dict[str, dict]:
     return out
 
 
+def conv_forward_fused(conv, feats, edges, geom, training: bool):
+    """`conv_forward` with one autograd node per edge type and per node type (train_fused.py)."""
+    agg = {}
+    for name in ("ff", "pf", "fp", "pp"):                         # reference etype order (dynamics_gvp.py:46-54)
+        e = edges[name]
+        key = f"{e['src_nt']}_{name}_{e['dst_nt']}"
+        h_src, v_src = feats[e["src_nt"]]
+        xd, rbf = geom[name]
+        a_h, a_v = F.message_chain(conv.edge_message_fns[key], h_src, v_src, xd, rbf, e)
+        prev = agg.get(e["dst_nt"])
+        agg[e["dst_nt"]] = (a_h, a_v) if prev is None else (prev[0] + a_h, prev[1] + a_v)   # cross_reducer="sum"
+    return {nt: F.node_update(conv, nt, feats[nt][0], feats[nt][1], agg[nt][0], agg[nt][1], training)
+            for nt in ("pharm", "prot")}
+
+
 def conv_forward(conv, feats, edges, geom, training: bool):
     """GVPMultiEdgeConv.forward (gvp.py:459-538) for message_norm='mean'.  feats[ntype] = (h [N,128], v [N,3,16])."""
+    if HOST_FUSED:
+        return conv_forward_fused(conv, feats, edges, geom, training)
     agg = {}
     for name in ("ff", "pf", "fp", "pp"):                         # reference etype order (dynamics_gvp.py:46-54)
         e = edges[name]
@@ -139,7 +163,10 @@ def dynamics_forward(dyn, g: GraphBatch, t: torch.Tensor, training: bool = True)
         feats = conv_forward(conv, feats, edges, geom, training)
     head = dyn.noise_predictor.noise_predictor
     sca, vec = feats["pharm"]
-    for m in head.gvps:
-        sca, vec = gvp_forward(m, sca, vec)
+    if HOST_FUSED:
+        sca, vec = F.gvp_stack(head.gvps, sca, vec)
+    else:
+        for m in head.gvps:
+            sca, vec = gvp_forward(m, sca, vec)
     eps_h = T.linear(sca, head.to_scalar_output.weight, head.to_scalar_output.bias)
     return eps_h, vec.reshape(vec.shape[0], 3)

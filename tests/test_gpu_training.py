@@ -240,3 +240,44 @@ def test_dataset_items_collate_into_a_training_batch(tmp_path, sd, dyn_cfg):
     total, losses, metrics = model.training_step(g)
     total.backward()
     assert np.isfinite(float(total)) and model.dynamics.pharm_encoder[0].weight.grad is not None
+
+
+def test_fused_host_graph_matches_op_by_op_graph(sd, dyn_cfg):
+    """train_fused.py (one autograd node per message chain / node update / noise-head stack) against the op-by-op graph
+    of train_graph.py on the same batch, weights, (t, eps) and dropout masks (same seed -> same draws in the same order):
+    same kernels in the same order, so losses are equal and gradients differ only by the float atomics of the
+    LayerNorm / scatter backward kernels."""
+    from pharmacoforge_b200 import train_graph
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    pockets = [Pocket.from_numpy(*make_pocket(120 + 30 * i, seed=70 + i)) for i in range(3)]
+    sizes = [[5], [4], [7]]
+    nf = sum(s[0] for s in sizes)
+    gen = torch.Generator().manual_seed(11)
+    h0 = torch.nn.functional.one_hot(torch.randint(0, 6, (nf,), generator=gen), 6).float()
+    x0 = torch.cat([p.prot_x.mean(0, keepdim=True) + torch.randn(s[0], 3, generator=gen) for p, s in zip(pockets, sizes)])
+    t_int = torch.tensor([15, 55, 90])
+    eps = {"x": torch.randn(nf, 3, generator=gen), "h": torch.randn(nf, 6, generator=gen)}
+    model = _model(sd, dyn_cfg, dropout=0.2).train()
+    res = []
+    was = train_graph.HOST_FUSED
+    try:
+        for fused in (True, False):
+            train_graph.HOST_FUSED = fused
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(123)
+            gb = GraphBatch.from_pockets(pockets, sizes, "cuda:0").set_pharmacophores(x0, h0)
+            total, _, _ = model.training_step(gb, t_int=t_int, eps=eps)
+            total.backward()
+            res.append((float(total), {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}))
+    finally:
+        train_graph.HOST_FUSED = was
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * max(1.0, abs(res[1][0])), (res[0][0], res[1][0])
+    n_live = 0
+    for n, ga in res[0][1].items():
+        gb_ = res[1][1][n]
+        assert (ga is None) == (gb_ is None), n
+        if ga is not None and ga.numel():
+            n_live += 1
+            close(ga, gb_, rtol=1e-4, what=n)
+    assert n_live >= 190
