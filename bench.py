@@ -421,8 +421,13 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "edge_pp_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = tj["dram_bytes_per_edge"] * n_pp_edges     # ncu capture at 8 pockets, scaled per edge
-        tnote = (f"; traffic = {tj['dram_bytes_per_edge']:.0f} B/edge (ncu --set full at 8 pockets) x edges; ncu tensor "
+        # ncu --set full AT BENCH SCALE (256 pockets x 30): average of the seeded layer-0 launch and the general layer-1
+        # launch, per edge; at other batch sizes the per-edge figure is scaled by the edge count
+        traffic = tj["dram_bytes_per_edge"] * n_pp_edges
+        tnote = (f"; traffic = {tj['dram_bytes_per_edge']:.0f} B/edge x edges (ncu --set full at {tj['edges_per_launch']} "
+                 f"edges per launch, mean of the seeded layer-0 and the general layer-1 launch: "
+                 f"{(tj['seeded']['dram_bytes_read'] + tj['seeded']['dram_bytes_write']) / 1e9:.2f} / "
+                 f"{(tj['layer1']['dram_bytes_read'] + tj['layer1']['dram_bytes_write']) / 1e9:.2f} GB); ncu tensor "
                  f"pipe active {tj['sm__pipe_tensor_cycles_active_pct']}% (3 fp16 passes per product)")
     tc_path = g.tile_rows == 128
     roofline = {"kernel": ("edge_conv_tc_kernel" if tc_path else "edge_conv_kernel") + " (pp edges)", "bound": "tensor",

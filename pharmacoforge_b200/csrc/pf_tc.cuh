@@ -61,6 +61,42 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gmem_src, uint32_t 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 
+// L2 eviction-priority hints (createpolicy + .L2::cache_hint).  evict_last: lines that are re-read soon (a tile's normalised
+// rows between the front and the back end of the node update); evict_first: streaming data that is dead after this access.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_global_hint(float4* ptr, const float4 v, const uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_global_hint(const float4* ptr, const uint64_t pol) {  // plain (coherent) load
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* ptr, const uint64_t pol) {  // read-only path
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2_evict_last(const void* gmem) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(gmem));
+}
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

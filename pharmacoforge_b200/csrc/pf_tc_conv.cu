@@ -137,6 +137,13 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
 #ifndef PF_K4_TILE_ALT
 #define PF_K4_TILE_ALT 0
 #endif
+#ifndef PF_K4_L2HINT
+#define PF_K4_L2HINT 15  // (default: all four, measured 3.09 / 3.12 -> 2.99 / 3.00 ms at 3.07 M nodes, identical outputs)
+                         // node update, L2 eviction hints (bits): 1 = the normalised rows written by the front end and re-read
+                         // by the back end are stored evict_last; 2 = the input rows (h_in, agg_h, v_in, agg_v) and the
+                         // residual re-reads are loaded evict_first; 4 = the final rows are stored evict_first; 8 = the
+                         // next tile's L2 prefetch asks for evict_last
+#endif
 #ifndef PF_K4_CTA_STAGGER_NS
 #define PF_K4_CTA_STAGGER_NS 0
 #endif
@@ -1240,8 +1247,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row < nrows) {
             const size_t o = (size_t)(n0 + row) * kHidden + 32 * (2 * hh + c2) + 4 * piece;
+#if PF_K4_L2HINT & 2
+            x = tc::ld_global_hint(reinterpret_cast<const float4*>(p.h_in + o), tc::l2_policy_evict_first());
+            const float4 a = tc::ldg_hint(reinterpret_cast<const float4*>(p.agg_h + o), tc::l2_policy_evict_first());
+#else
             x = *reinterpret_cast<const float4*>(p.h_in + o);  // plain load: h_out may alias h_in
             const float4 a = __ldg(reinterpret_cast<const float4*>(p.agg_h + o));
+#endif
             x.x += a.x;
             x.y += a.y;
             x.z += a.z;
@@ -1278,7 +1290,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           y.y = (y.y - mean) * rstd * lw.y + lb.y;
           y.z = (y.z - mean) * rstd * lw.z + lb.z;
           y.w = (y.w - mean) * rstd * lw.w + lb.w;
+#if PF_K4_L2HINT & 1
+          if (row < nrows)
+            tc::st_global_hint(reinterpret_cast<float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece), y,
+                               tc::l2_policy_evict_last());
+#else
           if (row < nrows) *reinterpret_cast<float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece) = y;
+#endif
           *reinterpret_cast<float4*>(tb + (4 * i + prow) * 36 + 4 * piece) = y;
         }
         __syncwarp();
@@ -1328,8 +1346,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
             as[k] = xs[k];
             if (row < nrows) {
               const size_t o = (size_t)(n0 + row) * kVRow + 4 * pc;
+#if PF_K4_L2HINT & 2
+              xs[k] = tc::ldg_hint(reinterpret_cast<const float4*>(p.agg_v + o), tc::l2_policy_evict_first());
+              if constexpr (HAS_V) as[k] = tc::ld_global_hint(reinterpret_cast<const float4*>(p.v_in + o), tc::l2_policy_evict_first());
+#else
               xs[k] = __ldg(reinterpret_cast<const float4*>(p.agg_v + o));
               if constexpr (HAS_V) as[k] = *reinterpret_cast<const float4*>(p.v_in + o);
+#endif
             }
           }
 #pragma unroll
@@ -1368,7 +1391,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           Vu[8 * c + 4 * u4 + 1] = x.y;
           Vu[8 * c + 4 * u4 + 2] = x.z;
           Vu[8 * c + 4 * u4 + 3] = x.w;
+#if PF_K4_L2HINT & 1
+          if (et < nrows)
+            tc::st_global_hint(reinterpret_cast<float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4), x,
+                               tc::l2_policy_evict_last());
+#else
           if (et < nrows) *reinterpret_cast<float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4) = x;
+#endif
           pm = fmaxf(fmaxf(pm, fabsf(x.x)), fmaxf(fabsf(x.y), fmaxf(fabsf(x.z), fabsf(x.w))));
         }
       s_xch[et * 2 + hh].z = pm;
@@ -1397,14 +1426,20 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       const long long mrem = p.n_nodes - m0;
       const int mrows = mrem < kRows ? (int)mrem : kRows;
       const int lines_h = mrows * 4, lines_v = (mrows * kVRow * 4 + 127) / 128;  // 128-byte lines
+#if PF_K4_L2HINT & 8
+#define PF_K4_PREFETCH tc::prefetch_l2_evict_last
+#else
+#define PF_K4_PREFETCH tc::prefetch_l2
+#endif
       for (int l = stid; l < lines_h; l += 256) {
-        tc::prefetch_l2(reinterpret_cast<const char*>(p.h_in + m0 * kHidden) + (size_t)l * 128);
-        tc::prefetch_l2(reinterpret_cast<const char*>(p.agg_h + m0 * kHidden) + (size_t)l * 128);
+        PF_K4_PREFETCH(reinterpret_cast<const char*>(p.h_in + m0 * kHidden) + (size_t)l * 128);
+        PF_K4_PREFETCH(reinterpret_cast<const char*>(p.agg_h + m0 * kHidden) + (size_t)l * 128);
       }
       for (int l = stid; l < lines_v; l += 256) {
-        tc::prefetch_l2(reinterpret_cast<const char*>(p.agg_v + m0 * kVRow) + (size_t)l * 128);
-        if constexpr (HAS_V) tc::prefetch_l2(reinterpret_cast<const char*>(p.v_in + m0 * kVRow) + (size_t)l * 128);
+        PF_K4_PREFETCH(reinterpret_cast<const char*>(p.agg_v + m0 * kVRow) + (size_t)l * 128);
+        if constexpr (HAS_V) PF_K4_PREFETCH(reinterpret_cast<const char*>(p.v_in + m0 * kVRow) + (size_t)l * 128);
       }
+#undef PF_K4_PREFETCH
     }
 #pragma unroll 1
     for (int g = 0; g < 2; ++g) {
@@ -1548,7 +1583,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 #pragma unroll
         for (int u4 = 0; u4 < 2; ++u4) {
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+#if PF_K4_L2HINT & 2
+          if (et < nrows)
+            x = tc::ld_global_hint(reinterpret_cast<const float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4),
+                                   tc::l2_policy_evict_first());
+#else
           if (et < nrows) x = *reinterpret_cast<const float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4);
+#endif
           Vu[8 * c + 4 * u4] += x.x;
           Vu[8 * c + 4 * u4 + 1] += x.y;
           Vu[8 * c + 4 * u4 + 2] += x.z;
@@ -1572,7 +1613,12 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
               x.y = Vu[8 * c + 4 * u4 + 1] * ivn;
               x.z = Vu[8 * c + 4 * u4 + 2] * ivn;
               x.w = Vu[8 * c + 4 * u4 + 3] * ivn;
+#if PF_K4_L2HINT & 4
+              tc::st_global_hint(reinterpret_cast<float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4), x,
+                                 tc::l2_policy_evict_first());
+#else
               *reinterpret_cast<float4*>(p.v_out + (size_t)(n0 + et) * kVRow + 16 * c + 8 * hh + 4 * u4) = x;
+#endif
             }
         }
       }
@@ -1587,7 +1633,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         for (int i = 0; i < 8; ++i) {
           const int row = 32 * q + 4 * i + prow;
           xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#if PF_K4_L2HINT & 2
+          if (row < nrows)
+            xr[i] = tc::ld_global_hint(reinterpret_cast<const float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece),
+                                       tc::l2_policy_evict_first());
+#else
           if (row < nrows) xr[i] = *reinterpret_cast<const float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece);
+#endif
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(tb + (4 * i + prow) * 36 + 4 * piece) = xr[i];
@@ -1646,7 +1698,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         for (int i = 0; i < 8; ++i) {
           const int row = 32 * q + 4 * i + prow;
           const float4 x = *reinterpret_cast<const float4*>(tb + (4 * i + prow) * 36 + 4 * piece);
+#if PF_K4_L2HINT & 4
+          if (row < nrows)
+            tc::st_global_hint(reinterpret_cast<float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece), x,
+                               tc::l2_policy_evict_first());
+#else
           if (row < nrows) *reinterpret_cast<float4*>(p.h_out + (size_t)(n0 + row) * kHidden + 32 * c + 4 * piece) = x;
+#endif
         }
         __syncwarp();
       }

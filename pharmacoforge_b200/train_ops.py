@@ -35,6 +35,11 @@ def _workspace(device):
     return ws
 
 
+def _raw(t: torch.Tensor) -> int:
+    """Device address of a buffer the calling op allocated itself (no validation: see ops._p for the checked form)."""
+    return t.data_ptr()
+
+
 def _ws_args(device):
     ws = _workspace(device)
     return (C.c_void_p(ws.data_ptr()), ws.numel() * 4) if ws is not None else (None, 0)
@@ -383,8 +388,9 @@ def _gvp_fwd(feats: torch.Tensor, vec: torch.Tensor, Wh: torch.Tensor, Wu: torch
     vo, no = Wu.shape[1], Wf.shape[0]
     e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=feats.device)
     Vh, Vu, s, z, f, gates, vout = e(3 * M, h), e(3 * M, vo), e(M, n + h), e(M, no), e(M, no), e(M, vo), e(M, 3, vo)
+    q = _raw   # buffers allocated right here: fp32, contiguous, on the inputs' device -- no need to re-validate them
     _lib.check(_L.pf_train_gvp_fwd(_f(feats), _f(vec), _f(Wh), _f(Wu), _f(Wf), _f(bf), _f(Wg), _f(bg), M, n, vi, h, vo, no,
-                                   int(act_sigmoid), _f(Vh), _f(Vu), _f(s), _f(z), _f(f), _f(gates), _f(vout),
+                                   int(act_sigmoid), q(Vh), q(Vu), q(s), q(z), q(f), q(gates), q(vout),
                                    *_ws_args(feats.device), _s()), "pf_train_gvp_fwd")
     return f, vout, Vh, Vu, s, z, gates
 
@@ -407,14 +413,23 @@ def _gvp_bwd(vec: torch.Tensor, Wh: torch.Tensor, Wu: torch.Tensor, Wf: torch.Te
     vo, no = Wu.shape[1], Wf.shape[0]
     n = Wf.shape[1] - h
     e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=z.device)
-    dgates, dVu, dfz, ds, dVh = e(M, vo), e(3 * M, vo), e(M, no), e(M, n + h), e(3 * M, h)
+    # the five per-row temporaries (dgates, dVu, dfz, ds, dVh) share one allocation: they never leave this call
+    al = lambda k: (k + 63) & ~63
+    offs, tot = [], 0
+    for k in (M * vo, 3 * M * vo, M * no, M * (n + h), 3 * M * h):
+        offs.append(tot)
+        tot += al(k)
+    tmp = e(max(tot, 1))
+    t0 = tmp.data_ptr()
+    dgates, dVu, dfz, ds, dVh = (t0 + 4 * o for o in offs)
     dfeats, dvec = e(M, n), e(M, 3, vi)
     dWh, dWu, dWf, dWg = e(vi, h), e(h, vo), e(no, n + h), e(vo, no)
     dbf, dbg = torch.zeros(no, device=z.device), torch.zeros(vo, device=z.device)
+    q = _raw
     _lib.check(_L.pf_train_gvp_bwd(_f(vec), _f(Wh), _f(Wu), _f(Wf), _f(Wg), _f(Vh), _f(Vu), _f(s), _f(z), _f(f), _f(gates),
-                                   _f(df), _f(dvout), M, n, vi, h, vo, no, int(act_sigmoid), _f(dgates), _f(dVu), _f(dfz),
-                                   _f(ds), _f(dVh), _f(dfeats), _f(dvec), _f(dWh), _f(dWu), _f(dWf), _f(dbf), _f(dWg),
-                                   _f(dbg), *_ws_args(z.device), _s()), "pf_train_gvp_bwd")
+                                   _f(df), _f(dvout), M, n, vi, h, vo, no, int(act_sigmoid), dgates, dVu, dfz,
+                                   ds, dVh, q(dfeats), q(dvec), q(dWh), q(dWu), q(dWf), q(dbf), q(dWg),
+                                   q(dbg), *_ws_args(z.device), _s()), "pf_train_gvp_bwd")
     return dfeats, dvec, dWh, dWu, dWf, dbf, dWg, dbg
 
 
