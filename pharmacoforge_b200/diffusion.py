@@ -431,6 +431,9 @@ class PharmacophoreDiff(nn.Module):
         """pharmacodiff.py:254-263: Adam(base_lr, weight_decay) + ReduceLROnPlateau from lr_scheduler_config."""
         cfg = self.lr_scheduler_config or {}
         opt = torch.optim.Adam(self.parameters(), lr=cfg.get("base_lr", 1e-4), weight_decay=cfg.get("weight_decay", 0.0))
+        # The packed kernel weights are cached on (data_ptr, _version) of every parameter.  Not every in-place update
+        # bumps the version counter (measured: torch.optim.Adam(fused=True) does not), so a step also drops the cache.
+        opt.register_step_post_hook(lambda *_: setattr(self.dynamics, "_packed_key", None))
         sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, **cfg.get("reducelronplateau", {}))
         return {"optimizer": opt, "lr_scheduler": {"scheduler": sched, "monitor": cfg.get("monitor"),
                                                    "interval": cfg.get("interval"), "frequency": cfg.get("frequency")}}
