@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 2
+#define PF_ABI_VERSION 3
 
 enum PfStatus {
   PF_OK = 0,
@@ -244,6 +244,19 @@ int pf_posterior_step_philox(float* pharm_x, float* pharm_h, int32_t nh, const f
                              void* stream);
 int pf_philox_normal(float* out, int64_t n, const uint64_t* seed_dev, uint32_t stream_id, uint32_t step, void* stream);
 
+/* The same step for models trained with the ENDPOINT parameterisation (pharmacodiff.py:413-418; `endpoint_param_coord` /
+ * `endpoint_param_feat`: the network output is the predicted x_0 / h_0 instead of eps):
+ *   mu = ep_c1 * z_t + ep_c2 * pred,  ep_c1 = alpha_{t|s} sigma_s^2 / sigma_t^2,  ep_c2 = alpha_s sigma^2_{t|s} / sigma_t^2
+ * for the parts selected by ep_mode (PF_EP_COORD: x, PF_EP_FEAT: h); the other part keeps the eps form.  Noise: pass
+ * noise_x and noise_h (injected), or both NULL and seed_dev / noise_step (in-kernel Philox). */
+#define PF_EP_COORD 1
+#define PF_EP_FEAT 2
+int pf_posterior_step_ep(float* pharm_x, float* pharm_h, int32_t nh, const float* pred_x, const float* pred_h,
+                         const float* noise_x, const float* noise_h, const uint64_t* seed_dev, uint32_t noise_step,
+                         const int32_t* pharm_ptr, float* prot_x, const int32_t* prot_ptr, int32_t n_graphs,
+                         float alpha_ts, float var_terms, float sigma_q, float ep_c1, float ep_c2, int32_t ep_mode,
+                         void* stream);
+
 /* per-graph mean of x over [ptr[g], ptr[g+1]) -> com[g][3]; and x[n] += sign * com[graph(n)]
  * (dgl.readout_nodes + broadcast subtract/add, pharmacodiff.py:442-452,483-486) */
 int pf_segment_mean3(const float* x, const int32_t* ptr, int32_t n_graphs, float* com, void* stream);
@@ -327,6 +340,10 @@ typedef struct PfSampleArgs {
   float *c_x, *c_h, *c_v, *c_agg_h, *c_agg_v; /* compact protein rows, one per fp segment slot: [pf_k * n_pharm][...] */
   const int32_t* c_seg_id;     /* [pf_k * n_pharm] identity */
   int32_t* pf_col_c;           /* [pf_k * n_pharm] compact source row of every pf edge */
+  /* endpoint parameterisation (pf_posterior_step_ep): per-step coefficient tables (host) and the PF_EP_* mode bits;
+   * ep_mode == 0 (configs/dev.yml) leaves the eps form of every step */
+  const float *ep_c1_host, *ep_c2_host;
+  int32_t ep_mode;
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph

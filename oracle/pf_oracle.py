@@ -66,6 +66,20 @@ def posterior_coefficients(gamma_s: torch.Tensor, gamma_t: torch.Tensor):
     return alpha_ts, var_terms, sigma_q
 
 
+def endpoint_coefficients(gamma_s: torch.Tensor, gamma_t: torch.Tensor):
+    """The endpoint-parameterisation branch of sample_p_zs_given_zt (pharmacodiff.py:413-418):
+    mu = c1 z_t + c2 pred with c1 = alpha_{t|s} sigma_s^2 / sigma_t^2, c2 = alpha_s sigma^2_{t|s} / sigma_t^2,
+    evaluated with the reference's operator order."""
+    sigma2_ts = -torch.expm1(F.softplus(gamma_s) - F.softplus(gamma_t))
+    log_a2_t = F.logsigmoid(-gamma_t)
+    log_a2_s = F.logsigmoid(-gamma_s)
+    alpha_ts = torch.exp(0.5 * (log_a2_t - log_a2_s))
+    alpha_s = torch.exp(0.5 * log_a2_s)
+    sigma_s = torch.sqrt(torch.sigmoid(gamma_s))
+    sigma_t = torch.sqrt(torch.sigmoid(gamma_t))
+    return alpha_ts * (sigma_s ** 2) / (sigma_t ** 2), alpha_s * sigma2_ts / (sigma_t ** 2)
+
+
 # --------------------------------------------------------------------------- graph construction
 def _sqdist(q: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
     """Canonical fp32 squared distance ((dx*dx + dy*dy) + dz*dz), no FMA."""
@@ -343,8 +357,9 @@ def remove_pharm_com(b: FlatBatch):
     b.prot_x = b.prot_x - com[b.prot_b]
 
 
-def reverse_step(sd, b: FlatBatch, s_int: int, T: int, gamma: torch.Tensor, cfg: dict, noise_x, noise_h):
-    """sample_p_zs_given_zt, pharmacodiff.py:380-431 (eps parameterisation)."""
+def reverse_step(sd, b: FlatBatch, s_int: int, T: int, gamma: torch.Tensor, cfg: dict, noise_x, noise_h,
+                 endpoint_feat: bool = False, endpoint_coord: bool = False):
+    """sample_p_zs_given_zt, pharmacodiff.py:380-431 (eps parameterisation, or the endpoint branch :413-418 per part)."""
     B = b.n_graphs
     s_arr = torch.full((B,), s_int).float() / T
     t_arr = torch.full((B,), s_int + 1).float() / T
@@ -352,8 +367,16 @@ def reverse_step(sd, b: FlatBatch, s_int: int, T: int, gamma: torch.Tensor, cfg:
     alpha_ts, var_terms, sigma_q = posterior_coefficients(g_s, g_t)
     eps_h, eps_x = denoiser(sd, b, t_arr, cfg)
     fb = b.pharm_b
-    mu_x = b.pharm_x / alpha_ts[fb].view(-1, 1) - var_terms[fb].view(-1, 1) * eps_x
-    mu_h = b.pharm_h / alpha_ts[fb].view(-1, 1) - var_terms[fb].view(-1, 1) * eps_h
+    c1, c2 = endpoint_coefficients(g_s, g_t)
+    c1, c2 = c1[fb].view(-1, 1), c2[fb].view(-1, 1)
+    if endpoint_coord:
+        mu_x = c1 * b.pharm_x + c2 * eps_x
+    else:
+        mu_x = b.pharm_x / alpha_ts[fb].view(-1, 1) - var_terms[fb].view(-1, 1) * eps_x
+    if endpoint_feat:
+        mu_h = c1 * b.pharm_h + c2 * eps_h
+    else:
+        mu_h = b.pharm_h / alpha_ts[fb].view(-1, 1) - var_terms[fb].view(-1, 1) * eps_h
     b.pharm_x = mu_x + sigma_q[fb].view(-1, 1) * noise_x
     b.pharm_h = mu_h + sigma_q[fb].view(-1, 1) * noise_h
     remove_pharm_com(b)
@@ -361,7 +384,8 @@ def reverse_step(sd, b: FlatBatch, s_int: int, T: int, gamma: torch.Tensor, cfg:
 
 
 def sample(sd, b: FlatBatch, noise: torch.Tensor, T: int, gamma: torch.Tensor, cfg: dict,
-           init_pharm_com: Optional[torch.Tensor] = None, norm_const: float = 1.0, record=None, steps=None):
+           init_pharm_com: Optional[torch.Tensor] = None, norm_const: float = 1.0, record=None, steps=None,
+           endpoint_feat: bool = False, endpoint_coord: bool = False):
     """sample_given_receptor, pharmacodiff.py:433-514.  noise [T+1, Nf, 9]: row 0 = initial z_T
     (x cols 0:3, h cols 3:9), row 1+i = the i-th loop iteration (s = T-1-i), x drawn before h."""
     init_prot_com = segment_mean(b.prot_x, b.prot_b, b.n_graphs)
@@ -376,7 +400,7 @@ def sample(sd, b: FlatBatch, noise: torch.Tensor, T: int, gamma: torch.Tensor, c
     for i, s in enumerate(reversed(range(T))):
         if i >= n_steps:
             break
-        reverse_step(sd, b, s, T, gamma, cfg, noise[1 + i, :, 0:3], noise[1 + i, :, 3:9])
+        reverse_step(sd, b, s, T, gamma, cfg, noise[1 + i, :, 0:3], noise[1 + i, :, 3:9], endpoint_feat, endpoint_coord)
         if record is not None:
             record.append((b.pharm_x.clone(), b.pharm_h.clone(), b.prot_x.clone()))
     # final frame restore, pharmacodiff.py:480-488
@@ -439,10 +463,13 @@ def sample_multi(sd, pockets: List[Tuple[torch.Tensor, torch.Tensor]], n_pharms:
 
 def forward_loss(sd, b: FlatBatch, x0: torch.Tensor, h0: torch.Tensor, t_int: torch.Tensor, eps_x: torch.Tensor,
                  eps_h: torch.Tensor, T: int, gamma: torch.Tensor, cfg: dict, norm_const: float = 1.0,
-                 weighted_loss: bool = False, phase: str = "train"):
-    """PharmacophoreDiff.forward, pharmacodiff.py:162-243, eps parameterisation (dev.yml): normalise h_0 (:81-83),
-    remove the pharmacophore COM of x_0 from the complex (:178), noise with (t, eps) (:110-127), remove the COM of x_t,
-    predict, and form the two MSE losses and the four metrics.  t_int [B] in [0, T) and eps are injected."""
+                 weighted_loss: bool = False, phase: str = "train", endpoint_feat: bool = False,
+                 endpoint_coord: bool = False, remove_com: bool = True):
+    """PharmacophoreDiff.forward, pharmacodiff.py:162-243: normalise h_0 (:81-83), remove the pharmacophore COM of x_0 from
+    the complex (:178), noise with (t, eps) (:110-127), remove the COM of x_t (unless remove_com is off, :123-125),
+    predict, and form the two losses and the four metrics -- MSE on eps (dev.yml), or, per part, the endpoint
+    parameterisation (:204-216): cross entropy on the predicted h_0 / MSE on the predicted x_0 (+ the COM of x_t).
+    t_int [B] in [0, T) and eps are injected."""
     fb = b.pharm_b
     h0 = h0 / norm_const
     com0 = segment_mean(x0, fb, b.n_graphs)
@@ -454,12 +481,23 @@ def forward_loss(sd, b: FlatBatch, x0: torch.Tensor, h0: torch.Tensor, t_int: to
     sigma_t = torch.sqrt(torch.sigmoid(g_t))[fb].view(-1, 1)
     b.pharm_x = alpha_t * x0 + sigma_t * eps_x
     b.pharm_h = alpha_t * h0 + sigma_t * eps_h
-    remove_pharm_com(b)
+    com_t = None
+    if remove_com:
+        com_t = segment_mean(b.pharm_x, fb, b.n_graphs)[fb]
+        remove_pharm_com(b)
     h_dyn, x_dyn = denoiser(sd, b, t, cfg)
-    h_loss = (eps_h - h_dyn).square().sum(dim=1)
-    x_loss = (eps_x - x_dyn).square().sum(dim=1)
-    h0_pred = (b.pharm_h - sigma_t * h_dyn) / alpha_t
-    x0_pred = (b.pharm_x - sigma_t * x_dyn) / alpha_t
+    if endpoint_feat:
+        h0_pred = h_dyn
+        h_loss = F.cross_entropy(h0_pred, h0.argmax(dim=1), reduction="none")
+    else:
+        h_loss = (eps_h - h_dyn).square().sum(dim=1)
+        h0_pred = (b.pharm_h - sigma_t * h_dyn) / alpha_t
+    if endpoint_coord:
+        x0_pred = x_dyn + com_t if remove_com else x_dyn
+        x_loss = (x0_pred - x0).square().sum(dim=1)
+    else:
+        x_loss = (eps_x - x_dyn).square().sum(dim=1)
+        x0_pred = (b.pharm_x - sigma_t * x_dyn) / alpha_t
     w_metric = 1 - t[fb]
     w_loss = w_metric if weighted_loss else torch.ones_like(w_metric)
     losses = {phase + " pos loss": (x_loss * w_loss).sum() / eps_x.numel(),

@@ -64,6 +64,9 @@ SIGNATURES = {
     "pf_noise_head": (C.c_int, [c_f32p, c_f32p, C.c_int64, c_f32p, C.c_int32, C.c_int32, c_f32p, c_f32p, STREAM]),
     "pf_posterior_step": (C.c_int, [c_f32p, c_f32p, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p,
                                     c_i32p, C.c_int32, C.c_float, C.c_float, C.c_float, STREAM]),
+    "pf_posterior_step_ep": (C.c_int, [c_f32p, c_f32p, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_uint32, c_i32p,
+                                       c_f32p, c_i32p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_int32, STREAM]),
     "pf_posterior_step_philox": (C.c_int, [c_f32p, c_f32p, C.c_int32, c_f32p, c_f32p, C.c_void_p, C.c_uint32, c_i32p,
                                            c_f32p, c_i32p, C.c_int32, C.c_float, C.c_float, C.c_float, STREAM]),
     "pf_philox_normal": (C.c_int, [c_f32p, C.c_int64, C.c_void_p, C.c_uint32, C.c_uint32, STREAM]),
@@ -99,7 +102,7 @@ SIGNATURES = {
 }
 
 MAX_CONVS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class PfSampleArgs(C.Structure):
@@ -148,6 +151,7 @@ class PfSampleArgs(C.Structure):
         ("enc_rep", C.c_void_p), ("enc_table", C.c_void_p), ("aggd_h", C.c_void_p), ("aggd_v", C.c_void_p),
         ("c_x", C.c_void_p), ("c_h", C.c_void_p), ("c_v", C.c_void_p), ("c_agg_h", C.c_void_p), ("c_agg_v", C.c_void_p),
         ("c_seg_id", C.c_void_p), ("pf_col_c", C.c_void_p),
+        ("ep_c1_host", C.c_void_p), ("ep_c2_host", C.c_void_p), ("ep_mode", C.c_int32),
     ]
 
 

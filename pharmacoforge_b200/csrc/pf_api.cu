@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
                                                         float* __restrict__ prot_x, const int* __restrict__ prot_ptr,
                                                         int n_graphs, float alpha_ts, float var_terms,
                                                         float sigma_q, const unsigned long long* __restrict__ seed_dev,
-                                                        unsigned noise_step) {
+                                                        unsigned noise_step, float ep_c1, float ep_c2, int ep_mode) {
   const unsigned long long seed = noise_x == nullptr ? *seed_dev : 0ull;
   // The new coordinates of a graph are kept in shared memory between the update and the centre-of-mass pass (up to
   // kPostCache / 3 pharmacophore centres; larger graphs go through global memory as before): the three sequential sums
@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
     const bool cached = nf * 3 <= kPostCache;
     for (int i = threadIdx.x; i < nf * 3; i += blockDim.x) {
       const size_t o = (size_t)fa * 3 + i;
-      const float mu = __fsub_rn(__fdiv_rn(pharm_x[o], alpha_ts), __fmul_rn(var_terms, eps_x[o]));
+      // eps parameterisation: z / alpha_ts - var_terms * eps; endpoint parameterisation (pharmacodiff.py:413-414, the
+      // network output is the predicted x_0): c1 * z + c2 * pred -- every product and sum rounded, as the tensor ops do
+      const float mu = (ep_mode & PF_EP_COORD) ? __fadd_rn(__fmul_rn(ep_c1, pharm_x[o]), __fmul_rn(ep_c2, eps_x[o]))
+                                               : __fsub_rn(__fdiv_rn(pharm_x[o], alpha_ts), __fmul_rn(var_terms, eps_x[o]));
       const float nz = noise_x != nullptr ? noise_x[o] : philox_normal(seed, kNoiseStreamX, noise_step, o);
       const float z = __fadd_rn(mu, __fmul_rn(sigma_q, nz));
       if (cached)
@@ -126,7 +129,8 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
     }
     for (int i = threadIdx.x; i < nf * nh; i += blockDim.x) {
       const size_t o = (size_t)fa * nh + i;
-      const float mu = __fsub_rn(__fdiv_rn(pharm_h[o], alpha_ts), __fmul_rn(var_terms, eps_h[o]));
+      const float mu = (ep_mode & PF_EP_FEAT) ? __fadd_rn(__fmul_rn(ep_c1, pharm_h[o]), __fmul_rn(ep_c2, eps_h[o]))
+                                              : __fsub_rn(__fdiv_rn(pharm_h[o], alpha_ts), __fmul_rn(var_terms, eps_h[o]));
       const float nz = noise_x != nullptr ? noise_h[o] : philox_normal(seed, kNoiseStreamH, noise_step, o);
       pharm_h[o] = __fadd_rn(mu, __fmul_rn(sigma_q, nz));
     }
@@ -251,7 +255,8 @@ extern "C" int64_t pf_gvp_layout(int vi, int vo, int si, int so, int64_t offsets
 static int posterior_launch(float* pharm_x, float* pharm_h, int32_t nh, const float* eps_x, const float* eps_h,
                             const float* noise_x, const float* noise_h, const int32_t* pharm_ptr, float* prot_x,
                             const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms, float sigma_q,
-                            const uint64_t* seed_dev, uint32_t noise_step, void* stream) {
+                            const uint64_t* seed_dev, uint32_t noise_step, void* stream, float ep_c1 = 0.f,
+                            float ep_c2 = 0.f, int ep_mode = 0) {
   PF_CHECK_ARG(pharm_x && pharm_h && eps_x && eps_h && pharm_ptr && prot_x && prot_ptr, "pf_posterior_step: null pointer");
   PF_CHECK_ARG((noise_x && noise_h) || (!noise_x && !noise_h && seed_dev),
                "pf_posterior_step: pass both noise arrays, or neither and a device seed");
@@ -259,7 +264,8 @@ static int posterior_launch(float* pharm_x, float* pharm_h, int32_t nh, const fl
   const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
   posterior_kernel<<<grid, 128, 0, as_stream(stream)>>>(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h, pharm_ptr,
                                                         prot_x, prot_ptr, n_graphs, alpha_ts, var_terms, sigma_q,
-                                                        reinterpret_cast<const unsigned long long*>(seed_dev), noise_step);
+                                                        reinterpret_cast<const unsigned long long*>(seed_dev), noise_step,
+                                                        ep_c1, ep_c2, ep_mode);
   PF_CHECK_LAUNCH("pf_posterior_step");
   return PF_OK;
 }
@@ -279,6 +285,16 @@ extern "C" int pf_posterior_step_philox(float* pharm_x, float* pharm_h, int32_t 
                                         float var_terms, float sigma_q, void* stream) {
   return posterior_launch(pharm_x, pharm_h, nh, eps_x, eps_h, nullptr, nullptr, pharm_ptr, prot_x, prot_ptr, n_graphs,
                           alpha_ts, var_terms, sigma_q, seed_dev, noise_step, stream);
+}
+
+extern "C" int pf_posterior_step_ep(float* pharm_x, float* pharm_h, int32_t nh, const float* pred_x, const float* pred_h,
+                                    const float* noise_x, const float* noise_h, const uint64_t* seed_dev,
+                                    uint32_t noise_step, const int32_t* pharm_ptr, float* prot_x, const int32_t* prot_ptr,
+                                    int32_t n_graphs, float alpha_ts, float var_terms, float sigma_q, float ep_c1,
+                                    float ep_c2, int32_t ep_mode, void* stream) {
+  PF_CHECK_ARG((ep_mode & ~(PF_EP_COORD | PF_EP_FEAT)) == 0, "pf_posterior_step_ep: unknown mode bits");
+  return posterior_launch(pharm_x, pharm_h, nh, pred_x, pred_h, noise_x, noise_h, pharm_ptr, prot_x, prot_ptr, n_graphs,
+                          alpha_ts, var_terms, sigma_q, seed_dev, noise_step, stream, ep_c1, ep_c2, ep_mode);
 }
 
 extern "C" int pf_philox_normal(float* out, int64_t n, const uint64_t* seed_dev, uint32_t stream_id, uint32_t step,
@@ -511,6 +527,7 @@ extern "C" int pf_sample_loop(const PfSampleArgs* a, void* stream) {
   const bool philox = a->noise_x == nullptr;
   PF_CHECK_ARG(philox ? (a->noise_h == nullptr && a->noise_seed != nullptr) : a->noise_h != nullptr,
                "pf_sample_loop: pass noise_x and noise_h, or neither and noise_seed (in-kernel Philox)");
+  PF_CHECK_ARG(a->ep_mode == 0 || (a->ep_c1_host && a->ep_c2_host), "pf_sample_loop: endpoint mode without its coefficient tables");
   const size_t fx = (size_t)a->n_pharm * 3, fh = (size_t)a->n_pharm * a->n_pharm_feats;
   for (int i = 0; i < a->n_steps; ++i) {
     PF_TRY(pf_fill_f32(a->t_graph, a->n_graphs, a->t_host[i], stream));
@@ -519,7 +536,8 @@ extern "C" int pf_sample_loop(const PfSampleArgs* a, void* stream) {
   PF_TRY(posterior_launch(a->pharm_x, a->pharm_h, a->n_pharm_feats, a->eps_x, a->eps_h,
                             philox ? nullptr : a->noise_x + i * fx, philox ? nullptr : a->noise_h + i * fh, a->pharm_ptr,
                             a->prot_x, a->prot_ptr, a->n_graphs, a->alpha_ts_host[i], a->var_terms_host[i],
-                            a->sigma_q_host[i], a->noise_seed, (uint32_t)(a->noise_step0 + i), stream));
+                            a->sigma_q_host[i], a->noise_seed, (uint32_t)(a->noise_step0 + i), stream,
+                            a->ep_mode ? a->ep_c1_host[i] : 0.f, a->ep_mode ? a->ep_c2_host[i] : 0.f, a->ep_mode));
   prof_end(kSitePosterior, as_stream(stream));
   }
   return PF_OK;

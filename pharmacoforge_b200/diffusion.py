@@ -84,10 +84,6 @@ class PharmacophoreDiff(nn.Module):
                  endpoint_param_feat: bool = False, endpoint_param_coord: bool = False, weighted_loss: bool = False,
                  remove_com: bool = True, **kwargs):
         super().__init__()
-        if endpoint_param_feat or endpoint_param_coord:
-            raise NotImplementedError("only the eps parameterisation (configs/dev.yml) is built")
-        if not remove_com:
-            raise NotImplementedError("remove_com=False is not built")
         self.hparams = dict(pharm_nf=pharm_nf, rec_nf=rec_nf, ph_type_map=ph_type_map,
                             processed_data_dir=processed_data_dir, n_timesteps=n_timesteps, graph_config=graph_config,
                             dynamics_config=dynamics_config, lr_scheduler_config=lr_scheduler_config,
@@ -102,6 +98,7 @@ class PharmacophoreDiff(nn.Module):
         self.ph_type_map = ph_type_map
         self.n_timesteps = n_timesteps
         self.remove_com = remove_com
+        self.endpoint_param_feat, self.endpoint_param_coord = bool(endpoint_param_feat), bool(endpoint_param_coord)
         self.pharm_feat_norm_constant = pharm_feat_norm_constant
         self.weighted_loss = weighted_loss
         self.gamma = PredefinedNoiseSchedule("polynomial_2", n_timesteps, precision)
@@ -185,7 +182,17 @@ class PharmacophoreDiff(nn.Module):
         sigma_s, sigma_t = self.sigma(g_s), self.sigma(g_t)
         var_terms = sigma2_ts / alpha_ts / sigma_t
         sigma_q = sigma_ts * sigma_s / sigma_t
-        return [np.ascontiguousarray(v.numpy(), dtype=np.float32) for v in (t_arr, alpha_ts, var_terms, sigma_q)]
+        # endpoint parameterisation (pharmacodiff.py:413-418): mu = c1 z_t + c2 pred, same operator order as upstream
+        _, _, _, alpha_s = self.sigma_and_alpha_t_given_s(g_t, g_s)
+        ep_c1 = alpha_ts * (sigma_s ** 2) / (sigma_t ** 2)
+        ep_c2 = alpha_s * sigma2_ts / (sigma_t ** 2)
+        return [np.ascontiguousarray(v.numpy(), dtype=np.float32)
+                for v in (t_arr, alpha_ts, var_terms, sigma_q, ep_c1, ep_c2)]
+
+    @property
+    def ep_mode(self) -> int:
+        """PF_EP_COORD | PF_EP_FEAT bits of include/pharmacoforge_b200.h."""
+        return (1 if self.endpoint_param_coord else 0) | (2 if self.endpoint_param_feat else 0)
 
     # ------------------------------------------------------------------ sampling
     @torch.no_grad()
@@ -264,11 +271,14 @@ class PharmacophoreDiff(nn.Module):
         off = first  # tables are in loop order; the same offset applies to every table
         if getattr(self, "_tables", None) is None:      # direct callers (tests) that did not go through the sampler
             self._tables = self.step_tables()
-        t_host, alpha_ts, var_terms, sigma_q = self._tables
+        t_host, alpha_ts, var_terms, sigma_q, ep_c1, ep_c2 = self._tables
         a.t_host = t_host[off:].ctypes.data
         a.alpha_ts_host = alpha_ts[off:].ctypes.data
         a.var_terms_host = var_terms[off:].ctypes.data
         a.sigma_q_host = sigma_q[off:].ctypes.data
+        a.ep_c1_host = ep_c1[off:].ctypes.data
+        a.ep_c2_host = ep_c2[off:].ctypes.data
+        a.ep_mode = self.ep_mode
         philox = nx is None
         a.noise_x = nx[1 + first:].data_ptr() if (count and not philox) else 0
         a.noise_h = nhh[1 + first:].data_ptr() if (count and not philox) else 0
@@ -284,7 +294,7 @@ class PharmacophoreDiff(nn.Module):
         # The whole loop as ONE CUDA graph (Philox mode only: every kernel argument is then the same from call to call --
         # buffers of this batch, the schedule constants, the device-resident seed).  Captured on the second use of a
         # (batch, first, count, flags) combination: the first one runs eagerly so that every kernel has been configured.
-        key = (first, count, int(a.flags))
+        key = (first, count, int(a.flags), int(a.ep_mode))
         gr = st.graphs.get(key)
         if gr is None and not st.warmed:
             ops.sample_loop(g.pharm_x, g.pharm_h, g.prot_x, st.addr)
@@ -375,9 +385,11 @@ class PharmacophoreDiff(nn.Module):
                 g.pharm_h = torch.zeros(max(g.n_pharm, 1), self.n_pharm_feats, device=dev)
             g.pharm_x.copy_(alpha_t * x0 + sigma_t * eps_x)                    # noised_representation, :110-127
             g.pharm_h.copy_(alpha_t * h0 + sigma_t * eps_h)
-            com_t = ops.segment_mean3(g.pharm_x, g.pharm_ptr)
-            ops.segment_shift3(g.pharm_x, g.pharm_ptr, com_t, -1.0)
-            ops.segment_shift3(g.prot_x, g.prot_ptr, com_t, -1.0)
+            com_t = None
+            if self.remove_com:                                                # :123-125
+                com_t = ops.segment_mean3(g.pharm_x, g.pharm_ptr)
+                ops.segment_shift3(g.pharm_x, g.pharm_ptr, com_t, -1.0)
+                ops.segment_shift3(g.prot_x, g.prot_ptr, com_t, -1.0)
         if differentiable:
             if not next(self.dynamics.parameters()).is_cuda:
                 raise RuntimeError("training needs the model parameters on the GPU: call model.to(g.device)")
@@ -391,15 +403,23 @@ class PharmacophoreDiff(nn.Module):
                 finally:
                     self.dynamics.check_status_every_call = True
         g.check_status()
-        h_loss = (eps_h - h_dyn).square().sum(dim=1)
-        x_loss = (eps_x - x_dyn).square().sum(dim=1)
+        if self.endpoint_param_feat:       # the network predicts h_0: cross entropy on its logits (pharmacodiff.py:204-206)
+            h0_pred = h_dyn
+            h_loss = F.cross_entropy(h0_pred, h0.argmax(dim=1), reduction="none")
+        else:
+            h_loss = (eps_h - h_dyn).square().sum(dim=1)
+            h0_pred = (g.pharm_h - sigma_t * h_dyn) / alpha_t
+        if self.endpoint_param_coord:      # ... and x_0, in the frame before the COM of x_t was removed (:210-216)
+            x0_pred = x_dyn + com_t[fb] if self.remove_com else x_dyn
+            x_loss = (x0_pred - x0).square().sum(dim=1)
+        else:
+            x_loss = (eps_x - x_dyn).square().sum(dim=1)
+            x0_pred = (g.pharm_x - sigma_t * x_dyn) / alpha_t
         w_metric = 1 - t[fb]
         w_loss = w_metric if self.weighted_loss else torch.ones_like(w_metric)
         losses = {phase + " pos loss": (x_loss * w_loss).sum() / eps_x.numel(),
                   phase + " feat loss": (h_loss * w_loss).sum() / eps_h.numel()}
         with torch.no_grad():
-            h0_pred = (g.pharm_h - sigma_t * h_dyn) / alpha_t
-            x0_pred = (g.pharm_x - sigma_t * x_dyn) / alpha_t
             sq = (x0_pred - x0).square().sum(dim=1)
             hit = (h0_pred.argmax(dim=1) == h0.argmax(dim=1)).float()
             metrics = {phase + " position error": sq.mean(), phase + " weighted position error": (w_metric * sq).mean(),

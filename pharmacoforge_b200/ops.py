@@ -298,6 +298,18 @@ def posterior_step(pharm_x: torch.Tensor, pharm_h: torch.Tensor, eps_x: torch.Te
                                     alpha_ts, var_terms, sigma_q, _s()), "pf_posterior_step")
 
 
+@torch.library.custom_op(f"{NS}::posterior_step_ep", mutates_args=("pharm_x", "pharm_h", "prot_x"))
+def posterior_step_ep(pharm_x: torch.Tensor, pharm_h: torch.Tensor, pred_x: torch.Tensor, pred_h: torch.Tensor,
+                      noise_x: torch.Tensor, noise_h: torch.Tensor, pharm_ptr: torch.Tensor, prot_x: torch.Tensor,
+                      prot_ptr: torch.Tensor, alpha_ts: float, var_terms: float, sigma_q: float, ep_c1: float, ep_c2: float,
+                      ep_mode: int) -> None:
+    """sample_p_zs_given_zt with the endpoint parameterisation for the parts in ep_mode (1: coordinates, 2: features;
+    pharmacodiff.py:413-418), injected noise."""
+    _lib.check(_L.pf_posterior_step_ep(_f(pharm_x), _f(pharm_h), pharm_h.shape[1], _f(pred_x), _f(pred_h), _f(noise_x),
+                                       _f(noise_h), None, 0, _i(pharm_ptr), _f(prot_x), _i(prot_ptr), prot_ptr.numel() - 1,
+                                       alpha_ts, var_terms, sigma_q, ep_c1, ep_c2, ep_mode, _s()), "pf_posterior_step_ep")
+
+
 @torch.library.custom_op(f"{NS}::philox_normal", mutates_args=("out",))
 def philox_normal(out: torch.Tensor, seed: torch.Tensor, stream_id: int, step: int) -> None:
     """out <- N(0, 1) draws of (stream_id, step) under the int64 device seed (Philox4x32-10 + Box-Muller)."""

@@ -162,3 +162,50 @@ def test_oracle_gradients_match_reference_backward(golden, sd, dyn_cfg):
             ref = t(g[k])
             got = sdg[k[6:]].grad
             assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max()), k
+
+
+# ---- the endpoint parameterisation and remove_com=False (outside configs/dev.yml; README.md names an endpoint_param.yaml)
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("tag,flags", [("ep", dict(endpoint_feat=True, endpoint_coord=True)),
+                                       ("epx", dict(endpoint_coord=True)), ("nocom", dict(remove_com=False)),
+                                       ("ep_nocom", dict(endpoint_feat=True, endpoint_coord=True, remove_com=False))])
+def test_forward_loss_endpoint_and_nocom_against_reference(golden, sd, dyn_cfg, tag, flags):
+    g = golden("endpoint_param.npz")
+    pos, onehot = make_pocket(120, seed=5)
+    b = O.build_batch([(t(pos), t(onehot))], [list(map(int, g["sizes"]))])
+    lo, me = O.forward_loss(sd, b, t(g["x0"]), t(g["h0"]), t(g["t_int"]), t(g["eps_x"]), t(g["eps_h"]), 100,
+                            sd["gamma.gamma"], dyn_cfg, phase="val", **flags)
+    for k, v in {**lo, **me}.items():
+        ref = float(g[f"{tag}__{k.replace(' ', '_')}"])
+        assert abs(float(v) - ref) <= 2e-5 * max(1.0, abs(ref)), (tag, k, float(v), ref)
+
+
+@pytest.mark.parametrize("tag,flags", [("ep", dict(endpoint_feat=True, endpoint_coord=True)), ("eph", dict(endpoint_feat=True))])
+def test_endpoint_reverse_diffusion_against_reference(golden, sd, dyn_cfg, tag, flags):
+    """The endpoint posterior (pharmacodiff.py:413-418): coefficient tables bit-identical to the reference's formulas, the
+    first reverse steps of the reference's own run reproduced from its injected noise, and -- for the all-endpoint model,
+    whose chain is contractive -- the final sample."""
+    g = golden("endpoint_param.npz")
+    gam = sd["gamma.gamma"]
+    T = 100
+    s = torch.arange(T).float() / T
+    tt = (torch.arange(T) + 1).float() / T
+    c1, c2 = O.endpoint_coefficients(O.gamma_at(gam, s, T), O.gamma_at(gam, tt, T))
+    assert np.array_equal(c1.numpy(), g["ep_c1"]) and np.array_equal(c2.numpy(), g["ep_c2"])
+    pos, onehot = make_pocket(100, seed=5)
+    sizes = list(map(int, g["sample_sizes"]))
+    noise, tx, th = (t(g[f"s_{tag}__{k}"]) for k in ("noise", "traj_x", "traj_h"))
+    b = O.build_batch([(t(pos), t(onehot))], [sizes])
+    rec = []
+    n = 100 if tag == "ep" else 6
+    x0, h0, _, _ = O.sample(sd, b, noise, T, gam, dyn_cfg, record=rec, steps=n, endpoint_feat=flags.get("endpoint_feat", False),
+                            endpoint_coord=flags.get("endpoint_coord", False))
+    for i in range(0, n + 1, max(1, n // 6)):
+        sx, sh = max(1.0, float(tx[i].abs().max())), max(1.0, float(th[i].abs().max()))
+        assert float((rec[i][0] - tx[i]).abs().max()) <= 1e-3 * sx, (tag, i, float((rec[i][0] - tx[i]).abs().max()))
+        assert float((rec[i][1] - th[i]).abs().max()) <= 1e-3 * sh, (tag, i)
+    if tag == "ep":
+        assert float((x0 - t(g["s_ep__final_x"])).abs().max()) <= 2e-3
+        assert float((h0 - t(g["s_ep__final_h"])).abs().max()) <= 2e-3
