@@ -360,6 +360,20 @@ typedef struct PfSampleArgs {
  * rows the last layer's pf edges read (the fp segment destinations) are encoded and updated, in a compact buffer.  Equal to
  * the nominal path up to fp32 rounding of x_src - x_dst; never the default, reported separately by bench.py. */
 #define PF_FLAG_SHARE_POCKET_MESSAGES 8u
+/* First-layer encoder TABLE (tcgen05 path, one-hot protein features, enc_* buffers bound): the encoder output of a
+ * protein node depends only on (graph, atom type), so the first conv layer reads the protein scalars from the
+ * [n_graphs * n_prot_feats][128] table enc_table through the row map seed_row instead of a materialised [n_prot][128]
+ * array -- the pf message gather (pf_edge_conv_tc_mapped) and the protein node update (pf_node_update_tc_mapped, which
+ * writes the full prot_h) -- and the per-node encoder pass disappears.  Same arithmetic on the same values: results are
+ * bit-identical.  PF_FLAG_NO_LAYER0_TABLE is the A/B switch. */
+#define PF_FLAG_NO_LAYER0_TABLE 16u
+int pf_edge_conv_tc_mapped(const float* src_h, const int32_t* src_map, const float* src_v, const float* src_x,
+                           const float* dst_x, const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
+                           const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
+                           const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, int32_t f16, void* stream);
+int pf_node_update_tc_mapped(const float* h_in, const int32_t* h_map, const float* v_in, const float* agg_h,
+                             const float* agg_v, int64_t n_nodes, const void* wblob, float* h_out, float* v_out,
+                             int32_t f16, void* stream);
 int pf_share_index(const int32_t* pharm_ptr, int32_t n_graphs, int32_t pf_k, const int32_t* pf_cnt, const int32_t* pf_col,
                    const int32_t* fp_seg_dst, const int32_t* fp_seg_cnt, int32_t* pf_col_c, void* stream);
 /* stage 0: c_x / c_h from prot_x and the encoder table; stage 1: c_agg += pp means of the row's distinct node */

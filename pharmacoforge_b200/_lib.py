@@ -48,6 +48,10 @@ SIGNATURES = {
     "pf_node_update_tc": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_void_p, c_f32p, c_f32p, STREAM]),
     "pf_edge_conv_tc": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                   C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, STREAM]),
+    "pf_node_update_tc_mapped": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_void_p, c_f32p, c_f32p,
+                                           C.c_int32, STREAM]),
+    "pf_edge_conv_tc_mapped": (C.c_int, [c_f32p, c_i32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
+                                         c_i32p, C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, C.c_int32, STREAM]),
     "pf_node_update_tc_f16": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_void_p, c_f32p, c_f32p, STREAM]),
     "pf_edge_conv_tc_f16": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                       C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_int32, STREAM]),

@@ -262,10 +262,20 @@ class GraphBatch:
             pk_x=pk_x.contiguous(), pk_start=pk_rowptr[:-1].contiguous(), pk_cnt=pk_cnt, pk_col=pk_col,
             pk_tiles=tiles[:2 * max(n, 1)].clone(), pk_n_tiles=n_tiles, pk_max_tiles=n, n_distinct=n_d,
             pk_seed_row=pk_seed_row, pk_node0=g_pk_off.to(torch.int32).contiguous(),
-            enc_feats=torch.eye(F, device=dev).repeat(B, 1).contiguous(),
-            enc_ptr=(F * torch.arange(B + 1, device=dev)).to(torch.int32),
-            enc_rep=torch.arange(B * F, device=dev, dtype=torch.int32))
+            **self.enc_arrays())
         return self._share_arrays
+
+    def enc_arrays(self):
+        """Inputs of the per-(graph, atom type) encoder table (one-hot protein features): identity blocks as the encoder's
+        feature rows, F rows per graph, every table row its own representative."""
+        cached = getattr(self, "_enc_arrays", None)
+        if cached is None:
+            dev, F, B = self.device, self.n_prot_feats, self.n_graphs
+            cached = self._enc_arrays = dict(
+                enc_feats=torch.eye(F, device=dev).repeat(B, 1).contiguous(),
+                enc_ptr=(F * torch.arange(B + 1, device=dev)).to(torch.int32),
+                enc_rep=torch.arange(B * F, device=dev, dtype=torch.int32))
+        return cached
 
     def seed_arrays(self):
         """(seed_row [n_prot] int32, seed_rep [n_graphs * F] int32) for the first-layer seeding of the pp messages, or

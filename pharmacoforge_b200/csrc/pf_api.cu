@@ -462,8 +462,15 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   // encoders (dynamics_gvp.py:143-151); node vectors start at zero (:162-173) and are never materialised
   PF_TRY(pf_encode(a->pharm_h, a->n_pharm_feats, a->pharm_ptr, a->n_graphs, a->t_graph, a->w_pharm_enc, a->pharm_hh,
                    stream));
-  PF_TRY(pf_encode(a->prot_feats, a->n_prot_feats, a->prot_ptr, a->n_graphs, a->t_graph, a->w_prot_enc, a->prot_h,
-                   stream));
+  // First-layer encoder table (see PF_FLAG_NO_LAYER0_TABLE): one encoder row per (graph, atom type) instead of one per node
+  const bool table0 = tc && a->seed_row != nullptr && a->enc_feats && a->enc_ptr && a->enc_rep && a->enc_table &&
+                      a->n_upd_gvps == 2 && a->w_upd_tc[0][1] != nullptr &&
+                      !(a->flags & (PF_FLAG_NO_LAYER0_SEED | PF_FLAG_NO_LAYER0_TABLE));
+  if (table0)
+    PF_TRY(pf_encode(a->enc_feats, a->n_prot_feats, a->enc_ptr, a->n_graphs, a->t_graph, a->w_prot_enc, a->enc_table, stream));
+  else
+    PF_TRY(pf_encode(a->prot_feats, a->n_prot_feats, a->prot_ptr, a->n_graphs, a->t_graph, a->w_prot_enc, a->prot_h,
+                     stream));
   for (int l = 0; l < a->n_convs; ++l) {
     const float* fv = l == 0 ? nullptr : a->pharm_v;
     const float* pv = l == 0 ? nullptr : a->prot_v;
@@ -474,6 +481,11 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                          a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 0, stream));
   prof_end(kSiteFF, as_stream(stream));
     prof_begin(kSitePF, as_stream(stream));
+    if (l == 0 && table0)
+      PF_TRY(pf_edge_conv_tc_mapped(a->enc_table, a->seed_row, nullptr, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr,
+                                    a->pf_col, a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg_tc[l][1],
+                                    a->pharm_agg_h, a->pharm_agg_v, 1, f16 ? 1 : 0, stream));
+    else
     PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col,
                          a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->w_msg_tc[l][1],
                          a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
@@ -485,6 +497,9 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     if (l == 0 && tc && a->seed_row != nullptr && !(a->flags & PF_FLAG_NO_LAYER0_SEED)) {
       // first layer: the per-node part of GVP 0 from the (graph, atom type) table, the rest per edge (timed with the site)
       PF_CHECK_ARG(a->seed_rep && a->seed_table && a->n_seed_rows > 0, "pf_denoiser: incomplete seed arrays");
+      if (table0)   // table row r is its own representative
+        PF_TRY(pf_seed_table(a->enc_table, a->enc_rep, a->n_seed_rows, a->w_msg[l][3], a->seed_table, stream));
+      else
       PF_TRY(pf_seed_table(a->prot_h, a->seed_rep, a->n_seed_rows, a->w_msg[l][3], a->seed_table, stream));
       PF_TRY(pf_edge_conv_tc_seeded(a->seed_row, a->seed_table, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr,
                                     a->pp_col, a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg_tc[l][3],
@@ -508,6 +523,10 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   prof_end(kSiteUpdPharm, as_stream(stream));
     if (prot_side) {
     prof_begin(kSiteUpdProt, as_stream(stream));
+    if (l == 0 && table0)
+      PF_TRY(pf_node_update_tc_mapped(a->enc_table, a->seed_row, nullptr, a->prot_agg_h, a->prot_agg_v, a->n_prot,
+                                      a->w_upd_tc[l][1], a->prot_h, a->prot_v, f16 ? 1 : 0, stream));
+    else
     PF_TRY(node_update_any(f16, tc && a->n_upd_gvps == 2 ? a->w_upd_tc[l][1] : nullptr, a->prot_h, pv, a->prot_agg_h,
                            a->prot_agg_v, a->n_prot, a->w_upd[l][1], a->n_upd_gvps, a->prot_h, a->prot_v, stream));
   prof_end(kSiteUpdProt, as_stream(stream));

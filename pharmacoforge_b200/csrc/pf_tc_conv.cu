@@ -100,6 +100,10 @@ struct Params {
   // k Wf0[:, 0:128] h_src, the per-node part of GVP 0's scalar contraction (pf_seed_table); src_h is not read
   const int* seed_row;
   const float* seed;
+  // optional row map of src_h (general kernels): source node n reads scalar row src_map[n] instead of row n -- the first
+  // conv layer's protein scalars are one encoder row per (graph, atom type), read from that table instead of a
+  // materialised [n_prot][128] array (src_v / src_x are indexed by the node as always)
+  const int* src_map;
 };
 
 // sigma(y) = 1 / (1 + 2^(-y log2 e)) on the two MUFU ops with no range fix-up code: ex2.approx overflows to +inf for
@@ -708,10 +712,11 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
       // first one's staging stores and flies under its fp16 split.  With all 16 loads in flight the 64 data registers did
       // not fit next to the tile state (96 registers per thread): 23 of the loaded values went through local memory.
       float4 ga[8], gb[8];
+      const int srch = (p.src_map != nullptr && src >= 0) ? __ldg(p.src_map + src) : src;   // scalar row of the source
       auto load8 = [&](float4 (&g)[8], const int c2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int sr = __shfl_sync(0xffffffffu, src, 4 * i + (lane >> 3));
+          const int sr = __shfl_sync(0xffffffffu, srch, 4 * i + (lane >> 3));
           g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (sr >= 0)
             g[i] = __ldg(reinterpret_cast<const float4*>(p.src_h + (size_t)sr * kHidden + 32 * (2 * hh + c2)) + (lane & 7));
@@ -833,7 +838,7 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
         } else if (g == 2 && nx_src >= 0) {
           if constexpr (SEED) {
             nx_srow = __ldg(p.seed_row + nx_src);
-          } else {
+          } else if (p.src_map == nullptr) {   // (a mapped source is a small table that lives in L2 anyway)
             const char* hrow = reinterpret_cast<const char*>(p.src_h + (size_t)nx_src * kHidden) + 256 * hh;
             tc::prefetch_l2(hrow);
             tc::prefetch_l2(hrow + 128);
@@ -1183,6 +1188,7 @@ struct NodeParams {
   const uint8_t* wblob;
   float *h_out, *v_out;
   long long* trace;
+  const int* h_map;   // optional: node n reads its input scalars from row h_map[n] of h_in (see Params::src_map)
 };
 
 __device__ __forceinline__ float xor8_sum(float v) {  // sum over the 8 lanes that share one row of a 4-row pass
@@ -1192,7 +1198,7 @@ __device__ __forceinline__ float xor8_sum(float v) {  // sum over the 8 lanes th
   return v;
 }
 
-template <bool HAS_V, bool FAST, bool TRACE>
+template <bool HAS_V, bool FAST, bool TRACE, bool MAPPED>
 __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* smem, uint32_t tmem, SlotBars* sb,
                                    uint64_t* bar_small, uint64_t* bar_stagger, int my_tiles) {
   const int stid = threadIdx.x & 255;
@@ -1237,8 +1243,13 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       // two-pass form needed a second slot barrier.
       float4 g4[2][8];
       float rs[8], rq[8];
+      int hrow[8];   // table rows of this thread's eight node rows (h_map mode only)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rs[i] = rq[i] = 0.f;
+      for (int i = 0; i < 8; ++i) {
+        rs[i] = rq[i] = 0.f;
+        const int row = 32 * q + 4 * i + prow;
+        hrow[i] = (MAPPED && row < nrows) ? __ldg(p.h_map + n0 + row) : 0;
+      }
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2)
 #pragma unroll
@@ -1247,13 +1258,23 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row < nrows) {
             const size_t o = (size_t)(n0 + row) * kHidden + 32 * (2 * hh + c2) + 4 * piece;
+            float4 a;
+            if constexpr (MAPPED) {   // input scalars from a (small, L2-resident) row table
+              x = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)hrow[i] * kHidden + 32 * (2 * hh + c2) + 4 * piece));
+#if PF_K4_L2HINT & 2
+              a = tc::ldg_hint(reinterpret_cast<const float4*>(p.agg_h + o), tc::l2_policy_evict_first());
+#else
+              a = __ldg(reinterpret_cast<const float4*>(p.agg_h + o));
+#endif
+            } else {
 #if PF_K4_L2HINT & 2
             x = tc::ld_global_hint(reinterpret_cast<const float4*>(p.h_in + o), tc::l2_policy_evict_first());
-            const float4 a = tc::ldg_hint(reinterpret_cast<const float4*>(p.agg_h + o), tc::l2_policy_evict_first());
+            a = tc::ldg_hint(reinterpret_cast<const float4*>(p.agg_h + o), tc::l2_policy_evict_first());
 #else
             x = *reinterpret_cast<const float4*>(p.h_in + o);  // plain load: h_out may alias h_in
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.agg_h + o));
+            a = __ldg(reinterpret_cast<const float4*>(p.agg_h + o));
 #endif
+            }
             x.x += a.x;
             x.y += a.y;
             x.z += a.z;
@@ -1432,7 +1453,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
 #define PF_K4_PREFETCH tc::prefetch_l2
 #endif
       for (int l = stid; l < lines_h; l += 256) {
-        PF_K4_PREFETCH(reinterpret_cast<const char*>(p.h_in + m0 * kHidden) + (size_t)l * 128);
+        if constexpr (!MAPPED) PF_K4_PREFETCH(reinterpret_cast<const char*>(p.h_in + m0 * kHidden) + (size_t)l * 128);
         PF_K4_PREFETCH(reinterpret_cast<const char*>(p.agg_h + m0 * kHidden) + (size_t)l * 128);
       }
       for (int l = stid; l < lines_v; l += 256) {
@@ -1713,7 +1734,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
   }
 }
 
-template <bool HAS_V, bool FAST, bool TRACE>
+template <bool HAS_V, bool FAST, bool TRACE, bool MAPPED = false>
 __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const NodeParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -1756,7 +1777,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) node_update_tc_kernel(const Nod
   const uint32_t tmem = *s_tmem;
 
   if (warp < 16) {
-    node_epilogue_role<HAS_V, FAST, TRACE>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
+    node_epilogue_role<HAS_V, FAST, TRACE, MAPPED>(p, warp >> 3, smem, tmem, sb, bar_small, bar_stagger, my_tiles);
   } else if (warp < 18) {
     mma_role<1, true, FAST, TRACE>(warp - 16, smem, tmem, bar_full, bar_empty, sb, bar_small, bar_stagger, s_turn, my_tiles, p.trace);
   } else {
@@ -1785,7 +1806,8 @@ static int launch_edge_conv_tc(bool fast, const float* src_h, const float* src_v
                                const int32_t* seg_start, const int32_t* seg_cnt, const int32_t* seg_dst,
                                const int32_t* col, const int32_t* tiles, const int32_t* n_tiles, int32_t max_tiles,
                                const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream,
-                               const int32_t* seed_row = nullptr, const float* seed = nullptr) {
+                               const int32_t* seed_row = nullptr, const float* seed = nullptr,
+                               const int32_t* src_map = nullptr) {
   const bool seeded = seed_row != nullptr;
   PF_CHECK_ARG((src_h || seeded) && src_x && dst_x && seg_start && seg_cnt && col && tiles && n_tiles && wblob && agg_h && agg_v,
                "pf_edge_conv_tc: null pointer");
@@ -1815,7 +1837,7 @@ static int launch_edge_conv_tc(bool fast, const float* src_h, const float* src_v
     configured.done[dev_] = true;
   }
   tcc::Params p{src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
-                static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate, g_tc_trace, seed_row, seed};
+                static_cast<const uint8_t*>(wblob), agg_h, agg_v, accumulate, g_tc_trace, seed_row, seed, src_map};
   const int grid = max_tiles < num_sms() ? max_tiles : num_sms();
   const int which = (src_v != nullptr ? 1 : 0) + (fast ? 2 : 0) + (g_tc_trace != nullptr ? 4 : 0);
   const KernelFn fn = seeded ? seeded_fns[(fast ? 1 : 0) + (g_tc_trace != nullptr ? 2 : 0)] : fns[which];
@@ -1830,6 +1852,18 @@ extern "C" int pf_edge_conv_tc(const float* src_h, const float* src_v, const flo
                                const void* wblob, float* agg_h, float* agg_v, int32_t accumulate, void* stream) {
   return launch_edge_conv_tc(false, src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
                              max_tiles, wblob, agg_h, agg_v, accumulate, stream);
+}
+
+// General kernel with a row map on the source scalars: node n reads row src_map[n] of src_h (a table with one row per
+// distinct encoder output) instead of row n; src_v / src_x are indexed by the node.  f16 != 0: single-pass mode.
+extern "C" int pf_edge_conv_tc_mapped(const float* src_h, const int32_t* src_map, const float* src_v, const float* src_x,
+                                      const float* dst_x, const int32_t* seg_start, const int32_t* seg_cnt,
+                                      const int32_t* seg_dst, const int32_t* col, const int32_t* tiles, const int32_t* n_tiles,
+                                      int32_t max_tiles, const void* wblob, float* agg_h, float* agg_v, int32_t accumulate,
+                                      int32_t f16, void* stream) {
+  PF_CHECK_ARG(src_map != nullptr, "pf_edge_conv_tc_mapped: null row map");
+  return launch_edge_conv_tc(f16 != 0, src_h, src_v, src_x, dst_x, seg_start, seg_cnt, seg_dst, col, tiles, n_tiles,
+                             max_tiles, wblob, agg_h, agg_v, accumulate, stream, nullptr, nullptr, src_map);
 }
 
 // Single-pass fp16 variant (the "bf16 edge-MLP path" of BASELINE.json configs[3]): same arguments and weight image,
@@ -1920,8 +1954,10 @@ extern "C" int pf_edge_conv_tc_seeded(const int32_t* seed_row, const float* seed
 }
 
 static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
-                                 int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream) {
+                                 int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream,
+                                 const int32_t* h_map = nullptr) {
   PF_CHECK_ARG(h_in && agg_h && agg_v && wblob && h_out && v_out, "pf_node_update_tc: null pointer");
+  PF_CHECK_ARG(h_map == nullptr || h_in != h_out, "pf_node_update_tc_mapped: the row table cannot be the output");
   PF_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 15) == 0, "pf_node_update_tc: weight blob must be 16-byte aligned");
   if (n_nodes <= 0) return PF_OK;
   using KernelFn = void (*)(tcc::NodeParams);
@@ -1930,10 +1966,15 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
       tcc::node_update_tc_kernel<false, true, false>,  tcc::node_update_tc_kernel<true, true, false>,
       tcc::node_update_tc_kernel<false, false, true>,  tcc::node_update_tc_kernel<true, false, true>,
       tcc::node_update_tc_kernel<false, true, true>,   tcc::node_update_tc_kernel<true, true, true>};
+  static const KernelFn mapped_fns[4] = {  // index = FAST + 2 TRACE (first layer: no input vectors)
+      tcc::node_update_tc_kernel<false, false, false, true>, tcc::node_update_tc_kernel<false, true, false, true>,
+      tcc::node_update_tc_kernel<false, false, true, true>,  tcc::node_update_tc_kernel<false, true, true, true>};
+  PF_CHECK_ARG(h_map == nullptr || v_in == nullptr, "pf_node_update_tc_mapped: built for the first layer (no input vectors)");
   static PerDeviceFlag configured = {};
   const int dev_ = current_device();
   if (!configured.done[dev_]) {
-    for (KernelFn f : fns) {
+    for (int i = 0; i < 12; ++i) {
+      const KernelFn f = i < 8 ? fns[i] : mapped_fns[i - 8];
       const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, tcc::kSmemBytes);
       if (e != cudaSuccess) {
         set_error("pf_node_update_tc: cudaFuncSetAttribute(smem=%d): %s", tcc::kSmemBytes, cudaGetErrorString(e));
@@ -1943,11 +1984,12 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
     configured.done[dev_] = true;
   }
   tcc::NodeParams p{h_in, v_in, agg_h, agg_v, (long long)n_nodes, static_cast<const uint8_t*>(wblob), h_out, v_out,
-                    g_tc_trace};
+                    g_tc_trace, h_map};
   const long long tiles = (n_nodes + tcc::kRows - 1) / tcc::kRows;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   const int which = (v_in != nullptr ? 1 : 0) + (fast ? 2 : 0) + (g_tc_trace != nullptr ? 4 : 0);
-  fns[which]<<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
+  const KernelFn fn = h_map != nullptr ? mapped_fns[(fast ? 1 : 0) + (g_tc_trace != nullptr ? 2 : 0)] : fns[which];
+  fn<<<grid, tcc::kThreadsTc, tcc::kSmemBytes, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_node_update_tc");
   return PF_OK;
 }
@@ -1955,6 +1997,14 @@ static int launch_node_update_tc(bool fast, const float* h_in, const float* v_in
 extern "C" int pf_node_update_tc(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,
                                  int64_t n_nodes, const void* wblob, float* h_out, float* v_out, void* stream) {
   return launch_node_update_tc(false, h_in, v_in, agg_h, agg_v, n_nodes, wblob, h_out, v_out, stream);
+}
+
+// Node update whose input scalars come from a row table: node n reads row h_map[n] of h_in (see pf_edge_conv_tc_mapped).
+extern "C" int pf_node_update_tc_mapped(const float* h_in, const int32_t* h_map, const float* v_in, const float* agg_h,
+                                        const float* agg_v, int64_t n_nodes, const void* wblob, float* h_out, float* v_out,
+                                        int32_t f16, void* stream) {
+  PF_CHECK_ARG(h_map != nullptr, "pf_node_update_tc_mapped: null row map");
+  return launch_node_update_tc(f16 != 0, h_in, v_in, agg_h, agg_v, n_nodes, wblob, h_out, v_out, stream, h_map);
 }
 
 extern "C" int pf_node_update_tc_f16(const float* h_in, const float* v_in, const float* agg_h, const float* agg_v,

@@ -7,6 +7,8 @@ any parameter changes), binds the batch's device buffers into a `PfSampleArgs` a
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from typing import Dict, Optional, Union
@@ -166,6 +168,12 @@ class _DeviceState:
             self.seed_table = torch.zeros(seed_rep.numel(), 128, **f32)
             a.seed_row, a.seed_rep, a.seed_table = seed_row.data_ptr(), seed_rep.data_ptr(), self.seed_table.data_ptr()
             a.n_seed_rows = seed_rep.numel()
+            # first-layer encoder table (PF_FLAG_NO_LAYER0_TABLE in the header): the protein scalars of the first conv layer
+            # are read from one row per (graph, atom type) instead of a materialised [n_prot][128] array
+            self.enc = g.enc_arrays()
+            self.enc_table = torch.zeros(seed_rep.numel(), 128, **f32)
+            a.enc_feats, a.enc_ptr, a.enc_rep = (self.enc[k].data_ptr() for k in ("enc_feats", "enc_ptr", "enc_rep"))
+            a.enc_table = self.enc_table.data_ptr()
         self.share = None     # buffers of the shared-pocket mode, bound on first use (bind_share)
         if g.tile_rows == 128:
             if w.tc is None:
@@ -191,7 +199,7 @@ class _DeviceState:
         dev, a = g.device, self.args
         f32 = dict(dtype=torch.float32, device=dev)
         n_c, n_d, rows = max(g.pf_k * g.n_pharm, 1), sh["n_distinct"], sh["enc_rep"].numel()
-        buf = dict(enc_table=torch.zeros(rows, 128, **f32), aggd_h=torch.zeros(n_d, 128, **f32),
+        buf = dict(enc_table=self.enc_table, aggd_h=torch.zeros(n_d, 128, **f32),
                    aggd_v=torch.zeros(n_d, 48, **f32), c_x=torch.zeros(n_c, 3, **f32), c_h=torch.zeros(n_c, 128, **f32),
                    c_v=torch.zeros(n_c, 48, **f32), c_agg_h=torch.zeros(n_c, 128, **f32), c_agg_v=torch.zeros(n_c, 48, **f32),
                    c_seg_id=torch.arange(n_c, dtype=torch.int32, device=dev),
@@ -256,6 +264,10 @@ class PharmRecDynamicsGVP(nn.Module):
         # (graph, atom type) table instead of a per-edge gather + contraction (SURVEY.md hard part 2's exact split; needs
         # one-hot protein features, checked per batch).  False = the general kernel, the A/B switch of the parity tests.
         self.layer0_seed = True
+        # First conv layer, protein scalars: one encoder row per (graph, atom type) read through a row map by the pf
+        # message gather and the protein node update, instead of a per-node encoder pass and a [n_prot][128] array
+        # (PF_FLAG_NO_LAYER0_TABLE; same values, bit-identical results; one-hot protein features, with layer0_seed).
+        self.layer0_table = os.environ.get("PF_LAYER0_TABLE", "1") != "0"   # env: A/B switch for measurements
         # Opt-in exact work elimination for SAMPLING (SURVEY.md hard part 5a + 5b + 5c, csrc/pf_share.cu): first-layer pp
         # messages once per distinct pocket, protein rows encoded / updated only where the last layer reads them.  Needs
         # the same timestep for every graph (the reverse-diffusion loop; forward() checks it) and one-hot protein
@@ -296,7 +308,8 @@ class PharmRecDynamicsGVP(nn.Module):
         st.args.flags = ((1 if (self.skip_dead_work or share) else 0) |     # PF_FLAG_SKIP_DEAD_WORK
                          (2 if self.edge_mlp_precision == "fp16" else 0) |  # PF_FLAG_FP16_SINGLE_PASS
                          (0 if self.layer0_seed else 4) |                   # PF_FLAG_NO_LAYER0_SEED
-                         (8 if share else 0))                               # PF_FLAG_SHARE_POCKET_MESSAGES
+                         (8 if share else 0) |                              # PF_FLAG_SHARE_POCKET_MESSAGES
+                         (0 if self.layer0_table else 16))                  # PF_FLAG_NO_LAYER0_TABLE
         return st
 
     # ------------------------------------------------------------------ forward

@@ -237,6 +237,19 @@ def edge_conv_tc(src_h: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torc
                                   _f(agg_v), int(accumulate), _s()), "pf_edge_conv_tc")
 
 
+@torch.library.custom_op(f"{NS}::edge_conv_tc_mapped", mutates_args=("agg_h", "agg_v"))
+def edge_conv_tc_mapped(src_h: torch.Tensor, src_map: torch.Tensor, src_v: Optional[torch.Tensor], src_x: torch.Tensor,
+                        dst_x: torch.Tensor, seg_start: torch.Tensor, seg_cnt: torch.Tensor, seg_dst: Optional[torch.Tensor],
+                        col: torch.Tensor, tiles: torch.Tensor, n_tiles: torch.Tensor, wblob: torch.Tensor,
+                        agg_h: torch.Tensor, agg_v: torch.Tensor, accumulate: bool, fp16: bool = False) -> None:
+    """K3 (general tcgen05 kernel) whose source scalars come from a row table: node n reads row src_map[n] of src_h."""
+    if wblob.dtype != torch.uint8 or wblob.numel() != _L.pf_tc_msg_blob_bytes():
+        raise _lib.PfError("edge_conv_tc_mapped: wblob must be the uint8 image built by weights.pack_message_tc")
+    _lib.check(_L.pf_edge_conv_tc_mapped(_f(src_h), _i(src_map), _f(src_v), _f(src_x), _f(dst_x), _i(seg_start), _i(seg_cnt),
+                                         _i(seg_dst), _i(col), _i(tiles), _i(n_tiles), tiles.numel() // 2, _p(wblob),
+                                         _f(agg_h), _f(agg_v), int(accumulate), int(fp16), _s()), "pf_edge_conv_tc_mapped")
+
+
 @torch.library.custom_op(f"{NS}::seed_table", mutates_args=("table",))
 def seed_table(h: torch.Tensor, rep_node: torch.Tensor, w_msg: torch.Tensor, table: torch.Tensor) -> None:
     """table[r] = k Wf0[:, 0:128] h[rep_node[r]] (rows with rep_node[r] < 0 untouched); w_msg = fp32 packed message chain."""
@@ -272,6 +285,17 @@ def node_update_tc(h_in: torch.Tensor, v_in: Optional[torch.Tensor], agg_h: torc
         raise _lib.PfError("node_update_tc: wblob must be the uint8 image built by weights.pack_update_tc")
     _lib.check((_L.pf_node_update_tc_f16 if fp16 else _L.pf_node_update_tc)(_f(h_in), _f(v_in), _f(agg_h), _f(agg_v), h_in.shape[0], _p(wblob), _f(h_out),
                                     _f(v_out), _s()), "pf_node_update_tc")
+
+
+@torch.library.custom_op(f"{NS}::node_update_tc_mapped", mutates_args=("h_out", "v_out"))
+def node_update_tc_mapped(h_table: torch.Tensor, h_map: torch.Tensor, agg_h: torch.Tensor, agg_v: torch.Tensor,
+                          wblob: torch.Tensor, h_out: torch.Tensor, v_out: torch.Tensor, fp16: bool = False) -> None:
+    """K4 of the first conv layer (no input vectors) whose input scalars come from a row table: node n reads row
+    h_map[n] of h_table; h_out / v_out are full per-node arrays."""
+    if wblob.dtype != torch.uint8 or wblob.numel() != _L.pf_tc_upd_blob_bytes():
+        raise _lib.PfError("node_update_tc_mapped: wblob must be the uint8 image built by weights.pack_update_tc")
+    _lib.check(_L.pf_node_update_tc_mapped(_f(h_table), _i(h_map), None, _f(agg_h), _f(agg_v), h_map.numel(), _p(wblob),
+                                           _f(h_out), _f(v_out), int(fp16), _s()), "pf_node_update_tc_mapped")
 
 
 @torch.library.custom_op(f"{NS}::noise_head", mutates_args=())

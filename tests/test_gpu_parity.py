@@ -454,6 +454,32 @@ def test_edge_conv_seeded_first_layer(env, fp16):
         close(out[True][1], out[False][1], rtol=2e-5, atol=2e-6, what="seeded vs general vectors")
 
 
+def test_denoiser_layer0_encoder_table_is_bit_identical(env):
+    """PF_FLAG_NO_LAYER0_TABLE: reading the first layer's protein scalars from the (graph, atom type) encoder table through
+    the row map (pf_edge_conv_tc_mapped / pf_node_update_tc_mapped) is the same arithmetic on the same values as the
+    per-node encoder pass: eps and the final protein features agree bit for bit, ragged batch, per-graph timesteps."""
+    g, b = env.build([(400, 0), (250, 1), (1, 4), (77, 9)], [[3, 8, 5], [4, 6], [3], [16, 3]])
+    x, h, prot = random_state(b, 23, 4.0)
+    st = env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    tt = torch.rand(g.n_graphs, generator=torch.Generator().manual_seed(3))
+    dyn = env.model.dynamics
+    res = {}
+    try:
+        for on in (True, False):
+            dyn.layer0_table = on
+            st.prot_h.fill_(float("nan"))
+            gh, gx = dyn(g, tt, None)
+            res[on] = (gh.clone(), gx.clone(), st.prot_h.clone(), st.prot_v.clone())
+    finally:
+        dyn.layer0_table = True
+    for a_, b_ in zip(res[True], res[False]):
+        assert torch.equal(a_, b_)
+    wh, wx = env.O.denoiser(env.sd, b, tt, env.cfg)
+    close(res[True][0], wh, what="eps_h (encoder table)")
+    close(res[True][1], wx, what="eps_x (encoder table)")
+
+
 def test_denoiser_layer0_seed_switch(env):
     """PF_FLAG_NO_LAYER0_SEED: the general first-layer kernel and the seeded one give the same eps (per-graph timesteps);
     a batch whose protein features are not one-hot falls back to the general kernel by itself."""

@@ -92,3 +92,58 @@ def test_tc_gemm_weight_gradient_is_accurate_and_deterministic(rows, N, K):
     ref = dy.double().t() @ x.double()
     err = (outs[0].double() - ref).abs().max().item()
     assert err <= 5e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+def test_mapped_kernels_equal_the_materialised_rows():
+    """pf_edge_conv_tc_mapped / pf_node_update_tc_mapped (source / input scalars read through a row map from a small
+    table) against the plain kernels on the materialised rows table[map]: bit-identical outputs."""
+    import json
+    import os
+    from pharmacoforge_b200 import ops
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.diffusion import PharmacophoreDiff
+    from pharmacoforge_b200.hostutil import polynomial_gamma
+    from pharmacoforge_b200.synthetic import make_pocket, synth_state_dict
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    layout = json.load(open(os.path.join(root, "tests/golden/state_dict_layout.json")))
+    sd = synth_state_dict(layout, seed=0)
+    sd["gamma.gamma"] = polynomial_gamma(100, 1e-5, 2.0)
+    dyn = dict(vector_size=16, n_convs=2, n_hidden_scalars=128, message_norm="mean", dropout=0.1, ff_k=0, pf_k=5,
+               n_message_gvps=3, n_update_gvps=2, n_noise_gvps=4)
+    model = PharmacophoreDiff(6, 11, list("abcdef"), n_timesteps=100, graph_config={"graph_cutoffs": {"pp": 3.5, "pf": 8, "fp": 8, "ff": 9}},
+                              dynamics_config=dyn, precision=1e-5)
+    model.load_state_dict(sd)
+    dev = torch.device("cuda:0")
+    g = GraphBatch.from_pockets([Pocket.from_numpy(*make_pocket(n, seed=s)) for n, s in ((300, 1), (77, 2), (1, 3))],
+                                [[3, 8], [5], [4, 4, 4]], dev)
+    W = model.dynamics.packed_weights(dev)
+    gen = torch.Generator().manual_seed(5)
+    table = torch.randn(g.n_graphs * 11, 128, generator=gen).to(dev)
+    row = torch.randint(0, table.shape[0], (g.n_prot,), generator=gen).to(dev).to(torch.int32)
+    full = table[row.long()].contiguous()
+    # K3 over the pp edges, general kernel without source vectors
+    blob = W.tc[3 * W.tc_stride:4 * W.tc_stride]
+    outs = []
+    for mapped in (False, True):
+        ah, av = torch.full((g.n_prot, 128), float("nan"), device=dev), torch.full((g.n_prot, 48), float("nan"), device=dev)
+        if mapped:
+            ops.edge_conv_tc_mapped(table, row, None, g.prot_x, g.prot_x, g.pp_start, g.pp_cnt, None, g.pp_col, g.pp_tiles,
+                                    g.pp_n_tiles, blob, ah, av, False, False)
+        else:
+            ops.edge_conv_tc(full, None, g.prot_x, g.prot_x, g.pp_start, g.pp_cnt, None, g.pp_col, g.pp_tiles, g.pp_n_tiles,
+                             blob, ah, av, False, False)
+        outs.append((ah, av))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert bool(torch.isfinite(outs[1][0]).all())
+    # K4, first layer (no input vectors)
+    agg_h, agg_v = outs[0]
+    res = []
+    for mapped in (False, True):
+        oh, ov = torch.empty(g.n_prot, 128, device=dev), torch.empty(g.n_prot, 48, device=dev)
+        if mapped:
+            ops.node_update_tc_mapped(table, row, agg_h, agg_v, W.tcu_view(0, 1), oh, ov, False)
+        else:
+            ops.node_update_tc(full, None, agg_h, agg_v, W.tcu_view(0, 1), oh, ov, False)
+        res.append((oh, ov))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert bool(torch.isfinite(res[1][0]).all())
