@@ -138,6 +138,10 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
                                // EPI-B (1.25 MUFU + 8 instructions per element); 0: one per element (2 MUFU + 6): the XU pipe,
                                // not the issue slots, is the scarcer resource of that stage
 #endif
+#ifndef PF_MEAN_SPLIT
+#define PF_MEAN_SPLIT 1   // 1 (default, measured -1.1 .. -1.5 % per pp launch, bit-identical): one column quad per thread in
+                          // the segmented mean (16 threads per segment), see segment_means1; 0: two quads, 8 threads
+#endif
 #ifndef PF_K4_TILE_ALT
 #define PF_K4_TILE_ALT 0
 #endif
@@ -512,6 +516,43 @@ __device__ __forceinline__ void segment_means(const float* bx, const float* by, 
     } else {
       *reinterpret_cast<float4*>(ox + o) = a0;
       *reinterpret_cast<float4*>(oy + o) = a1;
+    }
+  }
+}
+
+// The same reduction with ONE column quad per thread (PF_MEAN_SPLIT): 16 threads per segment, 16 segments in flight per
+// slot.  A tile of the pp graph holds ~17 segments, so with 32 segment slots x 2 quads per thread half of the slot's threads
+// idle while the others do twice the work; per (segment, column) the rows are summed in the same order: identical results.
+template <int PITCH>
+__device__ __forceinline__ void segment_means1(const float* bx, const int jfirst, const int jstep, const int nseg,
+                                               const int4* s_rec, float* ox, const int out_pitch, const int accumulate) {
+  const uint32_t ax = tc::smem_u32(bx);
+  for (int j = jfirst; j < nseg; j += jstep) {
+    const int4 rec = s_rec[j];
+    const int r0 = rec.x, r1 = rec.y;
+    if (accumulate && r1 == r0) continue;
+    uint64_t s0 = 0, s1 = 0;
+    for (int r = r0; r < r1; r += 8) {
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      lds128_rows8<PITCH>(x, ax + r * (PITCH * 4), r1 - r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s0 = tc::add2(s0, tc::pack2(x[i].x, x[i].y));
+        s1 = tc::add2(s1, tc::pack2(x[i].z, x[i].w));
+      }
+    }
+    const float rc = __int_as_float(rec.w);
+    const uint64_t rc2 = tc::pack2(rc, rc);
+    float4 a0;
+    tc::unpack2(tc::mul2(s0, rc2), a0.x, a0.y);
+    tc::unpack2(tc::mul2(s1, rc2), a0.z, a0.w);
+    const size_t o = (size_t)rec.z * out_pitch;
+    if (accumulate) {
+      atomicAdd(reinterpret_cast<float4*>(ox + o), a0);
+    } else {
+      *reinterpret_cast<float4*>(ox + o) = a0;
     }
   }
 }
@@ -1034,10 +1075,16 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
             trace_ev<TRACE>(trace, T, tn, (g << 8) | (0x23 + 3 * ps));
             {
               // staging columns [0, 32) = columns 32 ps .. of half 0, [32, 64) = the same of half 1
+#if PF_MEAN_SPLIT
+              const int c8 = stid & 7, hf = (stid >> 3) & 1;
+              segment_means1<kMeanPitch>(ab + 32 * hf + 4 * c8, stid >> 4, 16, nseg, s_rec,
+                                         p.agg_h + 32 * ps + 4 * c8 + 64 * hf, kHidden, p.accumulate);
+#else
               const int c8 = stid & 7;
               float* out = p.agg_h + 32 * ps + 4 * c8;
               segment_means<kMeanPitch>(ab + 4 * c8, ab + 32 + 4 * c8, stid >> 3, nseg, s_rec, out, out + 64, kHidden,
                                         p.accumulate);
+#endif
             }
             trace_ev<TRACE>(trace, T, tn, (g << 8) | (0x24 + 3 * ps));
             slot_barrier(T);
@@ -1101,10 +1148,16 @@ __device__ void epilogue_role(const Params& p, const int T, uint8_t* smem, uint3
                   make_float4(Vu[8 * c + 4 * u4], Vu[8 * c + 4 * u4 + 1], Vu[8 * c + 4 * u4 + 2], Vu[8 * c + 4 * u4 + 3]);
           slot_barrier(T);
           {
+#if PF_MEAN_SPLIT
+            const int c16 = stid & 15;
+            if (c16 < kVRow / 4)
+              segment_means1<kMeanPitchV>(ab + 4 * c16, stid >> 4, 16, nseg, s_rec, p.agg_v + 4 * c16, kVRow, p.accumulate);
+#else
             const int c8 = stid & 7;
             if (c8 < kVRow / 8)
               segment_means<kMeanPitchV>(ab + 4 * c8, ab + 24 + 4 * c8, stid >> 3, nseg, s_rec, p.agg_v + 4 * c8,
                                          p.agg_v + 24 + 4 * c8, kVRow, p.accumulate);
+#endif
           }
         }
       }
