@@ -143,7 +143,10 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
                           // the segmented mean (16 threads per segment), see segment_means1; 0: two quads, 8 threads
 #endif
 #ifndef PF_K4_TILE_ALT
-#define PF_K4_TILE_ALT 0
+#define PF_K4_TILE_ALT 1   // node update: S jobs of the two slots alternate TILE-wise and the weight ring is loaded in that order
+                           // (one consumer per slab): the slots sit ~a quarter period apart instead of marching in lockstep
+                           // through load phase, GVP chain and store phase.  Measured 3.01 / 3.02 -> 2.87 / 2.85 ms at 3.07 M
+                           // nodes, identical outputs.  0: job-wise alternation on a ring shared by both slots (K3's scheme)
 #endif
 #ifndef PF_K4_L2HINT
 #define PF_K4_L2HINT 15  // (default: all four, measured 3.09 / 3.12 -> 2.99 / 3.00 ms at 3.07 M nodes, identical outputs)
@@ -193,6 +196,23 @@ __device__ void producer_role(const uint8_t* wblob, uint8_t* smem, uint64_t* bar
 #pragma unroll
   for (int i = 0; i < Cfg<MODE>::kSmallBytes / 8192; ++i)
     tc::bulk_g2s(smem + kOffSmall + i * 8192, wblob + blob_small_off<MODE>() + i * 8192, 8192, bar_small);
+  if constexpr (MODE == 1 && PF_K4_TILE_ALT != 0) {
+    // Tile-wise order (node update, PF_K4_TILE_ALT): the slab sequence of tile q (slot q & 1) follows that of tile q - 1,
+    // every slab has ONE consumer (the slot of its tile) and one `empty` barrier per ring position; the S jobs are issued
+    // in the same order (mma_role), so loads and consumption walk the ring in lockstep and the two slots can sit half a
+    // tile apart (one in its memory phases while the other runs its GVP chain).  Costs each slab twice per tile pair.
+#pragma unroll 1
+    for (int q = 0; q < my_tiles; ++q) {
+#pragma unroll 1
+      for (int i = 0; i < kSlabsPerTile; ++i) {
+        const int n = kSlabsPerTile * q + i, pos = n % kRing, u = n / kRing;
+        if (u >= 1) tc::mbar_wait(&bar_empty[pos], (uint32_t)(u - 1) & 1u);
+        tc::mbar_expect_tx(&bar_full[pos], kSlab);
+        tc::bulk_g2s(smem + kOffRing + pos * kSlab, wblob + (size_t)(i + Cfg<MODE>::kBlobSlab0) * kSlab, kSlab, &bar_full[pos]);
+      }
+    }
+    return;
+  }
   const int pairs = (my_tiles + 1) >> 1;
 #pragma unroll 1
   for (int t = 0; t < pairs; ++t) {
@@ -350,16 +370,23 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
           tc::mma_ss(Dreg, a_lo, b_hi, kI128, 1);
         }
       }
-      tc::mma_commit(&my_empty[pos]);
+      tc::mma_commit(kTileAlt ? &bar_empty[pos] : &my_empty[pos]);
     };
 #pragma unroll
     for (int k = 0; k < nslab; k += 2) {
       constexpr int base = slab_base<MODE>(g);
-      const int i0 = base + k, pos0 = i0 % kRing;
+      const int i0 = base + k;
       const bool two = k + 1 < nslab;
-      const int i1 = i0 + 1, pos1 = i1 % kRing;
-      tc::mbar_wait(&bar_full[pos0], full_parity<MODE>(i0, t));
-      if (two) tc::mbar_wait(&bar_full[pos1], full_parity<MODE>(i1, t));
+      const int i1 = i0 + 1;
+      // tile-wise order: slab i of this slot's t-th tile is slab (2 t + T) kSlabsPerTile + i of the CTA's sequence
+      const int n0 = kTileAlt ? (Cfg<MODE>::kSlabsPerTile * T) % kRing + i0 : i0, n1 = n0 + 1;
+      const int pos0 = n0 % kRing, pos1 = n1 % kRing;
+      const uint32_t tile_uses = (uint32_t)(2 * Cfg<MODE>::kSlabsPerTile / kRing) * t +
+                                 (uint32_t)((Cfg<MODE>::kSlabsPerTile * T) / kRing);   // ring laps before this tile
+      const uint32_t par0 = kTileAlt ? (tile_uses + (uint32_t)(n0 / kRing)) & 1u : full_parity<MODE>(i0, t);
+      const uint32_t par1 = kTileAlt ? (tile_uses + (uint32_t)(n1 / kRing)) & 1u : full_parity<MODE>(i1, t);
+      tc::mbar_wait(&bar_full[pos0], par0);
+      if (two) tc::mbar_wait(&bar_full[pos1], par1);
       if (tc::elect_one()) {
         issue_slab(k, pos0);
         if (two) issue_slab(k + 1, pos1);

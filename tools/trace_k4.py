@@ -4,7 +4,8 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pharmacoforge_b200 import ops, _lib
-from pharmacoforge_b200.diffusion import PharmacophoreDiff, polynomial_gamma
+from pharmacoforge_b200.diffusion import PharmacophoreDiff
+from pharmacoforge_b200.hostutil import polynomial_gamma
 from pharmacoforge_b200.synthetic import synth_state_dict
 layout = json.load(open(os.path.join(ROOT, "tests/golden/state_dict_layout.json")))
 sd = synth_state_dict(layout, seed=0); sd["gamma.gamma"] = polynomial_gamma(100, 1e-5, 2.0)
