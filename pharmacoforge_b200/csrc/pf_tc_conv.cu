@@ -148,6 +148,13 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
                            // through load phase, GVP chain and store phase.  Measured 3.01 / 3.02 -> 2.87 / 2.85 ms at 3.07 M
                            // nodes, identical outputs.  0: job-wise alternation on a ring shared by both slots (K3's scheme)
 #endif
+#ifndef PF_K4_PREFETCH_AT
+#define PF_K4_PREFETCH_AT 6   // where / how a slot pulls its NEXT tile's rows into L2: 0 never, 1 per-thread prefetches at the
+                              // start of the GVP chain, 2 at tile start, 3 at the start of the back end, 4 at 1 and 3, 5 / 6 =
+                              // 1 / 3 as four bulk-copy prefetches (cp.async.bulk.prefetch.L2, one per array).  Measured at
+                              // 3.07 M nodes with the tile-wise ring order (layer-1 launch): 0: 3.05 ms, 1: 2.84, 2: 3.29,
+                              // 3: 2.81, 4: 2.99, 5: 2.77, 6: 2.72 (default)
+#endif
 #ifndef PF_K4_L2HINT
 #define PF_K4_L2HINT 15  // (default: all four, measured 3.09 / 3.12 -> 2.99 / 3.00 ms at 3.07 M nodes, identical outputs)
                          // node update, L2 eviction hints (bits): 1 = the normalised rows written by the front end and re-read
@@ -1315,6 +1322,40 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
     const int nrows = rem < kRows ? (int)rem : kRows;
     slot_barrier(T);  // everyone is done with the previous tile's staging / exchange buffers
     trace_ev<TRACE>(trace, T, tn, 0x01);
+    auto prefetch_next = [&]() {
+      if (it + 2 < my_tiles) {
+        const long long m0 = n0 + 2LL * gridDim.x * kRows;
+        const long long mrem = p.n_nodes - m0;
+        const int mrows = mrem < kRows ? (int)mrem : kRows;
+        const int lines_h = mrows * 4, lines_v = (mrows * kVRow * 4 + 127) / 128;  // 128-byte lines
+#if PF_K4_L2HINT & 8
+#define PF_K4_PREFETCH tc::prefetch_l2_evict_last
+#else
+#define PF_K4_PREFETCH tc::prefetch_l2
+#endif
+        for (int l = stid; l < lines_h; l += 256) {
+          if constexpr (!MAPPED) PF_K4_PREFETCH(reinterpret_cast<const char*>(p.h_in + m0 * kHidden) + (size_t)l * 128);
+          PF_K4_PREFETCH(reinterpret_cast<const char*>(p.agg_h + m0 * kHidden) + (size_t)l * 128);
+        }
+        for (int l = stid; l < lines_v; l += 256) {
+          PF_K4_PREFETCH(reinterpret_cast<const char*>(p.agg_v + m0 * kVRow) + (size_t)l * 128);
+          if constexpr (HAS_V) PF_K4_PREFETCH(reinterpret_cast<const char*>(p.v_in + m0 * kVRow) + (size_t)l * 128);
+        }
+#undef PF_K4_PREFETCH
+      }
+    };
+    if (PF_K4_PREFETCH_AT == 2) prefetch_next();
+    auto prefetch_next_bulk = [&]() {   // the same ranges by the bulk-copy engine: one instruction per array and tile
+      if (it + 2 < my_tiles && stid < 4) {
+        const long long m0 = n0 + 2LL * gridDim.x * kRows;
+        const long long mrem = p.n_nodes - m0;
+        const int mrows = mrem < kRows ? (int)mrem : kRows;
+        if (stid == 0 && !MAPPED) tc::prefetch_l2_bulk(p.h_in + m0 * kHidden, (uint32_t)mrows * kHidden * 4);
+        if (stid == 1) tc::prefetch_l2_bulk(p.agg_h + m0 * kHidden, (uint32_t)mrows * kHidden * 4);
+        if (stid == 2) tc::prefetch_l2_bulk(p.agg_v + m0 * kVRow, (uint32_t)mrows * kVRow * 4);
+        if (stid == 3 && HAS_V) tc::prefetch_l2_bulk(p.v_in + m0 * kVRow, (uint32_t)mrows * kVRow * 4);
+      }
+    };
 
     // ---- scalars: x = h_in + agg_h (own 64 columns, cooperative layout), LayerNorm_msg over the full row
     {
@@ -1522,26 +1563,8 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
     // during which DRAM idles.  Pull the rows of the slot's NEXT tile into L2 now, under the GVP chain (per-thread
     // prefetches: the bulk-copy engine would queue them in front of the weight slabs).  Issued at tile start instead,
     // the same prefetch made the kernel 5 % slower (it joins the demand burst and doubles the L2 footprint).
-    if (it + 2 < my_tiles) {
-      const long long m0 = n0 + 2LL * gridDim.x * kRows;
-      const long long mrem = p.n_nodes - m0;
-      const int mrows = mrem < kRows ? (int)mrem : kRows;
-      const int lines_h = mrows * 4, lines_v = (mrows * kVRow * 4 + 127) / 128;  // 128-byte lines
-#if PF_K4_L2HINT & 8
-#define PF_K4_PREFETCH tc::prefetch_l2_evict_last
-#else
-#define PF_K4_PREFETCH tc::prefetch_l2
-#endif
-      for (int l = stid; l < lines_h; l += 256) {
-        if constexpr (!MAPPED) PF_K4_PREFETCH(reinterpret_cast<const char*>(p.h_in + m0 * kHidden) + (size_t)l * 128);
-        PF_K4_PREFETCH(reinterpret_cast<const char*>(p.agg_h + m0 * kHidden) + (size_t)l * 128);
-      }
-      for (int l = stid; l < lines_v; l += 256) {
-        PF_K4_PREFETCH(reinterpret_cast<const char*>(p.agg_v + m0 * kVRow) + (size_t)l * 128);
-        if constexpr (HAS_V) PF_K4_PREFETCH(reinterpret_cast<const char*>(p.v_in + m0 * kVRow) + (size_t)l * 128);
-      }
-#undef PF_K4_PREFETCH
-    }
+    if (PF_K4_PREFETCH_AT == 1 || PF_K4_PREFETCH_AT == 4) prefetch_next();
+    if (PF_K4_PREFETCH_AT == 5) prefetch_next_bulk();
 #pragma unroll 1
     for (int g = 0; g < 2; ++g) {
       const uint32_t Areg = g == 1 ? Q : P, Dreg = g == 1 ? P : Q;
@@ -1673,6 +1696,8 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
       }
     }
 
+    if (PF_K4_PREFETCH_AT == 3 || PF_K4_PREFETCH_AT == 4) prefetch_next();
+    if (PF_K4_PREFETCH_AT == 6) prefetch_next_bulk();
     // ================= back end: residual + GVPLayerNorm_upd.  Last GVP was g = 1: f (hi, lo) sits in region P,
     // region Q is free (its gate columns were read above).
     trace_ev<TRACE>(trace, T, tn, 0x43);
