@@ -142,6 +142,11 @@ __device__ __forceinline__ void stage_store16(uint8_t* slab, int m, const float*
 #define PF_MEAN_SPLIT 1   // 1 (default, measured -1.1 .. -1.5 % per pp launch, bit-identical): one column quad per thread in
                           // the segmented mean (16 threads per segment), see segment_means1; 0: two quads, 8 threads
 #endif
+#ifndef PF_K3_TILE_ALT
+#define PF_K3_TILE_ALT 0   // the same tile-wise order for the edge kernels (every weight slab then comes twice per tile pair from
+                           // L2: 232 KB per 128-edge tile instead of per pair).  Measured at 23.2 M edges: general kernel
+                           // without / with source vectors 14.22 -> 16.56 / 16.65 -> 17.11 ms: worse, stays off
+#endif
 #ifndef PF_K4_TILE_ALT
 #define PF_K4_TILE_ALT 1   // node update: S jobs of the two slots alternate TILE-wise and the weight ring is loaded in that order
                            // (one consumer per slab): the slots sit ~a quarter period apart instead of marching in lockstep
@@ -189,6 +194,8 @@ __device__ __forceinline__ void pair_barrier(int T, int q) { tc::named_bar_sync(
 
 // ------------------------------------------------------------------------------------------------ producer
 template <int MODE>
+__host__ __device__ constexpr bool tile_alt() { return MODE == 1 ? (PF_K4_TILE_ALT != 0) : (PF_K3_TILE_ALT != 0); }
+template <int MODE>
 __host__ __device__ constexpr int ring_uses_p(int pos) { return (Cfg<MODE>::kSlabsPerTile - pos + kRing - 1) / kRing; }
 
 // Slab i of the tile sequence goes to ring position i % kRing (see ring_uses / full_parity below).  Before the copy,
@@ -203,7 +210,7 @@ __device__ void producer_role(const uint8_t* wblob, uint8_t* smem, uint64_t* bar
 #pragma unroll
   for (int i = 0; i < Cfg<MODE>::kSmallBytes / 8192; ++i)
     tc::bulk_g2s(smem + kOffSmall + i * 8192, wblob + blob_small_off<MODE>() + i * 8192, 8192, bar_small);
-  if constexpr (MODE == 1 && PF_K4_TILE_ALT != 0) {
+  if constexpr (tile_alt<MODE>()) {
     // Tile-wise order (node update, PF_K4_TILE_ALT): the slab sequence of tile q (slot q & 1) follows that of tile q - 1,
     // every slab has ONE consumer (the slot of its tile) and one `empty` barrier per ring position; the S jobs are issued
     // in the same order (mma_role), so loads and consumption walk the ring in lockstep and the two slots can sit half a
@@ -282,7 +289,7 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
   // alternation (slot 0 job j, slot 1 job j, ...).  Node update (kTileAlt): TILE-wise alternation (both jobs of slot 0's
   // tile, then both of slot 1's): a slot's GVP chain then runs under the other slot's memory phases (back end + front end)
   // instead of both slots loading, computing and storing in lockstep.
-  constexpr bool kTileAlt = (MODE == 1) && (PF_K4_TILE_ALT != 0);
+  constexpr bool kTileAlt = tile_alt<MODE>();
   constexpr int kG = Cfg<MODE>::kGvps;
   auto seq_of = [&](int slot, int j) { return kTileAlt ? (2 * (j / kG) + slot) * kG + (j % kG) : 2 * j + slot; };
   auto seq_valid = [&](int sq) {   // does the job with this sequence number exist?
@@ -386,12 +393,13 @@ __device__ void mma_role(const int T, uint8_t* smem, uint32_t tmem, uint64_t* ba
       const bool two = k + 1 < nslab;
       const int i1 = i0 + 1;
       // tile-wise order: slab i of this slot's t-th tile is slab (2 t + T) kSlabsPerTile + i of the CTA's sequence
-      const int n0 = kTileAlt ? (Cfg<MODE>::kSlabsPerTile * T) % kRing + i0 : i0, n1 = n0 + 1;
-      const int pos0 = n0 % kRing, pos1 = n1 % kRing;
-      const uint32_t tile_uses = (uint32_t)(2 * Cfg<MODE>::kSlabsPerTile / kRing) * t +
-                                 (uint32_t)((Cfg<MODE>::kSlabsPerTile * T) / kRing);   // ring laps before this tile
-      const uint32_t par0 = kTileAlt ? (tile_uses + (uint32_t)(n0 / kRing)) & 1u : full_parity<MODE>(i0, t);
-      const uint32_t par1 = kTileAlt ? (tile_uses + (uint32_t)(n1 / kRing)) & 1u : full_parity<MODE>(i1, t);
+      // (tile_n0 = slabs of the CTA's sequence before this tile, tile 2 t + T: position and lap of slab i follow from it)
+      const uint32_t tile_n0 = (uint32_t)Cfg<MODE>::kSlabsPerTile * (2u * t + (uint32_t)T);
+      const uint32_t n0 = kTileAlt ? tile_n0 % kRing + (uint32_t)i0 : (uint32_t)i0, n1 = n0 + 1;
+      const int pos0 = (int)(n0 % kRing), pos1 = (int)(n1 % kRing);
+      const uint32_t tile_uses = tile_n0 / kRing;   // ring laps before this tile
+      const uint32_t par0 = kTileAlt ? (tile_uses + n0 / kRing) & 1u : full_parity<MODE>(i0, t);
+      const uint32_t par1 = kTileAlt ? (tile_uses + n1 / kRing) & 1u : full_parity<MODE>(i1, t);
       tc::mbar_wait(&bar_full[pos0], par0);
       if (two) tc::mbar_wait(&bar_full[pos1], par1);
       if (tc::elect_one()) {
