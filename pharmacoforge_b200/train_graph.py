@@ -94,11 +94,15 @@ def build_edges(g: GraphBatch) -> Dict[str, dict]:
     return out
 
 
-def conv_forward_fused(conv, feats, edges, geom, training: bool):
-    """`conv_forward` with one autograd node per edge type and per node type (train_fused.py)."""
+def conv_forward_fused(conv, feats, edges, geom, training: bool, pharm_only: bool = False):
+    """`conv_forward` with one autograd node per edge type and per node type (train_fused.py).  pharm_only: the opt-in
+    exact dead-work elimination (dynamics.skip_dead_work) for the LAST layer -- nothing reads its protein side
+    (dynamics_gvp.py:84-92), autograd never visits it either, so its pp / fp messages and protein update are not run."""
     agg = {}
     for name in ("ff", "pf", "fp", "pp"):                         # reference etype order (dynamics_gvp.py:46-54)
         e = edges[name]
+        if pharm_only and e["dst_nt"] == "prot":
+            continue
         key = f"{e['src_nt']}_{name}_{e['dst_nt']}"
         h_src, v_src = feats[e["src_nt"]]
         xd, rbf = geom[name]
@@ -106,7 +110,7 @@ def conv_forward_fused(conv, feats, edges, geom, training: bool):
         prev = agg.get(e["dst_nt"])
         agg[e["dst_nt"]] = (a_h, a_v) if prev is None else (prev[0] + a_h, prev[1] + a_v)   # cross_reducer="sum"
     return {nt: F.node_update(conv, nt, feats[nt][0], feats[nt][1], agg[nt][0], agg[nt][1], training)
-            for nt in ("pharm", "prot")}
+            for nt in (("pharm",) if pharm_only else ("pharm", "prot"))}
 
 
 def conv_forward(conv, feats, edges, geom, training: bool):
@@ -159,8 +163,12 @@ def dynamics_forward(dyn, g: GraphBatch, t: torch.Tensor, training: bool = True)
     vs = dyn.vector_size
     feats = {"pharm": (h_f, torch.zeros(g.n_pharm, 3, vs, device=dev)),
              "prot": (h_p, torch.zeros(g.n_prot, 3, vs, device=dev))}
-    for conv in dyn.noise_predictor.conv_layers:
-        feats = conv_forward(conv, feats, edges, geom, training)
+    layers = list(dyn.noise_predictor.conv_layers)
+    for li, conv in enumerate(layers):
+        if HOST_FUSED and getattr(dyn, "skip_dead_work", False) and li == len(layers) - 1:
+            feats = conv_forward_fused(conv, feats, edges, geom, training, pharm_only=True)
+        else:
+            feats = conv_forward(conv, feats, edges, geom, training)
     head = dyn.noise_predictor.noise_predictor
     sca, vec = feats["pharm"]
     if HOST_FUSED:

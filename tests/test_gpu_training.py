@@ -281,3 +281,40 @@ def test_fused_host_graph_matches_op_by_op_graph(sd, dyn_cfg):
             n_live += 1
             close(ga, gb_, rtol=1e-4, what=n)
     assert n_live >= 190
+
+
+def test_training_dead_work_elimination_is_exact(sd, dyn_cfg):
+    """dynamics.skip_dead_work in training mode: the last layer's protein side (pp / fp messages, protein update) is not
+    run; losses and the gradient of every live parameter are the same numbers (same kernels on the same inputs for
+    everything that is read), the dead parameters keep grad None either way."""
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    pockets = [Pocket.from_numpy(*make_pocket(140 + 25 * i, seed=80 + i)) for i in range(3)]
+    sizes = [[6], [4], [8]]
+    nf = sum(s[0] for s in sizes)
+    gen = torch.Generator().manual_seed(21)
+    h0 = torch.nn.functional.one_hot(torch.randint(0, 6, (nf,), generator=gen), 6).float()
+    x0 = torch.cat([p.prot_x.mean(0, keepdim=True) + torch.randn(s[0], 3, generator=gen) for p, s in zip(pockets, sizes)])
+    t_int = torch.tensor([5, 60, 95])
+    eps = {"x": torch.randn(nf, 3, generator=gen), "h": torch.randn(nf, 6, generator=gen)}
+    model = _model(sd, dyn_cfg, dropout=0.1).train()
+    res = []
+    try:
+        for skip in (False, True):
+            model.dynamics.skip_dead_work = skip
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(77)
+            gb = GraphBatch.from_pockets(pockets, sizes, "cuda:0").set_pharmacophores(x0, h0)
+            total, _, _ = model.training_step(gb, t_int=t_int, eps=eps)
+            total.backward()
+            res.append((float(total), {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}))
+    finally:
+        model.dynamics.skip_dead_work = False
+    # dropout masks: the skipped protein update does not draw its four masks, and it is the LAST draw of the forward pass, so
+    # every mask that is used is the same in both runs
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * max(1.0, abs(res[0][0])), (res[0][0], res[1][0])
+    for n, ga in res[0][1].items():
+        gb_ = res[1][1][n]
+        assert (ga is None) == (gb_ is None), n
+        if ga is not None and ga.numel():
+            close(ga, gb_, rtol=1e-4, what=n)
