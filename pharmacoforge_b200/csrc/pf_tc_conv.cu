@@ -1413,6 +1413,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
           rs[i] += (x.x + x.y) + (x.z + x.w);
           rq[i] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
         }
+      trace_ev<TRACE>(trace, T, tn, 0x4a);   // all 32 row loads of this thread have arrived
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         rs[i] = xor8_sum(rs[i]);
@@ -1424,6 +1425,7 @@ __device__ void node_epilogue_role(const NodeParams& p, const int T, uint8_t* sm
         }
       }
       pair_barrier(T, q);
+      trace_ev<TRACE>(trace, T, tn, 0x4b);   // row statistics exchanged
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         const int c = 2 * hh + c2;

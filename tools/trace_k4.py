@@ -34,7 +34,7 @@ run(); torch.cuda.synchronize()
 lib.pf_tc_trace(None)
 t = tr.cpu().numpy()[:4 * 4096 * 2].reshape(4, 4096, 2)
 t0 = min(t[r, 0, 1] for r in range(4) if t[r, 0, 1] > 0)
-names = {0x01: "tile start", 0x41: "front H done", 0x42: "front H barrier", 0x10: "vec staged / GVP start", 0x43: "GVPs done", 0x44: "back V done", 0x45: "back H stats done", 0x46: "V loads stored", 0x47: "V loads barrier", 0x48: "V normalised", 0x49: "V barrier 2"}
+names = {0x01: "tile start", 0x41: "front H done", 0x42: "front H barrier", 0x10: "vec staged / GVP start", 0x43: "GVPs done", 0x44: "back V done", 0x45: "back H stats done", 0x46: "V loads stored", 0x47: "V loads barrier", 0x48: "V normalised", 0x49: "V barrier 2", 0x4a: "front H loads arrived", 0x4b: "front H stats exchanged"}
 mn = {0x10: "V issue", 0x11: "V committed", 0x20: "S start", 0x21: "S committed", 0x30: "G issue", 0x31: "G committed"}
 ev = []
 for r in range(4):
