@@ -101,7 +101,11 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
                                                         float* __restrict__ prot_x, const int* __restrict__ prot_ptr,
                                                         int n_graphs, float alpha_ts, float var_terms,
                                                         float sigma_q, const unsigned long long* __restrict__ seed_dev,
-                                                        unsigned noise_step, float ep_c1, float ep_c2, int ep_mode) {
+                                                        unsigned noise_step, float ep_c1, float ep_c2, int ep_mode,
+                                                        float* __restrict__ com_out) {
+  // com_out != nullptr (the sampling loop): the graph's centre of mass goes to com_out[3 g ..] and the protein is shifted by
+  // prot_shift_kernel afterwards -- a streaming pass with one warp per graph -- instead of by this CTA after its two
+  // barriers; same arithmetic per element either way.
   const unsigned long long seed = noise_x == nullptr ? *seed_dev : 0ull;
   // The new coordinates of a graph are kept in shared memory between the update and the centre-of-mass pass (up to
   // kPostCache / 3 pharmacophore centres; larger graphs go through global memory as before): the three sequential sums
@@ -150,13 +154,42 @@ __global__ void __launch_bounds__(128) posterior_kernel(float* __restrict__ phar
         const size_t o = (size_t)fa * 3 + i;
         pharm_x[o] = __fsub_rn(cached ? s_z[i] : pharm_x[o], s_com[i % 3]);
       }
-      const int pa = prot_ptr[g], pb = prot_ptr[g + 1];
-      for (int i = threadIdx.x; i < (pb - pa) * 3; i += blockDim.x) {
-        const size_t o = (size_t)pa * 3 + i;
-        prot_x[o] = __fsub_rn(prot_x[o], s_com[i % 3]);
+      if (com_out != nullptr) {
+        if (threadIdx.x < 3) com_out[(size_t)g * 3 + threadIdx.x] = s_com[threadIdx.x];
+      } else {
+        const int pa = prot_ptr[g], pb = prot_ptr[g + 1];
+        for (int i = threadIdx.x; i < (pb - pa) * 3; i += blockDim.x) {
+          const size_t o = (size_t)pa * 3 + i;
+          prot_x[o] = __fsub_rn(prot_x[o], s_com[i % 3]);
+        }
       }
     }
     __syncthreads();
+  }
+}
+
+// x[n] -= com[graph(n)] for the protein atoms of every graph that has pharmacophore nodes (com_removal, pharmacodiff.py:106-107):
+// one WARP per graph, four independent 128-byte rows of loads in flight per lane, grid-stride over the graphs.
+__global__ void __launch_bounds__(256) prot_shift_kernel(float* __restrict__ prot_x, const int* __restrict__ prot_ptr,
+                                                         const int* __restrict__ pharm_ptr, int n_graphs,
+                                                         const float* __restrict__ com) {
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_graphs; g += n_warps) {
+    if (pharm_ptr[g + 1] == pharm_ptr[g]) continue;   // no pharmacophore nodes: nothing was removed
+    const int pa = prot_ptr[g], n3 = (prot_ptr[g + 1] - pa) * 3;
+    float* x = prot_x + (size_t)pa * 3;
+    const float c0 = com[(size_t)g * 3], c1 = com[(size_t)g * 3 + 1], c2 = com[(size_t)g * 3 + 2];
+    for (int i0 = lane; i0 < n3; i0 += 128) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = i0 + 32 * k < n3 ? x[i0 + 32 * k] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + 32 * k, m = i % 3;
+        if (i < n3) x[i] = __fsub_rn(v[k], m == 0 ? c0 : (m == 1 ? c1 : c2));
+      }
+    }
   }
 }
 
@@ -256,16 +289,31 @@ static int posterior_launch(float* pharm_x, float* pharm_h, int32_t nh, const fl
                             const float* noise_x, const float* noise_h, const int32_t* pharm_ptr, float* prot_x,
                             const int32_t* prot_ptr, int32_t n_graphs, float alpha_ts, float var_terms, float sigma_q,
                             const uint64_t* seed_dev, uint32_t noise_step, void* stream, float ep_c1 = 0.f,
-                            float ep_c2 = 0.f, int ep_mode = 0) {
+                            float ep_c2 = 0.f, int ep_mode = 0, float* com_scratch = nullptr) {
   PF_CHECK_ARG(pharm_x && pharm_h && eps_x && eps_h && pharm_ptr && prot_x && prot_ptr, "pf_posterior_step: null pointer");
   PF_CHECK_ARG((noise_x && noise_h) || (!noise_x && !noise_h && seed_dev),
                "pf_posterior_step: pass both noise arrays, or neither and a device seed");
   if (n_graphs <= 0) return PF_OK;
+  if (com_scratch != nullptr) {
+    // two launches: a 64-thread CTA per graph for the pharmacophore update + centre of mass (at most 16 x 9 values per graph),
+    // then the protein shift as a streaming pass
+    const int grid = n_graphs < 64 * num_sms() ? n_graphs : 64 * num_sms();
+    posterior_kernel<<<grid, 64, 0, as_stream(stream)>>>(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h, pharm_ptr,
+                                                         prot_x, prot_ptr, n_graphs, alpha_ts, var_terms, sigma_q,
+                                                         reinterpret_cast<const unsigned long long*>(seed_dev), noise_step,
+                                                         ep_c1, ep_c2, ep_mode, com_scratch);
+    PF_CHECK_LAUNCH("pf_posterior_step");
+    const int warps = n_graphs, blocks = (warps + 7) / 8;
+    prot_shift_kernel<<<blocks < 16 * num_sms() ? blocks : 16 * num_sms(), 256, 0, as_stream(stream)>>>(
+        prot_x, prot_ptr, pharm_ptr, n_graphs, com_scratch);
+    PF_CHECK_LAUNCH("pf_posterior_step(prot shift)");
+    return PF_OK;
+  }
   const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
   posterior_kernel<<<grid, 128, 0, as_stream(stream)>>>(pharm_x, pharm_h, nh, eps_x, eps_h, noise_x, noise_h, pharm_ptr,
                                                         prot_x, prot_ptr, n_graphs, alpha_ts, var_terms, sigma_q,
                                                         reinterpret_cast<const unsigned long long*>(seed_dev), noise_step,
-                                                        ep_c1, ep_c2, ep_mode);
+                                                        ep_c1, ep_c2, ep_mode, nullptr);
   PF_CHECK_LAUNCH("pf_posterior_step");
   return PF_OK;
 }
@@ -556,7 +604,9 @@ extern "C" int pf_sample_loop(const PfSampleArgs* a, void* stream) {
                             philox ? nullptr : a->noise_x + i * fx, philox ? nullptr : a->noise_h + i * fh, a->pharm_ptr,
                             a->prot_x, a->prot_ptr, a->n_graphs, a->alpha_ts_host[i], a->var_terms_host[i],
                             a->sigma_q_host[i], a->noise_seed, (uint32_t)(a->noise_step0 + i), stream,
-                            a->ep_mode ? a->ep_c1_host[i] : 0.f, a->ep_mode ? a->ep_c2_host[i] : 0.f, a->ep_mode));
+                            a->ep_mode ? a->ep_c1_host[i] : 0.f, a->ep_mode ? a->ep_c2_host[i] : 0.f, a->ep_mode,
+                            // per-graph centres of mass in a buffer that is dead between two denoiser calls
+                            (a->prot_agg_v != nullptr && (int64_t)a->n_prot * 16 >= a->n_graphs) ? a->prot_agg_v : nullptr));
   prof_end(kSitePosterior, as_stream(stream));
   }
   return PF_OK;
