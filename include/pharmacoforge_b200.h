@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 3
+#define PF_ABI_VERSION 4
 
 enum PfStatus {
   PF_OK = 0,
@@ -344,6 +344,11 @@ typedef struct PfSampleArgs {
    * ep_mode == 0 (configs/dev.yml) leaves the eps form of every step */
   const float *ep_c1_host, *ep_c2_host;
   int32_t ep_mode;
+  /* numeric message_norm (gvp.py:375-389, 512-517; configs/dev.yml uses 'mean' = both zero): aggregation is the SUM over the
+   * in-edges divided by the norm of the destination node type.  The edge kernels then write each edge type's means to
+   * tmp_agg_* ([max(n_prot, n_pharm)][128] / [..][48], scratch) and pf_scaled_accumulate folds them in as count / norm * mean. */
+  float msg_norm_pharm, msg_norm_prot;
+  float *tmp_agg_h, *tmp_agg_v;
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph
@@ -381,6 +386,11 @@ int pf_share_gather(const int32_t* pharm_ptr, const int32_t* prot_ptr, const int
                     int32_t pf_k, const int32_t* fp_seg_dst, const int32_t* fp_seg_cnt, const float* prot_x,
                     const int32_t* seed_row, const float* enc_table, const float* aggd_h, const float* aggd_v, float* c_x, float* c_h,
                     float* c_agg_h, float* c_agg_v, int32_t stage, void* stream);
+
+/* agg[d] (+)= tmp[d] * seg_cnt[s] * inv_norm for every segment s (d = seg_dst ? seg_dst[s] : s): mean -> scaled sum (numeric
+ * message_norm, see PfSampleArgs.msg_norm_*).  Rows: agg_h / tmp_h [n][128], agg_v / tmp_v [n][48]. */
+int pf_scaled_accumulate(const float* tmp_h, const float* tmp_v, const int32_t* seg_cnt, const int32_t* seg_dst, int64_t n_seg,
+                         float inv_norm, float* agg_h, float* agg_v, int32_t accumulate, void* stream);
 
 /* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the
  * timestep value of graph g.  Results in a->eps_h / a->eps_x. */

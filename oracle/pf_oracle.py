@@ -229,8 +229,9 @@ def mean_aggregate(msg: torch.Tensor, dst: torch.Tensor, n_dst: int) -> torch.Te
 
 def conv_layer(sd, p: str, feats: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
                edges: Dict[str, Tuple[torch.Tensor, torch.Tensor]], n_message_gvps=3, n_update_gvps=2,
-               return_messages: bool = False):
-    """GVPMultiEdgeConv.forward, gvp.py:459-538, message_norm='mean', eval mode (dropout = identity).
+               return_messages: bool = False, message_norm="mean"):
+    """GVPMultiEdgeConv.forward, gvp.py:459-538, eval mode (dropout = identity).  message_norm='mean' (dev.yml): mean over
+    the in-edges per edge type; a positive number: SUM over the in-edges (gvp.py:386-389) divided by it (:512-517).
 
     feats[ntype] = (h [N,128], x [N,3], v [N,16,3]); edges[etype] = (src, dst).
     """
@@ -245,8 +246,12 @@ def conv_layer(sd, p: str, feats: Dict[str, Tuple[torch.Tensor, torch.Tensor, to
         ms, mv = edge_messages(sd, f"{p}.edge_message_fns.{snt}_{et}_{dnt}", hs[src], vs[src], xs[src], xd[dst],
                                n_message_gvps)
         n_dst = feats[dnt][0].shape[0]
-        a_s = mean_aggregate(ms, dst, n_dst)
-        a_v = mean_aggregate(mv, dst, n_dst)
+        if message_norm == "mean":
+            a_s = mean_aggregate(ms, dst, n_dst)
+            a_v = mean_aggregate(mv, dst, n_dst)
+        else:
+            a_s = torch.zeros((n_dst,) + tuple(ms.shape[1:]), dtype=ms.dtype).index_add_(0, dst, ms) / float(message_norm)
+            a_v = torch.zeros((n_dst,) + tuple(mv.shape[1:]), dtype=mv.dtype).index_add_(0, dst, mv) / float(message_norm)
         agg_s[dnt] = a_s if agg_s[dnt] is None else agg_s[dnt] + a_s
         agg_v[dnt] = a_v if agg_v[dnt] is None else agg_v[dnt] + a_v
     out = {}
@@ -335,7 +340,8 @@ def denoiser(sd, b: FlatBatch, t: torch.Tensor, cfg: dict, prefix: str = "dynami
         trace["enc"] = {k: v[0] for k, v in feats.items()}
     for li in range(cfg.get("n_convs", 2)):
         feats = conv_layer(sd, f"{prefix}.noise_predictor.conv_layers.{li}", feats, edges,
-                           cfg.get("n_message_gvps", 3), cfg.get("n_update_gvps", 2))
+                           cfg.get("n_message_gvps", 3), cfg.get("n_update_gvps", 2),
+                           message_norm=cfg.get("message_norm", "mean"))
         if trace is not None:
             trace[f"conv{li}"] = {k: (v[0], v[2]) for k, v in feats.items()}
     return noise_head(sd, f"{prefix}.noise_predictor.noise_predictor", feats["pharm"][0], feats["pharm"][2],

@@ -101,12 +101,13 @@ SIGNATURES = {
                              C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, STREAM]),
     "pf_train_gemm": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                 C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, STREAM]),
+    "pf_scaled_accumulate": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, C.c_int64, C.c_float, c_f32p, c_f32p, C.c_int32, STREAM]),
     "pf_denoiser": (C.c_int, [C.c_void_p, STREAM]),
     "pf_sample_loop": (C.c_int, [C.c_void_p, STREAM]),
 }
 
 MAX_CONVS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class PfSampleArgs(C.Structure):
@@ -156,6 +157,7 @@ class PfSampleArgs(C.Structure):
         ("c_x", C.c_void_p), ("c_h", C.c_void_p), ("c_v", C.c_void_p), ("c_agg_h", C.c_void_p), ("c_agg_v", C.c_void_p),
         ("c_seg_id", C.c_void_p), ("pf_col_c", C.c_void_p),
         ("ep_c1_host", C.c_void_p), ("ep_c2_host", C.c_void_p), ("ep_mode", C.c_int32),
+        ("msg_norm_pharm", C.c_float), ("msg_norm_prot", C.c_float), ("tmp_agg_h", C.c_void_p), ("tmp_agg_v", C.c_void_p),
     ]
 
 

@@ -217,6 +217,50 @@ __global__ void __launch_bounds__(128) segment_shift3_kernel(float* __restrict__
   }
 }
 
+// rows seg_dst[s] of (h, v) <- 0 for every non-empty segment s of a segment list
+__global__ void __launch_bounds__(256) zero_listed_rows_kernel(float* __restrict__ h, float* __restrict__ v,
+                                                               const int* __restrict__ seg_cnt, const int* __restrict__ seg_dst,
+                                                               long long n_seg) {
+  const int lane = threadIdx.x & 31;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_seg; s += n_warps) {
+    if (seg_cnt[s] == 0) continue;
+    const long long d = seg_dst[s];
+    *reinterpret_cast<float4*>(h + d * kHidden + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < kVRow / 4) *reinterpret_cast<float4*>(v + d * kVRow + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// Numeric message_norm (gvp.py:386-389, 512-517: SUM over the in-edges divided by a constant instead of the mean): the edge
+// kernels leave the per-destination MEAN of one edge type in tmp; agg[d] (+)= tmp[d] * count * inv_norm turns it into the scaled
+// sum.  One warp per segment s (destination d = seg_dst ? seg_dst[s] : s); empty segments contribute zero.
+__global__ void __launch_bounds__(256) scaled_accumulate_kernel(const float* __restrict__ tmp_h, const float* __restrict__ tmp_v,
+                                                                const int* __restrict__ seg_cnt, const int* __restrict__ seg_dst,
+                                                                long long n_seg, float inv_norm, float* __restrict__ agg_h,
+                                                                float* __restrict__ agg_v, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_seg; s += n_warps) {
+    const int cnt = seg_cnt[s];
+    if (seg_dst != nullptr && cnt == 0) continue;   // an unused slot of a segment list: no destination
+    const long long d = seg_dst != nullptr ? seg_dst[s] : s;
+    const float sc = (float)cnt * inv_norm;
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f), v = h;
+    if (cnt > 0) {
+      h = *reinterpret_cast<const float4*>(tmp_h + d * kHidden + 4 * lane);
+      if (lane < kVRow / 4) v = *reinterpret_cast<const float4*>(tmp_v + d * kVRow + 4 * lane);
+    }
+    float4* oh = reinterpret_cast<float4*>(agg_h + d * kHidden + 4 * lane);
+    float4 a = accumulate ? *oh : make_float4(0.f, 0.f, 0.f, 0.f);
+    *oh = make_float4(fmaf(h.x, sc, a.x), fmaf(h.y, sc, a.y), fmaf(h.z, sc, a.z), fmaf(h.w, sc, a.w));
+    if (lane < kVRow / 4) {
+      float4* ov = reinterpret_cast<float4*>(agg_v + d * kVRow + 4 * lane);
+      a = accumulate ? *ov : make_float4(0.f, 0.f, 0.f, 0.f);
+      *ov = make_float4(fmaf(v.x, sc, a.x), fmaf(v.y, sc, a.y), fmaf(v.z, sc, a.z), fmaf(v.w, sc, a.w));
+    }
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -382,6 +426,19 @@ extern "C" int pf_fill_f32(float* p, int64_t n, float v, void* stream) {
 }
 
 
+extern "C" int pf_scaled_accumulate(const float* tmp_h, const float* tmp_v, const int32_t* seg_cnt, const int32_t* seg_dst,
+                                    int64_t n_seg, float inv_norm, float* agg_h, float* agg_v, int32_t accumulate,
+                                    void* stream) {
+  PF_CHECK_ARG(tmp_h && tmp_v && seg_cnt && agg_h && agg_v, "pf_scaled_accumulate: null pointer");
+  if (n_seg <= 0) return PF_OK;
+  const long long blocks = (n_seg + 7) / 8;
+  const int grid = (int)(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
+  scaled_accumulate_kernel<<<grid, 256, 0, as_stream(stream)>>>(tmp_h, tmp_v, seg_cnt, seg_dst, n_seg, inv_norm, agg_h, agg_v,
+                                                                accumulate);
+  PF_CHECK_LAUNCH("pf_scaled_accumulate");
+  return PF_OK;
+}
+
 #define PF_TRY(call)       \
   do {                     \
     int rc_ = (call);      \
@@ -506,6 +563,16 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                        a->dyn_n_tiles + 1, a->dev_status, stream));
   PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->tile_rows, a->fp_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 2, a->dev_status, stream));
+  // numeric message_norm: every edge type's means go to tmp_agg_* and are folded into the aggregate as count / norm * mean
+  const bool summode = a->msg_norm_pharm > 0.f || a->msg_norm_prot > 0.f;
+  PF_CHECK_ARG(!summode || (a->msg_norm_pharm > 0.f && a->msg_norm_prot > 0.f && a->tmp_agg_h && a->tmp_agg_v),
+               "pf_denoiser: numeric message_norm needs both norms and the tmp_agg buffers");
+  PF_CHECK_ARG(!summode || !(a->flags & PF_FLAG_SHARE_POCKET_MESSAGES), "pf_denoiser: the shared-pocket mode is built for message_norm = 'mean'");
+  float* const fagg_h = summode ? a->tmp_agg_h : a->pharm_agg_h;   // where the pharm-side / prot-side edge kernels write
+  float* const fagg_v = summode ? a->tmp_agg_v : a->pharm_agg_v;
+  float* const pagg_h = summode ? a->tmp_agg_h : a->prot_agg_h;
+  float* const pagg_v = summode ? a->tmp_agg_v : a->prot_agg_v;
+  const int acc1 = summode ? 0 : 1;                                // second edge type of a node type: accumulate (mean mode)
   if (a->flags & PF_FLAG_SHARE_POCKET_MESSAGES) return denoiser_shared(a, stream);
   // encoders (dynamics_gvp.py:143-151); node vectors start at zero (:162-173) and are never materialised
   PF_TRY(pf_encode(a->pharm_h, a->n_pharm_feats, a->pharm_ptr, a->n_graphs, a->t_graph, a->w_pharm_enc, a->pharm_hh,
@@ -526,17 +593,23 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     prof_begin(kSiteFF, as_stream(stream));
     PF_TRY(edge_conv_any(tc, f16, a->pharm_hh, fv, a->pharm_x, a->pharm_x, a->ff_start, a->ff_cnt, nullptr, a->ff_col,
                          a->ff_tiles, a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg[l][0], a->w_msg_tc[l][0],
-                         a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 0, stream));
+                         a->n_msg_gvps, fagg_h, fagg_v, 0, stream));
+    if (summode)
+      PF_TRY(pf_scaled_accumulate(fagg_h, fagg_v, a->ff_cnt, nullptr, a->n_pharm, 1.0f / a->msg_norm_pharm, a->pharm_agg_h,
+                                  a->pharm_agg_v, 0, stream));
   prof_end(kSiteFF, as_stream(stream));
     prof_begin(kSitePF, as_stream(stream));
     if (l == 0 && table0)
       PF_TRY(pf_edge_conv_tc_mapped(a->enc_table, a->seed_row, nullptr, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr,
                                     a->pf_col, a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg_tc[l][1],
-                                    a->pharm_agg_h, a->pharm_agg_v, 1, f16 ? 1 : 0, stream));
+                                    fagg_h, fagg_v, acc1, f16 ? 1 : 0, stream));
     else
     PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col,
                          a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->w_msg_tc[l][1],
-                         a->n_msg_gvps, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
+                         a->n_msg_gvps, fagg_h, fagg_v, acc1, stream));
+    if (summode)
+      PF_TRY(pf_scaled_accumulate(fagg_h, fagg_v, a->pf_cnt, nullptr, a->n_pharm, 1.0f / a->msg_norm_pharm, a->pharm_agg_h,
+                                  a->pharm_agg_v, 1, stream));
   prof_end(kSitePF, as_stream(stream));
     // exact dead-work elimination (opt-in): nothing reads the protein side of the last layer
     const bool prot_side = !((a->flags & PF_FLAG_SKIP_DEAD_WORK) && l == a->n_convs - 1);
@@ -551,17 +624,34 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
       PF_TRY(pf_seed_table(a->prot_h, a->seed_rep, a->n_seed_rows, a->w_msg[l][3], a->seed_table, stream));
       PF_TRY(pf_edge_conv_tc_seeded(a->seed_row, a->seed_table, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr,
                                     a->pp_col, a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg_tc[l][3],
-                                    a->prot_agg_h, a->prot_agg_v, 0, f16 ? 1 : 0, stream));
+                                    pagg_h, pagg_v, 0, f16 ? 1 : 0, stream));
     } else {
     PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, a->prot_x, a->pp_start, a->pp_cnt, nullptr, a->pp_col,
                          a->pp_tiles, a->pp_n_tiles, a->pp_max_tiles, a->w_msg[l][3], a->w_msg_tc[l][3],
-                         a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 0, stream));
+                         a->n_msg_gvps, pagg_h, pagg_v, 0, stream));
     }
+    if (summode)
+      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->pp_cnt, nullptr, a->n_prot, 1.0f / a->msg_norm_prot, a->prot_agg_h,
+                                  a->prot_agg_v, 0, stream));
   prof_end(kSitePP, as_stream(stream));
     prof_begin(kSiteFP, as_stream(stream));
+    if (summode) {
+      // the fp segment list has unused slots (count 0, destination = the graph's first atom): in store mode the edge kernel
+      // would write zeros through them, so the listed rows of tmp are cleared and the kernel accumulates as always
+      const long long n_slots = (long long)a->pf_k * a->n_pharm;
+      if (n_slots > 0) {
+        const long long blocks = (n_slots + 7) / 8;
+        zero_listed_rows_kernel<<<(int)(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms()), 256, 0, as_stream(stream)>>>(
+            pagg_h, pagg_v, a->fp_seg_cnt, a->fp_seg_dst, n_slots);
+        PF_CHECK_LAUNCH("pf_denoiser(zero fp rows)");
+      }
+    }
     PF_TRY(edge_conv_any(tc, f16, a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
                          a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2],
-                         a->w_msg_tc[l][2], a->n_msg_gvps, a->prot_agg_h, a->prot_agg_v, 1, stream));
+                         a->w_msg_tc[l][2], a->n_msg_gvps, pagg_h, pagg_v, 1, stream));
+    if (summode)
+      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->fp_seg_cnt, a->fp_seg_dst, (int64_t)a->pf_k * a->n_pharm,
+                                  1.0f / a->msg_norm_prot, a->prot_agg_h, a->prot_agg_v, 1, stream));
   prof_end(kSiteFP, as_stream(stream));
     }
     // node updates, in place (gvp.py:501-536)

@@ -66,6 +66,7 @@ class GVPMultiEdgeConv(nn.Module):
                  message_norm="mean", dropout=0.0):
         super().__init__()
         self.etypes = etypes
+        self.message_norm = message_norm
         self.edge_message_fns = nn.ModuleDict()
         for et in etypes:
             gvps = []
@@ -174,6 +175,12 @@ class _DeviceState:
             self.enc_table = torch.zeros(seed_rep.numel(), 128, **f32)
             a.enc_feats, a.enc_ptr, a.enc_rep = (self.enc[k].data_ptr() for k in ("enc_feats", "enc_ptr", "enc_rep"))
             a.enc_table = self.enc_table.data_ptr()
+        if dyn.message_norm != "mean":      # numeric message_norm: scratch for one edge type's means (see the header)
+            rows = max(npn, nfn)
+            self.tmp_agg_h = torch.empty(rows, 128, **f32)
+            self.tmp_agg_v = torch.empty(rows, 48, **f32)
+            a.tmp_agg_h, a.tmp_agg_v = self.tmp_agg_h.data_ptr(), self.tmp_agg_v.data_ptr()
+            a.msg_norm_pharm = a.msg_norm_prot = float(dyn.message_norm)
         self.share = None     # buffers of the shared-pocket mode, bound on first use (bind_share)
         if g.tile_rows == 128:
             if w.tc is None:
@@ -231,8 +238,21 @@ class PharmRecDynamicsGVP(nn.Module):
         if vector_size != 16 or n_hidden_scalars != 128:
             raise NotImplementedError("the sm_100a kernels are built for vector_size=16, n_hidden_scalars=128 "
                                       "(configs/dev.yml); other widths need a rebuild with new tile constants")
-        if message_norm != "mean":
-            raise NotImplementedError("only message_norm='mean' (configs/dev.yml) is built")
+        # message_norm (gvp.py:375-389): 'mean' (configs/dev.yml) = mean over the in-edges per edge type; a positive number =
+        # SUM over the in-edges divided by it (the reference constructor's default is 1).  0 (divide by the per-graph mean
+        # degree + 1, :504-507) is not built; a dict raises upstream too (check_message_norm calls .keys() on a set, :453).
+        if isinstance(message_norm, str):
+            if message_norm != "mean":
+                raise ValueError(f"invalid message_norm {message_norm!r}")
+        elif isinstance(message_norm, (int, float)) and not isinstance(message_norm, bool):
+            if message_norm < 0:
+                raise ValueError("message_norm must be >= 0")
+            if message_norm == 0:
+                raise NotImplementedError("message_norm = 0 (per-graph mean degree + 1, gvp.py:504-507) is not built")
+        else:
+            raise NotImplementedError("message_norm must be 'mean' or a positive number (a dict fails in the reference's own "
+                                      "check_message_norm, gvp.py:453)")
+        self.message_norm = message_norm
         if pf_k <= 0:
             raise NotImplementedError("pf_k == 0 (pf / fp edges from radius(pharm, prot, r=8), dynamics_gvp.py:211) is not "
                                       "built: a pharmacophore centre then has ~120 in-edges at the default cutoff, more than "
@@ -301,6 +321,8 @@ class PharmRecDynamicsGVP(nn.Module):
             raise ValueError("edge_mlp_precision must be 'fp32' or 'fp16'")
         share = False
         if self.share_pocket_messages:
+            if self.message_norm != "mean":
+                raise NotImplementedError("share_pocket_messages is built for message_norm = 'mean'")
             if self.n_convs != 2 or self.n_message_gvps != 3 or self.n_update_gvps != 2 or g.tile_rows != 128:
                 raise NotImplementedError("share_pocket_messages is built for the dev.yml shape (n_convs=2, 3 message / 2 "
                                           "update GVPs) on the tcgen05 path")

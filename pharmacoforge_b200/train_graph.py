@@ -81,17 +81,28 @@ def build_edges(g: GraphBatch) -> Dict[str, dict]:
     out = {}
     pp_dst = torch.repeat_interleave(torch.arange(g.n_prot, device=dev), g.pp_cnt.long())
     out["pp"] = dict(src=i32(g.pp_col), dst=i32(pp_dst), ptr=i32(g.pp_rowptr), seg_dst=None, n_dst=g.n_prot,
-                     src_nt="prot", dst_nt="prot")
+                     src_nt="prot", dst_nt="prot", deg=g.pp_cnt[:g.n_prot].float())
     for name, cnt in (("ff", g.ff_cnt), ("pf", g.pf_cnt)):
         ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(cnt[:n].long(), 0)])
         s, d = dyn[name]
         out[name] = dict(src=i32(s), dst=i32(d), ptr=i32(ptr), seg_dst=None, n_dst=n,
-                         src_nt="pharm" if name == "ff" else "prot", dst_nt="pharm")
+                         src_nt="pharm" if name == "ff" else "prot", dst_nt="pharm", deg=cnt[:n].float())
     ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(g.fp_seg_cnt[:k * n].long(), 0)])
     s, d = dyn["fp"]
+    fp_deg = torch.zeros(g.n_prot, device=dev).index_add_(0, g.fp_seg_dst[:k * n].long(), g.fp_seg_cnt[:k * n].float())
     out["fp"] = dict(src=i32(s), dst=i32(d), ptr=i32(ptr), seg_dst=i32(g.fp_seg_dst[:k * n]), n_dst=g.n_prot,
-                     src_nt="pharm", dst_nt="prot")
+                     src_nt="pharm", dst_nt="prot", deg=fp_deg)
     return out
+
+
+def _norm_scale(conv, e, a_h, a_v):
+    """message_norm: 'mean' keeps the per-edge-type mean; a number turns it into SUM / norm = mean * in-degree / norm
+    (gvp.py:386-389, 512-517)."""
+    nv = getattr(conv, "message_norm", "mean")
+    if nv == "mean":
+        return a_h, a_v
+    sc = e["deg"] / float(nv)
+    return a_h * sc[:, None], a_v * sc[:, None, None]
 
 
 def conv_forward_fused(conv, feats, edges, geom, training: bool, pharm_only: bool = False):
@@ -106,7 +117,7 @@ def conv_forward_fused(conv, feats, edges, geom, training: bool, pharm_only: boo
         key = f"{e['src_nt']}_{name}_{e['dst_nt']}"
         h_src, v_src = feats[e["src_nt"]]
         xd, rbf = geom[name]
-        a_h, a_v = F.message_chain(conv.edge_message_fns[key], h_src, v_src, xd, rbf, e)
+        a_h, a_v = _norm_scale(conv, e, *F.message_chain(conv.edge_message_fns[key], h_src, v_src, xd, rbf, e))
         prev = agg.get(e["dst_nt"])
         agg[e["dst_nt"]] = (a_h, a_v) if prev is None else (prev[0] + a_h, prev[1] + a_v)   # cross_reducer="sum"
     return {nt: F.node_update(conv, nt, feats[nt][0], feats[nt][1], agg[nt][0], agg[nt][1], training)
@@ -129,6 +140,7 @@ def conv_forward(conv, feats, edges, geom, training: bool):
             sca, vec = gvp_forward(m, sca, vec)
         a_h = T.segmean(sca, e["ptr"], e["seg_dst"], e["n_dst"])                                # fn.mean, gvp.py:488-497
         a_v = T.segmean(vec, e["ptr"], e["seg_dst"], e["n_dst"])
+        a_h, a_v = _norm_scale(conv, e, a_h, a_v)
         if e["dst_nt"] in agg:                                                                  # cross_reducer="sum"
             agg[e["dst_nt"]] = (agg[e["dst_nt"]][0] + a_h, agg[e["dst_nt"]][1] + a_v)
         else:

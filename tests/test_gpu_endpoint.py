@@ -110,3 +110,49 @@ def test_forward_losses_and_gradients_against_reference(golden, sd, dyn_cfg, tag
         gr = params[n].grad
         assert gr is not None, n
         assert abs(float(gr.double().norm()) - norm) <= 2e-3 * max(norm, 1e-6), (tag, n, float(gr.norm()), norm)
+
+
+@pytest.mark.parametrize("tag", ["n4", "n1"])
+def test_numeric_message_norm_against_reference(golden, sd, dyn_cfg, tag):
+    """message_norm = a positive number (sum aggregation / norm, gvp.py:386-389, 512-517; the reference constructor's default is
+    1): the fused denoiser -- per-layer features and eps -- and the differentiable training graph against a denoiser call of
+    the reference's own code (oracle/make_golden_msgnorm.py)."""
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    d = golden("message_norm.npz")
+    nv = float(d[f"{tag}__norm"])
+    model = _model(sd, dict(dyn_cfg, message_norm=nv)).eval()
+    sizes = [int(v) for v in d["sizes"]]
+    g = GraphBatch.from_pockets([Pocket.from_numpy(*make_pocket(int(d["n_atoms"]), seed=int(d["pocket_seed"])))], [sizes], "cuda:0")
+    dyn = model.dynamics
+    st = dyn.bind(g)
+    g.prot_x.copy_(t(d["prot_x"]))
+    g.pharm_x.copy_(t(d["x_t"]))
+    g.pharm_h.copy_(t(d["h_t"]))
+    with torch.no_grad():
+        eps_h, eps_x = dyn(g, t(d["t"]), None)
+
+    errs = {}
+
+    def close(a, ref, what, rtol=1e-4):
+        ref = t(ref)
+        err = float((a.cpu() - ref).abs().max())
+        errs[what] = err / max(float(ref.abs().max()), 1e-6)
+        assert err <= rtol * max(float(ref.abs().max()), 1e-6) + 1e-6, (tag, what, err)
+    close(eps_h, d[f"{tag}__eps_h"], "eps_h")
+    close(eps_x, d[f"{tag}__eps_x"], "eps_x")
+    close(st.pharm_hh, d[f"{tag}__conv1_pharm_h"], "conv1 pharm h")
+    close(st.prot_h, d[f"{tag}__conv1_prot_h"], "conv1 prot h")
+    # vectors: ours are component-major [N, 3, 16], the reference's [N, 16, 3]
+    close(st.prot_v.view(-1, 3, 16).transpose(1, 2), d[f"{tag}__conv1_prot_v"], "conv1 prot v")
+    # differentiable graph (training mode, dropout 0): same eps
+    from pharmacoforge_b200 import train_graph
+    model.train()
+    g.prot_x.copy_(t(d["prot_x"]))
+    g.pharm_x.copy_(t(d["x_t"]))
+    g.pharm_h.copy_(t(d["h_t"]))
+    th, tx = train_graph.dynamics_forward(dyn, g, t(d["t"]), training=True)
+    close(th.detach(), d[f"{tag}__eps_h"], "train eps_h", rtol=2e-4)
+    close(tx.detach(), d[f"{tag}__eps_x"], "train eps_x", rtol=2e-4)
+    (th.sum() + tx.sum()).backward()
+    assert dyn.pharm_encoder[0].weight.grad is not None

@@ -209,3 +209,22 @@ def test_endpoint_reverse_diffusion_against_reference(golden, sd, dyn_cfg, tag, 
     if tag == "ep":
         assert float((x0 - t(g["s_ep__final_x"])).abs().max()) <= 2e-3
         assert float((h0 - t(g["s_ep__final_h"])).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("tag", ["n4", "n1"])
+def test_denoiser_numeric_message_norm_against_reference(golden, sd, dyn_cfg, tag):
+    """message_norm = a positive number: sum aggregation divided by it (gvp.py:386-389, 512-517) -- the constructor default
+    of the reference's dynamics is 1; fixture from the reference's own code (oracle/make_golden_msgnorm.py)."""
+    d = golden("message_norm.npz")
+    b = _denoiser_batch(d)
+    cfg = dict(dyn_cfg, message_norm=float(d[f"{tag}__norm"]))
+    trace = {}
+    eps_h, eps_x = O.denoiser(sd, b, t(d["t"]), cfg, trace=trace)
+    for li in range(2):
+        for nt in ("pharm", "prot"):
+            h, v = trace[f"conv{li}"][nt]
+            ref_h, ref_v = t(d[f"{tag}__conv{li}_{nt}_h"]), t(d[f"{tag}__conv{li}_{nt}_v"])
+            assert float((h - ref_h).abs().max()) <= 2e-5 * max(1.0, float(ref_h.abs().max())), (tag, li, nt)
+            assert float((v - ref_v).abs().max()) <= 2e-5 * max(1.0, float(ref_v.abs().max())), (tag, li, nt)
+    assert float((eps_h - t(d[f"{tag}__eps_h"])).abs().max()) <= 2e-5
+    assert float((eps_x - t(d[f"{tag}__eps_x"])).abs().max()) <= 2e-5
