@@ -317,12 +317,38 @@ def build_batch(pockets: List[Tuple[torch.Tensor, torch.Tensor]], sizes: List[Li
     return FlatBatch(torch.cat(px), torch.cat(ph), torch.tensor(pptr), torch.tensor(fptr), torch.cat(es), torch.cat(ed))
 
 
-def dynamic_edges(b: FlatBatch, ff_cutoff: float = 9.0, pf_k: int = 5, ff_k: int = 0):
-    """dynamics_gvp.py:187-215 (ff_k=0 -> radius, ff_k>0 -> kNN graph; pf_k>0 -> kNN, fp = reverse of pf)."""
+def radius_bipartite_edges(prot_x, prot_ptr, pharm_x, pharm_ptr, r: float, max_num_neighbors: int = 100):
+    """radius(x=pharm, y=prot, r, max_num_neighbors) per graph (dynamics_gvp.py:211): for every protein atom (query) the
+    pharmacophore nodes of its graph with squared distance < r*r, ascending index, at most max_num_neighbors.
+    Returns (prot_idx, pharm_idx) int64."""
+    qs, cs = [], []
+    r2 = torch.tensor(float(r), dtype=torch.float32) * torch.tensor(float(r), dtype=torch.float32)
+    for g in range(prot_ptr.numel() - 1):
+        a, b = int(prot_ptr[g]), int(prot_ptr[g + 1])
+        qa, qb = int(pharm_ptr[g]), int(pharm_ptr[g + 1])
+        if b == a or qb == qa:
+            continue
+        hit = _sqdist(prot_x[a:b], pharm_x[qa:qb]) < r2
+        hit = hit & (torch.cumsum(hit.to(torch.int64), dim=1) <= max_num_neighbors)
+        pi, fi = torch.nonzero(hit, as_tuple=True)
+        qs.append(pi + a)
+        cs.append(fi + qa)
+    if not qs:
+        z = torch.zeros(0, dtype=torch.int64)
+        return z, z.clone()
+    return torch.cat(qs), torch.cat(cs)
+
+
+def dynamic_edges(b: FlatBatch, ff_cutoff: float = 9.0, pf_k: int = 5, ff_k: int = 0, pf_cutoff: float = 8.0):
+    """dynamics_gvp.py:187-215 (ff_k=0 -> radius, ff_k>0 -> kNN graph; pf_k>0 -> kNN, pf_k=0 -> radius(pharm, prot, r_pf);
+    fp = reverse of pf)."""
     if ff_k > 0:
         ff_src, ff_dst = knn_graph_edges(b.pharm_x, b.pharm_ptr, ff_k)
     else:
         ff_src, ff_dst = radius_edges(b.pharm_x, b.pharm_ptr, ff_cutoff, 200)
+    if pf_k == 0:
+        c, q = radius_bipartite_edges(b.prot_x, b.prot_ptr, b.pharm_x, b.pharm_ptr, pf_cutoff, 100)
+        return {"ff": (ff_src, ff_dst), "pf": (c, q), "fp": (q, c), "pp": b.pp}
     q, c = knn_edges(b.prot_x, b.prot_ptr, b.pharm_x, b.pharm_ptr, pf_k)
     return {"ff": (ff_src, ff_dst), "pf": (c, q), "fp": (q, c), "pp": b.pp}
 
@@ -334,7 +360,8 @@ def denoiser(sd, b: FlatBatch, t: torch.Tensor, cfg: dict, prefix: str = "dynami
     h_p = encoder(sd, f"{prefix}.prot_encoder", b.prot_h, t[b.prot_b])
     feats = {"pharm": (h_f, b.pharm_x, torch.zeros(h_f.shape[0], vs, 3)),
              "prot": (h_p, b.prot_x, torch.zeros(h_p.shape[0], vs, 3))}
-    edges = dynamic_edges(b, cfg["graph_cutoffs"]["ff"], cfg.get("pf_k", 5), cfg.get("ff_k", 0))
+    edges = dynamic_edges(b, cfg["graph_cutoffs"]["ff"], cfg.get("pf_k", 5), cfg.get("ff_k", 0),
+                          cfg["graph_cutoffs"].get("pf", 8.0))
     if trace is not None:
         trace["edges"] = edges
         trace["enc"] = {k: v[0] for k, v in feats.items()}

@@ -228,3 +228,24 @@ def test_denoiser_numeric_message_norm_against_reference(golden, sd, dyn_cfg, ta
             assert float((v - ref_v).abs().max()) <= 2e-5 * max(1.0, float(ref_v.abs().max())), (tag, li, nt)
     assert float((eps_h - t(d[f"{tag}__eps_h"])).abs().max()) <= 2e-5
     assert float((eps_x - t(d[f"{tag}__eps_x"])).abs().max()) <= 2e-5
+
+
+def test_denoiser_radius_pf_edges_against_reference(golden, sd, dyn_cfg):
+    """pf_k = 0: pf / fp edges from radius(pharm, prot, r_pf, max 100 per protein atom) (dynamics_gvp.py:210-216): edge sets
+    bit-exact, features and eps against a denoiser call of the reference's own code (oracle/make_golden_pfradius.py)."""
+    d = golden("pf_radius.npz")
+    b = _denoiser_batch(d)
+    cuts = dict(dyn_cfg["graph_cutoffs"], pf=float(d["pf_cutoff"]), fp=float(d["pf_cutoff"]))
+    cfg = dict(dyn_cfg, pf_k=0, graph_cutoffs=cuts)
+    trace = {}
+    eps_h, eps_x = O.denoiser(sd, b, t(d["t"]), cfg, trace=trace)
+    for et in ("ff", "pf", "fp"):
+        s_, d_ = _canon(*trace["edges"][et])
+        assert np.array_equal(s_, d[f"e_{et}_src"]) and np.array_equal(d_, d[f"e_{et}_dst"]), et
+    assert np.bincount(d["e_pf_dst"]).max() > 128          # the fixture exercises destinations wider than one tile
+    for nt in ("pharm", "prot"):
+        h = trace["conv1"][nt][0]
+        ref = t(d[f"conv1_{nt}_h"])
+        assert float((h - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), nt
+    assert float((eps_h - t(d["eps_h"])).abs().max()) <= 2e-5
+    assert float((eps_x - t(d["eps_x"])).abs().max()) <= 2e-5
