@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 4
+#define PF_ABI_VERSION 5
 
 enum PfStatus {
   PF_OK = 0,
@@ -124,6 +124,29 @@ int pf_dyn_graph_ffk(const float* prot_x, const int32_t* prot_ptr, const float* 
                      int32_t n_graphs, float ff_r, int32_t ff_max_nbrs, int32_t ff_k, int32_t pf_k, const int32_t* ff_start,
                      int32_t* ff_cnt, int32_t* ff_col, int32_t* pf_cnt, int32_t* pf_col, int32_t* fp_seg_dst,
                      int32_t* fp_seg_start, int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status, void* stream);
+
+/* The pf_k == 0 branch of the same call site (dynamics_gvp.py:210-216, the reference constructor's default; configs/dev.yml
+ * uses pf_k = 5): pf / fp edges from radius(x = pharm x_t, y = prot x_0, r = pf_r, max_num_neighbors = pf_max_nbrs) -- every
+ * protein atom keeps the pharmacophore nodes of its graph with squared distance < r * r in ascending index, at most
+ * pf_max_nbrs; pf = (prot -> pharm), fp = the reverse.  ff as in pf_dyn_graph_ffk.  Static inputs (per batch): pf_start[i] =
+ * first slot of pharmacophore node i in pf_col (capacity = the atoms of its graph), sub_ptr[i] = first of its
+ * ceil(atoms / sub_rows) sub-segment slots, fp_base[g] = first fp_col slot of graph g (min(nf, pf_max_nbrs) per atom).
+ * Written: pf_cnt[i] (in-degree), pf_col (atom ids, ascending), sub_start / sub_cnt (the node's pf segment cut into pieces of
+ * at most sub_rows edges: what the edge kernels run on, one mean per piece -> pf_combine_subsegments), sub_x[s][3] (the
+ * coordinates of the piece's destination node: the edge kernels' dst_x, indexed by piece like their output), and one fp segment per
+ * protein atom: fp_seg_start / fp_seg_cnt [n_prot], fp_col (pharm ids, ascending). */
+int pf_dyn_graph_radius(const float* prot_x, const int32_t* prot_ptr, const float* pharm_x, const int32_t* pharm_ptr,
+                        int32_t n_graphs, float ff_r, int32_t ff_max_nbrs, int32_t ff_k, float pf_r, int32_t pf_max_nbrs,
+                        int32_t sub_rows, const int32_t* ff_start, int32_t* ff_cnt, int32_t* ff_col, const int32_t* pf_start,
+                        const int32_t* sub_ptr, const int32_t* fp_base, int32_t* pf_cnt, int32_t* pf_col, int32_t* sub_start,
+                        int32_t* sub_cnt, float* sub_x, int32_t* fp_seg_start, int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status,
+                        void* stream);
+
+/* agg[d] (+)= sum over s in [sub_ptr[d], sub_ptr[d+1]) of sub[s] * sub_cnt[s] * w with w = 1 / tot_cnt[d] (inv_norm == 0: the
+ * mean over all in-edges of d, fn.mean of gvp.py:488-497) or w = inv_norm (numeric message_norm).  Rows as pf_scaled_accumulate. */
+int pf_combine_subsegments(const float* sub_h, const float* sub_v, const int32_t* sub_cnt, const int32_t* sub_ptr,
+                           const int32_t* tot_cnt, int64_t n_dst, float inv_norm, float* agg_h, float* agg_v,
+                           int32_t accumulate, void* stream);
 
 /* ---- tile planner --------------------------------------------------------------------------------
  * Greedily packs consecutive segments of each chunk [chunk_ptr[c], chunk_ptr[c+1]) into tiles of at
@@ -349,6 +372,18 @@ typedef struct PfSampleArgs {
    * tmp_agg_* ([max(n_prot, n_pharm)][128] / [..][48], scratch) and pf_scaled_accumulate folds them in as count / norm * mean. */
   float msg_norm_pharm, msg_norm_prot;
   float *tmp_agg_h, *tmp_agg_v;
+  /* pf_k == 0: pf / fp edges from the radius graph (pf_dyn_graph_radius).  pf_start / pf_cnt / pf_col then describe whole pf
+   * segments (capacity = atoms of the graph per pharmacophore node), fp_seg_start / fp_seg_cnt are [n_prot] with identity
+   * destinations (fp_seg_dst unused), fp_chunk_ptr / n_fp_chunks chunk the protein atoms, and the pf edge kernels run on the
+   * sub-segment list below, one mean per sub-segment into sub_agg_*, folded in by pf_combine_subsegments. */
+  float pf_r;
+  int32_t pf_max_nbrs;
+  const int32_t *pf_sub_ptr, *fp_base;       /* [n_pharm + 1], [n_graphs] static */
+  int32_t *pf_sub_start, *pf_sub_cnt;        /* [n_pf_sub] */
+  const int32_t* pf_sub_chunk_ptr;           /* planner chunks over the sub-segment slots */
+  int32_t n_pf_sub_chunks, n_pf_sub;
+  float *sub_agg_h, *sub_agg_v;              /* [n_pf_sub][128], [n_pf_sub][48] scratch */
+  float* pf_sub_x;                           /* [n_pf_sub][3] destination coordinates per sub-segment */
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph

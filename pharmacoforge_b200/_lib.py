@@ -34,6 +34,11 @@ SIGNATURES = {
                                c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
     "pf_dyn_graph_ffk": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32,
                                    c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
+    "pf_dyn_graph_radius": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_float,
+                                      C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
+                                      c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
+    "pf_combine_subsegments": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, C.c_int64, C.c_float, c_f32p, c_f32p,
+                                         C.c_int32, STREAM]),
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
     "pf_share_index": (C.c_int, [c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, STREAM]),
@@ -107,7 +112,7 @@ SIGNATURES = {
 }
 
 MAX_CONVS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class PfSampleArgs(C.Structure):
@@ -158,6 +163,10 @@ class PfSampleArgs(C.Structure):
         ("c_seg_id", C.c_void_p), ("pf_col_c", C.c_void_p),
         ("ep_c1_host", C.c_void_p), ("ep_c2_host", C.c_void_p), ("ep_mode", C.c_int32),
         ("msg_norm_pharm", C.c_float), ("msg_norm_prot", C.c_float), ("tmp_agg_h", C.c_void_p), ("tmp_agg_v", C.c_void_p),
+        ("pf_r", C.c_float), ("pf_max_nbrs", C.c_int32), ("pf_sub_ptr", C.c_void_p), ("fp_base", C.c_void_p),
+        ("pf_sub_start", C.c_void_p), ("pf_sub_cnt", C.c_void_p), ("pf_sub_chunk_ptr", C.c_void_p),
+        ("n_pf_sub_chunks", C.c_int32), ("n_pf_sub", C.c_int32), ("sub_agg_h", C.c_void_p), ("sub_agg_v", C.c_void_p),
+        ("pf_sub_x", C.c_void_p),
     ]
 
 

@@ -83,7 +83,7 @@ class GraphBatch:
     @classmethod
     def from_pockets(cls, pockets: Sequence[Pocket], sizes: Sequence[Sequence[int]], device, pp_cutoff: float = 3.5,
                      pf_k: int = 5, ff_max_nbrs: int = 200, pp_max_nbrs: int = 100,
-                     graph_range: Optional[range] = None, tile_rows: int = 128) -> "GraphBatch":
+                     graph_range: Optional[range] = None, tile_rows: int = 128, pf_max_nbrs: int = 100) -> "GraphBatch":
         """One graph per (pocket, requested pharmacophore size), pocket-major, exactly the order
         `PharmacophoreDiff.sample` flattens them in (pharmacodiff.py:538-544).  `graph_range` restricts the batch
         to a slice of that flattened list (max_batch_size chunking / multi-GPU sharding)."""
@@ -94,13 +94,16 @@ class GraphBatch:
             dev = torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(dev):   # the kernels launch on the current device
             return cls._from_pockets(pockets, sizes, dev, pp_cutoff, pf_k, ff_max_nbrs, pp_max_nbrs, graph_range,
-                                     tile_rows)
+                                     tile_rows, pf_max_nbrs)
 
     @classmethod
-    def _from_pockets(cls, pockets, sizes, dev, pp_cutoff, pf_k, ff_max_nbrs, pp_max_nbrs, graph_range, tile_rows):
+    def _from_pockets(cls, pockets, sizes, dev, pp_cutoff, pf_k, ff_max_nbrs, pp_max_nbrs, graph_range, tile_rows,
+                      pf_max_nbrs=100):
         self = cls()
         self.device = dev
-        self.pf_k, self.ff_max_nbrs = int(pf_k), int(ff_max_nbrs)
+        self.pf_k, self.ff_max_nbrs, self.pf_max_nbrs = int(pf_k), int(ff_max_nbrs), int(pf_max_nbrs)
+        if self.pf_k < 0 or self.pf_max_nbrs < 1:
+            raise ValueError("pf_k >= 0 and pf_max_nbrs >= 1")
         tile_rows = int(os.environ.get("PF_TILE_ROWS", tile_rows))   # A/B switch: 64 = fp32 FFMA kernels
         if tile_rows not in (64, 128):
             raise ValueError("tile_rows: 128 (tcgen05 kernels) or 64 (fp32 FFMA kernels)")
@@ -196,12 +199,52 @@ class GraphBatch:
         self.fp_seg_start = torch.zeros(max(k * n, 1), **i32)
         self.fp_seg_cnt = torch.zeros(max(k * n, 1), **i32)
         self.fp_col = torch.zeros(max(k * n, 1), **i32)
+        self.n_fp_chunks = self.n_chunks
         self.dyn_max_tiles = k * n + self.n_chunks + 1
+        if k == 0:
+            self._radius_buffers(graph_nf, graph_np, local)
         self.ff_tiles = torch.zeros(2 * self.dyn_max_tiles, **i32)
         self.pf_tiles = torch.zeros(2 * self.dyn_max_tiles, **i32)
         self.fp_tiles = torch.zeros(2 * self.dyn_max_tiles, **i32)
         self.dyn_n_tiles = torch.zeros(3, **i32)
         return self
+
+    def _radius_buffers(self, nf, np_g, local):
+        """pf_k == 0 (dynamics_gvp.py:210-216): pf / fp edges from radius(pharm, prot, r_pf, pf_max_nbrs per protein atom),
+        refilled every step by pf_dyn_graph_radius.  A pharmacophore node can collect every atom of its pocket, more than an
+        edge tile holds, so its pf segment has capacity n_prot(graph) and is cut into ceil(n_prot(graph) / tile_rows)
+        sub-segment slots (the edge kernels write one mean per slot, pf_combine_subsegments folds them); fp has one
+        segment per protein atom with capacity min(nf, pf_max_nbrs).  Replaces the kNN-mode pf / fp buffers."""
+        dev, n, B, rows = self.device, self.n_pharm, self.n_graphs, self.tile_rows
+        i32 = dict(dtype=torch.int32, device=dev)
+        n_sub_g = -(-np_g // rows)
+        pf_base = np.concatenate([[0], np.cumsum(nf * np_g)])
+        sub_base = np.concatenate([[0], np.cumsum(nf * n_sub_g)])
+        fp_cap = np.minimum(nf, self.pf_max_nbrs)
+        fp_base = np.concatenate([[0], np.cumsum(np_g * fp_cap)])
+        if max(int(pf_base[-1]), int(fp_base[-1])) >= 2 ** 31:
+            raise ValueError("pf_k == 0: the radius pf / fp edge buffers of this batch exceed int32 indexing; use smaller batches")
+        pf_start = np.repeat(pf_base[:-1], nf) + local * np.repeat(np_g, nf)
+        sub_ptr = np.concatenate([np.repeat(sub_base[:-1], nf) + local * np.repeat(n_sub_g, nf), sub_base[-1:]])
+        small = torch.from_numpy(np.concatenate([pf_start, sub_ptr, fp_base[:-1], sub_base]).astype(np.int32)).to(dev)
+        self.pf_start = small[:n].contiguous()
+        self.pf_sub_ptr = small[n:2 * n + 1].contiguous()
+        self.fp_base = small[2 * n + 1:2 * n + 1 + B].contiguous()
+        self.pf_sub_chunk_ptr = small[2 * n + 1 + B:].contiguous()       # planner chunks: the sub-segment slots of one graph
+        self.n_pf_sub = int(sub_base[-1])
+        self.pf_col = torch.zeros(max(int(pf_base[-1]), 1), **i32)
+        self.pf_sub_start = torch.zeros(max(self.n_pf_sub, 1), **i32)
+        self.pf_sub_cnt = torch.zeros(max(self.n_pf_sub, 1), **i32)
+        self.pf_sub_x = torch.zeros(max(self.n_pf_sub, 1), 3, dtype=torch.float32, device=dev)
+        self.fp_seg_start = torch.zeros(max(self.n_prot, 1), **i32)
+        self.fp_seg_cnt = torch.zeros(max(self.n_prot, 1), **i32)
+        self.fp_col = torch.zeros(max(int(fp_base[-1]), 1), **i32)
+        self.fp_chunk_ptr = self.prot_ptr                                 # fp planner chunks: the atoms of one graph
+        self.n_fp_chunks = B
+        # tiles: ff <= one per node; pf <= one per sub-segment slot; fp: two consecutive tiles of a chunk hold more than
+        # tile_rows edges or tile_rows segments between them
+        fp_tiles = int(np.minimum(np_g, 2 * (-(-(np_g * fp_cap) // rows)) + -(-np_g // rows) + 2).sum())
+        self.dyn_max_tiles = max(n + self.n_chunks + 1, self.n_pf_sub + 1, fp_tiles + 1)
 
     def set_pharmacophores(self, x_0: torch.Tensor, h_0: torch.Tensor) -> "GraphBatch":
         """Ground-truth pharmacophores of a training / validation batch: `g.nodes['pharm'].data['x_0' / 'h_0']` of the
@@ -334,6 +377,13 @@ class GraphBatch:
         cnt = self.pf_cnt[:n].long()
         dst = torch.repeat_interleave(ar, cnt)
         within = torch.arange(dst.numel(), device=self.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+        if k == 0:    # radius mode: whole pf segments at pf_start, one fp segment per protein atom
+            out["pf"] = (self.pf_col[self.pf_start.long()[dst] + within].long(), dst)
+            scnt = self.fp_seg_cnt[:self.n_prot].long()
+            seg = torch.repeat_interleave(torch.arange(self.n_prot, device=self.device), scnt)
+            within = torch.arange(seg.numel(), device=self.device) - torch.repeat_interleave(torch.cumsum(scnt, 0) - scnt, scnt)
+            out["fp"] = (self.fp_col[self.fp_seg_start.long()[seg] + within].long(), seg)
+            return out
         out["pf"] = (self.pf_col[k * dst + within].long(), dst)
         scnt = self.fp_seg_cnt[:k * n].long()
         seg = torch.repeat_interleave(torch.arange(k * n, device=self.device), scnt)

@@ -542,11 +542,31 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_CHECK_ARG(a != nullptr, "pf_denoiser: null args");
   PF_CHECK_ARG(a->n_convs >= 1 && a->n_convs <= 8, "pf_denoiser: n_convs out of range (1..8)");
   // graph of this step: ff radius + pf kNN + fp reverse (dynamics_gvp.py:176-177)
+  // pf_k == 0: pf / fp edges from radius(pharm, prot, r_pf) (dynamics_gvp.py:210-216).  A pharmacophore node then has more
+  // in-edges than a tile holds: the pf edge kernels run on sub-segments of at most tile_rows edges and write one mean per
+  // sub-segment to sub_agg_*, pf_combine_subsegments folds them into the node's aggregate; fp has one segment per protein atom.
+  const bool radius = a->pf_k == 0;
+  PF_CHECK_ARG(!radius || (a->pf_sub_ptr && a->fp_base && a->pf_sub_start && a->pf_sub_cnt && a->pf_sub_chunk_ptr &&
+                           a->sub_agg_h && a->sub_agg_v && a->pf_sub_x && a->pf_r > 0.f && a->pf_max_nbrs >= 1),
+               "pf_denoiser: pf_k == 0 needs the radius-graph buffers (pf_sub_*, fp_base, sub_agg_*, pf_r, pf_max_nbrs)");
+  PF_CHECK_ARG(!radius || !(a->flags & PF_FLAG_SHARE_POCKET_MESSAGES), "pf_denoiser: the shared-pocket mode is built for pf_k >= 1");
   prof_begin(kSiteGraph, as_stream(stream));
+  if (radius)
+    PF_TRY(pf_dyn_graph_radius(a->prot_x, a->prot_ptr, a->pharm_x, a->pharm_ptr, a->n_graphs, a->ff_r, a->ff_max_nbrs, a->ff_k,
+                               a->pf_r, a->pf_max_nbrs, a->tile_rows, a->ff_start, a->ff_cnt, a->ff_col, a->pf_start,
+                               a->pf_sub_ptr, a->fp_base, a->pf_cnt, a->pf_col, a->pf_sub_start, a->pf_sub_cnt, a->pf_sub_x,
+                               a->fp_seg_start,
+                               a->fp_seg_cnt, a->fp_col, a->dev_status, stream));
+  else
   PF_TRY(pf_dyn_graph_ffk(a->prot_x, a->prot_ptr, a->pharm_x, a->pharm_ptr, a->n_graphs, a->ff_r, a->ff_max_nbrs, a->ff_k, a->pf_k,
                       a->ff_start, a->ff_cnt, a->ff_col, a->pf_cnt, a->pf_col, a->fp_seg_dst, a->fp_seg_start,
                       a->fp_seg_cnt, a->fp_col, a->dev_status, stream));
   prof_end(kSiteGraph, as_stream(stream));
+  const int32_t* const pf_seg_start = radius ? a->pf_sub_start : a->pf_start;   // what the pf edge kernels run on
+  const int32_t* const pf_seg_cnt = radius ? a->pf_sub_cnt : a->pf_cnt;
+  const float* const pf_dst_x = radius ? a->pf_sub_x : a->pharm_x;              // destination coordinates, indexed like the output rows
+  const int32_t* const fp_dst = radius ? nullptr : a->fp_seg_dst;               // radius: one fp segment per protein atom
+  const int64_t n_fp_seg = radius ? (int64_t)a->n_prot : (int64_t)a->pf_k * a->n_pharm;
   PF_TRY(pf_zero_i32(a->dyn_n_tiles, 3, stream));
   PF_CHECK_ARG(a->tile_rows == PF_TILE_ROWS || a->tile_rows == PF_TC_TILE_ROWS, "pf_denoiser: tile_rows must be 64 or 128");
   const bool tc = a->tile_rows == PF_TC_TILE_ROWS;
@@ -559,7 +579,8 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   }
   PF_TRY(pf_plan_tiles(a->ff_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 0, a->tile_rows, a->ff_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 0, a->dev_status, stream));
-  PF_TRY(pf_plan_tiles(a->pf_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 1, a->tile_rows, a->pf_tiles, a->dyn_max_tiles,
+  PF_TRY(pf_plan_tiles(pf_seg_cnt, radius ? a->pf_sub_chunk_ptr : a->pharm_chunk_ptr,
+                       radius ? a->n_pf_sub_chunks : a->n_pharm_chunks, 1, a->tile_rows, a->pf_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 1, a->dev_status, stream));
   PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->tile_rows, a->fp_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 2, a->dev_status, stream));
@@ -573,6 +594,9 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   float* const pagg_h = summode ? a->tmp_agg_h : a->prot_agg_h;
   float* const pagg_v = summode ? a->tmp_agg_v : a->prot_agg_v;
   const int acc1 = summode ? 0 : 1;                                // second edge type of a node type: accumulate (mean mode)
+  float* const pf_out_h = radius ? a->sub_agg_h : fagg_h;          // where the pf edge kernels write, and how
+  float* const pf_out_v = radius ? a->sub_agg_v : fagg_v;
+  const int pf_acc = radius ? 0 : acc1;
   if (a->flags & PF_FLAG_SHARE_POCKET_MESSAGES) return denoiser_shared(a, stream);
   // encoders (dynamics_gvp.py:143-151); node vectors start at zero (:162-173) and are never materialised
   PF_TRY(pf_encode(a->pharm_h, a->n_pharm_feats, a->pharm_ptr, a->n_graphs, a->t_graph, a->w_pharm_enc, a->pharm_hh,
@@ -600,14 +624,17 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   prof_end(kSiteFF, as_stream(stream));
     prof_begin(kSitePF, as_stream(stream));
     if (l == 0 && table0)
-      PF_TRY(pf_edge_conv_tc_mapped(a->enc_table, a->seed_row, nullptr, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr,
+      PF_TRY(pf_edge_conv_tc_mapped(a->enc_table, a->seed_row, nullptr, a->prot_x, pf_dst_x, pf_seg_start, pf_seg_cnt, nullptr,
                                     a->pf_col, a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg_tc[l][1],
-                                    fagg_h, fagg_v, acc1, f16 ? 1 : 0, stream));
+                                    pf_out_h, pf_out_v, pf_acc, f16 ? 1 : 0, stream));
     else
-    PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, a->pharm_x, a->pf_start, a->pf_cnt, nullptr, a->pf_col,
+    PF_TRY(edge_conv_any(tc, f16, a->prot_h, pv, a->prot_x, pf_dst_x, pf_seg_start, pf_seg_cnt, nullptr, a->pf_col,
                          a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->w_msg_tc[l][1],
-                         a->n_msg_gvps, fagg_h, fagg_v, acc1, stream));
-    if (summode)
+                         a->n_msg_gvps, pf_out_h, pf_out_v, pf_acc, stream));
+    if (radius)   // mean over ALL in-edges of the node (or SUM / norm) from the sub-segment means, added to the ff aggregate
+      PF_TRY(pf_combine_subsegments(a->sub_agg_h, a->sub_agg_v, a->pf_sub_cnt, a->pf_sub_ptr, a->pf_cnt, a->n_pharm,
+                                    summode ? 1.0f / a->msg_norm_pharm : 0.f, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
+    else if (summode)
       PF_TRY(pf_scaled_accumulate(fagg_h, fagg_v, a->pf_cnt, nullptr, a->n_pharm, 1.0f / a->msg_norm_pharm, a->pharm_agg_h,
                                   a->pharm_agg_v, 1, stream));
   prof_end(kSitePF, as_stream(stream));
@@ -639,18 +666,24 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
       // the fp segment list has unused slots (count 0, destination = the graph's first atom): in store mode the edge kernel
       // would write zeros through them, so the listed rows of tmp are cleared and the kernel accumulates as always
       const long long n_slots = (long long)a->pf_k * a->n_pharm;
-      if (n_slots > 0) {
+      if (radius) {   // identity destinations: every row of tmp is a destination
+        if (cudaMemsetAsync(pagg_h, 0, (size_t)a->n_prot * kHidden * sizeof(float), as_stream(stream)) != cudaSuccess ||
+            cudaMemsetAsync(pagg_v, 0, (size_t)a->n_prot * kVRow * sizeof(float), as_stream(stream)) != cudaSuccess) {
+          set_error("pf_denoiser: cudaMemsetAsync failed");
+          return PF_ERR_LAUNCH;
+        }
+      } else if (n_slots > 0) {
         const long long blocks = (n_slots + 7) / 8;
         zero_listed_rows_kernel<<<(int)(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms()), 256, 0, as_stream(stream)>>>(
             pagg_h, pagg_v, a->fp_seg_cnt, a->fp_seg_dst, n_slots);
         PF_CHECK_LAUNCH("pf_denoiser(zero fp rows)");
       }
     }
-    PF_TRY(edge_conv_any(tc, f16, a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, a->fp_seg_dst,
+    PF_TRY(edge_conv_any(tc, f16, a->pharm_hh, fv, a->pharm_x, a->prot_x, a->fp_seg_start, a->fp_seg_cnt, fp_dst,
                          a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2],
                          a->w_msg_tc[l][2], a->n_msg_gvps, pagg_h, pagg_v, 1, stream));
     if (summode)
-      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->fp_seg_cnt, a->fp_seg_dst, (int64_t)a->pf_k * a->n_pharm,
+      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->fp_seg_cnt, fp_dst, n_fp_seg,
                                   1.0f / a->msg_norm_prot, a->prot_agg_h, a->prot_agg_v, 1, stream));
   prof_end(kSiteFP, as_stream(stream));
     }

@@ -393,6 +393,67 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return ((unsigned long long)hi << 32) | lo;
 }
 
+// ff edges of pharmacophore node i of a graph (one warp): radius_graph(pharm x_t, r, max) or, with ff_k > 0, the kNN graph
+// (dynamics_gvp.py:193-196).  fx / fy / fz hold the graph's nf pharmacophore coordinates; writes ff_col / ff_cnt.
+__device__ __forceinline__ void ff_edges_of_node(const DynGraphParams& p, const float* fx, const float* fy, const float* fz,
+                                                 const int nf, const int fa, const int i, const int lane) {
+  const float qx = fx[i], qy = fy[i], qz = fz[i];
+  int rank_run = 0, kept_run = 0;
+  const int out0 = p.ff_start[fa + i];
+  if (p.ff_k > 0) {
+    // ---- ff: knn_graph(pharm x_t, k = ff_k) (dynamics_gvp.py:194) = the ff_k + 1 nearest nodes INCLUDING the centre,
+    // ordered by (distance, index), then the self pair is dropped.  nf <= 128: four candidates per lane; the key
+    // (distance bits, index) is unique, so each round of the warp-wide minimum selects exactly one candidate.
+    unsigned long long key[kMaxF / 32];
+    unsigned sel = 0;
+#pragma unroll
+    for (int t = 0; t < kMaxF / 32; ++t) {
+      const int j = lane + 32 * t;
+      key[t] = j < nf ? (((unsigned long long)__float_as_uint(sqdist3(qx, qy, qz, fx[j], fy[j], fz[j])) << 32) | (unsigned)j)
+                      : ~0ull;
+    }
+    const int take = p.ff_k + 1 < nf ? p.ff_k + 1 : nf;
+    for (int r = 0; r < take; ++r) {
+      unsigned long long mine = ~0ull;
+#pragma unroll
+      for (int t = 0; t < kMaxF / 32; ++t)
+        if (!(sel & (1u << t)) && key[t] < mine) mine = key[t];
+      unsigned long long best = mine;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = shfl_xor_u64(best, o);
+        best = other < best ? other : best;
+      }
+      if (mine == best && best != ~0ull) {
+#pragma unroll
+        for (int t = 0; t < kMaxF / 32; ++t)
+          if (key[t] == best) sel |= 1u << t;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kMaxF / 32; ++t) {   // neighbours in ascending index
+      const int j = lane + 32 * t;
+      const bool keep = (sel & (1u << t)) && j != i;
+      const unsigned kb = __ballot_sync(0xffffffffu, keep);
+      if (keep) p.ff_col[out0 + kept_run + __popc(kb & ((1u << lane) - 1u))] = fa + j;
+      kept_run += __popc(kb);
+    }
+  } else
+  // ---- ff: radius_graph(pharm x_t, r, max) (dynamics_gvp.py:196); centre i, neighbours ascending
+  for (int j0 = 0; j0 < nf; j0 += 32) {
+    const int j = j0 + lane;
+    const bool hit = j < nf && sqdist3(qx, qy, qz, fx[j < nf ? j : 0], fy[j < nf ? j : 0], fz[j < nf ? j : 0]) < p.ff_r2;
+    const unsigned hb = __ballot_sync(0xffffffffu, hit);
+    const int rank = rank_run + __popc(hb & ((1u << lane) - 1u)) + 1;
+    const bool keep = hit && rank <= p.ff_max + 1 && j != i;
+    const unsigned kb = __ballot_sync(0xffffffffu, keep);
+    if (keep) p.ff_col[out0 + kept_run + __popc(kb & ((1u << lane) - 1u))] = fa + j;
+    rank_run += __popc(hb);
+    kept_run += __popc(kb);
+  }
+  if (lane == 0) p.ff_cnt[fa + i] = kept_run;
+}
+
 template <int K>
 __global__ void __launch_bounds__(kDynThreads) dyn_graph_kernel(const DynGraphParams p) {
   __shared__ float fx[kMaxF], fy[kMaxF], fz[kMaxF];
@@ -478,60 +539,7 @@ __global__ void __launch_bounds__(kDynThreads) dyn_graph_kernel(const DynGraphPa
       }
       if (lane == 0) p.pf_cnt[fa + i] = kk;
 
-      int rank_run = 0, kept_run = 0;
-      const int out0 = p.ff_start[fa + i];
-      if (p.ff_k > 0) {
-        // ---- ff: knn_graph(pharm x_t, k = ff_k) (dynamics_gvp.py:194) = the ff_k + 1 nearest nodes INCLUDING the centre,
-        // ordered by (distance, index), then the self pair is dropped.  nf <= 128: four candidates per lane; the key
-        // (distance bits, index) is unique, so each round of the warp-wide minimum selects exactly one candidate.
-        unsigned long long key[kMaxF / 32];
-        unsigned sel = 0;
-#pragma unroll
-        for (int t = 0; t < kMaxF / 32; ++t) {
-          const int j = lane + 32 * t;
-          key[t] = j < nf ? (((unsigned long long)__float_as_uint(sqdist3(qx, qy, qz, fx[j], fy[j], fz[j])) << 32) | (unsigned)j)
-                          : ~0ull;
-        }
-        const int take = p.ff_k + 1 < nf ? p.ff_k + 1 : nf;
-        for (int r = 0; r < take; ++r) {
-          unsigned long long mine = ~0ull;
-#pragma unroll
-          for (int t = 0; t < kMaxF / 32; ++t)
-            if (!(sel & (1u << t)) && key[t] < mine) mine = key[t];
-          unsigned long long best = mine;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = shfl_xor_u64(best, o);
-            best = other < best ? other : best;
-          }
-          if (mine == best && best != ~0ull) {
-#pragma unroll
-            for (int t = 0; t < kMaxF / 32; ++t)
-              if (key[t] == best) sel |= 1u << t;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < kMaxF / 32; ++t) {   // neighbours in ascending index
-          const int j = lane + 32 * t;
-          const bool keep = (sel & (1u << t)) && j != i;
-          const unsigned kb = __ballot_sync(0xffffffffu, keep);
-          if (keep) p.ff_col[out0 + kept_run + __popc(kb & ((1u << lane) - 1u))] = fa + j;
-          kept_run += __popc(kb);
-        }
-      } else
-      // ---- ff: radius_graph(pharm x_t, r, max) (dynamics_gvp.py:196); centre i, neighbours ascending
-      for (int j0 = 0; j0 < nf; j0 += 32) {
-        const int j = j0 + lane;
-        const bool hit = j < nf && sqdist3(qx, qy, qz, fx[j < nf ? j : 0], fy[j < nf ? j : 0], fz[j < nf ? j : 0]) < p.ff_r2;
-        const unsigned hb = __ballot_sync(0xffffffffu, hit);
-        const int rank = rank_run + __popc(hb & ((1u << lane) - 1u)) + 1;
-        const bool keep = hit && rank <= p.ff_max + 1 && j != i;
-        const unsigned kb = __ballot_sync(0xffffffffu, keep);
-        if (keep) p.ff_col[out0 + kept_run + __popc(kb & ((1u << lane) - 1u))] = fa + j;
-        rank_run += __popc(hb);
-        kept_run += __popc(kb);
-      }
-      if (lane == 0) p.ff_cnt[fa + i] = kept_run;
+      ff_edges_of_node(p, fx, fy, fz, nf, fa, i, lane);
     }
     __syncthreads();
 
@@ -581,6 +589,127 @@ __global__ void __launch_bounds__(kDynThreads) dyn_graph_kernel(const DynGraphPa
     }
   }
 }
+
+// K2 variant for pf_k == 0 (dynamics_gvp.py:210-216): pf / fp edges from radius(x = pharm, y = prot, r, max_num_neighbors) --
+// every protein atom (the query) keeps the pharmacophore nodes of its graph with squared distance < r * r, ascending index, at
+// most max_nbrs of them; pf = (prot -> pharm), fp = the reverse.  A pharmacophore node then has up to n_prot(graph) in-edges,
+// more than one edge tile holds, so its pf segment is cut into sub-segments of PF_TC_TILE_ROWS rows: the edge kernels write
+// one mean per sub-segment and pf_combine_subsegments folds them into the node's aggregate.  fp segments are one per protein
+// atom (identity destination).  One CTA per graph.  Capacities are static per batch: pharmacophore node i of a graph with np
+// atoms owns pf_col [pf_start[i], + np) and the sub-segment slots [sub_ptr[i], sub_ptr[i + 1]) = ceil(np / rows) of them;
+// protein atom c of graph g owns fp_col [fp_base[g] + c * min(nf, max_nbrs), ...).
+struct DynRadiusParams {
+  DynGraphParams d;       // ff part and the coordinate / ptr arrays; the kNN outputs of d are unused
+  float pf_r2;
+  int pf_max, sub_rows;
+  const int *pf_start, *sub_ptr;  // [n_pharm], [n_pharm + 1] static
+  const int* fp_base;             // [n_graphs] static
+  int *sub_start, *sub_cnt;
+  float* sub_x;  // [n_sub][3] coordinates of the sub-segment's destination node: the dst_x array of the pf edge kernels
+};
+
+__global__ void __launch_bounds__(kDynThreads) dyn_graph_radius_kernel(const DynRadiusParams q) {
+  __shared__ float fx[kMaxF], fy[kMaxF], fz[kMaxF];
+  const DynGraphParams& p = q.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int g = blockIdx.x; g < p.n_graphs; g += gridDim.x) {
+    const int pa = p.prot_ptr[g], pb = p.prot_ptr[g + 1];
+    const int fa = p.pharm_ptr[g], fb = p.pharm_ptr[g + 1];
+    const int nf = fb - fa, np_ = pb - pa;
+    if (nf > kMaxF) {
+      if (threadIdx.x == 0) atomicOr(p.status, PF_DEV_GRAPH_TOO_LARGE);
+      continue;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf; i += kDynThreads) {
+      fx[i] = p.pharm_x[3 * (size_t)(fa + i)];
+      fy[i] = p.pharm_x[3 * (size_t)(fa + i) + 1];
+      fz[i] = p.pharm_x[3 * (size_t)(fa + i) + 2];
+    }
+    __syncthreads();
+    const int n_sub = (np_ + q.sub_rows - 1) / q.sub_rows;
+    for (int i = warp; i < nf; i += kDynWarps) {
+      ff_edges_of_node(p, fx, fy, fz, nf, fa, i, lane);
+      // ---- pf: in-edges of pharmacophore node i = the protein atoms that keep it, ascending atom index
+      const float qx = fx[i], qy = fy[i], qz = fz[i];
+      const int out0 = q.pf_start[fa + i];
+      int run = 0;
+      for (int c0 = 0; c0 < np_; c0 += 32) {
+        const int c = c0 + lane;
+        bool hit = false;
+        if (c < np_) {
+          const float px = p.prot_x[3 * (size_t)(pa + c)], py = p.prot_x[3 * (size_t)(pa + c) + 1],
+                      pz = p.prot_x[3 * (size_t)(pa + c) + 2];
+          hit = sqdist3(px, py, pz, qx, qy, qz) < q.pf_r2;
+          if (hit && i >= q.pf_max) {   // the atom's cap: node i is kept iff fewer than max_nbrs lower-index nodes hit
+            int rank = 0;
+            for (int j = 0; j < i; ++j) rank += sqdist3(px, py, pz, fx[j], fy[j], fz[j]) < q.pf_r2;
+            hit = rank < q.pf_max;
+          }
+        }
+        const unsigned hb = __ballot_sync(0xffffffffu, hit);
+        if (hit) p.pf_col[out0 + run + __popc(hb & ((1u << lane) - 1u))] = pa + c;
+        run += __popc(hb);
+      }
+      const int sub0 = q.sub_ptr[fa + i];
+      if (lane == 0) p.pf_cnt[fa + i] = run;
+      for (int s = lane; s < n_sub; s += 32) {
+        const int left = run - s * q.sub_rows;
+        q.sub_start[sub0 + s] = out0 + s * q.sub_rows;
+        q.sub_cnt[sub0 + s] = left < 0 ? 0 : (left > q.sub_rows ? q.sub_rows : left);
+        q.sub_x[3 * (size_t)(sub0 + s)] = qx;
+        q.sub_x[3 * (size_t)(sub0 + s) + 1] = qy;
+        q.sub_x[3 * (size_t)(sub0 + s) + 2] = qz;
+      }
+    }
+    // ---- fp: in-edges of protein atom c = its kept pharmacophore nodes, ascending node index
+    const int cap = nf < q.pf_max ? nf : q.pf_max;
+    for (int c = threadIdx.x; c < np_; c += kDynThreads) {
+      const float px = p.prot_x[3 * (size_t)(pa + c)], py = p.prot_x[3 * (size_t)(pa + c) + 1],
+                  pz = p.prot_x[3 * (size_t)(pa + c) + 2];
+      const int out0 = q.fp_base[g] + c * cap;
+      int o = 0;
+      for (int j = 0; j < nf && o < q.pf_max; ++j)
+        if (sqdist3(px, py, pz, fx[j], fy[j], fz[j]) < q.pf_r2) p.fp_col[out0 + o++] = fa + j;
+      p.fp_seg_start[pa + c] = out0;
+      p.fp_seg_cnt[pa + c] = o;
+    }
+  }
+}
+
+// agg[d] (+)= sum over the sub-segments s in [sub_ptr[d], sub_ptr[d+1]) of sub[s] * sub_cnt[s] * w, w = 1 / tot_cnt[d] (the
+// mean over all in-edges, inv_norm == 0) or inv_norm (numeric message_norm: SUM / norm).  One warp per destination; empty
+// sub-segments are skipped (their rows of `sub` may never have been written), a destination without in-edges gets zero.
+__global__ void __launch_bounds__(256) combine_subsegments_kernel(const float* __restrict__ sub_h, const float* __restrict__ sub_v,
+                                                                  const int* __restrict__ sub_cnt, const int* __restrict__ sub_ptr,
+                                                                  const int* __restrict__ tot_cnt, long long n_dst,
+                                                                  float inv_norm, float* __restrict__ agg_h,
+                                                                  float* __restrict__ agg_v, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; d < n_dst; d += n_warps) {
+    const int tot = tot_cnt[d];
+    const float w = inv_norm != 0.f ? inv_norm : (tot > 0 ? __fdividef(1.0f, (float)tot) : 0.f);
+    float4* oh = reinterpret_cast<float4*>(agg_h + d * kHidden + 4 * lane);
+    float4* ov = reinterpret_cast<float4*>(agg_v + d * kVRow + 4 * lane);
+    float4 h = accumulate ? *oh : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = (accumulate && lane < kVRow / 4) ? *ov : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = sub_ptr[d]; s < sub_ptr[d + 1]; ++s) {
+      const int cnt = sub_cnt[s];
+      if (cnt == 0) continue;
+      const float sc = (float)cnt * w;
+      const float4 a = *reinterpret_cast<const float4*>(sub_h + (long long)s * kHidden + 4 * lane);
+      h = make_float4(fmaf(a.x, sc, h.x), fmaf(a.y, sc, h.y), fmaf(a.z, sc, h.z), fmaf(a.w, sc, h.w));
+      if (lane < kVRow / 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sub_v + (long long)s * kVRow + 4 * lane);
+        v = make_float4(fmaf(b.x, sc, v.x), fmaf(b.y, sc, v.y), fmaf(b.z, sc, v.z), fmaf(b.w, sc, v.w));
+      }
+    }
+    *oh = h;
+    if (lane < kVRow / 4) *ov = v;
+  }
+}
+
 
 // ------------------------------------------------------------------------------------------------ planner
 __global__ void __launch_bounds__(128) plan_tiles_kernel(const int* __restrict__ seg_cnt,
@@ -798,8 +927,8 @@ extern "C" int pf_dyn_graph_ffk(const float* prot_x, const int32_t* prot_ptr, co
                    fp_seg_dst && fp_seg_start && fp_seg_cnt && fp_col && dev_status,
                "pf_dyn_graph: null pointer");
   if (pf_k < 1 || pf_k > kMaxK) {
-    set_error("pf_dyn_graph: pf_k=%d unsupported (1..%d; the radius variant of pf edges, pf_k=0, is not built)", pf_k,
-              kMaxK);
+    set_error("pf_dyn_graph: pf_k=%d unsupported (1..%d; pf_k = 0, the radius variant of the pf edges, is pf_dyn_graph_radius)",
+              pf_k, kMaxK);
     return PF_ERR_UNSUPPORTED;
   }
   if (n_graphs <= 0) return PF_OK;
@@ -811,6 +940,42 @@ extern "C" int pf_dyn_graph_ffk(const float* prot_x, const int32_t* prot_ptr, co
   else
     dyn_graph_kernel<16><<<grid, kDynThreads, 0, as_stream(stream)>>>(p);
   PF_CHECK_LAUNCH("pf_dyn_graph");
+  return PF_OK;
+}
+
+extern "C" int pf_dyn_graph_radius(const float* prot_x, const int32_t* prot_ptr, const float* pharm_x, const int32_t* pharm_ptr,
+                                   int32_t n_graphs, float ff_r, int32_t ff_max_nbrs, int32_t ff_k, float pf_r,
+                                   int32_t pf_max_nbrs, int32_t sub_rows, const int32_t* ff_start, int32_t* ff_cnt,
+                                   int32_t* ff_col, const int32_t* pf_start, const int32_t* sub_ptr, const int32_t* fp_base,
+                                   int32_t* pf_cnt, int32_t* pf_col, int32_t* sub_start, int32_t* sub_cnt, float* sub_x,
+                                   int32_t* fp_seg_start, int32_t* fp_seg_cnt, int32_t* fp_col, uint32_t* dev_status,
+                                   void* stream) {
+  PF_CHECK_ARG(ff_k >= 0 && pf_max_nbrs >= 1 && pf_r > 0.f, "pf_dyn_graph_radius: ff_k < 0, pf_max_nbrs < 1 or pf_r <= 0");
+  PF_CHECK_ARG(sub_rows == PF_TILE_ROWS || sub_rows == PF_TC_TILE_ROWS, "pf_dyn_graph_radius: sub_rows must be 64 or 128");
+  PF_CHECK_ARG(prot_x && prot_ptr && pharm_x && pharm_ptr && ff_start && ff_cnt && ff_col && pf_start && sub_ptr && fp_base &&
+                   pf_cnt && pf_col && sub_start && sub_cnt && sub_x && fp_seg_start && fp_seg_cnt && fp_col && dev_status,
+               "pf_dyn_graph_radius: null pointer");
+  if (n_graphs <= 0) return PF_OK;
+  DynRadiusParams q{{prot_x, pharm_x, prot_ptr, pharm_ptr, n_graphs, ff_r * ff_r, ff_max_nbrs, 0, ff_k, ff_start, ff_cnt, ff_col,
+                     pf_cnt, pf_col, nullptr, fp_seg_start, fp_seg_cnt, fp_col, dev_status},
+                    pf_r * pf_r, pf_max_nbrs, sub_rows, pf_start, sub_ptr, fp_base, sub_start, sub_cnt, sub_x};
+  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
+  dyn_graph_radius_kernel<<<grid, kDynThreads, 0, as_stream(stream)>>>(q);
+  PF_CHECK_LAUNCH("pf_dyn_graph_radius");
+  return PF_OK;
+}
+
+extern "C" int pf_combine_subsegments(const float* sub_h, const float* sub_v, const int32_t* sub_cnt, const int32_t* sub_ptr,
+                                      const int32_t* tot_cnt, int64_t n_dst, float inv_norm, float* agg_h, float* agg_v,
+                                      int32_t accumulate, void* stream) {
+  PF_CHECK_ARG(sub_h && sub_v && sub_cnt && sub_ptr && tot_cnt && agg_h && agg_v, "pf_combine_subsegments: null pointer");
+  PF_CHECK_ARG(inv_norm >= 0.f, "pf_combine_subsegments: negative inv_norm");
+  if (n_dst <= 0) return PF_OK;
+  const long long blocks = (n_dst + 7) / 8;
+  const int grid = (int)(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
+  combine_subsegments_kernel<<<grid, 256, 0, as_stream(stream)>>>(sub_h, sub_v, sub_cnt, sub_ptr, tot_cnt, n_dst, inv_norm,
+                                                                  agg_h, agg_v, accumulate);
+  PF_CHECK_LAUNCH("pf_combine_subsegments");
   return PF_OK;
 }
 

@@ -139,6 +139,9 @@ class _DeviceState:
         a.n_graphs, a.n_prot, a.n_pharm = g.n_graphs, g.n_prot, g.n_pharm
         a.n_prot_feats, a.n_pharm_feats = dyn.n_prot_scalars, dyn.n_pharm_scalars
         a.n_convs, a.n_msg_gvps, a.n_upd_gvps, a.n_noise_gvps = dyn.n_convs, dyn.n_message_gvps, dyn.n_update_gvps, dyn.n_noise_gvps
+        if g.pf_k != dyn.pf_k:
+            raise ValueError(f"the batch was built for pf_k = {g.pf_k}, the model has pf_k = {dyn.pf_k} "
+                             "(GraphBatch.from_pockets(pf_k=...))")
         a.pf_k, a.ff_max_nbrs, a.ff_r = g.pf_k, g.ff_max_nbrs, float(dyn.graph_cutoffs["ff"])
         a.ff_k = int(dyn.ff_k)
         for name in ("prot_x", "prot_feats", "prot_ptr", "pharm_x", "pharm_h", "pharm_ptr", "pp_start", "pp_cnt",
@@ -150,7 +153,15 @@ class _DeviceState:
                      "pharm_agg_v", "eps_h", "eps_x", "t_graph"):
             setattr(a, name, getattr(self, name).data_ptr())
         a.pp_max_tiles = g.pp_num_tiles
-        a.n_pharm_chunks = a.n_fp_chunks = g.n_chunks
+        a.n_pharm_chunks, a.n_fp_chunks = g.n_chunks, g.n_fp_chunks
+        if g.pf_k == 0:       # radius pf / fp edges: sub-segment list of the pf segments + scratch for one mean per sub-segment
+            a.pf_r, a.pf_max_nbrs = float(dyn.graph_cutoffs["pf"]), g.pf_max_nbrs
+            for name in ("pf_sub_ptr", "fp_base", "pf_sub_start", "pf_sub_cnt", "pf_sub_chunk_ptr", "pf_sub_x"):
+                setattr(a, name, getattr(g, name).data_ptr())
+            a.n_pf_sub_chunks, a.n_pf_sub = g.n_graphs, g.n_pf_sub
+            self.sub_agg_h = torch.empty(max(g.n_pf_sub, 1), 128, **f32)
+            self.sub_agg_v = torch.empty(max(g.n_pf_sub, 1), 48, **f32)
+            a.sub_agg_h, a.sub_agg_v = self.sub_agg_h.data_ptr(), self.sub_agg_v.data_ptr()
         a.dyn_max_tiles = g.dyn_max_tiles
         a.dev_status = g.status.data_ptr()
         a.w_pharm_enc, a.w_prot_enc, a.w_noise = w.ptr("pharm_enc"), w.ptr("prot_enc"), w.ptr("noise")
@@ -253,10 +264,12 @@ class PharmRecDynamicsGVP(nn.Module):
             raise NotImplementedError("message_norm must be 'mean' or a positive number (a dict fails in the reference's own "
                                       "check_message_norm, gvp.py:453)")
         self.message_norm = message_norm
-        if pf_k <= 0:
-            raise NotImplementedError("pf_k == 0 (pf / fp edges from radius(pharm, prot, r=8), dynamics_gvp.py:211) is not "
-                                      "built: a pharmacophore centre then has ~120 in-edges at the default cutoff, more than "
-                                      "one 128-row tile of the edge kernels holds; configs/dev.yml uses pf_k = 5")
+        # pf_k == 0 (the reference constructor's default; configs/dev.yml uses 5): pf / fp edges from radius(pharm, prot,
+        # r = graph_cutoffs['pf'], 100 per protein atom) instead of kNN (dynamics_gvp.py:210-216) -- pf_dyn_graph_radius
+        if pf_k < 0:
+            raise ValueError("pf_k must be >= 0")
+        if pf_k == 0 and "pf" not in graph_cutoffs:
+            raise KeyError("pf_k == 0 reads graph_cutoffs['pf'] (dynamics_gvp.py:211)")
         if ff_k < 0:
             raise ValueError("ff_k must be >= 0")
         if act_fn is not nn.SiLU:
@@ -323,6 +336,8 @@ class PharmRecDynamicsGVP(nn.Module):
         if self.share_pocket_messages:
             if self.message_norm != "mean":
                 raise NotImplementedError("share_pocket_messages is built for message_norm = 'mean'")
+            if self.pf_k == 0:
+                raise NotImplementedError("share_pocket_messages is built for pf_k >= 1 (kNN pf edges)")
             if self.n_convs != 2 or self.n_message_gvps != 3 or self.n_update_gvps != 2 or g.tile_rows != 128:
                 raise NotImplementedError("share_pocket_messages is built for the dev.yml shape (n_convs=2, 3 message / 2 "
                                           "update GVPs) on the tcgen05 path")

@@ -177,6 +177,33 @@ def dyn_graph(prot_x: torch.Tensor, prot_ptr: torch.Tensor, pharm_x: torch.Tenso
                "pf_dyn_graph")
 
 
+@torch.library.custom_op(f"{NS}::dyn_graph_radius",
+                         mutates_args=("ff_cnt", "ff_col", "pf_cnt", "pf_col", "sub_start", "sub_cnt", "sub_x", "fp_seg_start",
+                                       "fp_seg_cnt", "fp_col", "status"))
+def dyn_graph_radius(prot_x: torch.Tensor, prot_ptr: torch.Tensor, pharm_x: torch.Tensor, pharm_ptr: torch.Tensor,
+                     ff_r: float, ff_max_nbrs: int, ff_k: int, pf_r: float, pf_max_nbrs: int, sub_rows: int,
+                     ff_start: torch.Tensor, ff_cnt: torch.Tensor, ff_col: torch.Tensor, pf_start: torch.Tensor,
+                     sub_ptr: torch.Tensor, fp_base: torch.Tensor, pf_cnt: torch.Tensor, pf_col: torch.Tensor,
+                     sub_start: torch.Tensor, sub_cnt: torch.Tensor, sub_x: torch.Tensor, fp_seg_start: torch.Tensor,
+                     fp_seg_cnt: torch.Tensor,
+                     fp_col: torch.Tensor, status: torch.Tensor) -> None:
+    """K2 with pf_k == 0: pf / fp edges from radius(pharm, prot, r_pf, max per protein atom) (dynamics_gvp.py:210-216)."""
+    _lib.check(_L.pf_dyn_graph_radius(_f(prot_x), _i(prot_ptr), _f(pharm_x), _i(pharm_ptr), prot_ptr.numel() - 1, ff_r,
+                                      ff_max_nbrs, ff_k, pf_r, pf_max_nbrs, sub_rows, _i(ff_start), _i(ff_cnt), _i(ff_col),
+                                      _i(pf_start), _i(sub_ptr), _i(fp_base), _i(pf_cnt), _i(pf_col), _i(sub_start),
+                                      _i(sub_cnt), _f(sub_x), _i(fp_seg_start), _i(fp_seg_cnt), _i(fp_col), _p(status), _s()),
+               "pf_dyn_graph_radius")
+
+
+@torch.library.custom_op(f"{NS}::combine_subsegments", mutates_args=("agg_h", "agg_v"))
+def combine_subsegments(sub_h: torch.Tensor, sub_v: torch.Tensor, sub_cnt: torch.Tensor, sub_ptr: torch.Tensor,
+                        tot_cnt: torch.Tensor, inv_norm: float, agg_h: torch.Tensor, agg_v: torch.Tensor,
+                        accumulate: bool) -> None:
+    """agg[d] (+)= sum of the sub-segment means of d weighted by count / total (inv_norm == 0) or count * inv_norm."""
+    _lib.check(_L.pf_combine_subsegments(_f(sub_h), _f(sub_v), _i(sub_cnt), _i(sub_ptr), _i(tot_cnt), agg_h.shape[0],
+                                         inv_norm, _f(agg_h), _f(agg_v), int(accumulate), _s()), "pf_combine_subsegments")
+
+
 @torch.library.custom_op(f"{NS}::plan_tiles", mutates_args=("tiles", "n_tiles", "status"))
 def plan_tiles(seg_cnt: torch.Tensor, chunk_ptr: torch.Tensor, skip_empty: bool, tile_rows: int, tiles: torch.Tensor,
                n_tiles: torch.Tensor, status: torch.Tensor) -> None:

@@ -87,6 +87,13 @@ def build_edges(g: GraphBatch) -> Dict[str, dict]:
         s, d = dyn[name]
         out[name] = dict(src=i32(s), dst=i32(d), ptr=i32(ptr), seg_dst=None, n_dst=n,
                          src_nt="pharm" if name == "ff" else "prot", dst_nt="pharm", deg=cnt[:n].float())
+    if k == 0:   # radius pf / fp edges (pf_k == 0): one fp segment per protein atom, identity destinations
+        cnt = g.fp_seg_cnt[:g.n_prot]
+        ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(cnt.long(), 0)])
+        s, d = dyn["fp"]
+        out["fp"] = dict(src=i32(s), dst=i32(d), ptr=i32(ptr), seg_dst=None, n_dst=g.n_prot, src_nt="pharm", dst_nt="prot",
+                         deg=cnt.float())
+        return out
     ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(g.fp_seg_cnt[:k * n].long(), 0)])
     s, d = dyn["fp"]
     fp_deg = torch.zeros(g.n_prot, device=dev).index_add_(0, g.fp_seg_dst[:k * n].long(), g.fp_seg_cnt[:k * n].float())
@@ -162,9 +169,17 @@ def dynamics_forward(dyn, g: GraphBatch, t: torch.Tensor, training: bool = True)
     """PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185) with an autograd graph: (eps_h [Nf, F], eps_x [Nf, 3]).
     g.pharm_x / g.pharm_h hold (x_t, h_t); t [B] is the timestep value per graph."""
     dev = g.device
-    ops.dyn_graph(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, float(dyn.graph_cutoffs["ff"]), g.ff_max_nbrs, g.pf_k,
-                  g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt, g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt, g.fp_col,
-                  g.status)
+    if g.pf_k != dyn.pf_k:
+        raise ValueError(f"the batch was built for pf_k = {g.pf_k}, the model has pf_k = {dyn.pf_k}")
+    if g.pf_k == 0:
+        ops.dyn_graph_radius(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, float(dyn.graph_cutoffs["ff"]), g.ff_max_nbrs,
+                             int(dyn.ff_k), float(dyn.graph_cutoffs["pf"]), g.pf_max_nbrs, g.tile_rows, g.ff_start, g.ff_cnt,
+                             g.ff_col, g.pf_start, g.pf_sub_ptr, g.fp_base, g.pf_cnt, g.pf_col, g.pf_sub_start, g.pf_sub_cnt, g.pf_sub_x,
+                             g.fp_seg_start, g.fp_seg_cnt, g.fp_col, g.status)
+    else:
+        ops.dyn_graph(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, float(dyn.graph_cutoffs["ff"]), g.ff_max_nbrs, g.pf_k,
+                      g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt, g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt,
+                      g.fp_col, g.status, int(dyn.ff_k))
     edges = build_edges(g)
     x = {"pharm": g.pharm_x, "prot": g.prot_x}
     geom = {n: T.edge_geom(x[e["src_nt"]], x[e["dst_nt"]], e["src"], e["dst"]) for n, e in edges.items()}

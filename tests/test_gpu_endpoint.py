@@ -156,3 +156,170 @@ def test_numeric_message_norm_against_reference(golden, sd, dyn_cfg, tag):
     close(tx.detach(), d[f"{tag}__eps_x"], "train eps_x", rtol=2e-4)
     (th.sum() + tx.sum()).backward()
     assert dyn.pharm_encoder[0].weight.grad is not None
+
+
+# ------------------------------------------------------------------------------------------------ pf_k == 0
+def _canon(src, dst):
+    s, d = src.cpu().numpy().astype(np.int64), dst.cpu().numpy().astype(np.int64)
+    o = np.lexsort((s, d))
+    return s[o], d[o]
+
+
+def _radius_batch(pocket_specs, sizes, tile_rows=128, pf_max_nbrs=100):
+    import pf_oracle as O
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    pk = [make_pocket(n, seed=s) for n, s in pocket_specs]
+    g = GraphBatch.from_pockets([Pocket.from_numpy(p, h) for p, h in pk], sizes, "cuda:0", pf_k=0, tile_rows=tile_rows,
+                                pf_max_nbrs=pf_max_nbrs)
+    b = O.build_batch([(t(p), t(h)) for p, h in pk], sizes)
+    return g, b
+
+
+def _radius_graph(g, pf_r, ff_k=0):
+    from pharmacoforge_b200 import ops
+    ops.dyn_graph_radius(g.prot_x, g.prot_ptr, g.pharm_x, g.pharm_ptr, 9.0, g.ff_max_nbrs, ff_k, pf_r, g.pf_max_nbrs, g.tile_rows,
+                         g.ff_start, g.ff_cnt, g.ff_col, g.pf_start, g.pf_sub_ptr, g.fp_base, g.pf_cnt, g.pf_col, g.pf_sub_start,
+                         g.pf_sub_cnt, g.pf_sub_x, g.fp_seg_start, g.fp_seg_cnt, g.fp_col, g.status)
+    g.check_status()
+
+
+@pytest.mark.parametrize("pf_r,cap,tile_rows", [(8.0, 100, 128), (11.0, 100, 128), (30.0, 3, 128), (4.0, 100, 64)])
+def test_pf_radius_graph_bit_exact(pf_r, cap, tile_rows):
+    """pf_dyn_graph_radius (pf_k == 0, dynamics_gvp.py:210-216): ff / pf / fp edge lists bit-exact against the oracle on a ragged
+    batch (a 1,500-atom pocket, a 3-atom pocket, a 1-node graph, a centre far from its pocket), the per-atom cap (cap = 3 with a
+    radius that reaches everything: every atom keeps its three lowest-index nodes), and the sub-segment cut of the pf segments."""
+    import pf_oracle as O
+    g, b = _radius_batch([(400, 0), (1500, 3), (3, 9), (60, 7)], [[3, 8, 5], [6, 16], [4], [1, 12]], tile_rows, cap)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(g.n_pharm, 3, generator=gen) * 4.0
+    x[1] = torch.tensor([60.0, 0.0, 0.0])
+    com = torch.stack([b.prot_x[int(b.prot_ptr[i]):int(b.prot_ptr[i + 1])].mean(0) for i in range(b.n_graphs)])
+    prot = b.prot_x - com[b.prot_b]
+    g.pharm_x.copy_(x)
+    g.prot_x.copy_(prot)
+    b.pharm_x, b.prot_x = x, prot
+    _radius_graph(g, pf_r)
+    got = g.dynamic_edges()
+    want = O.dynamic_edges(b, 9.0, 0, 0, pf_r)
+    q, c = O.radius_bipartite_edges(b.prot_x, b.prot_ptr, b.pharm_x, b.pharm_ptr, pf_r, cap)
+    want["pf"], want["fp"] = (q, c), (c, q)
+    for et in ("ff", "pf", "fp"):
+        s, d = _canon(*got[et])
+        so, do = _canon(*want[et])
+        assert np.array_equal(s, so) and np.array_equal(d, do), et
+    # both lists come out destination-major with ascending sources, as radius() orders them
+    assert np.array_equal(got["fp"][0].cpu().numpy(), c.numpy()) and np.array_equal(got["fp"][1].cpu().numpy(), q.numpy())
+    n = g.n_pharm
+    cnt, sub_ptr = g.pf_cnt[:n].cpu().numpy(), g.pf_sub_ptr.cpu().numpy()
+    sub_cnt, sub_start = g.pf_sub_cnt.cpu().numpy(), g.pf_sub_start.cpu().numpy()
+    pf_start = g.pf_start.cpu().numpy()
+    assert sub_ptr[-1] == g.n_pf_sub and sub_cnt.max() <= tile_rows
+    for i in range(n):
+        sl = slice(sub_ptr[i], sub_ptr[i + 1])
+        assert sub_cnt[sl].sum() == cnt[i]
+        assert np.array_equal(sub_start[sl], pf_start[i] + tile_rows * np.arange(sub_ptr[i + 1] - sub_ptr[i]))
+    if pf_r >= 8.0 and cap == 100:
+        assert cnt.max() > tile_rows           # the case the sub-segments exist for
+    if cap == 3:
+        assert int(g.fp_seg_cnt[:g.n_prot].max()) == 3
+
+
+@pytest.mark.parametrize("tile_rows", [128, 64])
+def test_denoiser_radius_pf_edges_against_reference(golden, sd, dyn_cfg, tile_rows):
+    """dynamics_config pf_k = 0: the fused denoiser (tcgen05 and FFMA kernels) and the differentiable training graph against a
+    denoiser call of the reference's own code with that switch (oracle/make_golden_pfradius.py: pf cutoff 11 A on a 400-atom
+    pocket, pharmacophore in-degrees up to ~400 = four tiles), edge lists bit-exact, per-layer features and eps."""
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    d = golden("pf_radius.npz")
+    cuts = dict(dyn_cfg["graph_cutoffs"], pf=float(d["pf_cutoff"]), fp=float(d["pf_cutoff"]))
+    model = _model(sd, dict(dyn_cfg, pf_k=0, graph_cutoffs=cuts)).eval()
+    sizes = [int(v) for v in d["sizes"]]
+    g = GraphBatch.from_pockets([Pocket.from_numpy(*make_pocket(int(d["n_atoms"]), seed=int(d["pocket_seed"])))], [sizes], "cuda:0",
+                                pf_k=0, tile_rows=tile_rows)
+    dyn = model.dynamics
+    st = dyn.bind(g)
+
+    def load():
+        g.prot_x.copy_(t(d["prot_x"]))
+        g.pharm_x.copy_(t(d["x_t"]))
+        g.pharm_h.copy_(t(d["h_t"]))
+    load()
+    with torch.no_grad():
+        eps_h, eps_x = dyn(g, t(d["t"]), None)
+    got = g.dynamic_edges()
+    for et in ("ff", "pf", "fp"):
+        s_, d_ = _canon(*got[et])
+        assert np.array_equal(s_, d[f"e_{et}_src"]) and np.array_equal(d_, d[f"e_{et}_dst"]), et
+    assert int(g.pf_cnt.max()) > 128
+
+    def close(a, ref, what, rtol=1e-4):
+        ref = t(ref)
+        err = float((a.cpu() - ref).abs().max())
+        print(tile_rows, what, "max abs err", err, "relative to max", err / max(float(ref.abs().max()), 1e-6))
+        assert err <= rtol * max(float(ref.abs().max()), 1e-6) + 1e-6, (what, err)
+    close(eps_h, d["eps_h"], "eps_h")
+    close(eps_x, d["eps_x"], "eps_x")
+    close(st.pharm_hh, d["conv1_pharm_h"], "conv1 pharm h")
+    close(st.prot_h, d["conv1_prot_h"], "conv1 prot h")
+    if tile_rows == 128:
+        # every layer-0 switch gives the same eps (the table / seeded first layer run on the sub-segment list too)
+        for attr in ("layer0_table", "layer0_seed"):
+            setattr(dyn, attr, False)
+            load()
+            with torch.no_grad():
+                eh2, ex2 = dyn(g, t(d["t"]), None)
+            close(eh2, d["eps_h"], f"eps_h ({attr} off)")
+            close(ex2, d["eps_x"], f"eps_x ({attr} off)")
+        dyn.layer0_table = dyn.layer0_seed = True
+        # differentiable graph (training mode, dropout 0): same eps, gradients reach the encoders
+        from pharmacoforge_b200 import train_graph
+        model.train()
+        load()
+        th, tx = train_graph.dynamics_forward(dyn, g, t(d["t"]), training=True)
+        close(th.detach(), d["eps_h"], "train eps_h", rtol=2e-4)
+        close(tx.detach(), d["eps_x"], "train eps_x", rtol=2e-4)
+        (th.sum() + tx.sum()).backward()
+        assert dyn.prot_encoder[0].weight.grad is not None and torch.isfinite(dyn.prot_encoder[0].weight.grad).all()
+
+
+def test_radius_pf_edges_numeric_norm_and_sampling(sd, dyn_cfg):
+    """pf_k = 0 together with a numeric message_norm against the oracle, and a short reverse diffusion (8 steps) whose result is
+    bit-identical between one batch and batches of one graph (the sub-segment combine keeps the batch-composition invariance)."""
+    import pf_oracle as O
+    cuts = dict(dyn_cfg["graph_cutoffs"], pf=8.0, fp=8.0)
+    cfg = dict(dyn_cfg, pf_k=0, message_norm=10.0, graph_cutoffs=cuts)
+    model = _model(sd, cfg).eval()
+    g, b = _radius_batch([(400, 1), (150, 4)], [[4, 7], [5]])
+    gen = torch.Generator().manual_seed(17)
+    x, h = torch.randn(g.n_pharm, 3, generator=gen) * 3.0, torch.randn(g.n_pharm, 6, generator=gen)
+    com = torch.stack([b.prot_x[int(b.prot_ptr[i]):int(b.prot_ptr[i + 1])].mean(0) for i in range(b.n_graphs)])
+    prot = b.prot_x - com[b.prot_b]
+    model.dynamics.bind(g)
+    g.pharm_x.copy_(x)
+    g.pharm_h.copy_(h)
+    g.prot_x.copy_(prot)
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    tt = torch.tensor([0.3, 0.3, 0.75])
+    wh, wx = O.denoiser(sd, b, tt, cfg)
+    with torch.no_grad():
+        gh, gx = model.dynamics(g, tt, None)
+    for a_, w_, what in ((gh, wh, "eps_h"), (gx, wx, "eps_x")):
+        err = float((a_.cpu() - w_).abs().max())
+        assert err <= 1e-4 * max(float(w_.abs().max()), 1e-6) + 1e-6, (what, err)
+    # sampling: the second pocket alone gives bit-identical results (a graph never sees its batch neighbours)
+    from pharmacoforge_b200.batch import Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    model = _model(sd, dict(dyn_cfg, pf_k=0, graph_cutoffs=cuts)).eval()
+    pockets = [Pocket.from_numpy(*make_pocket(n, seed=s_)) for n, s_ in ((400, 1), (150, 4))]
+    noise = torch.randn(9, 16, 9, generator=torch.Generator().manual_seed(3))
+    x1, h1 = model.sample_given_receptor(model.make_batch(pockets, [[4, 7], [5]], "cuda:0"), noise=noise, n_steps=8,
+                                         return_tensors=True)
+    x2, h2 = model.sample_given_receptor(model.make_batch(pockets[1:], [[5]], "cuda:0"), noise=noise[:, 11:].contiguous(),
+                                         n_steps=8, return_tensors=True)
+    assert torch.isfinite(x1).all() and torch.isfinite(h1).all()
+    assert torch.equal(x2, x1[11:]) and torch.equal(h2, h1[11:])
+    # and the Philox / CUDA-graph throughput path runs in this mode
+    out = model.sample_given_receptor(model.make_batch(pockets, [[4, 7], [5]], "cuda:0"))
+    assert len(out) == 3 and all(torch.isfinite(o.ph_coords).all() and torch.isfinite(o.ph_feats).all() for o in out)

@@ -97,14 +97,17 @@ def test_unsupported_configs_fail_loudly():
     from pharmacoforge_b200.dynamics import PharmRecDynamicsGVP
     with pytest.raises(NotImplementedError):
         PharmRecDynamicsGVP(6, 11, vector_size=8, n_convs=2, graph_cutoffs={"ff": 9}, message_norm="mean", pf_k=5)
-    # a positive numeric message_norm (sum aggregation / norm) is built; 0, dicts and pf_k = 0 are not
+    # a positive numeric message_norm (sum aggregation / norm) and pf_k = 0 (radius pf edges) are built; 0 and dicts are not
     assert PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm=10, pf_k=5).message_norm == 10
     with pytest.raises(NotImplementedError):
         PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm=0, pf_k=5)
     with pytest.raises(NotImplementedError):
         PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm={"prot": 1, "pharm": 1}, pf_k=5)
-    with pytest.raises(NotImplementedError):
+    assert PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9, "pf": 8}, message_norm="mean", pf_k=0).pf_k == 0
+    with pytest.raises(KeyError):       # pf_k = 0 reads graph_cutoffs['pf'] (dynamics_gvp.py:211)
         PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm="mean", pf_k=0)
+    with pytest.raises(ValueError):
+        PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm="mean", pf_k=-1)
 
 
 def test_ops_refuse_cpu_tensors():
