@@ -143,10 +143,11 @@ int pf_dyn_graph_radius(const float* prot_x, const int32_t* prot_ptr, const floa
                         void* stream);
 
 /* agg[d] (+)= sum over s in [sub_ptr[d], sub_ptr[d+1]) of sub[s] * sub_cnt[s] * w with w = 1 / tot_cnt[d] (inv_norm == 0: the
- * mean over all in-edges of d, fn.mean of gvp.py:488-497) or w = inv_norm (numeric message_norm).  Rows as pf_scaled_accumulate. */
+ * mean over all in-edges of d, fn.mean of gvp.py:488-497), w = inv_norm (numeric message_norm) or, when inv_norm_node is
+ * given, w = inv_norm_node[d] (message_norm = 0).  Rows as pf_scaled_accumulate. */
 int pf_combine_subsegments(const float* sub_h, const float* sub_v, const int32_t* sub_cnt, const int32_t* sub_ptr,
-                           const int32_t* tot_cnt, int64_t n_dst, float inv_norm, float* agg_h, float* agg_v,
-                           int32_t accumulate, void* stream);
+                           const int32_t* tot_cnt, int64_t n_dst, float inv_norm, const float* inv_norm_node, float* agg_h,
+                           float* agg_v, int32_t accumulate, void* stream);
 
 /* ---- tile planner --------------------------------------------------------------------------------
  * Greedily packs consecutive segments of each chunk [chunk_ptr[c], chunk_ptr[c+1]) into tiles of at
@@ -384,6 +385,9 @@ typedef struct PfSampleArgs {
   int32_t n_pf_sub_chunks, n_pf_sub;
   float *sub_agg_h, *sub_agg_v;              /* [n_pf_sub][128], [n_pf_sub][48] scratch */
   float* pf_sub_x;                           /* [n_pf_sub][3] destination coordinates per sub-segment */
+  /* message_norm = 0: SUM / (edges per node of the graph + 1), pf_degree_norms; tmp_agg_* as for a numeric norm */
+  int32_t msg_norm_degree;
+  float *inv_norm_pharm, *inv_norm_prot;     /* [n_pharm], [n_prot] */
 } PfSampleArgs;
 #define PF_FLAG_SKIP_DEAD_WORK 1u
 /* PF_FLAG_FP16_SINGLE_PASS: K3 / K4 run pf_edge_conv_tc_f16 / pf_node_update_tc_f16 (tcgen05 path only); the graph
@@ -423,9 +427,19 @@ int pf_share_gather(const int32_t* pharm_ptr, const int32_t* prot_ptr, const int
                     float* c_agg_h, float* c_agg_v, int32_t stage, void* stream);
 
 /* agg[d] (+)= tmp[d] * seg_cnt[s] * inv_norm for every segment s (d = seg_dst ? seg_dst[s] : s): mean -> scaled sum (numeric
- * message_norm, see PfSampleArgs.msg_norm_*).  Rows: agg_h / tmp_h [n][128], agg_v / tmp_v [n][48]. */
+ * message_norm, see PfSampleArgs.msg_norm_*); with inv_norm_node != NULL the factor is inv_norm_node[d] (message_norm = 0).
+ * Rows: agg_h / tmp_h [n][128], agg_v / tmp_v [n][48]. */
 int pf_scaled_accumulate(const float* tmp_h, const float* tmp_v, const int32_t* seg_cnt, const int32_t* seg_dst, int64_t n_seg,
-                         float inv_norm, float* agg_h, float* agg_v, int32_t accumulate, void* stream);
+                         float inv_norm, const float* inv_norm_node, float* agg_h, float* agg_v, int32_t accumulate,
+                         void* stream);
+
+/* message_norm = 0 (gvp.py:504-507): 1 / ((edges of every type into the node type) / (nodes of the type) + 1) per graph, written
+ * per node.  Per-graph edge counts as add_pharm_edges records them (dynamics_gvp.py:219-221): ff / pp true counts; pf (= fp)
+ * through prot_batch_idx[pf_idxs[0]] -- true counts with radius edges (radius_mode = 1), and with kNN edges the edges of
+ * pharmacophore node i counted for the graph that owns protein atom i (the reference's behaviour, kept). */
+int pf_degree_norms(const int32_t* prot_ptr, const int32_t* pharm_ptr, int32_t n_graphs, int32_t n_pharm, const int32_t* ff_cnt,
+                    const int32_t* pf_cnt, const int32_t* pp_cnt, int32_t radius_mode, float* inv_norm_pharm,
+                    float* inv_norm_prot, void* stream);
 
 /* One eps prediction, PharmRecDynamicsGVP.forward (dynamics_gvp.py:131-185); a->t_graph[g] must hold the
  * timestep value of graph g.  Results in a->eps_h / a->eps_x. */

@@ -16,14 +16,14 @@ sys.path.insert(0, HERE)
 import make_golden as MG  # noqa: E402
 
 
-def main():
+def main(tags=(("n4", 4.0), ("n1", 1)), out_name="message_norm.npz"):
     MG.reference_loader.load()
     import yaml
     from pharmacoforge.config_utils.load_from_config import model_from_config
     from pharmacoforge.utils import get_batch_idxs
     from pharmacoforge_b200.synthetic import synth_state_dict
     save = {}
-    for tag, nv in (("n4", 4.0), ("n1", 1)):
+    for tag, nv in tags:
         cfg = copy.deepcopy(yaml.safe_load(open(os.path.join(MG.reference_loader.REFERENCE_ROOT, "configs", "dev.yml"))))
         cfg["dynamics"]["message_norm"] = nv
         torch.manual_seed(0)
@@ -67,9 +67,12 @@ def main():
         for k, v in cap.items():
             save[f"{tag}__{k}"] = v.numpy()
         print(tag, float(eps_h.abs().max()), float(eps_x.abs().max()))
-    np.savez_compressed(os.path.join(MG.GOLD, "message_norm.npz"), **save)
-    print(os.path.getsize(os.path.join(MG.GOLD, "message_norm.npz")))
+    np.savez_compressed(os.path.join(MG.GOLD, out_name), **save)
+    print(os.path.getsize(os.path.join(MG.GOLD, out_name)))
 
 
 if __name__ == "__main__":
     main()
+    # message_norm = 0: SUM / (edges into the node type per graph / nodes of the type per graph + 1), gvp.py:504-507, with the
+    # per-graph edge counts exactly as add_pharm_edges records them (dynamics_gvp.py:219-221)
+    main(tags=(("n0", 0),), out_name="message_norm0.npz")

@@ -229,9 +229,10 @@ def mean_aggregate(msg: torch.Tensor, dst: torch.Tensor, n_dst: int) -> torch.Te
 
 def conv_layer(sd, p: str, feats: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
                edges: Dict[str, Tuple[torch.Tensor, torch.Tensor]], n_message_gvps=3, n_update_gvps=2,
-               return_messages: bool = False, message_norm="mean"):
+               return_messages: bool = False, message_norm="mean", norm0: Optional[Dict[str, torch.Tensor]] = None):
     """GVPMultiEdgeConv.forward, gvp.py:459-538, eval mode (dropout = identity).  message_norm='mean' (dev.yml): mean over
-    the in-edges per edge type; a positive number: SUM over the in-edges (gvp.py:386-389) divided by it (:512-517).
+    the in-edges per edge type; a positive number: SUM over the in-edges (gvp.py:386-389) divided by it (:512-517); 0: SUM
+    divided by the per-node value norm0[ntype] (`degree_norms`, gvp.py:504-507).
 
     feats[ntype] = (h [N,128], x [N,3], v [N,16,3]); edges[etype] = (src, dst).
     """
@@ -249,6 +250,9 @@ def conv_layer(sd, p: str, feats: Dict[str, Tuple[torch.Tensor, torch.Tensor, to
         if message_norm == "mean":
             a_s = mean_aggregate(ms, dst, n_dst)
             a_v = mean_aggregate(mv, dst, n_dst)
+        elif message_norm == 0:
+            a_s = torch.zeros((n_dst,) + tuple(ms.shape[1:]), dtype=ms.dtype).index_add_(0, dst, ms) / norm0[dnt].view(-1, 1)
+            a_v = torch.zeros((n_dst,) + tuple(mv.shape[1:]), dtype=mv.dtype).index_add_(0, dst, mv) / norm0[dnt].view(-1, 1, 1)
         else:
             a_s = torch.zeros((n_dst,) + tuple(ms.shape[1:]), dtype=ms.dtype).index_add_(0, dst, ms) / float(message_norm)
             a_v = torch.zeros((n_dst,) + tuple(mv.shape[1:]), dtype=mv.dtype).index_add_(0, dst, mv) / float(message_norm)
@@ -353,6 +357,26 @@ def dynamic_edges(b: FlatBatch, ff_cutoff: float = 9.0, pf_k: int = 5, ff_k: int
     return {"ff": (ff_src, ff_dst), "pf": (c, q), "fp": (q, c), "pp": b.pp}
 
 
+def degree_norms(b: FlatBatch, edges, pf_k: int) -> Dict[str, torch.Tensor]:
+    """message_norm = 0 (gvp.py:504-507): per graph, (edges of every type into the node type) / (nodes of the type) + 1,
+    broadcast to the nodes.  The per-graph edge counts are the ones add_pharm_edges records (dynamics_gvp.py:219-221): ff by
+    the graph of the edge's first index (true counts); pp from the batched dataset graph (true counts); pf -- and fp, which
+    copies it -- by `prot_batch_idx[pf_idxs[0]]`: with radius edges (pf_k = 0) pf_idxs[0] holds protein atoms (true counts),
+    with kNN edges it holds PHARMACOPHORE node indices, so the edges of pharmacophore node i are counted for the graph that
+    owns PROTEIN ATOM i.  That is what the reference computes; it is restated here, not corrected."""
+    B = b.n_graphs
+    cnt = lambda idx, owner: torch.bincount(owner[idx], minlength=B)
+    e_ff = cnt(edges["ff"][0], b.pharm_b)
+    e_pp = cnt(edges["pp"][1], b.prot_b)
+    if pf_k > 0:
+        e_pf = cnt(edges["pf"][1], b.prot_b)        # pharm node index looked up in the PROTEIN batch index (see above)
+    else:
+        e_pf = cnt(edges["pf"][0], b.prot_b)
+    n_f = (b.pharm_ptr[1:] - b.pharm_ptr[:-1]).long()
+    n_p = (b.prot_ptr[1:] - b.prot_ptr[:-1]).long()
+    return {"pharm": ((e_ff + e_pf) / n_f + 1)[b.pharm_b], "prot": ((e_pf + e_pp) / n_p + 1)[b.prot_b]}
+
+
 def denoiser(sd, b: FlatBatch, t: torch.Tensor, cfg: dict, prefix: str = "dynamics", trace: Optional[dict] = None):
     """PharmRecDynamicsGVP.forward, dynamics_gvp.py:131-185 -> (eps_h [Nf,6], eps_x [Nf,3])."""
     vs = cfg.get("vector_size", 16)
@@ -362,13 +386,15 @@ def denoiser(sd, b: FlatBatch, t: torch.Tensor, cfg: dict, prefix: str = "dynami
              "prot": (h_p, b.prot_x, torch.zeros(h_p.shape[0], vs, 3))}
     edges = dynamic_edges(b, cfg["graph_cutoffs"]["ff"], cfg.get("pf_k", 5), cfg.get("ff_k", 0),
                           cfg["graph_cutoffs"].get("pf", 8.0))
+    mn = cfg.get("message_norm", "mean")
+    norm0 = degree_norms(b, edges, cfg.get("pf_k", 5)) if (not isinstance(mn, str) and mn == 0) else None
     if trace is not None:
         trace["edges"] = edges
         trace["enc"] = {k: v[0] for k, v in feats.items()}
+        trace["norm0"] = norm0
     for li in range(cfg.get("n_convs", 2)):
         feats = conv_layer(sd, f"{prefix}.noise_predictor.conv_layers.{li}", feats, edges,
-                           cfg.get("n_message_gvps", 3), cfg.get("n_update_gvps", 2),
-                           message_norm=cfg.get("message_norm", "mean"))
+                           cfg.get("n_message_gvps", 3), cfg.get("n_update_gvps", 2), message_norm=mn, norm0=norm0)
         if trace is not None:
             trace[f"conv{li}"] = {k: (v[0], v[2]) for k, v in feats.items()}
     return noise_head(sd, f"{prefix}.noise_predictor.noise_predictor", feats["pharm"][0], feats["pharm"][2],

@@ -37,7 +37,7 @@ SIGNATURES = {
     "pf_dyn_graph_radius": (C.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_float,
                                       C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                       c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, C.c_void_p, STREAM]),
-    "pf_combine_subsegments": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, C.c_int64, C.c_float, c_f32p, c_f32p,
+    "pf_combine_subsegments": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, C.c_int64, C.c_float, c_f32p, c_f32p, c_f32p,
                                          C.c_int32, STREAM]),
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
@@ -106,7 +106,10 @@ SIGNATURES = {
                              C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, STREAM]),
     "pf_train_gemm": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                 C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, STREAM]),
-    "pf_scaled_accumulate": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, C.c_int64, C.c_float, c_f32p, c_f32p, C.c_int32, STREAM]),
+    "pf_scaled_accumulate": (C.c_int, [c_f32p, c_f32p, c_i32p, c_i32p, C.c_int64, C.c_float, c_f32p, c_f32p, c_f32p, C.c_int32,
+                                       STREAM]),
+    "pf_degree_norms": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, C.c_int32, c_f32p, c_f32p,
+                                  STREAM]),
     "pf_denoiser": (C.c_int, [C.c_void_p, STREAM]),
     "pf_sample_loop": (C.c_int, [C.c_void_p, STREAM]),
 }
@@ -167,6 +170,7 @@ class PfSampleArgs(C.Structure):
         ("pf_sub_start", C.c_void_p), ("pf_sub_cnt", C.c_void_p), ("pf_sub_chunk_ptr", C.c_void_p),
         ("n_pf_sub_chunks", C.c_int32), ("n_pf_sub", C.c_int32), ("sub_agg_h", C.c_void_p), ("sub_agg_v", C.c_void_p),
         ("pf_sub_x", C.c_void_p),
+        ("msg_norm_degree", C.c_int32), ("inv_norm_pharm", C.c_void_p), ("inv_norm_prot", C.c_void_p),
     ]
 
 

@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(256) zero_listed_rows_kernel(float* __restrict
 // sum.  One warp per segment s (destination d = seg_dst ? seg_dst[s] : s); empty segments contribute zero.
 __global__ void __launch_bounds__(256) scaled_accumulate_kernel(const float* __restrict__ tmp_h, const float* __restrict__ tmp_v,
                                                                 const int* __restrict__ seg_cnt, const int* __restrict__ seg_dst,
-                                                                long long n_seg, float inv_norm, float* __restrict__ agg_h,
+                                                                long long n_seg, float inv_norm,
+                                                                const float* __restrict__ inv_norm_node, float* __restrict__ agg_h,
                                                                 float* __restrict__ agg_v, int accumulate) {
   const int lane = threadIdx.x & 31;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(256) scaled_accumulate_kernel(const float* __r
     const int cnt = seg_cnt[s];
     if (seg_dst != nullptr && cnt == 0) continue;   // an unused slot of a segment list: no destination
     const long long d = seg_dst != nullptr ? seg_dst[s] : s;
-    const float sc = (float)cnt * inv_norm;
+    const float sc = (float)cnt * (inv_norm_node != nullptr ? inv_norm_node[d] : inv_norm);
     float4 h = make_float4(0.f, 0.f, 0.f, 0.f), v = h;
     if (cnt > 0) {
       h = *reinterpret_cast<const float4*>(tmp_h + d * kHidden + 4 * lane);
@@ -258,6 +259,41 @@ __global__ void __launch_bounds__(256) scaled_accumulate_kernel(const float* __r
       a = accumulate ? *ov : make_float4(0.f, 0.f, 0.f, 0.f);
       *ov = make_float4(fmaf(v.x, sc, a.x), fmaf(v.y, sc, a.y), fmaf(v.z, sc, a.z), fmaf(v.w, sc, a.w));
     }
+  }
+}
+
+// message_norm = 0 (gvp.py:504-507): per graph, (edges of every type into the node type) / (nodes of the type) + 1; the
+// reciprocal is written per node.  Edge counts per graph as add_pharm_edges records them (dynamics_gvp.py:219-221): ff and pp
+// are the true counts; pf (and fp, which copies it) is counted through prot_batch_idx[pf_idxs[0]] -- protein atoms with radius
+// edges (true counts), but PHARMACOPHORE node indices with kNN edges, so there the edges of pharmacophore node i go to the graph
+// that owns protein atom i.  Reproduced as is (the oracle is pinned to the reference's own output).  One CTA per graph.
+__global__ void __launch_bounds__(128) degree_norms_kernel(const int* __restrict__ prot_ptr, const int* __restrict__ pharm_ptr,
+                                                           int n_graphs, int n_pharm, const int* __restrict__ ff_cnt,
+                                                           const int* __restrict__ pf_cnt, const int* __restrict__ pp_cnt,
+                                                           int radius_mode, float* __restrict__ inv_pharm,
+                                                           float* __restrict__ inv_prot) {
+  __shared__ int s_sum[3];
+  for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
+    const int pa = prot_ptr[g], pb = prot_ptr[g + 1], fa = pharm_ptr[g], fb = pharm_ptr[g + 1];
+    __syncthreads();
+    if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
+    __syncthreads();
+    int e_ff = 0, e_pf = 0, e_pp = 0;
+    for (int i = fa + threadIdx.x; i < fb; i += blockDim.x) {
+      e_ff += ff_cnt[i];
+      if (radius_mode) e_pf += pf_cnt[i];
+    }
+    if (!radius_mode)
+      for (int i = pa + threadIdx.x; i < pb && i < n_pharm; i += blockDim.x) e_pf += pf_cnt[i];
+    for (int c = pa + threadIdx.x; c < pb; c += blockDim.x) e_pp += pp_cnt[c];
+    atomicAdd(&s_sum[0], e_ff);   // integer sums: order-independent
+    atomicAdd(&s_sum[1], e_pf);
+    atomicAdd(&s_sum[2], e_pp);
+    __syncthreads();
+    const float nf = __fadd_rn(__fdiv_rn((float)(s_sum[0] + s_sum[1]), (float)(fb - fa)), 1.0f);
+    const float np_ = __fadd_rn(__fdiv_rn((float)(s_sum[1] + s_sum[2]), (float)(pb - pa)), 1.0f);
+    for (int i = fa + threadIdx.x; i < fb; i += blockDim.x) inv_pharm[i] = __fdiv_rn(1.0f, nf);
+    for (int c = pa + threadIdx.x; c < pb; c += blockDim.x) inv_prot[c] = __fdiv_rn(1.0f, np_);
   }
 }
 
@@ -426,15 +462,28 @@ extern "C" int pf_fill_f32(float* p, int64_t n, float v, void* stream) {
 }
 
 
+extern "C" int pf_degree_norms(const int32_t* prot_ptr, const int32_t* pharm_ptr, int32_t n_graphs, int32_t n_pharm,
+                               const int32_t* ff_cnt, const int32_t* pf_cnt, const int32_t* pp_cnt, int32_t radius_mode,
+                               float* inv_norm_pharm, float* inv_norm_prot, void* stream) {
+  PF_CHECK_ARG(prot_ptr && pharm_ptr && ff_cnt && pf_cnt && pp_cnt && inv_norm_pharm && inv_norm_prot,
+               "pf_degree_norms: null pointer");
+  if (n_graphs <= 0) return PF_OK;
+  const int grid = n_graphs < 32 * num_sms() ? n_graphs : 32 * num_sms();
+  degree_norms_kernel<<<grid, 128, 0, as_stream(stream)>>>(prot_ptr, pharm_ptr, n_graphs, n_pharm, ff_cnt, pf_cnt, pp_cnt,
+                                                           radius_mode, inv_norm_pharm, inv_norm_prot);
+  PF_CHECK_LAUNCH("pf_degree_norms");
+  return PF_OK;
+}
+
 extern "C" int pf_scaled_accumulate(const float* tmp_h, const float* tmp_v, const int32_t* seg_cnt, const int32_t* seg_dst,
-                                    int64_t n_seg, float inv_norm, float* agg_h, float* agg_v, int32_t accumulate,
-                                    void* stream) {
+                                    int64_t n_seg, float inv_norm, const float* inv_norm_node, float* agg_h, float* agg_v,
+                                    int32_t accumulate, void* stream) {
   PF_CHECK_ARG(tmp_h && tmp_v && seg_cnt && agg_h && agg_v, "pf_scaled_accumulate: null pointer");
   if (n_seg <= 0) return PF_OK;
   const long long blocks = (n_seg + 7) / 8;
   const int grid = (int)(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
-  scaled_accumulate_kernel<<<grid, 256, 0, as_stream(stream)>>>(tmp_h, tmp_v, seg_cnt, seg_dst, n_seg, inv_norm, agg_h, agg_v,
-                                                                accumulate);
+  scaled_accumulate_kernel<<<grid, 256, 0, as_stream(stream)>>>(tmp_h, tmp_v, seg_cnt, seg_dst, n_seg, inv_norm, inv_norm_node,
+                                                                agg_h, agg_v, accumulate);
   PF_CHECK_LAUNCH("pf_scaled_accumulate");
   return PF_OK;
 }
@@ -585,9 +634,18 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
   PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->tile_rows, a->fp_tiles, a->dyn_max_tiles,
                        a->dyn_n_tiles + 2, a->dev_status, stream));
   // numeric message_norm: every edge type's means go to tmp_agg_* and are folded into the aggregate as count / norm * mean
-  const bool summode = a->msg_norm_pharm > 0.f || a->msg_norm_prot > 0.f;
-  PF_CHECK_ARG(!summode || (a->msg_norm_pharm > 0.f && a->msg_norm_prot > 0.f && a->tmp_agg_h && a->tmp_agg_v),
+  // message_norm = 0 (msg_norm_degree): the divisor is per graph, edges per node + 1 (pf_degree_norms), read per destination
+  const bool norm0 = a->msg_norm_degree != 0;
+  const bool summode = norm0 || a->msg_norm_pharm > 0.f || a->msg_norm_prot > 0.f;
+  PF_CHECK_ARG(!summode || ((norm0 || (a->msg_norm_pharm > 0.f && a->msg_norm_prot > 0.f)) && a->tmp_agg_h && a->tmp_agg_v),
                "pf_denoiser: numeric message_norm needs both norms and the tmp_agg buffers");
+  PF_CHECK_ARG(!norm0 || (a->inv_norm_pharm && a->inv_norm_prot), "pf_denoiser: message_norm = 0 needs the inv_norm_* arrays");
+  if (norm0)
+    PF_TRY(pf_degree_norms(a->prot_ptr, a->pharm_ptr, a->n_graphs, a->n_pharm, a->ff_cnt, a->pf_cnt, a->pp_cnt, radius ? 1 : 0,
+                           a->inv_norm_pharm, a->inv_norm_prot, stream));
+  const float inv_f = summode && !norm0 ? 1.0f / a->msg_norm_pharm : 0.f, inv_p = summode && !norm0 ? 1.0f / a->msg_norm_prot : 0.f;
+  const float* const node_f = norm0 ? a->inv_norm_pharm : nullptr;
+  const float* const node_p = norm0 ? a->inv_norm_prot : nullptr;
   PF_CHECK_ARG(!summode || !(a->flags & PF_FLAG_SHARE_POCKET_MESSAGES), "pf_denoiser: the shared-pocket mode is built for message_norm = 'mean'");
   float* const fagg_h = summode ? a->tmp_agg_h : a->pharm_agg_h;   // where the pharm-side / prot-side edge kernels write
   float* const fagg_v = summode ? a->tmp_agg_v : a->pharm_agg_v;
@@ -619,7 +677,7 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                          a->ff_tiles, a->dyn_n_tiles + 0, a->dyn_max_tiles, a->w_msg[l][0], a->w_msg_tc[l][0],
                          a->n_msg_gvps, fagg_h, fagg_v, 0, stream));
     if (summode)
-      PF_TRY(pf_scaled_accumulate(fagg_h, fagg_v, a->ff_cnt, nullptr, a->n_pharm, 1.0f / a->msg_norm_pharm, a->pharm_agg_h,
+      PF_TRY(pf_scaled_accumulate(fagg_h, fagg_v, a->ff_cnt, nullptr, a->n_pharm, inv_f, node_f, a->pharm_agg_h,
                                   a->pharm_agg_v, 0, stream));
   prof_end(kSiteFF, as_stream(stream));
     prof_begin(kSitePF, as_stream(stream));
@@ -632,10 +690,10 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                          a->pf_tiles, a->dyn_n_tiles + 1, a->dyn_max_tiles, a->w_msg[l][1], a->w_msg_tc[l][1],
                          a->n_msg_gvps, pf_out_h, pf_out_v, pf_acc, stream));
     if (radius)   // mean over ALL in-edges of the node (or SUM / norm) from the sub-segment means, added to the ff aggregate
-      PF_TRY(pf_combine_subsegments(a->sub_agg_h, a->sub_agg_v, a->pf_sub_cnt, a->pf_sub_ptr, a->pf_cnt, a->n_pharm,
-                                    summode ? 1.0f / a->msg_norm_pharm : 0.f, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
+      PF_TRY(pf_combine_subsegments(a->sub_agg_h, a->sub_agg_v, a->pf_sub_cnt, a->pf_sub_ptr, a->pf_cnt, a->n_pharm, inv_f,
+                                    node_f, a->pharm_agg_h, a->pharm_agg_v, 1, stream));
     else if (summode)
-      PF_TRY(pf_scaled_accumulate(fagg_h, fagg_v, a->pf_cnt, nullptr, a->n_pharm, 1.0f / a->msg_norm_pharm, a->pharm_agg_h,
+      PF_TRY(pf_scaled_accumulate(fagg_h, fagg_v, a->pf_cnt, nullptr, a->n_pharm, inv_f, node_f, a->pharm_agg_h,
                                   a->pharm_agg_v, 1, stream));
   prof_end(kSitePF, as_stream(stream));
     // exact dead-work elimination (opt-in): nothing reads the protein side of the last layer
@@ -658,7 +716,7 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                          a->n_msg_gvps, pagg_h, pagg_v, 0, stream));
     }
     if (summode)
-      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->pp_cnt, nullptr, a->n_prot, 1.0f / a->msg_norm_prot, a->prot_agg_h,
+      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->pp_cnt, nullptr, a->n_prot, inv_p, node_p, a->prot_agg_h,
                                   a->prot_agg_v, 0, stream));
   prof_end(kSitePP, as_stream(stream));
     prof_begin(kSiteFP, as_stream(stream));
@@ -683,8 +741,8 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
                          a->fp_col, a->fp_tiles, a->dyn_n_tiles + 2, a->dyn_max_tiles, a->w_msg[l][2],
                          a->w_msg_tc[l][2], a->n_msg_gvps, pagg_h, pagg_v, 1, stream));
     if (summode)
-      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->fp_seg_cnt, fp_dst, n_fp_seg,
-                                  1.0f / a->msg_norm_prot, a->prot_agg_h, a->prot_agg_v, 1, stream));
+      PF_TRY(pf_scaled_accumulate(pagg_h, pagg_v, a->fp_seg_cnt, fp_dst, n_fp_seg, inv_p, node_p, a->prot_agg_h,
+                                  a->prot_agg_v, 1, stream));
   prof_end(kSiteFP, as_stream(stream));
     }
     // node updates, in place (gvp.py:501-536)

@@ -678,18 +678,20 @@ __global__ void __launch_bounds__(kDynThreads) dyn_graph_radius_kernel(const Dyn
 }
 
 // agg[d] (+)= sum over the sub-segments s in [sub_ptr[d], sub_ptr[d+1]) of sub[s] * sub_cnt[s] * w, w = 1 / tot_cnt[d] (the
-// mean over all in-edges, inv_norm == 0) or inv_norm (numeric message_norm: SUM / norm).  One warp per destination; empty
+// mean over all in-edges, inv_norm == 0), inv_norm (numeric message_norm: SUM / norm) or inv_norm_node[d] (message_norm = 0).  One warp per destination; empty
 // sub-segments are skipped (their rows of `sub` may never have been written), a destination without in-edges gets zero.
 __global__ void __launch_bounds__(256) combine_subsegments_kernel(const float* __restrict__ sub_h, const float* __restrict__ sub_v,
                                                                   const int* __restrict__ sub_cnt, const int* __restrict__ sub_ptr,
                                                                   const int* __restrict__ tot_cnt, long long n_dst,
-                                                                  float inv_norm, float* __restrict__ agg_h,
+                                                                  float inv_norm, const float* __restrict__ inv_norm_node,
+                                                                  float* __restrict__ agg_h,
                                                                   float* __restrict__ agg_v, int accumulate) {
   const int lane = threadIdx.x & 31;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; d < n_dst; d += n_warps) {
     const int tot = tot_cnt[d];
-    const float w = inv_norm != 0.f ? inv_norm : (tot > 0 ? __fdividef(1.0f, (float)tot) : 0.f);
+    const float w = inv_norm_node != nullptr ? inv_norm_node[d]
+                                             : (inv_norm != 0.f ? inv_norm : (tot > 0 ? __fdividef(1.0f, (float)tot) : 0.f));
     float4* oh = reinterpret_cast<float4*>(agg_h + d * kHidden + 4 * lane);
     float4* ov = reinterpret_cast<float4*>(agg_v + d * kVRow + 4 * lane);
     float4 h = accumulate ? *oh : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -966,15 +968,15 @@ extern "C" int pf_dyn_graph_radius(const float* prot_x, const int32_t* prot_ptr,
 }
 
 extern "C" int pf_combine_subsegments(const float* sub_h, const float* sub_v, const int32_t* sub_cnt, const int32_t* sub_ptr,
-                                      const int32_t* tot_cnt, int64_t n_dst, float inv_norm, float* agg_h, float* agg_v,
-                                      int32_t accumulate, void* stream) {
+                                      const int32_t* tot_cnt, int64_t n_dst, float inv_norm, const float* inv_norm_node,
+                                      float* agg_h, float* agg_v, int32_t accumulate, void* stream) {
   PF_CHECK_ARG(sub_h && sub_v && sub_cnt && sub_ptr && tot_cnt && agg_h && agg_v, "pf_combine_subsegments: null pointer");
   PF_CHECK_ARG(inv_norm >= 0.f, "pf_combine_subsegments: negative inv_norm");
   if (n_dst <= 0) return PF_OK;
   const long long blocks = (n_dst + 7) / 8;
   const int grid = (int)(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
   combine_subsegments_kernel<<<grid, 256, 0, as_stream(stream)>>>(sub_h, sub_v, sub_cnt, sub_ptr, tot_cnt, n_dst, inv_norm,
-                                                                  agg_h, agg_v, accumulate);
+                                                                  inv_norm_node, agg_h, agg_v, accumulate);
   PF_CHECK_LAUNCH("pf_combine_subsegments");
   return PF_OK;
 }

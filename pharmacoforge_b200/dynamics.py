@@ -192,6 +192,14 @@ class _DeviceState:
             self.tmp_agg_v = torch.empty(rows, 48, **f32)
             a.tmp_agg_h, a.tmp_agg_v = self.tmp_agg_h.data_ptr(), self.tmp_agg_v.data_ptr()
             a.msg_norm_pharm = a.msg_norm_prot = float(dyn.message_norm)
+            if dyn.message_norm == 0:       # per-graph divisor (edges per node + 1), one reciprocal per node
+                if g.pf_k > 0 and g.n_pharm > g.n_prot:
+                    raise ValueError("message_norm = 0 with kNN pf edges needs n_pharm <= n_prot: the reference looks the "
+                                     "pharmacophore node index up in the protein batch index (dynamics_gvp.py:220)")
+                self.inv_norm_pharm = torch.empty(nfn, **f32)
+                self.inv_norm_prot = torch.empty(npn, **f32)
+                a.msg_norm_degree = 1
+                a.inv_norm_pharm, a.inv_norm_prot = self.inv_norm_pharm.data_ptr(), self.inv_norm_prot.data_ptr()
         self.share = None     # buffers of the shared-pocket mode, bound on first use (bind_share)
         if g.tile_rows == 128:
             if w.tc is None:
@@ -250,18 +258,16 @@ class PharmRecDynamicsGVP(nn.Module):
             raise NotImplementedError("the sm_100a kernels are built for vector_size=16, n_hidden_scalars=128 "
                                       "(configs/dev.yml); other widths need a rebuild with new tile constants")
         # message_norm (gvp.py:375-389): 'mean' (configs/dev.yml) = mean over the in-edges per edge type; a positive number =
-        # SUM over the in-edges divided by it (the reference constructor's default is 1).  0 (divide by the per-graph mean
-        # degree + 1, :504-507) is not built; a dict raises upstream too (check_message_norm calls .keys() on a set, :453).
+        # SUM over the in-edges divided by it (the reference constructor's default is 1); 0 = SUM divided by the graph's edges
+        # per node + 1 (:504-507, pf_degree_norms).  A dict raises upstream too (check_message_norm calls .keys() on a set, :453).
         if isinstance(message_norm, str):
             if message_norm != "mean":
                 raise ValueError(f"invalid message_norm {message_norm!r}")
         elif isinstance(message_norm, (int, float)) and not isinstance(message_norm, bool):
             if message_norm < 0:
                 raise ValueError("message_norm must be >= 0")
-            if message_norm == 0:
-                raise NotImplementedError("message_norm = 0 (per-graph mean degree + 1, gvp.py:504-507) is not built")
         else:
-            raise NotImplementedError("message_norm must be 'mean' or a positive number (a dict fails in the reference's own "
+            raise NotImplementedError("message_norm must be 'mean' or a number >= 0 (a dict fails in the reference's own "
                                       "check_message_norm, gvp.py:453)")
         self.message_norm = message_norm
         # pf_k == 0 (the reference constructor's default; configs/dev.yml uses 5): pf / fp edges from radius(pharm, prot,

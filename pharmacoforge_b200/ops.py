@@ -198,10 +198,11 @@ def dyn_graph_radius(prot_x: torch.Tensor, prot_ptr: torch.Tensor, pharm_x: torc
 @torch.library.custom_op(f"{NS}::combine_subsegments", mutates_args=("agg_h", "agg_v"))
 def combine_subsegments(sub_h: torch.Tensor, sub_v: torch.Tensor, sub_cnt: torch.Tensor, sub_ptr: torch.Tensor,
                         tot_cnt: torch.Tensor, inv_norm: float, agg_h: torch.Tensor, agg_v: torch.Tensor,
-                        accumulate: bool) -> None:
+                        accumulate: bool, inv_norm_node: Optional[torch.Tensor] = None) -> None:
     """agg[d] (+)= sum of the sub-segment means of d weighted by count / total (inv_norm == 0) or count * inv_norm."""
     _lib.check(_L.pf_combine_subsegments(_f(sub_h), _f(sub_v), _i(sub_cnt), _i(sub_ptr), _i(tot_cnt), agg_h.shape[0],
-                                         inv_norm, _f(agg_h), _f(agg_v), int(accumulate), _s()), "pf_combine_subsegments")
+                                         inv_norm, _f(inv_norm_node), _f(agg_h), _f(agg_v), int(accumulate), _s()),
+               "pf_combine_subsegments")
 
 
 @torch.library.custom_op(f"{NS}::plan_tiles", mutates_args=("tiles", "n_tiles", "status"))

@@ -71,6 +71,22 @@ def encoder(seq, x):
     return T.layernorm(T.silu(T.linear(x, seq[0].weight, seq[0].bias)), seq[2].weight, seq[2].bias)
 
 
+def degree_norms(g: GraphBatch, edges: Dict[str, dict]) -> Dict[str, torch.Tensor]:
+    """message_norm = 0 (gvp.py:504-507): per node, (edges of every type into the node type in its graph) / (nodes of the type
+    in its graph) + 1.  Per-graph edge counts as add_pharm_edges records them (dynamics_gvp.py:219-221): the pf (= fp) edges
+    are assigned through prot_batch_idx[pf_idxs[0]] -- true counts with radius edges, and with kNN edges the edges of
+    pharmacophore node i go to the graph that owns protein atom i (the reference's behaviour, see pf_degree_norms)."""
+    bi = g.batch_idxs()
+    B = g.n_graphs
+    count = lambda idx, owner: torch.bincount(owner[idx.long()], minlength=B)
+    e_ff = count(edges["ff"]["src"], bi["pharm"])
+    e_pp = count(edges["pp"]["dst"], bi["prot"])
+    e_pf = count(edges["pf"]["src"] if g.pf_k == 0 else edges["pf"]["dst"], bi["prot"])
+    n_f = (g.pharm_ptr[1:] - g.pharm_ptr[:-1]).long()
+    n_p = (g.prot_ptr[1:] - g.prot_ptr[:-1]).long()
+    return {"pharm": ((e_ff + e_pf) / n_f + 1)[bi["pharm"]], "prot": ((e_pf + e_pp) / n_p + 1)[bi["prot"]]}
+
+
 def build_edges(g: GraphBatch) -> Dict[str, dict]:
     """Destination-sorted edge lists of the four edge types as int32 tensors: src, dst (per edge), ptr (segment
     offsets into the edge list), seg_dst (node of each segment, None = segment index), n_dst."""
@@ -108,7 +124,7 @@ def _norm_scale(conv, e, a_h, a_v):
     nv = getattr(conv, "message_norm", "mean")
     if nv == "mean":
         return a_h, a_v
-    sc = e["deg"] / float(nv)
+    sc = e["deg"] / (e["norm0"] if nv == 0 else float(nv))
     return a_h * sc[:, None], a_v * sc[:, None, None]
 
 
@@ -181,6 +197,10 @@ def dynamics_forward(dyn, g: GraphBatch, t: torch.Tensor, training: bool = True)
                       g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt, g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt,
                       g.fp_col, g.status, int(dyn.ff_k))
     edges = build_edges(g)
+    if dyn.message_norm == 0:
+        norm0 = degree_norms(g, edges)
+        for e in edges.values():
+            e["norm0"] = norm0[e["dst_nt"]]
     x = {"pharm": g.pharm_x, "prot": g.prot_x}
     geom = {n: T.edge_geom(x[e["src_nt"]], x[e["dst_nt"]], e["src"], e["dst"]) for n, e in edges.items()}
     bi = g.batch_idxs()

@@ -112,14 +112,14 @@ def test_forward_losses_and_gradients_against_reference(golden, sd, dyn_cfg, tag
         assert abs(float(gr.double().norm()) - norm) <= 2e-3 * max(norm, 1e-6), (tag, n, float(gr.norm()), norm)
 
 
-@pytest.mark.parametrize("tag", ["n4", "n1"])
+@pytest.mark.parametrize("tag", ["n4", "n1", "n0"])
 def test_numeric_message_norm_against_reference(golden, sd, dyn_cfg, tag):
     """message_norm = a positive number (sum aggregation / norm, gvp.py:386-389, 512-517; the reference constructor's default is
     1): the fused denoiser -- per-layer features and eps -- and the differentiable training graph against a denoiser call of
     the reference's own code (oracle/make_golden_msgnorm.py)."""
     from pharmacoforge_b200.batch import GraphBatch, Pocket
     from pharmacoforge_b200.synthetic import make_pocket
-    d = golden("message_norm.npz")
+    d = golden("message_norm0.npz" if tag == "n0" else "message_norm.npz")   # n0: message_norm = 0, edges per node + 1
     nv = float(d[f"{tag}__norm"])
     model = _model(sd, dict(dyn_cfg, message_norm=nv)).eval()
     sizes = [int(v) for v in d["sizes"]]
@@ -285,29 +285,30 @@ def test_denoiser_radius_pf_edges_against_reference(golden, sd, dyn_cfg, tile_ro
 
 
 def test_radius_pf_edges_numeric_norm_and_sampling(sd, dyn_cfg):
-    """pf_k = 0 together with a numeric message_norm against the oracle, and a short reverse diffusion (8 steps) whose result is
+    """pf_k = 0 together with a numeric message_norm (10, and 0) against the oracle, and a short reverse diffusion (8 steps) whose result is
     bit-identical between one batch and batches of one graph (the sub-segment combine keeps the batch-composition invariance)."""
     import pf_oracle as O
     cuts = dict(dyn_cfg["graph_cutoffs"], pf=8.0, fp=8.0)
-    cfg = dict(dyn_cfg, pf_k=0, message_norm=10.0, graph_cutoffs=cuts)
-    model = _model(sd, cfg).eval()
-    g, b = _radius_batch([(400, 1), (150, 4)], [[4, 7], [5]])
-    gen = torch.Generator().manual_seed(17)
-    x, h = torch.randn(g.n_pharm, 3, generator=gen) * 3.0, torch.randn(g.n_pharm, 6, generator=gen)
-    com = torch.stack([b.prot_x[int(b.prot_ptr[i]):int(b.prot_ptr[i + 1])].mean(0) for i in range(b.n_graphs)])
-    prot = b.prot_x - com[b.prot_b]
-    model.dynamics.bind(g)
-    g.pharm_x.copy_(x)
-    g.pharm_h.copy_(h)
-    g.prot_x.copy_(prot)
-    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
-    tt = torch.tensor([0.3, 0.3, 0.75])
-    wh, wx = O.denoiser(sd, b, tt, cfg)
-    with torch.no_grad():
-        gh, gx = model.dynamics(g, tt, None)
-    for a_, w_, what in ((gh, wh, "eps_h"), (gx, wx, "eps_x")):
-        err = float((a_.cpu() - w_).abs().max())
-        assert err <= 1e-4 * max(float(w_.abs().max()), 1e-6) + 1e-6, (what, err)
+    for mn in (10.0, 0):      # 0: edges per node of the graph + 1, true per-graph counts in this mode (pf_degree_norms)
+        cfg = dict(dyn_cfg, pf_k=0, message_norm=mn, graph_cutoffs=cuts)
+        model = _model(sd, cfg).eval()
+        g, b = _radius_batch([(400, 1), (150, 4)], [[4, 7], [5]])
+        gen = torch.Generator().manual_seed(17)
+        x, h = torch.randn(g.n_pharm, 3, generator=gen) * 3.0, torch.randn(g.n_pharm, 6, generator=gen)
+        com = torch.stack([b.prot_x[int(b.prot_ptr[i]):int(b.prot_ptr[i + 1])].mean(0) for i in range(b.n_graphs)])
+        prot = b.prot_x - com[b.prot_b]
+        model.dynamics.bind(g)
+        g.pharm_x.copy_(x)
+        g.pharm_h.copy_(h)
+        g.prot_x.copy_(prot)
+        b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+        tt = torch.tensor([0.3, 0.3, 0.75])
+        wh, wx = O.denoiser(sd, b, tt, cfg)
+        with torch.no_grad():
+            gh, gx = model.dynamics(g, tt, None)
+        for a_, w_, what in ((gh, wh, "eps_h"), (gx, wx, "eps_x")):
+            err = float((a_.cpu() - w_).abs().max())
+            assert err <= 1e-4 * max(float(w_.abs().max()), 1e-6) + 1e-6, (mn, what, err)
     # sampling: the second pocket alone gives bit-identical results (a graph never sees its batch neighbours)
     from pharmacoforge_b200.batch import Pocket
     from pharmacoforge_b200.synthetic import make_pocket

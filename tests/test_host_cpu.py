@@ -97,10 +97,12 @@ def test_unsupported_configs_fail_loudly():
     from pharmacoforge_b200.dynamics import PharmRecDynamicsGVP
     with pytest.raises(NotImplementedError):
         PharmRecDynamicsGVP(6, 11, vector_size=8, n_convs=2, graph_cutoffs={"ff": 9}, message_norm="mean", pf_k=5)
-    # a positive numeric message_norm (sum aggregation / norm) and pf_k = 0 (radius pf edges) are built; 0 and dicts are not
+    # a numeric message_norm (sum aggregation / norm; 0 = per-graph edges per node + 1) and pf_k = 0 (radius pf edges) are
+    # built; dicts are not (they fail in the reference's own constructor check)
     assert PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm=10, pf_k=5).message_norm == 10
-    with pytest.raises(NotImplementedError):
-        PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm=0, pf_k=5)
+    assert PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm=0, pf_k=5).message_norm == 0
+    with pytest.raises(ValueError):
+        PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm=-1, pf_k=5)
     with pytest.raises(NotImplementedError):
         PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9}, message_norm={"prot": 1, "pharm": 1}, pf_k=5)
     assert PharmRecDynamicsGVP(6, 11, n_convs=2, graph_cutoffs={"ff": 9, "pf": 8}, message_norm="mean", pf_k=0).pf_k == 0

@@ -211,11 +211,12 @@ def test_endpoint_reverse_diffusion_against_reference(golden, sd, dyn_cfg, tag, 
         assert float((h0 - t(g["s_ep__final_h"])).abs().max()) <= 2e-3
 
 
-@pytest.mark.parametrize("tag", ["n4", "n1"])
+@pytest.mark.parametrize("tag", ["n4", "n1", "n0"])
 def test_denoiser_numeric_message_norm_against_reference(golden, sd, dyn_cfg, tag):
     """message_norm = a positive number: sum aggregation divided by it (gvp.py:386-389, 512-517) -- the constructor default
-    of the reference's dynamics is 1; fixture from the reference's own code (oracle/make_golden_msgnorm.py)."""
-    d = golden("message_norm.npz")
+    of the reference's dynamics is 1; 0: divided by edges per node of the graph + 1 (:504-507), with the per-graph edge counts
+    as dynamics_gvp.py:219-221 records them.  Fixtures from the reference's own code (oracle/make_golden_msgnorm.py)."""
+    d = golden("message_norm0.npz" if tag == "n0" else "message_norm.npz")
     b = _denoiser_batch(d)
     cfg = dict(dyn_cfg, message_norm=float(d[f"{tag}__norm"]))
     trace = {}
