@@ -46,6 +46,9 @@ class Pocket:
         return pocket_to_dgl(self, graph_cutoffs)
 
 
+MAX_PHARM_PER_GRAPH = 128   # PF_MAX_PHARM_PER_GRAPH of include/pharmacoforge_b200.h
+
+
 def _chunk_graphs(weights: np.ndarray, target: int) -> np.ndarray:
     """Group consecutive graphs into planner chunks of roughly `target` edge rows (boundaries in graphs)."""
     bounds = [0]
@@ -117,6 +120,9 @@ class GraphBatch:
             graph_pocket = graph_pocket[graph_range.start:graph_range.stop]
             graph_nf = graph_nf[graph_range.start:graph_range.stop]
         B = len(graph_pocket)
+        if any(nf < 1 or nf > MAX_PHARM_PER_GRAPH for nf in graph_nf):
+            raise ValueError(f"pharmacophore sizes must be in 1..{MAX_PHARM_PER_GRAPH} (PF_MAX_PHARM_PER_GRAPH: the per-step "
+                             "graph kernel keeps a graph's centres in shared memory)")
         used = sorted(set(graph_pocket))
         remap = {p: i for i, p in enumerate(used)}
         graph_pocket = np.asarray([remap[p] for p in graph_pocket], dtype=np.int64)

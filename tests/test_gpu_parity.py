@@ -1126,3 +1126,30 @@ def test_fp16_single_pass_denoiser_and_sampling(env, golden):
         assert dx < 0.25 and dh < 0.25, (dx, dh)
     finally:
         dyn.edge_mlp_precision = "fp32"
+
+
+def test_edge_cases_max_size_graph_and_empty_size_lists(env):
+    """Limits of the batch layout: a graph with PF_MAX_PHARM_PER_GRAPH = 128 centres (ff in-degree 127, one full tile) next to a
+    one-centre graph through the fused denoiser against the oracle; 129 centres are refused on the host; a pocket with an empty
+    size list contributes no graph and `sample` regroups around it (pharmacodiff.py:538-576)."""
+    g, b = env.build([(400, 0), (40, 3)], [[128, 1], [2]])
+    x, h, prot = random_state(b, 31, 2.5)
+    env.set_state(g, b, x.cuda(), h.cuda(), prot.cuda())
+    b.pharm_x, b.pharm_h, b.prot_x = x, h, prot
+    tt = torch.tensor([0.4, 0.4, 0.9])
+    wh, wx = env.O.denoiser(env.sd, b, tt, env.cfg)
+    gh, gx = env.model.dynamics(g, tt, None)
+    close(gh, wh, what="eps_h (128 centres)")
+    close(gx, wx, what="eps_x (128 centres)")
+    assert int(g.ff_cnt.max()) == 127
+    with pytest.raises(ValueError):
+        env.build([(400, 0)], [[129]])
+    pockets = [env.Pocket.from_numpy(*env.make_pocket(n, seed=s)) for n, s in ((120, 1), (90, 2), (60, 3))]
+    sizes = [[3, 4], [], [5]]
+    noise = torch.randn(6, 12, 9, generator=torch.Generator().manual_seed(2))
+    out = env.model.sample(pockets, sizes, max_batch_size=2, noise=noise, n_steps=5)
+    assert [len(o) for o in out] == [2, 0, 1] and [p.n_ph_centers for o in out for p in o] == [3, 4, 5]
+    # the same graphs without the empty pocket: identical samples
+    out2 = env.model.sample([pockets[0], pockets[2]], [[3, 4], [5]], max_batch_size=2, noise=noise, n_steps=5)
+    for a_, b_ in zip([p for o in out for p in o], [p for o in out2 for p in o]):
+        assert torch.equal(a_.ph_coords, b_.ph_coords) and torch.equal(a_.ph_feats, b_.ph_feats)
