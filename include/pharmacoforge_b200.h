@@ -455,7 +455,8 @@ size_t pf_sample_args_size(void); /* sizeof(PfSampleArgs), for binding self-chec
  * Vectors are component-major [rows][3][channels].  Kernels whose name says `accumulate` / `+=` add into the output. */
 /* C[M][N] (ldc) (+)= A(m,k) B(k,n) (+ bias[n]); A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs]: nn.Linear forward
  * (gvp.py:76-79, 84), its dgrad and wgrad, and the Wh / Wu contractions (gvp.py:99-100).  split_k > 1 splits K over
- * CTAs (atomic accumulation: the wgrad reductions over all edges). */
+ * CTAs (the wgrad reductions over all edges); this entry point has no workspace and accumulates the splits with atomicAdd
+ * (order-dependent rounding) -- pf_train_gemm with a training workspace reduces them deterministically. */
 int pf_train_sgemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                    int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate, int32_t split_k,
                    void* stream);
@@ -472,7 +473,16 @@ int pf_tc_gemm(const float* A, const float* B, const float* bias, float* C, int3
 int pf_train_gemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                   int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate, int32_t split_k,
                   void* workspace, size_t workspace_bytes, void* stream);
-int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* stream); /* out[n] += sum_m x[m][n] (bias grad) */
+/* The TRAINING WORKSPACE (one per device and stream, caller-owned): pf_train_workspace_bytes() bytes, ZERO-FILLED once
+ * before its first use.  Its front holds the partials of every reduction that is split over CTAs -- split-K weight
+ * gradients (tensor-core and FFMA kernels: a second launch adds the splits up in split order), bias column sums and
+ * LayerNorm affine gradients (the last CTA to arrive adds the CTAs' partials in CTA order; ticket counters in the last
+ * PF_TRAIN_WS_TAIL bytes, which every call leaves at zero) -- so the gradients are bit-identical from run to run: no
+ * atomics on floating-point data.  workspace == NULL selects the atomicAdd fallbacks. */
+#define PF_TRAIN_WS_TAIL 16384
+size_t pf_train_workspace_bytes(void);
+/* out[n] += sum_m x[m][n] (bias gradient) */
+int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* workspace, size_t workspace_bytes, void* stream);
 /* SiLU (gvp.py:78): dy == NULL -> out = silu(x); else out = dy * silu'(x) */
 int pf_train_silu(const float* x, const float* dy, float* out, int64_t n, void* stream);
 /* vector gating (gvp.py:108-114): dout == NULL -> out = act(gate) * Vu; else dgate (in out_or_dgate) and dVu */
@@ -484,12 +494,17 @@ int pf_train_vecnorm(const float* vh, const float* dsh, float* out, int64_t rows
 int pf_train_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int64_t rows,
                            int32_t D, void* stream);
 int pf_train_layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, float* dx, float* dw,
-                           float* db, int64_t rows, int32_t D, void* stream); /* dw, db += */
+                           float* db, int64_t rows, int32_t D, void* workspace, size_t workspace_bytes,
+                           void* stream); /* dw, db += */
 /* vector half of GVPLayerNorm (gvp.py:163-165): dout == NULL -> out = v / vn; else out = dv */
 int pf_train_vecln(const float* v, const float* dout, float* out, int64_t rows, int32_t U, void* stream);
 /* edges.src[...] (gvp.py:543-545): backward == 0 -> out[e] = x[idx[e]]; else dx[idx[e]] += dout[e] (atomic) */
 int pf_train_gather(const float* x_or_dout, const int32_t* idx, float* out_or_dx, int64_t E, int32_t D, int32_t backward,
                     void* stream);
+/* the backward without atomics: perm = the edges grouped by source row (a stable sort of idx), row n owns
+ * perm[ptr[n] .. ptr[n+1]); dx[n] = sum of dout[perm[e]] in that order (dx is written, not accumulated) */
+int pf_train_gather_bwd_sorted(const float* dout, const int32_t* perm, const int32_t* ptr, float* dx, int64_t n_rows,
+                               int32_t D, void* stream);
 /* fn.mean per destination + cross-etype sum (gvp.py:488-497) over destination-sorted message rows: segment s = rows
  * [ptr[s], ptr[s+1]) -> node seg_dst[s] (NULL: s).  backward == 0 -> out[node] += mean; else dmsg[row] = dout[node]/cnt */
 int pf_train_segmean(const float* msg_or_dout, const int32_t* ptr, const int32_t* seg_dst, float* out_or_dmsg,

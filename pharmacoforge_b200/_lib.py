@@ -88,13 +88,15 @@ SIGNATURES = {
     "pf_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32]),
     "pf_train_sgemm": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                  C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, STREAM]),
-    "pf_train_colsum": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
+    "pf_train_colsum": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_void_p, C.c_size_t, STREAM]),
+    "pf_train_workspace_bytes": (C.c_size_t, []),
+    "pf_train_gather_bwd_sorted": (C.c_int, [c_f32p, c_i32p, c_i32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
     "pf_train_silu": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, STREAM]),
     "pf_train_gate": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, STREAM]),
     "pf_train_vecnorm": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
     "pf_train_layernorm_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
     "pf_train_layernorm_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32,
-                                         STREAM]),
+                                         C.c_void_p, C.c_size_t, STREAM]),
     "pf_train_vecln": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, STREAM]),
     "pf_train_gather": (C.c_int, [c_f32p, c_i32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, STREAM]),
     "pf_train_segmean": (C.c_int, [c_f32p, c_i32p, c_i32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, STREAM]),

@@ -9,6 +9,73 @@
 namespace pf {
 namespace train {
 
+// ------------------------------------------------------------------------------------------------ deterministic reductions
+// Reductions that are split over CTAs park one partial per CTA in the caller's workspace and add the partials up in a FIXED
+// order, so the result does not depend on the order the CTAs ran in (run-to-run bit-identical gradients): the split-K weight
+// gradients through a second small launch (splitk_reduce_kernel, in place of the memset the atomic form needs), the column
+// sums and LayerNorm affine gradients inside the same launch by the LAST CTA to arrive (a ticket counter per output block in
+// the zeroed tail of the workspace, reset by that CTA).  Without a workspace the kernels fall back to atomicAdd into a
+// zeroed output (pf_train_sgemm's legacy behaviour).
+constexpr int kWsTailBytes = PF_TRAIN_WS_TAIL;                 // zeroed ticket counters at the END of the workspace
+constexpr int kWsCounters = kWsTailBytes / (int)sizeof(unsigned);
+struct SplitWs {
+  float* part;         // partials (nullptr: atomic fallback)
+  unsigned* counters;  // [kWsCounters], all zero between calls
+};
+// sum of q[z * stride] over z = first, first + step, ... < n in a FIXED association: four running sums over every fourth term,
+// combined as (a0 + a1) + (a2 + a3) -- independent loads in flight, the same result whatever order the CTAs ran in
+__device__ __forceinline__ float ordered_sum(const float* q, size_t stride, int first, int step, int n) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int z = first;
+  for (; z + 3 * step < n; z += 4 * step) {
+    const float x0 = __ldcg(q + (size_t)z * stride), x1 = __ldcg(q + (size_t)(z + step) * stride);
+    const float x2 = __ldcg(q + (size_t)(z + 2 * step) * stride), x3 = __ldcg(q + (size_t)(z + 3 * step) * stride);
+    a0 += x0;
+    a1 += x1;
+    a2 += x2;
+    a3 += x3;
+  }
+  for (; z < n; z += step) a0 += __ldcg(q + (size_t)z * stride);
+  return (a0 + a1) + (a2 + a3);
+}
+// Second stage of a split-K GEMM: C (+)= sum over the splits of the row-major partial tiles part[split][tile][TM][TN] (+ bias).
+// One warp per output element: lane l adds splits l, l + 32, ... in order, then a fixed xor tree over the lanes -- the result
+// does not depend on the order the first stage's CTAs ran in.  (A last-CTA-per-tile reduction inside the GEMM kernel was
+// measured first: one CTA adding 592 x 289 partials is latency-bound at 40-60 us; this launch replaces the memset of C that
+// the atomic form needs, so the launch count is the same.)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int n_splits, int TM, int TN,
+                                                            int tiles_x, int n_tiles, const float* __restrict__ bias,
+                                                            float* __restrict__ C, int M, int N, int ldc, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= (long long)M * N) return;
+  const int gm = (int)(o / N), gn = (int)(o - (long long)gm * N);
+  const int tile = (gm / TM) * tiles_x + gn / TN;
+  const float* q = part + (size_t)tile * (TM * TN) + (gm % TM) * TN + gn % TN;
+  float v = ordered_sum(q, (size_t)n_tiles * (TM * TN), lane, 32, n_splits);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane == 0) {
+    if (bias != nullptr) v += bias[gn];
+    float* out = C + (size_t)gm * ldc + gn;
+    *out = accumulate ? *out + v : v;
+  }
+}
+// returns true in every thread of the LAST CTA of `tile` (of `n_splits`) once all partials are visible
+__device__ __forceinline__ bool last_cta_of_tile(unsigned* counters, int tile, int n_splits) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counters + tile, 1u);
+    s_last = prev == (unsigned)(n_splits - 1);
+    if (s_last) counters[tile] = 0;   // nobody else touches this counter before the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
 // ------------------------------------------------------------------------------------------------ strided SGEMM
 // C[M][N] (row-major, ldc) (+)= A(m, k) * B(k, n) (+ bias[n]); A(m, k) = A[m * a_rs + k * a_cs], B(k, n) = B[k * b_rs +
 // n * b_cs].  One kernel covers y = x W^T + b, dx = dy W and dW = dy^T x.  K step 16, 256 threads, 128 x 128 tiles with
@@ -19,7 +86,7 @@ template <int TM, int TN, int R>  // TM x TN tile, R x R outputs per thread, (TM
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                     const float* __restrict__ bias, float* __restrict__ C, int M, int N,
                                                     int K, long long a_rs, long long a_cs, long long b_rs,
-                                                    long long b_cs, int ldc, int accumulate, int k_chunk) {
+                                                    long long b_cs, int ldc, int accumulate, int k_chunk, SplitWs ws) {
   static_assert((TM / R) * (TN / R) == 256 && R % 4 == 0, "tile shape");
   __shared__ __align__(16) float sA[kTK][TM + 4];
   __shared__ __align__(16) float sB[kTK][TN + 4];
@@ -61,6 +128,18 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     }
     __syncthreads();
   }
+  if (gridDim.z > 1 && ws.part != nullptr) {
+    // deterministic split-K, first stage: this split's partial tile, row-major; splitk_reduce_kernel adds the splits up
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x, n_tiles = gridDim.x * gridDim.y;
+    float* mine = ws.part + ((size_t)blockIdx.z * n_tiles + tile) * (TM * TN);
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < R; j += 4)
+        if (m0 + tm + i < M && n0 + tn + j < N)   // only the part of the tile that exists is ever read back
+          *reinterpret_cast<float4*>(mine + (tm + i) * TN + tn + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     const int gm = m0 + tm + i;
@@ -89,7 +168,7 @@ template <int TM, int TN>
 __global__ void __launch_bounds__(256, 2) sgemm_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                          const float* __restrict__ bias, float* __restrict__ C, int M,
                                                          int N, int K, long long a_rs, long long a_cs, long long b_rs,
-                                                         long long b_cs, int ldc, int accumulate, int k_chunk) {
+                                                         long long b_cs, int ldc, int accumulate, int k_chunk, SplitWs ws) {
   constexpr int TK = 8, RM = TM / 16, RN = TN / 16, LA = TM * TK / 256, LB = TN * TK / 256;
   static_assert((RM == 4 || RM == 8) && (RN == 4 || RN == 8), "tile shape");
   __shared__ __align__(16) float sA[2][TK][TM + 4];
@@ -157,6 +236,21 @@ __global__ void __launch_bounds__(256, 2) sgemm_pipe_kernel(const float* __restr
     if (t + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
   }
+  if (gridDim.z > 1 && ws.part != nullptr) {   // deterministic split-K, first stage (see sgemm_kernel)
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x, n_tiles = gridDim.x * gridDim.y;
+    float* mine = ws.part + ((size_t)blockIdx.z * n_tiles + tile) * (TM * TN);
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const int r = (i / 4) * (TM / 2) + ty * 4 + (i & 3);
+#pragma unroll
+      for (int j4 = 0; j4 < RN; j4 += 4) {
+        const int c = (j4 / 4) * (TN / 2) + tx * 4;
+        if (m0 + r < M && n0 + c < N)
+          *reinterpret_cast<float4*>(mine + r * TN + c) = make_float4(acc[i][j4], acc[i][j4 + 1], acc[i][j4 + 2], acc[i][j4 + 3]);
+      }
+    }
+    return;
+  }
   const bool vec = gridDim.z == 1 && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
 #pragma unroll
   for (int i = 0; i < RM; ++i) {
@@ -196,15 +290,41 @@ __global__ void __launch_bounds__(256, 2) sgemm_pipe_kernel(const float* __restr
   }
 }
 
-// column sums of a row-major [M][N] matrix (bias gradients), accumulated with atomicAdd into out[N]
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// column sums of a row-major [M][N] matrix (bias gradients): out[n] += sum_m x[m][n].  256 threads = 32 columns x 8 row lanes,
+// gridDim.y row chunks: lane j adds rows r0 + j, r0 + j + 8, ... in order, the lanes are added in lane order.  With a workspace
+// the chunks' partial sums go to part[chunk][column] and the last CTA of each column block adds them the same way (8 chunk
+// lanes, lane order) -- deterministic; without one, atomicAdd.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N,
+                                                     SplitWs ws) {
+  __shared__ float s_p[8][32];
+  const int cx = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + cx;
   const long long rows_per = (M + gridDim.y - 1) / gridDim.y;
   const long long r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
   float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += x[r * N + n];
-  atomicAdd(out + n, s);
+  if (n < N)
+    for (long long r = r0 + j; r < r1; r += 8) s += x[r * N + n];
+  s_p[j][cx] = s;
+  __syncthreads();
+  if (j == 0) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += s_p[q][cx];
+    if (ws.part == nullptr) {
+      if (n < N) atomicAdd(out + n, s);
+    } else {
+      ws.part[(size_t)blockIdx.y * (gridDim.x * 32) + n] = s;
+    }
+  }
+  if (ws.part == nullptr) return;
+  if (!last_cta_of_tile(ws.counters, blockIdx.x, gridDim.y)) return;
+  s_p[j][cx] = ordered_sum(ws.part + n, (size_t)gridDim.x * 32, j, 8, gridDim.y);
+  __syncthreads();
+  if (j == 0 && n < N) {
+    float v = s_p[0][cx];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) v += s_p[q][cx];
+    out[n] += v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise
@@ -307,7 +427,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
     stats[2 * r + 1] = rstd;
   }
 }
-// dx per row; dw / db accumulated over rows with atomicAdd (one partial per warp-row)
+// dx per row; dw / db accumulated over rows with atomicAdd (one partial per warp-row): the fallback without a workspace
 __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                      const float* __restrict__ stats, const float* __restrict__ dy,
                                      float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
@@ -332,6 +452,62 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
     dx[r * D + i] = rstd * (dy[r * D + i] * w[i] - s1 - xh * s2);
   }
 }
+// The same with deterministic dw / db (D <= 128): a CTA of 8 warps owns kLnRows consecutive rows (an argument), each warp sums its rows'
+// contributions in row order (4 columns per lane), the warps' sums are added in warp order, the CTA's partial goes to the
+// workspace and the last CTA adds the partials in CTA order: dw[i] += ..., db[i] += ... exactly once.
+__global__ void __launch_bounds__(256) layernorm_bwd_det_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ stats, const float* __restrict__ dy,
+                                                                float* __restrict__ dx, float* __restrict__ dw,
+                                                                float* __restrict__ db, long long rows, int D,
+                                                                int kLnRows, SplitWs ws) {
+  __shared__ float s_w[8][2][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long rbase = (long long)blockIdx.x * kLnRows;
+  for (int rr = warp; rr < kLnRows; rr += 8) {
+    const long long r = rbase + rr;
+    if (r >= rows) break;
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    float xh[4], dyv[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = lane + 32 * j;
+      xh[j] = dyv[j] = 0.f;
+      if (i < D) {
+        xh[j] = (x[r * D + i] - mean) * rstd;
+        dyv[j] = dy[r * D + i];
+        const float g = dyv[j] * w[i];
+        s1 += g;
+        s2 = fmaf(g, xh[j], s2);
+        aw[j] = fmaf(dyv[j], xh[j], aw[j]);
+        ab[j] += dyv[j];
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = lane + 32 * j;
+      if (i < D) dx[r * D + i] = rstd * (dyv[j] * w[i] - s1 - xh[j] * s2);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s_w[warp][0][lane + 32 * j] = aw[j];
+    s_w[warp][1][lane + 32 * j] = ab[j];
+  }
+  __syncthreads();
+  const int which = threadIdx.x >> 7, col = threadIdx.x & 127;   // 256 threads = (dw | db) x 128 columns
+  float v = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v += s_w[q][which][col];
+  ws.part[(size_t)blockIdx.x * 256 + threadIdx.x] = v;
+  if (!last_cta_of_tile(ws.counters, 0, gridDim.x)) return;
+  if (col >= D) return;
+  float* o = which ? db : dw;
+  o[col] += ordered_sum(ws.part + threadIdx.x, 256, 0, 1, gridDim.x);
+}
+
 
 // GVPLayerNorm on vectors (gvp.py:163-165): out = v / vn, vn = sqrt(mean_u(max(|v_u|^2, 1e-8)) + 1e-5) + 1e-5.
 // One thread per row ([3][U], U <= 32).
@@ -387,6 +563,18 @@ __global__ void gather_bwd_kernel(const float* __restrict__ dout, const int* __r
   const long long e = i / D;
   atomicAdd(dx + (long long)idx[e] * D + (i % D), dout[i]);
 }
+// deterministic form of gather_bwd: perm lists the edges grouped by source row (a stable sort of idx), row n owns
+// perm[ptr[n] .. ptr[n + 1]); one thread per (row, column) adds its edges' gradients in that order and WRITES dx
+__global__ void gather_bwd_sorted_kernel(const float* __restrict__ dout, const int* __restrict__ perm,
+                                         const int* __restrict__ ptr, float* __restrict__ dx, long long n_rows, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * D) return;
+  const long long n = i / D;
+  const int d = (int)(i % D);
+  float acc = 0.f;
+  for (int e = ptr[n]; e < ptr[n + 1]; ++e) acc += dout[(long long)perm[e] * D + d];
+  dx[i] = acc;
+}
 // mean of the message rows of every destination (fn.mean + cross_reducer sum, gvp.py:488-497): edges are sorted by
 // destination, segment s = rows [ptr[s], ptr[s+1]) aggregates onto node seg_dst[s] (or s); out is ACCUMULATED into.
 __global__ void segmean_fwd_kernel(const float* __restrict__ msg, const int* __restrict__ ptr,
@@ -441,60 +629,87 @@ namespace T = pf::train;
 
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
-extern "C" int pf_train_sgemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
-                              int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate,
-                              int32_t split_k, void* stream) {
+// workspace -> (partials, ticket counters) when it holds `need_floats` partials in front of its zeroed tail and the launch
+// needs at most kWsCounters tickets; {nullptr, nullptr} (atomic fallback) otherwise
+extern "C" size_t pf_train_workspace_bytes(void) { return pf_tc_gemm_workspace_bytes(128, 176, 0) + PF_TRAIN_WS_TAIL; }
+
+static T::SplitWs split_ws(void* workspace, size_t workspace_bytes, size_t need_floats, long long tickets) {
+  if (workspace == nullptr || workspace_bytes < (size_t)T::kWsTailBytes + need_floats * sizeof(float) || tickets > T::kWsCounters)
+    return T::SplitWs{nullptr, nullptr};
+  return T::SplitWs{static_cast<float*>(workspace),
+                    reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + workspace_bytes - T::kWsTailBytes)};
+}
+
+static int sgemm_impl(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                      int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate,
+                      int32_t split_k, void* workspace, size_t workspace_bytes, void* stream) {
   PF_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0 && ldc >= N, "pf_train_sgemm: arguments");
   if (M == 0 || N == 0) return PF_OK;
   int splits = split_k < 1 ? 1 : split_k;
   int chunk = ((K + splits - 1) / splits + T::kTK - 1) / T::kTK * T::kTK;
   if (chunk < T::kTK) chunk = T::kTK;
   splits = K > 0 ? (K + chunk - 1) / chunk : 1;
-  if (splits > 1 && !accumulate) {
-    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, as_stream(stream));
-    if (e != cudaSuccess) {
-      set_error("pf_train_sgemm: memset: %s", cudaGetErrorString(e));
-      return PF_ERR_LAUNCH;
-    }
-  }
   // Shape dispatch: the pipelined 8 x 8 (or 8 x 4 / 4 x 8) kernel for the GEMMs with at least ~100 columns and rows (the
   // scalar Linear of every GVP: forward, dgrad, wgrad), the single-stage 64 x 64 kernel for the skinny vector-channel
   // contractions (N = 16 / 17 / 32 over 3E rows), which are memory-bound and measured slower on large tiles.
   const long long work = (long long)M * N;
-  if (N >= 96 && M >= 96 && work >= (1 << 16)) {
-    const bool wide_n = N > 64 && (N % 128 == 0 || N % 128 > 64);   // 161 -> 3 x 64, 128 / 144 -> 128-wide tiles
-    const bool wide_m = M > 64 && (M % 128 == 0 || M % 128 > 64 || M >= 1024);
-    if (wide_m && wide_n) {
-      dim3 grid((N + 127) / 128, (M + 127) / 128, splits);
-      T::sgemm_pipe_kernel<128, 128><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
-                                                                         ldc, accumulate, chunk);
-    } else if (wide_m) {
-      dim3 grid((N + 63) / 64, (M + 127) / 128, splits);
-      T::sgemm_pipe_kernel<128, 64><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
-                                                                        ldc, accumulate, chunk);
-    } else {
-      dim3 grid((N + 127) / 128, (M + 63) / 64, splits);
-      T::sgemm_pipe_kernel<64, 128><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
-                                                                        ldc, accumulate, chunk);
+  const bool pipe = N >= 96 && M >= 96 && work >= (1 << 16);
+  const bool wide_n = N > 64 && (N % 128 == 0 || N % 128 > 64);   // 161 -> 3 x 64, 128 / 144 -> 128-wide tiles
+  const bool wide_m = M > 64 && (M % 128 == 0 || M % 128 > 64 || M >= 1024);
+  const int TM = pipe ? (wide_m ? 128 : 64) : 64, TN = pipe ? ((wide_m && !wide_n) ? 64 : 128) : 64;
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
+  // split-K: deterministic in-kernel reduction through the workspace when it fits, else atomicAdd into a zeroed C
+  T::SplitWs ws{nullptr, nullptr};
+  if (splits > 1) {
+    ws = split_ws(workspace, workspace_bytes, (size_t)splits * grid.x * grid.y * TM * TN, 0);   // two launches, no tickets
+    if (ws.part == nullptr && !accumulate) {
+      cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, as_stream(stream));
+      if (e != cudaSuccess) {
+        set_error("pf_train_sgemm: memset: %s", cudaGetErrorString(e));
+        return PF_ERR_LAUNCH;
+      }
     }
+  }
+  if (pipe) {
+    if (wide_m && wide_n)
+      T::sgemm_pipe_kernel<128, 128><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
+                                                                         ldc, accumulate, chunk, ws);
+    else if (wide_m)
+      T::sgemm_pipe_kernel<128, 64><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
+                                                                        ldc, accumulate, chunk, ws);
+    else
+      T::sgemm_pipe_kernel<64, 128><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs,
+                                                                        ldc, accumulate, chunk, ws);
   } else {
-    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
     T::sgemm_kernel<64, 64, 4><<<grid, 256, 0, as_stream(stream)>>>(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc,
-                                                                   accumulate, chunk);
+                                                                   accumulate, chunk, ws);
   }
   PF_CHECK_LAUNCH("pf_train_sgemm");
+  if (ws.part != nullptr) {
+    const long long n_out = (long long)M * N;
+    T::splitk_reduce_kernel<<<(unsigned)((n_out + 7) / 8), 256, 0, as_stream(stream)>>>(
+        ws.part, splits, TM, TN, (int)grid.x, (int)(grid.x * grid.y), bias, C, M, N, ldc, accumulate);
+    PF_CHECK_LAUNCH("pf_train_sgemm (split-K reduce)");
+  }
   return PF_OK;
 }
 
-extern "C" int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* stream) {
+extern "C" int pf_train_sgemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                              int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int32_t ldc, int32_t accumulate,
+                              int32_t split_k, void* stream) {
+  return sgemm_impl(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, nullptr, 0, stream);
+}
+
+extern "C" int pf_train_colsum(const float* x, float* out, int64_t M, int32_t N, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   PF_CHECK_ARG(x && out && M >= 0 && N > 0, "pf_train_colsum: arguments");
   if (M == 0) return PF_OK;
-  // rows are split over many CTAs (about 256 rows each): the reduction is bandwidth-trivial but latency-bound per thread
-  const long long want = (M + 255) / 256;
+  // rows are split over many CTAs (about 1024 rows = 128 per row lane each): bandwidth-trivial, latency-bound per thread
+  const long long want = (M + 1023) / 1024;
   const int ysplit = (int)(want > 2048 ? 2048 : (want > 0 ? want : 1));
-  const int tx = N >= 128 ? 128 : 32;
-  dim3 grid((N + tx - 1) / tx, ysplit);
-  T::colsum_kernel<<<grid, tx, 0, as_stream(stream)>>>(x, out, M, N);
+  dim3 grid((N + 31) / 32, ysplit);
+  const T::SplitWs ws = split_ws(workspace, workspace_bytes, (size_t)ysplit * grid.x * 32, grid.x);
+  T::colsum_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, out, M, N, ws);
   PF_CHECK_LAUNCH("pf_train_colsum");
   return PF_OK;
 }
@@ -546,10 +761,19 @@ extern "C" int pf_train_layernorm_fwd(const float* x, const float* w, const floa
   return PF_OK;
 }
 extern "C" int pf_train_layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, float* dx,
-                                      float* dw, float* db, int64_t rows, int32_t D, void* stream) {
+                                      float* dw, float* db, int64_t rows, int32_t D, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
   PF_CHECK_ARG(x && w && stats && dy && dx && dw && db && rows >= 0 && D > 0, "pf_train_layernorm_bwd: arguments");
   if (rows == 0) return PF_OK;
-  T::layernorm_bwd_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(x, w, stats, dy, dx, dw, db, rows, D);
+  // deterministic dw / db: at most ~300 CTAs of at least 128 rows, one 256-float partial each
+  long long per = (rows + 295) / 296;
+  per = per < 128 ? 128 : (per + 7) / 8 * 8;
+  const long long ctas = (rows + per - 1) / per;
+  const T::SplitWs ws = D <= 128 ? split_ws(workspace, workspace_bytes, (size_t)ctas * 256, 1) : T::SplitWs{nullptr, nullptr};
+  if (ws.part != nullptr)
+    T::layernorm_bwd_det_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(x, w, stats, dy, dx, dw, db, rows, D, (int)per, ws);
+  else
+    T::layernorm_bwd_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(x, w, stats, dy, dx, dw, db, rows, D);
   PF_CHECK_LAUNCH("pf_train_layernorm_bwd");
   return PF_OK;
 }
@@ -574,6 +798,15 @@ extern "C" int pf_train_gather(const float* x_or_dout, const int32_t* idx, float
   else
     T::gather_bwd_kernel<<<blocks_for(E * D, 256), 256, 0, as_stream(stream)>>>(x_or_dout, idx, out_or_dx, E, D);
   PF_CHECK_LAUNCH("pf_train_gather");
+  return PF_OK;
+}
+
+extern "C" int pf_train_gather_bwd_sorted(const float* dout, const int32_t* perm, const int32_t* ptr, float* dx,
+                                          int64_t n_rows, int32_t D, void* stream) {
+  PF_CHECK_ARG(dout && perm && ptr && dx && n_rows >= 0 && D > 0, "pf_train_gather_bwd_sorted: arguments");
+  if (n_rows == 0) return PF_OK;
+  T::gather_bwd_sorted_kernel<<<blocks_for(n_rows * D, 256), 256, 0, as_stream(stream)>>>(dout, perm, ptr, dx, n_rows, D);
+  PF_CHECK_LAUNCH("pf_train_gather_bwd_sorted");
   return PF_OK;
 }
 
@@ -625,7 +858,7 @@ static int sgemm_ld(const float* A, const float* B, const float* bias, float* C,
     return pf_tc_gemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, ws.ptr, ws.bytes, stream);
   if (tc_ok && K >= 16384 && M <= 128 && M >= 64 && N >= 64 && bias == nullptr && ws.bytes >= pf_tc_gemm_workspace_bytes(M, N, K))
     return pf_tc_gemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, ws.ptr, ws.bytes, stream);
-  return pf_train_sgemm(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, stream);
+  return sgemm_impl(A, B, bias, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, accumulate, split_k, ws.ptr, ws.bytes, stream);
 }
 
 extern "C" int pf_train_gemm(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
@@ -698,7 +931,7 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(gate)");
   // gates = f Wg^T + bg
   if ((rc = sgemm_ld(dgates, f, nullptr, dWg, vo, no, Mi, 1, vo, no, 1, no, 0, wgrad_splits(M, vo, no), stream, ws)) != PF_OK) return rc;  // dWg = dgates^T f
-  if ((rc = pf_train_colsum(dgates, dbg, M, vo, stream)) != PF_OK) return rc;
+  if ((rc = pf_train_colsum(dgates, dbg, M, vo, ws.ptr, ws.bytes, stream)) != PF_OK) return rc;
   cudaError_t e = cudaMemcpyAsync(dfz, df_out, (size_t)M * no * 4, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) {
     set_error("pf_train_gvp_bwd: copy: %s", cudaGetErrorString(e));
@@ -709,7 +942,7 @@ extern "C" int pf_train_gvp_bwd(const float* vec, const float* Wh, const float* 
   PF_CHECK_LAUNCH("pf_train_gvp_bwd(silu)");
   // z = s Wf^T + bf
   if ((rc = sgemm_ld(dfz, s, nullptr, dWf, no, K, Mi, 1, no, K, 1, K, 0, wgrad_splits(M, no, K), stream, ws)) != PF_OK) return rc;       // dWf = dz^T s
-  if ((rc = pf_train_colsum(dfz, dbf, M, no, stream)) != PF_OK) return rc;
+  if ((rc = pf_train_colsum(dfz, dbf, M, no, ws.ptr, ws.bytes, stream)) != PF_OK) return rc;
   if ((rc = sgemm_ld(dfz, Wf, nullptr, ds, Mi, K, no, no, 1, K, 1, K, 0, 1, stream, ws)) != PF_OK) return rc;        // ds = dz Wf
   e = cudaMemcpy2DAsync(dfeats, (size_t)n * 4, ds, (size_t)K * 4, (size_t)n * 4, (size_t)M, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) {

@@ -61,7 +61,9 @@ class MessageChain(torch.autograd.Function):
     destination (fn.mean, gvp.py:488-497).  (h_src [Ns,128], v_src [Ns,3,16]) -> (a_h [Nd,128], a_v [Nd,3,16])."""
 
     @staticmethod
-    def forward(ctx, h_src, v_src, xd, rbf, src, ptr, seg_dst, n_dst: int, acts: Tuple[bool, ...], *params):
+    def forward(ctx, h_src, v_src, xd, rbf, src, ptr, seg_dst, n_dst: int, acts: Tuple[bool, ...], src_sorted, *params):
+        # src_sorted = T.sort_by_row(src, n_src) or None: the edges grouped by source row, for the deterministic scatter of
+        # the gather's backward (computed once per edge type and step by train_graph.build_edges)
         gh, gv = T.gather(h_src, src), T.gather(v_src, src)
         sca = torch.cat([gh, rbf], dim=1)                                   # gvp.py:545
         vec = torch.cat([xd.unsqueeze(2), gv], dim=2)                       # gvp.py:543
@@ -70,6 +72,7 @@ class MessageChain(torch.autograd.Function):
         a_v = T.segmean(vec, ptr, seg_dst, n_dst)
         ctx.acts, ctx.n_src, ctx.n_edges, ctx.has_dst = acts, h_src.shape[0], src.numel(), seg_dst is not None
         ctx.n_h = h_src.shape[1]
+        ctx.src_sorted = src_sorted
         idx = (src, ptr, seg_dst) if seg_dst is not None else (src, ptr)
         ctx.save_for_backward(*idx, *params, *_flatten_tape(tape))
         ctx.n_idx, ctx.n_params = len(idx), len(params)
@@ -89,11 +92,12 @@ class MessageChain(torch.autograd.Function):
               else torch.zeros(vout_shape, device=f_last.device))
         df, dv, grads = _gvp_chain_bwd(df, dv, params, ctx.acts, tape)
         dh_src = dv_src = None
+        perm, sptr = ctx.src_sorted if ctx.src_sorted is not None else T.sort_by_row(src, ctx.n_src)
         if ctx.needs_input_grad[0]:
-            dh_src = T.gather_bwd(df[:, :ctx.n_h].contiguous(), src, ctx.n_src)
+            dh_src = T.gather_bwd(df[:, :ctx.n_h].contiguous(), src, ctx.n_src, perm, sptr)
         if ctx.needs_input_grad[1]:
-            dv_src = T.gather_bwd(dv[:, :, 1:].contiguous(), src, ctx.n_src)
-        return (dh_src, dv_src, None, None, None, None, None, None, None, *grads)
+            dv_src = T.gather_bwd(dv[:, :, 1:].contiguous(), src, ctx.n_src, perm, sptr)
+        return (dh_src, dv_src, None, None, None, None, None, None, None, None, *grads)
 
 
 class NodeUpdate(torch.autograd.Function):
@@ -180,7 +184,7 @@ def _params(gvps) -> Tuple[torch.Tensor, ...]:
 
 def message_chain(gvps, h_src, v_src, xd, rbf, e):
     return MessageChain.apply(h_src, v_src, xd, rbf, e["src"], e["ptr"], e["seg_dst"], e["n_dst"], _acts(gvps),
-                              *_params(gvps))
+                              e.get("src_sorted"), *_params(gvps))
 
 
 def node_update(conv, nt: str, h, v, m_h, m_v, training: bool):

@@ -197,6 +197,14 @@ def dynamics_forward(dyn, g: GraphBatch, t: torch.Tensor, training: bool = True)
                       g.ff_start, g.ff_cnt, g.ff_col, g.pf_cnt, g.pf_col, g.fp_seg_dst, g.fp_seg_start, g.fp_seg_cnt,
                       g.fp_col, g.status, int(dyn.ff_k))
     edges = build_edges(g)
+    for name, e in edges.items():   # edges grouped by source row: the deterministic scatter of the gather's backward
+        n_src = g.n_prot if e["src_nt"] == "prot" else g.n_pharm
+        if name == "pp":            # static graph: sorted once per batch
+            if getattr(g, "_pp_src_sorted", None) is None:
+                g._pp_src_sorted = T.sort_by_row(e["src"], n_src)
+            e["src_sorted"] = g._pp_src_sorted
+        else:
+            e["src_sorted"] = T.sort_by_row(e["src"], n_src)
     if dyn.message_norm == 0:
         norm0 = degree_norms(g, edges)
         for e in edges.values():

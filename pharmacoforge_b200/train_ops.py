@@ -24,14 +24,16 @@ _WS = {}
 
 
 def _workspace(device):
-    """Scratch of the tensor-core GEMMs (split-K partials of the weight gradients), one per device.  PF_TRAIN_GEMM=ffma
-    disables the tensor-core kernel (A/B switch: every contraction then runs on the fp32 FFMA kernels)."""
+    """The training workspace (see pf_train_workspace_bytes in the header), one per device: partials of every reduction that
+    is split over CTAs (split-K weight gradients, bias column sums, LayerNorm affine gradients) and, in its zeroed tail, the
+    ticket counters of their deterministic last-CTA reductions.  PF_TRAIN_GEMM=ffma disables the tensor-core kernel AND the
+    workspace (A/B switch: every contraction on the fp32 FFMA kernels, split reductions through atomicAdd)."""
     import os
     if os.environ.get("PF_TRAIN_GEMM", "tc") == "ffma":
         return None
     ws = _WS.get(device)
     if ws is None:
-        ws = _WS[device] = torch.empty(_L.pf_tc_gemm_workspace_bytes(128, 176, 0) // 4, dtype=torch.float32, device=device)
+        ws = _WS[device] = torch.zeros(_L.pf_train_workspace_bytes() // 4, dtype=torch.float32, device=device)
     return ws
 
 
@@ -77,7 +79,7 @@ def linear_bwd(x: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_bias: bo
     _gemm(dy, x, None, dw, N, K, M, 1, N, K, 1, split_k=max(1, min(64, M // 512)))   # dw = dy^T x, K' = M split over CTAs
     db = torch.zeros(N if need_bias else 0, dtype=torch.float32, device=x.device)
     if need_bias:
-        _lib.check(_L.pf_train_colsum(_f(dy), _f(db), M, N, _s()), "pf_train_colsum")
+        _lib.check(_L.pf_train_colsum(_f(dy), _f(db), M, N, *_ws_args(dy.device), _s()), "pf_train_colsum")
     return dx, dw, db
 
 
@@ -224,7 +226,7 @@ def layernorm_bwd(x: torch.Tensor, w: torch.Tensor, stats: torch.Tensor, dy: tor
     dx = torch.empty_like(x)
     dw, db = torch.zeros_like(w), torch.zeros_like(w)
     _lib.check(_L.pf_train_layernorm_bwd(_f(x), _f(w), _f(stats), _f(dy), _f(dx), _f(dw), _f(db), x.shape[0], x.shape[1],
-                                         _s()), "pf_train_layernorm_bwd")
+                                         *_ws_args(x.device), _s()), "pf_train_layernorm_bwd")
     return dx, dw, db
 
 
@@ -295,16 +297,32 @@ def _(x, idx):
     return x.new_empty((idx.numel(),) + tuple(x.shape[1:]))
 
 
+def sort_by_row(idx: torch.Tensor, n_rows: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(perm, ptr) for the deterministic gather backward: the edges grouped by the row they read (stable sort: ascending
+    edge index within a row), row n owns perm[ptr[n] : ptr[n + 1]]."""
+    srt = torch.sort(idx.long(), stable=True)
+    ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=idx.device)
+    torch.cumsum(torch.bincount(srt.values, minlength=n_rows), 0, out=ptr[1:])
+    return srt.indices.to(torch.int32), ptr.to(torch.int32)
+
+
 @torch.library.custom_op(f"{NS}::train_gather_bwd", mutates_args=())
-def gather_bwd(dout: torch.Tensor, idx: torch.Tensor, n_rows: int) -> torch.Tensor:
-    dx = torch.zeros((n_rows,) + tuple(dout.shape[1:]), dtype=torch.float32, device=dout.device)
+def gather_bwd(dout: torch.Tensor, idx: torch.Tensor, n_rows: int, perm: Optional[torch.Tensor] = None,
+               ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx[n] = sum of dout[e] over the edges e with idx[e] == n, added in ascending edge order (no atomics: gradients are
+    bit-reproducible).  (perm, ptr) = sort_by_row(idx, n_rows) when the caller has it (train_graph.build_edges computes it
+    once per edge type and step), else it is computed here."""
+    if perm is None or ptr is None:
+        perm, ptr = sort_by_row(idx, n_rows)
+    dx = torch.empty((n_rows,) + tuple(dout.shape[1:]), dtype=torch.float32, device=dout.device)
     D = int(math.prod(dout.shape[1:]))
-    _lib.check(_L.pf_train_gather(_f(dout), _i(idx), _f(dx), idx.numel(), D, 1, _s()), "pf_train_gather")
+    _lib.check(_L.pf_train_gather_bwd_sorted(_f(dout), _i(perm), _i(ptr), _f(dx), n_rows, D, _s()),
+               "pf_train_gather_bwd_sorted")
     return dx
 
 
 @gather_bwd.register_fake
-def _(dout, idx, n_rows):
+def _(dout, idx, n_rows, perm=None, ptr=None):
     return dout.new_empty((n_rows,) + tuple(dout.shape[1:]))
 
 

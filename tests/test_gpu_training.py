@@ -318,3 +318,46 @@ def test_training_dead_work_elimination_is_exact(sd, dyn_cfg):
         assert (ga is None) == (gb_ is None), n
         if ga is not None and ga.numel():
             close(ga, gb_, rtol=1e-4, what=n)
+
+
+def test_training_gradients_are_bit_reproducible(sd, dyn_cfg):
+    """No floating-point atomics on the training path: split-K weight gradients, bias column sums and LayerNorm affine
+    gradients are reduced by the last CTA in split order (the training workspace of the header), the gather's backward adds
+    a row's edges in edge order.  Two backward passes from the same state give BIT-identical gradients on every parameter
+    (64 pockets: the shapes of bench_train.py, where every one of those reductions is split over many CTAs), and the
+    workspace's ticket counters are back at zero afterwards."""
+    from pharmacoforge_b200 import train_ops
+    from pharmacoforge_b200.batch import GraphBatch, Pocket
+    from pharmacoforge_b200.synthetic import make_pocket
+    rng = np.random.default_rng(5)
+    pockets = [Pocket.from_numpy(*make_pocket(int(rng.integers(250, 600)), seed=100 + i)) for i in range(24)]
+    sizes = [[int(rng.integers(4, 9))] for _ in pockets]
+    nf = sum(s[0] for s in sizes)
+    gen = torch.Generator().manual_seed(9)
+    x0 = torch.randn(nf, 3, generator=gen) * 4.0
+    h0 = torch.nn.functional.one_hot(torch.randint(0, 6, (nf,), generator=gen), 6).float()
+    t_int = torch.randint(1, 100, (len(pockets),), generator=gen)
+    eps = {"x": torch.randn(nf, 3, generator=gen), "h": torch.randn(nf, 6, generator=gen)}
+    model = _model(sd, dyn_cfg, dropout=0.0).train()
+    grads = []
+    for _ in range(2):
+        gb = GraphBatch.from_pockets(pockets, sizes, "cuda:0")
+        gb.set_pharmacophores(x0, h0)
+        model.zero_grad(set_to_none=True)
+        total, _, _ = model.training_step(gb, t_int=t_int, eps=eps)
+        total.backward()
+        grads.append({n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert len(grads[0]) >= 190 and grads[0].keys() == grads[1].keys()
+    for n in grads[0]:
+        assert torch.isfinite(grads[0][n]).all(), n
+        assert torch.equal(grads[0][n], grads[1][n]), n
+    ws = train_ops._workspace(torch.device("cuda:0"))
+    tail = _lib_tail_words()
+    assert int(ws.view(torch.int32)[-tail:].abs().sum()) == 0
+
+
+def _lib_tail_words():
+    import re
+    import os
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pharmacoforge_b200.h")).read()
+    return int(re.search(r"#define PF_TRAIN_WS_TAIL (\d+)", hdr).group(1)) // 4

@@ -73,9 +73,21 @@ def _fake_ops():
     T.vecln, T.vecln_bwd, T.segmean, T.segmean_bwd = _vecln, vecln_bwd, _segmean, segmean_bwd
     T.gather = lambda x, idx: x[idx.long()]
 
-    def gather_bwd(dout, idx, n_rows):
-        return torch.zeros((n_rows,) + tuple(dout.shape[1:])).index_add_(0, idx.long(), dout)
-    T.gather_bwd = gather_bwd
+    def sort_by_row(idx, n_rows):   # the kernel's contract: edges grouped by the row they read, ascending edge index
+        srt = torch.sort(idx.long(), stable=True)
+        ptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(torch.bincount(srt.values, minlength=n_rows), 0)])
+        return srt.indices.to(torch.int32), ptr.to(torch.int32)
+
+    def gather_bwd(dout, idx, n_rows, perm=None, ptr=None):
+        if perm is None:
+            perm, ptr = sort_by_row(idx, n_rows)
+        out = torch.zeros((n_rows,) + tuple(dout.shape[1:]))
+        for n in range(n_rows):      # what pf_train_gather_bwd_sorted does: row n adds its edges in perm order
+            for e in perm[int(ptr[n]):int(ptr[n + 1])]:
+                assert int(idx[int(e)]) == n
+                out[n] = out[n] + dout[int(e)]
+        return out
+    T.gather_bwd, T.sort_by_row = gather_bwd, sort_by_row
     return T
 
 
