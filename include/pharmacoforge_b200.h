@@ -157,6 +157,11 @@ int pf_combine_subsegments(const float* sub_h, const float* sub_v, const int32_t
 int pf_plan_tiles(const int32_t* seg_cnt, const int32_t* chunk_ptr, int32_t n_chunks, int32_t skip_empty,
                   int32_t tile_rows, int32_t* tiles, int32_t max_tiles, int32_t* n_tiles, uint32_t* dev_status,
                   void* stream);
+/* Three plans (the per-step ff / pf / fp plans of pf_denoiser) in one launch: arrays of three HOST-side entries each,
+ * n_tiles3[i] is plan i's counter (zeroed by the caller). */
+int pf_plan_tiles3(const int32_t* const seg_cnt[3], const int32_t* const chunk_ptr[3], const int32_t n_chunks[3],
+                   const int32_t skip_empty[3], int32_t tile_rows, int32_t* const tiles[3], int32_t max_tiles,
+                   int32_t* n_tiles3, uint32_t* dev_status, void* stream);
 int pf_zero_i32(int32_t* p, int64_t n, void* stream);
 /* The same plan with the tiles in CHUNK ORDER (a chunk's tiles contiguous, chunks ascending), for the static pp plan: the
  * persistent kernels process consecutive tiles concurrently, so the source rows of a graph are fetched from DRAM once and

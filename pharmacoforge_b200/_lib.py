@@ -41,6 +41,8 @@ SIGNATURES = {
                                          C.c_int32, STREAM]),
     "pf_plan_tiles": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, c_i32p, C.c_void_p,
                                 STREAM]),
+    "pf_plan_tiles3": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.c_int32, C.POINTER(C.c_void_p), C.c_int32, c_i32p, C.c_void_p, STREAM]),
     "pf_share_index": (C.c_int, [c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, STREAM]),
     "pf_share_gather": (C.c_int, [c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_f32p, c_i32p, c_f32p, c_f32p,
                                   c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, STREAM]),

@@ -626,13 +626,15 @@ extern "C" int pf_denoiser(const PfSampleArgs* a, void* stream) {
     for (int l = 0; l < a->n_convs; ++l)
       for (int e = 0; e < 4; ++e) PF_CHECK_ARG(a->w_msg_tc[l][e] != nullptr, "pf_denoiser: missing tcgen05 weight blob");
   }
-  PF_TRY(pf_plan_tiles(a->ff_cnt, a->pharm_chunk_ptr, a->n_pharm_chunks, 0, a->tile_rows, a->ff_tiles, a->dyn_max_tiles,
-                       a->dyn_n_tiles + 0, a->dev_status, stream));
-  PF_TRY(pf_plan_tiles(pf_seg_cnt, radius ? a->pf_sub_chunk_ptr : a->pharm_chunk_ptr,
-                       radius ? a->n_pf_sub_chunks : a->n_pharm_chunks, 1, a->tile_rows, a->pf_tiles, a->dyn_max_tiles,
-                       a->dyn_n_tiles + 1, a->dev_status, stream));
-  PF_TRY(pf_plan_tiles(a->fp_seg_cnt, a->fp_chunk_ptr, a->n_fp_chunks, 1, a->tile_rows, a->fp_tiles, a->dyn_max_tiles,
-                       a->dyn_n_tiles + 2, a->dev_status, stream));
+  {   // the per-step tile plans of ff, pf (or its sub-segments) and fp in one launch
+    const int32_t* const cnts[3] = {a->ff_cnt, pf_seg_cnt, a->fp_seg_cnt};
+    const int32_t* const chunks[3] = {a->pharm_chunk_ptr, radius ? a->pf_sub_chunk_ptr : a->pharm_chunk_ptr, a->fp_chunk_ptr};
+    const int32_t n_chunks[3] = {a->n_pharm_chunks, radius ? a->n_pf_sub_chunks : a->n_pharm_chunks, a->n_fp_chunks};
+    const int32_t skip[3] = {0, 1, 1};
+    int32_t* const tiles[3] = {a->ff_tiles, a->pf_tiles, a->fp_tiles};
+    PF_TRY(pf_plan_tiles3(cnts, chunks, n_chunks, skip, a->tile_rows, tiles, a->dyn_max_tiles, a->dyn_n_tiles, a->dev_status,
+                          stream));
+  }
   // numeric message_norm: every edge type's means go to tmp_agg_* and are folded into the aggregate as count / norm * mean
   // message_norm = 0 (msg_norm_degree): the divisor is per graph, edges per node + 1 (pf_degree_norms), read per destination
   const bool norm0 = a->msg_norm_degree != 0;

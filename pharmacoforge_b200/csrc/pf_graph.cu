@@ -749,6 +749,48 @@ __global__ void __launch_bounds__(128) plan_tiles_kernel(const int* __restrict__
   }
 }
 
+// The three per-step plans (ff, pf, fp) in ONE launch: blockIdx.y selects the plan.  Each plan is a latency-bound walk of one
+// thread per chunk (~47 us whatever the batch size); as three launches they ran back to back on the stream.
+struct PlanDesc {
+  const int *seg_cnt, *chunk_ptr;
+  int n_chunks, skip_empty;
+  int *tiles, *n_tiles;
+};
+struct Plan3 {
+  PlanDesc d[3];
+};
+__global__ void __launch_bounds__(128) plan_tiles3_kernel(const Plan3 p, int tile_rows, int max_tiles, unsigned* __restrict__ status) {
+  const PlanDesc& d = p.d[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.n_chunks) return;
+  int s = d.chunk_ptr[c];
+  const int s_end = d.chunk_ptr[c + 1];
+  while (s < s_end) {
+    int rows = 0, e = s;
+    while (e < s_end && e - s < tile_rows) {
+      const int cnt = d.seg_cnt[e];
+      if (rows + cnt > tile_rows) break;
+      rows += cnt;
+      ++e;
+    }
+    if (e == s) {  // a single destination with more in-edges than a tile holds
+      atomicOr(status, PF_DEV_DEGREE_OVERFLOW);
+      s = s + 1;
+      continue;
+    }
+    if (!(d.skip_empty && rows == 0)) {
+      const int slot = atomicAdd(d.n_tiles, 1);
+      if (slot < max_tiles) {
+        d.tiles[2 * slot] = s;
+        d.tiles[2 * slot + 1] = e;
+      } else {
+        atomicOr(status, PF_DEV_TILE_OVERFLOW);
+      }
+    }
+    s = e;
+  }
+}
+
 // Ordered variant for the static pp plan: tiles come out in chunk (graph) order, a graph's tiles contiguous.  The persistent
 // edge kernels hand tile k to CTA k mod grid, so with this order the ~25 tiles of a 400-atom graph run on 25 SMs AT THE SAME
 // TIME and the graph's source rows (282 KB) are fetched from DRAM once and then hit L2 for their other ~6.5 uses.  With the
@@ -991,6 +1033,24 @@ extern "C" int pf_plan_tiles(const int32_t* seg_cnt, const int32_t* chunk_ptr, i
                                                                           tile_rows, tiles, max_tiles, n_tiles,
                                                                           dev_status);
   PF_CHECK_LAUNCH("pf_plan_tiles");
+  return PF_OK;
+}
+
+extern "C" int pf_plan_tiles3(const int32_t* const seg_cnt[3], const int32_t* const chunk_ptr[3], const int32_t n_chunks[3],
+                              const int32_t skip_empty[3], int32_t tile_rows, int32_t* const tiles[3], int32_t max_tiles,
+                              int32_t* n_tiles3, uint32_t* dev_status, void* stream) {
+  PF_CHECK_ARG(seg_cnt && chunk_ptr && n_chunks && skip_empty && tiles && n_tiles3 && dev_status, "pf_plan_tiles3: null pointer");
+  PF_CHECK_ARG(tile_rows == PF_TILE_ROWS || tile_rows == PF_TC_TILE_ROWS, "pf_plan_tiles3: tile_rows must be 64 or 128");
+  Plan3 p;
+  int most = 0;
+  for (int i = 0; i < 3; ++i) {
+    PF_CHECK_ARG(seg_cnt[i] && chunk_ptr[i] && tiles[i] && n_chunks[i] >= 0, "pf_plan_tiles3: null plan array");
+    p.d[i] = PlanDesc{seg_cnt[i], chunk_ptr[i], n_chunks[i], skip_empty[i], tiles[i], n_tiles3 + i};
+    most = n_chunks[i] > most ? n_chunks[i] : most;
+  }
+  if (most == 0) return PF_OK;
+  plan_tiles3_kernel<<<dim3((most + 127) / 128, 3), 128, 0, as_stream(stream)>>>(p, tile_rows, max_tiles, dev_status);
+  PF_CHECK_LAUNCH("pf_plan_tiles3");
   return PF_OK;
 }
 
