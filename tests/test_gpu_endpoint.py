@@ -321,6 +321,22 @@ def test_radius_pf_edges_numeric_norm_and_sampling(sd, dyn_cfg):
                                          n_steps=8, return_tensors=True)
     assert torch.isfinite(x1).all() and torch.isfinite(h1).all()
     assert torch.equal(x2, x1[11:]) and torch.equal(h2, h1[11:])
-    # and the Philox / CUDA-graph throughput path runs in this mode
+    # and the Philox / CUDA-graph throughput path in this mode: the captured loop replays the eager one bit for bit
     out = model.sample_given_receptor(model.make_batch(pockets, [[4, 7], [5]], "cuda:0"))
     assert len(out) == 3 and all(torch.isfinite(o.ph_coords).all() and torch.isfinite(o.ph_feats).all() for o in out)
+    gb = model.make_batch(pockets, [[4, 7], [5]], "cuda:0")
+
+    def run(graph):
+        model.use_cuda_graph = graph
+        torch.manual_seed(5)
+        gb.prot_x.copy_(gb.prot_x0)
+        xx, hh = model.sample_given_receptor(gb, n_steps=10, return_tensors=True)
+        return xx.clone(), hh.clone()
+    try:
+        e1 = run(False)
+        g1, g2 = run(True), run(True)      # captures, then replays
+        assert len(model.dynamics.bind(gb).graphs) == 1
+        for r in (g1, g2):
+            assert torch.equal(r[0], e1[0]) and torch.equal(r[1], e1[1])
+    finally:
+        model.use_cuda_graph = False
