@@ -1,6 +1,8 @@
-"""The endpoint parameterisation (`endpoint_param_feat` / `endpoint_param_coord`, pharmacodiff.py:204-216, 413-418) and
-`remove_com=False` (:123-125) on the GPU against the fixture written by the reference's own code with those flags
-(`oracle/make_golden_endpoint.py` -> tests/golden/endpoint_param.npz) and against the oracle."""
+"""Configuration switches beyond configs/dev.yml on the GPU, each against a fixture written by the reference's own code with the
+switch set (and against the oracle): the endpoint parameterisation (`endpoint_param_feat` / `endpoint_param_coord`,
+pharmacodiff.py:204-216, 413-418) and `remove_com=False` (:123-125) -- `oracle/make_golden_endpoint.py` ->
+tests/golden/endpoint_param.npz; a numeric `message_norm`, incl. 0 (gvp.py:375-389, 504-517) -- message_norm.npz /
+message_norm0.npz; `pf_k = 0`, radius pf / fp edges (dynamics_gvp.py:210-216) -- pf_radius.npz."""
 import numpy as np
 import pytest
 import torch

@@ -272,3 +272,16 @@ def test_bench_arguments_name_the_configs(monkeypatch):
     from pharmacoforge_b200.synthetic import uniform_sizes
     s = uniform_sizes(16, 3, 16, seed=0)
     assert len(s) == 16 and min(s) >= 3 and max(s) <= 16
+
+
+def test_sort_by_row_groups_edges_in_edge_order():
+    """train_ops.sort_by_row: the (perm, ptr) contract of pf_train_gather_bwd_sorted -- row n owns perm[ptr[n]:ptr[n+1]], the
+    edges that read row n in ASCENDING edge index (what makes the gather's backward order-fixed), rows without edges are empty."""
+    from pharmacoforge_b200.train_ops import sort_by_row
+    idx = torch.tensor([4, 1, 4, 0, 1, 4, 6], dtype=torch.int32)
+    perm, ptr = sort_by_row(idx, 8)
+    assert perm.dtype == torch.int32 and ptr.dtype == torch.int32
+    assert ptr.tolist() == [0, 1, 3, 3, 3, 6, 6, 7, 7]
+    assert perm.tolist() == [3, 1, 4, 0, 2, 5, 6]
+    perm, ptr = sort_by_row(torch.zeros(0, dtype=torch.int32), 3)
+    assert perm.numel() == 0 and ptr.tolist() == [0, 0, 0, 0]
