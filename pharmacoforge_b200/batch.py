@@ -185,7 +185,9 @@ class GraphBatch:
         local = np.arange(self.n_pharm) - np.repeat(pharm_ptr[:-1].astype(np.int64), nf)
         ff_start = (np.repeat(ff_base[:-1], nf) + local * np.repeat(np.maximum(nf - 1, 0), nf)).astype(np.int32)
         self.ff_capacity = int(ff_base[-1])
-        gb = _chunk_graphs(np.maximum(nf * np.maximum(nf - 1, 0), k * nf), 256)
+        # planner chunks of ~PF_PLAN_CHUNK edge rows (whole graphs): a tile never spans two chunks, so a chunk's last tile is
+        # partly filled -- 1,024 rows keep that to ~1 tile in 9 (256, the value of the one-thread-per-chunk planner: 1 in 3)
+        gb = _chunk_graphs(np.maximum(nf * np.maximum(nf - 1, 0), k * nf), int(os.environ.get("PF_PLAN_CHUNK", 1024)))
         pharm_chunk = pharm_ptr[gb].astype(np.int32)
         fp_chunk = (k * pharm_ptr[gb].astype(np.int64)).astype(np.int32)
         small = torch.from_numpy(np.concatenate([ff_start, (k * np.arange(self.n_pharm)).astype(np.int32), pharm_chunk,

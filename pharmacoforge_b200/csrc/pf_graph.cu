@@ -749,8 +749,12 @@ __global__ void __launch_bounds__(128) plan_tiles_kernel(const int* __restrict__
   }
 }
 
-// The three per-step plans (ff, pf, fp) in ONE launch: blockIdx.y selects the plan.  Each plan is a latency-bound walk of one
-// thread per chunk (~47 us whatever the batch size); as three launches they ran back to back on the stream.
+// The three per-step plans (ff, pf, fp) in ONE launch: blockIdx.y selects the plan, ONE WARP per chunk.  The greedy packing of
+// plan_tiles_kernel (consecutive segments while they fit tile_rows edges and tile_rows segments) is a prefix-sum question: the
+// warp loads a window of tile_rows segment sizes (tile_rows / 32 consecutive ones per lane), scans it, and the segments whose
+// inclusive prefix stays within tile_rows form the tile -- a handful of instructions per tile instead of one dependent global
+// load per segment (the one-thread-per-chunk walk took ~47 us per plan whatever the batch size and forced small chunks, i.e.
+// a poorly filled last tile per chunk).  Same tiles as the sequential walk; their order in the list is arbitrary, as before.
 struct PlanDesc {
   const int *seg_cnt, *chunk_ptr;
   int n_chunks, skip_empty;
@@ -761,33 +765,56 @@ struct Plan3 {
 };
 __global__ void __launch_bounds__(128) plan_tiles3_kernel(const Plan3 p, int tile_rows, int max_tiles, unsigned* __restrict__ status) {
   const PlanDesc& d = p.d[blockIdx.y];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= d.n_chunks) return;
   int s = d.chunk_ptr[c];
   const int s_end = d.chunk_ptr[c + 1];
+  const int per = tile_rows >> 5;   // 2 or 4 segments per lane
   while (s < s_end) {
-    int rows = 0, e = s;
-    while (e < s_end && e - s < tile_rows) {
-      const int cnt = d.seg_cnt[e];
-      if (rows + cnt > tile_rows) break;
-      rows += cnt;
-      ++e;
+    int incl[4], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = s + lane * per + j;
+      // past the chunk (or the window): a size that can never fit, so nothing behind it fits either
+      const int cnt = (j < per && idx < s_end) ? d.seg_cnt[idx] : tile_rows + 1;
+      tot += j < per ? cnt : 0;
+      incl[j] = tot;
     }
-    if (e == s) {  // a single destination with more in-edges than a tile holds
-      atomicOr(status, PF_DEV_DEGREE_OVERFLOW);
+    int base = tot;   // exclusive scan of the lanes' totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, base, o);
+      if (lane >= o) base += t;
+    }
+    base -= tot;
+    int n_fit = 0, rows = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < per && base + incl[j] <= tile_rows) {
+        ++n_fit;
+        rows = base + incl[j];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      n_fit += __shfl_xor_sync(0xffffffffu, n_fit, o);
+      rows = max(rows, __shfl_xor_sync(0xffffffffu, rows, o));
+    }
+    if (n_fit == 0) {  // a single destination with more in-edges than a tile holds
+      if (lane == 0) atomicOr(status, PF_DEV_DEGREE_OVERFLOW);
       s = s + 1;
       continue;
     }
-    if (!(d.skip_empty && rows == 0)) {
+    if (lane == 0 && !(d.skip_empty && rows == 0)) {
       const int slot = atomicAdd(d.n_tiles, 1);
       if (slot < max_tiles) {
         d.tiles[2 * slot] = s;
-        d.tiles[2 * slot + 1] = e;
+        d.tiles[2 * slot + 1] = s + n_fit;
       } else {
         atomicOr(status, PF_DEV_TILE_OVERFLOW);
       }
     }
-    s = e;
+    s += n_fit;
   }
 }
 
@@ -1049,7 +1076,7 @@ extern "C" int pf_plan_tiles3(const int32_t* const seg_cnt[3], const int32_t* co
     most = n_chunks[i] > most ? n_chunks[i] : most;
   }
   if (most == 0) return PF_OK;
-  plan_tiles3_kernel<<<dim3((most + 127) / 128, 3), 128, 0, as_stream(stream)>>>(p, tile_rows, max_tiles, dev_status);
+  plan_tiles3_kernel<<<dim3((most + 3) / 4, 3), 128, 0, as_stream(stream)>>>(p, tile_rows, max_tiles, dev_status);   // 4 warps = 4 chunks per CTA
   PF_CHECK_LAUNCH("pf_plan_tiles3");
   return PF_OK;
 }
