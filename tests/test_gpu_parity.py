@@ -287,6 +287,16 @@ def test_denoiser_with_ff_knn_graph(env):
     close(gx, wx, what="eps_x (ff kNN)")
     n_knn = int(g.ff_cnt.sum().item())
     assert n_knn == env.O.dynamic_edges(b, 9.0, 5, 4)["ff"][0].numel() < env.O.dynamic_edges(b, 9.0, 5, 0)["ff"][0].numel()
+    # the differentiable training graph builds the same kNN ff edges (it used to ignore ff_k) and gives the same eps
+    from pharmacoforge_b200 import train_graph
+    g.pharm_h.copy_(h.cuda())
+    g.pharm_x.copy_(x.cuda())
+    g.prot_x.copy_(prot.cuda())
+    model.cuda()          # the training graph reads the nn.Parameters themselves (the fused path packs its own device images)
+    th, tx = train_graph.dynamics_forward(model.dynamics, g, tt, training=False)
+    assert int(g.ff_cnt.sum().item()) == n_knn
+    close(th.detach(), wh, rtol=2e-4, what="train eps_h (ff kNN)")
+    close(tx.detach(), wx, rtol=2e-4, what="train eps_x (ff kNN)")
 
 
 def test_knn_ties_prefer_lower_index(env):
