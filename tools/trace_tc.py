@@ -1,7 +1,7 @@
 import os, sys, json, ctypes as C
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 from pharmacoforge_b200 import ops, _lib
 from pharmacoforge_b200.batch import GraphBatch, Pocket
 from pharmacoforge_b200.diffusion import PharmacophoreDiff
